@@ -1,0 +1,202 @@
+/*
+ * mlmap_b200.h — C ABI of the B200-native MLMapping hot path (the drop-in boundary).
+ *
+ * The reference has no FFI layer: its boundary is the C++ class `mlmap`
+ * (reference include/mlmap.h:105-139).  A maintainer binds these entry points
+ * from that class; every function below cites the
+ * reference method it replaces.  Plain pointers and sizes only; no C++/torch
+ * types cross this boundary; nothing throws.
+ *
+ * Threading contract: one handle owns one CUDA stream.  Calls on a
+ * handle are stream-ordered and must be externally serialised; distinct handles
+ * are independent.  Queries observe every previously submitted update.
+ *
+ * Pose layout everywhere: double[7] = { tx, ty, tz, qw, qx, qy, qz }.  The
+ * quaternion is normalised on entry exactly as Sophus::SO3(Quaterniond) does
+ * (reference 3rdPartLib/Sophus/sophus/so3.cpp:42-47).
+ */
+#ifndef MLMAP_B200_H
+#define MLMAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define MLM_ABI_VERSION 1
+
+/* status codes returned by every entry point */
+enum {
+  MLM_OK = 0,
+  MLM_ERR_INVALID_ARG = 1,    /* null pointer, bad size, bad handle */
+  MLM_ERR_INVALID_CONFIG = 2, /* violates a precondition of the reference's tables */
+  MLM_ERR_CUDA = 3,           /* a CUDA runtime call failed; see mlm_last_error() */
+  MLM_ERR_POOL_EXHAUSTED = 4, /* submap pool or hash table full */
+  MLM_ERR_CAPACITY = 5,       /* more points/records in one frame than the handle was sized for */
+  MLM_ERR_UNSUPPORTED = 6,    /* option not implemented on the GPU path (never a silent CPU fallback) */
+  MLM_ERR_NO_DEVICE = 7       /* no CUDA device / wrong architecture */
+};
+
+/* occupancy codes, reference include/mlmap.h:109-114 */
+enum { MLM_FREE = 1, MLM_OCCUPIED = 0, MLM_UNKNOWN = -1 };
+
+/*
+ * Configuration = the YAML keys mlmap::init_map reads (reference src/mlmap.cpp:10-33,37-53,75-85)
+ * as a plain struct (yamlRead.h is out of scope).
+ */
+typedef struct mlm_config {
+  /* awareness_map_cylindrical::init_map arguments (reference src/map_awareness.cpp:19) */
+  double am_d_rho;      /* mlmapping_am_d_Rho      */
+  double am_d_phi_deg;  /* mlmapping_am_d_Phi_deg  */
+  double am_d_z;        /* mlmapping_am_d_Z        */
+  int32_t am_n_rho;     /* mlmapping_am_n_Rho      */
+  int32_t am_n_z_below; /* mlmapping_am_n_Z_below  */
+  int32_t am_n_z_over;  /* mlmapping_am_n_Z_over   */
+  int32_t use_raycasting; /* mlmapping_use_raycasting */
+  int32_t _pad0;
+  double depth_noise_coe; /* mlmapping_depth_noise_coe */
+
+  /* local_map_cartesian::init_map arguments (reference src/map_local.cpp:46-53) */
+  double subbox_d_xyz;  /* mlmapping_subbox_d_xyz */
+  int32_t subbox_n;     /* mlmapping_subbox_n     */
+  float log_odds_min;   /* mlmapping_lm_log_odds_min */
+  float log_odds_max;   /* mlmapping_lm_log_odds_max */
+  float log_odds_hit;   /* mlmapping_lm_measurement_hit (read, stored, never used: map_local.cpp:128) */
+  float log_odds_miss;  /* mlmapping_lm_measurement_miss */
+  float log_odds_occupied_sh; /* mlmapping_lm_occupied_sh */
+  int32_t use_exploration_frontiers; /* use_exploration_frontiers */
+  int32_t _pad1;
+
+  /* camera intrinsics, float members in the reference (include/mlmap.h:92) */
+  float cam_cx, cam_cy, cam_fx, cam_fy;
+
+  /* T_B_S (sensor in body) as pose[7]; reference src/mlmap.cpp:22-25 */
+  double T_bs[7];
+
+  /* inflation layer (reference src/mlmap.cpp:10,84-85; include/map_local.h:63-65) */
+  int32_t inflate_n;
+  int32_t inflate_global_n;
+  int32_t apply_inflate;
+  int32_t _pad2;
+  double inflate_height; /* local_map_cartesian::flate_height, default 0.1 */
+
+  /* project_depth: 0 = full-frame mode (every non-zero pixel, row-major);
+   * >0 = mlmapping_sample_cnt random pixels via glibc rand() (reference src/mlmap.cpp:321-326) */
+  int32_t sample_cnt;
+
+  /* capacities of the GPU-resident structures (no reference equivalent: the reference mallocs) */
+  int32_t max_points;     /* max points (pixels) per frame */
+  int32_t pool_submaps;   /* capacity of the submap block pool */
+  int32_t _pad3;
+} mlm_config;
+
+typedef struct mlm_map *mlm_handle;
+
+/* per-frame counters (reference public counters ram_expand_cnt/obs_cnt, include/map_local.h:79-80) */
+typedef struct mlm_frame_stats {
+  int32_t n_points;        /* points fed to input_pc_pose */
+  int32_t n_inside;        /* points inside the awareness range (update_hits calls) */
+  int32_t n_cast;          /* rays cast (can_do_cast && visibility_check) */
+  int32_t n_hit_cells;     /* distinct keys of hit_idx_odds_hashmap */
+  int32_t n_miss_cells;    /* distinct entries of miss_idx_set */
+  int32_t n_touched_voxels;/* distinct local-map cells receiving any update */
+  int32_t n_new_submaps;   /* allocate_ram() insertions this frame */
+  int32_t hit_bucket_count;/* emulated libstdc++ bucket count of the hit map after this frame */
+  int32_t ordering_slow_path; /* 1 if the frame crossed a libstdc++ rehash */
+  int32_t status;          /* MLM_OK or the error raised on device */
+  int64_t ram_expand_cnt;  /* cumulative */
+  int64_t obs_cnt;         /* cumulative */
+} mlm_frame_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+
+/* Fill cfg with the live reference configuration (launch/config/config_sim.yaml) */
+int mlm_default_config(mlm_config *cfg);
+
+/* mlmap::init_map (reference src/mlmap.cpp:3-149) minus ROS: builds the awareness tables
+ * (map_awareness.cpp:19-82) and local-map tables (map_local.cpp:46-139), allocates device state. */
+int mlm_create(const mlm_config *cfg, int device, mlm_handle *out);
+int mlm_destroy(mlm_handle h);
+const char *mlm_last_error(void);
+int mlm_abi_version(void);
+
+/* ---- per-frame update (the north-star path) --------------------------------------------------- */
+
+/* project_depth() + update_map() (reference src/mlmap.cpp:311-349,382-386) on a HOST depth image
+ * (uint16 millimetres, row stride in bytes).  H2D copy, all kernels and the stats read-back are
+ * inside the call. */
+int mlm_integrate_depth_u16(mlm_handle h, const uint16_t *img, int rows, int cols, size_t stride_bytes,
+                            const double T_wb[7], mlm_frame_stats *stats /* may be NULL */);
+/* same with the image already resident in device memory (dense rows) */
+int mlm_integrate_depth_u16_device(mlm_handle h, const uint16_t *d_img, int rows, int cols,
+                                   const double T_wb[7], mlm_frame_stats *stats);
+
+/* awareness_map_cylindrical::input_pc_pose + local_map_cartesian::input_pc_pose_direct
+ * (reference src/map_awareness.cpp:173, src/map_local.cpp:143) on sensor-frame points, xyz doubles. */
+int mlm_integrate_points_f64(mlm_handle h, const double *xyz, int n, const double T_wb[7],
+                             mlm_frame_stats *stats);
+int mlm_integrate_points_f64_device(mlm_handle h, const double *d_xyz, int n, const double T_wb[7],
+                                    mlm_frame_stats *stats);
+
+/* mlmap::setFree_map_in_bound (reference src/mlmap.cpp:388-407) */
+int mlm_set_free_in_bound(mlm_handle h, const double box_min[3], const double box_max[3]);
+
+/* mlmap::inflate_map (reference src/mlmap.cpp:286-309) around centre position ct_pos */
+int mlm_inflate_map(mlm_handle h, const double ct_pos[3]);
+
+/* ---- batched queries (reference include/mlmap.h:142-295); pos = n x 3 doubles ------------------ */
+
+int mlm_get_occupancy(mlm_handle h, const double *pos, size_t n, int32_t *out);
+int mlm_get_occupancy_inflate(mlm_handle h, const double *pos, size_t n, float inflate, int32_t *out);
+int mlm_get_inflate_occupancy(mlm_handle h, const double *pos, size_t n, int32_t *out);
+int mlm_get_odd(mlm_handle h, const double *pos, size_t n, float *out);
+int mlm_get_odd_grad(mlm_handle h, const double *pos, size_t n, size_t max_iter, double *out3n);
+/* device-resident variants: pos/out are device pointers, the call only enqueues on the handle's stream */
+int mlm_get_occupancy_device(mlm_handle h, const double *d_pos, size_t n, int32_t *d_out);
+int mlm_get_odd_device(mlm_handle h, const double *d_pos, size_t n, float *d_out);
+int mlm_get_odd_grad_device(mlm_handle h, const double *d_pos, size_t n, size_t max_iter, double *d_out3n);
+
+/* ---- stream control / timing (CUDA events on the handle's own stream) ------------------------- */
+
+int mlm_sync(mlm_handle h);
+int mlm_timer_start(mlm_handle h);
+int mlm_timer_stop_ms(mlm_handle h, float *ms); /* records + synchronises; ms since mlm_timer_start */
+/* device scratch helpers for harnesses that keep inputs resident */
+int mlm_device_alloc(mlm_handle h, size_t bytes, void **d_ptr);
+int mlm_device_free(mlm_handle h, void *d_ptr);
+int mlm_copy_to_device(mlm_handle h, void *d_dst, const void *src, size_t bytes);
+int mlm_copy_to_host(mlm_handle h, void *dst, const void *d_src, size_t bytes);
+int mlm_flush_l2(mlm_handle h); /* writes a buffer larger than L2 (bench hygiene) */
+/* number of kernels launched by this handle since creation */
+int mlm_kernel_launch_count(mlm_handle h, int64_t *count);
+
+/* ---- parity / debug exports ------------------------------------------------------------------- */
+
+/* Last frame's hit_idx_odds_hashmap in the reference's iteration order: keys = n x 3 ints
+ * (rho,phi,z), p = n floats.  Returns the number of entries through *n_out (cap = array capacity). */
+int mlm_last_frame_hits(mlm_handle h, int32_t *keys3, float *p, size_t cap, size_t *n_out);
+/* Last frame's miss_idx_set (awareness cell indices, ascending). */
+int mlm_last_frame_misses(mlm_handle h, uint64_t *idx, size_t cap, size_t *n_out);
+
+/* Whole-map export.  mlm_export_map_count gives the number of submaps; mlm_export_map fills
+ * glb3 (n x 3 int32), collapsed (n bytes), and per submap cells = subbox_n^3 entries of
+ * occupancy chars ('u','f','o'), inflate chars and float log-odds (collapsed submaps: entry 0 valid). */
+int mlm_export_map_count(mlm_handle h, size_t *n_submaps);
+int mlm_export_map(mlm_handle h, size_t cap_submaps, int32_t *glb3, uint8_t *collapsed,
+                   char *occupancy, char *inflate_occupancy, float *log_odds, size_t *n_out);
+
+/* glibc-2.39 log10f as evaluated on device (parity test hook, SURVEY §7 hard part 3) */
+int mlm_debug_log10f(mlm_handle h, const float *x, size_t n, float *out);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLMAP_B200_H */

@@ -1,0 +1,452 @@
+"""ctypes binding of the C ABI (include/mlmap_b200.h) and a thin Python mirror of the reference's
+``class mlmap`` (reference include/mlmap.h:105-139): same method names, argument meaning and
+sentinel returns, batched over numpy arrays.  Nothing here computes map values; every call goes to
+the CUDA library and raises ``MlmError`` if that library or a B200 is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+_LIB_PATH = _PKG / "lib" / "libmlmap_b200.so"
+
+MLM_OK = 0
+ERR_NAMES = {
+    1: "MLM_ERR_INVALID_ARG",
+    2: "MLM_ERR_INVALID_CONFIG",
+    3: "MLM_ERR_CUDA",
+    4: "MLM_ERR_POOL_EXHAUSTED",
+    5: "MLM_ERR_CAPACITY",
+    6: "MLM_ERR_UNSUPPORTED",
+    7: "MLM_ERR_NO_DEVICE",
+}
+FREE, OCCUPIED, UNKNOWN = 1, 0, -1  # reference include/mlmap.h:109-114
+
+
+class MlmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class MlmConfig(C.Structure):
+    """mirror of ``mlm_config`` (field order and padding must match include/mlmap_b200.h)"""
+
+    _fields_ = [
+        ("am_d_rho", C.c_double),
+        ("am_d_phi_deg", C.c_double),
+        ("am_d_z", C.c_double),
+        ("am_n_rho", C.c_int32),
+        ("am_n_z_below", C.c_int32),
+        ("am_n_z_over", C.c_int32),
+        ("use_raycasting", C.c_int32),
+        ("_pad0", C.c_int32),
+        ("depth_noise_coe", C.c_double),
+        ("subbox_d_xyz", C.c_double),
+        ("subbox_n", C.c_int32),
+        ("log_odds_min", C.c_float),
+        ("log_odds_max", C.c_float),
+        ("log_odds_hit", C.c_float),
+        ("log_odds_miss", C.c_float),
+        ("log_odds_occupied_sh", C.c_float),
+        ("use_exploration_frontiers", C.c_int32),
+        ("_pad1", C.c_int32),
+        ("cam_cx", C.c_float),
+        ("cam_cy", C.c_float),
+        ("cam_fx", C.c_float),
+        ("cam_fy", C.c_float),
+        ("T_bs", C.c_double * 7),
+        ("inflate_n", C.c_int32),
+        ("inflate_global_n", C.c_int32),
+        ("apply_inflate", C.c_int32),
+        ("_pad2", C.c_int32),
+        ("inflate_height", C.c_double),
+        ("sample_cnt", C.c_int32),
+        ("max_points", C.c_int32),
+        ("pool_submaps", C.c_int32),
+        ("_pad3", C.c_int32),
+    ]
+
+    def copy(self) -> "MlmConfig":
+        c = MlmConfig()
+        C.memmove(C.byref(c), C.byref(self), C.sizeof(MlmConfig))
+        return c
+
+
+class FrameStats(C.Structure):
+    _fields_ = [
+        ("n_points", C.c_int32),
+        ("n_inside", C.c_int32),
+        ("n_cast", C.c_int32),
+        ("n_hit_cells", C.c_int32),
+        ("n_miss_cells", C.c_int32),
+        ("n_touched_voxels", C.c_int32),
+        ("n_new_submaps", C.c_int32),
+        ("hit_bucket_count", C.c_int32),
+        ("ordering_slow_path", C.c_int32),
+        ("status", C.c_int32),
+        ("ram_expand_cnt", C.c_int64),
+        ("obs_cnt", C.c_int64),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/mlmap_b200.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "mlm_default_config", "mlm_create", "mlm_destroy", "mlm_last_error", "mlm_abi_version",
+    "mlm_integrate_depth_u16", "mlm_integrate_depth_u16_device", "mlm_integrate_points_f64",
+    "mlm_integrate_points_f64_device", "mlm_set_free_in_bound", "mlm_inflate_map",
+    "mlm_get_occupancy", "mlm_get_occupancy_inflate", "mlm_get_inflate_occupancy", "mlm_get_odd",
+    "mlm_get_odd_grad", "mlm_get_occupancy_device", "mlm_get_odd_device", "mlm_get_odd_grad_device",
+    "mlm_sync", "mlm_timer_start", "mlm_timer_stop_ms", "mlm_device_alloc", "mlm_device_free",
+    "mlm_copy_to_device", "mlm_copy_to_host", "mlm_flush_l2", "mlm_kernel_launch_count",
+    "mlm_last_frame_hits", "mlm_last_frame_misses", "mlm_export_map_count", "mlm_export_map",
+    "mlm_debug_log10f",
+]
+
+_lib = None
+
+
+def library_path() -> Path:
+    return _LIB_PATH
+
+
+def build_library(verbose: bool = False) -> Path:
+    """compile csrc/ for sm_100a with nvcc (works without a GPU)"""
+    script = _PKG / "csrc" / "build.sh"
+    res = subprocess.run(["sh", str(script)], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout[-4000:])
+        print(res.stderr[-8000:])
+    if res.returncode != 0:
+        raise RuntimeError("nvcc build of libmlmap_b200.so failed")
+    return _LIB_PATH
+
+
+def load_library() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise MlmError(7, f"{_LIB_PATH} is missing: build it with mlmapping_b200.build_library() "
+                          "(python -c 'import __graft_entry__ as g; g.build()'); there is no CPU fallback")
+    lib = C.CDLL(str(_LIB_PATH))
+    vp, dp, ip, fp = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_float)
+    sz = C.c_size_t
+    sig = {
+        "mlm_default_config": ([C.POINTER(MlmConfig)], C.c_int),
+        "mlm_create": ([C.POINTER(MlmConfig), C.c_int, C.POINTER(vp)], C.c_int),
+        "mlm_destroy": ([vp], C.c_int),
+        "mlm_last_error": ([], C.c_char_p),
+        "mlm_abi_version": ([], C.c_int),
+        "mlm_integrate_depth_u16": ([vp, vp, C.c_int, C.c_int, sz, dp, C.POINTER(FrameStats)], C.c_int),
+        "mlm_integrate_depth_u16_device": ([vp, vp, C.c_int, C.c_int, dp, C.POINTER(FrameStats)], C.c_int),
+        "mlm_integrate_points_f64": ([vp, vp, C.c_int, dp, C.POINTER(FrameStats)], C.c_int),
+        "mlm_integrate_points_f64_device": ([vp, vp, C.c_int, dp, C.POINTER(FrameStats)], C.c_int),
+        "mlm_set_free_in_bound": ([vp, dp, dp], C.c_int),
+        "mlm_inflate_map": ([vp, dp], C.c_int),
+        "mlm_get_occupancy": ([vp, vp, sz, vp], C.c_int),
+        "mlm_get_occupancy_inflate": ([vp, vp, sz, C.c_float, vp], C.c_int),
+        "mlm_get_inflate_occupancy": ([vp, vp, sz, vp], C.c_int),
+        "mlm_get_odd": ([vp, vp, sz, vp], C.c_int),
+        "mlm_get_odd_grad": ([vp, vp, sz, sz, vp], C.c_int),
+        "mlm_get_occupancy_device": ([vp, vp, sz, vp], C.c_int),
+        "mlm_get_odd_device": ([vp, vp, sz, vp], C.c_int),
+        "mlm_get_odd_grad_device": ([vp, vp, sz, sz, vp], C.c_int),
+        "mlm_sync": ([vp], C.c_int),
+        "mlm_timer_start": ([vp], C.c_int),
+        "mlm_timer_stop_ms": ([vp, fp], C.c_int),
+        "mlm_device_alloc": ([vp, sz, C.POINTER(vp)], C.c_int),
+        "mlm_device_free": ([vp, vp], C.c_int),
+        "mlm_copy_to_device": ([vp, vp, vp, sz], C.c_int),
+        "mlm_copy_to_host": ([vp, vp, vp, sz], C.c_int),
+        "mlm_flush_l2": ([vp], C.c_int),
+        "mlm_kernel_launch_count": ([vp, C.POINTER(C.c_int64)], C.c_int),
+        "mlm_last_frame_hits": ([vp, vp, vp, sz, C.POINTER(sz)], C.c_int),
+        "mlm_last_frame_misses": ([vp, vp, sz, C.POINTER(sz)], C.c_int),
+        "mlm_export_map_count": ([vp, C.POINTER(sz)], C.c_int),
+        "mlm_export_map": ([vp, sz, vp, vp, vp, vp, vp, C.POINTER(sz)], C.c_int),
+        "mlm_debug_log10f": ([vp, vp, sz, vp], C.c_int),
+    }
+    for name, (args, ret) in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = ret
+    _lib = lib
+    return lib
+
+
+def default_config() -> MlmConfig:
+    """the live reference configuration, launch/config/config_sim.yaml (filled by the C library)"""
+    cfg = MlmConfig()
+    rc = load_library().mlm_default_config(C.byref(cfg))
+    if rc != MLM_OK:
+        raise MlmError(rc, "mlm_default_config")
+    return cfg
+
+
+def _base_config() -> MlmConfig:
+    """SURVEY §8d common parameters (config_sim.yaml:20-24,42,51-55) without needing the library"""
+    c = MlmConfig()
+    c.use_raycasting = 1
+    c.subbox_n = 10
+    c.log_odds_min, c.log_odds_max = -2.0, 4.2
+    c.log_odds_hit, c.log_odds_miss, c.log_odds_occupied_sh = 0.7, -0.9, 3.0
+    c.use_exploration_frontiers = 0
+    c.T_bs[:] = [0.12, 0.0, 0.0, 0.5, -0.5, 0.5, -0.5]
+    c.inflate_n, c.inflate_global_n, c.apply_inflate, c.inflate_height = 2, 2, 1, 0.1
+    c.sample_cnt = 0
+    return c
+
+
+def config_cfg_a() -> MlmConfig:
+    """CFG-A (BASELINE configs 1 & 2): D435i-like 640x480 @ 0.1 m"""
+    c = _base_config()
+    c.am_d_rho, c.am_d_phi_deg, c.am_d_z = 0.1, 1.0, 0.1
+    c.am_n_rho, c.am_n_z_below, c.am_n_z_over = 65, 20, 20
+    c.depth_noise_coe = 0.00375
+    c.subbox_d_xyz = 0.1
+    c.cam_cx, c.cam_cy, c.cam_fx, c.cam_fy = 320.0, 240.0, 347.99755859375, 347.99755859375
+    c.max_points = 640 * 480
+    c.pool_submaps = 16384
+    return c
+
+
+def config_cfg_b() -> MlmConfig:
+    """CFG-B (BASELINE config 3): L515-like 1024x768 @ 0.05 m (synthetic)"""
+    c = _base_config()
+    c.am_d_rho, c.am_d_phi_deg, c.am_d_z = 0.05, 1.0, 0.05
+    c.am_n_rho, c.am_n_z_below, c.am_n_z_over = 180, 40, 40
+    c.depth_noise_coe = 0.001
+    c.subbox_d_xyz = 0.05
+    c.cam_cx, c.cam_cy, c.cam_fx, c.cam_fy = 512.0, 384.0, 731.0, 731.0
+    c.max_points = 1024 * 768
+    c.pool_submaps = 131072
+    return c
+
+
+def config_cfg_c() -> MlmConfig:
+    """CFG-C (BASELINE config 4): 128-beam LiDAR, 0.2 m voxels, 50 m range (synthetic)"""
+    c = _base_config()
+    c.am_d_rho, c.am_d_phi_deg, c.am_d_z = 0.2, 1.0, 0.2
+    c.am_n_rho, c.am_n_z_below, c.am_n_z_over = 250, 100, 100
+    c.depth_noise_coe = 1e-4
+    c.subbox_d_xyz = 0.2
+    c.T_bs[:] = [0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0]
+    c.cam_cx, c.cam_cy, c.cam_fx, c.cam_fy = 0.0, 0.0, 1.0, 1.0
+    c.max_points = 128 * 2048
+    c.pool_submaps = 65536
+    return c
+
+
+def _pose7(T_wb) -> "C.Array":
+    a = np.ascontiguousarray(np.asarray(T_wb, dtype=np.float64).reshape(7))
+    return (C.c_double * 7)(*a.tolist())
+
+
+class MLMap:
+    """Host-side mirror of the reference's ``class mlmap`` (include/mlmap.h:105-139) over the C ABI.
+
+    ``init_map(ros::NodeHandle&)`` becomes the constructor taking an ``MlmConfig``;
+    ``project_depth()+update_map()`` become ``integrate_depth`` (full-frame mode); the inline
+    queries are batched: positions are ``(n,3)`` float64 arrays."""
+
+    FREE, OCCUPIED, UNKNOWN = FREE, OCCUPIED, UNKNOWN
+
+    def __init__(self, cfg: MlmConfig, device: int = 0):
+        self._lib = load_library()
+        self.cfg = cfg.copy()
+        self._h = C.c_void_p()
+        rc = self._lib.mlm_create(C.byref(self.cfg), device, C.byref(self._h))
+        if rc != MLM_OK:
+            raise MlmError(rc, self._lib.mlm_last_error().decode())
+        self.has_data = False
+        self.map_updated = False
+        self.cells = self.cfg.subbox_n ** 3
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.mlm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != MLM_OK:
+            raise MlmError(rc, self._lib.mlm_last_error().decode())
+
+    # ---- per-frame update ------------------------------------------------------------------
+    def integrate_depth(self, img_u16: np.ndarray, T_wb) -> FrameStats:
+        """project_depth() + update_map() (reference src/mlmap.cpp:311-349,382-386)"""
+        img = np.asarray(img_u16)
+        assert img.dtype == np.uint16 and img.ndim == 2
+        if img.strides[1] != 2:
+            img = np.ascontiguousarray(img)
+        st = FrameStats()
+        self._check(self._lib.mlm_integrate_depth_u16(self._h, img.ctypes.data, img.shape[0], img.shape[1],
+                                                      img.strides[0], _pose7(T_wb), C.byref(st)))
+        self.has_data = self.map_updated = True
+        return st
+
+    def integrate_depth_device(self, d_img: int, rows: int, cols: int, T_wb) -> FrameStats:
+        st = FrameStats()
+        self._check(self._lib.mlm_integrate_depth_u16_device(self._h, d_img, rows, cols, _pose7(T_wb), C.byref(st)))
+        return st
+
+    def integrate_points(self, xyz: np.ndarray, T_wb) -> FrameStats:
+        """awareness_map->input_pc_pose + local_map->input_pc_pose_direct (src/mlmap.cpp:382-386)"""
+        pts = np.ascontiguousarray(np.asarray(xyz, dtype=np.float64).reshape(-1, 3))
+        st = FrameStats()
+        self._check(self._lib.mlm_integrate_points_f64(self._h, pts.ctypes.data, pts.shape[0], _pose7(T_wb), C.byref(st)))
+        self.has_data = self.map_updated = True
+        return st
+
+    def integrate_points_device(self, d_xyz: int, n: int, T_wb) -> FrameStats:
+        st = FrameStats()
+        self._check(self._lib.mlm_integrate_points_f64_device(self._h, d_xyz, n, _pose7(T_wb), C.byref(st)))
+        return st
+
+    def setFree_map_in_bound(self, box_min, box_max):
+        mn = (C.c_double * 3)(*[float(v) for v in box_min])
+        mx = (C.c_double * 3)(*[float(v) for v in box_max])
+        self._check(self._lib.mlm_set_free_in_bound(self._h, mn, mx))
+
+    def inflate_map(self, ct_pos):
+        p = (C.c_double * 3)(*[float(v) for v in ct_pos])
+        self._check(self._lib.mlm_inflate_map(self._h, p))
+
+    # ---- queries ---------------------------------------------------------------------------------
+    @staticmethod
+    def _pos(pos_w):
+        return np.ascontiguousarray(np.asarray(pos_w, dtype=np.float64).reshape(-1, 3))
+
+    def getOccupancy(self, pos_w, inflate: float | None = None) -> np.ndarray:
+        p = self._pos(pos_w)
+        out = np.empty(p.shape[0], dtype=np.int32)
+        if inflate is None:
+            self._check(self._lib.mlm_get_occupancy(self._h, p.ctypes.data, p.shape[0], out.ctypes.data))
+        else:
+            self._check(self._lib.mlm_get_occupancy_inflate(self._h, p.ctypes.data, p.shape[0], float(inflate),
+                                                            out.ctypes.data))
+        return out
+
+    def getInflateOccupancy(self, pos_w) -> np.ndarray:
+        p = self._pos(pos_w)
+        out = np.empty(p.shape[0], dtype=np.int32)
+        self._check(self._lib.mlm_get_inflate_occupancy(self._h, p.ctypes.data, p.shape[0], out.ctypes.data))
+        return out
+
+    def getOdd(self, pos_w) -> np.ndarray:
+        p = self._pos(pos_w)
+        out = np.empty(p.shape[0], dtype=np.float32)
+        self._check(self._lib.mlm_get_odd(self._h, p.ctypes.data, p.shape[0], out.ctypes.data))
+        return out
+
+    def getOddGrad(self, pos_w, max_iter: int = 5) -> np.ndarray:
+        p = self._pos(pos_w)
+        out = np.empty((p.shape[0], 3), dtype=np.float64)
+        self._check(self._lib.mlm_get_odd_grad(self._h, p.ctypes.data, p.shape[0], max_iter, out.ctypes.data))
+        return out
+
+    # ---- stream / timing -------------------------------------------------------------------------
+    def sync(self):
+        self._check(self._lib.mlm_sync(self._h))
+
+    def timer_start(self):
+        self._check(self._lib.mlm_timer_start(self._h))
+
+    def timer_stop_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self._lib.mlm_timer_stop_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        self._check(self._lib.mlm_flush_l2(self._h))
+
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.mlm_device_alloc(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def device_free(self, ptr: int):
+        self._check(self._lib.mlm_device_free(self._h, ptr))
+
+    def to_device(self, arr: np.ndarray) -> int:
+        a = np.ascontiguousarray(arr)
+        p = self.device_alloc(max(a.nbytes, 16))
+        self._check(self._lib.mlm_copy_to_device(self._h, p, a.ctypes.data, a.nbytes))
+        return p
+
+    def to_host(self, ptr: int, shape, dtype) -> np.ndarray:
+        out = np.empty(shape, dtype=dtype)
+        self._check(self._lib.mlm_copy_to_host(self._h, out.ctypes.data, ptr, out.nbytes))
+        return out
+
+    def kernel_launch_count(self) -> int:
+        v = C.c_int64()
+        self._check(self._lib.mlm_kernel_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    # ---- device-resident queries (enqueue only) ---------------------------------------------------
+    def getOccupancy_device(self, d_pos: int, n: int, d_out: int):
+        self._check(self._lib.mlm_get_occupancy_device(self._h, d_pos, n, d_out))
+
+    def getOdd_device(self, d_pos: int, n: int, d_out: int):
+        self._check(self._lib.mlm_get_odd_device(self._h, d_pos, n, d_out))
+
+    def getOddGrad_device(self, d_pos: int, n: int, d_out: int, max_iter: int = 5):
+        self._check(self._lib.mlm_get_odd_grad_device(self._h, d_pos, n, max_iter, d_out))
+
+    # ---- parity / debug exports --------------------------------------------------------------------
+    def last_frame_hits(self):
+        """(keys[n,3] int32 (rho,phi,z), p[n] float32) in the reference's hash-map iteration order"""
+        n = C.c_size_t()
+        self._check(self._lib.mlm_last_frame_hits(self._h, None, None, 0, C.byref(n)))
+        keys = np.empty((n.value, 3), dtype=np.int32)
+        p = np.empty(n.value, dtype=np.float32)
+        if n.value:
+            self._check(self._lib.mlm_last_frame_hits(self._h, keys.ctypes.data, p.ctypes.data, n.value, C.byref(n)))
+        return keys, p
+
+    def last_frame_misses(self) -> np.ndarray:
+        n = C.c_size_t()
+        self._check(self._lib.mlm_last_frame_misses(self._h, None, 0, C.byref(n)))
+        idx = np.empty(n.value, dtype=np.uint64)
+        if n.value:
+            self._check(self._lib.mlm_last_frame_misses(self._h, idx.ctypes.data, n.value, C.byref(n)))
+        return idx
+
+    def export_map(self):
+        """dict with glb[n,3], collapsed[n], occupancy[n,cells] (S1), inflate[n,cells], log_odds[n,cells],
+        sorted by glb index"""
+        n = C.c_size_t()
+        self._check(self._lib.mlm_export_map_count(self._h, C.byref(n)))
+        cap = n.value
+        glb = np.zeros((cap, 3), dtype=np.int32)
+        col = np.zeros(cap, dtype=np.uint8)
+        occ = np.zeros((cap, self.cells), dtype="S1")
+        inf = np.zeros((cap, self.cells), dtype="S1")
+        lo = np.zeros((cap, self.cells), dtype=np.float32)
+        if cap:
+            self._check(self._lib.mlm_export_map(self._h, cap, glb.ctypes.data, col.ctypes.data, occ.ctypes.data,
+                                                 inf.ctypes.data, lo.ctypes.data, C.byref(n)))
+            assert n.value == cap, (n.value, cap)
+        order = np.lexsort((glb[:, 2], glb[:, 1], glb[:, 0]))
+        return {"glb": glb[order], "collapsed": col[order], "occupancy": occ[order], "inflate": inf[order],
+                "log_odds": lo[order]}
+
+    def debug_log10f(self, x: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.empty_like(a)
+        self._check(self._lib.mlm_debug_log10f(self._h, a.ctypes.data, a.size, out.ctypes.data))
+        return out

@@ -1,0 +1,769 @@
+// Per-frame map update kernels (sm_100a).  Replaces, on the GPU, the reference's
+//   mlmap::project_depth            src/mlmap.cpp:311-349            -> k_project_depth
+//   awareness::input_pc_pose        src/map_awareness.cpp:173-282    -> k_project_* + k_column
+//   awareness::update_hits          src/map_awareness.cpp:135-171    -> k_column (contributions + ordered fold)
+//   local::input_pc_pose_direct     src/map_local.cpp:143-207        -> k_column (staging) + k_submaps + k_fuse
+//   local::allocate_ram             include/map_local.h:215-231      -> k_submaps
+// Design notes are in DESIGN.md; every arithmetic step that decides an index or a float result
+// follows SURVEY Appendix A exactly (IEEE, no FMA contraction: this TU is built with -fmad=false).
+#pragma once
+#include "exact_math.cuh"
+#include "types.cuh"
+
+namespace mlm {
+
+// ---- small helpers -------------------------------------------------------------------------------
+
+// x86-64 cvttsd2si semantics (what the g++-compiled reference does for static_cast<int>(double)):
+// NaN / out-of-range -> INT_MIN ("integer indefinite").
+__device__ __forceinline__ int cvt_trunc_x86(double x) {
+  if (!(x > -2147483649.0 && x < 2147483648.0)) return (int)0x80000000;
+  return __double2int_rz(x);
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// warp-aggregated counter increment; returns this thread's slot
+__device__ __forceinline__ int agg_inc(int *ctr) {
+  unsigned mask = __activemask();
+  int leader = __ffs(mask) - 1;
+  int res = 0;
+  if (lane_id() == leader) res = atomicAdd(ctr, __popc(mask));
+  res = __shfl_sync(mask, res, leader);
+  return res + __popc(mask & ((1u << lane_id()) - 1));
+}
+
+__device__ __forceinline__ int floor_div(int a, int b) {
+  int q = a / b, r = a - q * b;
+  return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q;
+}
+
+// fast_atan / fast_atan2, reference include/map_awareness.h:86-118
+__device__ __forceinline__ double ref_fast_atan(double x) { return x * (45 - (x - 1) * (14 + 3.83 * x)); }
+__device__ __forceinline__ double ref_fast_atan2(double y, double x) {
+  const double deg2rad = M_PI / 180;  // "M_PI / 180 * (...)" associates as (M_PI/180) * (...)
+  double input = y / x;
+  double a_input = fabs(input);
+  double res;
+  if (a_input > 1) {
+    res = copysign(deg2rad * (90 - ref_fast_atan(1 / a_input)), input);
+  } else {
+    res = copysign(deg2rad * ref_fast_atan(a_input), input);
+  }
+  if (x > 0) return res;
+  if (y >= 0) return res + M_PI;
+  return res - M_PI;
+}
+
+// get_global_idx + get_subbox_id, reference include/map_local.h:148-152,167-173.
+// sub-index components outside [0,n) hit unordered_map::operator[] on a missing key -> id 0.
+struct CellRef {
+  int g[3];   // subbox (global) index
+  int sub;    // cell id inside the subbox
+  int c[3];   // canonical global cell coordinate g*n + xyz(sub)
+};
+__device__ __forceinline__ CellRef locate_cell(const MapParams &P, double px, double py, double pz) {
+  CellRef r;
+  double p[3] = {px, py, pz};
+  int loc[3];
+  bool ok = true;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    r.g[a] = cvt_trunc_x86(floor(p[a] / P.d_glb));
+    double l = floor(p[a] / P.d_sub) - (double)(r.g[a] * P.n);
+    loc[a] = cvt_trunc_x86(l);
+    ok = ok && loc[a] >= 0 && loc[a] < P.n;
+  }
+  if (!ok) loc[0] = loc[1] = loc[2] = 0;
+  r.sub = (loc[2] * P.n + loc[1]) * P.n + loc[0];
+#pragma unroll
+  for (int a = 0; a < 3; a++) r.c[a] = r.g[a] * P.n + loc[a];
+  return r;
+}
+
+__device__ __forceinline__ int lvg_index(const MapParams &P, const FrameParams &F, const CellRef &r) {
+  int lx = r.c[0] - F.lvg_base[0], ly = r.c[1] - F.lvg_base[1], lz = r.c[2] - F.lvg_base[2];
+  if ((unsigned)lx >= (unsigned)P.lvg_dim_xy || (unsigned)ly >= (unsigned)P.lvg_dim_xy ||
+      (unsigned)lz >= (unsigned)P.lvg_dim_z)
+    return -1;
+  return (lz * P.lvg_dim_xy + ly) * P.lvg_dim_xy + lx;
+}
+__device__ __forceinline__ int lsg_index(const MapParams &P, const FrameParams &F, const int g[3]) {
+  int lx = g[0] - F.lsg_base[0], ly = g[1] - F.lsg_base[1], lz = g[2] - F.lsg_base[2];
+  if ((unsigned)lx >= (unsigned)P.lsg_dim_xy || (unsigned)ly >= (unsigned)P.lsg_dim_xy ||
+      (unsigned)lz >= (unsigned)P.lsg_dim_z)
+    return -1;
+  return (lz * P.lsg_dim_xy + ly) * P.lsg_dim_xy + lx;
+}
+
+// raycasting_z_over_rho, reference src/map_awareness.cpp:64-71 and :252-259 (same expression)
+__device__ __forceinline__ double ray_rate(const MapParams &P, int rho, int z) {
+  return rho > 0 ? (double)(z - P.n_below) / ((double)rho * 1.0) : 0.0;
+}
+
+// 63-bit packing of a subbox index for the device hash table
+__device__ __forceinline__ bool pack_glb(const int g[3], uint64_t &key) {
+  const int lim = 1 << 20;
+  if (g[0] < -lim || g[0] >= lim || g[1] < -lim || g[1] >= lim || g[2] < -lim || g[2] >= lim) return false;
+  key = ((uint64_t)(uint32_t)(g[0] + lim) << 42) | ((uint64_t)(uint32_t)(g[1] + lim) << 21) |
+        (uint64_t)(uint32_t)(g[2] + lim);
+  return true;
+}
+__device__ __forceinline__ void unpack_glb(uint64_t key, int g[3]) {
+  const int lim = 1 << 20;
+  g[0] = (int)((key >> 42) & 0x1fffff) - lim;
+  g[1] = (int)((key >> 21) & 0x1fffff) - lim;
+  g[2] = (int)(key & 0x1fffff) - lim;
+}
+__device__ __forceinline__ uint32_t ht_hash(uint64_t k) {  // splitmix64 finaliser
+  k ^= k >> 30;
+  k *= 0xbf58476d1ce4e5b9ull;
+  k ^= k >> 27;
+  k *= 0x94d049bb133111ebull;
+  k ^= k >> 31;
+  return (uint32_t)k;
+}
+// read-only lookup of a subbox: returns pool block (>=0), or -1 if absent
+__device__ __forceinline__ int ht_find(const MapParams &P, const DeviceBuffers &D, const int g[3]) {
+  uint64_t key;
+  if (!pack_glb(g, key)) return -1;
+  uint32_t slot = ht_hash(key) & P.ht_mask;
+  for (uint32_t probe = 0; probe <= P.ht_mask; probe++) {
+    uint64_t k = D.ht_key[slot];
+    if (k == key) return D.ht_val[slot];
+    if (k == kEmptyKey) return -1;
+    slot = (slot + 1) & P.ht_mask;
+  }
+  return -1;
+}
+
+// ---- K0: per-frame reset ---------------------------------------------------------------------------
+__global__ void k_frame_begin(MapParams P, DeviceBuffers D) {
+  int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  int nth = gridDim.x * blockDim.x;
+  uint32_t B = D.fp->bucket_count;
+  for (uint32_t i = tid; i < B; i += nth) D.act[i] = 0xffffffffu;
+  for (int i = tid; i < P.nPhi; i += nth) {
+    D.phi_hist[i] = 0;
+    D.phi_cursor[i] = 0;
+  }
+  if (tid == 0) {
+    FrameCounters z;
+    memset(&z, 0, sizeof(z));
+    *D.fc = z;
+  }
+}
+
+// ---- K1: projection + transform + cylindrical index ------------------------------------------------
+// One thread per point.  Output: a RayRecord per castable / inside point (in point order) and the
+// per-phi-column histogram used to group the records by column.
+__device__ __forceinline__ void point_to_record(const MapParams &P, const FrameParams &F, double xs, double ys,
+                                                double zs, uint32_t t, RayRecord &rec, int &inside_out,
+                                                int &cast_out) {
+  // p_l = T_ls * p_s : Eigen Quaternion::_transformVector then + translation (se3.cpp:91-95)
+  const double qw = F.q_ls[0], qx = F.q_ls[1], qy = F.q_ls[2], qz = F.q_ls[3];
+  double uvx = qy * zs - qz * ys;
+  double uvy = qz * xs - qx * zs;
+  double uvz = qx * ys - qy * xs;
+  uvx += uvx;
+  uvy += uvy;
+  uvz += uvz;
+  double cx = qy * uvz - qz * uvy;
+  double cy = qz * uvx - qx * uvz;
+  double cz = qx * uvy - qy * uvx;
+  double x = ((xs + qw * uvx) + cx) + F.t_ls[0];
+  double y = ((ys + qw * uvy) + cy) + F.t_ls[1];
+  double z = ((zs + qw * uvz) + cz) + F.t_ls[2];
+  // xyz2RhoPhiZwithBoderCheck, src/map_awareness.cpp:84-107
+  double rho = sqrt(x * x + y * y);
+  int rho_idx = cvt_trunc_x86(rho / P.dRho);
+  double phi = ref_fast_atan2(y, x);
+  if (phi < 0) phi += 2 * M_PI;
+  int phi_idx = cvt_trunc_x86(phi / P.dPhi);
+  double zz = z - P.z_border_min;
+  int z_idx = cvt_trunc_x86(floor(zz / P.dZ));
+  bool can = rho_idx >= 0 && phi_idx >= 0 && phi_idx < P.nPhi;
+  bool inside = can && z_idx >= 0 && rho_idx < P.nRho && z_idx < P.nZ;
+  bool cast = can && P.visibility_check;
+  inside_out = inside;
+  cast_out = cast;
+  if (inside || cast) {
+    rec.rho = rho_idx;
+    rec.z = z_idx;
+    rec.phi_flags = (uint32_t)phi_idx | (inside ? kRecInside : 0u);
+    rec.t = t;
+  }
+}
+
+// exclusive scan of phi_hist -> phi_off by the last CTA to finish K1
+__device__ void scan_phi_hist_last_block(const MapParams &P, DeviceBuffers &D, int *s_tmp /*[blockDim]*/) {
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < P.nPhi; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    int v = i < P.nPhi ? __ldcg(&D.phi_hist[i]) : 0;
+    s_tmp[threadIdx.x] = v;
+    __syncthreads();
+    for (int ofs = 1; ofs < blockDim.x; ofs <<= 1) {  // Hillis-Steele inclusive scan
+      int add = threadIdx.x >= ofs ? s_tmp[threadIdx.x - ofs] : 0;
+      __syncthreads();
+      s_tmp[threadIdx.x] += add;
+      __syncthreads();
+    }
+    int incl = s_tmp[threadIdx.x];
+    if (i < P.nPhi) D.phi_off[i] = s_carry + incl - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry += incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) D.phi_off[P.nPhi] = s_carry;
+}
+
+template <bool kDepth>
+__global__ void __launch_bounds__(256) k_project(MapParams P, DeviceBuffers D, const void *input, int rows, int cols,
+                                                 int n_points, int *ticket) {
+  extern __shared__ int s_hist[];  // [nPhi] then [blockDim] scan scratch
+  __shared__ int s_cnt[3];
+  __shared__ int s_last;
+  const FrameParams &F = *D.fp;
+  for (int i = threadIdx.x; i < P.nPhi; i += blockDim.x) s_hist[i] = 0;
+  if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int N = kDepth ? rows * cols : n_points;
+  RayRecord rec;
+  rec.rho = 0;
+  rec.z = 0;
+  rec.t = 0;
+  rec.phi_flags = 0xffffffffu;
+  int valid = 0, inside = 0, cast = 0;
+  if (i < N) {
+    double xs, ys, zs;
+    if (kDepth) {
+      // project_depth, src/mlmap.cpp:329-346 (full-frame mode: every pixel, v outer, u inner)
+      uint16_t raw = __ldg(reinterpret_cast<const uint16_t *>(input) + i);
+      if (raw != 0) {
+        int v = i / cols, u = i - v * cols;
+        double depth = (double)(int)raw * P.inv_factor;
+        xs = (double)__fsub_rn((float)u, P.cx) * depth / (double)P.fx;
+        ys = (double)__fsub_rn((float)v, P.cy) * depth / (double)P.fy;
+        zs = depth;
+        valid = 1;
+      }
+    } else {
+      const double *xyz = reinterpret_cast<const double *>(input);
+      xs = xyz[3 * (size_t)i];
+      ys = xyz[3 * (size_t)i + 1];
+      zs = xyz[3 * (size_t)i + 2];
+      valid = 1;
+    }
+    if (valid) point_to_record(P, F, xs, ys, zs, (uint32_t)i, rec, inside, cast);
+    D.rec_lin[i] = rec;
+  }
+  if (rec.phi_flags != 0xffffffffu) atomicAdd(&s_hist[rec.phi_flags & kRecPhiMask], 1);
+  // CTA-level counters
+  unsigned bv = __ballot_sync(0xffffffffu, valid), bi = __ballot_sync(0xffffffffu, inside),
+           bc = __ballot_sync(0xffffffffu, cast);
+  if (lane_id() == 0) {
+    if (bv) atomicAdd(&s_cnt[0], __popc(bv));
+    if (bi) atomicAdd(&s_cnt[1], __popc(bi));
+    if (bc) atomicAdd(&s_cnt[2], __popc(bc));
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < P.nPhi; p += blockDim.x)
+    if (s_hist[p]) atomicAdd(&D.phi_hist[p], s_hist[p]);
+  if (threadIdx.x == 0) {
+    if (s_cnt[0]) atomicAdd(&D.fc->n_points, s_cnt[0]);
+    if (s_cnt[1]) atomicAdd(&D.fc->n_inside, s_cnt[1]);
+    if (s_cnt[2]) atomicAdd(&D.fc->n_cast, s_cnt[2]);
+  }
+  // last CTA scans the histogram
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tk = atomicAdd(ticket, 1);
+    s_last = (tk == (int)gridDim.x - 1);
+    if (s_last) *ticket = 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    scan_phi_hist_last_block(P, D, s_hist + P.nPhi);
+  }
+}
+
+// ---- K1b: group records by phi column ----------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scatter(MapParams P, DeviceBuffers D, int N) {
+  extern __shared__ int s_mem[];  // s_cnt[nPhi], s_base[nPhi]
+  int *s_cnt = s_mem, *s_base = s_mem + P.nPhi;
+  for (int i = threadIdx.x; i < P.nPhi; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  RayRecord rec;
+  rec.phi_flags = 0xffffffffu;
+  int rank = 0, phi = 0;
+  if (i < N) {
+    rec = D.rec_lin[i];
+    if (rec.phi_flags != 0xffffffffu) {
+      phi = rec.phi_flags & kRecPhiMask;
+      rank = atomicAdd(&s_cnt[phi], 1);
+    }
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < P.nPhi; p += blockDim.x)
+    if (s_cnt[p]) s_base[p] = D.phi_off[p] + atomicAdd(&D.phi_cursor[p], s_cnt[p]);
+  __syncthreads();
+  if (rec.phi_flags != 0xffffffffu) D.rec_col[s_base[phi] + rank] = rec;
+}
+
+// ---- K2: one CTA per phi column ------------------------------------------------------------------------
+// (a) expand inside records into hit contributions (update_hits), (b) sort them by (cell, insert
+// time), (c) fold each cell's contributions in insertion order (update_odds_hashmap), emit the
+// distinct hit keys with their first-insert stamps and stage them in the frame-local voxel grid,
+// (d) warp-cooperative ray walks into a shared-memory miss bitmap, (e) stage the distinct miss
+// cells in the voxel grid.
+constexpr int kColThreads = 512;
+constexpr int kCellBits = 20;
+
+__device__ __forceinline__ uint64_t contrib_key(int cell, uint32_t t, int substep) {
+  return ((uint64_t)(uint32_t)cell << 37) | ((uint64_t)t << 5) | (uint64_t)substep;
+}
+
+__device__ __forceinline__ void touch_subbox(const MapParams &P, const FrameParams &F, DeviceBuffers &D,
+                                             const int g[3]) {
+  int ls = lsg_index(P, F, g);
+  if (ls < 0) {
+    D.fc->error = kErrInternal;
+    return;
+  }
+  if (__ldcg(&D.lsg_flag[ls]) == 0) {
+    if (atomicExch(&D.lsg_flag[ls], 1) == 0) {
+      int pos = atomicAdd(&D.fc->n_touched_sub, 1);
+      D.touched_sub[pos] = ls;
+    }
+  }
+}
+
+// walk one ray toward the axis, reference src/map_awareness.cpp:261-275.  All 32 lanes cooperate:
+// lane l owns rho step r = 32*w + l, lanes that land in the same z row merge into one atomicOr.
+__device__ __forceinline__ void walk_ray(const MapParams &P, uint32_t *s_miss, int rho, int z) {
+  double rate = ray_rate(P, rho, z);
+  if (rho >= P.nRho) {
+    z = cvt_trunc_x86(round((double)z - (double)(rho - P.nRho + 1) * rate));
+    rho = P.nRho - 1;
+  }
+  const int lane = lane_id();
+  for (int w = (rho - 1) >> 5; w >= 0; --w) {
+    int r = (w << 5) + lane;
+    bool valid = r >= 1 && r <= rho - 1;
+    int zc = 0;
+    if (valid) {
+      zc = cvt_trunc_x86(round((double)z - (double)(rho - r) * rate));
+      valid = zc >= 0 && zc < P.nZ;
+    }
+    unsigned peers = __match_any_sync(0xffffffffu, valid ? zc : -1 - lane);
+    if (valid && lane == __ffs(peers) - 1) atomicOr(&s_miss[zc * P.words_per_row + w], peers);
+  }
+}
+
+__global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBuffers D) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const FrameParams &F = *D.fp;
+  const int phi = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int n_c = D.phi_hist[phi];
+  uint32_t *g_miss = D.miss_bitmap + (size_t)phi * P.col_words;
+  if (n_c == 0) {
+    for (int i = tid; i < P.col_words; i += blockDim.x) g_miss[i] = 0;
+    return;
+  }
+  const int off = D.phi_off[phi];
+  const RayRecord *recs = D.rec_col + off;
+
+  uint32_t *s_miss = reinterpret_cast<uint32_t *>(s_raw);
+  uint32_t *s_end = s_miss + P.col_words;
+  uint64_t *s_keys = reinterpret_cast<uint64_t *>(s_raw + (((size_t)2 * P.col_words * 4 + 15) & ~(size_t)15));
+  __shared__ int s_nk;
+  __shared__ int s_nmiss;
+  for (int i = tid; i < 2 * P.col_words; i += blockDim.x) s_miss[i] = 0;
+  if (tid == 0) {
+    s_nk = 0;
+    s_nmiss = 0;
+  }
+  // sort buffer: shared memory when the column's worst case fits, else the global spill region
+  const long long worst = (long long)n_c * P.contrib_per_point;
+  uint64_t *keys = worst <= P.sort_cap_smem ? s_keys : D.col_scratch + (size_t)2 * off * P.contrib_per_point;
+  __syncthreads();
+
+  // (a) contributions, update_hits src/map_awareness.cpp:135-171
+  for (int i = tid; i < n_c; i += blockDim.x) {
+    RayRecord rc = recs[i];
+    if (!(rc.phi_flags & kRecInside)) continue;
+    const int rho = rc.rho, z = rc.z;
+    if (P.visibility_check) atomicOr(&s_end[z * P.words_per_row + (rho >> 5)], 1u << (rho & 31));
+    double rate = ray_rate(P, rho, z);
+    int K = P.k_reach[rho];
+    int cnt = 1;
+    int zp[kDiffRange], zm[kDiffRange];
+    int dmax = 0;
+    for (int d = 1; d <= K && rho + d < P.nRho; d++) {
+      zp[d - 1] = cvt_trunc_x86(round((double)z + (double)d * rate));
+      zm[d - 1] = cvt_trunc_x86(round((double)z - (double)d * rate));
+      cnt += (zp[d - 1] >= 0 && zp[d - 1] < P.nZ) + (zm[d - 1] >= 0 && zm[d - 1] < P.nZ);
+      dmax = d;
+    }
+    int pos = atomicAdd(&s_nk, cnt);
+    keys[pos++] = contrib_key(z * P.nRho + rho, rc.t, 0);
+    for (int d = 1; d <= dmax; d++) {
+      if (zp[d - 1] >= 0 && zp[d - 1] < P.nZ) keys[pos++] = contrib_key(zp[d - 1] * P.nRho + rho + d, rc.t, 2 * d - 1);
+      if (zm[d - 1] >= 0 && zm[d - 1] < P.nZ) keys[pos++] = contrib_key(zm[d - 1] * P.nRho + rho - d, rc.t, 2 * d);
+    }
+  }
+  __syncthreads();
+  const int n_k = s_nk;
+
+  // (b) bitonic sort by (cell, point, substep)
+  int n_pad = 1;
+  while (n_pad < n_k) n_pad <<= 1;
+  for (int i = n_k + tid; i < n_pad; i += blockDim.x) keys[i] = ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= n_pad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < (n_pad >> 1); i += blockDim.x) {
+        int a = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+        int b = a | j;
+        uint64_t ka = keys[a], kb = keys[b];
+        bool up = (a & k) == 0;
+        if ((ka > kb) == up) {
+          keys[a] = kb;
+          keys[b] = ka;
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // (c) ordered fold per cell + staging of the distinct hit keys
+  for (int i = tid; i < n_k; i += blockDim.x) {
+    uint64_t k0 = keys[i];
+    int cell = (int)(k0 >> 37);
+    if (i > 0 && (int)(keys[i - 1] >> 37) == cell) continue;  // not the first contribution of its cell
+    const int zk = cell / P.nRho, rk = cell - zk * P.nRho;
+    float p = 0.f;
+    for (int j = i; j < n_k; j++) {
+      uint64_t kj = keys[j];
+      if ((int)(kj >> 37) != cell) break;
+      int s = (int)(kj & 31);
+      int d = s == 0 ? 0 : ((s & 1) ? (s + 1) >> 1 : -(s >> 1));
+      float odd = __ldg(&P.odds_table[(kDiffRange + d) * P.nRho + (rk - d)]);
+      p = (j == i) ? odd : odds_combine(p, odd);
+      if (p == 1.0f) break;  // saturated: 1 - (1-1)*(1-odd) == 1 for every later contribution
+    }
+    const uint32_t stamp = (uint32_t)(k0 & ((1ull << 37) - 1));  // t*32 + substep of the first insert
+    const int idx = agg_inc(&D.fc->n_hit);
+    if (idx >= P.max_hits) {
+      D.fc->error = kErrCapacity;
+      continue;
+    }
+    D.hit_key[idx] = (zk * P.nPhi + phi) * P.nRho + rk;  // mapIdx, map_awareness.h:81-84
+    D.hit_p[idx] = p;
+    D.hit_t[idx] = stamp;
+    // bucket activation stamp (libstdc++ iteration order)
+    atomicMin(&D.act[libstdcxx_bucket(vector_hash3(rk, phi, zk), F.bucket_count)], stamp);
+    // p_w = T_wa * centre  (identity rotation: one add per axis), src/map_local.cpp:151
+    double2 cxy = __ldg(&P.centre_xy[phi * P.nRho + rk]);
+    CellRef cr = locate_cell(P, cxy.x + F.t_wa[0], cxy.y + F.t_wa[1], __ldg(&P.centre_z[zk]) + F.t_wa[2]);
+    int lv = lvg_index(P, F, cr);
+    if (lv < 0) {
+      D.fc->error = kErrInternal;
+      D.hit_next[idx] = kLvgEmpty;
+      continue;
+    }
+    int old = atomicExch(&D.lvg_head[lv], idx);
+    D.hit_next[idx] = old;
+    if (old == kLvgEmpty) {
+      int tp = agg_inc(&D.fc->n_touched);
+      if (tp < P.max_touched) D.touched[tp] = (uint32_t)lv | kTouchedHitTag; else D.fc->error = kErrCapacity;
+    }
+    touch_subbox(P, F, D, cr.g);
+  }
+  __syncthreads();
+
+  // (d) ray walks, src/map_awareness.cpp:241-275
+  if (P.visibility_check) {
+    const int warp = tid >> 5, nwarps = blockDim.x >> 5;
+    // distinct inside end cells: each walks once (the walk depends only on (rho,phi,z))
+    for (int wi = warp; wi < P.col_words; wi += nwarps) {
+      uint32_t bits = s_end[wi];
+      const int z = wi / P.words_per_row, wr = wi - z * P.words_per_row;
+      while (bits) {
+        int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        walk_ray(P, s_miss, (wr << 5) + b, z);
+      }
+    }
+    // castable points outside the awareness range walk from the clamped cell (:261-265)
+    for (int base = warp * 32; base < n_c; base += nwarps * 32) {
+      int i = base + lane_id();
+      RayRecord rc;
+      rc.phi_flags = kRecInside;
+      if (i < n_c) rc = recs[i];
+      unsigned todo = __ballot_sync(0xffffffffu, !(rc.phi_flags & kRecInside));
+      while (todo) {
+        int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        int rho = __shfl_sync(0xffffffffu, rc.rho, src);
+        int z = __shfl_sync(0xffffffffu, rc.z, src);
+        walk_ray(P, s_miss, rho, z);
+      }
+    }
+  }
+  __syncthreads();
+
+  // (e) distinct miss cells -> voxel grid staging; bitmap to global for export
+  for (int wi = tid; wi < P.col_words; wi += blockDim.x) {
+    uint32_t bits = s_miss[wi];
+    g_miss[wi] = bits;
+    if (!bits) continue;
+    atomicAdd(&s_nmiss, __popc(bits));
+    const int z = wi / P.words_per_row, wr = wi - z * P.words_per_row;
+    const double pz = __ldg(&P.centre_z[z]) + F.t_wa[2];
+    while (bits) {
+      int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      int r = (wr << 5) + b;
+      double2 cxy = __ldg(&P.centre_xy[phi * P.nRho + r]);
+      CellRef cr = locate_cell(P, cxy.x + F.t_wa[0], cxy.y + F.t_wa[1], pz);
+      int lv = lvg_index(P, F, cr);
+      if (lv < 0) {
+        D.fc->error = kErrInternal;
+        continue;
+      }
+      int old = atomicAdd(&D.lvg_miss[lv], 1);
+      if (old == 0) {
+        int tp = agg_inc(&D.fc->n_touched);
+        if (tp < P.max_touched) D.touched[tp] = (uint32_t)lv; else D.fc->error = kErrCapacity;
+      }
+      touch_subbox(P, F, D, cr.g);
+    }
+  }
+  __syncthreads();
+  if (tid == 0 && s_nmiss) atomicAdd(&D.fc->n_miss, s_nmiss);
+}
+
+// ---- K3: resolve / allocate the subboxes touched this frame (allocate_ram, map_local.h:215-231) ------
+// One warp per touched subbox: lane 0 does the hash find-or-insert and pops a pool block for a
+// new subbox; the warp then initialises the block ('u', 'u', 0.f) with 16-byte stores.
+__global__ void __launch_bounds__(256) k_submaps(MapParams P, DeviceBuffers D) {
+  const FrameParams &F = *D.fp;
+  const int lane = lane_id();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n = D.fc->n_touched_sub;
+  for (int i = warp; i < n; i += nwarps) {
+    const int ls = D.touched_sub[i];
+    int block = -3, is_new = 0;
+    if (lane == 0) {
+      int lx = ls % P.lsg_dim_xy, ly = (ls / P.lsg_dim_xy) % P.lsg_dim_xy, lz = ls / (P.lsg_dim_xy * P.lsg_dim_xy);
+      int g[3] = {lx + F.lsg_base[0], ly + F.lsg_base[1], lz + F.lsg_base[2]};
+      uint64_t key;
+      if (!pack_glb(g, key)) {
+        D.fc->error = kErrRange;
+      } else {
+        uint32_t slot = ht_hash(key) & P.ht_mask;
+        bool done = false;
+        for (uint32_t probe = 0; probe <= P.ht_mask && !done; probe++) {
+          uint64_t k = D.ht_key[slot];
+          if (k == kEmptyKey) {
+            unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&D.ht_key[slot]),
+                                               (unsigned long long)kEmptyKey, (unsigned long long)key);
+            k = (old == kEmptyKey) ? kEmptyKey : (uint64_t)old;
+            if (old == kEmptyKey) {
+              int top = atomicSub(D.free_top, 1) - 1;
+              if (top < 0) {
+                atomicAdd(D.free_top, 1);
+                D.ht_key[slot] = key;  // keep the key so the table stays consistent; mark unusable
+                D.ht_val[slot] = -3;
+                D.fc->error = kErrPool;
+                block = -3;
+              } else {
+                block = D.free_stack[top];
+                D.ht_val[slot] = block;
+                is_new = 1;
+              }
+              done = true;
+              break;
+            }
+          }
+          if (k == key) {
+            block = D.ht_val[slot];
+            done = true;
+            break;
+          }
+          slot = (slot + 1) & P.ht_mask;
+        }
+        if (!done) D.fc->error = kErrPool;
+      }
+      D.lsg_block[ls] = block;
+      D.lsg_flag[ls] = 0;
+      if (is_new) atomicAdd(&D.fc->n_new_blocks, 1);
+    }
+    block = __shfl_sync(0xffffffffu, block, 0);
+    is_new = __shfl_sync(0xffffffffu, is_new, 0);
+    if (is_new) {
+      const size_t base = (size_t)block * P.cell_stride;  // stride is cells padded to a multiple of 16
+      uint4 *lo4 = reinterpret_cast<uint4 *>(D.pool_lo + base);
+      uint4 *oc4 = reinterpret_cast<uint4 *>(D.pool_occ + base);
+      uint4 *in4 = reinterpret_cast<uint4 *>(D.pool_inf + base);
+      const uint4 z4 = make_uint4(0, 0, 0, 0);
+      const uint32_t uu = 0x75757575u;  // 'u' x4
+      const uint4 u4 = make_uint4(uu, uu, uu, uu);
+      for (int j = lane; j < P.cell_stride / 4; j += 32) lo4[j] = z4;
+      for (int j = lane; j < P.cell_stride / 16; j += 32) {
+        oc4[j] = u4;
+        in4[j] = u4;
+      }
+    }
+  }
+}
+
+// ---- K5: clamped log-odds fusion, one thread per touched cell (map_local.cpp:147-207) ---------------
+constexpr int kFuseLocal = 16;
+__global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D) {
+  const FrameParams &F = *D.fp;
+  FrameCounters *fc = D.fc;
+  // a frame that crosses a libstdc++ rehash needs the slow ordering pass first (host re-launches)
+  if (F.order_mode == 0 && fc->n_hit > (int)F.bucket_count) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) fc->overflow = 1;
+    return;
+  }
+  const int n = min(fc->n_touched, P.max_touched);
+  const int dxy = P.lvg_dim_xy;
+  int my_touched = 0, my_obs = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t e = D.touched[i];
+    const int lv = (int)(e & ~kTouchedHitTag);
+    // A cell with both hits and misses appears twice in the touched list.  The first thread to
+    // swap in kLvgClaimed owns the cell; the other one only restores the empty marker.
+    const int head = atomicExch(&D.lvg_head[lv], kLvgClaimed);
+    if (head == kLvgClaimed) {
+      D.lvg_head[lv] = kLvgEmpty;
+      continue;
+    }
+    const int mc = D.lvg_miss[lv];
+    D.lvg_miss[lv] = 0;
+    if (!(head != kLvgEmpty && mc > 0)) D.lvg_head[lv] = kLvgEmpty;  // single entry: restore ourselves
+    int c[3] = {lv % dxy + F.lvg_base[0], (lv / dxy) % dxy + F.lvg_base[1], lv / (dxy * dxy) + F.lvg_base[2]};
+    int g[3], sub;
+    {
+      int l[3];
+      for (int a = 0; a < 3; a++) {
+        g[a] = floor_div(c[a], P.n);
+        l[a] = c[a] - g[a] * P.n;
+      }
+      sub = (l[2] * P.n + l[1]) * P.n + l[0];
+    }
+    const int ls = lsg_index(P, F, g);
+    const int block = ls >= 0 ? D.lsg_block[ls] : -3;
+    if (block < 0) continue;  // collapsed subbox (allocate_ram false) or pool error
+    const size_t addr = (size_t)block * P.cell_stride + sub;
+    float lo = D.pool_lo[addr];
+    char occ = D.pool_occ[addr];
+    my_touched++;
+
+    // hits in the reference's unordered_map iteration order: descending (bucket activation, insert stamp)
+    if (head != kLvgEmpty) {
+      int hidx[kFuseLocal];
+      uint64_t hst[kFuseLocal];
+      int cnt = 0;
+      for (int h = head; h != kLvgEmpty; h = D.hit_next[h]) {
+        if (cnt < kFuseLocal) {
+          int key = D.hit_key[h];
+          int zk = key / (P.nRho * P.nPhi), rem = key - zk * (P.nRho * P.nPhi);
+          int pk = rem / P.nRho, rk = rem - pk * P.nRho;
+          uint32_t a = D.act[libstdcxx_bucket(vector_hash3(rk, pk, zk), F.bucket_count)];
+          uint64_t st = ((uint64_t)a << 32) | D.hit_t[h];
+          int j = cnt;
+          while (j > 0 && hst[j - 1] < st) {
+            hst[j] = hst[j - 1];
+            hidx[j] = hidx[j - 1];
+            j--;
+          }
+          hst[j] = st;
+          hidx[j] = h;
+        }
+        cnt++;
+      }
+      uint64_t prev = ~0ull;
+      for (int k = 0; k < cnt; k++) {
+        int h;
+        if (cnt <= kFuseLocal) {
+          h = hidx[k];
+        } else {  // long list: selection by repeated traversal
+          uint64_t best = 0;
+          h = -1;
+          for (int q = head; q != kLvgEmpty; q = D.hit_next[q]) {
+            int key = D.hit_key[q];
+            int zk = key / (P.nRho * P.nPhi), rem = key - zk * (P.nRho * P.nPhi);
+            int pk = rem / P.nRho, rk = rem - pk * P.nRho;
+            uint32_t a = D.act[libstdcxx_bucket(vector_hash3(rk, pk, zk), F.bucket_count)];
+            uint64_t st = ((uint64_t)a << 32) | D.hit_t[q];
+            if (st < prev && (h < 0 || st > best)) {
+              best = st;
+              h = q;
+            }
+          }
+          prev = best;
+        }
+        // src/map_local.cpp:157-171
+        if (lo < P.lo_max) {
+          lo = __fadd_rn(lo, logit_f(D.hit_p[h], P.log10f_fma));
+          lo = lo > P.lo_max ? P.lo_max : lo;
+        }
+        if (lo > P.lo_sh && occ != 'o') {
+          occ = 'o';
+          my_obs++;
+        }
+      }
+    }
+    // misses: every miss cell mapping here applies the same step (src/map_local.cpp:188-203)
+    for (int k = 0; k < mc; k++) {
+      bool changed = false;
+      if (lo >= P.lo_min) {
+        float nl = __fadd_rn(lo, P.lo_miss);
+        nl = nl < P.lo_min ? P.lo_min : nl;
+        changed = nl != lo;
+        lo = nl;
+      }
+      if (lo < P.lo_sh && occ != 'f') {
+        occ = 'f';
+        changed = true;
+      }
+      if (!changed) break;  // fixed point: the remaining identical steps are no-ops
+    }
+    D.pool_lo[addr] = lo;
+    D.pool_occ[addr] = occ;
+  }
+  // counters
+  for (int ofs = 16; ofs > 0; ofs >>= 1) {
+    my_touched += __shfl_xor_sync(0xffffffffu, my_touched, ofs);
+    my_obs += __shfl_xor_sync(0xffffffffu, my_obs, ofs);
+  }
+  if (lane_id() == 0) {
+    if (my_touched) atomicAdd(&fc->n_touched_voxels, my_touched);
+    if (my_obs) atomicAdd(&fc->obs_delta, my_obs);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) fc->fused = 1;
+}
+
+// cumulative counters (ram_expand_cnt, obs_cnt), single thread after k_fuse
+__global__ void k_frame_end(DeviceBuffers D) {
+  if (D.fc->fused) {
+    D.cum[0] += D.fc->n_new_blocks;
+    D.cum[1] += D.fc->obs_delta;
+    D.cum[2] += D.fc->n_new_blocks;
+  }
+}
+
+}  // namespace mlm

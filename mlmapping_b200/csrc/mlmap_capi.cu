@@ -1,0 +1,1089 @@
+// C ABI of the B200-native MLMapping hot path (include/mlmap_b200.h).  Host logic only:
+// table construction (reference init_map functions), the per-frame launch sequence, the
+// libstdc++ bucket-count chain, and buffer management.  All map arithmetic runs in the
+// kernels of frame_kernels.cuh / order_kernels.cuh / query_kernels.cuh; there is no CPU
+// fallback — without a CUDA device mlm_create fails with MLM_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "../../include/mlmap_b200.h"
+#include "frame_kernels.cuh"
+#include "order_kernels.cuh"
+#include "query_kernels.cuh"
+
+using namespace mlm;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      g_last_error = std::string(#expr) + ": " + cudaGetErrorString(_e);                      \
+      return MLM_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+// ---- Sophus/Eigen subset on the host (reference 3rdPartLib/Sophus/sophus/so3.cpp:42-90, se3.cpp:59-95)
+struct HQuat {
+  double w, x, y, z;
+};
+struct HPose {
+  HQuat q;
+  double t[3];
+};
+HQuat h_normalized(const HQuat &q) {  // Eigen normalize(): coeffs / sqrt(squaredNorm), storage x,y,z,w
+  double n2 = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+  double n = sqrt(n2);
+  return HQuat{q.w / n, q.x / n, q.y / n, q.z / n};
+}
+HQuat h_mul(const HQuat &a, const HQuat &b) {
+  HQuat r;
+  r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+  r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+  r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+  r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+  return r;
+}
+void h_rotate(const HQuat &q, const double v[3], double out[3]) {  // Eigen _transformVector
+  double uvx = q.y * v[2] - q.z * v[1];
+  double uvy = q.z * v[0] - q.x * v[2];
+  double uvz = q.x * v[1] - q.y * v[0];
+  uvx += uvx;
+  uvy += uvy;
+  uvz += uvz;
+  double cx = q.y * uvz - q.z * uvy;
+  double cy = q.z * uvx - q.x * uvz;
+  double cz = q.x * uvy - q.y * uvx;
+  out[0] = v[0] + q.w * uvx + cx;
+  out[1] = v[1] + q.w * uvy + cy;
+  out[2] = v[2] + q.w * uvz + cz;
+}
+HPose h_pose_from7(const double p[7]) {  // SE3(SO3(Quaterniond), t): the SO3 ctor normalises
+  HPose r;
+  r.q = h_normalized(HQuat{p[3], p[4], p[5], p[6]});
+  r.t[0] = p[0];
+  r.t[1] = p[1];
+  r.t[2] = p[2];
+  return r;
+}
+HPose h_compose(const HPose &a, const HPose &b) {  // SE3::operator*
+  HPose r = a;
+  double rt[3];
+  h_rotate(a.q, b.t, rt);
+  for (int i = 0; i < 3; i++) r.t[i] = r.t[i] + rt[i];
+  r.q = h_normalized(h_mul(a.q, b.q));
+  return r;
+}
+HPose h_inverse(const HPose &a) {  // SE3::inverse
+  HPose r;
+  r.q = h_normalized(HQuat{a.q.w, -a.q.x, -a.q.y, -a.q.z});
+  double nt[3] = {a.t[0] * -1., a.t[1] * -1., a.t[2] * -1.};
+  h_rotate(r.q, nt, r.t);
+  return r;
+}
+
+// libstdc++ _Prime_rehash_policy growth chain from an empty table with max_load_factor 1:
+// first insert -> 13, then next_bkt(2*B) from the sparse __prime_list (SURVEY Appendix B;
+// verified against this toolchain's unordered_set in tests/test_host_logic.py).
+const uint32_t kBucketChain[] = {1,      13,     29,     59,      127,     257,     541,     1109,
+                                 2357,   5087,   10273,  20753,   42043,   85229,   172933,  351061,
+                                 712697, 1447153, 2938679, 5967347, 12117689, 24607243, 49969847, 101473717};
+constexpr int kBucketChainLen = sizeof(kBucketChain) / sizeof(kBucketChain[0]);
+uint32_t chain_next(uint32_t B) {
+  for (int i = 0; i + 1 < kBucketChainLen; i++)
+    if (kBucketChain[i] == B) return kBucketChain[i + 1];
+  return 0;
+}
+uint32_t chain_cover(uint32_t n) {  // smallest chain value >= n
+  for (int i = 0; i < kBucketChainLen; i++)
+    if (kBucketChain[i] >= n) return kBucketChain[i];
+  return 0;
+}
+
+int next_pow2(int n) {
+  int p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+int host_floor_div(int a, int b) {
+  int q = a / b, r = a - q * b;
+  return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q;
+}
+
+}  // namespace
+
+struct mlm_map {
+  mlm_config cfg;
+  MapParams P;
+  DeviceBuffers D;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  FrameParams *h_fp = nullptr;    // pinned
+  FrameCounters *h_fc = nullptr;  // pinned
+  int64_t *h_cum = nullptr;       // pinned
+  void *h_stage = nullptr;        // pinned input staging
+  size_t stage_bytes = 0;
+  void *d_input = nullptr;
+  size_t input_bytes = 0;
+  int *d_ticket = nullptr;
+  // slow-path ordering scratch
+  uint64_t *d_sort_a = nullptr, *d_sort_b = nullptr;
+  int *d_seq_a = nullptr, *d_seq_b = nullptr;
+  int sort_cap = 0;
+  uint32_t act_cap = 0;
+  uint32_t bucket_count = 1;  // emulated hit_idx_odds_hashmap.bucket_count()
+  uint32_t last_order_B = 1;  // bucket count the last frame's stamps refer to
+  int last_n_hit = 0;
+  int col_smem_bytes = 0;
+  std::vector<void *> allocs;
+  int64_t launches = 0;
+  HPose T_bs;
+  void *l2_buf = nullptr;
+  size_t l2_bytes = 0;
+  int sm_count = 148;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(mlm_map *h, T **p, size_t count) {
+  void *q = nullptr;
+  CUDA_TRY(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+  h->allocs.push_back(q);
+  *p = reinterpret_cast<T *>(q);
+  return MLM_OK;
+}
+
+// ---- awareness tables, reference src/map_awareness.cpp:19-82,119-132; include/map_awareness.h:120-146
+struct AwarenessTables {
+  std::vector<float> odds;  // [21][nRho]
+  std::vector<int> k_reach;
+  std::vector<double2> centre_xy;
+  std::vector<double> centre_z;
+  double dPhi, z_border_min;
+  int nPhi, nZ;
+};
+float host_sigma_in_dr(double coe, double dRho, size_t x) {
+  float dis = (x * dRho);
+  return coe * dis * dis / dRho;
+}
+float host_standard_ND(float x) {
+  double a1 = 0.254829592, a2 = -0.284496736, a3 = 1.421413741, a4 = -1.453152027, a5 = 1.061405429;
+  double p = 0.3275911;
+  int sign = 1;
+  if (x < 0) sign = -1;
+  x = fabsf(x) / sqrt(2.0);
+  double t = 1.0 / (1.0 + p * x);
+  // the reference's exp(-x * x) has a float argument and `using namespace std`: std::exp(float) == expf
+  double y = 1.0 - (((((a5 * t + a4) * t) + a3) * t + a2) * t + a1) * t * expf(-x * x);
+  return 0.5 * (1.0 + sign * y);
+}
+float host_get_odds(double coe, double dRho, int diff, size_t r) {
+  if (r == 0) r = 1;
+  float up = host_standard_ND(static_cast<float>(diff + 0.5) / host_sigma_in_dr(coe, dRho, r));
+  float down = host_standard_ND(static_cast<float>(diff - 0.5) / host_sigma_in_dr(coe, dRho, r));
+  float res = up - down < 0.001 ? 0.001 : up - down;
+  res = res >= 0.999 ? 0.999 : res;
+  return res;
+}
+int build_awareness_tables(const mlm_config &c, AwarenessTables &T) {
+  const int nRho = c.am_n_rho;
+  T.dPhi = c.am_d_phi_deg * M_PI / 180;
+  T.nPhi = static_cast<int>(360 / c.am_d_phi_deg);
+  T.nZ = c.am_n_z_below + c.am_n_z_over + 1;
+  T.z_border_min = -(c.am_n_z_below * c.am_d_z) - 0.5 * c.am_d_z;
+  T.odds.resize((size_t)kOddsRows * nRho);
+  for (int diff = -kDiffRange; diff < kDiffRange + 1; diff++)
+    for (int r = 0; r < nRho; r++)
+      T.odds[(size_t)(diff + kDiffRange) * nRho + r] = host_get_odds(c.depth_noise_coe, c.am_d_rho, diff, r);
+  T.k_reach.resize(nRho);
+  for (int r = 0; r < nRho; r++) {
+    // loop bound of update_hits: diff_r < 3 * sigma_in_dr(rho)   (int -> float compare)
+    int K = 0;
+    for (int d = 1; d < 3 * host_sigma_in_dr(c.depth_noise_coe, c.am_d_rho, r); d++) {
+      K = d;
+      if (d > 4 * kDiffRange) break;
+    }
+    T.k_reach[r] = K;
+  }
+  T.centre_z.resize(T.nZ);
+  for (int z = 0; z < T.nZ; z++) T.centre_z[z] = T.z_border_min + (c.am_d_z / 2) + (z * c.am_d_z);
+  T.centre_xy.resize((size_t)T.nPhi * nRho);
+  for (int phi = 0; phi < T.nPhi; phi++)
+    for (int rho = 0; rho < nRho; rho++) {
+      double center_rho = c.am_d_rho / 2 + (rho * c.am_d_rho);
+      double center_phi = T.dPhi / 2 + (phi * T.dPhi);
+      T.centre_xy[(size_t)phi * nRho + rho] = make_double2(center_rho * cos(center_phi), center_rho * sin(center_phi));
+    }
+  return MLM_OK;
+}
+
+int validate_config(const mlm_config &c, std::string &why) {
+  auto bad = [&](const char *m) {
+    why = m;
+    return MLM_ERR_INVALID_CONFIG;
+  };
+  if (!(c.am_d_rho > 0) || !(c.am_d_phi_deg > 0) || !(c.am_d_z > 0)) return bad("awareness resolutions must be > 0");
+  if (c.am_n_rho < 2 || c.am_n_z_below < 0 || c.am_n_z_over < 0) return bad("awareness extents");
+  if (!(c.subbox_d_xyz > 0) || c.subbox_n < 1 || c.subbox_n > 64) return bad("subbox size");
+  if (!(c.depth_noise_coe >= 0)) return bad("depth_noise_coe");
+  if (c.max_points < 1 || c.max_points > (1 << 26)) return bad("max_points must be in [1, 2^26]");
+  if (c.pool_submaps < 1) return bad("pool_submaps");
+  int nPhi = static_cast<int>(360 / c.am_d_phi_deg);
+  if (nPhi < 1 || nPhi > kMaxPhi) return bad("n_Phi out of supported range [1,4096]");
+  int nZ = c.am_n_z_below + c.am_n_z_over + 1;
+  if ((long long)nZ * c.am_n_rho >= (1ll << kCellBits)) return bad("n_Z*n_Rho must be < 2^20");
+  if ((long long)nZ * c.am_n_rho * nPhi >= (1ll << 31)) return bad("awareness cell count must be < 2^31");
+  return MLM_OK;
+}
+
+int map_device_error(int e) {
+  switch (e) {
+    case 0: return MLM_OK;
+    case kErrRange: return MLM_ERR_INVALID_ARG;
+    case kErrPool: return MLM_ERR_POOL_EXHAUSTED;
+    case kErrCapacity: return MLM_ERR_CAPACITY;
+    default: return MLM_ERR_CUDA;
+  }
+}
+
+inline int grid_for(size_t n, int threads) { return (int)std::max<size_t>(1, (n + threads - 1) / threads); }
+
+// full bitonic sort of keys[0..n_pad) ascending on the handle's stream
+void device_sort(mlm_map *h, uint64_t *keys, int n_pad) {
+  if (n_pad <= 1) return;
+  const int chunk = std::min(kSortChunk, n_pad);
+  const int nchunks = n_pad / chunk;
+  k_bitonic_local<<<nchunks, kSortThreads, 0, h->stream>>>(keys, n_pad, 2, chunk);
+  h->launches++;
+  for (int k = chunk << 1; k <= n_pad; k <<= 1) {
+    for (int j = k >> 1; j >= chunk; j >>= 1) {
+      k_bitonic_global<<<grid_for(n_pad >> 1, 256), 256, 0, h->stream>>>(keys, n_pad, j, k);
+      h->launches++;
+    }
+    k_bitonic_local<<<nchunks, kSortThreads, 0, h->stream>>>(keys, n_pad, k, k);
+    h->launches++;
+  }
+}
+
+// Slow ordering path: the frame's distinct hit keys exceed the emulated bucket count, so
+// libstdc++ would rehash mid-frame (possibly several times).  Produces virtual positions in
+// hit_t and bucket activations for the final bucket count.  Returns the final bucket count.
+int order_slow_path(mlm_map *h, int n, uint32_t *B_final_out) {
+  cudaStream_t s = h->stream;
+  const int T = 256;
+  int n_pad = next_pow2(n);
+  k_order_seed<<<grid_for(n_pad, T), T, 0, s>>>(h->D, h->d_sort_a, n, n_pad);
+  device_sort(h, h->d_sort_a, n_pad);
+  k_order_take_seq<<<grid_for(n, T), T, 0, s>>>(h->d_sort_a, h->d_seq_a, n);
+  h->launches += 2;
+  uint32_t B = h->bucket_count;
+  while ((uint32_t)n > B) {
+    int m = (int)std::min<uint32_t>(B, (uint32_t)n);
+    if (m > 1) {
+      int m_pad = next_pow2(m);
+      k_fill_u32<<<grid_for(B, T), T, 0, s>>>(h->D.act, 0xffffffffu, (int)B);
+      k_stage_act<<<grid_for(m, T), T, 0, s>>>(h->P, h->D, h->d_seq_a, m, B);
+      k_stage_keys<<<grid_for(m_pad, T), T, 0, s>>>(h->P, h->D, h->d_seq_a, h->d_sort_b, m, m_pad, B);
+      device_sort(h, h->d_sort_b, m_pad);
+      k_stage_apply<<<grid_for(m, T), T, 0, s>>>(h->d_sort_b, h->d_seq_a, h->d_seq_b, m);
+      k_copy_i32<<<grid_for(m, T), T, 0, s>>>(h->d_seq_a, h->d_seq_b, m);
+      h->launches += 5;
+    }
+    uint32_t nb = chain_next(B);
+    if (nb == 0 || nb > h->act_cap) {
+      g_last_error = "hit map bucket chain exceeded";
+      return MLM_ERR_CAPACITY;
+    }
+    B = nb;
+  }
+  k_fill_u32<<<grid_for(B, T), T, 0, s>>>(h->D.act, 0xffffffffu, (int)B);
+  k_order_final<<<grid_for(n, T), T, 0, s>>>(h->P, h->D, h->d_seq_a, n, B);
+  h->launches += 2;
+  *B_final_out = B;
+  return MLM_OK;
+}
+
+int run_frame(mlm_map *h, bool depth, const void *d_in, int rows, int cols, int n_points, const double T_wb[7],
+              mlm_frame_stats *stats) {
+  const MapParams &P = h->P;
+  cudaStream_t s = h->stream;
+  const int N = depth ? rows * cols : n_points;
+  if (N < 0 || N > P.max_points) {
+    g_last_error = "frame has more points than cfg.max_points";
+    return MLM_ERR_CAPACITY;
+  }
+  // input_pc_pose prologue, src/map_awareness.cpp:184-186
+  HPose Twb = h_pose_from7(T_wb);
+  HPose Twa;
+  Twa.q = h_normalized(HQuat{1, 0, 0, 0});
+  Twa.t[0] = Twb.t[0];
+  Twa.t[1] = Twb.t[1];
+  Twa.t[2] = Twb.t[2];
+  HPose Tws = h_compose(Twb, h->T_bs);
+  HPose Tls = h_compose(h_inverse(Twa), Tws);
+  FrameParams &F = *h->h_fp;
+  F.q_ls[0] = Tls.q.w;
+  F.q_ls[1] = Tls.q.x;
+  F.q_ls[2] = Tls.q.y;
+  F.q_ls[3] = Tls.q.z;
+  for (int i = 0; i < 3; i++) {
+    F.t_ls[i] = Tls.t[i];
+    F.t_wa[i] = Twa.t[i];
+  }
+  F.rows = rows;
+  F.cols = cols;
+  F.n_points = n_points;
+  F.bucket_count = h->bucket_count;
+  F.order_mode = 0;
+  // frame-local voxel grid origin: awareness bounding box around t_wa plus a margin
+  const double R = P.nRho * P.dRho;
+  F.lvg_base[0] = (int)floor((Twa.t[0] - R) / P.d_sub) - P.lvg_margin;
+  F.lvg_base[1] = (int)floor((Twa.t[1] - R) / P.d_sub) - P.lvg_margin;
+  F.lvg_base[2] = (int)floor((Twa.t[2] + P.z_border_min) / P.d_sub) - P.lvg_margin;
+  for (int i = 0; i < 3; i++) F.lsg_base[i] = host_floor_div(F.lvg_base[i], P.n) - 1;
+  CUDA_TRY(cudaMemcpyAsync(h->D.fp, h->h_fp, sizeof(FrameParams), cudaMemcpyHostToDevice, s));
+
+  k_frame_begin<<<h->sm_count, 256, 0, s>>>(P, h->D);
+  const size_t proj_smem = (size_t)(P.nPhi + 256) * sizeof(int);
+  if (depth)
+    k_project<true><<<grid_for(N, 256), 256, proj_smem, s>>>(P, h->D, d_in, rows, cols, 0, h->d_ticket);
+  else
+    k_project<false><<<grid_for(N, 256), 256, proj_smem, s>>>(P, h->D, d_in, 0, 0, n_points, h->d_ticket);
+  k_scatter<<<grid_for(N, 256), 256, (size_t)2 * P.nPhi * sizeof(int), s>>>(P, h->D, N);
+  k_column<<<P.nPhi, kColThreads, h->col_smem_bytes, s>>>(P, h->D);
+  k_submaps<<<h->sm_count, 256, 0, s>>>(P, h->D);
+  k_fuse<<<h->sm_count * 4, 256, 0, s>>>(P, h->D);
+  k_frame_end<<<1, 1, 0, s>>>(h->D);
+  h->launches += 7;
+  CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h->h_cum, h->D.cum, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+
+  int slow = 0;
+  uint32_t order_B = h->bucket_count;
+  if (h->h_fc->error == 0 && h->h_fc->overflow) {
+    slow = 1;
+    const int n = h->h_fc->n_hit;
+    if (n > h->sort_cap) {
+      g_last_error = "hit count exceeds ordering scratch";
+      return MLM_ERR_CAPACITY;
+    }
+    uint32_t Bf = 0;
+    int rc = order_slow_path(h, n, &Bf);
+    if (rc != MLM_OK) return rc;
+    order_B = Bf;
+    F.bucket_count = Bf;
+    F.order_mode = 1;
+    CUDA_TRY(cudaMemcpyAsync(h->D.fp, h->h_fp, sizeof(FrameParams), cudaMemcpyHostToDevice, s));
+    k_fuse<<<h->sm_count * 4, 256, 0, s>>>(P, h->D);
+    k_frame_end<<<1, 1, 0, s>>>(h->D);
+    h->launches += 2;
+    CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(h->h_cum, h->D.cum, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaGetLastError());
+  }
+  const FrameCounters &C = *h->h_fc;
+  // bucket-count evolution of hit_idx_odds_hashmap (clear() keeps the bucket array)
+  if (C.n_hit > 0 && h->bucket_count == 1) h->bucket_count = 13;
+  while ((uint32_t)C.n_hit > h->bucket_count) {
+    uint32_t nb = chain_next(h->bucket_count);
+    if (nb == 0) break;
+    h->bucket_count = nb;
+  }
+  h->last_order_B = order_B;
+  h->last_n_hit = C.n_hit;
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->n_points = C.n_points;
+    stats->n_inside = C.n_inside;
+    stats->n_cast = C.n_cast;
+    stats->n_hit_cells = C.n_hit;
+    stats->n_miss_cells = C.n_miss;
+    stats->n_touched_voxels = C.n_touched_voxels;
+    stats->n_new_submaps = C.n_new_blocks;
+    stats->hit_bucket_count = (int32_t)h->bucket_count;
+    stats->ordering_slow_path = slow;
+    stats->status = map_device_error(C.error);
+    stats->ram_expand_cnt = h->h_cum[0];
+    stats->obs_cnt = h->h_cum[1];
+  }
+  if (C.error) {
+    g_last_error = "device raised error code " + std::to_string(C.error);
+    return map_device_error(C.error);
+  }
+  return MLM_OK;
+}
+
+int ensure_input(mlm_map *h, size_t bytes) {
+  if (bytes <= h->input_bytes) return MLM_OK;
+  if (h->d_input) cudaFree(h->d_input);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  h->d_input = nullptr;
+  h->h_stage = nullptr;
+  CUDA_TRY(cudaMalloc(&h->d_input, bytes));
+  CUDA_TRY(cudaMallocHost(&h->h_stage, bytes));
+  h->input_bytes = h->stage_bytes = bytes;
+  return MLM_OK;
+}
+
+}  // namespace
+
+namespace {
+template <typename OutT, typename Launch>
+int host_query(mlm_handle h, const double *pos, size_t n, OutT *out, size_t out_per, Launch launch) {
+  if (!h || (!pos && n) || (!out && n)) return MLM_ERR_INVALID_ARG;
+  if (n == 0) return MLM_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  double *d_pos = nullptr;
+  OutT *d_out = nullptr;
+  CUDA_TRY(cudaMallocAsync((void **)&d_pos, n * 24, h->stream));
+  CUDA_TRY(cudaMallocAsync((void **)&d_out, n * out_per * sizeof(OutT), h->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_pos, pos, n * 24, cudaMemcpyHostToDevice, h->stream));
+  launch(d_pos, d_out);
+  h->launches++;
+  CUDA_TRY(cudaMemcpyAsync(out, d_out, n * out_per * sizeof(OutT), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaFreeAsync(d_pos, h->stream));
+  CUDA_TRY(cudaFreeAsync(d_out, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaGetLastError());
+  return MLM_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int mlm_abi_version(void) { return MLM_ABI_VERSION; }
+const char *mlm_last_error(void) { return g_last_error.c_str(); }
+
+int mlm_default_config(mlm_config *c) {
+  if (!c) return MLM_ERR_INVALID_ARG;
+  memset(c, 0, sizeof(*c));
+  // reference launch/config/config_sim.yaml:8-55
+  c->am_d_rho = 0.20;
+  c->am_d_phi_deg = 5;
+  c->am_d_z = 0.20;
+  c->am_n_rho = 40;
+  c->am_n_z_below = 20;
+  c->am_n_z_over = 20;
+  c->use_raycasting = 1;
+  c->depth_noise_coe = 0.000001;
+  c->subbox_d_xyz = 0.2;
+  c->subbox_n = 10;
+  c->log_odds_min = -2.0f;
+  c->log_odds_max = 4.2f;
+  c->log_odds_hit = 0.7f;
+  c->log_odds_miss = -0.9f;
+  c->log_odds_occupied_sh = 3.0f;
+  c->use_exploration_frontiers = 0;
+  c->cam_cx = 320.0f;
+  c->cam_cy = 180.0f;
+  c->cam_fx = 347.99755859375f;
+  c->cam_fy = 347.99755859375f;
+  // T_B_S rotation [[0,0,1],[-1,0,0],[0,-1,0]] as a unit quaternion, translation (0.12,0,0)
+  c->T_bs[0] = 0.12;
+  c->T_bs[1] = 0.0;
+  c->T_bs[2] = 0.0;
+  c->T_bs[3] = 0.5;
+  c->T_bs[4] = -0.5;
+  c->T_bs[5] = 0.5;
+  c->T_bs[6] = -0.5;
+  c->inflate_n = 2;
+  c->inflate_global_n = 2;
+  c->apply_inflate = 1;
+  c->inflate_height = 0.1;
+  c->sample_cnt = 0;  // full-frame mode (the north-star workload); the yaml's 500 selects sampled mode
+  c->max_points = 640 * 480;
+  c->pool_submaps = 32768;
+  return MLM_OK;
+}
+
+int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
+  if (!cfg || !out) return MLM_ERR_INVALID_ARG;
+  *out = nullptr;
+  std::string why;
+  int rc = validate_config(*cfg, why);
+  if (rc != MLM_OK) {
+    g_last_error = why;
+    return rc;
+  }
+  if (cfg->use_exploration_frontiers) {
+    g_last_error = "use_exploration_frontiers=true (update_observation / release pass) is not implemented on the GPU path";
+    return MLM_ERR_UNSUPPORTED;
+  }
+  if (cfg->sample_cnt != 0) {
+    g_last_error = "sampled project_depth (mlmapping_sample_cnt > 0) is not implemented; use full-frame mode (0)";
+    return MLM_ERR_UNSUPPORTED;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    g_last_error = "no CUDA device available: the mlmap_b200 hot path has no CPU fallback";
+    return MLM_ERR_NO_DEVICE;
+  }
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    g_last_error = "kernels are built for sm_100a only; found sm_" + std::to_string(prop.major * 10 + prop.minor);
+    return MLM_ERR_NO_DEVICE;
+  }
+
+  AwarenessTables T;
+  build_awareness_tables(*cfg, T);
+  int maxK = 0;
+  for (int r = 0; r < cfg->am_n_rho; r++) {
+    // preconditions of update_hits: table row index diff_r+10 <= 20 and rho-diff_r >= 0
+    if (T.k_reach[r] > kDiffRange || T.k_reach[r] > r) {
+      g_last_error = "depth_noise_coe too large: 3*sigma_in_dr(rho) reaches outside the odds table / below rho 0";
+      return MLM_ERR_INVALID_CONFIG;
+    }
+    maxK = std::max(maxK, T.k_reach[r]);
+  }
+
+  mlm_map *h = new mlm_map();
+  h->cfg = *cfg;
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->T_bs = h_pose_from7(cfg->T_bs);
+  MapParams &P = h->P;
+  memset(&P, 0, sizeof(P));
+  P.dRho = cfg->am_d_rho;
+  P.dPhi = T.dPhi;
+  P.dZ = cfg->am_d_z;
+  P.z_border_min = T.z_border_min;
+  P.nRho = cfg->am_n_rho;
+  P.nPhi = T.nPhi;
+  P.nZ = T.nZ;
+  P.n_below = cfg->am_n_z_below;
+  P.visibility_check = cfg->use_raycasting != 0;
+  P.maxK = maxK;
+  P.words_per_row = (P.nRho + 31) / 32;
+  P.col_words = P.nZ * P.words_per_row;
+  // local_map_cartesian::init_map, src/map_local.cpp:56-62
+  P.d_sub = cfg->subbox_d_xyz;
+  P.d_sub_half = P.d_sub * 0.5;
+  P.n = cfg->subbox_n;
+  P.d_glb = P.d_sub * P.n;
+  P.cells = P.n * P.n * P.n;
+  P.cell_stride = (P.cells + 15) & ~15;
+  P.lo_min = cfg->log_odds_min;
+  P.lo_max = cfg->log_odds_max;
+  P.lo_miss = cfg->log_odds_miss;
+  P.lo_sh = cfg->log_odds_occupied_sh;
+  P.cx = cfg->cam_cx;
+  P.cy = cfg->cam_cy;
+  P.fx = cfg->cam_fx;
+  P.fy = cfg->cam_fy;
+  P.inv_factor = 1.0 / 1000.0;  // src/mlmap.h:85-86
+  // glibc dispatches __logf to its FMA build when FMA and AVX2 are usable (ifunc-fma.h)
+  P.log10f_fma = (__builtin_cpu_supports("fma") && __builtin_cpu_supports("avx2")) ? 1 : 0;
+  P.lvg_margin = P.n + 1;
+  const double R = P.nRho * P.dRho;
+  P.lvg_dim_xy = (int)ceil(2 * R / P.d_sub) + 2 * P.lvg_margin + 2;
+  P.lvg_dim_z = (int)ceil(P.nZ * P.dZ / P.d_sub) + 2 * P.lvg_margin + 2;
+  P.lsg_dim_xy = P.lvg_dim_xy / P.n + 3;
+  P.lsg_dim_z = P.lvg_dim_z / P.n + 3;
+  const long long n_cells = (long long)P.nZ * P.nPhi * P.nRho;
+  const long long lvg_cells = (long long)P.lvg_dim_xy * P.lvg_dim_xy * P.lvg_dim_z;
+  const long long lsg_cells = (long long)P.lsg_dim_xy * P.lsg_dim_xy * P.lsg_dim_z;
+  if (lvg_cells >= (1ll << 31)) {
+    delete h;
+    g_last_error = "frame-local voxel grid too large (awareness range / voxel size)";
+    return MLM_ERR_INVALID_CONFIG;
+  }
+  P.max_points = cfg->max_points;
+  P.contrib_per_point = 1 + 2 * maxK;
+  P.max_hits = (int)std::min<long long>(n_cells, (long long)P.max_points * P.contrib_per_point);
+  P.max_touched = (int)std::min<long long>(2 * lvg_cells, 2 * n_cells);
+  P.pool_blocks = cfg->pool_submaps;
+  uint32_t ht_cap = 1;
+  while (ht_cap < 2u * (uint32_t)P.pool_blocks) ht_cap <<= 1;
+  P.ht_mask = ht_cap - 1;
+
+  // column kernel shared memory: two column bitmaps + the largest power-of-two sort buffer that fits
+  int max_optin = 0;
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  const size_t bm_bytes = (((size_t)2 * P.col_words * 4 + 15) & ~(size_t)15);
+  long long avail = (long long)max_optin - 2048 - (long long)bm_bytes;
+  if (avail < 8 * 1024) {
+    delete h;
+    g_last_error = "awareness column (n_Z*n_Rho bits) does not fit shared memory";
+    return MLM_ERR_INVALID_CONFIG;
+  }
+  int cap = 1024;
+  while ((long long)cap * 2 * 8 <= avail && cap < (1 << 16)) cap <<= 1;
+  P.sort_cap_smem = cap;
+  h->col_smem_bytes = (int)(bm_bytes + (size_t)cap * 8);
+
+#define TRY(x)            \
+  do {                    \
+    rc = (x);             \
+    if (rc != MLM_OK) {   \
+      mlm_destroy(h);     \
+      return rc;          \
+    }                     \
+  } while (0)
+#define CUDA_TRY_H(expr)                                                   \
+  do {                                                                     \
+    cudaError_t _e = (expr);                                               \
+    if (_e != cudaSuccess) {                                               \
+      g_last_error = std::string(#expr) + ": " + cudaGetErrorString(_e);   \
+      mlm_destroy(h);                                                      \
+      return MLM_ERR_CUDA;                                                 \
+    }                                                                      \
+  } while (0)
+
+  CUDA_TRY_H(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_TRY_H(cudaEventCreate(&h->ev0));
+  CUDA_TRY_H(cudaEventCreate(&h->ev1));
+  CUDA_TRY_H(cudaMallocHost((void **)&h->h_fp, sizeof(FrameParams)));
+  CUDA_TRY_H(cudaMallocHost((void **)&h->h_fc, sizeof(FrameCounters)));
+  CUDA_TRY_H(cudaMallocHost((void **)&h->h_cum, 3 * sizeof(int64_t)));
+  CUDA_TRY_H(cudaFuncSetAttribute(k_column, cudaFuncAttributeMaxDynamicSharedMemorySize, h->col_smem_bytes));
+
+  DeviceBuffers &D = h->D;
+  memset(&D, 0, sizeof(D));
+  float *d_odds;
+  int *d_k;
+  double2 *d_cxy;
+  double *d_cz;
+  TRY(dev_alloc(h, &d_odds, T.odds.size()));
+  TRY(dev_alloc(h, &d_k, T.k_reach.size()));
+  TRY(dev_alloc(h, &d_cxy, T.centre_xy.size()));
+  TRY(dev_alloc(h, &d_cz, T.centre_z.size()));
+  CUDA_TRY_H(cudaMemcpy(d_odds, T.odds.data(), T.odds.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_TRY_H(cudaMemcpy(d_k, T.k_reach.data(), T.k_reach.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY_H(cudaMemcpy(d_cxy, T.centre_xy.data(), T.centre_xy.size() * sizeof(double2), cudaMemcpyHostToDevice));
+  CUDA_TRY_H(cudaMemcpy(d_cz, T.centre_z.data(), T.centre_z.size() * sizeof(double), cudaMemcpyHostToDevice));
+  P.odds_table = d_odds;
+  P.k_reach = d_k;
+  P.centre_xy = d_cxy;
+  P.centre_z = d_cz;
+
+  TRY(dev_alloc(h, &D.fp, 1));
+  TRY(dev_alloc(h, &D.fc, 1));
+  TRY(dev_alloc(h, &D.rec_lin, (size_t)P.max_points));
+  TRY(dev_alloc(h, &D.rec_col, (size_t)P.max_points));
+  TRY(dev_alloc(h, &D.phi_hist, (size_t)P.nPhi));
+  TRY(dev_alloc(h, &D.phi_off, (size_t)P.nPhi + 1));
+  TRY(dev_alloc(h, &D.phi_cursor, (size_t)P.nPhi));
+  TRY(dev_alloc(h, &D.col_scratch, (size_t)2 * P.max_points * P.contrib_per_point));
+  TRY(dev_alloc(h, &D.hit_key, (size_t)P.max_hits));
+  TRY(dev_alloc(h, &D.hit_p, (size_t)P.max_hits));
+  TRY(dev_alloc(h, &D.hit_t, (size_t)P.max_hits));
+  TRY(dev_alloc(h, &D.hit_next, (size_t)P.max_hits));
+  TRY(dev_alloc(h, &D.miss_bitmap, (size_t)P.nPhi * P.col_words));
+  h->act_cap = chain_cover((uint32_t)P.max_hits);
+  if (h->act_cap == 0) {
+    g_last_error = "max hit cells exceed the bucket chain table";
+    mlm_destroy(h);
+    return MLM_ERR_INVALID_CONFIG;
+  }
+  TRY(dev_alloc(h, &D.act, (size_t)h->act_cap));
+  TRY(dev_alloc(h, &D.lvg_head, (size_t)lvg_cells));
+  TRY(dev_alloc(h, &D.lvg_miss, (size_t)lvg_cells));
+  TRY(dev_alloc(h, &D.touched, (size_t)P.max_touched));
+  TRY(dev_alloc(h, &D.lsg_flag, (size_t)lsg_cells));
+  TRY(dev_alloc(h, &D.lsg_block, (size_t)lsg_cells));
+  TRY(dev_alloc(h, &D.touched_sub, (size_t)lsg_cells));
+  TRY(dev_alloc(h, &D.ht_key, (size_t)ht_cap));
+  TRY(dev_alloc(h, &D.ht_val, (size_t)ht_cap));
+  TRY(dev_alloc(h, &D.free_stack, (size_t)P.pool_blocks));
+  TRY(dev_alloc(h, &D.free_top, 1));
+  TRY(dev_alloc(h, &D.pool_lo, (size_t)P.pool_blocks * P.cell_stride));
+  TRY(dev_alloc(h, &D.pool_occ, (size_t)P.pool_blocks * P.cell_stride));
+  TRY(dev_alloc(h, &D.pool_inf, (size_t)P.pool_blocks * P.cell_stride));
+  TRY(dev_alloc(h, &D.cum, 4));
+  TRY(dev_alloc(h, &h->d_ticket, 1));
+  h->sort_cap = P.max_hits;
+  const size_t sort_pad = (size_t)next_pow2(P.max_hits);
+  TRY(dev_alloc(h, &h->d_sort_a, sort_pad));
+  TRY(dev_alloc(h, &h->d_sort_b, sort_pad));
+  TRY(dev_alloc(h, &h->d_seq_a, (size_t)P.max_hits));
+  TRY(dev_alloc(h, &h->d_seq_b, (size_t)P.max_hits));
+
+  // initial state
+  CUDA_TRY_H(cudaMemset(D.lvg_head, 0xff, (size_t)lvg_cells * 4));
+  CUDA_TRY_H(cudaMemset(D.lvg_miss, 0, (size_t)lvg_cells * 4));
+  CUDA_TRY_H(cudaMemset(D.lsg_flag, 0, (size_t)lsg_cells * 4));
+  CUDA_TRY_H(cudaMemset(D.lsg_block, 0xff, (size_t)lsg_cells * 4));
+  CUDA_TRY_H(cudaMemset(D.ht_key, 0xff, (size_t)ht_cap * 8));
+  CUDA_TRY_H(cudaMemset(D.ht_val, 0xff, (size_t)ht_cap * 4));
+  CUDA_TRY_H(cudaMemset(D.cum, 0, 4 * sizeof(int64_t)));
+  CUDA_TRY_H(cudaMemset(h->d_ticket, 0, sizeof(int)));
+  CUDA_TRY_H(cudaMemset(D.fc, 0, sizeof(FrameCounters)));
+  CUDA_TRY_H(cudaMemset(D.miss_bitmap, 0, (size_t)P.nPhi * P.col_words * 4));
+  {
+    std::vector<int> stack(P.pool_blocks);
+    for (int i = 0; i < P.pool_blocks; i++) stack[i] = P.pool_blocks - 1 - i;  // block 0 popped first
+    CUDA_TRY_H(cudaMemcpy(D.free_stack, stack.data(), stack.size() * sizeof(int), cudaMemcpyHostToDevice));
+    int top = P.pool_blocks;
+    CUDA_TRY_H(cudaMemcpy(D.free_top, &top, sizeof(int), cudaMemcpyHostToDevice));
+  }
+  CUDA_TRY_H(cudaDeviceSynchronize());
+#undef TRY
+#undef CUDA_TRY_H
+  *out = h;
+  return MLM_OK;
+}
+
+int mlm_destroy(mlm_handle h) {
+  if (!h) return MLM_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void *p : h->allocs) cudaFree(p);
+  if (h->d_input) cudaFree(h->d_input);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  if (h->l2_buf) cudaFree(h->l2_buf);
+  if (h->h_fp) cudaFreeHost(h->h_fp);
+  if (h->h_fc) cudaFreeHost(h->h_fc);
+  if (h->h_cum) cudaFreeHost(h->h_cum);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return MLM_OK;
+}
+
+int mlm_integrate_depth_u16(mlm_handle h, const uint16_t *img, int rows, int cols, size_t stride_bytes,
+                            const double T_wb[7], mlm_frame_stats *stats) {
+  if (!h || !img || !T_wb || rows <= 0 || cols <= 0 || stride_bytes < (size_t)cols * 2) return MLM_ERR_INVALID_ARG;
+  if ((long long)rows * cols > h->P.max_points) {
+    g_last_error = "image larger than cfg.max_points";
+    return MLM_ERR_CAPACITY;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t bytes = (size_t)rows * cols * 2;
+  int rc = ensure_input(h, bytes);
+  if (rc != MLM_OK) return rc;
+  // pack rows into the pinned staging buffer (dense), then one async H2D copy
+  if (stride_bytes == (size_t)cols * 2) {
+    memcpy(h->h_stage, img, bytes);
+  } else {
+    for (int v = 0; v < rows; v++)
+      memcpy((char *)h->h_stage + (size_t)v * cols * 2, (const char *)img + (size_t)v * stride_bytes, (size_t)cols * 2);
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->d_input, h->h_stage, bytes, cudaMemcpyHostToDevice, h->stream));
+  return run_frame(h, true, h->d_input, rows, cols, 0, T_wb, stats);
+}
+
+int mlm_integrate_depth_u16_device(mlm_handle h, const uint16_t *d_img, int rows, int cols, const double T_wb[7],
+                                   mlm_frame_stats *stats) {
+  if (!h || !d_img || !T_wb || rows <= 0 || cols <= 0) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
+  return run_frame(h, true, d_img, rows, cols, 0, T_wb, stats);
+}
+
+int mlm_integrate_points_f64(mlm_handle h, const double *xyz, int n, const double T_wb[7], mlm_frame_stats *stats) {
+  if (!h || (!xyz && n > 0) || !T_wb || n < 0) return MLM_ERR_INVALID_ARG;
+  if (n > h->P.max_points) {
+    g_last_error = "more points than cfg.max_points";
+    return MLM_ERR_CAPACITY;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t bytes = (size_t)std::max(n, 1) * 24;
+  int rc = ensure_input(h, bytes);
+  if (rc != MLM_OK) return rc;
+  if (n > 0) {
+    memcpy(h->h_stage, xyz, (size_t)n * 24);
+    CUDA_TRY(cudaMemcpyAsync(h->d_input, h->h_stage, (size_t)n * 24, cudaMemcpyHostToDevice, h->stream));
+  }
+  return run_frame(h, false, h->d_input, 0, 0, n, T_wb, stats);
+}
+
+int mlm_integrate_points_f64_device(mlm_handle h, const double *d_xyz, int n, const double T_wb[7],
+                                    mlm_frame_stats *stats) {
+  if (!h || (!d_xyz && n > 0) || !T_wb || n < 0) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
+  return run_frame(h, false, d_xyz, 0, 0, n, T_wb, stats);
+}
+
+int mlm_set_free_in_bound(mlm_handle h, const double box_min[3], const double box_max[3]) {
+  if (!h || !box_min || !box_max) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
+  // coordinates by repeated "+=" in double, like the reference loops (src/mlmap.cpp:392-396)
+  std::vector<double> ax[3];
+  for (int a = 0; a < 3; a++) {
+    for (double v = box_min[a]; v <= box_max[a]; v += h->P.d_sub) {
+      ax[a].push_back(v);
+      if (ax[a].size() > (size_t)1 << 24) return MLM_ERR_INVALID_ARG;
+    }
+    if (ax[a].empty()) return MLM_OK;
+  }
+  size_t total = ax[0].size() * ax[1].size() * ax[2].size();
+  size_t ncoord = ax[0].size() + ax[1].size() + ax[2].size();
+  double *d_c = nullptr;
+  CUDA_TRY(cudaMallocAsync((void **)&d_c, ncoord * sizeof(double), h->stream));
+  std::vector<double> flat;
+  flat.reserve(ncoord);
+  for (int a = 0; a < 3; a++) flat.insert(flat.end(), ax[a].begin(), ax[a].end());
+  CUDA_TRY(cudaMemcpyAsync(d_c, flat.data(), ncoord * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  k_set_free<<<grid_for(total, 256), 256, 0, h->stream>>>(h->P, h->D, d_c, (int)ax[0].size(), d_c + ax[0].size(),
+                                                           (int)ax[1].size(), d_c + ax[0].size() + ax[1].size(),
+                                                           (int)ax[2].size());
+  h->launches++;
+  CUDA_TRY(cudaFreeAsync(d_c, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));  // flat must outlive the copy
+  CUDA_TRY(cudaGetLastError());
+  return MLM_OK;
+}
+
+int mlm_inflate_map(mlm_handle h, const double ct_pos[3]) {
+  (void)ct_pos;
+  if (!h) return MLM_ERR_INVALID_ARG;
+  g_last_error = "inflate_map is a SURVEY §8(f) 'next' row and not implemented yet";
+  return MLM_ERR_UNSUPPORTED;
+}
+
+// ---- queries ------------------------------------------------------------------------------------------
+
+int mlm_get_occupancy(mlm_handle h, const double *pos, size_t n, int32_t *out) {
+  return host_query<int32_t>(h, pos, n, out, 1, [&](double *dp, int32_t *dout) {
+    k_get_occupancy<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->D, dp, n, dout);
+  });
+}
+int mlm_get_occupancy_inflate(mlm_handle h, const double *pos, size_t n, float inflate, int32_t *out) {
+  return host_query<int32_t>(h, pos, n, out, 1, [&](double *dp, int32_t *dout) {
+    k_get_occupancy_inflate<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->D, dp, n, inflate, dout);
+  });
+}
+int mlm_get_inflate_occupancy(mlm_handle h, const double *pos, size_t n, int32_t *out) {
+  return host_query<int32_t>(h, pos, n, out, 1, [&](double *dp, int32_t *dout) {
+    k_get_inflate_occupancy<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->D, dp, n, dout);
+  });
+}
+int mlm_get_odd(mlm_handle h, const double *pos, size_t n, float *out) {
+  return host_query<float>(h, pos, n, out, 1, [&](double *dp, float *dout) {
+    k_get_odd<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->D, dp, n, dout);
+  });
+}
+int mlm_get_odd_grad(mlm_handle h, const double *pos, size_t n, size_t max_iter, double *out3n) {
+  return host_query<double>(h, pos, n, out3n, 3, [&](double *dp, double *dout) {
+    k_get_odd_grad<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->D, dp, n, (int)max_iter, dout);
+  });
+}
+int mlm_get_occupancy_device(mlm_handle h, const double *d_pos, size_t n, int32_t *d_out) {
+  if (!h || (!d_pos && n) || (!d_out && n)) return MLM_ERR_INVALID_ARG;
+  if (n == 0) return MLM_OK;
+  k_get_occupancy<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->D, d_pos, n, d_out);
+  h->launches++;
+  return MLM_OK;
+}
+int mlm_get_odd_device(mlm_handle h, const double *d_pos, size_t n, float *d_out) {
+  if (!h || (!d_pos && n) || (!d_out && n)) return MLM_ERR_INVALID_ARG;
+  if (n == 0) return MLM_OK;
+  k_get_odd<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->D, d_pos, n, d_out);
+  h->launches++;
+  return MLM_OK;
+}
+int mlm_get_odd_grad_device(mlm_handle h, const double *d_pos, size_t n, size_t max_iter, double *d_out3n) {
+  if (!h || (!d_pos && n) || (!d_out3n && n)) return MLM_ERR_INVALID_ARG;
+  if (n == 0) return MLM_OK;
+  k_get_odd_grad<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->D, d_pos, n, (int)max_iter, d_out3n);
+  h->launches++;
+  return MLM_OK;
+}
+
+// ---- stream control ----------------------------------------------------------------------------------
+int mlm_sync(mlm_handle h) {
+  if (!h) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaGetLastError());
+  return MLM_OK;
+}
+int mlm_timer_start(mlm_handle h) {
+  if (!h) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  return MLM_OK;
+}
+int mlm_timer_stop_ms(mlm_handle h, float *ms) {
+  if (!h || !ms) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  CUDA_TRY(cudaEventSynchronize(h->ev1));
+  CUDA_TRY(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return MLM_OK;
+}
+int mlm_device_alloc(mlm_handle h, size_t bytes, void **d_ptr) {
+  if (!h || !d_ptr) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMalloc(d_ptr, bytes));
+  return MLM_OK;
+}
+int mlm_device_free(mlm_handle h, void *d_ptr) {
+  if (!h) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaFree(d_ptr));
+  return MLM_OK;
+}
+int mlm_copy_to_device(mlm_handle h, void *d_dst, const void *src, size_t bytes) {
+  if (!h || !d_dst || !src) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return MLM_OK;
+}
+int mlm_copy_to_host(mlm_handle h, void *dst, const void *d_src, size_t bytes) {
+  if (!h || !dst || !d_src) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return MLM_OK;
+}
+int mlm_flush_l2(mlm_handle h) {
+  if (!h) return MLM_ERR_INVALID_ARG;
+  if (!h->l2_buf) {
+    h->l2_bytes = (size_t)256 << 20;  // > 126 MB L2
+    CUDA_TRY(cudaMalloc(&h->l2_buf, h->l2_bytes));
+  }
+  static uint32_t v = 1;
+  k_l2_flush<<<h->sm_count * 8, 256, 0, h->stream>>>((uint4 *)h->l2_buf, h->l2_bytes / 16, v++);
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return MLM_OK;
+}
+int mlm_kernel_launch_count(mlm_handle h, int64_t *count) {
+  if (!h || !count) return MLM_ERR_INVALID_ARG;
+  *count = h->launches;
+  return MLM_OK;
+}
+
+// ---- parity / debug exports --------------------------------------------------------------------------
+int mlm_last_frame_hits(mlm_handle h, int32_t *keys3, float *p, size_t cap, size_t *n_out) {
+  if (!h || !n_out) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int n = h->last_n_hit;
+  *n_out = (size_t)n;
+  if (n == 0 || cap < (size_t)n || !keys3 || !p) return MLM_OK;
+  cudaStream_t s = h->stream;
+  const int T = 256, n_pad = next_pow2(n);
+  k_order_seed<<<grid_for(n_pad, T), T, 0, s>>>(h->D, h->d_sort_a, n, n_pad);
+  device_sort(h, h->d_sort_a, n_pad);
+  k_export_hit_keys<<<grid_for(n_pad, T), T, 0, s>>>(h->P, h->D, h->d_sort_b, n, n_pad, h->last_order_B);
+  device_sort(h, h->d_sort_b, n_pad);
+  int *d_k3 = nullptr;
+  float *d_p = nullptr;
+  CUDA_TRY(cudaMallocAsync((void **)&d_k3, (size_t)n * 12, s));
+  CUDA_TRY(cudaMallocAsync((void **)&d_p, (size_t)n * 4, s));
+  k_export_hit_gather<<<grid_for(n, T), T, 0, s>>>(h->P, h->D, h->d_sort_a, h->d_sort_b, n, d_k3, d_p);
+  h->launches += 3;
+  CUDA_TRY(cudaMemcpyAsync(keys3, d_k3, (size_t)n * 12, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(p, d_p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaFreeAsync(d_k3, s));
+  CUDA_TRY(cudaFreeAsync(d_p, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  return MLM_OK;
+}
+
+int mlm_last_frame_misses(mlm_handle h, uint64_t *idx, size_t cap, size_t *n_out) {
+  if (!h || !n_out) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  int *d_cnt = nullptr;
+  unsigned long long *d_out = nullptr;
+  const size_t words = (size_t)h->P.nPhi * h->P.col_words;
+  CUDA_TRY(cudaMallocAsync((void **)&d_cnt, sizeof(int), s));
+  CUDA_TRY(cudaMallocAsync((void **)&d_out, std::max<size_t>(cap, 1) * 8, s));
+  CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(int), s));
+  k_export_miss<<<grid_for(words, 256), 256, 0, s>>>(h->P, h->D, d_out, d_cnt, (int)std::min<size_t>(cap, 0x7fffffff));
+  h->launches++;
+  int cnt = 0;
+  CUDA_TRY(cudaMemcpyAsync(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  *n_out = (size_t)cnt;
+  if (idx && cap >= (size_t)cnt && cnt > 0) {
+    CUDA_TRY(cudaMemcpyAsync(idx, d_out, (size_t)cnt * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    std::sort(idx, idx + cnt);  // export formatting only: ascending cell index
+  }
+  CUDA_TRY(cudaFreeAsync(d_cnt, s));
+  CUDA_TRY(cudaFreeAsync(d_out, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  return MLM_OK;
+}
+
+int mlm_export_map_count(mlm_handle h, size_t *n_submaps) {
+  if (!h || !n_submaps) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
+  int64_t cum[3];
+  CUDA_TRY(cudaMemcpyAsync(cum, h->D.cum, sizeof(cum), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  *n_submaps = (size_t)cum[2];
+  return MLM_OK;
+}
+
+int mlm_export_map(mlm_handle h, size_t cap_submaps, int32_t *glb3, uint8_t *collapsed, char *occupancy,
+                   char *inflate_occupancy, float *log_odds, size_t *n_out) {
+  if (!h || !n_out || !glb3 || !collapsed || !occupancy || !inflate_occupancy || !log_odds) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const MapParams &P = h->P;
+  int *d_cnt = nullptr, *d_glb = nullptr, *d_blk = nullptr;
+  const size_t cap = std::max<size_t>(cap_submaps, 1);
+  CUDA_TRY(cudaMallocAsync((void **)&d_cnt, sizeof(int), s));
+  CUDA_TRY(cudaMallocAsync((void **)&d_glb, cap * 12, s));
+  CUDA_TRY(cudaMallocAsync((void **)&d_blk, cap * 4, s));
+  CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(int), s));
+  k_export_list<<<grid_for((size_t)P.ht_mask + 1, 256), 256, 0, s>>>(P, h->D, d_glb, d_blk, d_cnt, (int)cap_submaps);
+  int cnt = 0;
+  CUDA_TRY(cudaMemcpyAsync(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  *n_out = (size_t)cnt;
+  if (cnt > 0 && (size_t)cnt <= cap_submaps) {
+    char *d_occ = nullptr, *d_inf = nullptr;
+    float *d_lo = nullptr;
+    const size_t cells = (size_t)cnt * P.cells;
+    CUDA_TRY(cudaMallocAsync((void **)&d_occ, cells, s));
+    CUDA_TRY(cudaMallocAsync((void **)&d_inf, cells, s));
+    CUDA_TRY(cudaMallocAsync((void **)&d_lo, cells * 4, s));
+    k_export_blocks<<<cnt, 256, 0, s>>>(P, h->D, d_blk, cnt, d_occ, d_inf, d_lo);
+    CUDA_TRY(cudaMemcpyAsync(glb3, d_glb, (size_t)cnt * 12, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(occupancy, d_occ, cells, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(inflate_occupancy, d_inf, cells, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(log_odds, d_lo, cells * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaFreeAsync(d_occ, s));
+    CUDA_TRY(cudaFreeAsync(d_inf, s));
+    CUDA_TRY(cudaFreeAsync(d_lo, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    memset(collapsed, 0, (size_t)cnt);
+    h->launches += 2;
+  }
+  CUDA_TRY(cudaFreeAsync(d_cnt, s));
+  CUDA_TRY(cudaFreeAsync(d_glb, s));
+  CUDA_TRY(cudaFreeAsync(d_blk, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  return MLM_OK;
+}
+
+int mlm_debug_log10f(mlm_handle h, const float *x, size_t n, float *out) {
+  if (!h || (!x && n) || (!out && n)) return MLM_ERR_INVALID_ARG;
+  if (n == 0) return MLM_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  float *d_x = nullptr, *d_o = nullptr;
+  CUDA_TRY(cudaMallocAsync((void **)&d_x, n * 4, h->stream));
+  CUDA_TRY(cudaMallocAsync((void **)&d_o, n * 4, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_x, x, n * 4, cudaMemcpyHostToDevice, h->stream));
+  k_debug_log10f<<<grid_for(n, 256), 256, 0, h->stream>>>(d_x, n, d_o, h->P.log10f_fma);
+  h->launches++;
+  CUDA_TRY(cudaMemcpyAsync(out, d_o, n * 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaFreeAsync(d_x, h->stream));
+  CUDA_TRY(cudaFreeAsync(d_o, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaGetLastError());
+  return MLM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,210 @@
+// Batched point queries, box fill, inflation and map export kernels.  Replaces the reference's
+//   mlmap::getOccupancy / getOdd / getOddGrad / getInflateOccupancy   include/mlmap.h:142-295
+//   mlmap::setFree_map_in_bound                                        src/mlmap.cpp:388-407
+// One thread per query; the subbox hash table and pool blocks are read-only here.
+#pragma once
+#include "frame_kernels.cuh"
+
+namespace mlm {
+
+// logit_inv, include/mlmap.h:40: pow(10, x) / (1 + pow(10, x)) in double, returned as float
+__device__ __forceinline__ float logit_inv_f(float lo) {
+  double y = pow(10.0, (double)lo);
+  return (float)(y / (1 + y));
+}
+
+// getOdd(glb, sub), include/mlmap.h:227-235
+__device__ __forceinline__ float odd_at(const MapParams &P, const DeviceBuffers &D, const int g[3], int sub) {
+  int block = ht_find(P, D, g);
+  if (block < 0) return 0.5f;
+  return logit_inv_f(D.pool_lo[(size_t)block * P.cell_stride + sub]);
+}
+
+__device__ __forceinline__ int occupancy_at(const MapParams &P, const DeviceBuffers &D, double x, double y,
+                                            double z) {  // include/mlmap.h:170-193
+  CellRef c = locate_cell(P, x, y, z);
+  int block = ht_find(P, D, c.g);
+  if (block < 0) return -1;
+  char res = D.pool_occ[(size_t)block * P.cell_stride + c.sub];
+  return res == 'o' ? 0 : (res == 'f' ? 1 : -1);
+}
+
+__global__ void __launch_bounds__(256) k_get_occupancy(MapParams P, DeviceBuffers D, const double *pos, size_t n,
+                                                       int *out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = occupancy_at(P, D, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+}
+
+// getOccupancy(pos, inflate): 19-point stencil, include/mlmap.h:142-169 (short-circuit order kept
+// only as far as the result is concerned: any OCCUPIED probe -> OCCUPIED)
+__global__ void __launch_bounds__(256) k_get_occupancy_inflate(MapParams P, DeviceBuffers D, const double *pos,
+                                                               size_t n, float inflate, int *out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
+  const double f = (double)inflate, m = (double)(-inflate);
+  const double off[19][3] = {{0, 0, 0}, {0, 0, f}, {0, 0, m}, {0, f, 0}, {0, m, 0}, {f, 0, 0}, {m, 0, 0},
+                             {m, f, 0}, {m, m, 0}, {f, f, 0}, {f, m, 0}, {0, m, f}, {0, m, m}, {0, f, f},
+                             {0, f, m}, {m, 0, f}, {m, 0, m}, {f, 0, f}, {f, 0, m}};
+  int res = 1;
+  for (int k = 0; k < 19; k++) {
+    if (occupancy_at(P, D, x + off[k][0], y + off[k][1], z + off[k][2]) == 0) {
+      res = 0;
+      break;
+    }
+  }
+  out[i] = res;
+}
+
+__global__ void __launch_bounds__(256) k_get_inflate_occupancy(MapParams P, DeviceBuffers D, const double *pos,
+                                                               size_t n, int *out) {  // mlmap.h:195-211
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  CellRef c = locate_cell(P, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+  int block = ht_find(P, D, c.g);
+  int r = -1;
+  if (block >= 0 && D.pool_inf[(size_t)block * P.cell_stride + c.sub] == 'o') r = 0;
+  out[i] = r;
+}
+
+__global__ void __launch_bounds__(256) k_get_odd(MapParams P, DeviceBuffers D, const double *pos, size_t n,
+                                                 float *out) {  // mlmap.h:213-225
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  CellRef c = locate_cell(P, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+  out[i] = odd_at(P, D, c.g, c.sub);
+}
+
+// subbox_neighbors row i of cell sub (src/map_local.cpp:78-120): order +z,-z,+y,-y,+x,-x
+__device__ __forceinline__ void neighbor_step(const MapParams &P, int dir, int g[3], int &sub) {
+  int x = sub % P.n, y = (sub / P.n) % P.n, z = sub / (P.n * P.n);
+  int c[3] = {x, y, z};
+  const int axis = 2 - (dir >> 1);
+  c[axis] += (dir & 1) ? -1 : 1;
+  if (c[axis] >= P.n) {
+    g[axis] += 1;
+    c[axis] = 0;
+  } else if (c[axis] < 0) {
+    g[axis] -= 1;
+    c[axis] = P.n - 1;
+  }
+  sub = (c[2] * P.n + c[1]) * P.n + c[0];
+}
+
+__global__ void __launch_bounds__(256) k_get_odd_grad(MapParams P, DeviceBuffers D, const double *pos, size_t n,
+                                                      int max_iter, double *out) {  // mlmap.h:237-295
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double px = pos[3 * i], py = pos[3 * i + 1], pz = pos[3 * i + 2];
+  CellRef c = locate_cell(P, px, py, pz);
+  float min_odd = odd_at(P, D, c.g, c.sub);
+  const float ori_odd = min_odd;
+  int nb_g[6][3], nb_sub[6];
+  int best_g[3] = {0, 0, 0}, best_sub = 0;
+  bool flag = false;
+  for (int iter = 0; iter < max_iter && !flag; iter++) {
+    for (int d = 0; d < 6; d++) {
+      if (iter == 0) {
+        nb_g[d][0] = c.g[0];
+        nb_g[d][1] = c.g[1];
+        nb_g[d][2] = c.g[2];
+        nb_sub[d] = c.sub;
+      }
+      neighbor_step(P, d, nb_g[d], nb_sub[d]);  // keep searching along the original direction
+      float tmp = odd_at(P, D, nb_g[d], nb_sub[d]);
+      if (tmp < min_odd) {
+        min_odd = tmp;
+        best_g[0] = nb_g[d][0];
+        best_g[1] = nb_g[d][1];
+        best_g[2] = nb_g[d][2];
+        best_sub = nb_sub[d];
+        flag = true;
+      }
+    }
+  }
+  double gx = 0.0, gy = 0.0, gz = 0.0;
+  if (flag) {
+    // subbox_id2xyz_glb_vec (map_local.h:208-213) - pos, times (double)(float)(ori - min)
+    int x = best_sub % P.n, y = (best_sub / P.n) % P.n, z = best_sub / (P.n * P.n);
+    double s = (double)__fsub_rn(ori_odd, min_odd);
+    gx = ((((double)best_g[0] * P.d_glb + (double)x * P.d_sub) + P.d_sub_half) - px) * s;
+    gy = ((((double)best_g[1] * P.d_glb + (double)y * P.d_sub) + P.d_sub_half) - py) * s;
+    gz = ((((double)best_g[2] * P.d_glb + (double)z * P.d_sub) + P.d_sub_half) - pz) * s;
+  }
+  out[3 * i] = gx;
+  out[3 * i + 1] = gy;
+  out[3 * i + 2] = gz;
+}
+
+// setFree_map_in_bound: the per-axis coordinate sequences are generated on the host by repeated
+// "+= d" exactly like the reference loops (src/mlmap.cpp:392-396); one thread per (x,y,z) triple.
+__global__ void __launch_bounds__(256) k_set_free(MapParams P, DeviceBuffers D, const double *xs, int nx,
+                                                  const double *ys, int ny, const double *zs, int nz) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)nx * ny * nz;
+  if (i >= total) return;
+  int iz = (int)(i % nz), iy = (int)((i / nz) % ny), ix = (int)(i / ((size_t)nz * ny));
+  CellRef c = locate_cell(P, xs[ix], ys[iy], zs[iz]);
+  int block = ht_find(P, D, c.g);
+  if (block < 0) return;
+  size_t addr = (size_t)block * P.cell_stride + c.sub;
+  D.pool_occ[addr] = 'f';
+  D.pool_lo[addr] = 0.f;
+}
+
+// ---- export -----------------------------------------------------------------------------------------
+__global__ void k_export_list(MapParams P, DeviceBuffers D, int *out_glb3, int *out_block, int *counter, int cap) {
+  uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot > P.ht_mask) return;
+  uint64_t k = D.ht_key[slot];
+  if (k == kEmptyKey) return;
+  int block = D.ht_val[slot];
+  if (block < 0) return;
+  int idx = atomicAdd(counter, 1);
+  if (idx >= cap) return;
+  int g[3];
+  unpack_glb(k, g);
+  out_glb3[3 * idx] = g[0];
+  out_glb3[3 * idx + 1] = g[1];
+  out_glb3[3 * idx + 2] = g[2];
+  out_block[idx] = block;
+}
+__global__ void k_export_blocks(MapParams P, DeviceBuffers D, const int *blocks, int n, char *occ, char *inf,
+                                float *lo) {
+  int b = blockIdx.x;
+  if (b >= n) return;
+  size_t src = (size_t)blocks[b] * P.cell_stride, dst = (size_t)b * P.cells;
+  for (int i = threadIdx.x; i < P.cells; i += blockDim.x) {
+    occ[dst + i] = D.pool_occ[src + i];
+    inf[dst + i] = D.pool_inf[src + i];
+    lo[dst + i] = D.pool_lo[src + i];
+  }
+}
+// miss set export: ascending awareness indices from the per-column bitmaps
+__global__ void k_export_miss(MapParams P, DeviceBuffers D, unsigned long long *out, int *counter, int cap) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= P.nPhi * P.col_words) return;
+  uint32_t bits = D.miss_bitmap[w];
+  int phi = w / P.col_words, wi = w - phi * P.col_words;
+  int z = wi / P.words_per_row, wr = wi - z * P.words_per_row;
+  while (bits) {
+    int b = __ffs(bits) - 1;
+    bits &= bits - 1;
+    int idx = atomicAdd(counter, 1);
+    if (idx < cap) out[idx] = (unsigned long long)((z * P.nPhi + phi) * P.nRho + (wr << 5) + b);
+  }
+}
+
+__global__ void k_debug_log10f(const float *x, size_t n, float *out, int use_fma) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = glibc_log10f_sel(x[i], use_fma);
+}
+
+__global__ void k_l2_flush(uint4 *buf, size_t n16, uint32_t v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n16; i += stride) buf[i] = make_uint4(v, v, v, v);
+}
+
+}  // namespace mlm

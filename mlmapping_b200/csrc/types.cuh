@@ -1,0 +1,129 @@
+// Device-visible state of one map handle.  Names follow the reference's domain:
+// awareness cells (rho,phi,z), subboxes/submaps, cells, log-odds, hit map / miss set.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mlm {
+
+constexpr int kDiffRange = 10;          // awareness_map_cylindrical::diff_range (map_awareness.cpp:36)
+constexpr int kOddsRows = 2 * kDiffRange + 1;
+constexpr int kMaxPhi = 4096;           // upper bound on nPhi for the shared-memory histogram
+constexpr uint64_t kEmptyKey = ~0ull;   // empty slot of the submap hash table
+constexpr int kBlockPending = -1;
+constexpr int kLvgEmpty = -1;
+constexpr int kLvgClaimed = -2;
+// device-raised error codes (mapped to MLM_ERR_* by the host)
+constexpr int kErrRange = 1, kErrPool = 4, kErrCapacity = 5, kErrInternal = 100;
+constexpr uint32_t kTouchedHitTag = 0x80000000u;
+
+// record of one castable point after projection (K1 output)
+struct __align__(16) RayRecord {
+  int rho;        // rho_idx as the reference computes it (may be >= nRho)
+  int z;          // z_idx (may be out of range)
+  uint32_t phi_flags;  // phi_idx | inside<<30
+  uint32_t t;     // point order stamp = index of the point in input_pc_pose's loop
+};
+constexpr uint32_t kRecInside = 1u << 30;
+constexpr uint32_t kRecPhiMask = (1u << 16) - 1;
+
+// constants of a handle (mlmap::init_map), immutable after mlm_create
+struct MapParams {
+  // awareness_map_cylindrical members (include/map_awareness.h:16-30,61-65)
+  double dRho, dPhi, dZ, z_border_min;
+  int nRho, nPhi, nZ, n_below;
+  int visibility_check;
+  int maxK;               // max over rho of the neighbour reach K(rho)
+  int words_per_row;      // ceil(nRho / 32): bitmap words per (phi,z) row
+  int col_words;          // nZ * words_per_row
+  // local_map_cartesian members (include/map_local.h:66-78)
+  double d_sub, d_glb, d_sub_half;
+  int n;                  // subbox_nxyz
+  int cells;              // cell_num_subbox
+  int cell_stride;        // cells rounded up to 16: per-block stride of the pool arrays
+  float lo_min, lo_max, lo_miss, lo_sh;
+  // camera (include/mlmap.h:85-86,92)
+  float cx, cy, fx, fy;
+  double inv_factor;
+  int log10f_fma;         // which glibc __logf variant the host CPU dispatches to
+  // local voxel grid (frame-local staging) geometry
+  int lvg_dim_xy, lvg_dim_z;   // cells per axis
+  int lvg_margin;              // cells between awareness bounding box and grid border
+  int lsg_dim_xy, lsg_dim_z;   // local submap grid dims
+  // capacities
+  int max_points;
+  int max_hits;           // capacity of the per-frame hit list
+  int max_touched;
+  int pool_blocks;
+  uint32_t ht_mask;       // hash table capacity - 1 (power of two)
+  int sort_cap_smem;      // 64-bit keys the column kernel can sort in shared memory
+  int contrib_per_point;  // 1 + 2*maxK
+  // tables (device pointers)
+  const float *odds_table;    // [21][nRho]   get_odds_table (map_awareness.cpp:36-46)
+  const int *k_reach;         // [nRho]       number of diff_r >= 1 with diff_r < 3*sigma_in_dr(rho)
+  const double2 *centre_xy;   // [nPhi*nRho]  cell centre x,y (map_awareness.cpp:58-61)
+  const double *centre_z;     // [nZ]
+};
+
+// values that change every frame; lives in device memory so a captured graph can be replayed
+struct FrameParams {
+  double q_ls[4];   // T_ls rotation (w,x,y,z)
+  double t_ls[3];   // T_ls translation
+  double t_wa[3];   // T_wa translation (= t_wb)
+  int rows, cols;
+  int n_points;     // point-cloud input
+  uint32_t bucket_count;  // emulated hit_idx_odds_hashmap.bucket_count() at frame start
+  int lvg_base[3];  // global cell coordinate of local voxel grid origin
+  int lsg_base[3];  // global subbox coordinate of local submap grid origin
+  int order_mode;   // 0: stamps are (bucket activation, first-insert time); 1: virtual sequence positions
+};
+
+// per-frame counters + error word, reset by k_frame_begin
+struct FrameCounters {
+  int n_points, n_inside, n_cast;
+  int n_hit, n_miss;
+  int n_touched, n_touched_sub, n_new_blocks;
+  int n_touched_voxels;   // distinct voxels actually fused
+  int error;              // MLM_ERR_* raised on device
+  int overflow;           // 1: n_hit > bucket_count -> fuse skipped, slow ordering path needed
+  int obs_delta;          // occupancy 'o' transitions this frame
+  int fused;              // set by k_fuse when it ran to completion
+  int pad[3];
+};
+
+struct DeviceBuffers {
+  FrameParams *fp;
+  FrameCounters *fc;
+  // K1/K1b
+  RayRecord *rec_lin;     // [max_points] in point order (phi_flags==~0u: no record)
+  RayRecord *rec_col;     // [max_points] grouped by phi column
+  int *phi_hist;          // [nPhi]
+  int *phi_off;           // [nPhi+1]
+  int *phi_cursor;        // [nPhi]
+  uint64_t *col_scratch;  // [max_points*contrib_per_point] sort spill for oversized columns
+  // per-frame hit map / miss set
+  int *hit_key;           // [max_hits] awareness linear index (mapIdx)
+  float *hit_p;           // [max_hits]
+  uint32_t *hit_t;        // [max_hits] first-insert stamp (t*32+substep) or virtual position
+  int *hit_next;          // [max_hits] next hit in the same voxel's list
+  uint32_t *miss_bitmap;  // [nPhi*col_words]
+  uint32_t *act;          // [bucket capacity] bucket activation stamps
+  // local voxel / submap grids
+  int *lvg_head;          // [lvg cells] head of hit list, -1 empty
+  int *lvg_miss;          // [lvg cells] number of miss cells this frame
+  uint32_t *touched;      // [max_touched] local voxel index (| kTouchedHitTag)
+  int *lsg_flag;          // [lsg cells]
+  int *lsg_block;         // [lsg cells] pool block of that subbox this frame
+  int *touched_sub;       // [lsg cells]
+  // submap pool + spatial hash
+  uint64_t *ht_key;       // [ht cap]
+  int *ht_val;            // [ht cap] pool block index
+  int *free_stack;        // [pool_blocks]
+  int *free_top;          // scalar: number of free blocks on the stack
+  float *pool_lo;         // [pool_blocks*cells]
+  char *pool_occ;         // [pool_blocks*cells]
+  char *pool_inf;         // [pool_blocks*cells]
+  int64_t *cum;           // [0]=ram_expand_cnt [1]=obs_cnt [2]=n_submaps
+};
+
+}  // namespace mlm

@@ -1,0 +1,160 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical seeded
+inputs.  Bar (BASELINE.json north_star): per-frame hit/miss cell sets, allocated subboxes and
+occupancy states bit-exact; log-odds within 1e-6 absolute (tolerance written here: LO_TOL)."""
+import numpy as np
+import pytest
+
+from mlmapping_b200 import MLMap, config_cfg_a, config_cfg_c, scenes
+from mlmapping_b200.capi import MlmError
+from oracle_binding import Oracle
+from parity_utils import assert_frame_parity, assert_map_parity
+
+pytestmark = pytest.mark.gpu
+LO_TOL = 1e-6
+
+
+def _small_cfg():
+    c = config_cfg_a()
+    return c
+
+
+def test_single_frame_cfg_a():
+    """BASELINE config 1: one 640x480 frame of the box corridor, body at (5,0,1.2), yaw 0"""
+    cfg = config_cfg_a()
+    pose = scenes.pose_from_xyz_yaw(5.0, 0.0, 1.2, 0.0)
+    img = scenes.corridor_depth_frame(cfg, pose)
+    gpu, orc = MLMap(cfg), Oracle(cfg)
+    st_g, st_o = gpu.integrate_depth(img, pose), orc.integrate_depth(img, pose)
+    assert st_g.ordering_slow_path == 1  # first frame of a fresh map always crosses libstdc++ rehashes
+    assert_frame_parity(gpu, orc, st_g, st_o, tag="frame0")
+    info = assert_map_parity(gpu, orc, LO_TOL)
+    assert info["subboxes"] > 0
+    # same frame again: steady-state (no rehash) ordering path, saturating updates
+    st_g, st_o = gpu.integrate_depth(img, pose), orc.integrate_depth(img, pose)
+    assert st_g.ordering_slow_path == 0
+    assert_frame_parity(gpu, orc, st_g, st_o, tag="frame0-again")
+    assert_map_parity(gpu, orc, LO_TOL)
+
+
+def test_trajectory_cfg_a():
+    """BASELINE config 2 (first 40 frames): streaming allocate as the body moves and yaws"""
+    cfg = config_cfg_a()
+    gpu, orc = MLMap(cfg), Oracle(cfg)
+    exact = []
+    for k in range(40):
+        pose = scenes.corridor_trajectory_pose(k * 5)  # stride 5 -> 0.25 m steps, new subboxes every few frames
+        img = scenes.corridor_depth_frame(cfg, pose, frame_idx=k)
+        st_g, st_o = gpu.integrate_depth(img, pose), orc.integrate_depth(img, pose)
+        assert_frame_parity(gpu, orc, st_g, st_o, tag=f"frame{k}")
+        if k % 10 == 9:
+            exact.append(assert_map_parity(gpu, orc, LO_TOL, tag=f"frame{k}"))
+    assert exact[-1]["subboxes"] > 100
+
+
+def test_strided_image_and_rotated_pose():
+    """row stride != cols*2 and a pose with roll/pitch (phi columns no longer follow image columns)"""
+    cfg = config_cfg_a()
+    pose = np.array([7.0, 0.2, 1.0, 0.9, 0.1, -0.15, 0.3])
+    img_full = np.zeros((480, 704), dtype=np.uint16)
+    img_full[:, :640] = scenes.corridor_depth_frame(cfg, pose, frame_idx=3)
+    view = img_full[:, :640]
+    gpu, orc = MLMap(cfg), Oracle(cfg)
+    st_g, st_o = gpu.integrate_depth(view, pose), orc.integrate_depth(np.ascontiguousarray(view), pose)
+    assert_frame_parity(gpu, orc, st_g, st_o)
+    assert_map_parity(gpu, orc, LO_TOL)
+
+
+def test_point_cloud_input_lidar_small():
+    """input_pc_pose on sensor-frame points (LiDAR-like), reduced CFG-C grid"""
+    cfg = config_cfg_c()
+    cfg.am_n_rho, cfg.am_n_z_below, cfg.am_n_z_over = 120, 30, 30
+    cfg.max_points = 32 * 512
+    cfg.pool_submaps = 8192
+    gpu, orc = MLMap(cfg), Oracle(cfg)
+    for k in range(3):
+        pose = scenes.lidar_loop_pose(k * 3)
+        pts = scenes.lidar_scan(pose, frame_idx=k, beams=32, azimuths=512)
+        st_g, st_o = gpu.integrate_points(pts, pose), orc.integrate_points(pts, pose)
+        assert_frame_parity(gpu, orc, st_g, st_o, tag=f"scan{k}")
+    assert_map_parity(gpu, orc, LO_TOL)
+
+
+def test_empty_and_degenerate_frames():
+    cfg = config_cfg_a()
+    gpu, orc = MLMap(cfg), Oracle(cfg)
+    pose = scenes.pose_from_xyz_yaw(5.0, 0.0, 1.2, 0.0)
+    zero = np.zeros((480, 640), dtype=np.uint16)
+    st_g, st_o = gpu.integrate_depth(zero, pose), orc.integrate_depth(zero, pose)
+    assert st_g.n_points == 0 and st_o.n_points == 0
+    assert_frame_parity(gpu, orc, st_g, st_o)
+    # a single valid pixel, then a ragged small image
+    one = zero.copy()
+    one[240, 320] = 2500
+    st_g, st_o = gpu.integrate_depth(one, pose), orc.integrate_depth(one, pose)
+    assert_frame_parity(gpu, orc, st_g, st_o)
+    small = scenes.corridor_depth_frame(cfg, pose, rows=37, cols=53)
+    st_g, st_o = gpu.integrate_depth(small, pose), orc.integrate_depth(small, pose)
+    assert_frame_parity(gpu, orc, st_g, st_o)
+    # maximum depth everywhere: every ray is outside the awareness range and is clamped
+    far = np.full((480, 640), 65535, dtype=np.uint16)
+    st_g, st_o = gpu.integrate_depth(far, pose), orc.integrate_depth(far, pose)
+    assert st_g.n_inside == 0
+    assert_frame_parity(gpu, orc, st_g, st_o)
+    assert_map_parity(gpu, orc, LO_TOL)
+    with pytest.raises(MlmError):
+        gpu.integrate_depth(np.zeros((481, 640), dtype=np.uint16), pose)  # exceeds cfg.max_points
+
+
+def test_queries_and_set_free():
+    cfg = config_cfg_a()
+    gpu, orc = MLMap(cfg), Oracle(cfg)
+    for k in range(6):
+        pose = scenes.corridor_trajectory_pose(k * 10)
+        img = scenes.corridor_depth_frame(cfg, pose, frame_idx=k)
+        gpu.integrate_depth(img, pose)
+        orc.integrate_depth(img, pose)
+    m = orc.export_map()
+    lo = m["glb"].min(0) * cfg.subbox_d_xyz * cfg.subbox_n
+    hi = (m["glb"].max(0) + 1) * cfg.subbox_d_xyz * cfg.subbox_n
+    pos = scenes.query_positions(200000, lo, hi, seed=5, inflate=2.0)
+    # cell-boundary and exact-lattice positions exercise the floor()/division quirks
+    lattice = np.round(pos[:20000] / cfg.subbox_d_xyz) * cfg.subbox_d_xyz
+    pos = np.concatenate([pos, lattice, -lattice[:100]])
+    assert np.array_equal(gpu.getOccupancy(pos), orc.getOccupancy(pos))
+    og, oo = gpu.getOdd(pos), orc.getOdd(pos)
+    assert np.abs(og.astype(np.float64) - oo.astype(np.float64)).max() <= 1.2e-7  # <= 1 float ulp of odds in [0.5,1]
+    gg, go = gpu.getOddGrad(pos[:100000]), orc.getOddGrad(pos[:100000])
+    assert np.abs(gg - go).max() <= 1e-6
+    assert np.array_equal(gpu.getOccupancy(pos[:50000], 0.15), orc.getOccupancy(pos[:50000], 0.15))
+    # setFree_map_in_bound, then everything again
+    bmin, bmax = [5.0, -0.5, 0.3], [8.0, 0.5, 2.0]
+    gpu.setFree_map_in_bound(bmin, bmax)
+    orc.setFree_map_in_bound(bmin, bmax)
+    assert_map_parity(gpu, orc, LO_TOL)
+    assert np.array_equal(gpu.getOccupancy(pos), orc.getOccupancy(pos))
+
+
+def test_log10f_matches_host_glibc():
+    """device log10f == this box's glibc log10f on every float in [2^-14, 2^27) (the logit() domain
+    p/(1-p), p in [0.001, 1)) plus a strided sweep of all positive floats"""
+    from oracle_binding import load_oracle
+    lib = load_oracle()
+    cfg = config_cfg_a()
+    gpu = MLMap(cfg)
+    lo_bits, hi_bits = np.float32(2.0 ** -14).view(np.uint32), np.float32(2.0 ** 27).view(np.uint32)
+    total_bad = 0
+    chunk = 1 << 24
+    for start in range(int(lo_bits), int(hi_bits), chunk):
+        bits = np.arange(start, min(start + chunk, int(hi_bits)), dtype=np.uint32)
+        x = bits.view(np.float32)
+        ref = np.empty_like(x)
+        lib.orc_log10f_array(x.ctypes.data, x.size, ref.ctypes.data)
+        got = gpu.debug_log10f(x)
+        total_bad += int((got.view(np.uint32) != ref.view(np.uint32)).sum())
+    assert total_bad == 0
+    bits = np.arange(1, 0x7F800000, 997, dtype=np.uint32)  # subnormals .. max finite
+    x = bits.view(np.float32)
+    ref = np.empty_like(x)
+    lib.orc_log10f_array(x.ctypes.data, x.size, ref.ctypes.data)
+    got = gpu.debug_log10f(x)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
