@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — rays integrated / second of the MLMapping per-frame map update on B200.
+
+Workload (BASELINE.json configs[1], SURVEY §8d CFG-A config 2): the synthetic corridor trajectory,
+640x480 uint16 depth @ 0.1 m voxels, streaming global-map submap allocation.  One "step" = one
+depth frame integrated end to end (projection + awareness ray cast + log-odds fusion).  With
+--gpus N each rank owns an independent agent map on its own trajectory (CFG-D style sharding:
+no data-path collective), so scaling is weak.
+
+  value  : valid rays / s over the K timed steps with the frames already resident in HBM
+           (CUDA events on the library's stream around each step, L2 flushed between steps)
+  e2e    : same metric through the host-buffer C-ABI call mlm_integrate_depth_u16
+           (pinned staging + H2D copy + kernels + D2H stats inside the timed region)
+  roofline / cpu_baseline : see DESIGN.md "Measurement"
+
+`--impl reference` times the CPU oracle (the reference's algorithm restated, single-threaded like
+the reference) on the same frames and prints the same JSON shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "rays_integrated_per_sec"
+UNIT = "rays/s"
+ROWS, COLS = 480, 640
+WORKLOAD = "cfg_a_corridor_trajectory_640x480_d0.1m_streaming_submaps"
+TRAJ_STRIDE = 1  # frame k of the 1000-frame trajectory
+
+
+def gen_frames(cfg, n, agent=0):
+    from mlmapping_b200 import scenes
+    frames, poses = [], []
+    for k in range(n):
+        kk = (k * TRAJ_STRIDE) % 1000
+        pose = scenes.corridor_trajectory_pose(kk, y_offset=20.0 * agent)
+        frames.append(scenes.corridor_depth_frame(cfg, pose, frame_idx=kk, seed_drop=1 + 10 * agent,
+                                                  seed_noise=2 + 10 * agent, y_offset=20.0 * agent))
+        poses.append(pose)
+    return frames, poses
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region"""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                smax.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(stats) -> int:
+    """B_frame = 2*W*H + 56 + 10*N_touch + 6000*N_new"""
+    return 2 * ROWS * COLS + 56 + 10 * stats.n_touched_voxels + 6000 * stats.n_new_submaps
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def run_cpu_sample(cfg, frames, poses, n_frames):
+    """oracle (port of the reference's algorithm) timed on the first n_frames of the workload, 1 core"""
+    from oracle_binding import Oracle
+    orc = Oracle(cfg, bookkeeping=False)
+    rays, secs = 0, 0.0
+    for k in range(n_frames):
+        st = orc.integrate_depth(frames[k], poses[k])
+        rays += st.n_points
+        secs += orc.last_seconds
+    orc.close()
+    return rays, secs
+
+
+def run_reference(args, rank, world):
+    from mlmapping_b200 import config_cfg_a
+    if rank != 0:
+        return
+    cfg = config_cfg_a()
+    total = args.steps + args.warmup
+    frames, poses = gen_frames(cfg, total)
+    from oracle_binding import Oracle
+    orc = Oracle(cfg, bookkeeping=False)
+    for k in range(args.warmup):
+        orc.integrate_depth(frames[k], poses[k])
+    rays, secs = 0, 0.0
+    for k in range(args.warmup, total):
+        st = orc.integrate_depth(frames[k], poses[k])
+        rays += st.n_points
+        secs += orc.last_seconds
+    value = rays / secs
+    sample = f"{args.steps} frames of {WORKLOAD} after {args.warmup} warm-up frames, single thread"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rows": ROWS, "cols": COLS, "timing": "steady_clock around project_depth+update_map"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-frames", type=int, default=60, help="frames of the workload timed on the CPU oracle")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the mlmap_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from mlmapping_b200 import MLMap, config_cfg_a
+    import ctypes as C
+    from mlmapping_b200.capi import FrameStats
+
+    cfg = config_cfg_a()
+    total = args.steps + args.warmup
+    frames, poses = gen_frames(cfg, total, agent=rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- pass 1: device-resident inputs ("value") ----------------
+    m = MLMap(cfg, device=local_rank)
+    d_frames = [m.to_device(f) for f in frames]
+    for k in range(args.warmup):
+        m.integrate_depth_device(d_frames[k], ROWS, COLS, poses[k])
+    sampler = ClockSampler(local_rank)
+    launches0 = m.kernel_launch_count()
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    dev_ms, rays, alg_bytes, slow_frames = 0.0, 0, 0, 0
+    for k in range(args.warmup, total):
+        m.flush_l2()
+        m.timer_start()
+        st = m.integrate_depth_device(d_frames[k], ROWS, COLS, poses[k])
+        dev_ms += m.timer_stop_ms()
+        rays += st.n_points
+        alg_bytes += algorithmic_bytes(st)
+        slow_frames += st.ordering_slow_path
+    barrier()
+    wall1 = time.perf_counter()
+    clocks = sampler.stop()
+    launches = m.kernel_launch_count() - launches0 - args.steps  # minus the L2-flush launches
+    submaps = m.export_map()["glb"].shape[0] if rank == 0 else 0
+
+    # ---------------- pass 2: per-kernel events on the same frames (roofline share) ----------------
+    m.close()
+    m = MLMap(cfg, device=local_rank)
+    m.set_profiling(True)
+    for k in range(args.warmup):
+        m.integrate_depth(frames[k], poses[k])
+    kern = {}
+    for k in range(args.warmup, total):
+        m.flush_l2()
+        m.integrate_depth(frames[k], poses[k])
+        for name, ms in m.last_frame_kernel_ms().items():
+            kern[name] = kern.get(name, 0.0) + ms
+    m.set_profiling(False)
+    m.close()
+
+    # ---------------- pass 3: end to end through the host-buffer C-ABI call ("e2e") ----------------
+    m = MLMap(cfg, device=local_rank)
+    for k in range(args.warmup):
+        m.integrate_depth(frames[k], poses[k])
+    barrier()
+    e2e_s, e2e_rays = 0.0, 0
+    for k in range(args.warmup, total):
+        m.flush_l2()
+        t0 = time.perf_counter()
+        st = m.integrate_depth(frames[k], poses[k])
+        e2e_s += time.perf_counter() - t0
+        e2e_rays += st.n_points
+    barrier()
+    m.close()
+
+    # ---------------- reduce over ranks: max time, sum of rays ----------------
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        r = torch.tensor([rays, e2e_rays, launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_s = float(t[0]), float(t[1])
+        rays, e2e_rays, launches = int(r[0]), int(r[1]), int(r[2])
+
+    if rank == 0:
+        value = rays / (dev_ms * 1e-3)
+        top = max(kern, key=kern.get)
+        top_ms = kern[top] / args.steps
+        peak, peak_src = measured_peak_gbs()
+        per_rank_bytes = alg_bytes / args.steps
+        achieved = per_rank_bytes / (top_ms * 1e-3) / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rows": ROWS, "cols": COLS, "voxel_m": 0.1, "frames_per_step": 1,
+                       "l2": "flushed between timed steps (256 MiB write)", "agents": world,
+                       "slow_ordering_frames": slow_frames, "submaps_allocated_rank0": submaps,
+                       "wall_s_timed_loop": wall1 - wall0},
+            "us_per_frame": 1e3 * dev_ms / args.steps,
+            "e2e": {"value": e2e_rays / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 2 * ROWS * COLS + 136,
+                    "d2h_bytes_per_step": 64 + 24, "us_per_frame": 1e6 * e2e_s / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": per_rank_bytes, "kernel_us": 1e3 * top_ms,
+                         "kernel_us_per_frame": {k: 1e3 * v / args.steps for k, v in kern.items()},
+                         "note": "latency/atomic-bound stage: ~1.8 MB of algorithmic traffic per frame (SURVEY 8d)"},
+        }
+        if not args.no_cpu:
+            nf = min(args.cpu_frames, total)
+            c_rays, c_s = run_cpu_sample(cfg, frames, poses, nf)
+            out["cpu_baseline"] = {"value": c_rays / c_s, "unit": UNIT, "cores": 1, "kind": "port",
+                                   "sample": f"first {nf} frames of {WORKLOAD} on the CPU oracle, single thread "
+                                             f"({os.cpu_count()} host cores present)",
+                                   "us_per_frame": 1e6 * c_s / nf}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

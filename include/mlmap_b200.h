@@ -172,6 +172,13 @@ int mlm_device_free(mlm_handle h, void *d_ptr);
 int mlm_copy_to_device(mlm_handle h, void *d_dst, const void *src, size_t bytes);
 int mlm_copy_to_host(mlm_handle h, void *dst, const void *d_src, size_t bytes);
 int mlm_flush_l2(mlm_handle h); /* writes a buffer larger than L2 (bench hygiene) */
+/* per-kernel timing of the frame pipeline (CUDA events between launches on the handle's stream).
+ * enable=1 records events in every following frame; mlm_last_frame_kernel_ms returns the durations
+ * of the MLM_NUM_FRAME_KERNELS stages of the last frame in launch order:
+ * 0 k_frame_begin, 1 k_project, 2 k_scatter, 3 k_column, 4 k_submaps, 5 k_fuse, 6 k_frame_end */
+#define MLM_NUM_FRAME_KERNELS 7
+int mlm_set_profiling(mlm_handle h, int enable);
+int mlm_last_frame_kernel_ms(mlm_handle h, float ms[MLM_NUM_FRAME_KERNELS]);
 /* number of kernels launched by this handle since creation */
 int mlm_kernel_launch_count(mlm_handle h, int64_t *count);
 

@@ -107,8 +107,9 @@ ABI_SYMBOLS = [
     "mlm_sync", "mlm_timer_start", "mlm_timer_stop_ms", "mlm_device_alloc", "mlm_device_free",
     "mlm_copy_to_device", "mlm_copy_to_host", "mlm_flush_l2", "mlm_kernel_launch_count",
     "mlm_last_frame_hits", "mlm_last_frame_misses", "mlm_export_map_count", "mlm_export_map",
-    "mlm_debug_log10f",
+    "mlm_debug_log10f", "mlm_set_profiling", "mlm_last_frame_kernel_ms",
 ]
+FRAME_KERNELS = ["k_frame_begin", "k_project", "k_scatter", "k_column", "k_submaps", "k_fuse", "k_frame_end"]
 
 _lib = None
 
@@ -173,6 +174,8 @@ def load_library() -> C.CDLL:
         "mlm_export_map_count": ([vp, C.POINTER(sz)], C.c_int),
         "mlm_export_map": ([vp, sz, vp, vp, vp, vp, vp, C.POINTER(sz)], C.c_int),
         "mlm_debug_log10f": ([vp, vp, sz, vp], C.c_int),
+        "mlm_set_profiling": ([vp, C.c_int], C.c_int),
+        "mlm_last_frame_kernel_ms": ([vp, fp], C.c_int),
     }
     for name, (args, ret) in sig.items():
         fn = getattr(lib, name)
@@ -391,6 +394,14 @@ class MLMap:
         out = np.empty(shape, dtype=dtype)
         self._check(self._lib.mlm_copy_to_host(self._h, out.ctypes.data, ptr, out.nbytes))
         return out
+
+    def set_profiling(self, enable: bool = True):
+        self._check(self._lib.mlm_set_profiling(self._h, 1 if enable else 0))
+
+    def last_frame_kernel_ms(self) -> dict:
+        ms = (C.c_float * len(FRAME_KERNELS))()
+        self._check(self._lib.mlm_last_frame_kernel_ms(self._h, ms))
+        return dict(zip(FRAME_KERNELS, [float(v) for v in ms]))
 
     def kernel_launch_count(self) -> int:
         v = C.c_int64()

@@ -259,9 +259,30 @@ __global__ void __launch_bounds__(256) k_project(MapParams P, DeviceBuffers D, c
       valid = 1;
     }
     if (valid) point_to_record(P, F, xs, ys, zs, (uint32_t)i, rec, inside, cast);
-    D.rec_lin[i] = rec;
   }
-  if (rec.phi_flags != 0xffffffffu) atomicAdd(&s_hist[rec.phi_flags & kRecPhiMask], 1);
+  // Run-length merge: consecutive points (in input order) that land in the same awareness cell
+  // contribute the same (key, odd) list back to back, so for every key their contributions are
+  // adjacent in the key's insertion sequence.  One record with a repeat count is therefore exact
+  // for the ordered fold, the first-insert stamps and the (idempotent) ray walk.  Runs are cut at
+  // warp boundaries and at points without a record.
+  {
+    const int lane = lane_id();
+    const bool has = rec.phi_flags != 0xffffffffu;
+    int p_rho = __shfl_up_sync(0xffffffffu, rec.rho, 1);
+    int p_z = __shfl_up_sync(0xffffffffu, rec.z, 1);
+    uint32_t p_pf = __shfl_up_sync(0xffffffffu, rec.phi_flags, 1);
+    const bool same = has && lane > 0 && p_pf == rec.phi_flags && p_rho == rec.rho && p_z == rec.z;
+    const unsigned sames = __ballot_sync(0xffffffffu, same);
+    if (has && !same) {
+      unsigned follow = lane < 31 ? (sames >> (lane + 1)) : 0u;
+      int m = 1 + (__ffs(~follow) - 1);  // consecutive followers that repeat this cell
+      rec.phi_flags |= (uint32_t)m << kRecCountShift;
+      atomicAdd(&s_hist[rec.phi_flags & kRecPhiMask], 1);
+    } else {
+      rec.phi_flags = 0xffffffffu;
+    }
+    if (i < N) D.rec_lin[i] = rec;
+  }
   // CTA-level counters
   unsigned bv = __ballot_sync(0xffffffffu, valid), bi = __ballot_sync(0xffffffffu, inside),
            bc = __ballot_sync(0xffffffffu, cast);
@@ -326,8 +347,10 @@ __global__ void __launch_bounds__(256) k_scatter(MapParams P, DeviceBuffers D, i
 constexpr int kColThreads = 512;
 constexpr int kCellBits = 20;
 
-__device__ __forceinline__ uint64_t contrib_key(int cell, uint32_t t, int substep) {
-  return ((uint64_t)(uint32_t)cell << 37) | ((uint64_t)t << 5) | (uint64_t)substep;
+// [63:44] cell in column, [43:12] point stamp t, [11:7] substep, [6:0] repeat count of the run
+constexpr int kKeyCellShift = 44;
+__device__ __forceinline__ uint64_t contrib_key(int cell, uint32_t t, int substep, int reps) {
+  return ((uint64_t)(uint32_t)cell << kKeyCellShift) | ((uint64_t)t << 12) | ((uint64_t)substep << 7) | (uint64_t)reps;
 }
 
 __device__ __forceinline__ void touch_subbox(const MapParams &P, const FrameParams &F, DeviceBuffers &D,
@@ -386,21 +409,33 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   uint64_t *s_keys = reinterpret_cast<uint64_t *>(s_raw + (((size_t)2 * P.col_words * 4 + 15) & ~(size_t)15));
   __shared__ int s_nk;
   __shared__ int s_nmiss;
+  __shared__ int s_bound;
   for (int i = tid; i < 2 * P.col_words; i += blockDim.x) s_miss[i] = 0;
   if (tid == 0) {
     s_nk = 0;
     s_nmiss = 0;
+    s_bound = 0;
   }
-  // sort buffer: shared memory when the column's worst case fits, else the global spill region
-  const long long worst = (long long)n_c * P.contrib_per_point;
-  uint64_t *keys = worst <= P.sort_cap_smem ? s_keys : D.col_scratch + (size_t)2 * off * P.contrib_per_point;
   __syncthreads();
-
+  // upper bound of this column's contributions: 1 + 2*min(K(rho), nRho-1-rho) per inside record
+  {
+    int bound = 0;
+    for (int i = tid; i < n_c; i += blockDim.x) {
+      RayRecord rc = recs[i];
+      if (rc.phi_flags & kRecInside) bound += 1 + 2 * min(P.k_reach[rc.rho], P.nRho - 1 - rc.rho);
+    }
+    for (int ofs = 16; ofs > 0; ofs >>= 1) bound += __shfl_xor_sync(0xffffffffu, bound, ofs);
+    if (lane_id() == 0 && bound) atomicAdd(&s_bound, bound);
+  }
+  __syncthreads();
+  // sort buffer: shared memory when the bound fits, else the global spill region (slow, still exact)
+  uint64_t *keys = s_bound <= P.sort_cap_smem ? s_keys : D.col_scratch + (size_t)2 * off * P.contrib_per_point;
   // (a) contributions, update_hits src/map_awareness.cpp:135-171
   for (int i = tid; i < n_c; i += blockDim.x) {
     RayRecord rc = recs[i];
     if (!(rc.phi_flags & kRecInside)) continue;
     const int rho = rc.rho, z = rc.z;
+    const int reps = (int)((rc.phi_flags >> kRecCountShift) & kRecCountMask);
     if (P.visibility_check) atomicOr(&s_end[z * P.words_per_row + (rho >> 5)], 1u << (rho & 31));
     double rate = ray_rate(P, rho, z);
     int K = P.k_reach[rho];
@@ -414,10 +449,10 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
       dmax = d;
     }
     int pos = atomicAdd(&s_nk, cnt);
-    keys[pos++] = contrib_key(z * P.nRho + rho, rc.t, 0);
+    keys[pos++] = contrib_key(z * P.nRho + rho, rc.t, 0, reps);
     for (int d = 1; d <= dmax; d++) {
-      if (zp[d - 1] >= 0 && zp[d - 1] < P.nZ) keys[pos++] = contrib_key(zp[d - 1] * P.nRho + rho + d, rc.t, 2 * d - 1);
-      if (zm[d - 1] >= 0 && zm[d - 1] < P.nZ) keys[pos++] = contrib_key(zm[d - 1] * P.nRho + rho - d, rc.t, 2 * d);
+      if (zp[d - 1] >= 0 && zp[d - 1] < P.nZ) keys[pos++] = contrib_key(zp[d - 1] * P.nRho + rho + d, rc.t, 2 * d - 1, reps);
+      if (zm[d - 1] >= 0 && zm[d - 1] < P.nZ) keys[pos++] = contrib_key(zm[d - 1] * P.nRho + rho - d, rc.t, 2 * d, reps);
     }
   }
   __syncthreads();
@@ -447,20 +482,27 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   // (c) ordered fold per cell + staging of the distinct hit keys
   for (int i = tid; i < n_k; i += blockDim.x) {
     uint64_t k0 = keys[i];
-    int cell = (int)(k0 >> 37);
-    if (i > 0 && (int)(keys[i - 1] >> 37) == cell) continue;  // not the first contribution of its cell
+    int cell = (int)(k0 >> kKeyCellShift);
+    if (i > 0 && (int)(keys[i - 1] >> kKeyCellShift) == cell) continue;  // not the first contribution of its cell
     const int zk = cell / P.nRho, rk = cell - zk * P.nRho;
     float p = 0.f;
-    for (int j = i; j < n_k; j++) {
+    bool first = true;
+    for (int j = i; j < n_k && p != 1.0f; j++) {
       uint64_t kj = keys[j];
-      if ((int)(kj >> 37) != cell) break;
-      int s = (int)(kj & 31);
+      if ((int)(kj >> kKeyCellShift) != cell) break;
+      int s = (int)((kj >> 7) & 31);
+      int reps = (int)(kj & 127);
       int d = s == 0 ? 0 : ((s & 1) ? (s + 1) >> 1 : -(s >> 1));
       float odd = __ldg(&P.odds_table[(kDiffRange + d) * P.nRho + (rk - d)]);
-      p = (j == i) ? odd : odds_combine(p, odd);
-      if (p == 1.0f) break;  // saturated: 1 - (1-1)*(1-odd) == 1 for every later contribution
+      for (int r = 0; r < reps; r++) {
+        float np_ = first ? odd : odds_combine(p, odd);
+        bool stuck = !first && np_ == p;  // fixed point of this odd: the rest of the run is a no-op
+        first = false;
+        p = np_;
+        if (stuck || p == 1.0f) break;    // p == 1: 1 - (1-1)*(1-odd) == 1 for every later contribution
+      }
     }
-    const uint32_t stamp = (uint32_t)(k0 & ((1ull << 37) - 1));  // t*32 + substep of the first insert
+    const uint32_t stamp = (uint32_t)((k0 >> 7) & 0xffffffffull);  // t*32 + substep of the first insert
     const int idx = agg_inc(&D.fc->n_hit);
     if (idx >= P.max_hits) {
       D.fc->error = kErrCapacity;

@@ -153,6 +153,9 @@ struct mlm_map {
   void *l2_buf = nullptr;
   size_t l2_bytes = 0;
   int sm_count = 148;
+  int profiling = 0;
+  cudaEvent_t kev[MLM_NUM_FRAME_KERNELS + 1] = {};
+  float kms[MLM_NUM_FRAME_KERNELS] = {};
 };
 
 namespace {
@@ -356,23 +359,36 @@ int run_frame(mlm_map *h, bool depth, const void *d_in, int rows, int cols, int 
   for (int i = 0; i < 3; i++) F.lsg_base[i] = host_floor_div(F.lvg_base[i], P.n) - 1;
   CUDA_TRY(cudaMemcpyAsync(h->D.fp, h->h_fp, sizeof(FrameParams), cudaMemcpyHostToDevice, s));
 
+  const bool prof = h->profiling != 0;
+#define MLM_MARK(i) do { if (prof) cudaEventRecord(h->kev[i], s); } while (0)
+  MLM_MARK(0);
   k_frame_begin<<<h->sm_count, 256, 0, s>>>(P, h->D);
+  MLM_MARK(1);
   const size_t proj_smem = (size_t)(P.nPhi + 256) * sizeof(int);
   if (depth)
     k_project<true><<<grid_for(N, 256), 256, proj_smem, s>>>(P, h->D, d_in, rows, cols, 0, h->d_ticket);
   else
     k_project<false><<<grid_for(N, 256), 256, proj_smem, s>>>(P, h->D, d_in, 0, 0, n_points, h->d_ticket);
+  MLM_MARK(2);
   k_scatter<<<grid_for(N, 256), 256, (size_t)2 * P.nPhi * sizeof(int), s>>>(P, h->D, N);
+  MLM_MARK(3);
   k_column<<<P.nPhi, kColThreads, h->col_smem_bytes, s>>>(P, h->D);
+  MLM_MARK(4);
   k_submaps<<<h->sm_count, 256, 0, s>>>(P, h->D);
+  MLM_MARK(5);
   k_fuse<<<h->sm_count * 4, 256, 0, s>>>(P, h->D);
+  MLM_MARK(6);
   k_frame_end<<<1, 1, 0, s>>>(h->D);
+  MLM_MARK(7);
+#undef MLM_MARK
   h->launches += 7;
   CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(h->h_cum, h->D.cum, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   CUDA_TRY(cudaGetLastError());
 
+  if (prof)
+    for (int i = 0; i < MLM_NUM_FRAME_KERNELS; i++) cudaEventElapsedTime(&h->kms[i], h->kev[i], h->kev[i + 1]);
   int slow = 0;
   uint32_t order_B = h->bucket_count;
   if (h->h_fc->error == 0 && h->h_fc->overflow) {
@@ -755,6 +771,8 @@ int mlm_destroy(mlm_handle h) {
   if (h->h_cum) cudaFreeHost(h->h_cum);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (int i = 0; i <= MLM_NUM_FRAME_KERNELS; i++)
+    if (h->kev[i]) cudaEventDestroy(h->kev[i]);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return MLM_OK;
@@ -950,6 +968,18 @@ int mlm_flush_l2(mlm_handle h) {
   static uint32_t v = 1;
   k_l2_flush<<<h->sm_count * 8, 256, 0, h->stream>>>((uint4 *)h->l2_buf, h->l2_bytes / 16, v++);
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return MLM_OK;
+}
+int mlm_set_profiling(mlm_handle h, int enable) {
+  if (!h) return MLM_ERR_INVALID_ARG;
+  if (enable && !h->kev[0])
+    for (int i = 0; i <= MLM_NUM_FRAME_KERNELS; i++) CUDA_TRY(cudaEventCreate(&h->kev[i]));
+  h->profiling = enable != 0;
+  return MLM_OK;
+}
+int mlm_last_frame_kernel_ms(mlm_handle h, float ms[MLM_NUM_FRAME_KERNELS]) {
+  if (!h || !ms) return MLM_ERR_INVALID_ARG;
+  for (int i = 0; i < MLM_NUM_FRAME_KERNELS; i++) ms[i] = h->kms[i];
   return MLM_OK;
 }
 int mlm_kernel_launch_count(mlm_handle h, int64_t *count) {

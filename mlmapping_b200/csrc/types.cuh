@@ -21,11 +21,13 @@ constexpr uint32_t kTouchedHitTag = 0x80000000u;
 struct __align__(16) RayRecord {
   int rho;        // rho_idx as the reference computes it (may be >= nRho)
   int z;          // z_idx (may be out of range)
-  uint32_t phi_flags;  // phi_idx | inside<<30
+  uint32_t phi_flags;  // phi_idx | run length << 16 | inside << 30
   uint32_t t;     // point order stamp = index of the point in input_pc_pose's loop
 };
 constexpr uint32_t kRecInside = 1u << 30;
 constexpr uint32_t kRecPhiMask = (1u << 16) - 1;
+constexpr int kRecCountShift = 16;          // run length (1..32) of identical consecutive points
+constexpr uint32_t kRecCountMask = 0x3f;
 
 // constants of a handle (mlmap::init_map), immutable after mlm_create
 struct MapParams {
