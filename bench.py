@@ -258,13 +258,10 @@ def main():
     m.close()
 
     # ---------------- reduce over ranks: max time, sum of rays ----------------
-    if world > 1:
-        t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        r = torch.tensor([rays, e2e_rays, launches], dtype=torch.float64, device="cuda")
-        dist.all_reduce(r, op=dist.ReduceOp.SUM)
-        dev_ms, e2e_s = float(t[0]), float(t[1])
-        rays, e2e_rays, launches = int(r[0]), int(r[1]), int(r[2])
+    from mlmapping_b200.sharding import reduce_timing
+    (dev_ms, e2e_s), (rays, e2e_rays, launches) = reduce_timing([dev_ms, e2e_s], [rays, e2e_rays, launches],
+                                                                device="cuda" if world > 1 else None)
+    rays, e2e_rays, launches = int(rays), int(e2e_rays), int(launches)
 
     if rank == 0:
         value = rays / (dev_ms * 1e-3)

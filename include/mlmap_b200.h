@@ -124,6 +124,9 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out);
 int mlm_destroy(mlm_handle h);
 const char *mlm_last_error(void);
 int mlm_abi_version(void);
+/* sizeof(mlm_config) / sizeof(mlm_frame_stats) as compiled, for binding self-checks */
+size_t mlm_sizeof_config(void);
+size_t mlm_sizeof_frame_stats(void);
 
 /* ---- per-frame update (the north-star path) --------------------------------------------------- */
 

@@ -107,7 +107,8 @@ ABI_SYMBOLS = [
     "mlm_sync", "mlm_timer_start", "mlm_timer_stop_ms", "mlm_device_alloc", "mlm_device_free",
     "mlm_copy_to_device", "mlm_copy_to_host", "mlm_flush_l2", "mlm_kernel_launch_count",
     "mlm_last_frame_hits", "mlm_last_frame_misses", "mlm_export_map_count", "mlm_export_map",
-    "mlm_debug_log10f", "mlm_set_profiling", "mlm_last_frame_kernel_ms",
+    "mlm_debug_log10f", "mlm_set_profiling", "mlm_last_frame_kernel_ms", "mlm_sizeof_config",
+    "mlm_sizeof_frame_stats",
 ]
 FRAME_KERNELS = ["k_frame_begin", "k_project", "k_scatter", "k_column", "k_submaps", "k_fuse", "k_frame_end"]
 
@@ -146,6 +147,8 @@ def load_library() -> C.CDLL:
         "mlm_destroy": ([vp], C.c_int),
         "mlm_last_error": ([], C.c_char_p),
         "mlm_abi_version": ([], C.c_int),
+        "mlm_sizeof_config": ([], C.c_size_t),
+        "mlm_sizeof_frame_stats": ([], C.c_size_t),
         "mlm_integrate_depth_u16": ([vp, vp, C.c_int, C.c_int, sz, dp, C.POINTER(FrameStats)], C.c_int),
         "mlm_integrate_depth_u16_device": ([vp, vp, C.c_int, C.c_int, dp, C.POINTER(FrameStats)], C.c_int),
         "mlm_integrate_points_f64": ([vp, vp, C.c_int, dp, C.POINTER(FrameStats)], C.c_int),
@@ -181,6 +184,8 @@ def load_library() -> C.CDLL:
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = ret
+    if lib.mlm_sizeof_config() != C.sizeof(MlmConfig) or lib.mlm_sizeof_frame_stats() != C.sizeof(FrameStats):
+        raise MlmError(1, "ctypes struct layout does not match include/mlmap_b200.h")
     _lib = lib
     return lib
 

@@ -344,13 +344,79 @@ __global__ void __launch_bounds__(256) k_scatter(MapParams P, DeviceBuffers D, i
 // distinct hit keys with their first-insert stamps and stage them in the frame-local voxel grid,
 // (d) warp-cooperative ray walks into a shared-memory miss bitmap, (e) stage the distinct miss
 // cells in the voxel grid.
-constexpr int kColThreads = 512;
+constexpr int kColThreads = 1024;
+constexpr int kColWarps = kColThreads / 32;
+constexpr int kRadixBits = 8;
+constexpr int kRadixDigits = 1 << kRadixBits;
 constexpr int kCellBits = 20;
 
-// [63:44] cell in column, [43:12] point stamp t, [11:7] substep, [6:0] repeat count of the run
-constexpr int kKeyCellShift = 44;
-__device__ __forceinline__ uint64_t contrib_key(int cell, uint32_t t, int substep, int reps) {
-  return ((uint64_t)(uint32_t)cell << kKeyCellShift) | ((uint64_t)t << 12) | ((uint64_t)substep << 7) | (uint64_t)reps;
+// contribution key, sorted by (cell, t):
+//   [.. : 12+tbits] cell in column | [12+tbits-1 : 12] point stamp t | [11:7] substep | [6:0] run length
+// (cell, t) is unique per contribution (one record reaches a cell at most once: every contribution
+// of a record has a different rho), so substep and run length ride along as payload.
+__device__ __forceinline__ uint64_t contrib_key(int cell, uint32_t t, int substep, int reps, int tbits) {
+  return ((uint64_t)(uint32_t)cell << (12 + tbits)) | ((uint64_t)t << 12) | ((uint64_t)substep << 7) | (uint64_t)reps;
+}
+
+// One stable LSD radix pass over 8 key bits for the whole CTA (src -> dst), keys in shared or
+// global memory.  Warp w owns a contiguous chunk; cnt[digit*W + w] after the exclusive scan is the
+// output cursor of (digit, warp), so order inside a digit is (warp, position) = input order.
+__device__ __forceinline__ void radix_pass(const uint64_t *src, uint64_t *dst, int n, int shift, uint32_t *cnt,
+                                           uint32_t *warp_sums) {
+  const int W = kColWarps, w = threadIdx.x >> 5, lane = lane_id(), tid = threadIdx.x;
+  const int chunk = (((n + W - 1) / W) + 31) & ~31;
+  const int beg = min(w * chunk, n), end = min(beg + chunk, n);
+  for (int i = tid; i < kRadixDigits * W; i += kColThreads) cnt[i] = 0;
+  __syncthreads();
+  for (int i = beg + lane; i < end; i += 32)
+    atomicAdd(&cnt[(int)((src[i] >> shift) & (kRadixDigits - 1)) * W + w], 1u);
+  __syncthreads();
+  // exclusive scan over the kRadixDigits*W counters: 8 consecutive entries per thread
+  constexpr int E = kRadixDigits * W / kColThreads;
+  uint32_t v[E], sum = 0;
+#pragma unroll
+  for (int e = 0; e < E; e++) {
+    v[e] = cnt[E * tid + e];
+    sum += v[e];
+  }
+  uint32_t incl = sum;
+#pragma unroll
+  for (int ofs = 1; ofs < 32; ofs <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, incl, ofs);
+    if (lane >= ofs) incl += t;
+  }
+  if (lane == 31) warp_sums[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t sv = lane < W ? warp_sums[lane] : 0, si = sv;
+#pragma unroll
+    for (int ofs = 1; ofs < 32; ofs <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, si, ofs);
+      if (lane >= ofs) si += t;
+    }
+    if (lane < W) warp_sums[lane] = si - sv;
+  }
+  __syncthreads();
+  uint32_t run = warp_sums[w] + incl - sum;
+#pragma unroll
+  for (int e = 0; e < E; e++) {
+    cnt[E * tid + e] = run;
+    run += v[e];
+  }
+  __syncthreads();
+  for (int base = beg; base < end; base += 32) {
+    const int i = base + lane;
+    const bool ok = i < end;
+    const uint64_t key = ok ? src[i] : 0;
+    const int d = ok ? (int)((key >> shift) & (kRadixDigits - 1)) : kRadixDigits + lane;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int rank = __popc(peers & ((1u << lane) - 1));
+    if (ok) dst[cnt[d * W + w] + rank] = key;
+    __syncwarp();
+    if (ok && rank == 0) cnt[d * W + w] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
 }
 
 __device__ __forceinline__ void touch_subbox(const MapParams &P, const FrameParams &F, DeviceBuffers &D,
@@ -390,6 +456,19 @@ __device__ __forceinline__ void walk_ray(const MapParams &P, uint32_t *s_miss, i
   }
 }
 
+// CTA-wide compaction of the set bits of bm[w0,w1) into list (entries = word*32 + bit), any order.
+__device__ __forceinline__ void compact_bits(const uint32_t *bm, int w0, int w1, uint32_t *list, int *counter) {
+  const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int wi = w0 + warp; wi < w1; wi += nwarps) {
+    const uint32_t bits = bm[wi];
+    if (!bits) continue;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(counter, __popc(bits));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if ((bits >> lane) & 1u) list[base + __popc(bits & ((1u << lane) - 1))] = ((uint32_t)wi << 5) | (uint32_t)lane;
+  }
+}
+
 __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBuffers D) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   const FrameParams &F = *D.fp;
@@ -404,9 +483,13 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   const int off = D.phi_off[phi];
   const RayRecord *recs = D.rec_col + off;
 
+  // shared memory: [miss bitmap][end-cell bitmap][radix counters][warp sums][keys A][keys B]
   uint32_t *s_miss = reinterpret_cast<uint32_t *>(s_raw);
   uint32_t *s_end = s_miss + P.col_words;
-  uint64_t *s_keys = reinterpret_cast<uint64_t *>(s_raw + (((size_t)2 * P.col_words * 4 + 15) & ~(size_t)15));
+  uint32_t *s_cnt = s_end + P.col_words;
+  uint32_t *s_wsum = s_cnt + kRadixDigits * kColWarps;
+  uint64_t *s_keys = reinterpret_cast<uint64_t *>(
+      s_raw + ((((size_t)2 * P.col_words + kRadixDigits * kColWarps + kColWarps) * 4 + 15) & ~(size_t)15));
   __shared__ int s_nk;
   __shared__ int s_nmiss;
   __shared__ int s_bound;
@@ -429,7 +512,10 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   }
   __syncthreads();
   // sort buffer: shared memory when the bound fits, else the global spill region (slow, still exact)
-  uint64_t *keys = s_bound <= P.sort_cap_smem ? s_keys : D.col_scratch + (size_t)2 * off * P.contrib_per_point;
+  const bool in_smem = s_bound <= P.sort_cap_smem;
+  uint64_t *keys = in_smem ? s_keys : D.col_scratch + (size_t)2 * off * P.contrib_per_point;
+  uint64_t *keys_alt = in_smem ? s_keys + P.sort_cap_smem : keys + (size_t)n_c * P.contrib_per_point;
+  const int tbits = F.tbits;
   // (a) contributions, update_hits src/map_awareness.cpp:135-171
   for (int i = tid; i < n_c; i += blockDim.x) {
     RayRecord rc = recs[i];
@@ -449,47 +535,39 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
       dmax = d;
     }
     int pos = atomicAdd(&s_nk, cnt);
-    keys[pos++] = contrib_key(z * P.nRho + rho, rc.t, 0, reps);
+    keys[pos++] = contrib_key(z * P.nRho + rho, rc.t, 0, reps, tbits);
     for (int d = 1; d <= dmax; d++) {
-      if (zp[d - 1] >= 0 && zp[d - 1] < P.nZ) keys[pos++] = contrib_key(zp[d - 1] * P.nRho + rho + d, rc.t, 2 * d - 1, reps);
-      if (zm[d - 1] >= 0 && zm[d - 1] < P.nZ) keys[pos++] = contrib_key(zm[d - 1] * P.nRho + rho - d, rc.t, 2 * d, reps);
+      if (zp[d - 1] >= 0 && zp[d - 1] < P.nZ) keys[pos++] = contrib_key(zp[d - 1] * P.nRho + rho + d, rc.t, 2 * d - 1, reps, tbits);
+      if (zm[d - 1] >= 0 && zm[d - 1] < P.nZ) keys[pos++] = contrib_key(zm[d - 1] * P.nRho + rho - d, rc.t, 2 * d, reps, tbits);
     }
   }
   __syncthreads();
   const int n_k = s_nk;
 
-  // (b) bitonic sort by (cell, point, substep)
-  int n_pad = 1;
-  while (n_pad < n_k) n_pad <<= 1;
-  for (int i = n_k + tid; i < n_pad; i += blockDim.x) keys[i] = ~0ull;
-  __syncthreads();
-  for (int k = 2; k <= n_pad; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < (n_pad >> 1); i += blockDim.x) {
-        int a = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-        int b = a | j;
-        uint64_t ka = keys[a], kb = keys[b];
-        bool up = (a & k) == 0;
-        if ((ka > kb) == up) {
-          keys[a] = kb;
-          keys[b] = ka;
-        }
-      }
-      __syncthreads();
+  // (b) stable LSD radix sort by (cell, t): bits [12, 12 + tbits + cell_bits)
+  {
+    const int hi_bit = 12 + tbits + P.cell_bits;
+    for (int shift = 12; shift < hi_bit; shift += kRadixBits) {
+      radix_pass(keys, keys_alt, n_k, shift, s_cnt, s_wsum);
+      uint64_t *t = keys;
+      keys = keys_alt;
+      keys_alt = t;
     }
   }
+  const int cell_shift = 12 + tbits;
+  const uint64_t t_mask = (1ull << tbits) - 1;
 
   // (c) ordered fold per cell + staging of the distinct hit keys
   for (int i = tid; i < n_k; i += blockDim.x) {
     uint64_t k0 = keys[i];
-    int cell = (int)(k0 >> kKeyCellShift);
-    if (i > 0 && (int)(keys[i - 1] >> kKeyCellShift) == cell) continue;  // not the first contribution of its cell
+    int cell = (int)(k0 >> cell_shift);
+    if (i > 0 && (int)(keys[i - 1] >> cell_shift) == cell) continue;  // not the first contribution of its cell
     const int zk = cell / P.nRho, rk = cell - zk * P.nRho;
     float p = 0.f;
     bool first = true;
     for (int j = i; j < n_k && p != 1.0f; j++) {
       uint64_t kj = keys[j];
-      if ((int)(kj >> kKeyCellShift) != cell) break;
+      if ((int)(kj >> cell_shift) != cell) break;
       int s = (int)((kj >> 7) & 31);
       int reps = (int)(kj & 127);
       int d = s == 0 ? 0 : ((s & 1) ? (s + 1) >> 1 : -(s >> 1));
@@ -502,7 +580,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
         if (stuck || p == 1.0f) break;    // p == 1: 1 - (1-1)*(1-odd) == 1 for every later contribution
       }
     }
-    const uint32_t stamp = (uint32_t)((k0 >> 7) & 0xffffffffull);  // t*32 + substep of the first insert
+    const uint32_t stamp = (uint32_t)((((k0 >> 12) & t_mask) << 5) | ((k0 >> 7) & 31));  // t*32 + substep of the first insert
     const int idx = agg_inc(&D.fc->n_hit);
     if (idx >= P.max_hits) {
       D.fc->error = kErrCapacity;
@@ -532,18 +610,27 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   }
   __syncthreads();
 
+  // The sorted keys are dead from here on: the key area becomes scratch for compacted cell lists.
+  uint32_t *s_list = reinterpret_cast<uint32_t *>(s_keys);
+  const int list_cap = P.sort_cap_smem * 4;            // 32-bit entries in the two key buffers
+  const int words_per_chunk = max(1, list_cap >> 5);   // a chunk of words can never overflow the list
+
   // (d) ray walks, src/map_awareness.cpp:241-275
   if (P.visibility_check) {
     const int warp = tid >> 5, nwarps = blockDim.x >> 5;
     // distinct inside end cells: each walks once (the walk depends only on (rho,phi,z))
-    for (int wi = warp; wi < P.col_words; wi += nwarps) {
-      uint32_t bits = s_end[wi];
-      const int z = wi / P.words_per_row, wr = wi - z * P.words_per_row;
-      while (bits) {
-        int b = __ffs(bits) - 1;
-        bits &= bits - 1;
-        walk_ray(P, s_miss, (wr << 5) + b, z);
+    for (int w0 = 0; w0 < P.col_words; w0 += words_per_chunk) {
+      if (tid == 0) s_nk = 0;
+      __syncthreads();
+      compact_bits(s_end, w0, min(w0 + words_per_chunk, P.col_words), s_list, &s_nk);
+      __syncthreads();
+      const int n_list = s_nk;
+      for (int k = warp; k < n_list; k += nwarps) {
+        const uint32_t e = s_list[k];
+        const int wi = (int)(e >> 5), z = wi / P.words_per_row, wr = wi - z * P.words_per_row;
+        walk_ray(P, s_miss, (wr << 5) + (int)(e & 31), z);
       }
+      __syncthreads();
     }
     // castable points outside the awareness range walk from the clamped cell (:261-265)
     for (int base = warp * 32; base < n_c; base += nwarps * 32) {
@@ -563,20 +650,20 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   }
   __syncthreads();
 
-  // (e) distinct miss cells -> voxel grid staging; bitmap to global for export
-  for (int wi = tid; wi < P.col_words; wi += blockDim.x) {
-    uint32_t bits = s_miss[wi];
-    g_miss[wi] = bits;
-    if (!bits) continue;
-    atomicAdd(&s_nmiss, __popc(bits));
-    const int z = wi / P.words_per_row, wr = wi - z * P.words_per_row;
-    const double pz = __ldg(&P.centre_z[z]) + F.t_wa[2];
-    while (bits) {
-      int b = __ffs(bits) - 1;
-      bits &= bits - 1;
-      int r = (wr << 5) + b;
+  // (e) distinct miss cells -> voxel grid staging (one cell per thread); bitmap to global for export
+  for (int wi = tid; wi < P.col_words; wi += blockDim.x) g_miss[wi] = s_miss[wi];
+  for (int w0 = 0; w0 < P.col_words; w0 += words_per_chunk) {
+    if (tid == 0) s_nk = 0;
+    __syncthreads();
+    compact_bits(s_miss, w0, min(w0 + words_per_chunk, P.col_words), s_list, &s_nk);
+    __syncthreads();
+    const int n_list = s_nk;
+    for (int k = tid; k < n_list; k += blockDim.x) {
+      const uint32_t e = s_list[k];
+      const int wi = (int)(e >> 5), z = wi / P.words_per_row, wr = wi - z * P.words_per_row;
+      const int r = (wr << 5) + (int)(e & 31);
       double2 cxy = __ldg(&P.centre_xy[phi * P.nRho + r]);
-      CellRef cr = locate_cell(P, cxy.x + F.t_wa[0], cxy.y + F.t_wa[1], pz);
+      CellRef cr = locate_cell(P, cxy.x + F.t_wa[0], cxy.y + F.t_wa[1], __ldg(&P.centre_z[z]) + F.t_wa[2]);
       int lv = lvg_index(P, F, cr);
       if (lv < 0) {
         D.fc->error = kErrInternal;
@@ -589,8 +676,9 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
       }
       touch_subbox(P, F, D, cr.g);
     }
+    if (tid == 0) s_nmiss += n_list;
+    __syncthreads();
   }
-  __syncthreads();
   if (tid == 0 && s_nmiss) atomicAdd(&D.fc->n_miss, s_nmiss);
 }
 

@@ -351,6 +351,8 @@ int run_frame(mlm_map *h, bool depth, const void *d_in, int rows, int cols, int 
   F.n_points = n_points;
   F.bucket_count = h->bucket_count;
   F.order_mode = 0;
+  F.tbits = 1;
+  while ((1ll << F.tbits) < (long long)std::max(N, 2)) F.tbits++;
   // frame-local voxel grid origin: awareness bounding box around t_wa plus a margin
   const double R = P.nRho * P.dRho;
   F.lvg_base[0] = (int)floor((Twa.t[0] - R) / P.d_sub) - P.lvg_margin;
@@ -484,6 +486,8 @@ int host_query(mlm_handle h, const double *pos, size_t n, OutT *out, size_t out_
 extern "C" {
 
 int mlm_abi_version(void) { return MLM_ABI_VERSION; }
+size_t mlm_sizeof_config(void) { return sizeof(mlm_config); }
+size_t mlm_sizeof_frame_stats(void) { return sizeof(mlm_frame_stats); }
 const char *mlm_last_error(void) { return g_last_error.c_str(); }
 
 int mlm_default_config(mlm_config *c) {
@@ -590,6 +594,8 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   P.maxK = maxK;
   P.words_per_row = (P.nRho + 31) / 32;
   P.col_words = P.nZ * P.words_per_row;
+  P.cell_bits = 1;
+  while ((1 << P.cell_bits) < P.nZ * P.nRho) P.cell_bits++;
   // local_map_cartesian::init_map, src/map_local.cpp:56-62
   P.d_sub = cfg->subbox_d_xyz;
   P.d_sub_half = P.d_sub * 0.5;
@@ -634,17 +640,18 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   // column kernel shared memory: two column bitmaps + the largest power-of-two sort buffer that fits
   int max_optin = 0;
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-  const size_t bm_bytes = (((size_t)2 * P.col_words * 4 + 15) & ~(size_t)15);
-  long long avail = (long long)max_optin - 2048 - (long long)bm_bytes;
-  if (avail < 8 * 1024) {
+  const size_t bm_bytes =
+      ((((size_t)2 * P.col_words + (size_t)kRadixDigits * kColWarps + kColWarps) * 4 + 15) & ~(size_t)15);
+  long long avail = (long long)max_optin - 1024 - (long long)bm_bytes;
+  if (avail < 32 * 1024) {
     delete h;
     g_last_error = "awareness column (n_Z*n_Rho bits) does not fit shared memory";
     return MLM_ERR_INVALID_CONFIG;
   }
-  int cap = 1024;
-  while ((long long)cap * 2 * 8 <= avail && cap < (1 << 16)) cap <<= 1;
+  // two key buffers (radix ping-pong) of sort_cap_smem 64-bit keys each
+  int cap = (int)(avail / 16) & ~127;
   P.sort_cap_smem = cap;
-  h->col_smem_bytes = (int)(bm_bytes + (size_t)cap * 8);
+  h->col_smem_bytes = (int)(bm_bytes + (size_t)cap * 16);
 
 #define TRY(x)            \
   do {                    \

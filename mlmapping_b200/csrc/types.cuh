@@ -38,6 +38,7 @@ struct MapParams {
   int maxK;               // max over rho of the neighbour reach K(rho)
   int words_per_row;      // ceil(nRho / 32): bitmap words per (phi,z) row
   int col_words;          // nZ * words_per_row
+  int cell_bits;          // bits of a cell id inside a column: ceil(log2(nZ*nRho))
   // local_map_cartesian members (include/map_local.h:66-78)
   double d_sub, d_glb, d_sub_half;
   int n;                  // subbox_nxyz
@@ -77,6 +78,7 @@ struct FrameParams {
   uint32_t bucket_count;  // emulated hit_idx_odds_hashmap.bucket_count() at frame start
   int lvg_base[3];  // global cell coordinate of local voxel grid origin
   int lsg_base[3];  // global subbox coordinate of local submap grid origin
+  int tbits;        // bits needed for a point stamp this frame (ceil(log2(#points)))
   int order_mode;   // 0: stamps are (bucket activation, first-insert time); 1: virtual sequence positions
 };
 

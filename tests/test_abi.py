@@ -1,0 +1,73 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/mlmap_b200.h declares;
+ctypes struct layouts match; with no GPU the product fails loudly (no CPU fallback)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+import mlmapping_b200 as mlm
+from mlmapping_b200 import capi
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not mlm.library_path().exists():
+        mlm.build_library()
+    return mlm.load_library()
+
+
+def _declared_symbols():
+    text = (ROOT / "include" / "mlmap_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mlm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(lib):
+    declared = _declared_symbols()
+    assert len(declared) >= 35
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/mlmap_b200.h but not exported"
+    assert set(capi.ABI_SYMBOLS) == set(declared)
+
+
+def test_struct_layouts(lib):
+    assert lib.mlm_sizeof_config() == C.sizeof(capi.MlmConfig)
+    assert lib.mlm_sizeof_frame_stats() == C.sizeof(capi.FrameStats)
+    assert lib.mlm_abi_version() == 1
+
+
+def test_default_config_is_config_sim_yaml(lib):
+    c = mlm.default_config()  # reference launch/config/config_sim.yaml
+    assert (c.am_d_rho, c.am_d_phi_deg, c.am_d_z) == (0.20, 5.0, 0.20)
+    assert (c.am_n_rho, c.am_n_z_below, c.am_n_z_over) == (40, 20, 20)
+    assert c.subbox_n == 10 and abs(c.subbox_d_xyz - 0.2) < 1e-15
+    assert abs(c.log_odds_max - 4.2) < 1e-6 and abs(c.log_odds_miss + 0.9) < 1e-6
+    assert c.cam_fx == pytest.approx(347.99755859375)
+    assert list(c.T_bs) == [0.12, 0.0, 0.0, 0.5, -0.5, 0.5, -0.5]
+
+
+def test_invalid_config_and_no_silent_cpu_fallback(lib):
+    import torch
+    cfg = mlm.config_cfg_a()
+    h = C.c_void_p()
+    bad = cfg.copy()
+    bad.am_d_rho = -1.0
+    assert lib.mlm_create(C.byref(bad), 0, C.byref(h)) == 2  # MLM_ERR_INVALID_CONFIG
+    bad = cfg.copy()
+    bad.max_points = 0
+    assert lib.mlm_create(C.byref(bad), 0, C.byref(h)) == 2
+    assert lib.mlm_create(None, 0, C.byref(h)) == 1           # MLM_ERR_INVALID_ARG
+    bad = cfg.copy()
+    bad.use_exploration_frontiers = 1
+    assert lib.mlm_create(C.byref(bad), 0, C.byref(h)) == 6   # MLM_ERR_UNSUPPORTED, never a CPU path
+    if not torch.cuda.is_available():
+        rc = lib.mlm_create(C.byref(cfg), 0, C.byref(h))
+        assert rc == 7 and b"no CPU fallback" in lib.mlm_last_error()
+        with pytest.raises(mlm.MlmError):
+            mlm.MLMap(cfg)
+    # null handles are rejected, not dereferenced
+    assert lib.mlm_sync(None) == 1
+    assert lib.mlm_destroy(None) == 1

@@ -1,0 +1,186 @@
+"""CPU: pins for the oracle (oracle/mlmap_oracle.hpp).  The reference has no tests or golden vectors
+(SURVEY §4), so these are first-principles known answers for the reference's formulas, quirks the
+SURVEY derived from the cited lines, and the libstdc++ container model the CUDA path emulates."""
+import math
+
+import numpy as np
+import pytest
+
+from mlmapping_b200 import config_cfg_a, scenes
+from oracle_binding import Oracle, load_oracle
+from order_model import BUCKET_CHAIN, iteration_order, vector_hash
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return load_oracle()
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle(config_cfg_a())
+
+
+def test_logit_known_values(lib):
+    # SURVEY §4 [probe]: logit(0.999f) = 2.99957108, logit(1.0f) = +inf (include/map_local.h:8)
+    assert lib.orc_logit(np.float32(0.999)) == pytest.approx(2.99957108, abs=2e-7)
+    assert math.isinf(lib.orc_logit(np.float32(1.0)))
+    assert lib.orc_logit(np.float32(0.5)) == 0.0
+    # logit_inv (include/mlmap.h:40): double pow, float result
+    assert lib.orc_logit_inv(np.float32(0.0)) == 0.5
+    assert lib.orc_logit_inv(np.float32(-2.0)) == pytest.approx(0.00990099, abs=1e-8)
+    assert lib.orc_logit_inv(np.float32(4.2)) == pytest.approx(1 - 1 / (1 + 10 ** 4.2), abs=1e-7)
+
+
+def test_fast_atan2_quirks(lib, orc):
+    # include/map_awareness.h:86-113: (y>0, x=0) -> 3*pi/2 (sic); (y<0, x=0) -> -3pi/2 + ... = pi/2 after wrap
+    assert lib.orc_fast_atan2(orc.h, 1.0, 0.0) == pytest.approx(1.5 * math.pi, abs=1e-12)
+    v = lib.orc_fast_atan2(orc.h, -1.0, 0.0)
+    assert (v + 2 * math.pi if v < 0 else v) == pytest.approx(0.5 * math.pi, abs=1e-12)
+    # cubic approximation error stays below 0.1 degree
+    ang = np.linspace(-3.1, 3.1, 2001)
+    err = [abs(lib.orc_fast_atan2(orc.h, math.sin(a), math.cos(a)) - a) for a in ang]
+    assert max(err) < math.radians(0.1)
+
+
+def test_odds_table_clamps_and_reach(lib, orc):
+    cfg = orc.cfg
+    tab = np.array([[lib.orc_odds_table(orc.h, d, r) for r in range(cfg.am_n_rho)] for d in range(-10, 11)])
+    assert tab.min() >= np.float32(0.001) and tab.max() <= np.float32(0.999)   # map_awareness.cpp:128-129
+    assert tab[10, 1] == np.float32(0.999)        # near field: all mass in the centre cell
+    assert np.all(tab[10] >= tab[11]) and np.all(tab[10] >= tab[9])
+    assert tab[0, 0] == tab[0, 1] and tab[10, 0] == tab[10, 1]   # r == 0 treated as 1
+    # 3*sigma_in_dr(64) = 3*0.00375*6.4^2/0.1 = 4.608
+    assert lib.orc_three_sigma(orc.h, 64) == pytest.approx(4.608, abs=1e-5)
+    assert lib.orc_three_sigma(orc.h, 0) == 0.0
+
+
+def test_pow2_is_exact_square(lib):
+    rs = np.random.RandomState(0)
+    for x in rs.uniform(-100, 100, 2000):
+        assert lib.orc_pow2(x) == x * x
+
+
+def test_vector_hasher_matches_model(lib):
+    rs = np.random.RandomState(1)
+    keys = rs.randint(-5, 700, size=(4000, 3))
+    keys[:10] = [[0, 0, 0], [64, 359, 40], [-1, 0, 0], [2 ** 20, 3, 7], [1, 2, 3], [3, 2, 1], [65, 0, 20],
+                 [0, 359, 0], [7, 7, 7], [-3, -2, -1]]
+    model = vector_hash(keys)
+    for k, m in zip(keys, model):
+        assert lib.orc_vector_hash(int(k[0]), int(k[1]), int(k[2])) == int(m)
+
+
+def test_bucket_chain_matches_this_libstdcxx(lib):
+    # _Prime_rehash_policy: first insert -> 13 buckets, then next_bkt(2*B)
+    assert lib.orc_next_bucket_count(12) == 13
+    for b, nb in zip(BUCKET_CHAIN[1:20], BUCKET_CHAIN[2:21]):
+        assert lib.orc_next_bucket_count(2 * b) == nb, (b, nb)
+
+
+def test_T_ls_prologue(lib):
+    # input_pc_pose prologue (map_awareness.cpp:184-186): T_ls = T_wa^-1 * T_wb * T_bs; yaw-only body
+    import ctypes as C
+    T_bs = (C.c_double * 7)(0.12, 0, 0, 0.5, -0.5, 0.5, -0.5)
+    out = (C.c_double * 3)()
+    T_wb = (C.c_double * 7)(*scenes.pose_from_xyz_yaw(5.0, -1.0, 1.2, 0.0))
+    lib.orc_transform_point(T_wb, T_bs, (C.c_double * 3)(0.3, -0.2, 2.0), out)
+    # optical frame (x right, y down, z forward) -> awareness frame (x forward, y left, z up), + 0.12 forward
+    assert list(out) == pytest.approx([2.12, -0.3, 0.2], abs=1e-12)
+    T_wb = (C.c_double * 7)(*scenes.pose_from_xyz_yaw(5.0, -1.0, 1.2, math.pi / 2))
+    lib.orc_transform_point(T_wb, T_bs, (C.c_double * 3)(0.0, 0.0, 1.0), out)
+    assert list(out) == pytest.approx([0.0, 1.12, 0.0], abs=1e-12)
+
+
+def test_single_point_hit_miss_sets():
+    """one pixel, straight ahead at 1.0 m: hit cell + ray walk follow map_awareness.cpp:135-171,241-275"""
+    cfg = config_cfg_a()
+    o = Oracle(cfg)
+    img = np.zeros((480, 640), dtype=np.uint16)
+    img[240, 320] = 1000
+    pose = scenes.pose_from_xyz_yaw(5.0, 0.0, 1.2, 0.0)
+    st = o.integrate_depth(img, pose)
+    assert (st.n_points, st.n_inside, st.n_cast) == (1, 1, 1)
+    keys, p = o.last_frame_hits()
+    # p_l = (1.12, 0, 0): rho_idx 11, phi_idx 0, z_idx floor(2.05/0.1) = 20; sigma(11) = 0.045 cells:
+    # the whole mass falls in the centre cell -> clamped to 0.999; 3*sigma < 1 -> no neighbours
+    assert keys.tolist() == [[11, 0, 20]] and p[0] == np.float32(0.999)
+    miss = o.last_frame_misses()
+    nrho, nphi = cfg.am_n_rho, 360
+    expect = sorted(20 * nrho * nphi + 0 * nrho + r for r in range(1, 11))  # r = 10..1, same z row (rate 0)
+    assert miss.tolist() == expect
+    m = o.export_map()
+    assert (m["occupancy"] == b"o").sum() == 0          # logit(0.999) = 2.9996 < 3.0 threshold
+    assert (m["occupancy"] == b"f").sum() == 10
+    lo = m["log_odds"][m["occupancy"] == b"f"]
+    assert np.all(lo == np.float32(-0.9))
+    assert m["log_odds"].max() == pytest.approx(2.99957108, abs=3e-7)
+    # second identical frame: hit cell 2*2.9996 -> clamps to 4.2 and turns 'o'; free cells go to -1.8
+    o.integrate_depth(img, pose)
+    m = o.export_map()
+    assert (m["occupancy"] == b"o").sum() == 1
+    assert m["log_odds"].max() == np.float32(4.2)
+    assert m["log_odds"].min() == pytest.approx(-1.8, abs=1e-6)
+    # the occupied voxel holds the hit cell centre (5 + 1.15 cos 0.5deg, 1.15 sin 0.5deg, 1.2 + 0) in the world
+    si, ci = np.argwhere(m["occupancy"] == b"o")[0]
+    g = m["glb"][si]
+    xyz = np.array([ci % 10, (ci // 10) % 10, ci // 100])
+    centre = g * 1.0 + xyz * 0.1 + 0.05
+    assert abs(centre[0] - 6.15) < 0.051 and abs(centre[1] - 0.01) < 0.051 and abs(centre[2] - 1.2) < 0.051
+    assert o.getOccupancy([centre])[0] == 0
+    assert o.getOccupancy([centre - [0.6, 0, 0]])[0] == 1
+    assert o.getOdd([centre])[0] == pytest.approx(1 - 1 / (1 + 10 ** 4.2), abs=1e-7)
+    grad = o.getOddGrad([centre + [0.01, 0.0, 0.0]])[0]
+    assert np.abs(grad).sum() > 0   # some neighbour has lower odds -> non-zero pseudo-gradient
+    assert o.getOccupancy([[6.0, 5.0, 1.2]])[0] == -1
+    assert o.getOdd([[100.0, 0.0, 0.0]])[0] == 0.5
+    # third frame: free cells saturate at log_odds_min (-2.0), still 'f'
+    o.integrate_depth(img, pose)
+    assert o.export_map()["log_odds"].min() == np.float32(-2.0)
+
+
+def test_out_of_range_ray_is_clamped_not_dropped():
+    """rho beyond n_Rho: no hit, ray cast from rho = n_Rho-1 with the stale rate (map_awareness.cpp:261-265)"""
+    cfg = config_cfg_a()
+    o = Oracle(cfg)
+    img = np.zeros((480, 640), dtype=np.uint16)
+    img[240, 320] = 20000  # 20 m
+    st = o.integrate_depth(img, scenes.pose_from_xyz_yaw(5.0, 0.0, 1.2, 0.0))
+    assert (st.n_inside, st.n_cast, st.n_hit_cells) == (0, 1, 0)
+    assert st.n_miss_cells == cfg.am_n_rho - 2   # r = 63..1
+
+
+def test_iteration_order_model_with_rehashes():
+    """the data-parallel ordering scheme (stamp -> sort -> re-sequence per rehash) reproduces
+    std::unordered_map's iteration order, including frames that cross several rehashes"""
+    cfg = config_cfg_a()
+    o = Oracle(cfg)
+    o.set_log_inserts(True)
+    B = 1
+    sizes = [(60, 80), (120, 160), (480, 640), (20, 20), (480, 640)]
+    for k, (r, c) in enumerate(sizes):
+        pose = scenes.corridor_trajectory_pose(30 * k)
+        img = scenes.corridor_depth_frame(cfg, pose, rows=r, cols=c, frame_idx=k)
+        st = o.integrate_depth(img, pose)
+        model, B = iteration_order(o.insert_log(), B)
+        keys, _ = o.last_frame_hits()
+        assert np.array_equal(model, keys), k
+        assert B == st.hit_bucket_count
+
+
+def test_set_free_and_grad():
+    cfg = config_cfg_a()
+    o = Oracle(cfg)
+    pose = scenes.pose_from_xyz_yaw(5.0, 0.0, 1.2, 0.0)
+    img = scenes.corridor_depth_frame(cfg, pose, rows=120, cols=160)
+    c = cfg.copy()
+    o.integrate_depth(img, pose)
+    o.integrate_depth(img, pose)
+    before = o.export_map()
+    o.setFree_map_in_bound([5.0, -0.5, 0.5], [7.0, 0.5, 1.5])
+    after = o.export_map()
+    changed = (before["occupancy"] != after["occupancy"]) | (before["log_odds"] != after["log_odds"])
+    assert changed.any()
+    assert np.all(after["occupancy"][changed] == b"f") and np.all(after["log_odds"][changed] == 0.0)
+    g = o.getOddGrad([[100.0, 100.0, 100.0]])
+    assert np.all(g == 0.0)   # unknown space everywhere: no lower neighbour -> zero vector (mlmap.h:293)
