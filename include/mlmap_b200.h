@@ -182,6 +182,8 @@ int mlm_flush_l2(mlm_handle h); /* writes a buffer larger than L2 (bench hygiene
 #define MLM_NUM_FRAME_KERNELS 7
 int mlm_set_profiling(mlm_handle h, int enable);
 int mlm_last_frame_kernel_ms(mlm_handle h, float ms[MLM_NUM_FRAME_KERNELS]);
+/* per-column phase clocks of the last k_column launch (only filled by -DMLM_PHASE_TIMING builds) */
+int mlm_debug_phase_cycles(mlm_handle h, long long *out, size_t cap);
 /* number of kernels launched by this handle since creation */
 int mlm_kernel_launch_count(mlm_handle h, int64_t *count);
 

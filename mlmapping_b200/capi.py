@@ -108,7 +108,7 @@ ABI_SYMBOLS = [
     "mlm_copy_to_device", "mlm_copy_to_host", "mlm_flush_l2", "mlm_kernel_launch_count",
     "mlm_last_frame_hits", "mlm_last_frame_misses", "mlm_export_map_count", "mlm_export_map",
     "mlm_debug_log10f", "mlm_set_profiling", "mlm_last_frame_kernel_ms", "mlm_sizeof_config",
-    "mlm_sizeof_frame_stats",
+    "mlm_sizeof_frame_stats", "mlm_debug_phase_cycles",
 ]
 FRAME_KERNELS = ["k_frame_begin", "k_project", "k_scatter", "k_column", "k_submaps", "k_fuse", "k_frame_end"]
 
@@ -177,6 +177,7 @@ def load_library() -> C.CDLL:
         "mlm_export_map_count": ([vp, C.POINTER(sz)], C.c_int),
         "mlm_export_map": ([vp, sz, vp, vp, vp, vp, vp, C.POINTER(sz)], C.c_int),
         "mlm_debug_log10f": ([vp, vp, sz, vp], C.c_int),
+        "mlm_debug_phase_cycles": ([vp, vp, sz], C.c_int),
         "mlm_set_profiling": ([vp, C.c_int], C.c_int),
         "mlm_last_frame_kernel_ms": ([vp, fp], C.c_int),
     }
@@ -407,6 +408,12 @@ class MLMap:
         ms = (C.c_float * len(FRAME_KERNELS))()
         self._check(self._lib.mlm_last_frame_kernel_ms(self._h, ms))
         return dict(zip(FRAME_KERNELS, [float(v) for v in ms]))
+
+    def debug_phase_cycles(self) -> np.ndarray:
+        n = int(360 / self.cfg.am_d_phi_deg)
+        out = np.zeros((n, 16), dtype=np.int64)
+        self._check(self._lib.mlm_debug_phase_cycles(self._h, out.ctypes.data, out.size))
+        return out
 
     def kernel_launch_count(self) -> int:
         v = C.c_int64()

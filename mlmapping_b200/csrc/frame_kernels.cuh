@@ -23,6 +23,17 @@ __device__ __forceinline__ int cvt_trunc_x86(double x) {
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// static_cast<int>(round(v)) for |v| < 2^31: std::round is half-away-from-zero.  v - trunc(v) is exact,
+// so this equals the libm result bit for bit (falls back to cvt_trunc_x86(round(v)) outside the range).
+__device__ __forceinline__ int round_to_int_x86(double v) {
+  if (!(v > -2147483000.0 && v < 2147483000.0)) return cvt_trunc_x86(round(v));
+  int zi = __double2int_rz(v);
+  double frac = v - (double)zi;
+  if (frac >= 0.5) zi++;
+  else if (frac <= -0.5) zi--;
+  return zi;
+}
+
 // warp-aggregated counter increment; returns this thread's slot
 __device__ __forceinline__ int agg_inc(int *ctr) {
   unsigned mask = __activemask();
@@ -361,22 +372,25 @@ __device__ __forceinline__ uint64_t contrib_key(int cell, uint32_t t, int subste
 // One stable LSD radix pass over 8 key bits for the whole CTA (src -> dst), keys in shared or
 // global memory.  Warp w owns a contiguous chunk; cnt[digit*W + w] after the exclusive scan is the
 // output cursor of (digit, warp), so order inside a digit is (warp, position) = input order.
+constexpr int kCntStride = kColWarps + 1;                 // +1: (digit, warp) counters of one warp hit 32 banks
+constexpr int kCntTotal = kRadixDigits * kCntStride;
+constexpr int kCntPerThread = (kCntTotal + kColThreads - 1) / kColThreads;
 __device__ __forceinline__ void radix_pass(const uint64_t *src, uint64_t *dst, int n, int shift, uint32_t *cnt,
                                            uint32_t *warp_sums) {
   const int W = kColWarps, w = threadIdx.x >> 5, lane = lane_id(), tid = threadIdx.x;
   const int chunk = (((n + W - 1) / W) + 31) & ~31;
   const int beg = min(w * chunk, n), end = min(beg + chunk, n);
-  for (int i = tid; i < kRadixDigits * W; i += kColThreads) cnt[i] = 0;
+  for (int i = tid; i < kCntTotal; i += kColThreads) cnt[i] = 0;
   __syncthreads();
   for (int i = beg + lane; i < end; i += 32)
-    atomicAdd(&cnt[(int)((src[i] >> shift) & (kRadixDigits - 1)) * W + w], 1u);
+    atomicAdd(&cnt[(int)((src[i] >> shift) & (kRadixDigits - 1)) * kCntStride + w], 1u);
   __syncthreads();
-  // exclusive scan over the kRadixDigits*W counters: 8 consecutive entries per thread
-  constexpr int E = kRadixDigits * W / kColThreads;
-  uint32_t v[E], sum = 0;
+  // exclusive scan over the counters in (digit, warp) order: kCntPerThread consecutive entries per thread
+  uint32_t v[kCntPerThread], sum = 0;
 #pragma unroll
-  for (int e = 0; e < E; e++) {
-    v[e] = cnt[E * tid + e];
+  for (int e = 0; e < kCntPerThread; e++) {
+    const int idx = kCntPerThread * tid + e;
+    v[e] = idx < kCntTotal ? cnt[idx] : 0u;
     sum += v[e];
   }
   uint32_t incl = sum;
@@ -399,8 +413,9 @@ __device__ __forceinline__ void radix_pass(const uint64_t *src, uint64_t *dst, i
   __syncthreads();
   uint32_t run = warp_sums[w] + incl - sum;
 #pragma unroll
-  for (int e = 0; e < E; e++) {
-    cnt[E * tid + e] = run;
+  for (int e = 0; e < kCntPerThread; e++) {
+    const int idx = kCntPerThread * tid + e;
+    if (idx < kCntTotal) cnt[idx] = run;
     run += v[e];
   }
   __syncthreads();
@@ -411,9 +426,9 @@ __device__ __forceinline__ void radix_pass(const uint64_t *src, uint64_t *dst, i
     const int d = ok ? (int)((key >> shift) & (kRadixDigits - 1)) : kRadixDigits + lane;
     const unsigned peers = __match_any_sync(0xffffffffu, d);
     const int rank = __popc(peers & ((1u << lane) - 1));
-    if (ok) dst[cnt[d * W + w] + rank] = key;
+    if (ok) dst[cnt[d * kCntStride + w] + rank] = key;
     __syncwarp();
-    if (ok && rank == 0) cnt[d * W + w] += __popc(peers);
+    if (ok && rank == 0) cnt[d * kCntStride + w] += __popc(peers);
     __syncwarp();
   }
   __syncthreads();
@@ -434,25 +449,56 @@ __device__ __forceinline__ void touch_subbox(const MapParams &P, const FramePara
   }
 }
 
-// walk one ray toward the axis, reference src/map_awareness.cpp:261-275.  All 32 lanes cooperate:
-// lane l owns rho step r = 32*w + l, lanes that land in the same z row merge into one atomicOr.
-__device__ __forceinline__ void walk_ray(const MapParams &P, uint32_t *s_miss, int rho, int z) {
-  double rate = ray_rate(P, rho, z);
+// Ray walk toward the axis, reference src/map_awareness.cpp:243-275, split in two so that the scalar
+// part (rate division + range clamp, once per ray) runs one ray per LANE, and only the marking of
+// the <= nRho-2 cells runs one ray per WARP.
+struct WalkStart {
+  double rate;
+  int rho, z;  // start cell after the clamp of :261-265
+};
+__device__ __forceinline__ WalkStart walk_prepare(const MapParams &P, int rho, int z) {
+  WalkStart ws;
+  ws.rate = ray_rate(P, rho, z);
   if (rho >= P.nRho) {
-    z = cvt_trunc_x86(round((double)z - (double)(rho - P.nRho + 1) * rate));
+    z = round_to_int_x86((double)z - (double)(rho - P.nRho + 1) * ws.rate);
     rho = P.nRho - 1;
   }
+  ws.rho = rho;
+  ws.z = z;
+  return ws;
+}
+// All 32 lanes cooperate on one ray: lane l owns rho step r = 32*w + l; lanes that land in the same
+// z row merge into one shared-memory atomicOr (warp-aggregated by __match_any_sync).
+__device__ __forceinline__ void walk_mark(const MapParams &P, uint32_t *s_miss, double rate, int rho, int z) {
   const int lane = lane_id();
+  const double zd = (double)z;
   for (int w = (rho - 1) >> 5; w >= 0; --w) {
     int r = (w << 5) + lane;
     bool valid = r >= 1 && r <= rho - 1;
     int zc = 0;
     if (valid) {
-      zc = cvt_trunc_x86(round((double)z - (double)(rho - r) * rate));
+      zc = round_to_int_x86(zd - (double)(rho - r) * rate);
       valid = zc >= 0 && zc < P.nZ;
     }
     unsigned peers = __match_any_sync(0xffffffffu, valid ? zc : -1 - lane);
     if (valid && lane == __ffs(peers) - 1) atomicOr(&s_miss[zc * P.words_per_row + w], peers);
+  }
+}
+// one prepared ray per lane (need = this lane has one); the warp marks them one after the other
+__device__ __forceinline__ void walk_batch(const MapParams &P, uint32_t *s_miss, bool need, int rho, int z) {
+  WalkStart ws;
+  ws.rate = 0.0;
+  ws.rho = 0;
+  ws.z = 0;
+  if (need) ws = walk_prepare(P, rho, z);
+  unsigned todo = __ballot_sync(0xffffffffu, need);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const double rate = __shfl_sync(0xffffffffu, ws.rate, src);
+    const int r0 = __shfl_sync(0xffffffffu, ws.rho, src);
+    const int z0 = __shfl_sync(0xffffffffu, ws.z, src);
+    walk_mark(P, s_miss, rate, r0, z0);
   }
 }
 
@@ -469,6 +515,17 @@ __device__ __forceinline__ void compact_bits(const uint32_t *bm, int w0, int w1,
   }
 }
 
+// bytes of k_column's shared memory in front of the two key buffers
+__host__ __device__ inline size_t col_smem_prefix_bytes(int col_words, int nRho) {
+  return (((size_t)2 * col_words + kCntTotal + kColWarps + (size_t)kOddsRows * nRho + nRho) * 4 + 15) & ~(size_t)15;
+}
+
+#ifdef MLM_PHASE_TIMING
+#define MLM_PHASE(i) do { __syncthreads(); if (threadIdx.x == 0) D.debug_cycles[blockIdx.x * 16 + (i)] = clock64(); } while (0)
+#else
+#define MLM_PHASE(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBuffers D) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   const FrameParams &F = *D.fp;
@@ -482,22 +539,29 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   }
   const int off = D.phi_off[phi];
   const RayRecord *recs = D.rec_col + off;
+  MLM_PHASE(0);
 
-  // shared memory: [miss bitmap][end-cell bitmap][radix counters][warp sums][keys A][keys B]
+  // shared memory: [miss bitmap][end-cell bitmap][radix counters][warp sums][odds table][k_reach][keys A][keys B]
   uint32_t *s_miss = reinterpret_cast<uint32_t *>(s_raw);
   uint32_t *s_end = s_miss + P.col_words;
   uint32_t *s_cnt = s_end + P.col_words;
-  uint32_t *s_wsum = s_cnt + kRadixDigits * kColWarps;
-  uint64_t *s_keys = reinterpret_cast<uint64_t *>(
-      s_raw + ((((size_t)2 * P.col_words + kRadixDigits * kColWarps + kColWarps) * 4 + 15) & ~(size_t)15));
+  uint32_t *s_wsum = s_cnt + kCntTotal;
+  float *s_odds = reinterpret_cast<float *>(s_wsum + kColWarps);
+  int *s_reach = reinterpret_cast<int *>(s_odds + kOddsRows * P.nRho);
+  uint64_t *s_keys = reinterpret_cast<uint64_t *>(s_raw + col_smem_prefix_bytes(P.col_words, P.nRho));
+  for (int i = tid; i < kOddsRows * P.nRho; i += blockDim.x) s_odds[i] = __ldg(&P.odds_table[i]);
+  for (int i = tid; i < P.nRho; i += blockDim.x) s_reach[i] = __ldg(&P.k_reach[i]);
   __shared__ int s_nk;
   __shared__ int s_nmiss;
   __shared__ int s_bound;
+  __shared__ int s_nhead;
+  __shared__ int s_next;
   for (int i = tid; i < 2 * P.col_words; i += blockDim.x) s_miss[i] = 0;
   if (tid == 0) {
     s_nk = 0;
     s_nmiss = 0;
     s_bound = 0;
+    s_next = 0;
   }
   __syncthreads();
   // upper bound of this column's contributions: 1 + 2*min(K(rho), nRho-1-rho) per inside record
@@ -505,7 +569,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
     int bound = 0;
     for (int i = tid; i < n_c; i += blockDim.x) {
       RayRecord rc = recs[i];
-      if (rc.phi_flags & kRecInside) bound += 1 + 2 * min(P.k_reach[rc.rho], P.nRho - 1 - rc.rho);
+      if (rc.phi_flags & kRecInside) bound += 1 + 2 * min(s_reach[rc.rho], P.nRho - 1 - rc.rho);
     }
     for (int ofs = 16; ofs > 0; ofs >>= 1) bound += __shfl_xor_sync(0xffffffffu, bound, ofs);
     if (lane_id() == 0 && bound) atomicAdd(&s_bound, bound);
@@ -516,6 +580,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   uint64_t *keys = in_smem ? s_keys : D.col_scratch + (size_t)2 * off * P.contrib_per_point;
   uint64_t *keys_alt = in_smem ? s_keys + P.sort_cap_smem : keys + (size_t)n_c * P.contrib_per_point;
   const int tbits = F.tbits;
+  MLM_PHASE(1);
   // (a) contributions, update_hits src/map_awareness.cpp:135-171
   for (int i = tid; i < n_c; i += blockDim.x) {
     RayRecord rc = recs[i];
@@ -524,13 +589,13 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
     const int reps = (int)((rc.phi_flags >> kRecCountShift) & kRecCountMask);
     if (P.visibility_check) atomicOr(&s_end[z * P.words_per_row + (rho >> 5)], 1u << (rho & 31));
     double rate = ray_rate(P, rho, z);
-    int K = P.k_reach[rho];
+    int K = s_reach[rho];
     int cnt = 1;
     int zp[kDiffRange], zm[kDiffRange];
     int dmax = 0;
     for (int d = 1; d <= K && rho + d < P.nRho; d++) {
-      zp[d - 1] = cvt_trunc_x86(round((double)z + (double)d * rate));
-      zm[d - 1] = cvt_trunc_x86(round((double)z - (double)d * rate));
+      zp[d - 1] = round_to_int_x86((double)z + (double)d * rate);
+      zm[d - 1] = round_to_int_x86((double)z - (double)d * rate);
       cnt += (zp[d - 1] >= 0 && zp[d - 1] < P.nZ) + (zm[d - 1] >= 0 && zm[d - 1] < P.nZ);
       dmax = d;
     }
@@ -544,6 +609,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   __syncthreads();
   const int n_k = s_nk;
 
+  MLM_PHASE(2);
   // (b) stable LSD radix sort by (cell, t): bits [12, 12 + tbits + cell_bits)
   {
     const int hi_bit = 12 + tbits + P.cell_bits;
@@ -556,60 +622,132 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   }
   const int cell_shift = 12 + tbits;
   const uint64_t t_mask = (1ull << tbits) - 1;
-
-  // (c) ordered fold per cell + staging of the distinct hit keys
-  for (int i = tid; i < n_k; i += blockDim.x) {
-    uint64_t k0 = keys[i];
-    int cell = (int)(k0 >> cell_shift);
-    if (i > 0 && (int)(keys[i - 1] >> cell_shift) == cell) continue;  // not the first contribution of its cell
-    const int zk = cell / P.nRho, rk = cell - zk * P.nRho;
-    float p = 0.f;
-    bool first = true;
-    for (int j = i; j < n_k && p != 1.0f; j++) {
-      uint64_t kj = keys[j];
-      if ((int)(kj >> cell_shift) != cell) break;
-      int s = (int)((kj >> 7) & 31);
-      int reps = (int)(kj & 127);
-      int d = s == 0 ? 0 : ((s & 1) ? (s + 1) >> 1 : -(s >> 1));
-      float odd = __ldg(&P.odds_table[(kDiffRange + d) * P.nRho + (rk - d)]);
-      for (int r = 0; r < reps; r++) {
-        float np_ = first ? odd : odds_combine(p, odd);
-        bool stuck = !first && np_ == p;  // fixed point of this odd: the rest of the run is a no-op
-        first = false;
-        p = np_;
-        if (stuck || p == 1.0f) break;    // p == 1: 1 - (1-1)*(1-odd) == 1 for every later contribution
+  MLM_PHASE(3);
+  // (c1) ordered list of segment heads (first contribution of every distinct cell) in the idle
+  // ping-pong buffer: s_head[h] = index into keys, s_head_p[h] = folded probability
+  uint32_t *s_head = reinterpret_cast<uint32_t *>(keys_alt);
+  uint32_t *s_head_p = s_head + n_k;
+  {
+    const int W = kColWarps, w = tid >> 5, lane = lane_id();
+    const int chunk = (((n_k + W - 1) / W) + 31) & ~31;
+    const int beg = min(w * chunk, n_k), end = min(beg + chunk, n_k);
+    int cnt = 0;
+    for (int base = beg; base < end; base += 32) {
+      const int i = base + lane;
+      const bool head = i < end && (i == 0 || (keys[i - 1] >> cell_shift) != (keys[i] >> cell_shift));
+      cnt += __popc(__ballot_sync(0xffffffffu, head));
+    }
+    if (lane == 0) s_wsum[w] = (uint32_t)cnt;
+    __syncthreads();
+    if (w == 0) {
+      uint32_t sv = lane < W ? s_wsum[lane] : 0, si = sv;
+#pragma unroll
+      for (int ofs = 1; ofs < 32; ofs <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, si, ofs);
+        if (lane >= ofs) si += t;
       }
+      if (lane < W) s_wsum[lane] = si - sv;
+      if (lane == W - 1) s_nhead = (int)si;
     }
-    const uint32_t stamp = (uint32_t)((((k0 >> 12) & t_mask) << 5) | ((k0 >> 7) & 31));  // t*32 + substep of the first insert
-    const int idx = agg_inc(&D.fc->n_hit);
-    if (idx >= P.max_hits) {
-      D.fc->error = kErrCapacity;
-      continue;
+    __syncthreads();
+    int pos = (int)s_wsum[w];
+    for (int base = beg; base < end; base += 32) {
+      const int i = base + lane;
+      const bool head = i < end && (i == 0 || (keys[i - 1] >> cell_shift) != (keys[i] >> cell_shift));
+      const unsigned b = __ballot_sync(0xffffffffu, head);
+      if (head) s_head[pos + __popc(b & ((1u << lane) - 1))] = (uint32_t)i;
+      pos += __popc(b);
     }
-    D.hit_key[idx] = (zk * P.nPhi + phi) * P.nRho + rk;  // mapIdx, map_awareness.h:81-84
-    D.hit_p[idx] = p;
-    D.hit_t[idx] = stamp;
-    // bucket activation stamp (libstdc++ iteration order)
-    atomicMin(&D.act[libstdcxx_bucket(vector_hash3(rk, phi, zk), F.bucket_count)], stamp);
-    // p_w = T_wa * centre  (identity rotation: one add per axis), src/map_local.cpp:151
-    double2 cxy = __ldg(&P.centre_xy[phi * P.nRho + rk]);
-    CellRef cr = locate_cell(P, cxy.x + F.t_wa[0], cxy.y + F.t_wa[1], __ldg(&P.centre_z[zk]) + F.t_wa[2]);
-    int lv = lvg_index(P, F, cr);
-    if (lv < 0) {
-      D.fc->error = kErrInternal;
-      D.hit_next[idx] = kLvgEmpty;
-      continue;
+  }
+  __syncthreads();
+  // (c2) update_odds_hashmap fold: one thread per distinct cell, cells claimed dynamically so long
+  // chains do not serialise behind each other.  The chain p <- 1-(1-p)(1-odd) is inherently ordered;
+  // the next contribution (key + odds-table entry, both in shared memory) is fetched while the
+  // current one is folded.
+  {
+    const int n_head = s_nhead;
+    for (;;) {
+      const int h = atomicAdd(&s_next, 1);
+      if (h >= n_head) break;
+      int j = (int)s_head[h];
+      uint64_t kj = keys[j];
+      const int cell = (int)(kj >> cell_shift);
+      const int rk = cell - (cell / P.nRho) * P.nRho;
+      int sstep = (int)((kj >> 7) & 31);
+      int d = sstep == 0 ? 0 : ((sstep & 1) ? (sstep + 1) >> 1 : -(sstep >> 1));
+      float odd = s_odds[(kDiffRange + d) * P.nRho + (rk - d)];
+      int reps = (int)(kj & 127);
+      float p = odd;  // first insert: hit_idx_odds_hashmap[key] = odd
+      reps--;
+      for (;;) {
+        // prefetch the next contribution of this cell (independent of p)
+        const bool more = j + 1 < n_k && (int)(keys[j + 1] >> cell_shift) == cell;
+        float odd_n = 0.f;
+        int reps_n = 0;
+        if (more) {
+          const uint64_t kn = keys[j + 1];
+          const int sn = (int)((kn >> 7) & 31);
+          const int dn = sn == 0 ? 0 : ((sn & 1) ? (sn + 1) >> 1 : -(sn >> 1));
+          odd_n = s_odds[(kDiffRange + dn) * P.nRho + (rk - dn)];
+          reps_n = (int)(kn & 127);
+        }
+        for (int r = 0; r < reps; r++) {
+          const float np_ = odds_combine(p, odd);
+          if (np_ == p) break;  // fixed point of this odd (includes p == 1): the rest of the run is a no-op
+          p = np_;
+        }
+        if (!more || p == 1.0f) break;  // p == 1: 1 - (1-1)*(1-odd) == 1 for every later contribution
+        odd = odd_n;
+        reps = reps_n;
+        j++;
+      }
+      s_head_p[h] = __float_as_uint(p);
     }
-    int old = atomicExch(&D.lvg_head[lv], idx);
-    D.hit_next[idx] = old;
-    if (old == kLvgEmpty) {
-      int tp = agg_inc(&D.fc->n_touched);
-      if (tp < P.max_touched) D.touched[tp] = (uint32_t)lv | kTouchedHitTag; else D.fc->error = kErrCapacity;
+  }
+  __syncthreads();
+  MLM_PHASE(4);
+  {
+    const int n_head = s_nhead;
+    int base_idx = 0;
+    if (tid == 0) s_nk = atomicAdd(&D.fc->n_hit, n_head);  // one global reservation per column
+    __syncthreads();
+    base_idx = s_nk;
+    for (int k = tid; k < n_head; k += blockDim.x) {
+      const uint64_t k0 = keys[s_head[k]];
+      const int cell = (int)(k0 >> cell_shift);
+      const int zk = cell / P.nRho, rk = cell - zk * P.nRho;
+      const uint32_t stamp = (uint32_t)((((k0 >> 12) & t_mask) << 5) | ((k0 >> 7) & 31));  // t*32 + substep of the first insert
+      const int idx = base_idx + k;
+      if (idx >= P.max_hits) {
+        D.fc->error = kErrCapacity;
+        continue;
+      }
+      D.hit_key[idx] = (zk * P.nPhi + phi) * P.nRho + rk;  // mapIdx, map_awareness.h:81-84
+      D.hit_p[idx] = __uint_as_float(s_head_p[k]);
+      D.hit_t[idx] = stamp;
+      // bucket activation stamp (libstdc++ iteration order)
+      atomicMin(&D.act[libstdcxx_bucket(vector_hash3(rk, phi, zk), F.bucket_count)], stamp);
+      // p_w = T_wa * centre  (identity rotation: one add per axis), src/map_local.cpp:151
+      double2 cxy = __ldg(&P.centre_xy[phi * P.nRho + rk]);
+      CellRef cr = locate_cell(P, cxy.x + F.t_wa[0], cxy.y + F.t_wa[1], __ldg(&P.centre_z[zk]) + F.t_wa[2]);
+      int lv = lvg_index(P, F, cr);
+      if (lv < 0) {
+        D.fc->error = kErrInternal;
+        D.hit_next[idx] = kLvgEmpty;
+        continue;
+      }
+      int old = atomicExch(&D.lvg_head[lv], idx);
+      D.hit_next[idx] = old;
+      if (old == kLvgEmpty) {
+        int tp = agg_inc(&D.fc->n_touched);
+        if (tp < P.max_touched) D.touched[tp] = (uint32_t)lv | kTouchedHitTag; else D.fc->error = kErrCapacity;
+      }
+      touch_subbox(P, F, D, cr.g);
     }
-    touch_subbox(P, F, D, cr.g);
   }
   __syncthreads();
 
+  MLM_PHASE(5);
   // The sorted keys are dead from here on: the key area becomes scratch for compacted cell lists.
   uint32_t *s_list = reinterpret_cast<uint32_t *>(s_keys);
   const int list_cap = P.sort_cap_smem * 4;            // 32-bit entries in the two key buffers
@@ -625,31 +763,53 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
       compact_bits(s_end, w0, min(w0 + words_per_chunk, P.col_words), s_list, &s_nk);
       __syncthreads();
       const int n_list = s_nk;
-      for (int k = warp; k < n_list; k += nwarps) {
-        const uint32_t e = s_list[k];
-        const int wi = (int)(e >> 5), z = wi / P.words_per_row, wr = wi - z * P.words_per_row;
-        walk_ray(P, s_miss, (wr << 5) + (int)(e & 31), z);
+      // entry (it*32 + lane)*nwarps + warp: every warp gets the same share of the list
+      for (int it = 0; it * 32 * nwarps < n_list; it++) {
+        const int k = (it * 32 + lane_id()) * nwarps + warp;
+        int rho = 0, z = 0;
+        if (k < n_list) {
+          const uint32_t e = s_list[k];
+          const int wi = (int)(e >> 5), wr = wi - (wi / P.words_per_row) * P.words_per_row;
+          z = wi / P.words_per_row;
+          rho = (wr << 5) + (int)(e & 31);
+        }
+        walk_batch(P, s_miss, k < n_list, rho, z);
       }
       __syncthreads();
     }
-    // castable points outside the awareness range walk from the clamped cell (:261-265)
-    for (int base = warp * 32; base < n_c; base += nwarps * 32) {
-      int i = base + lane_id();
+    // castable points outside the awareness range walk from the clamped cell (:261-265).  Records
+    // with identical (rho,z) repeat the same walk: drop them through a small shared-memory set
+    // (walks are idempotent, so a missed duplicate only costs time).
+    int hcap = 1024;
+    while (hcap * 2 <= list_cap && hcap < 16384) hcap <<= 1;
+    for (int i = tid; i < hcap; i += blockDim.x) s_list[i] = 0xffffffffu;
+    __syncthreads();
+    for (int it = 0; it * 32 * nwarps < n_c; it++) {
+      const int i = (it * 32 + lane_id()) * nwarps + warp;
       RayRecord rc;
       rc.phi_flags = kRecInside;
       if (i < n_c) rc = recs[i];
-      unsigned todo = __ballot_sync(0xffffffffu, !(rc.phi_flags & kRecInside));
-      while (todo) {
-        int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        int rho = __shfl_sync(0xffffffffu, rc.rho, src);
-        int z = __shfl_sync(0xffffffffu, rc.z, src);
-        walk_ray(P, s_miss, rho, z);
+      bool need = !(rc.phi_flags & kRecInside);
+      if (need && rc.rho < 65536 && rc.z >= -32768 && rc.z < 32768) {
+        const uint32_t key = ((uint32_t)rc.rho << 16) | (uint32_t)(rc.z + 32768);
+        uint32_t slot = (key * 2654435761u) >> 7;
+        for (int probe = 0; probe < 8; probe++) {
+          slot &= (uint32_t)(hcap - 1);
+          uint32_t old = atomicCAS(&s_list[slot], 0xffffffffu, key);
+          if (old == 0xffffffffu) break;
+          if (old == key) {
+            need = false;
+            break;
+          }
+          slot++;
+        }
       }
+      walk_batch(P, s_miss, need, rc.rho, rc.z);
     }
   }
   __syncthreads();
 
+  MLM_PHASE(6);
   // (e) distinct miss cells -> voxel grid staging (one cell per thread); bitmap to global for export
   for (int wi = tid; wi < P.col_words; wi += blockDim.x) g_miss[wi] = s_miss[wi];
   for (int w0 = 0; w0 < P.col_words; w0 += words_per_chunk) {
@@ -679,6 +839,10 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
     if (tid == 0) s_nmiss += n_list;
     __syncthreads();
   }
+  MLM_PHASE(7);
+#ifdef MLM_PHASE_TIMING
+  if (tid == 0) { D.debug_cycles[blockIdx.x * 16 + 10] = n_c; D.debug_cycles[blockIdx.x * 16 + 11] = n_k; }
+#endif
   if (tid == 0 && s_nmiss) atomicAdd(&D.fc->n_miss, s_nmiss);
 }
 

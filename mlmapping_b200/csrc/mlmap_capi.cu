@@ -640,8 +640,7 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   // column kernel shared memory: two column bitmaps + the largest power-of-two sort buffer that fits
   int max_optin = 0;
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-  const size_t bm_bytes =
-      ((((size_t)2 * P.col_words + (size_t)kRadixDigits * kColWarps + kColWarps) * 4 + 15) & ~(size_t)15);
+  const size_t bm_bytes = col_smem_prefix_bytes(P.col_words, P.nRho);
   long long avail = (long long)max_optin - 1024 - (long long)bm_bytes;
   if (avail < 32 * 1024) {
     delete h;
@@ -732,6 +731,8 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   TRY(dev_alloc(h, &D.pool_occ, (size_t)P.pool_blocks * P.cell_stride));
   TRY(dev_alloc(h, &D.pool_inf, (size_t)P.pool_blocks * P.cell_stride));
   TRY(dev_alloc(h, &D.cum, 4));
+  TRY(dev_alloc(h, &D.debug_cycles, (size_t)P.nPhi * 16));
+  CUDA_TRY_H(cudaMemset(D.debug_cycles, 0, (size_t)P.nPhi * 16 * sizeof(long long)));
   TRY(dev_alloc(h, &h->d_ticket, 1));
   h->sort_cap = P.max_hits;
   const size_t sort_pad = (size_t)next_pow2(P.max_hits);
@@ -987,6 +988,12 @@ int mlm_set_profiling(mlm_handle h, int enable) {
 int mlm_last_frame_kernel_ms(mlm_handle h, float ms[MLM_NUM_FRAME_KERNELS]) {
   if (!h || !ms) return MLM_ERR_INVALID_ARG;
   for (int i = 0; i < MLM_NUM_FRAME_KERNELS; i++) ms[i] = h->kms[i];
+  return MLM_OK;
+}
+int mlm_debug_phase_cycles(mlm_handle h, long long *out, size_t cap) {
+  if (!h || !out) return MLM_ERR_INVALID_ARG;
+  size_t n = std::min(cap, (size_t)h->P.nPhi * 16);
+  CUDA_TRY(cudaMemcpy(out, h->D.debug_cycles, n * sizeof(long long), cudaMemcpyDeviceToHost));
   return MLM_OK;
 }
 int mlm_kernel_launch_count(mlm_handle h, int64_t *count) {

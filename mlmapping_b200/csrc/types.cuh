@@ -128,6 +128,7 @@ struct DeviceBuffers {
   char *pool_occ;         // [pool_blocks*cells]
   char *pool_inf;         // [pool_blocks*cells]
   int64_t *cum;           // [0]=ram_expand_cnt [1]=obs_cnt [2]=n_submaps
+  long long *debug_cycles; // [nPhi*16] per-column phase clocks (MLM_PHASE_TIMING builds only)
 };
 
 }  // namespace mlm
