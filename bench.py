@@ -244,14 +244,19 @@ def main():
 
     # ---------------- pass 3: end to end through the host-buffer C-ABI call ("e2e") ----------------
     m = MLMap(cfg, device=local_rank)
+    pinned = []
+    for f in frames:  # inputs live in pinned host memory (bench contract); the H2D copy is inside the call
+        pf = m.pinned_array(f.shape, np.uint16)
+        pf[...] = f
+        pinned.append(pf)
     for k in range(args.warmup):
-        m.integrate_depth(frames[k], poses[k])
+        m.integrate_depth(pinned[k], poses[k])
     barrier()
     e2e_s, e2e_rays = 0.0, 0
     for k in range(args.warmup, total):
         m.flush_l2()
         t0 = time.perf_counter()
-        st = m.integrate_depth(frames[k], poses[k])
+        st = m.integrate_depth(pinned[k], poses[k])
         e2e_s += time.perf_counter() - t0
         e2e_rays += st.n_points
     barrier()

@@ -172,14 +172,17 @@ int mlm_timer_stop_ms(mlm_handle h, float *ms); /* records + synchronises; ms si
 /* device scratch helpers for harnesses that keep inputs resident */
 int mlm_device_alloc(mlm_handle h, size_t bytes, void **d_ptr);
 int mlm_device_free(mlm_handle h, void *d_ptr);
+/* page-locked host buffers: images / point arrays placed here are DMA'd without the staging copy */
+int mlm_host_alloc(mlm_handle h, size_t bytes, void **ptr);
+int mlm_host_free(mlm_handle h, void *ptr);
 int mlm_copy_to_device(mlm_handle h, void *d_dst, const void *src, size_t bytes);
 int mlm_copy_to_host(mlm_handle h, void *dst, const void *d_src, size_t bytes);
 int mlm_flush_l2(mlm_handle h); /* writes a buffer larger than L2 (bench hygiene) */
 /* per-kernel timing of the frame pipeline (CUDA events between launches on the handle's stream).
  * enable=1 records events in every following frame; mlm_last_frame_kernel_ms returns the durations
  * of the MLM_NUM_FRAME_KERNELS stages of the last frame in launch order:
- * 0 k_frame_begin, 1 k_project, 2 k_scatter, 3 k_column, 4 k_submaps, 5 k_fuse, 6 k_frame_end */
-#define MLM_NUM_FRAME_KERNELS 7
+ * 0 k_project, 1 k_scatter, 2 k_column, 3 k_fuse */
+#define MLM_NUM_FRAME_KERNELS 4
 int mlm_set_profiling(mlm_handle h, int enable);
 int mlm_last_frame_kernel_ms(mlm_handle h, float ms[MLM_NUM_FRAME_KERNELS]);
 /* per-column phase clocks of the last k_column launch (only filled by -DMLM_PHASE_TIMING builds) */

@@ -108,9 +108,9 @@ ABI_SYMBOLS = [
     "mlm_copy_to_device", "mlm_copy_to_host", "mlm_flush_l2", "mlm_kernel_launch_count",
     "mlm_last_frame_hits", "mlm_last_frame_misses", "mlm_export_map_count", "mlm_export_map",
     "mlm_debug_log10f", "mlm_set_profiling", "mlm_last_frame_kernel_ms", "mlm_sizeof_config",
-    "mlm_sizeof_frame_stats", "mlm_debug_phase_cycles",
+    "mlm_sizeof_frame_stats", "mlm_debug_phase_cycles", "mlm_host_alloc", "mlm_host_free",
 ]
-FRAME_KERNELS = ["k_frame_begin", "k_project", "k_scatter", "k_column", "k_submaps", "k_fuse", "k_frame_end"]
+FRAME_KERNELS = ["k_project", "k_scatter", "k_column", "k_fuse"]
 
 _lib = None
 
@@ -168,6 +168,8 @@ def load_library() -> C.CDLL:
         "mlm_timer_stop_ms": ([vp, fp], C.c_int),
         "mlm_device_alloc": ([vp, sz, C.POINTER(vp)], C.c_int),
         "mlm_device_free": ([vp, vp], C.c_int),
+        "mlm_host_alloc": ([vp, sz, C.POINTER(vp)], C.c_int),
+        "mlm_host_free": ([vp, vp], C.c_int),
         "mlm_copy_to_device": ([vp, vp, vp, sz], C.c_int),
         "mlm_copy_to_host": ([vp, vp, vp, sz], C.c_int),
         "mlm_flush_l2": ([vp], C.c_int),
@@ -389,6 +391,15 @@ class MLMap:
 
     def device_free(self, ptr: int):
         self._check(self._lib.mlm_device_free(self._h, ptr))
+
+    def pinned_array(self, shape, dtype) -> np.ndarray:
+        """numpy view of page-locked host memory (never freed before the handle is closed)"""
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape)) * dt.itemsize
+        p = C.c_void_p()
+        self._check(self._lib.mlm_host_alloc(self._h, max(n, 16), C.byref(p)))
+        buf = (C.c_char * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=dt).reshape(shape)
 
     def to_device(self, arr: np.ndarray) -> int:
         a = np.ascontiguousarray(arr)

@@ -148,23 +148,6 @@ __device__ __forceinline__ int ht_find(const MapParams &P, const DeviceBuffers &
   return -1;
 }
 
-// ---- K0: per-frame reset ---------------------------------------------------------------------------
-__global__ void k_frame_begin(MapParams P, DeviceBuffers D) {
-  int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  int nth = gridDim.x * blockDim.x;
-  uint32_t B = D.fp->bucket_count;
-  for (uint32_t i = tid; i < B; i += nth) D.act[i] = 0xffffffffu;
-  for (int i = tid; i < P.nPhi; i += nth) {
-    D.phi_hist[i] = 0;
-    D.phi_cursor[i] = 0;
-  }
-  if (tid == 0) {
-    FrameCounters z;
-    memset(&z, 0, sizeof(z));
-    *D.fc = z;
-  }
-}
-
 // ---- K1: projection + transform + cylindrical index ------------------------------------------------
 // One thread per point.  Output: a RayRecord per castable / inside point (in point order) and the
 // per-phi-column histogram used to group the records by column.
@@ -206,14 +189,16 @@ __device__ __forceinline__ void point_to_record(const MapParams &P, const FrameP
   }
 }
 
-// exclusive scan of phi_hist -> phi_off by the last CTA to finish K1
-__device__ void scan_phi_hist_last_block(const MapParams &P, DeviceBuffers &D, int *s_tmp /*[blockDim]*/) {
+// exclusive scan of the per-column record histogram into shared memory (every k_scatter CTA needs the
+// offsets of the columns it writes to; CTA 0 also publishes them for k_column)
+__device__ void scan_phi_hist(const MapParams &P, const DeviceBuffers &D, int *s_off, int *s_tmp /*[blockDim]*/,
+                              bool publish) {
   __shared__ int s_carry;
   if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
   for (int base = 0; base < P.nPhi; base += blockDim.x) {
     int i = base + threadIdx.x;
-    int v = i < P.nPhi ? __ldcg(&D.phi_hist[i]) : 0;
+    int v = i < P.nPhi ? D.phi_hist[i] : 0;
     s_tmp[threadIdx.x] = v;
     __syncthreads();
     for (int ofs = 1; ofs < blockDim.x; ofs <<= 1) {  // Hillis-Steele inclusive scan
@@ -223,26 +208,30 @@ __device__ void scan_phi_hist_last_block(const MapParams &P, DeviceBuffers &D, i
       __syncthreads();
     }
     int incl = s_tmp[threadIdx.x];
-    if (i < P.nPhi) D.phi_off[i] = s_carry + incl - v;
+    if (i < P.nPhi) {
+      s_off[i] = s_carry + incl - v;
+      if (publish) D.phi_off[i] = s_carry + incl - v;
+    }
     __syncthreads();
     if (threadIdx.x == blockDim.x - 1) s_carry += incl;
     __syncthreads();
   }
-  if (threadIdx.x == 0) D.phi_off[P.nPhi] = s_carry;
+  if (publish && threadIdx.x == 0) D.phi_off[P.nPhi] = s_carry;
 }
 
 template <bool kDepth>
-__global__ void __launch_bounds__(256) k_project(MapParams P, DeviceBuffers D, const void *input, int rows, int cols,
-                                                 int n_points, int *ticket) {
-  extern __shared__ int s_hist[];  // [nPhi] then [blockDim] scan scratch
+__global__ void __launch_bounds__(256) k_project(MapParams P, DeviceBuffers D) {
+  extern __shared__ int s_hist[];  // [nPhi]
   __shared__ int s_cnt[3];
-  __shared__ int s_last;
   const FrameParams &F = *D.fp;
   for (int i = threadIdx.x; i < P.nPhi; i += blockDim.x) s_hist[i] = 0;
   if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int N = kDepth ? rows * cols : n_points;
+  const int N = F.n_total;
+  if (blockIdx.x * blockDim.x >= N) return;  // the grid is sized for cfg.max_points (graph replay)
+  const void *input = F.input;
+  const int cols = F.cols;
   RayRecord rec;
   rec.rho = 0;
   rec.z = 0;
@@ -306,30 +295,21 @@ __global__ void __launch_bounds__(256) k_project(MapParams P, DeviceBuffers D, c
   for (int p = threadIdx.x; p < P.nPhi; p += blockDim.x)
     if (s_hist[p]) atomicAdd(&D.phi_hist[p], s_hist[p]);
   if (threadIdx.x == 0) {
-    if (s_cnt[0]) atomicAdd(&D.fc->n_points, s_cnt[0]);
-    if (s_cnt[1]) atomicAdd(&D.fc->n_inside, s_cnt[1]);
-    if (s_cnt[2]) atomicAdd(&D.fc->n_cast, s_cnt[2]);
-  }
-  // last CTA scans the histogram
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int tk = atomicAdd(ticket, 1);
-    s_last = (tk == (int)gridDim.x - 1);
-    if (s_last) *ticket = 0;
-  }
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    scan_phi_hist_last_block(P, D, s_hist + P.nPhi);
+    FrameCounters *fc = D.fc[F.parity];
+    if (s_cnt[0]) atomicAdd(&fc->n_points, s_cnt[0]);
+    if (s_cnt[1]) atomicAdd(&fc->n_inside, s_cnt[1]);
+    if (s_cnt[2]) atomicAdd(&fc->n_cast, s_cnt[2]);
   }
 }
 
 // ---- K1b: group records by phi column ----------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_scatter(MapParams P, DeviceBuffers D, int N) {
-  extern __shared__ int s_mem[];  // s_cnt[nPhi], s_base[nPhi]
-  int *s_cnt = s_mem, *s_base = s_mem + P.nPhi;
+__global__ void __launch_bounds__(256) k_scatter(MapParams P, DeviceBuffers D) {
+  const int N = D.fp->n_total;
+  if (blockIdx.x * blockDim.x >= N) return;
+  extern __shared__ int s_mem[];  // s_cnt[nPhi], s_base[nPhi], s_tmp[blockDim]
+  int *s_cnt = s_mem, *s_base = s_mem + P.nPhi, *s_tmp = s_mem + 2 * P.nPhi;
   for (int i = threadIdx.x; i < P.nPhi; i += blockDim.x) s_cnt[i] = 0;
+  scan_phi_hist(P, D, s_base, s_tmp, blockIdx.x == 0);  // s_base[p] = first slot of column p
   __syncthreads();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   RayRecord rec;
@@ -344,7 +324,7 @@ __global__ void __launch_bounds__(256) k_scatter(MapParams P, DeviceBuffers D, i
   }
   __syncthreads();
   for (int p = threadIdx.x; p < P.nPhi; p += blockDim.x)
-    if (s_cnt[p]) s_base[p] = D.phi_off[p] + atomicAdd(&D.phi_cursor[p], s_cnt[p]);
+    if (s_cnt[p]) s_base[p] += atomicAdd(&D.phi_cursor[p], s_cnt[p]);
   __syncthreads();
   if (rec.phi_flags != 0xffffffffu) D.rec_col[s_base[phi] + rank] = rec;
 }
@@ -435,15 +415,15 @@ __device__ __forceinline__ void radix_pass(const uint64_t *src, uint64_t *dst, i
 }
 
 __device__ __forceinline__ void touch_subbox(const MapParams &P, const FrameParams &F, DeviceBuffers &D,
-                                             const int g[3]) {
+                                             FrameCounters *fc, const int g[3]) {
   int ls = lsg_index(P, F, g);
   if (ls < 0) {
-    D.fc->error = kErrInternal;
+    fc->error = kErrInternal;
     return;
   }
   if (__ldcg(&D.lsg_flag[ls]) == 0) {
     if (atomicExch(&D.lsg_flag[ls], 1) == 0) {
-      int pos = atomicAdd(&D.fc->n_touched_sub, 1);
+      int pos = atomicAdd(&fc->n_touched_sub, 1);
       D.touched_sub[pos] = ls;
     }
   }
@@ -515,6 +495,62 @@ __device__ __forceinline__ void compact_bits(const uint32_t *bm, int w0, int w1,
   }
 }
 
+// ---- resolve / allocate the subboxes touched this frame (allocate_ram, include/map_local.h:215-231) ----
+// Run by the LAST k_column CTA to finish (ticket): one thread per touched subbox does the hash
+// find-or-insert and, for a new subbox, pops a block from the free stack.  Blocks on the free
+// stack are always in the initial state ('u','u',0.f) — they are initialised when the pool is
+// created and when a block is returned — so allocation writes nothing.
+__device__ __forceinline__ void resolve_subboxes(const MapParams &P, const FrameParams &F, DeviceBuffers &D,
+                                                 FrameCounters *fc) {
+  const int n = *reinterpret_cast<volatile int *>(&fc->n_touched_sub);
+  int n_new = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int ls = __ldcg(&D.touched_sub[i]);
+    int block = -3;
+    int lx = ls % P.lsg_dim_xy, ly = (ls / P.lsg_dim_xy) % P.lsg_dim_xy, lz = ls / (P.lsg_dim_xy * P.lsg_dim_xy);
+    int g[3] = {lx + F.lsg_base[0], ly + F.lsg_base[1], lz + F.lsg_base[2]};
+    uint64_t key;
+    if (!pack_glb(g, key)) {
+      fc->error = kErrRange;
+    } else {
+      uint32_t slot = ht_hash(key) & P.ht_mask;
+      bool done = false;
+      for (uint32_t probe = 0; probe <= P.ht_mask && !done; probe++) {
+        uint64_t k = D.ht_key[slot];
+        if (k == kEmptyKey) {
+          unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&D.ht_key[slot]),
+                                             (unsigned long long)kEmptyKey, (unsigned long long)key);
+          if (old == kEmptyKey) {
+            int top = atomicSub(D.free_top, 1) - 1;
+            if (top < 0) {
+              atomicAdd(D.free_top, 1);
+              D.ht_val[slot] = -3;  // key stays so the table is consistent; the subbox is unusable
+              fc->error = kErrPool;
+            } else {
+              block = D.free_stack[top];
+              D.ht_val[slot] = block;
+              n_new++;
+            }
+            done = true;
+            break;
+          }
+          k = (uint64_t)old;
+        }
+        if (k == key) {
+          block = D.ht_val[slot];
+          done = true;
+          break;
+        }
+        slot = (slot + 1) & P.ht_mask;
+      }
+      if (!done) fc->error = kErrPool;
+    }
+    D.lsg_block[ls] = block;
+    D.lsg_flag[ls] = 0;
+  }
+  if (n_new) atomicAdd(&fc->n_new_blocks, n_new);
+}
+
 // bytes of k_column's shared memory in front of the two key buffers
 __host__ __device__ inline size_t col_smem_prefix_bytes(int col_words, int nRho) {
   return (((size_t)2 * col_words + kCntTotal + kColWarps + (size_t)kOddsRows * nRho + nRho) * 4 + 15) & ~(size_t)15;
@@ -529,12 +565,25 @@ __host__ __device__ inline size_t col_smem_prefix_bytes(int col_words, int nRho)
 __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBuffers D) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   const FrameParams &F = *D.fp;
+  FrameCounters *fc = D.fc[F.parity];
+  uint32_t *act = D.act[F.parity];
   const int phi = blockIdx.x;
   const int tid = threadIdx.x;
   const int n_c = D.phi_hist[phi];
   uint32_t *g_miss = D.miss_bitmap + (size_t)phi * P.col_words;
+  __shared__ int s_last;
   if (n_c == 0) {
     for (int i = tid; i < P.col_words; i += blockDim.x) g_miss[i] = 0;
+    if (tid == 0) {
+      __threadfence();
+      s_last = atomicAdd(D.col_ticket, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+      if (tid == 0) *D.col_ticket = 0;
+      __threadfence();
+      resolve_subboxes(P, F, D, fc);
+    }
     return;
   }
   const int off = D.phi_off[phi];
@@ -709,7 +758,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   {
     const int n_head = s_nhead;
     int base_idx = 0;
-    if (tid == 0) s_nk = atomicAdd(&D.fc->n_hit, n_head);  // one global reservation per column
+    if (tid == 0) s_nk = atomicAdd(&fc->n_hit, n_head);  // one global reservation per column
     __syncthreads();
     base_idx = s_nk;
     for (int k = tid; k < n_head; k += blockDim.x) {
@@ -719,30 +768,30 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
       const uint32_t stamp = (uint32_t)((((k0 >> 12) & t_mask) << 5) | ((k0 >> 7) & 31));  // t*32 + substep of the first insert
       const int idx = base_idx + k;
       if (idx >= P.max_hits) {
-        D.fc->error = kErrCapacity;
+        fc->error = kErrCapacity;
         continue;
       }
       D.hit_key[idx] = (zk * P.nPhi + phi) * P.nRho + rk;  // mapIdx, map_awareness.h:81-84
       D.hit_p[idx] = __uint_as_float(s_head_p[k]);
       D.hit_t[idx] = stamp;
       // bucket activation stamp (libstdc++ iteration order)
-      atomicMin(&D.act[libstdcxx_bucket(vector_hash3(rk, phi, zk), F.bucket_count)], stamp);
+      atomicMin(&act[libstdcxx_bucket(vector_hash3(rk, phi, zk), F.bucket_count)], stamp);
       // p_w = T_wa * centre  (identity rotation: one add per axis), src/map_local.cpp:151
       double2 cxy = __ldg(&P.centre_xy[phi * P.nRho + rk]);
       CellRef cr = locate_cell(P, cxy.x + F.t_wa[0], cxy.y + F.t_wa[1], __ldg(&P.centre_z[zk]) + F.t_wa[2]);
       int lv = lvg_index(P, F, cr);
       if (lv < 0) {
-        D.fc->error = kErrInternal;
+        fc->error = kErrInternal;
         D.hit_next[idx] = kLvgEmpty;
         continue;
       }
       int old = atomicExch(&D.lvg_head[lv], idx);
       D.hit_next[idx] = old;
       if (old == kLvgEmpty) {
-        int tp = agg_inc(&D.fc->n_touched);
-        if (tp < P.max_touched) D.touched[tp] = (uint32_t)lv | kTouchedHitTag; else D.fc->error = kErrCapacity;
+        int tp = agg_inc(&fc->n_touched);
+        if (tp < P.max_touched) D.touched[tp] = (uint32_t)lv | kTouchedHitTag; else fc->error = kErrCapacity;
       }
-      touch_subbox(P, F, D, cr.g);
+      touch_subbox(P, F, D, fc, cr.g);
     }
   }
   __syncthreads();
@@ -826,15 +875,15 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
       CellRef cr = locate_cell(P, cxy.x + F.t_wa[0], cxy.y + F.t_wa[1], __ldg(&P.centre_z[z]) + F.t_wa[2]);
       int lv = lvg_index(P, F, cr);
       if (lv < 0) {
-        D.fc->error = kErrInternal;
+        fc->error = kErrInternal;
         continue;
       }
       int old = atomicAdd(&D.lvg_miss[lv], 1);
       if (old == 0) {
-        int tp = agg_inc(&D.fc->n_touched);
-        if (tp < P.max_touched) D.touched[tp] = (uint32_t)lv; else D.fc->error = kErrCapacity;
+        int tp = agg_inc(&fc->n_touched);
+        if (tp < P.max_touched) D.touched[tp] = (uint32_t)lv; else fc->error = kErrCapacity;
       }
-      touch_subbox(P, F, D, cr.g);
+      touch_subbox(P, F, D, fc, cr.g);
     }
     if (tid == 0) s_nmiss += n_list;
     __syncthreads();
@@ -843,90 +892,31 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
 #ifdef MLM_PHASE_TIMING
   if (tid == 0) { D.debug_cycles[blockIdx.x * 16 + 10] = n_c; D.debug_cycles[blockIdx.x * 16 + 11] = n_k; }
 #endif
-  if (tid == 0 && s_nmiss) atomicAdd(&D.fc->n_miss, s_nmiss);
-}
-
-// ---- K3: resolve / allocate the subboxes touched this frame (allocate_ram, map_local.h:215-231) ------
-// One warp per touched subbox: lane 0 does the hash find-or-insert and pops a pool block for a
-// new subbox; the warp then initialises the block ('u', 'u', 0.f) with 16-byte stores.
-__global__ void __launch_bounds__(256) k_submaps(MapParams P, DeviceBuffers D) {
-  const FrameParams &F = *D.fp;
-  const int lane = lane_id();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int n = D.fc->n_touched_sub;
-  for (int i = warp; i < n; i += nwarps) {
-    const int ls = D.touched_sub[i];
-    int block = -3, is_new = 0;
-    if (lane == 0) {
-      int lx = ls % P.lsg_dim_xy, ly = (ls / P.lsg_dim_xy) % P.lsg_dim_xy, lz = ls / (P.lsg_dim_xy * P.lsg_dim_xy);
-      int g[3] = {lx + F.lsg_base[0], ly + F.lsg_base[1], lz + F.lsg_base[2]};
-      uint64_t key;
-      if (!pack_glb(g, key)) {
-        D.fc->error = kErrRange;
-      } else {
-        uint32_t slot = ht_hash(key) & P.ht_mask;
-        bool done = false;
-        for (uint32_t probe = 0; probe <= P.ht_mask && !done; probe++) {
-          uint64_t k = D.ht_key[slot];
-          if (k == kEmptyKey) {
-            unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&D.ht_key[slot]),
-                                               (unsigned long long)kEmptyKey, (unsigned long long)key);
-            k = (old == kEmptyKey) ? kEmptyKey : (uint64_t)old;
-            if (old == kEmptyKey) {
-              int top = atomicSub(D.free_top, 1) - 1;
-              if (top < 0) {
-                atomicAdd(D.free_top, 1);
-                D.ht_key[slot] = key;  // keep the key so the table stays consistent; mark unusable
-                D.ht_val[slot] = -3;
-                D.fc->error = kErrPool;
-                block = -3;
-              } else {
-                block = D.free_stack[top];
-                D.ht_val[slot] = block;
-                is_new = 1;
-              }
-              done = true;
-              break;
-            }
-          }
-          if (k == key) {
-            block = D.ht_val[slot];
-            done = true;
-            break;
-          }
-          slot = (slot + 1) & P.ht_mask;
-        }
-        if (!done) D.fc->error = kErrPool;
-      }
-      D.lsg_block[ls] = block;
-      D.lsg_flag[ls] = 0;
-      if (is_new) atomicAdd(&D.fc->n_new_blocks, 1);
-    }
-    block = __shfl_sync(0xffffffffu, block, 0);
-    is_new = __shfl_sync(0xffffffffu, is_new, 0);
-    if (is_new) {
-      const size_t base = (size_t)block * P.cell_stride;  // stride is cells padded to a multiple of 16
-      uint4 *lo4 = reinterpret_cast<uint4 *>(D.pool_lo + base);
-      uint4 *oc4 = reinterpret_cast<uint4 *>(D.pool_occ + base);
-      uint4 *in4 = reinterpret_cast<uint4 *>(D.pool_inf + base);
-      const uint4 z4 = make_uint4(0, 0, 0, 0);
-      const uint32_t uu = 0x75757575u;  // 'u' x4
-      const uint4 u4 = make_uint4(uu, uu, uu, uu);
-      for (int j = lane; j < P.cell_stride / 4; j += 32) lo4[j] = z4;
-      for (int j = lane; j < P.cell_stride / 16; j += 32) {
-        oc4[j] = u4;
-        in4[j] = u4;
-      }
-    }
+  if (tid == 0 && s_nmiss) atomicAdd(&fc->n_miss, s_nmiss);
+  // the last column to finish resolves the touched subboxes for k_fuse
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(D.col_ticket, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (s_last) {
+    if (tid == 0) *D.col_ticket = 0;
+    __threadfence();
+    resolve_subboxes(P, F, D, fc);
   }
 }
+
+// libstdc++ _Prime_rehash_policy growth chain, mirrored by the host in mlmap_capi.cu
+constexpr int kBucketChainLen = 24;
+__device__ __constant__ uint32_t c_bucket_chain[kBucketChainLen] = {
+    1,      13,     29,      59,      127,     257,      541,      1109,     2357,     5087,     10273,   20753,
+    42043,  85229,  172933,  351061,  712697,  1447153,  2938679,  5967347,  12117689, 24607243, 49969847, 101473717};
 
 // ---- K5: clamped log-odds fusion, one thread per touched cell (map_local.cpp:147-207) ---------------
 constexpr int kFuseLocal = 16;
 __global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D) {
   const FrameParams &F = *D.fp;
-  FrameCounters *fc = D.fc;
+  FrameCounters *fc = D.fc[F.parity];
+  const uint32_t *act = D.act[F.parity];
   // a frame that crosses a libstdc++ rehash needs the slow ordering pass first (host re-launches)
   if (F.order_mode == 0 && fc->n_hit > (int)F.bucket_count) {
     if (blockIdx.x == 0 && threadIdx.x == 0) fc->overflow = 1;
@@ -976,7 +966,7 @@ __global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D) {
           int key = D.hit_key[h];
           int zk = key / (P.nRho * P.nPhi), rem = key - zk * (P.nRho * P.nPhi);
           int pk = rem / P.nRho, rk = rem - pk * P.nRho;
-          uint32_t a = D.act[libstdcxx_bucket(vector_hash3(rk, pk, zk), F.bucket_count)];
+          uint32_t a = act[libstdcxx_bucket(vector_hash3(rk, pk, zk), F.bucket_count)];
           uint64_t st = ((uint64_t)a << 32) | D.hit_t[h];
           int j = cnt;
           while (j > 0 && hst[j - 1] < st) {
@@ -1001,7 +991,7 @@ __global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D) {
             int key = D.hit_key[q];
             int zk = key / (P.nRho * P.nPhi), rem = key - zk * (P.nRho * P.nPhi);
             int pk = rem / P.nRho, rk = rem - pk * P.nRho;
-            uint32_t a = D.act[libstdcxx_bucket(vector_hash3(rk, pk, zk), F.bucket_count)];
+            uint32_t a = act[libstdcxx_bucket(vector_hash3(rk, pk, zk), F.bucket_count)];
             uint64_t st = ((uint64_t)a << 32) | D.hit_t[q];
             if (st < prev && (h < 0 || st > best)) {
               best = st;
@@ -1049,14 +1039,23 @@ __global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D) {
     if (my_obs) atomicAdd(&fc->obs_delta, my_obs);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) fc->fused = 1;
-}
 
-// cumulative counters (ram_expand_cnt, obs_cnt), single thread after k_fuse
-__global__ void k_frame_end(DeviceBuffers D) {
-  if (D.fc->fused) {
-    D.cum[0] += D.fc->n_new_blocks;
-    D.cum[1] += D.fc->obs_delta;
-    D.cum[2] += D.fc->n_new_blocks;
+  // ---- reset of the NEXT frame's scratch (double-buffered, nothing below is read by this launch) ----
+  {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    // bucket count the hit map will have at the start of the next frame (clear() keeps the buckets)
+    uint32_t B = F.bucket_count;
+    const uint32_t n_hit = (uint32_t)fc->n_hit;
+    if (n_hit > 0 && B == 1) B = 13;
+    for (int c = 0; c + 1 < kBucketChainLen && n_hit > B; c++)
+      if (c_bucket_chain[c] == B) B = c_bucket_chain[c + 1];
+    uint32_t *act_next = D.act[F.parity ^ 1];
+    for (uint32_t i = gtid; i < B; i += nth) act_next[i] = 0xffffffffu;
+    for (int i = gtid; i < P.nPhi; i += nth) {
+      D.phi_hist[i] = 0;
+      D.phi_cursor[i] = 0;
+    }
+    if (gtid < (int)(sizeof(FrameCounters) / sizeof(int))) reinterpret_cast<int *>(D.fc[F.parity ^ 1])[gtid] = 0;
   }
 }
 

@@ -132,12 +132,15 @@ struct mlm_map {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   FrameParams *h_fp = nullptr;    // pinned
   FrameCounters *h_fc = nullptr;  // pinned
-  int64_t *h_cum = nullptr;       // pinned
+  int64_t cum_ram_expand = 0, cum_obs = 0, n_submaps = 0;  // cumulative counters (reference ram_expand_cnt / obs_cnt)
+  uint32_t frame_idx = 0;
+  int last_parity = 0;
+  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};  // [0] depth input, [1] point input
+  int use_graph = 1;
   void *h_stage = nullptr;        // pinned input staging
   size_t stage_bytes = 0;
   void *d_input = nullptr;
   size_t input_bytes = 0;
-  int *d_ticket = nullptr;
   // slow-path ordering scratch
   uint64_t *d_sort_a = nullptr, *d_sort_b = nullptr;
   int *d_seq_a = nullptr, *d_seq_b = nullptr;
@@ -286,6 +289,7 @@ void device_sort(mlm_map *h, uint64_t *keys, int n_pad) {
 // hit_t and bucket activations for the final bucket count.  Returns the final bucket count.
 int order_slow_path(mlm_map *h, int n, uint32_t *B_final_out) {
   cudaStream_t s = h->stream;
+  uint32_t *act = h->D.act[h->last_parity];
   const int T = 256;
   int n_pad = next_pow2(n);
   k_order_seed<<<grid_for(n_pad, T), T, 0, s>>>(h->D, h->d_sort_a, n, n_pad);
@@ -297,9 +301,9 @@ int order_slow_path(mlm_map *h, int n, uint32_t *B_final_out) {
     int m = (int)std::min<uint32_t>(B, (uint32_t)n);
     if (m > 1) {
       int m_pad = next_pow2(m);
-      k_fill_u32<<<grid_for(B, T), T, 0, s>>>(h->D.act, 0xffffffffu, (int)B);
-      k_stage_act<<<grid_for(m, T), T, 0, s>>>(h->P, h->D, h->d_seq_a, m, B);
-      k_stage_keys<<<grid_for(m_pad, T), T, 0, s>>>(h->P, h->D, h->d_seq_a, h->d_sort_b, m, m_pad, B);
+      k_fill_u32<<<grid_for(B, T), T, 0, s>>>(act, 0xffffffffu, (int)B);
+      k_stage_act<<<grid_for(m, T), T, 0, s>>>(h->P, h->D, act, h->d_seq_a, m, B);
+      k_stage_keys<<<grid_for(m_pad, T), T, 0, s>>>(h->P, h->D, act, h->d_seq_a, h->d_sort_b, m, m_pad, B);
       device_sort(h, h->d_sort_b, m_pad);
       k_stage_apply<<<grid_for(m, T), T, 0, s>>>(h->d_sort_b, h->d_seq_a, h->d_seq_b, m);
       k_copy_i32<<<grid_for(m, T), T, 0, s>>>(h->d_seq_a, h->d_seq_b, m);
@@ -312,8 +316,8 @@ int order_slow_path(mlm_map *h, int n, uint32_t *B_final_out) {
     }
     B = nb;
   }
-  k_fill_u32<<<grid_for(B, T), T, 0, s>>>(h->D.act, 0xffffffffu, (int)B);
-  k_order_final<<<grid_for(n, T), T, 0, s>>>(h->P, h->D, h->d_seq_a, n, B);
+  k_fill_u32<<<grid_for(B, T), T, 0, s>>>(act, 0xffffffffu, (int)B);
+  k_order_final<<<grid_for(n, T), T, 0, s>>>(h->P, h->D, act, h->d_seq_a, n, B);
   h->launches += 2;
   *B_final_out = B;
   return MLM_OK;
@@ -346,10 +350,16 @@ int run_frame(mlm_map *h, bool depth, const void *d_in, int rows, int cols, int 
     F.t_ls[i] = Tls.t[i];
     F.t_wa[i] = Twa.t[i];
   }
+  F.input = d_in;
   F.rows = rows;
   F.cols = cols;
   F.n_points = n_points;
+  F.n_total = N;
   F.bucket_count = h->bucket_count;
+  const int parity = (int)(h->frame_idx & 1);
+  h->frame_idx++;
+  h->last_parity = parity;
+  F.parity = parity;
   F.order_mode = 0;
   F.tbits = 1;
   while ((1ll << F.tbits) < (long long)std::max(N, 2)) F.tbits++;
@@ -359,33 +369,45 @@ int run_frame(mlm_map *h, bool depth, const void *d_in, int rows, int cols, int 
   F.lvg_base[1] = (int)floor((Twa.t[1] - R) / P.d_sub) - P.lvg_margin;
   F.lvg_base[2] = (int)floor((Twa.t[2] + P.z_border_min) / P.d_sub) - P.lvg_margin;
   for (int i = 0; i < 3; i++) F.lsg_base[i] = host_floor_div(F.lvg_base[i], P.n) - 1;
-  CUDA_TRY(cudaMemcpyAsync(h->D.fp, h->h_fp, sizeof(FrameParams), cudaMemcpyHostToDevice, s));
 
   const bool prof = h->profiling != 0;
-#define MLM_MARK(i) do { if (prof) cudaEventRecord(h->kev[i], s); } while (0)
-  MLM_MARK(0);
-  k_frame_begin<<<h->sm_count, 256, 0, s>>>(P, h->D);
-  MLM_MARK(1);
-  const size_t proj_smem = (size_t)(P.nPhi + 256) * sizeof(int);
-  if (depth)
-    k_project<true><<<grid_for(N, 256), 256, proj_smem, s>>>(P, h->D, d_in, rows, cols, 0, h->d_ticket);
-  else
-    k_project<false><<<grid_for(N, 256), 256, proj_smem, s>>>(P, h->D, d_in, 0, 0, n_points, h->d_ticket);
-  MLM_MARK(2);
-  k_scatter<<<grid_for(N, 256), 256, (size_t)2 * P.nPhi * sizeof(int), s>>>(P, h->D, N);
-  MLM_MARK(3);
-  k_column<<<P.nPhi, kColThreads, h->col_smem_bytes, s>>>(P, h->D);
-  MLM_MARK(4);
-  k_submaps<<<h->sm_count, 256, 0, s>>>(P, h->D);
-  MLM_MARK(5);
-  k_fuse<<<h->sm_count * 4, 256, 0, s>>>(P, h->D);
-  MLM_MARK(6);
-  k_frame_end<<<1, 1, 0, s>>>(h->D);
-  MLM_MARK(7);
+  const int full_grid = grid_for((size_t)P.max_points, 256);
+  auto launch_kernels = [&](bool mark) {
+#define MLM_MARK(i) do { if (mark) cudaEventRecord(h->kev[i], s); } while (0)
+    MLM_MARK(0);
+    if (depth)
+      k_project<true><<<full_grid, 256, (size_t)P.nPhi * sizeof(int), s>>>(P, h->D);
+    else
+      k_project<false><<<full_grid, 256, (size_t)P.nPhi * sizeof(int), s>>>(P, h->D);
+    MLM_MARK(1);
+    k_scatter<<<full_grid, 256, (size_t)(2 * P.nPhi + 256) * sizeof(int), s>>>(P, h->D);
+    MLM_MARK(2);
+    k_column<<<P.nPhi, kColThreads, h->col_smem_bytes, s>>>(P, h->D);
+    MLM_MARK(3);
+    k_fuse<<<h->sm_count * 4, 256, 0, s>>>(P, h->D);
+    MLM_MARK(4);
 #undef MLM_MARK
-  h->launches += 7;
-  CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(h->h_cum, h->D.cum, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  };
+  if (prof || !h->use_graph) {
+    CUDA_TRY(cudaMemcpyAsync(h->D.fp, h->h_fp, sizeof(FrameParams), cudaMemcpyHostToDevice, s));
+    launch_kernels(prof);
+    CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc[0], 2 * sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
+  } else {
+    // the whole frame (parameter upload, 4 kernels, counter read-back) is one graph launch
+    cudaGraphExec_t &ge = h->graph_exec[depth ? 0 : 1];
+    if (!ge) {
+      cudaGraph_t g = nullptr;
+      CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      cudaMemcpyAsync(h->D.fp, h->h_fp, sizeof(FrameParams), cudaMemcpyHostToDevice, s);
+      launch_kernels(false);
+      cudaMemcpyAsync(h->h_fc, h->D.fc[0], 2 * sizeof(FrameCounters), cudaMemcpyDeviceToHost, s);
+      CUDA_TRY(cudaStreamEndCapture(s, &g));
+      CUDA_TRY(cudaGraphInstantiate(&ge, g, 0));
+      cudaGraphDestroy(g);
+    }
+    CUDA_TRY(cudaGraphLaunch(ge, s));
+  }
+  h->launches += 4;
   CUDA_TRY(cudaStreamSynchronize(s));
   CUDA_TRY(cudaGetLastError());
 
@@ -393,9 +415,9 @@ int run_frame(mlm_map *h, bool depth, const void *d_in, int rows, int cols, int 
     for (int i = 0; i < MLM_NUM_FRAME_KERNELS; i++) cudaEventElapsedTime(&h->kms[i], h->kev[i], h->kev[i + 1]);
   int slow = 0;
   uint32_t order_B = h->bucket_count;
-  if (h->h_fc->error == 0 && h->h_fc->overflow) {
+  if (h->h_fc[parity].error == 0 && h->h_fc[parity].overflow) {
     slow = 1;
-    const int n = h->h_fc->n_hit;
+    const int n = h->h_fc[parity].n_hit;
     if (n > h->sort_cap) {
       g_last_error = "hit count exceeds ordering scratch";
       return MLM_ERR_CAPACITY;
@@ -408,14 +430,17 @@ int run_frame(mlm_map *h, bool depth, const void *d_in, int rows, int cols, int 
     F.order_mode = 1;
     CUDA_TRY(cudaMemcpyAsync(h->D.fp, h->h_fp, sizeof(FrameParams), cudaMemcpyHostToDevice, s));
     k_fuse<<<h->sm_count * 4, 256, 0, s>>>(P, h->D);
-    k_frame_end<<<1, 1, 0, s>>>(h->D);
-    h->launches += 2;
-    CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(h->h_cum, h->D.cum, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    h->launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc[0], 2 * sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaGetLastError());
   }
-  const FrameCounters &C = *h->h_fc;
+  const FrameCounters &C = h->h_fc[parity];
+  if (C.fused) {
+    h->cum_ram_expand += C.n_new_blocks;
+    h->cum_obs += C.obs_delta;
+    h->n_submaps += C.n_new_blocks;
+  }
   // bucket-count evolution of hit_idx_odds_hashmap (clear() keeps the bucket array)
   if (C.n_hit > 0 && h->bucket_count == 1) h->bucket_count = 13;
   while ((uint32_t)C.n_hit > h->bucket_count) {
@@ -437,8 +462,8 @@ int run_frame(mlm_map *h, bool depth, const void *d_in, int rows, int cols, int 
     stats->hit_bucket_count = (int32_t)h->bucket_count;
     stats->ordering_slow_path = slow;
     stats->status = map_device_error(C.error);
-    stats->ram_expand_cnt = h->h_cum[0];
-    stats->obs_cnt = h->h_cum[1];
+    stats->ram_expand_cnt = h->cum_ram_expand;
+    stats->obs_cnt = h->cum_obs;
   }
   if (C.error) {
     g_last_error = "device raised error code " + std::to_string(C.error);
@@ -674,8 +699,7 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   CUDA_TRY_H(cudaEventCreate(&h->ev0));
   CUDA_TRY_H(cudaEventCreate(&h->ev1));
   CUDA_TRY_H(cudaMallocHost((void **)&h->h_fp, sizeof(FrameParams)));
-  CUDA_TRY_H(cudaMallocHost((void **)&h->h_fc, sizeof(FrameCounters)));
-  CUDA_TRY_H(cudaMallocHost((void **)&h->h_cum, 3 * sizeof(int64_t)));
+  CUDA_TRY_H(cudaMallocHost((void **)&h->h_fc, 2 * sizeof(FrameCounters)));
   CUDA_TRY_H(cudaFuncSetAttribute(k_column, cudaFuncAttributeMaxDynamicSharedMemorySize, h->col_smem_bytes));
 
   DeviceBuffers &D = h->D;
@@ -698,7 +722,9 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   P.centre_z = d_cz;
 
   TRY(dev_alloc(h, &D.fp, 1));
-  TRY(dev_alloc(h, &D.fc, 1));
+  TRY(dev_alloc(h, &D.fc[0], 2));
+  D.fc[1] = D.fc[0] + 1;
+  TRY(dev_alloc(h, &D.col_ticket, 1));
   TRY(dev_alloc(h, &D.rec_lin, (size_t)P.max_points));
   TRY(dev_alloc(h, &D.rec_col, (size_t)P.max_points));
   TRY(dev_alloc(h, &D.phi_hist, (size_t)P.nPhi));
@@ -716,7 +742,8 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
     mlm_destroy(h);
     return MLM_ERR_INVALID_CONFIG;
   }
-  TRY(dev_alloc(h, &D.act, (size_t)h->act_cap));
+  TRY(dev_alloc(h, &D.act[0], (size_t)h->act_cap));
+  TRY(dev_alloc(h, &D.act[1], (size_t)h->act_cap));
   TRY(dev_alloc(h, &D.lvg_head, (size_t)lvg_cells));
   TRY(dev_alloc(h, &D.lvg_miss, (size_t)lvg_cells));
   TRY(dev_alloc(h, &D.touched, (size_t)P.max_touched));
@@ -733,7 +760,6 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   TRY(dev_alloc(h, &D.cum, 4));
   TRY(dev_alloc(h, &D.debug_cycles, (size_t)P.nPhi * 16));
   CUDA_TRY_H(cudaMemset(D.debug_cycles, 0, (size_t)P.nPhi * 16 * sizeof(long long)));
-  TRY(dev_alloc(h, &h->d_ticket, 1));
   h->sort_cap = P.max_hits;
   const size_t sort_pad = (size_t)next_pow2(P.max_hits);
   TRY(dev_alloc(h, &h->d_sort_a, sort_pad));
@@ -749,8 +775,16 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   CUDA_TRY_H(cudaMemset(D.ht_key, 0xff, (size_t)ht_cap * 8));
   CUDA_TRY_H(cudaMemset(D.ht_val, 0xff, (size_t)ht_cap * 4));
   CUDA_TRY_H(cudaMemset(D.cum, 0, 4 * sizeof(int64_t)));
-  CUDA_TRY_H(cudaMemset(h->d_ticket, 0, sizeof(int)));
-  CUDA_TRY_H(cudaMemset(D.fc, 0, sizeof(FrameCounters)));
+  CUDA_TRY_H(cudaMemset(D.col_ticket, 0, sizeof(int)));
+  CUDA_TRY_H(cudaMemset(D.fc[0], 0, 2 * sizeof(FrameCounters)));
+  CUDA_TRY_H(cudaMemset(D.act[0], 0xff, (size_t)h->act_cap * 4));
+  CUDA_TRY_H(cudaMemset(D.act[1], 0xff, (size_t)h->act_cap * 4));
+  CUDA_TRY_H(cudaMemset(D.phi_hist, 0, (size_t)P.nPhi * 4));
+  CUDA_TRY_H(cudaMemset(D.phi_cursor, 0, (size_t)P.nPhi * 4));
+  // every block on the free stack is in the initial state of allocate_ram: 'u', 'u', 0.f
+  CUDA_TRY_H(cudaMemset(D.pool_lo, 0, (size_t)P.pool_blocks * P.cell_stride * 4));
+  CUDA_TRY_H(cudaMemset(D.pool_occ, 'u', (size_t)P.pool_blocks * P.cell_stride));
+  CUDA_TRY_H(cudaMemset(D.pool_inf, 'u', (size_t)P.pool_blocks * P.cell_stride));
   CUDA_TRY_H(cudaMemset(D.miss_bitmap, 0, (size_t)P.nPhi * P.col_words * 4));
   {
     std::vector<int> stack(P.pool_blocks);
@@ -770,13 +804,14 @@ int mlm_destroy(mlm_handle h) {
   if (!h) return MLM_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  for (int i = 0; i < 2; i++)
+    if (h->graph_exec[i]) cudaGraphExecDestroy(h->graph_exec[i]);
   for (void *p : h->allocs) cudaFree(p);
   if (h->d_input) cudaFree(h->d_input);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->l2_buf) cudaFree(h->l2_buf);
   if (h->h_fp) cudaFreeHost(h->h_fp);
   if (h->h_fc) cudaFreeHost(h->h_fc);
-  if (h->h_cum) cudaFreeHost(h->h_cum);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (int i = 0; i <= MLM_NUM_FRAME_KERNELS; i++)
@@ -797,14 +832,23 @@ int mlm_integrate_depth_u16(mlm_handle h, const uint16_t *img, int rows, int col
   const size_t bytes = (size_t)rows * cols * 2;
   int rc = ensure_input(h, bytes);
   if (rc != MLM_OK) return rc;
-  // pack rows into the pinned staging buffer (dense), then one async H2D copy
-  if (stride_bytes == (size_t)cols * 2) {
-    memcpy(h->h_stage, img, bytes);
-  } else {
-    for (int v = 0; v < rows; v++)
-      memcpy((char *)h->h_stage + (size_t)v * cols * 2, (const char *)img + (size_t)v * stride_bytes, (size_t)cols * 2);
+  // Page-locked caller memory (mlm_host_alloc / cudaHostRegister) with dense rows is copied
+  // straight from the caller's buffer; anything else is packed into the pinned staging buffer first.
+  cudaPointerAttributes attr;
+  const bool pinned = stride_bytes == (size_t)cols * 2 && cudaPointerGetAttributes(&attr, img) == cudaSuccess &&
+                      attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  const void *src = img;
+  if (!pinned) {
+    if (stride_bytes == (size_t)cols * 2) {
+      memcpy(h->h_stage, img, bytes);
+    } else {
+      for (int v = 0; v < rows; v++)
+        memcpy((char *)h->h_stage + (size_t)v * cols * 2, (const char *)img + (size_t)v * stride_bytes, (size_t)cols * 2);
+    }
+    src = h->h_stage;
   }
-  CUDA_TRY(cudaMemcpyAsync(h->d_input, h->h_stage, bytes, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_input, src, bytes, cudaMemcpyHostToDevice, h->stream));
   return run_frame(h, true, h->d_input, rows, cols, 0, T_wb, stats);
 }
 
@@ -955,6 +999,17 @@ int mlm_device_free(mlm_handle h, void *d_ptr) {
   CUDA_TRY(cudaFree(d_ptr));
   return MLM_OK;
 }
+int mlm_host_alloc(mlm_handle h, size_t bytes, void **ptr) {
+  if (!h || !ptr) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMallocHost(ptr, bytes));
+  return MLM_OK;
+}
+int mlm_host_free(mlm_handle h, void *ptr) {
+  if (!h) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaFreeHost(ptr));
+  return MLM_OK;
+}
 int mlm_copy_to_device(mlm_handle h, void *d_dst, const void *src, size_t bytes) {
   if (!h || !d_dst || !src) return MLM_ERR_INVALID_ARG;
   CUDA_TRY(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
@@ -1013,7 +1068,8 @@ int mlm_last_frame_hits(mlm_handle h, int32_t *keys3, float *p, size_t cap, size
   const int T = 256, n_pad = next_pow2(n);
   k_order_seed<<<grid_for(n_pad, T), T, 0, s>>>(h->D, h->d_sort_a, n, n_pad);
   device_sort(h, h->d_sort_a, n_pad);
-  k_export_hit_keys<<<grid_for(n_pad, T), T, 0, s>>>(h->P, h->D, h->d_sort_b, n, n_pad, h->last_order_B);
+  k_export_hit_keys<<<grid_for(n_pad, T), T, 0, s>>>(h->P, h->D, h->D.act[h->last_parity], h->d_sort_b, n, n_pad,
+                                                      h->last_order_B);
   device_sort(h, h->d_sort_b, n_pad);
   int *d_k3 = nullptr;
   float *d_p = nullptr;
@@ -1061,10 +1117,7 @@ int mlm_last_frame_misses(mlm_handle h, uint64_t *idx, size_t cap, size_t *n_out
 int mlm_export_map_count(mlm_handle h, size_t *n_submaps) {
   if (!h || !n_submaps) return MLM_ERR_INVALID_ARG;
   CUDA_TRY(cudaSetDevice(h->device));
-  int64_t cum[3];
-  CUDA_TRY(cudaMemcpyAsync(cum, h->D.cum, sizeof(cum), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
-  *n_submaps = (size_t)cum[2];
+  *n_submaps = (size_t)h->n_submaps;
   return MLM_OK;
 }
 

@@ -81,16 +81,16 @@ __global__ void k_fill_u32(uint32_t *p, uint32_t v, int n) {
   if (i < n) p[i] = v;
 }
 // act[bucket] = earliest virtual position among the first m keys of the sequence
-__global__ void k_stage_act(MapParams P, DeviceBuffers D, const int *seq, int m, uint32_t B) {
+__global__ void k_stage_act(MapParams P, DeviceBuffers D, uint32_t *act, const int *seq, int m, uint32_t B) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < m) atomicMin(&D.act[hit_bucket(P, D.hit_key[seq[j]], B)], (uint32_t)j);
+  if (j < m) atomicMin(&act[hit_bucket(P, D.hit_key[seq[j]], B)], (uint32_t)j);
 }
 // sort key: descending (act, position)  ==  ascending 63-bit complement; padding sorts last
-__global__ void k_stage_keys(MapParams P, DeviceBuffers D, const int *seq, uint64_t *keys, int m, int m_pad,
-                             uint32_t B) {
+__global__ void k_stage_keys(MapParams P, DeviceBuffers D, const uint32_t *act, const int *seq, uint64_t *keys, int m,
+                             int m_pad, uint32_t B) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < m) {
-    uint64_t comp = ((uint64_t)D.act[hit_bucket(P, D.hit_key[seq[j]], B)] << 32) | (uint32_t)j;
+    uint64_t comp = ((uint64_t)act[hit_bucket(P, D.hit_key[seq[j]], B)] << 32) | (uint32_t)j;
     keys[j] = (~comp) & 0x7fffffffffffffffull;
   } else if (j < m_pad) {
     keys[j] = ~0ull;
@@ -108,12 +108,12 @@ __global__ void k_copy_i32(int *dst, const int *src, int n) {
   if (i < n) dst[i] = src[i];
 }
 // final: stamps become virtual positions; bucket activation over the whole sequence
-__global__ void k_order_final(MapParams P, DeviceBuffers D, const int *seq, int n, uint32_t B) {
+__global__ void k_order_final(MapParams P, DeviceBuffers D, uint32_t *act, const int *seq, int n, uint32_t B) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n) {
     int h = seq[j];
     D.hit_t[h] = (uint32_t)j;
-    atomicMin(&D.act[hit_bucket(P, D.hit_key[h], B)], (uint32_t)j);
+    atomicMin(&act[hit_bucket(P, D.hit_key[h], B)], (uint32_t)j);
   }
 }
 
@@ -121,10 +121,11 @@ __global__ void k_order_final(MapParams P, DeviceBuffers D, const int *seq, int 
 // keys_t : ascending (stamp, hit index) from k_order_seed + sort.  keys_o : ascending complement of
 // (bucket activation, stamp) = the iteration order.  The stamp is unique per key, so the hit index of
 // an ordered entry is recovered by binary search of its stamp in keys_t.
-__global__ void k_export_hit_keys(MapParams P, DeviceBuffers D, uint64_t *keys_o, int n, int n_pad, uint32_t B) {
+__global__ void k_export_hit_keys(MapParams P, DeviceBuffers D, const uint32_t *act, uint64_t *keys_o, int n, int n_pad,
+                                  uint32_t B) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    uint64_t comp = ((uint64_t)D.act[hit_bucket(P, D.hit_key[i], B)] << 32) | D.hit_t[i];
+    uint64_t comp = ((uint64_t)act[hit_bucket(P, D.hit_key[i], B)] << 32) | D.hit_t[i];
     keys_o[i] = (~comp) & 0x7fffffffffffffffull;
   } else if (i < n_pad) {
     keys_o[i] = ~0ull;

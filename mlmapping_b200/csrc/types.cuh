@@ -73,12 +73,15 @@ struct FrameParams {
   double q_ls[4];   // T_ls rotation (w,x,y,z)
   double t_ls[3];   // T_ls translation
   double t_wa[3];   // T_wa translation (= t_wb)
+  const void *input; // device pointer: uint16 depth image (rows*cols) or xyz doubles (n_points*3)
   int rows, cols;
   int n_points;     // point-cloud input
+  int n_total;      // rows*cols or n_points: number of input slots this frame
   uint32_t bucket_count;  // emulated hit_idx_odds_hashmap.bucket_count() at frame start
   int lvg_base[3];  // global cell coordinate of local voxel grid origin
   int lsg_base[3];  // global subbox coordinate of local submap grid origin
   int tbits;        // bits needed for a point stamp this frame (ceil(log2(#points)))
+  int parity;       // frame & 1: selects the double-buffered counters / activation stamps
   int order_mode;   // 0: stamps are (bucket activation, first-insert time); 1: virtual sequence positions
 };
 
@@ -92,12 +95,12 @@ struct FrameCounters {
   int overflow;           // 1: n_hit > bucket_count -> fuse skipped, slow ordering path needed
   int obs_delta;          // occupancy 'o' transitions this frame
   int fused;              // set by k_fuse when it ran to completion
-  int pad[3];
+  int pad[3];  // sizeof must stay a multiple of 4 (cleared word-wise by k_fuse)
 };
 
 struct DeviceBuffers {
   FrameParams *fp;
-  FrameCounters *fc;
+  FrameCounters *fc[2];   // double-buffered: frame f uses fc[f&1], k_fuse clears the other one
   // K1/K1b
   RayRecord *rec_lin;     // [max_points] in point order (phi_flags==~0u: no record)
   RayRecord *rec_col;     // [max_points] grouped by phi column
@@ -111,7 +114,8 @@ struct DeviceBuffers {
   uint32_t *hit_t;        // [max_hits] first-insert stamp (t*32+substep) or virtual position
   int *hit_next;          // [max_hits] next hit in the same voxel's list
   uint32_t *miss_bitmap;  // [nPhi*col_words]
-  uint32_t *act;          // [bucket capacity] bucket activation stamps
+  uint32_t *act[2];       // [bucket capacity] bucket activation stamps, double-buffered like fc
+  int *col_ticket;        // completion ticket of k_column (last CTA resolves the touched subboxes)
   // local voxel / submap grids
   int *lvg_head;          // [lvg cells] head of hit list, -1 empty
   int *lvg_miss;          // [lvg cells] number of miss cells this frame
