@@ -181,8 +181,8 @@ int mlm_flush_l2(mlm_handle h); /* writes a buffer larger than L2 (bench hygiene
 /* per-kernel timing of the frame pipeline (CUDA events between launches on the handle's stream).
  * enable=1 records events in every following frame; mlm_last_frame_kernel_ms returns the durations
  * of the MLM_NUM_FRAME_KERNELS stages of the last frame in launch order:
- * 0 k_project, 1 k_scatter, 2 k_column, 3 k_fuse */
-#define MLM_NUM_FRAME_KERNELS 4
+ * 0 k_project, 1 k_column, 2 k_fuse */
+#define MLM_NUM_FRAME_KERNELS 3
 int mlm_set_profiling(mlm_handle h, int enable);
 int mlm_last_frame_kernel_ms(mlm_handle h, float ms[MLM_NUM_FRAME_KERNELS]);
 /* per-column phase clocks of the last k_column launch (only filled by -DMLM_PHASE_TIMING builds) */

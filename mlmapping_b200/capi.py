@@ -110,7 +110,7 @@ ABI_SYMBOLS = [
     "mlm_debug_log10f", "mlm_set_profiling", "mlm_last_frame_kernel_ms", "mlm_sizeof_config",
     "mlm_sizeof_frame_stats", "mlm_debug_phase_cycles", "mlm_host_alloc", "mlm_host_free",
 ]
-FRAME_KERNELS = ["k_project", "k_scatter", "k_column", "k_fuse"]
+FRAME_KERNELS = ["k_project", "k_column", "k_fuse"]
 
 _lib = None
 

@@ -189,40 +189,48 @@ __device__ __forceinline__ void point_to_record(const MapParams &P, const FrameP
   }
 }
 
-// exclusive scan of the per-column record histogram into shared memory (every k_scatter CTA needs the
-// offsets of the columns it writes to; CTA 0 also publishes them for k_column)
-__device__ void scan_phi_hist(const MapParams &P, const DeviceBuffers &D, int *s_off, int *s_tmp /*[blockDim]*/,
-                              bool publish) {
-  __shared__ int s_carry;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  for (int base = 0; base < P.nPhi; base += blockDim.x) {
-    int i = base + threadIdx.x;
-    int v = i < P.nPhi ? D.phi_hist[i] : 0;
-    s_tmp[threadIdx.x] = v;
-    __syncthreads();
-    for (int ofs = 1; ofs < blockDim.x; ofs <<= 1) {  // Hillis-Steele inclusive scan
-      int add = threadIdx.x >= ofs ? s_tmp[threadIdx.x - ofs] : 0;
-      __syncthreads();
-      s_tmp[threadIdx.x] += add;
-      __syncthreads();
-    }
-    int incl = s_tmp[threadIdx.x];
-    if (i < P.nPhi) {
-      s_off[i] = s_carry + incl - v;
-      if (publish) D.phi_off[i] = s_carry + incl - v;
-    }
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) s_carry += incl;
-    __syncthreads();
+// CTA-wide exclusive scan of data[0,n) in shared memory (in place); returns the total.
+// Each thread scans a contiguous slice, slices are combined with warp shuffles.
+__device__ __forceinline__ int block_exclusive_scan(int *data, int n, int *s_warp /*[33]*/) {
+  const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = nt >> 5;
+  const int per = (n + nt - 1) / nt;
+  const int beg = min(tid * per, n), end = min(beg + per, n);
+  int sum = 0;
+  for (int i = beg; i < end; i++) sum += data[i];
+  int incl = sum;
+#pragma unroll
+  for (int ofs = 1; ofs < 32; ofs <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, ofs);
+    if (lane >= ofs) incl += t;
   }
-  if (publish && threadIdx.x == 0) D.phi_off[P.nPhi] = s_carry;
+  if (lane == 31) s_warp[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    int sv = lane < nw ? s_warp[lane] : 0, si = sv;
+#pragma unroll
+    for (int ofs = 1; ofs < 32; ofs <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, si, ofs);
+      if (lane >= ofs) si += t;
+    }
+    if (lane < nw) s_warp[lane] = si - sv;
+    if (lane == 31) s_warp[32] = si;
+  }
+  __syncthreads();
+  int run = s_warp[w] + incl - sum;
+  for (int i = beg; i < end; i++) {
+    int v = data[i];
+    data[i] = run;
+    run += v;
+  }
+  __syncthreads();
+  return s_warp[32];
 }
 
 template <bool kDepth>
 __global__ void __launch_bounds__(256) k_project(MapParams P, DeviceBuffers D) {
-  extern __shared__ int s_hist[];  // [nPhi]
+  extern __shared__ int s_hist[];  // [nPhi] counts, then [nPhi] offsets
   __shared__ int s_cnt[3];
+  __shared__ int s_warp[33];
   const FrameParams &F = *D.fp;
   for (int i = threadIdx.x; i < P.nPhi; i += blockDim.x) s_hist[i] = 0;
   if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
@@ -237,7 +245,7 @@ __global__ void __launch_bounds__(256) k_project(MapParams P, DeviceBuffers D) {
   rec.z = 0;
   rec.t = 0;
   rec.phi_flags = 0xffffffffu;
-  int valid = 0, inside = 0, cast = 0;
+  int valid = 0, inside = 0, cast = 0, rank = 0;
   if (i < N) {
     double xs, ys, zs;
     if (kDepth) {
@@ -277,11 +285,10 @@ __global__ void __launch_bounds__(256) k_project(MapParams P, DeviceBuffers D) {
       unsigned follow = lane < 31 ? (sames >> (lane + 1)) : 0u;
       int m = 1 + (__ffs(~follow) - 1);  // consecutive followers that repeat this cell
       rec.phi_flags |= (uint32_t)m << kRecCountShift;
-      atomicAdd(&s_hist[rec.phi_flags & kRecPhiMask], 1);
+      rank = atomicAdd(&s_hist[rec.phi_flags & kRecPhiMask], 1);
     } else {
       rec.phi_flags = 0xffffffffu;
     }
-    if (i < N) D.rec_lin[i] = rec;
   }
   // CTA-level counters
   unsigned bv = __ballot_sync(0xffffffffu, valid), bi = __ballot_sync(0xffffffffu, inside),
@@ -292,41 +299,26 @@ __global__ void __launch_bounds__(256) k_project(MapParams P, DeviceBuffers D) {
     if (bc) atomicAdd(&s_cnt[2], __popc(bc));
   }
   __syncthreads();
-  for (int p = threadIdx.x; p < P.nPhi; p += blockDim.x)
-    if (s_hist[p]) atomicAdd(&D.phi_hist[p], s_hist[p]);
+  // The CTA's records are written grouped by phi column into its own 256-slot window of rec_lin,
+  // with one directory word per (CTA, column): offset << 16 | count.  k_column gathers from there.
+  int *s_off = s_hist + P.nPhi;
+  for (int p = threadIdx.x; p < P.nPhi; p += blockDim.x) {
+    const int c = s_hist[p];
+    s_off[p] = c;
+    if (c) atomicAdd(&D.phi_hist[p], c);
+  }
+  __syncthreads();
+  block_exclusive_scan(s_off, P.nPhi, s_warp);
+  if (rec.phi_flags != 0xffffffffu)
+    D.rec_lin[(size_t)blockIdx.x * blockDim.x + s_off[rec.phi_flags & kRecPhiMask] + rank] = rec;
+  uint32_t *dir = D.rec_dir + (size_t)blockIdx.x * P.nPhi;
+  for (int p = threadIdx.x; p < P.nPhi; p += blockDim.x) dir[p] = ((uint32_t)s_off[p] << 16) | (uint32_t)s_hist[p];
   if (threadIdx.x == 0) {
     FrameCounters *fc = D.fc[F.parity];
     if (s_cnt[0]) atomicAdd(&fc->n_points, s_cnt[0]);
     if (s_cnt[1]) atomicAdd(&fc->n_inside, s_cnt[1]);
     if (s_cnt[2]) atomicAdd(&fc->n_cast, s_cnt[2]);
   }
-}
-
-// ---- K1b: group records by phi column ----------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_scatter(MapParams P, DeviceBuffers D) {
-  const int N = D.fp->n_total;
-  if (blockIdx.x * blockDim.x >= N) return;
-  extern __shared__ int s_mem[];  // s_cnt[nPhi], s_base[nPhi], s_tmp[blockDim]
-  int *s_cnt = s_mem, *s_base = s_mem + P.nPhi, *s_tmp = s_mem + 2 * P.nPhi;
-  for (int i = threadIdx.x; i < P.nPhi; i += blockDim.x) s_cnt[i] = 0;
-  scan_phi_hist(P, D, s_base, s_tmp, blockIdx.x == 0);  // s_base[p] = first slot of column p
-  __syncthreads();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  RayRecord rec;
-  rec.phi_flags = 0xffffffffu;
-  int rank = 0, phi = 0;
-  if (i < N) {
-    rec = D.rec_lin[i];
-    if (rec.phi_flags != 0xffffffffu) {
-      phi = rec.phi_flags & kRecPhiMask;
-      rank = atomicAdd(&s_cnt[phi], 1);
-    }
-  }
-  __syncthreads();
-  for (int p = threadIdx.x; p < P.nPhi; p += blockDim.x)
-    if (s_cnt[p]) s_base[p] += atomicAdd(&D.phi_cursor[p], s_cnt[p]);
-  __syncthreads();
-  if (rec.phi_flags != 0xffffffffu) D.rec_col[s_base[phi] + rank] = rec;
 }
 
 // ---- K2: one CTA per phi column ------------------------------------------------------------------------
@@ -586,8 +578,57 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
     }
     return;
   }
-  const int off = D.phi_off[phi];
-  const RayRecord *recs = D.rec_col + off;
+  // ---- gather this column's records from the per-CTA windows k_project wrote (replaces a scatter pass)
+  __shared__ int s_warp[33];
+  __shared__ int s_off;
+  {
+    // first slot of this column in rec_col = sum of the record counts of the columns before it
+    int part = 0;
+    for (int p = tid; p < phi; p += blockDim.x) part += D.phi_hist[p];
+    for (int ofs = 16; ofs > 0; ofs >>= 1) part += __shfl_xor_sync(0xffffffffu, part, ofs);
+    if (tid == 0) s_off = 0;
+    __syncthreads();
+    if (lane_id() == 0 && part) atomicAdd(&s_off, part);
+    __syncthreads();
+  }
+  const int off = s_off;
+  RayRecord *recs = D.rec_col + off;
+  {
+    const int nb = (F.n_total + 255) / 256;              // CTAs of k_project
+    const int per = (nb + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int b0 = min(tid * per, nb), b1 = min(b0 + per, nb);
+    int mine = 0;
+    for (int b = b0; b < b1; b++) mine += (int)(__ldg(&D.rec_dir[(size_t)b * P.nPhi + phi]) & 0xffffu);
+    // exclusive scan of `mine` over threads (thread order == CTA order == point order)
+    int incl = mine;
+    const int lane = lane_id(), w = tid >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int ofs = 1; ofs < 32; ofs <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, ofs);
+      if (lane >= ofs) incl += t;
+    }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      int sv = lane < nw ? s_warp[lane] : 0, si = sv;
+#pragma unroll
+      for (int ofs = 1; ofs < 32; ofs <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, si, ofs);
+        if (lane >= ofs) si += t;
+      }
+      if (lane < nw) s_warp[lane] = si - sv;
+    }
+    __syncthreads();
+    int dst = s_warp[w] + incl - mine;
+    for (int b = b0; b < b1; b++) {
+      const uint32_t d = __ldg(&D.rec_dir[(size_t)b * P.nPhi + phi]);
+      const int c = (int)(d & 0xffffu);
+      const RayRecord *src = D.rec_lin + (size_t)b * 256 + (d >> 16);
+      for (int r = 0; r < c; r++) recs[dst + r] = src[r];
+      dst += c;
+    }
+    __syncthreads();
+  }
   MLM_PHASE(0);
 
   // shared memory: [miss bitmap][end-cell bitmap][radix counters][warp sums][odds table][k_reach][keys A][keys B]
@@ -775,7 +816,9 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
       D.hit_p[idx] = __uint_as_float(s_head_p[k]);
       D.hit_t[idx] = stamp;
       // bucket activation stamp (libstdc++ iteration order)
-      atomicMin(&act[libstdcxx_bucket(vector_hash3(rk, phi, zk), F.bucket_count)], stamp);
+      const uint32_t bucket = libstdcxx_bucket(vector_hash3(rk, phi, zk), F.bucket_count);
+      D.hit_bucket[idx] = bucket;
+      atomicMin(&act[bucket], stamp);
       // p_w = T_wa * centre  (identity rotation: one add per axis), src/map_local.cpp:151
       double2 cxy = __ldg(&P.centre_xy[phi * P.nRho + rk]);
       CellRef cr = locate_cell(P, cxy.x + F.t_wa[0], cxy.y + F.t_wa[1], __ldg(&P.centre_z[zk]) + F.t_wa[2]);
@@ -785,7 +828,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
         D.hit_next[idx] = kLvgEmpty;
         continue;
       }
-      int old = atomicExch(&D.lvg_head[lv], idx);
+      int old = atomicExch(&D.lvg[lv].x, idx);
       D.hit_next[idx] = old;
       if (old == kLvgEmpty) {
         int tp = agg_inc(&fc->n_touched);
@@ -878,7 +921,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
         fc->error = kErrInternal;
         continue;
       }
-      int old = atomicAdd(&D.lvg_miss[lv], 1);
+      int old = atomicAdd(&D.lvg[lv].y, 1);
       if (old == 0) {
         int tp = agg_inc(&fc->n_touched);
         if (tp < P.max_touched) D.touched[tp] = (uint32_t)lv; else fc->error = kErrCapacity;
@@ -914,30 +957,28 @@ __device__ __constant__ uint32_t c_bucket_chain[kBucketChainLen] = {
 // ---- K5: clamped log-odds fusion, one thread per touched cell (map_local.cpp:147-207) ---------------
 constexpr int kFuseLocal = 16;
 __global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D) {
-  const FrameParams &F = *D.fp;
+#ifdef MLM_FUSE_TIMING
+  unsigned long long t_start;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+#endif
+  const FrameParams F = *D.fp;  // by value: no reloads behind the aliasing stores below
   FrameCounters *fc = D.fc[F.parity];
   const uint32_t *act = D.act[F.parity];
+  const int n_hit_frame = fc->n_hit;
   // a frame that crosses a libstdc++ rehash needs the slow ordering pass first (host re-launches)
-  if (F.order_mode == 0 && fc->n_hit > (int)F.bucket_count) {
+  if (F.order_mode == 0 && n_hit_frame > (int)F.bucket_count) {
     if (blockIdx.x == 0 && threadIdx.x == 0) fc->overflow = 1;
     return;
   }
   const int n = min(fc->n_touched, P.max_touched);
   const int dxy = P.lvg_dim_xy;
+  const unsigned long long kClaimed64 = (unsigned long long)(uint32_t)kLvgClaimed;  // {head = claimed, miss = 0}
+  const unsigned long long kEmpty64 = (unsigned long long)(uint32_t)kLvgEmpty;      // {head = empty,   miss = 0}
   int my_touched = 0, my_obs = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t e = D.touched[i];
     const int lv = (int)(e & ~kTouchedHitTag);
-    // A cell with both hits and misses appears twice in the touched list.  The first thread to
-    // swap in kLvgClaimed owns the cell; the other one only restores the empty marker.
-    const int head = atomicExch(&D.lvg_head[lv], kLvgClaimed);
-    if (head == kLvgClaimed) {
-      D.lvg_head[lv] = kLvgEmpty;
-      continue;
-    }
-    const int mc = D.lvg_miss[lv];
-    D.lvg_miss[lv] = 0;
-    if (!(head != kLvgEmpty && mc > 0)) D.lvg_head[lv] = kLvgEmpty;  // single entry: restore ourselves
+    // subbox of this cell (independent of the claim below, so its load overlaps the atomic)
     int c[3] = {lv % dxy + F.lvg_base[0], (lv / dxy) % dxy + F.lvg_base[1], lv / (dxy * dxy) + F.lvg_base[2]};
     int g[3], sub;
     {
@@ -949,65 +990,75 @@ __global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D) {
       sub = (l[2] * P.n + l[1]) * P.n + l[0];
     }
     const int ls = lsg_index(P, F, g);
-    const int block = ls >= 0 ? D.lsg_block[ls] : -3;
+    const int block = ls >= 0 ? __ldcg(&D.lsg_block[ls]) : -3;
+    // A cell with both hits and misses appears twice in the touched list.  The first thread to swap in
+    // the claimed marker owns the cell (and gets head + miss count in one 64-bit exchange); the other
+    // one only restores the empty marker.
+    unsigned long long *slot = reinterpret_cast<unsigned long long *>(&D.lvg[lv]);
+    const unsigned long long old = atomicExch(slot, kClaimed64);
+    const int head = (int)(uint32_t)old, mc = (int)(old >> 32);
+    if (head == kLvgClaimed) {
+      *slot = kEmpty64;
+      continue;
+    }
+    if (!(head != kLvgEmpty && mc > 0)) *slot = kEmpty64;  // single entry: restore ourselves
     if (block < 0) continue;  // collapsed subbox (allocate_ram false) or pool error
     const size_t addr = (size_t)block * P.cell_stride + sub;
     float lo = D.pool_lo[addr];
     char occ = D.pool_occ[addr];
     my_touched++;
 
-    // hits in the reference's unordered_map iteration order: descending (bucket activation, insert stamp)
+    // hits in the reference's unordered_map iteration order: descending (bucket activation, insert stamp).
+    // Up to 4 hits per cell are ordered in registers; longer lists use selection by repeated traversal.
     if (head != kLvgEmpty) {
-      int hidx[kFuseLocal];
-      uint64_t hst[kFuseLocal];
+      uint64_t st0 = 0, st1 = 0, st2 = 0, st3 = 0;
+      float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
       int cnt = 0;
       for (int h = head; h != kLvgEmpty; h = D.hit_next[h]) {
-        if (cnt < kFuseLocal) {
-          int key = D.hit_key[h];
-          int zk = key / (P.nRho * P.nPhi), rem = key - zk * (P.nRho * P.nPhi);
-          int pk = rem / P.nRho, rk = rem - pk * P.nRho;
-          uint32_t a = act[libstdcxx_bucket(vector_hash3(rk, pk, zk), F.bucket_count)];
-          uint64_t st = ((uint64_t)a << 32) | D.hit_t[h];
-          int j = cnt;
-          while (j > 0 && hst[j - 1] < st) {
-            hst[j] = hst[j - 1];
-            hidx[j] = hidx[j - 1];
-            j--;
-          }
-          hst[j] = st;
-          hidx[j] = h;
+        if (cnt < 4) {
+          const uint64_t st = ((uint64_t)act[D.hit_bucket[h]] << 32) | D.hit_t[h];
+          const float ph = D.hit_p[h];
+          if (cnt == 0) { st0 = st; p0 = ph; }
+          else if (cnt == 1) { st1 = st; p1 = ph; }
+          else if (cnt == 2) { st2 = st; p2 = ph; }
+          else { st3 = st; p3 = ph; }
         }
         cnt++;
       }
-      uint64_t prev = ~0ull;
-      for (int k = 0; k < cnt; k++) {
-        int h;
-        if (cnt <= kFuseLocal) {
-          h = hidx[k];
-        } else {  // long list: selection by repeated traversal
-          uint64_t best = 0;
-          h = -1;
-          for (int q = head; q != kLvgEmpty; q = D.hit_next[q]) {
-            int key = D.hit_key[q];
-            int zk = key / (P.nRho * P.nPhi), rem = key - zk * (P.nRho * P.nPhi);
-            int pk = rem / P.nRho, rk = rem - pk * P.nRho;
-            uint32_t a = act[libstdcxx_bucket(vector_hash3(rk, pk, zk), F.bucket_count)];
-            uint64_t st = ((uint64_t)a << 32) | D.hit_t[q];
-            if (st < prev && (h < 0 || st > best)) {
-              best = st;
-              h = q;
-            }
-          }
-          prev = best;
-        }
-        // src/map_local.cpp:157-171
+      auto apply_hit = [&](float ph) {  // src/map_local.cpp:157-171
         if (lo < P.lo_max) {
-          lo = __fadd_rn(lo, logit_f(D.hit_p[h], P.log10f_fma));
+          lo = __fadd_rn(lo, logit_f(ph, P.log10f_fma));
           lo = lo > P.lo_max ? P.lo_max : lo;
         }
         if (lo > P.lo_sh && occ != 'o') {
           occ = 'o';
           my_obs++;
+        }
+      };
+      if (cnt <= 4) {
+        // descending sorting network on (stamp, p); unused slots have stamp 0 and sink to the end
+#define MLM_CSWAP(sa, pa, sb, pb) if (sa < sb) { uint64_t ts = sa; sa = sb; sb = ts; float tp = pa; pa = pb; pb = tp; }
+        MLM_CSWAP(st0, p0, st1, p1) MLM_CSWAP(st2, p2, st3, p3) MLM_CSWAP(st0, p0, st2, p2)
+        MLM_CSWAP(st1, p1, st3, p3) MLM_CSWAP(st1, p1, st2, p2)
+#undef MLM_CSWAP
+        apply_hit(p0);
+        if (cnt > 1) apply_hit(p1);
+        if (cnt > 2) apply_hit(p2);
+        if (cnt > 3) apply_hit(p3);
+      } else {
+        uint64_t prev = ~0ull;
+        for (int k = 0; k < cnt; k++) {
+          uint64_t best = 0;
+          int hb = -1;
+          for (int q = head; q != kLvgEmpty; q = D.hit_next[q]) {
+            const uint64_t st = ((uint64_t)act[D.hit_bucket[q]] << 32) | D.hit_t[q];
+            if (st < prev && (hb < 0 || st > best)) {
+              best = st;
+              hb = q;
+            }
+          }
+          prev = best;
+          apply_hit(D.hit_p[hb]);
         }
       }
     }
@@ -1039,13 +1090,27 @@ __global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D) {
     if (my_obs) atomicAdd(&fc->obs_delta, my_obs);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) fc->fused = 1;
+#ifdef MLM_FUSE_TIMING
+  {
+    unsigned long long t_mid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_mid));
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.x < 1000) {
+      unsigned long long t_end;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+      D.debug_cycles[3 * blockIdx.x] = (long long)t_start;
+      D.debug_cycles[3 * blockIdx.x + 1] = (long long)t_mid;
+      D.debug_cycles[3 * blockIdx.x + 2] = (long long)t_end;
+    }
+  }
+#endif
 
   // ---- reset of the NEXT frame's scratch (double-buffered, nothing below is read by this launch) ----
   {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     // bucket count the hit map will have at the start of the next frame (clear() keeps the buckets)
     uint32_t B = F.bucket_count;
-    const uint32_t n_hit = (uint32_t)fc->n_hit;
+    const uint32_t n_hit = (uint32_t)n_hit_frame;
     if (n_hit > 0 && B == 1) B = 13;
     for (int c = 0; c + 1 < kBucketChainLen && n_hit > B; c++)
       if (c_bucket_chain[c] == B) B = c_bucket_chain[c + 1];

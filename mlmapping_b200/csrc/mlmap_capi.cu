@@ -376,16 +376,14 @@ int run_frame(mlm_map *h, bool depth, const void *d_in, int rows, int cols, int 
 #define MLM_MARK(i) do { if (mark) cudaEventRecord(h->kev[i], s); } while (0)
     MLM_MARK(0);
     if (depth)
-      k_project<true><<<full_grid, 256, (size_t)P.nPhi * sizeof(int), s>>>(P, h->D);
+      k_project<true><<<full_grid, 256, (size_t)2 * P.nPhi * sizeof(int), s>>>(P, h->D);
     else
-      k_project<false><<<full_grid, 256, (size_t)P.nPhi * sizeof(int), s>>>(P, h->D);
+      k_project<false><<<full_grid, 256, (size_t)2 * P.nPhi * sizeof(int), s>>>(P, h->D);
     MLM_MARK(1);
-    k_scatter<<<full_grid, 256, (size_t)(2 * P.nPhi + 256) * sizeof(int), s>>>(P, h->D);
-    MLM_MARK(2);
     k_column<<<P.nPhi, kColThreads, h->col_smem_bytes, s>>>(P, h->D);
-    MLM_MARK(3);
+    MLM_MARK(2);
     k_fuse<<<h->sm_count * 4, 256, 0, s>>>(P, h->D);
-    MLM_MARK(4);
+    MLM_MARK(3);
 #undef MLM_MARK
   };
   if (prof || !h->use_graph) {
@@ -407,7 +405,7 @@ int run_frame(mlm_map *h, bool depth, const void *d_in, int rows, int cols, int 
     }
     CUDA_TRY(cudaGraphLaunch(ge, s));
   }
-  h->launches += 4;
+  h->launches += 3;
   CUDA_TRY(cudaStreamSynchronize(s));
   CUDA_TRY(cudaGetLastError());
 
@@ -727,6 +725,7 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   TRY(dev_alloc(h, &D.col_ticket, 1));
   TRY(dev_alloc(h, &D.rec_lin, (size_t)P.max_points));
   TRY(dev_alloc(h, &D.rec_col, (size_t)P.max_points));
+  TRY(dev_alloc(h, &D.rec_dir, (size_t)((P.max_points + 255) / 256) * P.nPhi));
   TRY(dev_alloc(h, &D.phi_hist, (size_t)P.nPhi));
   TRY(dev_alloc(h, &D.phi_off, (size_t)P.nPhi + 1));
   TRY(dev_alloc(h, &D.phi_cursor, (size_t)P.nPhi));
@@ -735,6 +734,7 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   TRY(dev_alloc(h, &D.hit_p, (size_t)P.max_hits));
   TRY(dev_alloc(h, &D.hit_t, (size_t)P.max_hits));
   TRY(dev_alloc(h, &D.hit_next, (size_t)P.max_hits));
+  TRY(dev_alloc(h, &D.hit_bucket, (size_t)P.max_hits));
   TRY(dev_alloc(h, &D.miss_bitmap, (size_t)P.nPhi * P.col_words));
   h->act_cap = chain_cover((uint32_t)P.max_hits);
   if (h->act_cap == 0) {
@@ -744,8 +744,7 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   }
   TRY(dev_alloc(h, &D.act[0], (size_t)h->act_cap));
   TRY(dev_alloc(h, &D.act[1], (size_t)h->act_cap));
-  TRY(dev_alloc(h, &D.lvg_head, (size_t)lvg_cells));
-  TRY(dev_alloc(h, &D.lvg_miss, (size_t)lvg_cells));
+  TRY(dev_alloc(h, &D.lvg, (size_t)lvg_cells));
   TRY(dev_alloc(h, &D.touched, (size_t)P.max_touched));
   TRY(dev_alloc(h, &D.lsg_flag, (size_t)lsg_cells));
   TRY(dev_alloc(h, &D.lsg_block, (size_t)lsg_cells));
@@ -768,8 +767,10 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   TRY(dev_alloc(h, &h->d_seq_b, (size_t)P.max_hits));
 
   // initial state
-  CUDA_TRY_H(cudaMemset(D.lvg_head, 0xff, (size_t)lvg_cells * 4));
-  CUDA_TRY_H(cudaMemset(D.lvg_miss, 0, (size_t)lvg_cells * 4));
+  {
+    std::vector<int2> init((size_t)lvg_cells, make_int2(kLvgEmpty, 0));
+    CUDA_TRY_H(cudaMemcpy(D.lvg, init.data(), init.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  }
   CUDA_TRY_H(cudaMemset(D.lsg_flag, 0, (size_t)lsg_cells * 4));
   CUDA_TRY_H(cudaMemset(D.lsg_block, 0xff, (size_t)lsg_cells * 4));
   CUDA_TRY_H(cudaMemset(D.ht_key, 0xff, (size_t)ht_cap * 8));

@@ -113,7 +113,9 @@ __global__ void k_order_final(MapParams P, DeviceBuffers D, uint32_t *act, const
   if (j < n) {
     int h = seq[j];
     D.hit_t[h] = (uint32_t)j;
-    atomicMin(&act[hit_bucket(P, D.hit_key[h], B)], (uint32_t)j);
+    const uint32_t b = hit_bucket(P, D.hit_key[h], B);
+    D.hit_bucket[h] = b;
+    atomicMin(&act[b], (uint32_t)j);
   }
 }
 

@@ -102,23 +102,24 @@ struct DeviceBuffers {
   FrameParams *fp;
   FrameCounters *fc[2];   // double-buffered: frame f uses fc[f&1], k_fuse clears the other one
   // K1/K1b
-  RayRecord *rec_lin;     // [max_points] in point order (phi_flags==~0u: no record)
-  RayRecord *rec_col;     // [max_points] grouped by phi column
-  int *phi_hist;          // [nPhi]
-  int *phi_off;           // [nPhi+1]
-  int *phi_cursor;        // [nPhi]
+  RayRecord *rec_lin;     // [max_points] per k_project CTA: a 256-slot window, records grouped by column
+  uint32_t *rec_dir;      // [ceil(max_points/256)][nPhi] directory of those windows: offset << 16 | count
+  RayRecord *rec_col;     // [max_points] gathered by k_column: contiguous per phi column
+  int *phi_hist;          // [nPhi] records per column
+  int *phi_off;           // [nPhi+1] (unused)
+  int *phi_cursor;        // [nPhi] (unused)
   uint64_t *col_scratch;  // [max_points*contrib_per_point] sort spill for oversized columns
   // per-frame hit map / miss set
   int *hit_key;           // [max_hits] awareness linear index (mapIdx)
   float *hit_p;           // [max_hits]
   uint32_t *hit_t;        // [max_hits] first-insert stamp (t*32+substep) or virtual position
   int *hit_next;          // [max_hits] next hit in the same voxel's list
+  uint32_t *hit_bucket;   // [max_hits] libstdc++ bucket of the key at this frame's bucket count
   uint32_t *miss_bitmap;  // [nPhi*col_words]
   uint32_t *act[2];       // [bucket capacity] bucket activation stamps, double-buffered like fc
   int *col_ticket;        // completion ticket of k_column (last CTA resolves the touched subboxes)
   // local voxel / submap grids
-  int *lvg_head;          // [lvg cells] head of hit list, -1 empty
-  int *lvg_miss;          // [lvg cells] number of miss cells this frame
+  int2 *lvg;              // [lvg cells] .x head of this frame's hit list (-1 empty), .y number of miss cells
   uint32_t *touched;      // [max_touched] local voxel index (| kTouchedHitTag)
   int *lsg_flag;          // [lsg cells]
   int *lsg_block;         // [lsg cells] pool block of that subbox this frame
