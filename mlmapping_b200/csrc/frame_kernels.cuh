@@ -228,11 +228,15 @@ __device__ __forceinline__ int block_exclusive_scan(int *data, int n, int *s_war
 
 template <bool kDepth>
 __global__ void __launch_bounds__(256) k_project(MapParams P, DeviceBuffers D) {
-  extern __shared__ int s_hist[];  // [nPhi] counts, then [nPhi] offsets
+  extern __shared__ int s_hist[];  // [nPhi] counts, [nPhi] offsets, [nPhi] contribution bounds
   __shared__ int s_cnt[3];
   __shared__ int s_warp[33];
   const FrameParams &F = *D.fp;
-  for (int i = threadIdx.x; i < P.nPhi; i += blockDim.x) s_hist[i] = 0;
+  int *s_bnd = s_hist + 2 * P.nPhi;
+  for (int i = threadIdx.x; i < P.nPhi; i += blockDim.x) {
+    s_hist[i] = 0;
+    s_bnd[i] = 0;
+  }
   if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -285,9 +289,24 @@ __global__ void __launch_bounds__(256) k_project(MapParams P, DeviceBuffers D) {
       unsigned follow = lane < 31 ? (sames >> (lane + 1)) : 0u;
       int m = 1 + (__ffs(~follow) - 1);  // consecutive followers that repeat this cell
       rec.phi_flags |= (uint32_t)m << kRecCountShift;
-      rank = atomicAdd(&s_hist[rec.phi_flags & kRecPhiMask], 1);
+      // upper bound of the hit contributions of this record: 1 + 2*min(K(rho), nRho-1-rho)
+      if (rec.phi_flags & kRecInside)
+        atomicAdd(&s_bnd[rec.phi_flags & kRecPhiMask], 1 + 2 * min(__ldg(&P.k_reach[rec.rho]), P.nRho - 1 - rec.rho));
     } else {
       rec.phi_flags = 0xffffffffu;
+    }
+    // stable rank of the record among the CTA's records of the same column: point order is kept, so
+    // k_column's record list of a column is ordered by point stamp without any sorting
+    const bool holds = rec.phi_flags != 0xffffffffu;
+    const int myphi = holds ? (int)(rec.phi_flags & kRecPhiMask) : -1 - lane;
+    const unsigned peers = __match_any_sync(0xffffffffu, myphi);
+    const int before = __popc(peers & ((1u << lane) - 1));
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5;
+    for (int w = 0; w < nwarps; w++) {
+      if (warp == w && holds) rank = s_hist[myphi] + before;
+      __syncwarp();
+      if (warp == w && holds && before == 0) s_hist[myphi] += __popc(peers);
+      __syncthreads();
     }
   }
   // CTA-level counters
@@ -306,6 +325,7 @@ __global__ void __launch_bounds__(256) k_project(MapParams P, DeviceBuffers D) {
     const int c = s_hist[p];
     s_off[p] = c;
     if (c) atomicAdd(&D.phi_hist[p], c);
+    if (s_bnd[p]) atomicAdd(&D.phi_bound[p], s_bnd[p]);
   }
   __syncthreads();
   block_exclusive_scan(s_off, P.nPhi, s_warp);
@@ -332,13 +352,14 @@ constexpr int kColWarps = kColThreads / 32;
 constexpr int kRadixBits = 8;
 constexpr int kRadixDigits = 1 << kRadixBits;
 constexpr int kCellBits = 20;
+constexpr int kLongChain = 32;  // contributions per cell from which the fold claims the cell early
+constexpr int kMapCap = 4096;  // records per column addressed through the shared-memory index map
 
-// contribution key, sorted by (cell, t):
-//   [.. : 12+tbits] cell in column | [12+tbits-1 : 12] point stamp t | [11:7] substep | [6:0] run length
-// (cell, t) is unique per contribution (one record reaches a cell at most once: every contribution
-// of a record has a different rho), so substep and run length ride along as payload.
-__device__ __forceinline__ uint64_t contrib_key(int cell, uint32_t t, int substep, int reps, int tbits) {
-  return ((uint64_t)(uint32_t)cell << (12 + tbits)) | ((uint64_t)t << 12) | ((uint64_t)substep << 7) | (uint64_t)reps;
+// contribution key:  [.. : 12+kbits] cell in column | [12+kbits-1 : 12] record index k in the column
+// (records are in point order) | [11:7] substep | [6:0] run length.  Contributions are generated in
+// insertion order (k, substep), so a STABLE sort by cell alone yields every cell's insertion sequence.
+__device__ __forceinline__ uint64_t contrib_key(int cell, int k, int substep, int reps, int cell_shift) {
+  return ((uint64_t)(uint32_t)cell << cell_shift) | ((uint64_t)(uint32_t)k << 12) | ((uint64_t)substep << 7) | (uint64_t)reps;
 }
 
 // One stable LSD radix pass over 8 key bits for the whole CTA (src -> dst), keys in shared or
@@ -444,16 +465,16 @@ __device__ __forceinline__ WalkStart walk_prepare(const MapParams &P, int rho, i
 __device__ __forceinline__ void walk_mark(const MapParams &P, uint32_t *s_miss, double rate, int rho, int z) {
   const int lane = lane_id();
   const double zd = (double)z;
-  for (int w = (rho - 1) >> 5; w >= 0; --w) {
-    int r = (w << 5) + lane;
+  const int w_top = (rho - 1) >> 5;
+  double diff = (double)(rho - (w_top << 5) - lane);  // rho - r for r = 32*w + lane; +32 (exact) per step down
+  for (int w = w_top; w >= 0; --w, diff += 32.0) {
+    const int r = (w << 5) + lane;
     bool valid = r >= 1 && r <= rho - 1;
-    int zc = 0;
-    if (valid) {
-      zc = round_to_int_x86(zd - (double)(rho - r) * rate);
-      valid = zc >= 0 && zc < P.nZ;
-    }
-    unsigned peers = __match_any_sync(0xffffffffu, valid ? zc : -1 - lane);
-    if (valid && lane == __ffs(peers) - 1) atomicOr(&s_miss[zc * P.words_per_row + w], peers);
+    // |v| < 2^31 on every valid lane of a sane ray; round_to_int_x86 handles the rest exactly as x86 would
+    const int zc = round_to_int_x86(zd - diff * rate);
+    valid = valid && zc >= 0 && zc < P.nZ;
+    const unsigned peers = __match_any_sync(0xffffffffu, valid ? zc : -1 - lane);
+    if (valid && (peers & ((1u << lane) - 1)) == 0) atomicOr(&s_miss[zc * P.words_per_row + w], peers);
   }
 }
 // one prepared ray per lane (need = this lane has one); the warp marks them one after the other
@@ -545,7 +566,7 @@ __device__ __forceinline__ void resolve_subboxes(const MapParams &P, const Frame
 
 // bytes of k_column's shared memory in front of the two key buffers
 __host__ __device__ inline size_t col_smem_prefix_bytes(int col_words, int nRho) {
-  return (((size_t)2 * col_words + kCntTotal + kColWarps + (size_t)kOddsRows * nRho + nRho) * 4 + 15) & ~(size_t)15;
+  return (((size_t)2 * col_words + kCntTotal + kColWarps + (size_t)kOddsRows * nRho + nRho + kMapCap) * 4 + 15) & ~(size_t)15;
 }
 
 #ifdef MLM_PHASE_TIMING
@@ -578,11 +599,28 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
     }
     return;
   }
-  // ---- gather this column's records from the per-CTA windows k_project wrote (replaces a scatter pass)
+  MLM_PHASE(15);
+  // shared memory: [miss bitmap][end-cell bitmap][radix counters][warp sums][odds table][k_reach][record index map][keys A][keys B]
+  uint32_t *s_miss = reinterpret_cast<uint32_t *>(s_raw);
+  uint32_t *s_end = s_miss + P.col_words;
+  uint32_t *s_cnt = s_end + P.col_words;
+  uint32_t *s_wsum = s_cnt + kCntTotal;
+  float *s_odds = reinterpret_cast<float *>(s_wsum + kColWarps);
+  int *s_reach = reinterpret_cast<int *>(s_odds + kOddsRows * P.nRho);
+  int *s_map = s_reach + P.nRho;
+  uint64_t *s_keys = reinterpret_cast<uint64_t *>(s_raw + col_smem_prefix_bytes(P.col_words, P.nRho));
+  for (int i = tid; i < kOddsRows * P.nRho; i += blockDim.x) s_odds[i] = __ldg(&P.odds_table[i]);
+  for (int i = tid; i < P.nRho; i += blockDim.x) s_reach[i] = __ldg(&P.k_reach[i]);
+  // ---- locate this column's records in the per-CTA windows k_project wrote (replaces a scatter pass):
+  // s_map[k] = index into rec_lin of the column's k-th record
   __shared__ int s_warp[33];
   __shared__ int s_off;
-  {
-    // first slot of this column in rec_col = sum of the record counts of the columns before it
+  const int bound_c = D.phi_bound[phi];                  // upper bound of this column's hit contributions
+  const bool in_smem = bound_c <= P.sort_cap_smem;       // sort buffer in shared memory, else global spill (slow, exact)
+  const bool big = n_c > kMapCap;                      // more records than the shared-memory index map holds
+  int off = 0;
+  if (big || !in_smem) {
+    // rare: first slot of this column in the global spill / record areas = records of the columns before it
     int part = 0;
     for (int p = tid; p < phi; p += blockDim.x) part += D.phi_hist[p];
     for (int ofs = 16; ofs > 0; ofs >>= 1) part += __shfl_xor_sync(0xffffffffu, part, ofs);
@@ -590,16 +628,24 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
     __syncthreads();
     if (lane_id() == 0 && part) atomicAdd(&s_off, part);
     __syncthreads();
+    off = s_off;
   }
-  const int off = s_off;
-  RayRecord *recs = D.rec_col + off;
   {
     const int nb = (F.n_total + 255) / 256;              // CTAs of k_project
     const int per = (nb + (int)blockDim.x - 1) / (int)blockDim.x;
     const int b0 = min(tid * per, nb), b1 = min(b0 + per, nb);
+    uint32_t dsave[4];
     int mine = 0;
-    for (int b = b0; b < b1; b++) mine += (int)(__ldg(&D.rec_dir[(size_t)b * P.nPhi + phi]) & 0xffffu);
-    // exclusive scan of `mine` over threads (thread order == CTA order == point order)
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      dsave[q] = 0;
+      if (b0 + q < b1) {
+        dsave[q] = __ldg(&D.rec_dir[(size_t)(b0 + q) * P.nPhi + phi]);
+        mine += (int)(dsave[q] & 0xffffu);
+      }
+    }
+    for (int b = b0 + 4; b < b1; b++) mine += (int)(__ldg(&D.rec_dir[(size_t)b * P.nPhi + phi]) & 0xffffu);
+    // exclusive scan of `mine` over threads (thread order == CTA order)
     int incl = mine;
     const int lane = lane_id(), w = tid >> 5, nw = blockDim.x >> 5;
 #pragma unroll
@@ -621,102 +667,94 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
     __syncthreads();
     int dst = s_warp[w] + incl - mine;
     for (int b = b0; b < b1; b++) {
-      const uint32_t d = __ldg(&D.rec_dir[(size_t)b * P.nPhi + phi]);
+      const uint32_t d = b - b0 < 4 ? dsave[b - b0] : __ldg(&D.rec_dir[(size_t)b * P.nPhi + phi]);
       const int c = (int)(d & 0xffffu);
-      const RayRecord *src = D.rec_lin + (size_t)b * 256 + (d >> 16);
-      for (int r = 0; r < c; r++) recs[dst + r] = src[r];
+      const int src = b * 256 + (int)(d >> 16);
+      for (int r = 0; r < c; r++) {
+        if (big) D.rec_col[off + dst + r] = D.rec_lin[src + r];  // oversized column: materialise the records
+        else s_map[dst + r] = src + r;
+      }
       dst += c;
     }
-    __syncthreads();
   }
+  __syncthreads();
+  const RayRecord *recs = big ? D.rec_col + off : D.rec_lin;
+#define REC_AT(i) recs[big ? (i) : s_map[i]]
   MLM_PHASE(0);
 
-  // shared memory: [miss bitmap][end-cell bitmap][radix counters][warp sums][odds table][k_reach][keys A][keys B]
-  uint32_t *s_miss = reinterpret_cast<uint32_t *>(s_raw);
-  uint32_t *s_end = s_miss + P.col_words;
-  uint32_t *s_cnt = s_end + P.col_words;
-  uint32_t *s_wsum = s_cnt + kCntTotal;
-  float *s_odds = reinterpret_cast<float *>(s_wsum + kColWarps);
-  int *s_reach = reinterpret_cast<int *>(s_odds + kOddsRows * P.nRho);
-  uint64_t *s_keys = reinterpret_cast<uint64_t *>(s_raw + col_smem_prefix_bytes(P.col_words, P.nRho));
-  for (int i = tid; i < kOddsRows * P.nRho; i += blockDim.x) s_odds[i] = __ldg(&P.odds_table[i]);
-  for (int i = tid; i < P.nRho; i += blockDim.x) s_reach[i] = __ldg(&P.k_reach[i]);
   __shared__ int s_nk;
   __shared__ int s_nmiss;
-  __shared__ int s_bound;
   __shared__ int s_nhead;
   __shared__ int s_next;
+  __shared__ int s_nlong;
   for (int i = tid; i < 2 * P.col_words; i += blockDim.x) s_miss[i] = 0;
   if (tid == 0) {
     s_nk = 0;
     s_nmiss = 0;
-    s_bound = 0;
     s_next = 0;
+    s_nlong = 0;
   }
   __syncthreads();
-  // upper bound of this column's contributions: 1 + 2*min(K(rho), nRho-1-rho) per inside record
-  {
-    int bound = 0;
-    for (int i = tid; i < n_c; i += blockDim.x) {
-      RayRecord rc = recs[i];
-      if (rc.phi_flags & kRecInside) bound += 1 + 2 * min(s_reach[rc.rho], P.nRho - 1 - rc.rho);
-    }
-    for (int ofs = 16; ofs > 0; ofs >>= 1) bound += __shfl_xor_sync(0xffffffffu, bound, ofs);
-    if (lane_id() == 0 && bound) atomicAdd(&s_bound, bound);
-  }
-  __syncthreads();
-  // sort buffer: shared memory when the bound fits, else the global spill region (slow, still exact)
-  const bool in_smem = s_bound <= P.sort_cap_smem;
   uint64_t *keys = in_smem ? s_keys : D.col_scratch + (size_t)2 * off * P.contrib_per_point;
   uint64_t *keys_alt = in_smem ? s_keys + P.sort_cap_smem : keys + (size_t)n_c * P.contrib_per_point;
-  const int tbits = F.tbits;
+  int kbits = 1;
+  while ((1 << kbits) < n_c) kbits++;
+  const int cell_shift = 12 + kbits;
+  const int cell_sentinel = 1 << P.cell_bits;  // sorts behind every real cell
+  __syncthreads();
+
   MLM_PHASE(1);
-  // (a) contributions, update_hits src/map_awareness.cpp:135-171
+  // (a) contributions, update_hits src/map_awareness.cpp:135-171.  Record k of the column (point order)
+  // owns a fixed window of 1 + 2*min(K(rho), nRho-1-rho) slots at the prefix sum of the windows before
+  // it, so the contribution array is generated in insertion order (k, substep); neighbours that fall
+  // outside the z range leave a sentinel.
+  int *s_pos = reinterpret_cast<int *>(keys_alt);
   for (int i = tid; i < n_c; i += blockDim.x) {
-    RayRecord rc = recs[i];
+    const RayRecord rc = REC_AT(i);
+    s_pos[i] = (rc.phi_flags & kRecInside) ? 1 + 2 * min(s_reach[rc.rho], P.nRho - 1 - rc.rho) : 0;
+  }
+  __syncthreads();
+  const int n_k = block_exclusive_scan(s_pos, n_c, s_warp);  // == bound_c
+  for (int i = tid; i < n_c; i += blockDim.x) {
+    const RayRecord rc = REC_AT(i);
     if (!(rc.phi_flags & kRecInside)) continue;
     const int rho = rc.rho, z = rc.z;
     const int reps = (int)((rc.phi_flags >> kRecCountShift) & kRecCountMask);
     if (P.visibility_check) atomicOr(&s_end[z * P.words_per_row + (rho >> 5)], 1u << (rho & 31));
-    double rate = ray_rate(P, rho, z);
-    int K = s_reach[rho];
-    int cnt = 1;
-    int zp[kDiffRange], zm[kDiffRange];
-    int dmax = 0;
-    for (int d = 1; d <= K && rho + d < P.nRho; d++) {
-      zp[d - 1] = round_to_int_x86((double)z + (double)d * rate);
-      zm[d - 1] = round_to_int_x86((double)z - (double)d * rate);
-      cnt += (zp[d - 1] >= 0 && zp[d - 1] < P.nZ) + (zm[d - 1] >= 0 && zm[d - 1] < P.nZ);
-      dmax = d;
-    }
-    int pos = atomicAdd(&s_nk, cnt);
-    keys[pos++] = contrib_key(z * P.nRho + rho, rc.t, 0, reps, tbits);
+    const double rate = ray_rate(P, rho, z);
+    const int dmax = min(s_reach[rho], P.nRho - 1 - rho);
+    int pos = s_pos[i];
+    keys[pos++] = contrib_key(z * P.nRho + rho, i, 0, reps, cell_shift);
     for (int d = 1; d <= dmax; d++) {
-      if (zp[d - 1] >= 0 && zp[d - 1] < P.nZ) keys[pos++] = contrib_key(zp[d - 1] * P.nRho + rho + d, rc.t, 2 * d - 1, reps, tbits);
-      if (zm[d - 1] >= 0 && zm[d - 1] < P.nZ) keys[pos++] = contrib_key(zm[d - 1] * P.nRho + rho - d, rc.t, 2 * d, reps, tbits);
+      const int zp = round_to_int_x86((double)z + (double)d * rate);
+      const int zm = round_to_int_x86((double)z - (double)d * rate);
+      keys[pos++] = contrib_key(zp >= 0 && zp < P.nZ ? zp * P.nRho + rho + d : cell_sentinel, i, 2 * d - 1, reps, cell_shift);
+      keys[pos++] = contrib_key(zm >= 0 && zm < P.nZ ? zm * P.nRho + rho - d : cell_sentinel, i, 2 * d, reps, cell_shift);
     }
   }
   __syncthreads();
-  const int n_k = s_nk;
 
   MLM_PHASE(2);
-  // (b) stable LSD radix sort by (cell, t): bits [12, 12 + tbits + cell_bits)
+  // (b) stable LSD radix sort by cell only: bits [cell_shift, cell_shift + cell_bits + 1)
   {
-    const int hi_bit = 12 + tbits + P.cell_bits;
-    for (int shift = 12; shift < hi_bit; shift += kRadixBits) {
+    const int hi_bit = cell_shift + P.cell_bits + 1;
+    for (int shift = cell_shift; shift < hi_bit; shift += kRadixBits) {
       radix_pass(keys, keys_alt, n_k, shift, s_cnt, s_wsum);
       uint64_t *t = keys;
       keys = keys_alt;
       keys_alt = t;
     }
   }
-  const int cell_shift = 12 + tbits;
-  const uint64_t t_mask = (1ull << tbits) - 1;
+  const uint64_t k_mask = (1ull << kbits) - 1;
+
   MLM_PHASE(3);
-  // (c1) ordered list of segment heads (first contribution of every distinct cell) in the idle
-  // ping-pong buffer: s_head[h] = index into keys, s_head_p[h] = folded probability
+  // (c1) ordered list of segment heads (first contribution of every distinct cell) and a compact decode
+  // of every contribution, both in the idle ping-pong buffer:
+  //   s_head[h]  = index into keys of the h-th cell's first contribution
+  //   s_dec[i]   = odds-table index (25 bits) | run length - 1 (5 bits, bits 25..29) | last-of-cell (bit 30);
+  //                after the fold, s_dec[s_head[h]] holds the folded probability bits of cell h
   uint32_t *s_head = reinterpret_cast<uint32_t *>(keys_alt);
-  uint32_t *s_head_p = s_head + n_k;
+  uint32_t *s_dec = s_head + n_k;
   {
     const int W = kColWarps, w = tid >> 5, lane = lane_id();
     const int chunk = (((n_k + W - 1) / W) + 31) & ~31;
@@ -724,7 +762,20 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
     int cnt = 0;
     for (int base = beg; base < end; base += 32) {
       const int i = base + lane;
-      const bool head = i < end && (i == 0 || (keys[i - 1] >> cell_shift) != (keys[i] >> cell_shift));
+      bool head = false;
+      if (i < end) {
+        const uint64_t ki = keys[i];
+        const int cell = (int)(ki >> cell_shift);
+        if (cell != cell_sentinel) {
+          head = i == 0 || (int)(keys[i - 1] >> cell_shift) != cell;
+          const bool last = i + 1 >= n_k || (int)(keys[i + 1] >> cell_shift) != cell;
+          const int rk = cell - (cell / P.nRho) * P.nRho;
+          const int sstep = (int)((ki >> 7) & 31);
+          const int d = sstep == 0 ? 0 : ((sstep & 1) ? (sstep + 1) >> 1 : -(sstep >> 1));
+          const uint32_t oi = (uint32_t)((kDiffRange + d) * P.nRho + (rk - d));
+          s_dec[i] = oi | ((uint32_t)((ki & 127) - 1) << 25) | (last ? (1u << 30) : 0u);
+        }
+      }
       cnt += __popc(__ballot_sync(0xffffffffu, head));
     }
     if (lane == 0) s_wsum[w] = (uint32_t)cnt;
@@ -743,55 +794,53 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
     int pos = (int)s_wsum[w];
     for (int base = beg; base < end; base += 32) {
       const int i = base + lane;
-      const bool head = i < end && (i == 0 || (keys[i - 1] >> cell_shift) != (keys[i] >> cell_shift));
+      const bool head = i < end && (int)(keys[i] >> cell_shift) != cell_sentinel &&
+                        (i == 0 || (keys[i - 1] >> cell_shift) != (keys[i] >> cell_shift));
       const unsigned b = __ballot_sync(0xffffffffu, head);
       if (head) s_head[pos + __popc(b & ((1u << lane) - 1))] = (uint32_t)i;
       pos += __popc(b);
     }
   }
   __syncthreads();
-  // (c2) update_odds_hashmap fold: one thread per distinct cell, cells claimed dynamically so long
-  // chains do not serialise behind each other.  The chain p <- 1-(1-p)(1-odd) is inherently ordered;
-  // the next contribution (key + odds-table entry, both in shared memory) is fetched while the
-  // current one is folded.
+  // (c2) update_odds_hashmap fold, one thread per distinct cell (static: head h -> thread h, so the
+  // lanes of a warp stay in one loop).  The chain p <- 1-(1-p)(1-odd) is inherently ordered; it is
+  // flattened over (contribution, repeat) so that a lane never waits for another lane's run length,
+  // the next contribution is fetched one step ahead, and a lane leaves as soon as p saturates at 1
+  // (1 - (1-1)*(1-odd) == 1 for every later contribution).
   {
     const int n_head = s_nhead;
-    for (;;) {
-      const int h = atomicAdd(&s_next, 1);
-      if (h >= n_head) break;
-      int j = (int)s_head[h];
-      uint64_t kj = keys[j];
-      const int cell = (int)(kj >> cell_shift);
-      const int rk = cell - (cell / P.nRho) * P.nRho;
-      int sstep = (int)((kj >> 7) & 31);
-      int d = sstep == 0 ? 0 : ((sstep & 1) ? (sstep + 1) >> 1 : -(sstep >> 1));
-      float odd = s_odds[(kDiffRange + d) * P.nRho + (rk - d)];
-      int reps = (int)(kj & 127);
-      float p = odd;  // first insert: hit_idx_odds_hashmap[key] = odd
-      reps--;
-      for (;;) {
-        // prefetch the next contribution of this cell (independent of p)
-        const bool more = j + 1 < n_k && (int)(keys[j + 1] >> cell_shift) == cell;
-        float odd_n = 0.f;
-        int reps_n = 0;
-        if (more) {
-          const uint64_t kn = keys[j + 1];
-          const int sn = (int)((kn >> 7) & 31);
-          const int dn = sn == 0 ? 0 : ((sn & 1) ? (sn + 1) >> 1 : -(sn >> 1));
-          odd_n = s_odds[(kDiffRange + dn) * P.nRho + (rk - dn)];
-          reps_n = (int)(kn & 127);
+    // dense, static assignment (head h -> thread h).  With few warps in flight every dependent
+    // instruction costs ~5 cycles, so the loop is written for instruction count: a tight 3-op repeat
+    // loop per contribution, entries pre-decoded (s_dec), the next entry and its odds fetched ahead.
+    auto fold_chain = [&](const uint32_t *heads, uint32_t *dec) {
+      for (int h = tid; h < n_head; h += blockDim.x) {
+        const int i0 = (int)heads[h];
+        int i = i0;
+        uint32_t e = dec[i];
+        float p = s_odds[e & 0x1ffffffu];  // first insert: hit_idx_odds_hashmap[key] = odd
+        int reps = (int)((e >> 25) & 31);  // remaining repeats of the first contribution
+        float c1 = __fsub_rn(1.0f, p);     // (1 - odd)
+        for (;;) {
+          const bool last = (e >> 30) & 1u;
+          // next entry and its (1 - odd), independent of p
+          const uint32_t en = last ? 0u : dec[i + 1];
+          const float c1n = __fsub_rn(1.0f, s_odds[en & 0x1ffffffu]);
+          for (int r = 0; r < reps; r++) p = __fsub_rn(1.0f, __fmul_rn(__fsub_rn(1.0f, p), c1));
+          if (last || p == 1.0f) break;    // p == 1: 1 - (1-1)*(1-odd) == 1 for every later contribution
+          e = en;
+          c1 = c1n;
+          reps = (int)((e >> 25) & 31) + 1;
+          i++;
         }
-        for (int r = 0; r < reps; r++) {
-          const float np_ = odds_combine(p, odd);
-          if (np_ == p) break;  // fixed point of this odd (includes p == 1): the rest of the run is a no-op
-          p = np_;
-        }
-        if (!more || p == 1.0f) break;  // p == 1: 1 - (1-1)*(1-odd) == 1 for every later contribution
-        odd = odd_n;
-        reps = reps_n;
-        j++;
+        dec[i0] = __float_as_uint(p);
       }
-      s_head_p[h] = __float_as_uint(p);
+    };
+    if (in_smem) {
+      // same buffers, but addressed through the shared-memory window so the loads are LDS, not generic LD
+      uint32_t *sh = reinterpret_cast<uint32_t *>(keys_alt == s_keys ? s_keys : s_keys + P.sort_cap_smem);
+      fold_chain(sh, sh + n_k);
+    } else {
+      fold_chain(s_head, s_dec);
     }
   }
   __syncthreads();
@@ -806,14 +855,15 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
       const uint64_t k0 = keys[s_head[k]];
       const int cell = (int)(k0 >> cell_shift);
       const int zk = cell / P.nRho, rk = cell - zk * P.nRho;
-      const uint32_t stamp = (uint32_t)((((k0 >> 12) & t_mask) << 5) | ((k0 >> 7) & 31));  // t*32 + substep of the first insert
+      // first-insert stamp of the key: point stamp t of the record * 32 + substep
+      const uint32_t stamp = (REC_AT((int)((k0 >> 12) & k_mask)).t << 5) | (uint32_t)((k0 >> 7) & 31);
       const int idx = base_idx + k;
       if (idx >= P.max_hits) {
         fc->error = kErrCapacity;
         continue;
       }
       D.hit_key[idx] = (zk * P.nPhi + phi) * P.nRho + rk;  // mapIdx, map_awareness.h:81-84
-      D.hit_p[idx] = __uint_as_float(s_head_p[k]);
+      D.hit_p[idx] = __uint_as_float(s_dec[s_head[k]]);
       D.hit_t[idx] = stamp;
       // bucket activation stamp (libstdc++ iteration order)
       const uint32_t bucket = libstdcxx_bucket(vector_hash3(rk, phi, zk), F.bucket_count);
@@ -880,7 +930,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
       const int i = (it * 32 + lane_id()) * nwarps + warp;
       RayRecord rc;
       rc.phi_flags = kRecInside;
-      if (i < n_c) rc = recs[i];
+      if (i < n_c) rc = REC_AT(i);
       bool need = !(rc.phi_flags & kRecInside);
       if (need && rc.rho < 65536 && rc.z >= -32768 && rc.z < 32768) {
         const uint32_t key = ((uint32_t)rc.rho << 16) | (uint32_t)(rc.z + 32768);
@@ -1118,7 +1168,7 @@ __global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D) {
     for (uint32_t i = gtid; i < B; i += nth) act_next[i] = 0xffffffffu;
     for (int i = gtid; i < P.nPhi; i += nth) {
       D.phi_hist[i] = 0;
-      D.phi_cursor[i] = 0;
+      D.phi_bound[i] = 0;
     }
     if (gtid < (int)(sizeof(FrameCounters) / sizeof(int))) reinterpret_cast<int *>(D.fc[F.parity ^ 1])[gtid] = 0;
   }

@@ -376,9 +376,9 @@ int run_frame(mlm_map *h, bool depth, const void *d_in, int rows, int cols, int 
 #define MLM_MARK(i) do { if (mark) cudaEventRecord(h->kev[i], s); } while (0)
     MLM_MARK(0);
     if (depth)
-      k_project<true><<<full_grid, 256, (size_t)2 * P.nPhi * sizeof(int), s>>>(P, h->D);
+      k_project<true><<<full_grid, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(P, h->D);
     else
-      k_project<false><<<full_grid, 256, (size_t)2 * P.nPhi * sizeof(int), s>>>(P, h->D);
+      k_project<false><<<full_grid, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(P, h->D);
     MLM_MARK(1);
     k_column<<<P.nPhi, kColThreads, h->col_smem_bytes, s>>>(P, h->D);
     MLM_MARK(2);
@@ -727,8 +727,7 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   TRY(dev_alloc(h, &D.rec_col, (size_t)P.max_points));
   TRY(dev_alloc(h, &D.rec_dir, (size_t)((P.max_points + 255) / 256) * P.nPhi));
   TRY(dev_alloc(h, &D.phi_hist, (size_t)P.nPhi));
-  TRY(dev_alloc(h, &D.phi_off, (size_t)P.nPhi + 1));
-  TRY(dev_alloc(h, &D.phi_cursor, (size_t)P.nPhi));
+  TRY(dev_alloc(h, &D.phi_bound, (size_t)P.nPhi));
   TRY(dev_alloc(h, &D.col_scratch, (size_t)2 * P.max_points * P.contrib_per_point));
   TRY(dev_alloc(h, &D.hit_key, (size_t)P.max_hits));
   TRY(dev_alloc(h, &D.hit_p, (size_t)P.max_hits));
@@ -781,7 +780,7 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   CUDA_TRY_H(cudaMemset(D.act[0], 0xff, (size_t)h->act_cap * 4));
   CUDA_TRY_H(cudaMemset(D.act[1], 0xff, (size_t)h->act_cap * 4));
   CUDA_TRY_H(cudaMemset(D.phi_hist, 0, (size_t)P.nPhi * 4));
-  CUDA_TRY_H(cudaMemset(D.phi_cursor, 0, (size_t)P.nPhi * 4));
+  CUDA_TRY_H(cudaMemset(D.phi_bound, 0, (size_t)P.nPhi * 4));
   // every block on the free stack is in the initial state of allocate_ram: 'u', 'u', 0.f
   CUDA_TRY_H(cudaMemset(D.pool_lo, 0, (size_t)P.pool_blocks * P.cell_stride * 4));
   CUDA_TRY_H(cudaMemset(D.pool_occ, 'u', (size_t)P.pool_blocks * P.cell_stride));

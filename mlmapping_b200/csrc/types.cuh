@@ -106,8 +106,7 @@ struct DeviceBuffers {
   uint32_t *rec_dir;      // [ceil(max_points/256)][nPhi] directory of those windows: offset << 16 | count
   RayRecord *rec_col;     // [max_points] gathered by k_column: contiguous per phi column
   int *phi_hist;          // [nPhi] records per column
-  int *phi_off;           // [nPhi+1] (unused)
-  int *phi_cursor;        // [nPhi] (unused)
+  int *phi_bound;         // [nPhi] upper bound of hit contributions per column
   uint64_t *col_scratch;  // [max_points*contrib_per_point] sort spill for oversized columns
   // per-frame hit map / miss set
   int *hit_key;           // [max_hits] awareness linear index (mapIdx)

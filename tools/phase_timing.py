@@ -13,8 +13,9 @@ for k in range(6):
     m.integrate_depth(img, pose)
 c = m.debug_phase_cycles()
 act = c[:, 10] > 0
-names = ["bound", "contrib", "radix", "heads+fold", "hit-stage", "walks", "miss-stage"]
-d = np.diff(c[:, :8], axis=1)[act]
+names = ["gather", "bound", "contrib", "radix", "heads+fold", "hit-stage", "walks", "miss-stage"]
+cc = np.concatenate([c[:, 15:16], c[:, :8]], axis=1)
+d = np.diff(cc, axis=1)[act]
 tot = d.sum(1)
 order = np.argsort(-tot)
 print("columns", act.sum(), "cycles: total max", tot.max(), "mean", tot.mean())
