@@ -1,0 +1,65 @@
+// ROS-free harness in C++ over the reference-shaped façade (mlmapping_b200/include/mlmap.hpp):
+// integrates a few synthetic depth frames of a box corridor and runs the planner-facing queries.
+// Build: see __graft_entry__.build() (g++ -std=c++17 examples/corridor_harness.cpp -Lmlmapping_b200/lib -lmlmap_b200)
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <vector>
+
+#include "../mlmapping_b200/include/mlmap.hpp"
+
+using namespace mlmap_b200;
+
+// depth image of a 60 x 2.4 x 2.4 m corridor seen from (x,0,1.2) looking along +x (camera level)
+static void make_frame(std::vector<uint16_t> &img, int rows, int cols, float cx, float cy, float fx, float fy, double x0) {
+  img.resize((size_t)rows * cols);
+  for (int v = 0; v < rows; v++)
+    for (int u = 0; u < cols; u++) {
+      // optical frame: x right, y down, z forward  ->  world: forward +x, right -y, down -z
+      double dx = 1.0, dy = -(u - cx) / fx, dz = -(v - cy) / fy;
+      double t = (60.0 - (x0 + 0.12)) / dx;
+      if (dy > 0) t = std::fmin(t, 1.2 / dy);
+      if (dy < 0) t = std::fmin(t, -1.2 / dy);
+      if (dz > 0) t = std::fmin(t, 1.2 / dz);
+      if (dz < 0) t = std::fmin(t, -1.2 / dz);
+      double mm = std::round(t * 1000.0);
+      img[(size_t)v * cols + u] = mm > 65535 ? 0 : (uint16_t)mm;
+    }
+}
+
+int main() {
+  mlm_config cfg = mlmap::default_config();
+  // CFG-A of SURVEY §8d: 0.1 m cells, 65 x 360 x 41 awareness grid
+  cfg.am_d_rho = 0.1, cfg.am_d_phi_deg = 1.0, cfg.am_d_z = 0.1;
+  cfg.am_n_rho = 65, cfg.am_n_z_below = 20, cfg.am_n_z_over = 20;
+  cfg.depth_noise_coe = 0.00375, cfg.subbox_d_xyz = 0.1;
+  cfg.cam_cx = 320, cfg.cam_cy = 240;
+  cfg.max_points = 640 * 480, cfg.pool_submaps = 8192;
+  mlmap map;
+  try {
+    map.init_map(cfg);
+  } catch (const std::exception &e) {
+    std::printf("init_map failed: %s\n", e.what());
+    return 2;
+  }
+  std::vector<uint16_t> img;
+  double total_ms = 0;
+  const int frames = 20;
+  for (int k = 0; k < frames; k++) {
+    const double x = 5.0 + 0.05 * k;
+    make_frame(img, 480, 640, cfg.cam_cx, cfg.cam_cy, cfg.cam_fx, cfg.cam_fy, x);
+    auto t0 = std::chrono::steady_clock::now();
+    const mlm_frame_stats &st = map.depth_odom_input(img.data(), 480, 640, 640 * 2, SE3(1, 0, 0, 0, Vec3(x, 0, 1.2)));
+    total_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (k % 5 == 0)
+      std::printf("frame %2d: rays %d hit cells %d miss cells %d touched voxels %d submaps %lld\n", k, st.n_points,
+                  st.n_hit_cells, st.n_miss_cells, st.n_touched_voxels, (long long)st.ram_expand_cnt);
+  }
+  std::printf("[mlmapping] ave-time cost: %.4f ms per frame (host wall clock, H2D included)\n", total_ms / frames);
+  const Vec3 probe(7.0, 0.0, 1.2), wall(7.0, 1.22, 1.2), far(100, 0, 0);
+  std::printf("getOccupancy free=%d wall=%d unknown=%d  getOdd wall=%.4f\n", map.getOccupancy(probe), map.getOccupancy(wall),
+              map.getOccupancy(far), map.getOdd(wall));
+  Vec3 g = map.getOddGrad(Vec3(7.0, 1.12, 1.2));
+  std::printf("getOddGrad near wall = (%.4f, %.4f, %.4f)\n", g[0], g[1], g[2]);
+  return 0;
+}

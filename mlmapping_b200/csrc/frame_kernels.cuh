@@ -617,7 +617,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   __shared__ int s_off;
   const int bound_c = D.phi_bound[phi];                  // upper bound of this column's hit contributions
   const bool in_smem = bound_c <= P.sort_cap_smem;       // sort buffer in shared memory, else global spill (slow, exact)
-  const bool big = n_c > kMapCap;                      // more records than the shared-memory index map holds
+  const bool big = n_c > P.map_cap;                      // more records than the shared-memory index map holds
   int off = 0;
   if (big || !in_smem) {
     // rare: first slot of this column in the global spill / record areas = records of the columns before it

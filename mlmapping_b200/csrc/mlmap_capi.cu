@@ -673,6 +673,10 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   // two key buffers (radix ping-pong) of sort_cap_smem 64-bit keys each
   int cap = (int)(avail / 16) & ~127;
   P.sort_cap_smem = cap;
+  P.map_cap = kMapCap;
+  // test hooks: shrink the shared-memory capacities to force the global-memory fallback paths
+  if (const char *e = getenv("MLM_DEBUG_SORT_CAP")) P.sort_cap_smem = std::max(128, std::min(cap, atoi(e)) & ~127);
+  if (const char *e = getenv("MLM_DEBUG_MAP_CAP")) P.map_cap = std::max(1, std::min(kMapCap, atoi(e)));
   h->col_smem_bytes = (int)(bm_bytes + (size_t)cap * 16);
 
 #define TRY(x)            \

@@ -60,6 +60,7 @@ struct MapParams {
   int pool_blocks;
   uint32_t ht_mask;       // hash table capacity - 1 (power of two)
   int sort_cap_smem;      // 64-bit keys the column kernel can sort in shared memory
+  int map_cap;            // records per column addressed through the shared-memory index map (<= kMapCap)
   int contrib_per_point;  // 1 + 2*maxK
   // tables (device pointers)
   const float *odds_table;    // [21][nRho]   get_odds_table (map_awareness.cpp:36-46)

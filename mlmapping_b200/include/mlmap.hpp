@@ -1,0 +1,151 @@
+// mlmap.hpp — C++ host-side mirror of the reference's `class mlmap` (reference include/mlmap.h:42-140)
+// over the C ABI of the B200 library (include/mlmap_b200.h).  Same method names, argument meaning and
+// sentinel returns; ROS types are gone: init_map takes the plain config struct, the depth/odom callback
+// becomes depth_odom_input().  Header-only; link against libmlmap_b200.so.  No map arithmetic happens
+// here: every call is a stream-ordered submission to the CUDA library (no CPU fallback).
+#ifndef MLMAP_B200_MLMAP_HPP
+#define MLMAP_B200_MLMAP_HPP
+
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/mlmap_b200.h"
+
+namespace mlmap_b200 {
+
+// layout-compatible with Eigen::Matrix<double,3,1> / Eigen::Matrix<int,3,1> (reference include/common.h:22-23)
+struct Vec3 {
+  double v[3];
+  Vec3() : v{0, 0, 0} {}
+  Vec3(double x, double y, double z) : v{x, y, z} {}
+  double &operator()(int i) { return v[i]; }
+  double operator()(int i) const { return v[i]; }
+  double &operator[](int i) { return v[i]; }
+  double operator[](int i) const { return v[i]; }
+};
+static_assert(sizeof(Vec3) == 3 * sizeof(double), "Vec3 must be 3 contiguous doubles");
+
+// pose[7] = tx,ty,tz,qw,qx,qy,qz — what Sophus::SE3(SO3(Quaterniond), Vector3d) is built from
+struct SE3 {
+  double p[7];
+  SE3() : p{0, 0, 0, 1, 0, 0, 0} {}
+  SE3(double qw, double qx, double qy, double qz, const Vec3 &t) : p{t[0], t[1], t[2], qw, qx, qy, qz} {}
+};
+
+class mlmap {
+ public:
+  enum { FREE = MLM_FREE, OCCUPIED = MLM_OCCUPIED, UNKNOWN = MLM_UNKNOWN };  // include/mlmap.h:109-114
+  bool has_data = false;     // include/mlmap.h:115
+  bool map_updated = false;  // include/mlmap.h:116
+
+  mlmap() = default;
+  mlmap(const mlmap &) = delete;
+  mlmap &operator=(const mlmap &) = delete;
+  ~mlmap() {
+    if (h_) mlm_destroy(h_);
+  }
+
+  // mlmap::init_map(ros::NodeHandle&) (src/mlmap.cpp:3-149) with the YAML keys as a struct
+  void init_map(const mlm_config &cfg, int device = 0) {
+    if (h_) mlm_destroy(h_), h_ = nullptr;
+    check(mlm_create(&cfg, device, &h_), "mlm_create");
+    cfg_ = cfg;
+  }
+  static mlm_config default_config() {  // launch/config/config_sim.yaml
+    mlm_config c;
+    mlm_default_config(&c);
+    return c;
+  }
+
+  // depth_odom_input_callback (src/mlmap.cpp:463-532) without the ROS message plumbing: the caller
+  // provides the 16UC1 image and the (already latency-compensated) body pose.
+  const mlm_frame_stats &depth_odom_input(const uint16_t *img, int rows, int cols, size_t stride_bytes, const SE3 &T_wb) {
+    set_depth_image(img, rows, cols, stride_bytes);
+    T_wb_ = T_wb;
+    has_data = true;
+    project_depth();
+    update_map();
+    map_updated = true;
+    return stats_;
+  }
+  void set_depth_image(const uint16_t *img, int rows, int cols, size_t stride_bytes) {
+    img_ = img, rows_ = rows, cols_ = cols, stride_ = stride_bytes;
+  }
+  void set_pose(const SE3 &T_wb) { T_wb_ = T_wb; }
+
+  // project_depth() + update_map() (src/mlmap.cpp:311-349,382-386).  Back-projection runs inside the
+  // same device pass as the awareness/local update, so project_depth() only arms the frame.
+  void project_depth() { projected_ = img_ != nullptr; }
+  void update_map() {
+    if (!projected_) throw std::logic_error("update_map() without project_depth()");
+    check(mlm_integrate_depth_u16(h_, img_, rows_, cols_, stride_, T_wb_.p, &stats_), "mlm_integrate_depth_u16");
+    projected_ = false;
+  }
+  // awareness_map->input_pc_pose(PC_s, T_wb) + local_map->input_pc_pose_direct() for sensor-frame points
+  const mlm_frame_stats &input_pc_pose(const std::vector<Vec3> &PC_s, const SE3 &T_wb) {
+    check(mlm_integrate_points_f64(h_, PC_s.empty() ? nullptr : PC_s[0].v, (int)PC_s.size(), T_wb.p, &stats_),
+          "mlm_integrate_points_f64");
+    has_data = map_updated = true;
+    return stats_;
+  }
+
+  void setFree_map_in_bound(Vec3 box_min, Vec3 box_max) {  // src/mlmap.cpp:388-407
+    check(mlm_set_free_in_bound(h_, box_min.v, box_max.v), "mlm_set_free_in_bound");
+  }
+  void inflate_map(const Vec3 &ct_pos) { check(mlm_inflate_map(h_, ct_pos.v), "mlm_inflate_map"); }  // src/mlmap.cpp:286
+
+  // point queries, include/mlmap.h:142-295 (single-point forms: one-element batches)
+  int getOccupancy(const Vec3 &pos_w) {
+    int32_t r;
+    check(mlm_get_occupancy(h_, pos_w.v, 1, &r), "mlm_get_occupancy");
+    return r;
+  }
+  int getOccupancy(const Vec3 &pos_w, float inflate) {
+    int32_t r;
+    check(mlm_get_occupancy_inflate(h_, pos_w.v, 1, inflate, &r), "mlm_get_occupancy_inflate");
+    return r;
+  }
+  int getInflateOccupancy(const Vec3 &pos_w) {
+    int32_t r;
+    check(mlm_get_inflate_occupancy(h_, pos_w.v, 1, &r), "mlm_get_inflate_occupancy");
+    return r;
+  }
+  float getOdd(const Vec3 &pos_w) {
+    float r;
+    check(mlm_get_odd(h_, pos_w.v, 1, &r), "mlm_get_odd");
+    return r;
+  }
+  Vec3 getOddGrad(const Vec3 &pos_w, size_t max_iter = 5) {
+    Vec3 g;
+    check(mlm_get_odd_grad(h_, pos_w.v, 1, max_iter, g.v), "mlm_get_odd_grad");
+    return g;
+  }
+  // batched forms for trajectory optimisers: n positions, one kernel
+  void getOccupancy(const Vec3 *pos_w, size_t n, int32_t *out) { check(mlm_get_occupancy(h_, pos_w->v, n, out), "mlm_get_occupancy"); }
+  void getOdd(const Vec3 *pos_w, size_t n, float *out) { check(mlm_get_odd(h_, pos_w->v, n, out), "mlm_get_odd"); }
+  void getOddGrad(const Vec3 *pos_w, size_t n, Vec3 *out, size_t max_iter = 5) {
+    check(mlm_get_odd_grad(h_, pos_w->v, n, max_iter, out->v), "mlm_get_odd_grad");
+  }
+
+  const mlm_frame_stats &last_stats() const { return stats_; }
+  mlm_handle handle() const { return h_; }
+
+ private:
+  void check(int rc, const char *what) {
+    if (rc != MLM_OK) throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " + mlm_last_error());
+  }
+  mlm_handle h_ = nullptr;
+  mlm_config cfg_{};
+  mlm_frame_stats stats_{};
+  const uint16_t *img_ = nullptr;
+  int rows_ = 0, cols_ = 0;
+  size_t stride_ = 0;
+  SE3 T_wb_;
+  bool projected_ = false;
+};
+
+}  // namespace mlmap_b200
+#endif

@@ -158,3 +158,51 @@ def test_log10f_matches_host_glibc():
     lib.orc_log10f_array(x.ctypes.data, x.size, ref.ctypes.data)
     got = gpu.debug_log10f(x)
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+def test_fallback_paths_global_sort_spill_and_oversized_columns(monkeypatch):
+    """shrink the shared-memory capacities (debug env hooks) so columns take the global-memory sort
+    spill and the record-copy path; results must not change"""
+    cfg = config_cfg_a()
+    frames = []
+    for k in range(3):
+        pose = scenes.corridor_trajectory_pose(40 * k)
+        frames.append((scenes.corridor_depth_frame(cfg, pose, frame_idx=k), pose))
+    for env in ({"MLM_DEBUG_SORT_CAP": "256"}, {"MLM_DEBUG_MAP_CAP": "64"},
+                {"MLM_DEBUG_SORT_CAP": "128", "MLM_DEBUG_MAP_CAP": "1"}):
+        for k_, v_ in env.items():
+            monkeypatch.setenv(k_, v_)
+        gpu, orc = MLMap(cfg), Oracle(cfg)
+        for k_ in env:
+            monkeypatch.delenv(k_)
+        for i, (img, pose) in enumerate(frames):
+            st_g, st_o = gpu.integrate_depth(img, pose), orc.integrate_depth(img, pose)
+            assert_frame_parity(gpu, orc, st_g, st_o, tag=f"{env} frame{i}")
+        assert_map_parity(gpu, orc, LO_TOL)
+
+
+def test_full_size_cfg_b_l515_like():
+    """BASELINE config 3 geometry at full size: 1024x768 @ 0.05 m, n_Rho 180, n_Z 81 (3 frames)"""
+    from mlmapping_b200 import config_cfg_b
+    cfg = config_cfg_b()
+    cfg.pool_submaps = 32768
+    gpu, orc = MLMap(cfg), Oracle(cfg)
+    for k in range(3):
+        pose = scenes.corridor_trajectory_pose(k * 20, step=0.1)
+        img = scenes.corridor_depth_frame(cfg, pose, rows=768, cols=1024, frame_idx=k, length=200.0)
+        st_g, st_o = gpu.integrate_depth(img, pose), orc.integrate_depth(img, pose)
+        assert_frame_parity(gpu, orc, st_g, st_o, tag=f"cfgB frame{k}")
+    assert_map_parity(gpu, orc, LO_TOL)
+
+
+def test_full_size_cfg_c_lidar():
+    """BASELINE config 4 geometry at full size: 128x2048 LiDAR scan, n_Rho 250, n_Z 201, 0.2 m voxels"""
+    cfg = config_cfg_c()
+    gpu, orc = MLMap(cfg), Oracle(cfg)
+    for k in range(2):
+        pose = scenes.lidar_loop_pose(k * 5)
+        pts = scenes.lidar_scan(pose, frame_idx=k)
+        st_g, st_o = gpu.integrate_points(pts, pose), orc.integrate_points(pts, pose)
+        assert st_g.n_points > 200000
+        assert_frame_parity(gpu, orc, st_g, st_o, tag=f"cfgC scan{k}")
+    assert_map_parity(gpu, orc, LO_TOL)
