@@ -169,6 +169,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=60, help="frames of the workload timed on the CPU oracle")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-queries", action="store_true")
+    ap.add_argument("--queries", type=int, default=10_000_000, help="planner queries per step (4:4:2 odd/occupancy/grad)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -225,7 +227,44 @@ def main():
     wall1 = time.perf_counter()
     clocks = sampler.stop()
     launches = m.kernel_launch_count() - launches0 - args.steps  # minus the L2-flush launches
-    submaps = m.export_map()["glb"].shape[0] if rank == 0 else 0
+    exported = m.export_map()
+    submaps = exported["glb"].shape[0]
+
+    # ---------------- batched planner queries against the map just built (BASELINE config 5 mix) ----------------
+    queries = None
+    if not args.no_queries:
+        from mlmapping_b200 import scenes
+        from mlmapping_b200.sharding import split_range
+        nq = args.queries
+        qb, qe = split_range(nq, rank, world)
+        d = cfg.subbox_d_xyz * cfg.subbox_n
+        lo, hi = exported["glb"].min(0) * d, (exported["glb"].max(0) + 1) * d
+        pos = scenes.query_positions(nq, lo, hi, seed=5)[qb:qe]
+        n_odd, n_occ = int(0.4 * len(pos)), int(0.4 * len(pos))
+        n_grad = len(pos) - n_odd - n_occ
+        d_pos = m.to_device(pos)
+        d_o1, d_o2, d_o3 = m.device_alloc(4 * n_odd), m.device_alloc(4 * n_occ), m.device_alloc(24 * n_grad)
+        off_occ, off_grad = 24 * n_odd, 24 * (n_odd + n_occ)
+
+        def run_queries():
+            t = {}
+            m.flush_l2(); m.timer_start(); m.getOdd_device(d_pos, n_odd, d_o1); t["getOdd"] = m.timer_stop_ms()
+            m.flush_l2(); m.timer_start(); m.getOccupancy_device(d_pos + off_occ, n_occ, d_o2); t["getOccupancy"] = m.timer_stop_ms()
+            m.flush_l2(); m.timer_start(); m.getOddGrad_device(d_pos + off_grad, n_grad, d_o3, 5); t["getOddGrad"] = m.timer_stop_ms()
+            return t
+        for _ in range(3):
+            run_queries()
+        reps = 10
+        acc = {"getOdd": 0.0, "getOccupancy": 0.0, "getOddGrad": 0.0}
+        for _ in range(reps):
+            for k_, v_ in run_queries().items():
+                acc[k_] += v_ / reps
+        q_ms = sum(acc.values())
+        # SURVEY 8d algorithmic bytes: getOdd 32 B, getOccupancy 29 B, getOddGrad 76 B (one search round)
+        q_bytes = 32 * n_odd + 29 * n_occ + 76 * n_grad
+        queries = {"n_local": len(pos), "ms": acc, "total_ms": q_ms, "alg_bytes": q_bytes}
+        for pp in (d_pos, d_o1, d_o2, d_o3):
+            m.device_free(pp)
 
     # ---------------- pass 2: per-kernel events on the same frames (roofline share) ----------------
     m.close()
@@ -264,8 +303,9 @@ def main():
 
     # ---------------- reduce over ranks: max time, sum of rays ----------------
     from mlmapping_b200.sharding import reduce_timing
-    (dev_ms, e2e_s), (rays, e2e_rays, launches) = reduce_timing([dev_ms, e2e_s], [rays, e2e_rays, launches],
-                                                                device="cuda" if world > 1 else None)
+    q_ms_local = queries["total_ms"] if queries else 0.0
+    (dev_ms, e2e_s, q_ms_max), (rays, e2e_rays, launches) = reduce_timing(
+        [dev_ms, e2e_s, q_ms_local], [rays, e2e_rays, launches], device="cuda" if world > 1 else None)
     rays, e2e_rays, launches = int(rays), int(e2e_rays), int(launches)
 
     if rank == 0:
@@ -294,9 +334,37 @@ def main():
                          "kernel_us_per_frame": {k: 1e3 * v / args.steps for k, v in kern.items()},
                          "note": "latency/atomic-bound stage: ~1.8 MB of algorithmic traffic per frame (SURVEY 8d)"},
         }
+        if queries:
+            qpeak, _ = measured_peak_gbs()
+            per = {k_: {"ms": v_} for k_, v_ in queries["ms"].items()}
+            n_loc = queries["n_local"]
+            sizes = {"getOdd": (int(0.4 * n_loc), 32), "getOccupancy": (int(0.4 * n_loc), 29)}
+            sizes["getOddGrad"] = (n_loc - 2 * int(0.4 * n_loc), 76)
+            for k_, (cnt, bpq) in sizes.items():
+                gbs = cnt * bpq / (per[k_]["ms"] * 1e-3) / 1e9
+                per[k_].update({"queries": cnt, "queries_per_s": cnt / (per[k_]["ms"] * 1e-3), "alg_GB_per_s": gbs,
+                                "frac_of_hbm_peak": gbs / qpeak})
+            out["queries"] = {"metric": "queries_per_sec", "value": args.queries / (q_ms_max * 1e-3), "unit": "queries/s",
+                              "n_queries": args.queries, "mix": "40% getOdd, 40% getOccupancy, 20% getOddGrad(max_iter=5)",
+                              "ms_per_step": q_ms_max, "per_kernel_rank0": per, "inputs": "device-resident, L2 flushed",
+                              "split": "evenly over ranks, each rank queries its own agent map"}
         if not args.no_cpu:
             nf = min(args.cpu_frames, total)
             c_rays, c_s = run_cpu_sample(cfg, frames, poses, nf)
+            if queries:
+                from mlmapping_b200 import scenes as _sc
+                from oracle_binding import Oracle
+                orc = Oracle(cfg, bookkeeping=False)
+                for k in range(min(20, total)):
+                    orc.integrate_depth(frames[k], poses[k])
+                mo = orc.export_map()
+                dd = cfg.subbox_d_xyz * cfg.subbox_n
+                qp = _sc.query_positions(300000, mo["glb"].min(0) * dd, (mo["glb"].max(0) + 1) * dd, seed=5)
+                t0 = time.perf_counter(); orc.getOdd(qp[:120000]); orc.getOccupancy(qp[120000:240000]); orc.getOddGrad(qp[240000:])
+                tq = time.perf_counter() - t0
+                out["queries"]["cpu_baseline"] = {"value": 300000 / tq, "unit": "queries/s", "cores": 1, "kind": "port",
+                                                  "sample": "300k queries (same 4:4:2 mix) on a 20-frame oracle map"}
+                orc.close()
             out["cpu_baseline"] = {"value": c_rays / c_s, "unit": UNIT, "cores": 1, "kind": "port",
                                    "sample": f"first {nf} frames of {WORKLOAD} on the CPU oracle, single thread "
                                              f"({os.cpu_count()} host cores present)",

@@ -92,33 +92,71 @@ __device__ __forceinline__ void neighbor_step(const MapParams &P, int dir, int g
   sub = (c[2] * P.n + c[1]) * P.n + c[0];
 }
 
+// log-odds the reference's getOdd(glb, sub) would convert: absent subbox -> odds 0.5 == logit_inv(0.f)
+__device__ __forceinline__ float lo_at(const MapParams &P, const DeviceBuffers &D, const int g[3], int sub) {
+  int block = ht_find(P, D, g);
+  if (block < 0) return 0.0f;
+  return D.pool_lo[(size_t)block * P.cell_stride + sub];
+}
+
 __global__ void __launch_bounds__(256) k_get_odd_grad(MapParams P, DeviceBuffers D, const double *pos, size_t n,
                                                       int max_iter, double *out) {  // mlmap.h:237-295
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double px = pos[3 * i], py = pos[3 * i + 1], pz = pos[3 * i + 2];
   CellRef c = locate_cell(P, px, py, pz);
-  float min_odd = odd_at(P, D, c.g, c.sub);
+  // logit_inv is monotone non-decreasing in the log-odds (also after the cast to float), so a neighbour
+  // whose log-odds is not below the running minimum can never satisfy `tmp_odd < min_odd`: the double
+  // pow() is only evaluated for the candidates that can win.  The sequence of accepted minima, and
+  // therefore the result, is exactly the reference's.
+  const int blk0 = ht_find(P, D, c.g);
+  float min_lo = blk0 < 0 ? 0.0f : D.pool_lo[(size_t)blk0 * P.cell_stride + c.sub];
+  float min_odd = logit_inv_f(min_lo);
   const float ori_odd = min_odd;
-  int nb_g[6][3], nb_sub[6];
+  // The six probes walk along +z,-z,+y,-y,+x,-x (subbox_neighbors row order, src/map_local.cpp:78-120):
+  // only the coordinate on the probe's own axis changes, so each direction keeps (cell coordinate on its
+  // axis, subbox index on its axis, pool block); the hash lookup is repeated only when a subbox border
+  // is crossed.  Fully unrolled so the per-direction state lives in registers.
+  const int cxyz[3] = {c.sub % P.n, (c.sub / P.n) % P.n, c.sub / (P.n * P.n)};
+  const int stride[3] = {1, P.n, P.n * P.n};
+  int ca[6], ga[6], blk[6];
+#pragma unroll
+  for (int d = 0; d < 6; d++) {
+    ca[d] = cxyz[2 - (d >> 1)];
+    ga[d] = c.g[2 - (d >> 1)];
+    blk[d] = blk0;
+  }
   int best_g[3] = {0, 0, 0}, best_sub = 0;
   bool flag = false;
   for (int iter = 0; iter < max_iter && !flag; iter++) {
+#pragma unroll
     for (int d = 0; d < 6; d++) {
-      if (iter == 0) {
-        nb_g[d][0] = c.g[0];
-        nb_g[d][1] = c.g[1];
-        nb_g[d][2] = c.g[2];
-        nb_sub[d] = c.sub;
+      const int axis = 2 - (d >> 1);
+      ca[d] += (d & 1) ? -1 : 1;
+      bool crossed = false;
+      if (ca[d] >= P.n) {
+        ca[d] = 0;
+        ga[d] += 1;
+        crossed = true;
+      } else if (ca[d] < 0) {
+        ca[d] = P.n - 1;
+        ga[d] -= 1;
+        crossed = true;
       }
-      neighbor_step(P, d, nb_g[d], nb_sub[d]);  // keep searching along the original direction
-      float tmp = odd_at(P, D, nb_g[d], nb_sub[d]);
+      int g[3] = {c.g[0], c.g[1], c.g[2]};
+      g[axis] = ga[d];
+      if (crossed) blk[d] = ht_find(P, D, g);
+      const int sub = c.sub + (ca[d] - cxyz[axis]) * stride[axis];
+      const float lo = blk[d] < 0 ? 0.0f : D.pool_lo[(size_t)blk[d] * P.cell_stride + sub];
+      if (!(lo < min_lo)) continue;
+      const float tmp = logit_inv_f(lo);
       if (tmp < min_odd) {
         min_odd = tmp;
-        best_g[0] = nb_g[d][0];
-        best_g[1] = nb_g[d][1];
-        best_g[2] = nb_g[d][2];
-        best_sub = nb_sub[d];
+        min_lo = lo;
+        best_g[0] = g[0];
+        best_g[1] = g[1];
+        best_g[2] = g[2];
+        best_sub = sub;
         flag = true;
       }
     }
