@@ -133,29 +133,48 @@ def run_cpu_sample(cfg, frames, poses, n_frames):
 
 
 def run_reference(args, rank, world):
+    """CPU arm: the oracle (port of the reference's algorithm; the reference itself needs Eigen/PCL/ROS and
+    cannot be built here).  One map is single-threaded like the reference; with --gpus N the N independent
+    agent maps of the GPU arm run on N host threads (ctypes releases the GIL), one map each."""
+    import threading
     from mlmapping_b200 import config_cfg_a
     if rank != 0:
         return
     cfg = config_cfg_a()
     total = args.steps + args.warmup
-    frames, poses = gen_frames(cfg, total)
+    n_agents = max(1, args.gpus)
     from oracle_binding import Oracle
-    orc = Oracle(cfg, bookkeeping=False)
-    for k in range(args.warmup):
-        orc.integrate_depth(frames[k], poses[k])
-    rays, secs = 0, 0.0
-    for k in range(args.warmup, total):
-        st = orc.integrate_depth(frames[k], poses[k])
-        rays += st.n_points
-        secs += orc.last_seconds
+    data = [gen_frames(cfg, total, agent=a) for a in range(n_agents)]
+    res = [None] * n_agents
+
+    def work(a):
+        frames, poses = data[a]
+        orc = Oracle(cfg, bookkeeping=False)
+        for k in range(args.warmup):
+            orc.integrate_depth(frames[k], poses[k])
+        rays, secs = 0, 0.0
+        for k in range(args.warmup, total):
+            st = orc.integrate_depth(frames[k], poses[k])
+            rays += st.n_points
+            secs += orc.last_seconds
+        res[a] = (rays, secs)
+        orc.close()
+
+    th = [threading.Thread(target=work, args=(a,)) for a in range(n_agents)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    rays = sum(r for r, _ in res)
+    secs = max(s_ for _, s_ in res)
     value = rays / secs
-    sample = f"{args.steps} frames of {WORKLOAD} after {args.warmup} warm-up frames, single thread"
+    sample = (f"{args.steps} frames of {WORKLOAD} after {args.warmup} warm-up frames, {n_agents} agent map(s) on "
+              f"{n_agents} host thread(s), one map per thread ({os.cpu_count()} host cores present)")
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rows": ROWS, "cols": COLS, "timing": "steady_clock around project_depth+update_map"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "rows": ROWS, "cols": COLS, "agents": n_agents,
+                   "timing": "steady_clock around project_depth+update_map (the region the reference times, src/mlmap.cpp:474-511)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_agents, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
@@ -315,6 +334,17 @@ def main():
         peak, peak_src = measured_peak_gbs()
         per_rank_bytes = alg_bytes / args.steps
         achieved = per_rank_bytes / (top_ms * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
+            prof = json.loads((ROOT / "profiles" / "ncu_full_summary_r01.json").read_text())[top][0]
+
+            def _bytes(v):
+                num, unit = v.split()
+                return float(num) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+            traffic = _bytes(prof["dram__bytes_read.sum"]) + _bytes(prof["dram__bytes_write.sum"])
+            traffic_src = "profiles/ncu_full_summary_r01.json (bytes per launch, cold-cache ncu capture)"
+        except Exception:
+            pass
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -329,10 +359,12 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": per_rank_bytes, "kernel_us": 1e3 * top_ms,
                          "kernel_us_per_frame": {k: 1e3 * v / args.steps for k, v in kern.items()},
-                         "note": "latency/atomic-bound stage: ~1.8 MB of algorithmic traffic per frame (SURVEY 8d)"},
+                         "traffic_source": traffic_src,
+                         "note": "latency/issue-bound stage: ~1 MB of algorithmic traffic per frame (SURVEY 8d); "
+                                 "the bandwidth-shaped stage is the query batch, see 'queries'"},
         }
         if queries:
             qpeak, _ = measured_peak_gbs()
