@@ -136,6 +136,8 @@ struct mlm_map {
   uint32_t frame_idx = 0;
   int last_parity = 0;
   cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};  // [0] depth input, [1] point input
+  cudaGraph_t graph[2] = {nullptr, nullptr};
+  cudaGraphNode_t graph_nodes[2][3] = {};
   int use_graph = 1;
   void *h_stage = nullptr;        // pinned input staging
   size_t stage_bytes = 0;
@@ -372,38 +374,51 @@ int run_frame(mlm_map *h, bool depth, const void *d_in, int rows, int cols, int 
 
   const bool prof = h->profiling != 0;
   const int full_grid = grid_for((size_t)P.max_points, 256);
-  auto launch_kernels = [&](bool mark) {
-#define MLM_MARK(i) do { if (mark) cudaEventRecord(h->kev[i], s); } while (0)
+  const int proj_grid = grid_for((size_t)std::max(N, 1), 256);
+  MapParams Pk = P;
+  DeviceBuffers Dk = h->D;
+  FrameParams Fk = F;
+  void *kargs[3] = {&Pk, &Dk, &Fk};
+  if (prof || !h->use_graph) {
+#define MLM_MARK(i) do { if (prof) cudaEventRecord(h->kev[i], s); } while (0)
     MLM_MARK(0);
     if (depth)
-      k_project<true><<<full_grid, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(P, h->D);
+      k_project<true><<<proj_grid, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(Pk, Dk, Fk);
     else
-      k_project<false><<<full_grid, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(P, h->D);
+      k_project<false><<<proj_grid, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(Pk, Dk, Fk);
     MLM_MARK(1);
-    k_column<<<P.nPhi, kColThreads, h->col_smem_bytes, s>>>(P, h->D);
+    k_column<<<P.nPhi, kColThreads, h->col_smem_bytes, s>>>(Pk, Dk, Fk);
     MLM_MARK(2);
-    k_fuse<<<h->sm_count * 4, 256, 0, s>>>(P, h->D);
+    k_fuse<<<h->sm_count * 4, 256, 0, s>>>(Pk, Dk, Fk);
     MLM_MARK(3);
 #undef MLM_MARK
-  };
-  if (prof || !h->use_graph) {
-    CUDA_TRY(cudaMemcpyAsync(h->D.fp, h->h_fp, sizeof(FrameParams), cudaMemcpyHostToDevice, s));
-    launch_kernels(prof);
-    CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc[0], 2 * sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
   } else {
-    // the whole frame (parameter upload, 4 kernels, counter read-back) is one graph launch
-    cudaGraphExec_t &ge = h->graph_exec[depth ? 0 : 1];
-    if (!ge) {
-      cudaGraph_t g = nullptr;
-      CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-      cudaMemcpyAsync(h->D.fp, h->h_fp, sizeof(FrameParams), cudaMemcpyHostToDevice, s);
-      launch_kernels(false);
-      cudaMemcpyAsync(h->h_fc, h->D.fc[0], 2 * sizeof(FrameCounters), cudaMemcpyDeviceToHost, s);
-      CUDA_TRY(cudaStreamEndCapture(s, &g));
-      CUDA_TRY(cudaGraphInstantiate(&ge, g, 0));
-      cudaGraphDestroy(g);
+    // the whole frame is one launch of a 3-kernel graph; the per-frame values travel as kernel arguments
+    const int gi = depth ? 0 : 1;
+    cudaKernelNodeParams np[3] = {};
+    np[0].func = depth ? (void *)k_project<true> : (void *)k_project<false>;
+    np[0].gridDim = dim3(full_grid);  // fixed grid: CTAs beyond this frame's point count return at once
+    np[0].blockDim = dim3(256);
+    np[0].sharedMemBytes = (unsigned)((size_t)3 * P.nPhi * sizeof(int));
+    np[1].func = (void *)k_column;
+    np[1].gridDim = dim3(P.nPhi);
+    np[1].blockDim = dim3(kColThreads);
+    np[1].sharedMemBytes = (unsigned)h->col_smem_bytes;
+    np[2].func = (void *)k_fuse;
+    np[2].gridDim = dim3(h->sm_count * 4);
+    np[2].blockDim = dim3(256);
+    np[2].sharedMemBytes = 0;
+    for (int i = 0; i < 3; i++) np[i].kernelParams = kargs;
+    if (!h->graph_exec[gi]) {
+      CUDA_TRY(cudaGraphCreate(&h->graph[gi], 0));
+      for (int i = 0; i < 3; i++)
+        CUDA_TRY(cudaGraphAddKernelNode(&h->graph_nodes[gi][i], h->graph[gi], i ? &h->graph_nodes[gi][i - 1] : nullptr,
+                                        i ? 1 : 0, &np[i]));
+      CUDA_TRY(cudaGraphInstantiate(&h->graph_exec[gi], h->graph[gi], 0));
+    } else {
+      for (int i = 0; i < 3; i++) CUDA_TRY(cudaGraphExecKernelNodeSetParams(h->graph_exec[gi], h->graph_nodes[gi][i], &np[i]));
     }
-    CUDA_TRY(cudaGraphLaunch(ge, s));
+    CUDA_TRY(cudaGraphLaunch(h->graph_exec[gi], s));
   }
   h->launches += 3;
   CUDA_TRY(cudaStreamSynchronize(s));
@@ -413,9 +428,9 @@ int run_frame(mlm_map *h, bool depth, const void *d_in, int rows, int cols, int 
     for (int i = 0; i < MLM_NUM_FRAME_KERNELS; i++) cudaEventElapsedTime(&h->kms[i], h->kev[i], h->kev[i + 1]);
   int slow = 0;
   uint32_t order_B = h->bucket_count;
-  if (h->h_fc[parity].error == 0 && h->h_fc[parity].overflow) {
+  if (h->h_fc->error == 0 && h->h_fc->overflow) {
     slow = 1;
-    const int n = h->h_fc[parity].n_hit;
+    const int n = h->h_fc->n_hit;
     if (n > h->sort_cap) {
       g_last_error = "hit count exceeds ordering scratch";
       return MLM_ERR_CAPACITY;
@@ -426,14 +441,12 @@ int run_frame(mlm_map *h, bool depth, const void *d_in, int rows, int cols, int 
     order_B = Bf;
     F.bucket_count = Bf;
     F.order_mode = 1;
-    CUDA_TRY(cudaMemcpyAsync(h->D.fp, h->h_fp, sizeof(FrameParams), cudaMemcpyHostToDevice, s));
-    k_fuse<<<h->sm_count * 4, 256, 0, s>>>(P, h->D);
+    k_fuse<<<h->sm_count * 4, 256, 0, s>>>(P, h->D, F);
     h->launches += 1;
-    CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc[0], 2 * sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaGetLastError());
   }
-  const FrameCounters &C = h->h_fc[parity];
+  const FrameCounters &C = *h->h_fc;
   if (C.fused) {
     h->cum_ram_expand += C.n_new_blocks;
     h->cum_obs += C.obs_delta;
@@ -701,7 +714,8 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   CUDA_TRY_H(cudaEventCreate(&h->ev0));
   CUDA_TRY_H(cudaEventCreate(&h->ev1));
   CUDA_TRY_H(cudaMallocHost((void **)&h->h_fp, sizeof(FrameParams)));
-  CUDA_TRY_H(cudaMallocHost((void **)&h->h_fc, 2 * sizeof(FrameCounters)));
+  CUDA_TRY_H(cudaHostAlloc((void **)&h->h_fc, sizeof(FrameCounters), cudaHostAllocMapped));
+  memset(h->h_fc, 0, sizeof(FrameCounters));
   CUDA_TRY_H(cudaFuncSetAttribute(k_column, cudaFuncAttributeMaxDynamicSharedMemorySize, h->col_smem_bytes));
 
   DeviceBuffers &D = h->D;
@@ -723,7 +737,9 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   P.centre_xy = d_cxy;
   P.centre_z = d_cz;
 
-  TRY(dev_alloc(h, &D.fp, 1));
+  TRY(dev_alloc(h, &D.fuse_ticket, 1));
+  CUDA_TRY_H(cudaMemset(D.fuse_ticket, 0, sizeof(int)));
+  CUDA_TRY_H(cudaHostGetDevicePointer((void **)&D.host_fc, h->h_fc, 0));
   TRY(dev_alloc(h, &D.fc[0], 2));
   D.fc[1] = D.fc[0] + 1;
   TRY(dev_alloc(h, &D.col_ticket, 1));
@@ -808,8 +824,10 @@ int mlm_destroy(mlm_handle h) {
   if (!h) return MLM_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (int i = 0; i < 2; i++)
+  for (int i = 0; i < 2; i++) {
     if (h->graph_exec[i]) cudaGraphExecDestroy(h->graph_exec[i]);
+    if (h->graph[i]) cudaGraphDestroy(h->graph[i]);
+  }
   for (void *p : h->allocs) cudaFree(p);
   if (h->d_input) cudaFree(h->d_input);
   if (h->h_stage) cudaFreeHost(h->h_stage);

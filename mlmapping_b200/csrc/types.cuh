@@ -100,7 +100,8 @@ struct FrameCounters {
 };
 
 struct DeviceBuffers {
-  FrameParams *fp;
+  FrameCounters *host_fc;  // mapped pinned host memory: the last k_fuse block publishes the frame counters here
+  int *fuse_ticket;        // completion ticket of k_fuse
   FrameCounters *fc[2];   // double-buffered: frame f uses fc[f&1], k_fuse clears the other one
   // K1/K1b
   RayRecord *rec_lin;     // [max_points] per k_project CTA: a 256-slot window, records grouped by column
