@@ -66,6 +66,18 @@ __device__ __forceinline__ double ref_fast_atan2(double y, double x) {
   return res - M_PI;
 }
 
+// floor(fl(p / d)) without paying for an IEEE division on every call.  qa = p * fl(1/d) differs from the
+// correctly rounded quotient fl(p/d) by less than 4e-16 relative, so when qa is not within 1e-15 relative
+// of an integer both have the same floor; otherwise (lattice points, cell borders) the true division
+// decides.  The result is therefore always exactly what the reference's division + floor gives.
+__device__ __forceinline__ double floor_quot_exact(double p, double d, double inv_d) {
+  const double qa = p * inv_d;
+  double f = floor(qa);
+  const double eps = fabs(qa) * 1e-15;
+  if (!(qa - f > eps && (f + 1.0) - qa > eps)) f = floor(p / d);  // also taken for NaN / inf
+  return f;
+}
+
 // get_global_idx + get_subbox_id, reference include/map_local.h:148-152,167-173.
 // sub-index components outside [0,n) hit unordered_map::operator[] on a missing key -> id 0.
 struct CellRef {
@@ -80,8 +92,8 @@ __device__ __forceinline__ CellRef locate_cell(const MapParams &P, double px, do
   bool ok = true;
 #pragma unroll
   for (int a = 0; a < 3; a++) {
-    r.g[a] = cvt_trunc_x86(floor(p[a] / P.d_glb));
-    double l = floor(p[a] / P.d_sub) - (double)(r.g[a] * P.n);
+    r.g[a] = cvt_trunc_x86(floor_quot_exact(p[a], P.d_glb, P.inv_d_glb));
+    double l = floor_quot_exact(p[a], P.d_sub, P.inv_d_sub) - (double)(r.g[a] * P.n);
     loc[a] = cvt_trunc_x86(l);
     ok = ok && loc[a] >= 0 && loc[a] < P.n;
   }
@@ -170,12 +182,13 @@ __device__ __forceinline__ void point_to_record(const MapParams &P, const FrameP
   double z = ((zs + qw * uvz) + cz) + F.t_ls[2];
   // xyz2RhoPhiZwithBoderCheck, src/map_awareness.cpp:84-107
   double rho = sqrt(x * x + y * y);
-  int rho_idx = cvt_trunc_x86(rho / P.dRho);
+  // static_cast<int>(x / d) truncates; rho and the wrapped phi are >= 0 (or NaN -> exact path), so trunc == floor
+  int rho_idx = cvt_trunc_x86(floor_quot_exact(rho, P.dRho, P.inv_dRho));
   double phi = ref_fast_atan2(y, x);
   if (phi < 0) phi += 2 * M_PI;
-  int phi_idx = cvt_trunc_x86(phi / P.dPhi);
+  int phi_idx = phi >= 0 ? cvt_trunc_x86(floor_quot_exact(phi, P.dPhi, P.inv_dPhi)) : cvt_trunc_x86(phi / P.dPhi);
   double zz = z - P.z_border_min;
-  int z_idx = cvt_trunc_x86(floor(zz / P.dZ));
+  int z_idx = cvt_trunc_x86(floor_quot_exact(zz, P.dZ, P.inv_dZ));
   bool can = rho_idx >= 0 && phi_idx >= 0 && phi_idx < P.nPhi;
   bool inside = can && z_idx >= 0 && rho_idx < P.nRho && z_idx < P.nZ;
   bool cast = can && P.visibility_check;
@@ -351,6 +364,7 @@ constexpr int kColWarps = kColThreads / 32;
 constexpr int kRadixBits = 8;
 constexpr int kRadixDigits = 1 << kRadixBits;
 constexpr int kCellBits = 20;
+constexpr int kHalf = kColThreads / 2;  // threads per half-CTA group in k_column's overlapped phases
 constexpr int kLongChain = 32;  // contributions per cell from which the fold claims the cell early
 constexpr int kMapCap = 4096;  // records per column addressed through the shared-memory index map
 
@@ -494,9 +508,13 @@ __device__ __forceinline__ void walk_batch(const MapParams &P, uint32_t *s_miss,
   }
 }
 
+// named barrier over `count` threads (the two half-CTA groups of k_column use ids 1 and 2; 0 is __syncthreads)
+__device__ __forceinline__ void group_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 // CTA-wide compaction of the set bits of bm[w0,w1) into list (entries = word*32 + bit), any order.
-__device__ __forceinline__ void compact_bits(const uint32_t *bm, int w0, int w1, uint32_t *list, int *counter) {
-  const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+__device__ __forceinline__ void compact_bits(const uint32_t *bm, int w0, int w1, uint32_t *list, int *counter, int warp,
+                                             int nwarps) {
+  const int lane = lane_id();
   for (int wi = w0 + warp; wi < w1; wi += nwarps) {
     const uint32_t bits = bm[wi];
     if (!bits) continue;
@@ -683,6 +701,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   __shared__ int s_nk;
   __shared__ int s_nmiss;
   __shared__ int s_nhead;
+  __shared__ int s_nlist;
   for (int i = tid; i < 2 * P.col_words; i += blockDim.x) s_miss[i] = 0;
   if (tid == 0) {
     s_nk = 0;
@@ -742,216 +761,225 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   const uint64_t k_mask = (1ull << kbits) - 1;
 
   MLM_PHASE(3);
-  // (c1) ordered list of segment heads (first contribution of every distinct cell) and a compact decode
-  // of every contribution, both in the idle ping-pong buffer:
-  //   s_head[h]  = index into keys of the h-th cell's first contribution
-  //   s_dec[i]   = odds-table index (25 bits) | run length - 1 (5 bits, bits 25..29) | last-of-cell (bit 30);
-  //                after the fold, s_dec[s_head[h]] holds the folded probability bits of cell h
-  uint32_t *s_head = reinterpret_cast<uint32_t *>(keys_alt);
-  uint32_t *s_dec = s_head + n_k;
-  {
-    const int W = kColWarps, w = tid >> 5, lane = lane_id();
-    const int chunk = (((n_k + W - 1) / W) + 31) & ~31;
-    const int beg = min(w * chunk, n_k), end = min(beg + chunk, n_k);
-    int cnt = 0;
-    for (int base = beg; base < end; base += 32) {
-      const int i = base + lane;
-      bool head = false;
-      if (i < end) {
-        const uint64_t ki = keys[i];
-        const int cell = (int)(ki >> cell_shift);
-        if (cell != cell_sentinel) {
-          head = i == 0 || (int)(keys[i - 1] >> cell_shift) != cell;
-          const bool last = i + 1 >= n_k || (int)(keys[i + 1] >> cell_shift) != cell;
-          const int rk = cell - (cell / P.nRho) * P.nRho;
-          const int sstep = (int)((ki >> 7) & 31);
-          const int d = sstep == 0 ? 0 : ((sstep & 1) ? (sstep + 1) >> 1 : -(sstep >> 1));
-          const uint32_t oi = (uint32_t)((kDiffRange + d) * P.nRho + (rk - d));
-          s_dec[i] = oi | ((uint32_t)((ki & 127) - 1) << 25) | (last ? (1u << 30) : 0u);
-        }
-      }
-      cnt += __popc(__ballot_sync(0xffffffffu, head));
-    }
-    if (lane == 0) s_wsum[w] = (uint32_t)cnt;
-    __syncthreads();
-    if (w == 0) {
-      uint32_t sv = lane < W ? s_wsum[lane] : 0, si = sv;
-#pragma unroll
-      for (int ofs = 1; ofs < 32; ofs <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, si, ofs);
-        if (lane >= ofs) si += t;
-      }
-      if (lane < W) s_wsum[lane] = si - sv;
-      if (lane == W - 1) s_nhead = (int)si;
-    }
-    __syncthreads();
-    int pos = (int)s_wsum[w];
-    for (int base = beg; base < end; base += 32) {
-      const int i = base + lane;
-      const bool head = i < end && (int)(keys[i] >> cell_shift) != cell_sentinel &&
-                        (i == 0 || (keys[i - 1] >> cell_shift) != (keys[i] >> cell_shift));
-      const unsigned b = __ballot_sync(0xffffffffu, head);
-      if (head) s_head[pos + __popc(b & ((1u << lane) - 1))] = (uint32_t)i;
-      pos += __popc(b);
-    }
-  }
-  __syncthreads();
-  // (c2) update_odds_hashmap fold, one thread per distinct cell (static: head h -> thread h, so the
-  // lanes of a warp stay in one loop).  The chain p <- 1-(1-p)(1-odd) is inherently ordered; it is
-  // flattened over (contribution, repeat) so that a lane never waits for another lane's run length,
-  // the next contribution is fetched one step ahead, and a lane leaves as soon as p saturates at 1
-  // (1 - (1-1)*(1-odd) == 1 for every later contribution).
-  {
-    const int n_head = s_nhead;
-    // dense, static assignment (head h -> thread h).  With few warps in flight every dependent
-    // instruction costs ~5 cycles, so the loop is written for instruction count: a tight 3-op repeat
-    // loop per contribution, entries pre-decoded (s_dec), the next entry and its odds fetched ahead.
-    auto fold_chain = [&](const uint32_t *heads, uint32_t *dec) {
-      for (int h = tid; h < n_head; h += blockDim.x) {
-        const int i0 = (int)heads[h];
-        int i = i0;
-        uint32_t e = dec[i];
-        float p = s_odds[e & 0x1ffffffu];  // first insert: hit_idx_odds_hashmap[key] = odd
-        int reps = (int)((e >> 25) & 31);  // remaining repeats of the first contribution
-        float c1 = __fsub_rn(1.0f, p);     // (1 - odd)
-        for (;;) {
-          const bool last = (e >> 30) & 1u;
-          // next entry and its (1 - odd), independent of p
-          const uint32_t en = last ? 0u : dec[i + 1];
-          const float c1n = __fsub_rn(1.0f, s_odds[en & 0x1ffffffu]);
-          for (int r = 0; r < reps; r++) p = __fsub_rn(1.0f, __fmul_rn(__fsub_rn(1.0f, p), c1));
-          if (last || p == 1.0f) break;    // p == 1: 1 - (1-1)*(1-odd) == 1 for every later contribution
-          e = en;
-          c1 = c1n;
-          reps = (int)((e >> 25) & 31) + 1;
-          i++;
-        }
-        dec[i0] = __float_as_uint(p);
-      }
-    };
-    if (in_smem) {
-      // same buffers, but addressed through the shared-memory window so the loads are LDS, not generic LD
-      uint32_t *sh = reinterpret_cast<uint32_t *>(keys_alt == s_keys ? s_keys : s_keys + P.sort_cap_smem);
-      fold_chain(sh, sh + n_k);
-    } else {
-      fold_chain(s_head, s_dec);
-    }
-  }
-  __syncthreads();
-  MLM_PHASE(4);
-  {
-    const int n_head = s_nhead;
-    int base_idx = 0;
-    if (tid == 0) s_nk = atomicAdd(&fc->n_hit, n_head);  // one global reservation per column
-    __syncthreads();
-    base_idx = s_nk;
-    for (int k = tid; k < n_head; k += blockDim.x) {
-      const uint64_t k0 = keys[s_head[k]];
-      const int cell = (int)(k0 >> cell_shift);
-      const int zk = cell / P.nRho, rk = cell - zk * P.nRho;
-      // first-insert stamp of the key: point stamp t of the record * 32 + substep
-      const uint32_t stamp = (REC_AT((int)((k0 >> 12) & k_mask)).t << 5) | (uint32_t)((k0 >> 7) & 31);
-      const int idx = base_idx + k;
-      if (idx >= P.max_hits) {
-        fc->error = kErrCapacity;
-        continue;
-      }
-      D.hit_key[idx] = (zk * P.nPhi + phi) * P.nRho + rk;  // mapIdx, map_awareness.h:81-84
-      D.hit_p[idx] = __uint_as_float(s_dec[s_head[k]]);
-      D.hit_t[idx] = stamp;
-      // bucket activation stamp (libstdc++ iteration order)
-      const uint32_t bucket = libstdcxx_bucket(vector_hash3(rk, phi, zk), F.bucket_count);
-      D.hit_bucket[idx] = bucket;
-      atomicMin(&act[bucket], stamp);
-      // p_w = T_wa * centre  (identity rotation: one add per axis), src/map_local.cpp:151
-      double2 cxy = __ldg(&P.centre_xy[phi * P.nRho + rk]);
-      CellRef cr = locate_cell(P, cxy.x + F.t_wa[0], cxy.y + F.t_wa[1], __ldg(&P.centre_z[zk]) + F.t_wa[2]);
-      int lv = lvg_index(P, F, cr);
-      if (lv < 0) {
-        fc->error = kErrInternal;
-        D.hit_next[idx] = kLvgEmpty;
-        continue;
-      }
-      int old = atomicExch(&D.lvg[lv].x, idx);
-      D.hit_next[idx] = old;
-      if (old == kLvgEmpty) {
-        int tp = agg_inc(&fc->n_touched);
-        if (tp < P.max_touched) D.touched[tp] = (uint32_t)lv | kTouchedHitTag; else fc->error = kErrCapacity;
-      }
-      touch_subbox(P, F, D, fc, cr.g);
-    }
-  }
-  __syncthreads();
-
-  MLM_PHASE(5);
-  // The sorted keys are dead from here on: the key area becomes scratch for compacted cell lists.
-  uint32_t *s_list = reinterpret_cast<uint32_t *>(s_keys);
-  const int list_cap = P.sort_cap_smem * 4;            // 32-bit entries in the two key buffers
-  const int words_per_chunk = max(1, list_cap >> 5);   // a chunk of words can never overflow the list
-
-  // (d) ray walks, src/map_awareness.cpp:241-275
-  if (P.visibility_check) {
-    const int warp = tid >> 5, nwarps = blockDim.x >> 5;
-    // distinct inside end cells: each walks once (the walk depends only on (rho,phi,z))
-    for (int w0 = 0; w0 < P.col_words; w0 += words_per_chunk) {
-      if (tid == 0) s_nk = 0;
-      __syncthreads();
-      compact_bits(s_end, w0, min(w0 + words_per_chunk, P.col_words), s_list, &s_nk);
-      __syncthreads();
-      const int n_list = s_nk;
-      // entry (it*32 + lane)*nwarps + warp: every warp gets the same share of the list
-      for (int it = 0; it * 32 * nwarps < n_list; it++) {
-        const int k = (it * 32 + lane_id()) * nwarps + warp;
-        int rho = 0, z = 0;
-        if (k < n_list) {
-          const uint32_t e = s_list[k];
-          const int wi = (int)(e >> 5), wr = wi - (wi / P.words_per_row) * P.words_per_row;
-          z = wi / P.words_per_row;
-          rho = (wr << 5) + (int)(e & 31);
-        }
-        walk_batch(P, s_miss, k < n_list, rho, z);
-      }
-      __syncthreads();
-    }
-    // castable points outside the awareness range walk from the clamped cell (:261-265).  Records
-    // with identical (rho,z) repeat the same walk: drop them through a small shared-memory set
-    // (walks are idempotent, so a missed duplicate only costs time).
-    int hcap = 1024;
-    while (hcap * 2 <= list_cap && hcap < 16384) hcap <<= 1;
-    for (int i = tid; i < hcap; i += blockDim.x) s_list[i] = 0xffffffffu;
-    __syncthreads();
-    for (int it = 0; it * 32 * nwarps < n_c; it++) {
-      const int i = (it * 32 + lane_id()) * nwarps + warp;
-      RayRecord rc;
-      rc.phi_flags = kRecInside;
-      if (i < n_c) rc = REC_AT(i);
-      bool need = !(rc.phi_flags & kRecInside);
-      if (need && rc.rho < 65536 && rc.z >= -32768 && rc.z < 32768) {
-        const uint32_t key = ((uint32_t)rc.rho << 16) | (uint32_t)(rc.z + 32768);
-        uint32_t slot = (key * 2654435761u) >> 7;
-        for (int probe = 0; probe < 8; probe++) {
-          slot &= (uint32_t)(hcap - 1);
-          uint32_t old = atomicCAS(&s_list[slot], 0xffffffffu, key);
-          if (old == 0xffffffffu) break;
-          if (old == key) {
-            need = false;
-            break;
+  // From here the CTA works as two halves with their own named barriers: warps 0-15 detect the cell
+  // segments, fold them and stage the hit keys; warps 16-31 run the ray walks (which only need the
+  // records and the end-cell bitmap).  They meet again before the miss staging.
+  if (tid < kHalf) {
+    // (c1) ordered list of segment heads (first contribution of every distinct cell) and a compact decode
+    // of every contribution, both in the idle ping-pong buffer:
+    //   s_head[h]  = index into keys of the h-th cell's first contribution
+    //   s_dec[i]   = odds-table index (25 bits) | run length - 1 (5 bits, bits 25..29) | last-of-cell (bit 30);
+    //                after the fold, s_dec[s_head[h]] holds the folded probability bits of cell h
+    uint32_t *s_head = reinterpret_cast<uint32_t *>(keys_alt);
+    uint32_t *s_dec = s_head + n_k;
+    {
+      const int W = kHalf / 32, w = tid >> 5, lane = lane_id();
+      const int chunk = (((n_k + W - 1) / W) + 31) & ~31;
+      const int beg = min(w * chunk, n_k), end = min(beg + chunk, n_k);
+      int cnt = 0;
+      for (int base = beg; base < end; base += 32) {
+        const int i = base + lane;
+        bool head = false;
+        if (i < end) {
+          const uint64_t ki = keys[i];
+          const int cell = (int)(ki >> cell_shift);
+          if (cell != cell_sentinel) {
+            head = i == 0 || (int)(keys[i - 1] >> cell_shift) != cell;
+            const bool last = i + 1 >= n_k || (int)(keys[i + 1] >> cell_shift) != cell;
+            const int rk = cell - (cell / P.nRho) * P.nRho;
+            const int sstep = (int)((ki >> 7) & 31);
+            const int d = sstep == 0 ? 0 : ((sstep & 1) ? (sstep + 1) >> 1 : -(sstep >> 1));
+            const uint32_t oi = (uint32_t)((kDiffRange + d) * P.nRho + (rk - d));
+            s_dec[i] = oi | ((uint32_t)((ki & 127) - 1) << 25) | (last ? (1u << 30) : 0u);
           }
-          slot++;
         }
+        cnt += __popc(__ballot_sync(0xffffffffu, head));
       }
-      walk_batch(P, s_miss, need, rc.rho, rc.z);
+      if (lane == 0) s_wsum[w] = (uint32_t)cnt;
+      group_bar(1, kHalf);
+      if (w == 0) {
+        uint32_t sv = lane < W ? s_wsum[lane] : 0, si = sv;
+  #pragma unroll
+        for (int ofs = 1; ofs < 32; ofs <<= 1) {
+          uint32_t t = __shfl_up_sync(0xffffffffu, si, ofs);
+          if (lane >= ofs) si += t;
+        }
+        if (lane < W) s_wsum[lane] = si - sv;
+        if (lane == W - 1) s_nhead = (int)si;
+      }
+      group_bar(1, kHalf);
+      int pos = (int)s_wsum[w];
+      for (int base = beg; base < end; base += 32) {
+        const int i = base + lane;
+        const bool head = i < end && (int)(keys[i] >> cell_shift) != cell_sentinel &&
+                          (i == 0 || (keys[i - 1] >> cell_shift) != (keys[i] >> cell_shift));
+        const unsigned b = __ballot_sync(0xffffffffu, head);
+        if (head) s_head[pos + __popc(b & ((1u << lane) - 1))] = (uint32_t)i;
+        pos += __popc(b);
+      }
+    }
+    group_bar(1, kHalf);
+    // (c2) update_odds_hashmap fold, one thread per distinct cell (static: head h -> thread h, so the
+    // lanes of a warp stay in one loop).  The chain p <- 1-(1-p)(1-odd) is inherently ordered; it is
+    // flattened over (contribution, repeat) so that a lane never waits for another lane's run length,
+    // the next contribution is fetched one step ahead, and a lane leaves as soon as p saturates at 1
+    // (1 - (1-1)*(1-odd) == 1 for every later contribution).
+    {
+      const int n_head = s_nhead;
+      // dense, static assignment (head h -> thread h).  With few warps in flight every dependent
+      // instruction costs ~5 cycles, so the loop is written for instruction count: a tight 3-op repeat
+      // loop per contribution, entries pre-decoded (s_dec), the next entry and its odds fetched ahead.
+      auto fold_chain = [&](const uint32_t *heads, uint32_t *dec) {
+        for (int h = tid; h < n_head; h += kHalf) {
+          const int i0 = (int)heads[h];
+          int i = i0;
+          uint32_t e = dec[i];
+          float p = s_odds[e & 0x1ffffffu];  // first insert: hit_idx_odds_hashmap[key] = odd
+          int reps = (int)((e >> 25) & 31);  // remaining repeats of the first contribution
+          float c1 = __fsub_rn(1.0f, p);     // (1 - odd)
+          for (;;) {
+            const bool last = (e >> 30) & 1u;
+            // next entry and its (1 - odd), independent of p
+            const uint32_t en = last ? 0u : dec[i + 1];
+            const float c1n = __fsub_rn(1.0f, s_odds[en & 0x1ffffffu]);
+            for (int r = 0; r < reps; r++) p = __fsub_rn(1.0f, __fmul_rn(__fsub_rn(1.0f, p), c1));
+            if (last || p == 1.0f) break;    // p == 1: 1 - (1-1)*(1-odd) == 1 for every later contribution
+            e = en;
+            c1 = c1n;
+            reps = (int)((e >> 25) & 31) + 1;
+            i++;
+          }
+          dec[i0] = __float_as_uint(p);
+        }
+      };
+      if (in_smem) {
+        // same buffers, but addressed through the shared-memory window so the loads are LDS, not generic LD
+        uint32_t *sh = reinterpret_cast<uint32_t *>(keys_alt == s_keys ? s_keys : s_keys + P.sort_cap_smem);
+        fold_chain(sh, sh + n_k);
+      } else {
+        fold_chain(s_head, s_dec);
+      }
+    }
+    group_bar(1, kHalf);
+    {
+      const int n_head = s_nhead;
+      int base_idx = 0;
+      if (tid == 0) s_nk = atomicAdd(&fc->n_hit, n_head);  // one global reservation per column
+      group_bar(1, kHalf);
+      base_idx = s_nk;
+      for (int k = tid; k < n_head; k += kHalf) {
+        const uint64_t k0 = keys[s_head[k]];
+        const int cell = (int)(k0 >> cell_shift);
+        const int zk = cell / P.nRho, rk = cell - zk * P.nRho;
+        // first-insert stamp of the key: point stamp t of the record * 32 + substep
+        const uint32_t stamp = (REC_AT((int)((k0 >> 12) & k_mask)).t << 5) | (uint32_t)((k0 >> 7) & 31);
+        const int idx = base_idx + k;
+        if (idx >= P.max_hits) {
+          fc->error = kErrCapacity;
+          continue;
+        }
+        D.hit_key[idx] = (zk * P.nPhi + phi) * P.nRho + rk;  // mapIdx, map_awareness.h:81-84
+        D.hit_p[idx] = __uint_as_float(s_dec[s_head[k]]);
+        D.hit_t[idx] = stamp;
+        // bucket activation stamp (libstdc++ iteration order)
+        const uint32_t bucket = libstdcxx_bucket(vector_hash3(rk, phi, zk), F.bucket_count);
+        D.hit_bucket[idx] = bucket;
+        atomicMin(&act[bucket], stamp);
+        // p_w = T_wa * centre  (identity rotation: one add per axis), src/map_local.cpp:151
+        double2 cxy = __ldg(&P.centre_xy[phi * P.nRho + rk]);
+        CellRef cr = locate_cell(P, cxy.x + F.t_wa[0], cxy.y + F.t_wa[1], __ldg(&P.centre_z[zk]) + F.t_wa[2]);
+        int lv = lvg_index(P, F, cr);
+        if (lv < 0) {
+          fc->error = kErrInternal;
+          D.hit_next[idx] = kLvgEmpty;
+          continue;
+        }
+        int old = atomicExch(&D.lvg[lv].x, idx);
+        D.hit_next[idx] = old;
+        if (old == kLvgEmpty) {
+          int tp = agg_inc(&fc->n_touched);
+          if (tp < P.max_touched) D.touched[tp] = (uint32_t)lv | kTouchedHitTag; else fc->error = kErrCapacity;
+        }
+        touch_subbox(P, F, D, fc, cr.g);
+      }
+    }
+    group_bar(1, kHalf);
+
+  } else {
+    // scratch of the walk group: the radix counters are idle now -> [hash set of outside rays][end-cell list]
+    uint32_t *s_hash = s_cnt;
+    const int hcap = 4096;
+    uint32_t *s_list = s_cnt + hcap;
+    const int list_cap = kCntTotal - hcap;
+    const int words_per_chunk = max(1, list_cap >> 5);   // a chunk of words can never overflow the list
+    const int gt = tid - kHalf;                          // thread index inside the walk group
+
+    // (d) ray walks, src/map_awareness.cpp:241-275
+    if (P.visibility_check) {
+      const int warp = gt >> 5, nwarps = kHalf >> 5;
+      // distinct inside end cells: each walks once (the walk depends only on (rho,phi,z))
+      for (int w0 = 0; w0 < P.col_words; w0 += words_per_chunk) {
+        if (gt == 0) s_nlist = 0;
+        group_bar(2, kHalf);
+        compact_bits(s_end, w0, min(w0 + words_per_chunk, P.col_words), s_list, &s_nlist, warp, nwarps);
+        group_bar(2, kHalf);
+        const int n_list = s_nlist;
+        // entry (it*32 + lane)*nwarps + warp: every warp gets the same share of the list
+        for (int it = 0; it * 32 * nwarps < n_list; it++) {
+          const int k = (it * 32 + lane_id()) * nwarps + warp;
+          int rho = 0, z = 0;
+          if (k < n_list) {
+            const uint32_t e = s_list[k];
+            const int wi = (int)(e >> 5), wr = wi - (wi / P.words_per_row) * P.words_per_row;
+            z = wi / P.words_per_row;
+            rho = (wr << 5) + (int)(e & 31);
+          }
+          walk_batch(P, s_miss, k < n_list, rho, z);
+        }
+        group_bar(2, kHalf);
+      }
+      // castable points outside the awareness range walk from the clamped cell (:261-265).  Records
+      // with identical (rho,z) repeat the same walk: drop them through a small shared-memory set
+      // (walks are idempotent, so a missed duplicate only costs time).
+      for (int i = gt; i < hcap; i += kHalf) s_hash[i] = 0xffffffffu;
+      group_bar(2, kHalf);
+      for (int it = 0; it * 32 * nwarps < n_c; it++) {
+        const int i = (it * 32 + lane_id()) * nwarps + warp;
+        RayRecord rc;
+        rc.phi_flags = kRecInside;
+        if (i < n_c) rc = REC_AT(i);
+        bool need = !(rc.phi_flags & kRecInside);
+        if (need && rc.rho < 65536 && rc.z >= -32768 && rc.z < 32768) {
+          const uint32_t key = ((uint32_t)rc.rho << 16) | (uint32_t)(rc.z + 32768);
+          uint32_t slot = (key * 2654435761u) >> 7;
+          for (int probe = 0; probe < 8; probe++) {
+            slot &= (uint32_t)(hcap - 1);
+            uint32_t old = atomicCAS(&s_hash[slot], 0xffffffffu, key);
+            if (old == 0xffffffffu) break;
+            if (old == key) {
+              need = false;
+              break;
+            }
+            slot++;
+          }
+        }
+        walk_batch(P, s_miss, need, rc.rho, rc.z);
+      }
     }
   }
   __syncthreads();
 
   MLM_PHASE(6);
-  // (e) distinct miss cells -> voxel grid staging (one cell per thread); bitmap to global for export
+  // (e) distinct miss cells -> voxel grid staging (one cell per thread); bitmap to global for export.
+  // The sorted keys are dead now: the key area is the scratch for the compacted cell list.
+  uint32_t *s_list = reinterpret_cast<uint32_t *>(s_keys);
+  const int list_cap = P.sort_cap_smem * 4;            // 32-bit entries in the two key buffers
+  const int words_per_chunk = max(1, list_cap >> 5);   // a chunk of words can never overflow the list
   for (int wi = tid; wi < P.col_words; wi += blockDim.x) g_miss[wi] = s_miss[wi];
   for (int w0 = 0; w0 < P.col_words; w0 += words_per_chunk) {
     if (tid == 0) s_nk = 0;
     __syncthreads();
-    compact_bits(s_miss, w0, min(w0 + words_per_chunk, P.col_words), s_list, &s_nk);
+    compact_bits(s_miss, w0, min(w0 + words_per_chunk, P.col_words), s_list, &s_nk, tid >> 5, (int)blockDim.x >> 5);
     __syncthreads();
     const int n_list = s_nk;
     for (int k = tid; k < n_list; k += blockDim.x) {

@@ -638,6 +638,11 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   P.n = cfg->subbox_n;
   P.d_glb = P.d_sub * P.n;
   P.cells = P.n * P.n * P.n;
+  P.inv_d_sub = 1.0 / P.d_sub;
+  P.inv_d_glb = 1.0 / P.d_glb;
+  P.inv_dRho = 1.0 / P.dRho;
+  P.inv_dPhi = 1.0 / P.dPhi;
+  P.inv_dZ = 1.0 / P.dZ;
   P.cell_stride = (P.cells + 15) & ~15;
   P.lo_min = cfg->log_odds_min;
   P.lo_max = cfg->log_odds_max;

@@ -41,6 +41,7 @@ struct MapParams {
   int cell_bits;          // bits of a cell id inside a column: ceil(log2(nZ*nRho))
   // local_map_cartesian members (include/map_local.h:66-78)
   double d_sub, d_glb, d_sub_half;
+  double inv_d_sub, inv_d_glb, inv_dRho, inv_dPhi, inv_dZ;  // fl(1/d): fast path of floor_quot_exact only
   int n;                  // subbox_nxyz
   int cells;              // cell_num_subbox
   int cell_stride;        // cells rounded up to 16: per-block stride of the pool arrays

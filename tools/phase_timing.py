@@ -13,8 +13,8 @@ for k in range(6):
     m.integrate_depth(img, pose)
 c = m.debug_phase_cycles()
 act = c[:, 10] > 0
-names = ["gather", "bound", "contrib", "radix", "heads+fold", "hit-stage", "walks", "miss-stage"]
-cc = np.concatenate([c[:, 15:16], c[:, :8]], axis=1)
+names = ["gather", "bound", "contrib", "radix", "fold||walks", "miss-stage"]
+cc = np.concatenate([c[:, 15:16], c[:, :4], c[:, 6:8]], axis=1)
 d = np.diff(cc, axis=1)[act]
 tot = d.sum(1)
 order = np.argsort(-tot)
