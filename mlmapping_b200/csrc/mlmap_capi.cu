@@ -941,13 +941,40 @@ int mlm_set_free_in_bound(mlm_handle h, const double box_min[3], const double bo
 }
 
 int mlm_inflate_map(mlm_handle h, const double ct_pos[3]) {
-  (void)ct_pos;
-  if (!h) return MLM_ERR_INVALID_ARG;
-  g_last_error = "inflate_map is a SURVEY §8(f) 'next' row and not implemented yet";
-  return MLM_ERR_UNSUPPORTED;
+  if (!h || !ct_pos) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const MapParams &P = h->P;
+  if (h->cfg.inflate_n < 0 || h->cfg.inflate_global_n < 0 || h->cfg.inflate_global_n > 16) return MLM_ERR_INVALID_CONFIG;
+  InflateArgs A;
+  // local_map->get_global_idx(ct_pos, ct_glb, subbox_id): floor(p / d_glb) per axis (include/map_local.h:150)
+  for (int a = 0; a < 3; a++) A.ct_g[a] = (int)floor(ct_pos[a] / P.d_glb);
+  A.N = h->cfg.inflate_global_n;
+  A.r = h->cfg.inflate_n;
+  A.height = h->cfg.inflate_height;
+  const int W = 2 * A.N + 1, nwin = W * W * W;
+  cudaStream_t s = h->stream;
+  int *d_win = nullptr, *d_cnt = nullptr;
+  CUDA_TRY(cudaMallocAsync((void **)&d_win, (size_t)nwin * sizeof(int), s));
+  CUDA_TRY(cudaMallocAsync((void **)&d_cnt, 2 * sizeof(int), s));
+  CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), s));
+  k_inflate_reset<<<nwin, 256, 0, s>>>(P, h->D, A, d_win);
+  k_inflate_sources<false><<<nwin, 256, 0, s>>>(P, h->D, A, d_win, d_cnt);
+  k_inflate_sources<true><<<nwin, 256, 0, s>>>(P, h->D, A, d_win, d_cnt);
+  h->launches += 3;
+  int cnt[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaFreeAsync(d_win, s));
+  CUDA_TRY(cudaFreeAsync(d_cnt, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  h->cum_ram_expand += cnt[0];  // allocate_ram from inflate_atpos also counts (include/map_local.h:223)
+  h->n_submaps += cnt[0];
+  if (cnt[1]) {
+    g_last_error = "inflate_map: device raised error code " + std::to_string(cnt[1]);
+    return map_device_error(cnt[1]);
+  }
+  return MLM_OK;
 }
-
-// ---- queries ------------------------------------------------------------------------------------------
 
 int mlm_get_occupancy(mlm_handle h, const double *pos, size_t n, int32_t *out) {
   return host_query<int32_t>(h, pos, n, out, 1, [&](double *dp, int32_t *dout) {

@@ -191,6 +191,115 @@ __global__ void __launch_bounds__(256) k_set_free(MapParams P, DeviceBuffers D, 
   D.pool_lo[addr] = 0.f;
 }
 
+// ---- inflation layer: mlmap::inflate_map (src/mlmap.cpp:286-309) + inflate_atpos (include/map_local.h:233-264) ----
+// The reference walks the (2N+1)^3 window of subboxes around the body in a fixed order (x offset outermost,
+// then y, then z).  For every window subbox that exists and is not collapsed it first resets
+// inflate_occupancy to 'u', then stamps an L1 ball of radius inflate_n around each 'o' cell whose centre is
+// above flate_height; stamps cross subbox borders (allocating the neighbour if needed).  A stamp that lands
+// in a window subbox processed LATER is wiped by that subbox's reset, so the net effect is:
+//   target cell <- 'o'  iff  some source stamps it and NOT (target subbox is in the window, is processed
+//   after the source subbox, and exists when the loop gets to it).
+// Subboxes created by a stamp exist from then on (allocate_ram), so they count as "exists when reached".
+struct InflateArgs {
+  int ct_g[3];   // subbox of ct_pos
+  int N;         // inflate_global_n
+  int r;         // inflate_n
+  double height; // flate_height
+};
+__device__ __forceinline__ int window_order(const InflateArgs &A, const int g[3]) {
+  const int W = 2 * A.N + 1;
+  const int ox = g[0] - A.ct_g[0] + A.N, oy = g[1] - A.ct_g[1] + A.N, oz = g[2] - A.ct_g[2] + A.N;
+  if ((unsigned)ox >= (unsigned)W || (unsigned)oy >= (unsigned)W || (unsigned)oz >= (unsigned)W) return -1;
+  return (ox * W + oy) * W + oz;
+}
+// pass 1: reset the window subboxes that exist; remember their blocks (win_block[order], -1 = absent)
+__global__ void __launch_bounds__(256) k_inflate_reset(MapParams P, DeviceBuffers D, InflateArgs A, int *win_block) {
+  const int W = 2 * A.N + 1;
+  const int w = blockIdx.x;
+  if (w >= W * W * W) return;
+  int g[3] = {A.ct_g[0] + w / (W * W) - A.N, A.ct_g[1] + (w / W) % W - A.N, A.ct_g[2] + w % W - A.N};
+  const int block = ht_find(P, D, g);
+  if (threadIdx.x == 0) win_block[w] = block;
+  if (block < 0) return;
+  for (int i = threadIdx.x; i < P.cells; i += blockDim.x) D.pool_inf[(size_t)block * P.cell_stride + i] = 'u';
+}
+// pass 2 (ensure) / pass 3 (stamp): one thread per (window subbox, cell); sources are the 'o' cells above the height
+template <bool kStamp>
+__global__ void __launch_bounds__(256) k_inflate_sources(MapParams P, DeviceBuffers D, InflateArgs A, const int *win_block,
+                                                         int *counters /*[0]=new subboxes, [1]=error*/) {
+  const int W = 2 * A.N + 1;
+  const int w = blockIdx.x;
+  if (w >= W * W * W) return;
+  const int block = win_block[w];
+  if (block < 0) return;  // absent (or collapsed) when the loop reached it: nothing to scan
+  int g[3] = {A.ct_g[0] + w / (W * W) - A.N, A.ct_g[1] + (w / W) % W - A.N, A.ct_g[2] + w % W - A.N};
+  for (int it = threadIdx.x; it < P.cells; it += blockDim.x) {
+    if (D.pool_occ[(size_t)block * P.cell_stride + it] != 'o') continue;
+    const int cx = it % P.n, cy = (it / P.n) % P.n, cz = it / (P.n * P.n);
+    // subbox_id2xyz_glb_vec(temp_glb, it)(2) > flate_height
+    const double zc = ((double)g[2] * P.d_glb + (double)cz * P.d_sub) + P.d_sub_half;
+    if (!(zc > A.height)) continue;
+    for (int ox = -A.r; ox <= A.r; ox++)
+      for (int oy = -A.r; oy <= A.r; oy++)
+        for (int oz = -A.r; oz <= A.r; oz++) {
+          if (abs(ox) + abs(oy) + abs(oz) > A.r) continue;
+          int t[3] = {cx + ox, cy + oy, cz + oz};
+          int tg[3] = {g[0], g[1], g[2]};
+          bool expanded = false;
+          for (int m = 0; m < 3; m++) {
+            if (t[m] >= P.n) {
+              tg[m] += 1;
+              t[m] -= P.n;
+              expanded = true;
+            } else if (t[m] < 0) {
+              tg[m] -= 1;
+              t[m] += P.n;
+              expanded = true;
+            }
+          }
+          const int tsub = (t[2] * P.n + t[1]) * P.n + t[0];
+          if (!kStamp) {
+            // ensure pass: allocate_ram(glb_idx_inflate) for expanded targets (find-or-insert, one winner pops a block)
+            if (!expanded) continue;
+            uint64_t key;
+            if (!pack_glb(tg, key)) {
+              counters[1] = kErrRange;
+              continue;
+            }
+            uint32_t slot = ht_hash(key) & P.ht_mask;
+            for (uint32_t probe = 0; probe <= P.ht_mask; probe++) {
+              uint64_t k = D.ht_key[slot];
+              if (k == kEmptyKey) {
+                unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&D.ht_key[slot]),
+                                                   (unsigned long long)kEmptyKey, (unsigned long long)key);
+                if (old == kEmptyKey) {
+                  int top = atomicSub(D.free_top, 1) - 1;
+                  if (top < 0) {
+                    atomicAdd(D.free_top, 1);
+                    D.ht_val[slot] = -3;
+                    counters[1] = kErrPool;
+                  } else {
+                    D.ht_val[slot] = D.free_stack[top];
+                    atomicAdd(&counters[0], 1);
+                  }
+                  break;
+                }
+                k = (uint64_t)old;
+              }
+              if (k == key) break;
+              slot = (slot + 1) & P.ht_mask;
+            }
+          } else {
+            const int t_order = window_order(A, tg);
+            if (expanded && t_order > w) continue;  // the target subbox is reset later in the loop: stamp is wiped
+            const int tb = expanded ? ht_find(P, D, tg) : block;
+            if (tb < 0) continue;                   // collapsed / unusable subbox: allocate_ram returned false
+            D.pool_inf[(size_t)tb * P.cell_stride + tsub] = 'o';
+          }
+        }
+  }
+}
+
 // ---- export -----------------------------------------------------------------------------------------
 __global__ void k_export_list(MapParams P, DeviceBuffers D, int *out_glb3, int *out_block, int *counter, int cap) {
   uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;

@@ -206,3 +206,31 @@ def test_full_size_cfg_c_lidar():
         assert st_g.n_points > 200000
         assert_frame_parity(gpu, orc, st_g, st_o, tag=f"cfgC scan{k}")
     assert_map_parity(gpu, orc, LO_TOL)
+
+
+def test_inflate_map_and_inflate_occupancy():
+    """inflate_map (src/mlmap.cpp:286-309) incl. the wipe-by-later-reset order rule, cross-subbox stamps that
+    allocate neighbours, repeated calls at moving centres, getInflateOccupancy"""
+    cfg = config_cfg_a()
+    cfg.inflate_n, cfg.inflate_global_n = 2, 2
+    gpu, orc = MLMap(cfg), Oracle(cfg)
+    for k in range(8):
+        pose = scenes.corridor_trajectory_pose(k * 12)
+        img = scenes.corridor_depth_frame(cfg, pose, frame_idx=k)
+        st_g, st_o = gpu.integrate_depth(img, pose), orc.integrate_depth(img, pose)
+        if k % 3 == 2:
+            gpu.inflate_map(pose[:3])
+            orc.inflate_map(pose[:3])
+            assert_map_parity(gpu, orc, LO_TOL, tag=f"inflate@{k}")
+    st_g, st_o = gpu.integrate_depth(img, pose), orc.integrate_depth(img, pose)
+    assert st_g.ram_expand_cnt == st_o.ram_expand_cnt   # inflate_atpos allocations are counted too
+    m = orc.export_map()
+    assert (m["inflate"] == b"o").sum() > 1000
+    lo = m["glb"].min(0) * 1.0
+    hi = (m["glb"].max(0) + 1) * 1.0
+    pos = scenes.query_positions(200000, lo, hi, seed=7, inflate=1.0)
+    assert np.array_equal(gpu.getInflateOccupancy(pos), orc.getInflateOccupancy(pos))
+    # centre far from the data: empty window, nothing may change
+    gpu.inflate_map([100.0, 0.0, 0.0])
+    orc.inflate_map([100.0, 0.0, 0.0])
+    assert_map_parity(gpu, orc, LO_TOL, tag="inflate-empty-window")
