@@ -187,6 +187,11 @@ int mlm_set_profiling(mlm_handle h, int enable);
 int mlm_last_frame_kernel_ms(mlm_handle h, float ms[MLM_NUM_FRAME_KERNELS]);
 /* per-column phase clocks of the last k_column launch (only filled by -DMLM_PHASE_TIMING builds) */
 int mlm_debug_phase_cycles(mlm_handle h, long long *out, size_t cap);
+/* sampled project_depth (cfg.sample_cnt > 0) draws pixels from the handle's own glibc-compatible rand() stream
+ * (seed 1 like a process that never calls srand); mlm_srand reseeds it, mlm_debug_rand draws from it
+ * (h == NULL: from a fresh seed-1 stream) so tests can compare with libc's rand() */
+int mlm_srand(mlm_handle h, unsigned seed);
+int mlm_debug_rand(mlm_handle h, int32_t *out, size_t n);
 /* number of kernels launched by this handle since creation */
 int mlm_kernel_launch_count(mlm_handle h, int64_t *count);
 

@@ -108,7 +108,7 @@ ABI_SYMBOLS = [
     "mlm_copy_to_device", "mlm_copy_to_host", "mlm_flush_l2", "mlm_kernel_launch_count",
     "mlm_last_frame_hits", "mlm_last_frame_misses", "mlm_export_map_count", "mlm_export_map",
     "mlm_debug_log10f", "mlm_set_profiling", "mlm_last_frame_kernel_ms", "mlm_sizeof_config",
-    "mlm_sizeof_frame_stats", "mlm_debug_phase_cycles", "mlm_host_alloc", "mlm_host_free",
+    "mlm_sizeof_frame_stats", "mlm_debug_phase_cycles", "mlm_host_alloc", "mlm_host_free", "mlm_srand", "mlm_debug_rand",
 ]
 FRAME_KERNELS = ["k_project", "k_column", "k_fuse"]
 
@@ -180,6 +180,8 @@ def load_library() -> C.CDLL:
         "mlm_export_map": ([vp, sz, vp, vp, vp, vp, vp, C.POINTER(sz)], C.c_int),
         "mlm_debug_log10f": ([vp, vp, sz, vp], C.c_int),
         "mlm_debug_phase_cycles": ([vp, vp, sz], C.c_int),
+        "mlm_srand": ([vp, C.c_uint], C.c_int),
+        "mlm_debug_rand": ([vp, vp, sz], C.c_int),
         "mlm_set_profiling": ([vp, C.c_int], C.c_int),
         "mlm_last_frame_kernel_ms": ([vp, fp], C.c_int),
     }
@@ -425,6 +427,9 @@ class MLMap:
         out = np.zeros((n, 16), dtype=np.int64)
         self._check(self._lib.mlm_debug_phase_cycles(self._h, out.ctypes.data, out.size))
         return out
+
+    def srand(self, seed: int):
+        self._check(self._lib.mlm_srand(self._h, seed))
 
     def kernel_launch_count(self) -> int:
         v = C.c_int64()

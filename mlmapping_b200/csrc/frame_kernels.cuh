@@ -239,7 +239,9 @@ __device__ __forceinline__ int block_exclusive_scan(int *data, int n, int *s_war
   return s_warp[32];
 }
 
-template <bool kDepth>
+// kMode: 0 = sensor-frame points (xyz doubles), 1 = full depth image (every pixel, row-major),
+//        2 = sampled depth pixels: input is uint2 {pixel index, raw depth} in sampling order (src/mlmap.cpp:321-346)
+template <int kMode>
 __global__ void __launch_bounds__(256) k_project(MapParams P, DeviceBuffers D, FrameParams F) {
   extern __shared__ int s_hist[];  // [nPhi] counts, [nPhi] offsets, [nPhi] contribution bounds
   __shared__ int s_cnt[3];
@@ -264,11 +266,19 @@ __global__ void __launch_bounds__(256) k_project(MapParams P, DeviceBuffers D, F
   int valid = 0, inside = 0, cast = 0, rank = 0;
   if (i < N) {
     double xs, ys, zs;
-    if (kDepth) {
-      // project_depth, src/mlmap.cpp:329-346 (full-frame mode: every pixel, v outer, u inner)
-      uint16_t raw = __ldg(reinterpret_cast<const uint16_t *>(input) + i);
+    if (kMode != 0) {
+      // project_depth, src/mlmap.cpp:329-346 (kMode 1: every pixel, v outer / u inner; kMode 2: the sampled pixels)
+      int pix = i;
+      uint16_t raw;
+      if (kMode == 1) {
+        raw = __ldg(reinterpret_cast<const uint16_t *>(input) + i);
+      } else {
+        const uint2 sp = __ldg(reinterpret_cast<const uint2 *>(input) + i);
+        pix = (int)sp.x;
+        raw = (uint16_t)sp.y;
+      }
       if (raw != 0) {
-        int v = i / cols, u = i - v * cols;
+        int v = pix / cols, u = pix - v * cols;
         double depth = (double)(int)raw * P.inv_factor;
         xs = (double)__fsub_rn((float)u, P.cx) * depth / (double)P.fx;
         ys = (double)__fsub_rn((float)v, P.cy) * depth / (double)P.fy;

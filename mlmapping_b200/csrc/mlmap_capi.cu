@@ -111,6 +111,38 @@ uint32_t chain_cover(uint32_t n) {  // smallest chain value >= n
   return 0;
 }
 
+// glibc rand() == random_r() TYPE_3 (x^31 + x^3 + 1 additive feedback), stdlib/random_r.c: the reference
+// samples pixels with rand() (src/mlmap.cpp:324-325) and never calls srand(), i.e. seed 1.  Own state per
+// handle so the product does not share libc's global generator with anybody.
+struct GlibcRand {
+  int32_t r[31];
+  int f = 3, b = 0;
+  GlibcRand() { seed(1); }
+  void seed(unsigned s) {
+    if (s == 0) s = 1;
+    r[0] = (int32_t)s;
+    int32_t word = (int32_t)s;
+    for (int i = 1; i < 31; i++) {
+      long hi = word / 127773, lo = word % 127773;
+      long w = 16807 * lo - 2836 * hi;
+      if (w < 0) w += 2147483647;
+      word = (int32_t)w;
+      r[i] = word;
+    }
+    f = 3;
+    b = 0;
+    for (int i = 0; i < 310; i++) next();
+  }
+  int next() {
+    uint32_t v = (uint32_t)r[f] + (uint32_t)r[b];
+    r[f] = (int32_t)v;
+    int res = (int)((v >> 1) & 0x7fffffff);
+    if (++f >= 31) f = 0;
+    if (++b >= 31) b = 0;
+    return res;
+  }
+};
+
 int next_pow2(int n) {
   int p = 1;
   while (p < n) p <<= 1;
@@ -135,9 +167,10 @@ struct mlm_map {
   int64_t cum_ram_expand = 0, cum_obs = 0, n_submaps = 0;  // cumulative counters (reference ram_expand_cnt / obs_cnt)
   uint32_t frame_idx = 0;
   int last_parity = 0;
-  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};  // [0] depth input, [1] point input
-  cudaGraph_t graph[2] = {nullptr, nullptr};
-  cudaGraphNode_t graph_nodes[2][3] = {};
+  GlibcRand rng;  // project_depth's rand() stream (sampled mode)
+  cudaGraphExec_t graph_exec[3] = {nullptr, nullptr, nullptr};  // by input mode: points, depth image, sampled pixels
+  cudaGraph_t graph[3] = {nullptr, nullptr, nullptr};
+  cudaGraphNode_t graph_nodes[3][3] = {};
   int use_graph = 1;
   void *h_stage = nullptr;        // pinned input staging
   size_t stage_bytes = 0;
@@ -325,11 +358,13 @@ int order_slow_path(mlm_map *h, int n, uint32_t *B_final_out) {
   return MLM_OK;
 }
 
-int run_frame(mlm_map *h, bool depth, const void *d_in, int rows, int cols, int n_points, const double T_wb[7],
+// mode: 0 = points, 1 = full depth image, 2 = sampled depth pixels (d_in = uint2 {pixel, raw} x n_points)
+int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_points, const double T_wb[7],
               mlm_frame_stats *stats) {
+  const bool depth = mode == 1;
   const MapParams &P = h->P;
   cudaStream_t s = h->stream;
-  const int N = depth ? rows * cols : n_points;
+  const int N = depth ? rows * cols : n_points;  // sampled mode: n_points sampled pixels of a rows x cols image
   if (N < 0 || N > P.max_points) {
     g_last_error = "frame has more points than cfg.max_points";
     return MLM_ERR_CAPACITY;
@@ -382,10 +417,12 @@ int run_frame(mlm_map *h, bool depth, const void *d_in, int rows, int cols, int 
   if (prof || !h->use_graph) {
 #define MLM_MARK(i) do { if (prof) cudaEventRecord(h->kev[i], s); } while (0)
     MLM_MARK(0);
-    if (depth)
-      k_project<true><<<proj_grid, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(Pk, Dk, Fk);
+    if (mode == 1)
+      k_project<1><<<proj_grid, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(Pk, Dk, Fk);
+    else if (mode == 2)
+      k_project<2><<<proj_grid, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(Pk, Dk, Fk);
     else
-      k_project<false><<<proj_grid, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(Pk, Dk, Fk);
+      k_project<0><<<proj_grid, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(Pk, Dk, Fk);
     MLM_MARK(1);
     k_column<<<P.nPhi, kColThreads, h->col_smem_bytes, s>>>(Pk, Dk, Fk);
     MLM_MARK(2);
@@ -394,9 +431,9 @@ int run_frame(mlm_map *h, bool depth, const void *d_in, int rows, int cols, int 
 #undef MLM_MARK
   } else {
     // the whole frame is one launch of a 3-kernel graph; the per-frame values travel as kernel arguments
-    const int gi = depth ? 0 : 1;
+    const int gi = mode;
     cudaKernelNodeParams np[3] = {};
-    np[0].func = depth ? (void *)k_project<true> : (void *)k_project<false>;
+    np[0].func = mode == 1 ? (void *)k_project<1> : (mode == 2 ? (void *)k_project<2> : (void *)k_project<0>);
     np[0].gridDim = dim3(full_grid);  // fixed grid: CTAs beyond this frame's point count return at once
     np[0].blockDim = dim3(256);
     np[0].sharedMemBytes = (unsigned)((size_t)3 * P.nPhi * sizeof(int));
@@ -483,8 +520,11 @@ int run_frame(mlm_map *h, bool depth, const void *d_in, int rows, int cols, int 
   return MLM_OK;
 }
 
-int ensure_input(mlm_map *h, size_t bytes) {
+// input staging (device buffer + pinned host mirror).  `bytes` is what this frame needs, `capacity` what the
+// handle can ever need for this input kind: allocated once at capacity so frames of varying size never re-allocate
+int ensure_input(mlm_map *h, size_t bytes, size_t capacity = 0) {
   if (bytes <= h->input_bytes) return MLM_OK;
+  bytes = std::max(bytes, capacity);
   if (h->d_input) cudaFree(h->d_input);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   h->d_input = nullptr;
@@ -562,7 +602,7 @@ int mlm_default_config(mlm_config *c) {
   c->inflate_global_n = 2;
   c->apply_inflate = 1;
   c->inflate_height = 0.1;
-  c->sample_cnt = 0;  // full-frame mode (the north-star workload); the yaml's 500 selects sampled mode
+  c->sample_cnt = 500;  // mlmapping_sample_cnt (config_sim.yaml:37); 0 selects the full-frame mode of the north star
   c->max_points = 640 * 480;
   c->pool_submaps = 32768;
   return MLM_OK;
@@ -581,9 +621,9 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
     g_last_error = "use_exploration_frontiers=true (update_observation / release pass) is not implemented on the GPU path";
     return MLM_ERR_UNSUPPORTED;
   }
-  if (cfg->sample_cnt != 0) {
-    g_last_error = "sampled project_depth (mlmapping_sample_cnt > 0) is not implemented; use full-frame mode (0)";
-    return MLM_ERR_UNSUPPORTED;
+  if (cfg->sample_cnt < 0 || cfg->sample_cnt > cfg->max_points) {
+    g_last_error = "sample_cnt must be in [0, max_points]";
+    return MLM_ERR_INVALID_CONFIG;
   }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
@@ -829,7 +869,7 @@ int mlm_destroy(mlm_handle h) {
   if (!h) return MLM_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < 3; i++) {
     if (h->graph_exec[i]) cudaGraphExecDestroy(h->graph_exec[i]);
     if (h->graph[i]) cudaGraphDestroy(h->graph[i]);
   }
@@ -856,8 +896,29 @@ int mlm_integrate_depth_u16(mlm_handle h, const uint16_t *img, int rows, int col
     return MLM_ERR_CAPACITY;
   }
   CUDA_TRY(cudaSetDevice(h->device));
+  if (h->cfg.sample_cnt > 0) {
+    // mlmap::project_depth as written (src/mlmap.cpp:321-346): up to sample_cnt valid pixels out of at most
+    // 2*sample_cnt rand() draws; only the sampled (pixel, depth) pairs travel to the device
+    const size_t cnt_max = (size_t)h->cfg.sample_cnt;
+    int rc2 = ensure_input(h, cnt_max * sizeof(uint2), cnt_max * sizeof(uint2));
+    if (rc2 != MLM_OK) return rc2;
+    uint2 *pairs = reinterpret_cast<uint2 *>(h->h_stage);
+    size_t n_pts = 0;
+    int cnt = 0;
+    const int max_iter = 2 * (int)cnt_max;
+    while (n_pts < cnt_max && cnt < max_iter) {
+      cnt++;
+      const size_t v = (size_t)(h->rng.next() % rows);
+      const size_t u = (size_t)(h->rng.next() % cols);
+      const uint16_t raw = *reinterpret_cast<const uint16_t *>(reinterpret_cast<const char *>(img) + v * stride_bytes + u * 2);
+      if (raw == 0) continue;
+      pairs[n_pts++] = make_uint2((unsigned)(v * cols + u), raw);
+    }
+    if (n_pts) CUDA_TRY(cudaMemcpyAsync(h->d_input, pairs, n_pts * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
+    return run_frame(h, 2, h->d_input, rows, cols, (int)n_pts, T_wb, stats);
+  }
   const size_t bytes = (size_t)rows * cols * 2;
-  int rc = ensure_input(h, bytes);
+  int rc = ensure_input(h, bytes, (size_t)h->P.max_points * 2);
   if (rc != MLM_OK) return rc;
   // Page-locked caller memory (mlm_host_alloc / cudaHostRegister) with dense rows is copied
   // straight from the caller's buffer; anything else is packed into the pinned staging buffer first.
@@ -876,14 +937,18 @@ int mlm_integrate_depth_u16(mlm_handle h, const uint16_t *img, int rows, int col
     src = h->h_stage;
   }
   CUDA_TRY(cudaMemcpyAsync(h->d_input, src, bytes, cudaMemcpyHostToDevice, h->stream));
-  return run_frame(h, true, h->d_input, rows, cols, 0, T_wb, stats);
+  return run_frame(h, 1, h->d_input, rows, cols, 0, T_wb, stats);
 }
 
 int mlm_integrate_depth_u16_device(mlm_handle h, const uint16_t *d_img, int rows, int cols, const double T_wb[7],
                                    mlm_frame_stats *stats) {
   if (!h || !d_img || !T_wb || rows <= 0 || cols <= 0) return MLM_ERR_INVALID_ARG;
+  if (h->cfg.sample_cnt > 0) {
+    g_last_error = "sampled project_depth needs the host image (pixel values decide how many rand() draws are consumed)";
+    return MLM_ERR_UNSUPPORTED;
+  }
   CUDA_TRY(cudaSetDevice(h->device));
-  return run_frame(h, true, d_img, rows, cols, 0, T_wb, stats);
+  return run_frame(h, 1, d_img, rows, cols, 0, T_wb, stats);
 }
 
 int mlm_integrate_points_f64(mlm_handle h, const double *xyz, int n, const double T_wb[7], mlm_frame_stats *stats) {
@@ -894,20 +959,20 @@ int mlm_integrate_points_f64(mlm_handle h, const double *xyz, int n, const doubl
   }
   CUDA_TRY(cudaSetDevice(h->device));
   const size_t bytes = (size_t)std::max(n, 1) * 24;
-  int rc = ensure_input(h, bytes);
+  int rc = ensure_input(h, bytes, (size_t)h->P.max_points * 24);
   if (rc != MLM_OK) return rc;
   if (n > 0) {
     memcpy(h->h_stage, xyz, (size_t)n * 24);
     CUDA_TRY(cudaMemcpyAsync(h->d_input, h->h_stage, (size_t)n * 24, cudaMemcpyHostToDevice, h->stream));
   }
-  return run_frame(h, false, h->d_input, 0, 0, n, T_wb, stats);
+  return run_frame(h, 0, h->d_input, 0, 0, n, T_wb, stats);
 }
 
 int mlm_integrate_points_f64_device(mlm_handle h, const double *d_xyz, int n, const double T_wb[7],
                                     mlm_frame_stats *stats) {
   if (!h || (!d_xyz && n > 0) || !T_wb || n < 0) return MLM_ERR_INVALID_ARG;
   CUDA_TRY(cudaSetDevice(h->device));
-  return run_frame(h, false, d_xyz, 0, 0, n, T_wb, stats);
+  return run_frame(h, 0, d_xyz, 0, 0, n, T_wb, stats);
 }
 
 int mlm_set_free_in_bound(mlm_handle h, const double box_min[3], const double box_max[3]) {
@@ -1103,6 +1168,18 @@ int mlm_debug_phase_cycles(mlm_handle h, long long *out, size_t cap) {
   if (!h || !out) return MLM_ERR_INVALID_ARG;
   size_t n = std::min(cap, (size_t)h->P.nPhi * 16);
   CUDA_TRY(cudaMemcpy(out, h->D.debug_cycles, n * sizeof(long long), cudaMemcpyDeviceToHost));
+  return MLM_OK;
+}
+int mlm_srand(mlm_handle h, unsigned seed) {
+  if (!h) return MLM_ERR_INVALID_ARG;
+  h->rng.seed(seed);
+  return MLM_OK;
+}
+int mlm_debug_rand(mlm_handle h, int32_t *out, size_t n) {
+  if (!out && n) return MLM_ERR_INVALID_ARG;
+  GlibcRand local;
+  GlibcRand &g = h ? h->rng : local;
+  for (size_t i = 0; i < n; i++) out[i] = g.next();
   return MLM_OK;
 }
 int mlm_kernel_launch_count(mlm_handle h, int64_t *count) {

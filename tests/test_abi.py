@@ -46,6 +46,7 @@ def test_default_config_is_config_sim_yaml(lib):
     assert c.subbox_n == 10 and abs(c.subbox_d_xyz - 0.2) < 1e-15
     assert abs(c.log_odds_max - 4.2) < 1e-6 and abs(c.log_odds_miss + 0.9) < 1e-6
     assert c.cam_fx == pytest.approx(347.99755859375)
+    assert c.sample_cnt == 500
     assert list(c.T_bs) == [0.12, 0.0, 0.0, 0.5, -0.5, 0.5, -0.5]
 
 
@@ -71,3 +72,14 @@ def test_invalid_config_and_no_silent_cpu_fallback(lib):
     # null handles are rejected, not dereferenced
     assert lib.mlm_sync(None) == 1
     assert lib.mlm_destroy(None) == 1
+
+
+def test_rand_stream_is_glibc_rand(lib):
+    """sampled project_depth replays glibc's rand() (TYPE_3 random_r, seed 1) from a per-handle state"""
+    import numpy as np
+    out = np.zeros(4096, dtype=np.int32)
+    assert lib.mlm_debug_rand(None, out.ctypes.data, out.size) == 0
+    libc = C.CDLL("libc.so.6")
+    libc.srand(1)
+    ref = np.array([libc.rand() for _ in range(out.size)], dtype=np.int32)
+    assert np.array_equal(out, ref)

@@ -234,3 +234,24 @@ def test_inflate_map_and_inflate_occupancy():
     gpu.inflate_map([100.0, 0.0, 0.0])
     orc.inflate_map([100.0, 0.0, 0.0])
     assert_map_parity(gpu, orc, LO_TOL, tag="inflate-empty-window")
+
+
+def test_sampled_project_depth_matches_glibc_rand_stream():
+    """mlmapping_sample_cnt = 500 (the reference's live configuration, config_sim.yaml:37): pixels drawn with
+    rand() % rows / rand() % cols, at most 2*cnt draws, zero pixels skipped (src/mlmap.cpp:321-346)"""
+    import ctypes as C
+    cfg = config_cfg_a()
+    cfg.sample_cnt = 500
+    libc = C.CDLL("libc.so.6")
+    gpu, orc = MLMap(cfg), Oracle(cfg)
+    libc.srand(1)  # the oracle draws from libc's global stream like the reference; the handle owns a seed-1 stream
+    for k in range(12):
+        pose = scenes.corridor_trajectory_pose(k * 7)
+        img = scenes.corridor_depth_frame(cfg, pose, frame_idx=k)
+        if k == 5:
+            img[::2, :] = 0          # many invalid pixels: fewer than 500 points after 1000 draws
+        st_o = orc.integrate_depth(img, pose)
+        st_g = gpu.integrate_depth(img, pose)
+        assert st_g.n_points == st_o.n_points and (st_g.n_points == 500 or k == 5)
+        assert_frame_parity(gpu, orc, st_g, st_o, tag=f"sampled{k}")
+    assert_map_parity(gpu, orc, LO_TOL)
