@@ -210,6 +210,10 @@ int mlm_export_map_count(mlm_handle h, size_t *n_submaps);
 int mlm_export_map(mlm_handle h, size_t cap_submaps, int32_t *glb3, uint8_t *collapsed,
                    char *occupancy, char *inflate_occupancy, float *log_odds, size_t *n_out);
 
+/* Exploration mode: frontier set of every subbox (reference struct subbox::frontier, include/map_local.h:58) as a
+ * bitmask of ceil(subbox_n^3 / 32) 32-bit words per subbox (bit c = cell id c), with its own glb3 list. */
+int mlm_export_frontier(mlm_handle h, size_t cap_submaps, int32_t *glb3, uint32_t *frontier_words, size_t *n_out);
+
 /* glibc-2.39 log10f as evaluated on device (parity test hook, SURVEY §7 hard part 3) */
 int mlm_debug_log10f(mlm_handle h, const float *x, size_t n, float *out);
 

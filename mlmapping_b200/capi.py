@@ -108,7 +108,7 @@ ABI_SYMBOLS = [
     "mlm_copy_to_device", "mlm_copy_to_host", "mlm_flush_l2", "mlm_kernel_launch_count",
     "mlm_last_frame_hits", "mlm_last_frame_misses", "mlm_export_map_count", "mlm_export_map",
     "mlm_debug_log10f", "mlm_set_profiling", "mlm_last_frame_kernel_ms", "mlm_sizeof_config",
-    "mlm_sizeof_frame_stats", "mlm_debug_phase_cycles", "mlm_host_alloc", "mlm_host_free", "mlm_srand", "mlm_debug_rand",
+    "mlm_sizeof_frame_stats", "mlm_debug_phase_cycles", "mlm_host_alloc", "mlm_host_free", "mlm_srand", "mlm_debug_rand", "mlm_export_frontier",
 ]
 FRAME_KERNELS = ["k_project", "k_column", "k_fuse"]
 
@@ -178,6 +178,7 @@ def load_library() -> C.CDLL:
         "mlm_last_frame_misses": ([vp, vp, sz, C.POINTER(sz)], C.c_int),
         "mlm_export_map_count": ([vp, C.POINTER(sz)], C.c_int),
         "mlm_export_map": ([vp, sz, vp, vp, vp, vp, vp, C.POINTER(sz)], C.c_int),
+        "mlm_export_frontier": ([vp, sz, vp, vp, C.POINTER(sz)], C.c_int),
         "mlm_debug_log10f": ([vp, vp, sz, vp], C.c_int),
         "mlm_debug_phase_cycles": ([vp, vp, sz], C.c_int),
         "mlm_srand": ([vp, C.c_uint], C.c_int),
@@ -481,8 +482,19 @@ class MLMap:
                                                  inf.ctypes.data, lo.ctypes.data, C.byref(n)))
             assert n.value == cap, (n.value, cap)
         order = np.lexsort((glb[:, 2], glb[:, 1], glb[:, 0]))
-        return {"glb": glb[order], "collapsed": col[order], "occupancy": occ[order], "inflate": inf[order],
-                "log_odds": lo[order]}
+        out = {"glb": glb[order], "collapsed": col[order], "occupancy": occ[order], "inflate": inf[order],
+               "log_odds": lo[order]}
+        if self.cfg.use_exploration_frontiers:
+            fw = (self.cells + 31) // 32
+            g2 = np.zeros((cap, 3), dtype=np.int32)
+            words = np.zeros((cap, fw), dtype=np.uint32)
+            if cap:
+                self._check(self._lib.mlm_export_frontier(self._h, cap, g2.ctypes.data, words.ctypes.data, C.byref(n)))
+            o2 = np.lexsort((g2[:, 2], g2[:, 1], g2[:, 0]))
+            assert np.array_equal(g2[o2], out["glb"])
+            # same byte layout as the oracle's export: bit c of the little-endian bitmask, cells/8 bytes per subbox
+            out["frontier"] = words[o2].view(np.uint8)[:, :(self.cells + 7) // 8].copy()
+        return out
 
     def debug_log10f(self, x: np.ndarray) -> np.ndarray:
         a = np.ascontiguousarray(x, dtype=np.float32)

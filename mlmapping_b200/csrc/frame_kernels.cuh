@@ -146,6 +146,23 @@ __device__ __forceinline__ uint32_t ht_hash(uint64_t k) {  // splitmix64 finalis
   k ^= k >> 31;
   return (uint32_t)k;
 }
+// lookup that also reports the hash slot (collapsed subboxes keep their element 0 in per-slot arrays)
+__device__ __forceinline__ int ht_find_slot(const MapParams &P, const DeviceBuffers &D, const int g[3], uint32_t &slot_out) {
+  uint64_t key;
+  slot_out = 0;
+  if (!pack_glb(g, key)) return -1;
+  uint32_t slot = ht_hash(key) & P.ht_mask;
+  for (uint32_t probe = 0; probe <= P.ht_mask; probe++) {
+    uint64_t k = D.ht_key[slot];
+    if (k == key) {
+      slot_out = slot;
+      return D.ht_val[slot];
+    }
+    if (k == kEmptyKey) return -1;
+    slot = (slot + 1) & P.ht_mask;
+  }
+  return -1;
+}
 // read-only lookup of a subbox: returns pool block (>=0), or -1 if absent
 __device__ __forceinline__ int ht_find(const MapParams &P, const DeviceBuffers &D, const int g[3]) {
   uint64_t key;
@@ -485,7 +502,8 @@ __device__ __forceinline__ WalkStart walk_prepare(const MapParams &P, int rho, i
 }
 // All 32 lanes cooperate on one ray: lane l owns rho step r = 32*w + l; lanes that land in the same
 // z row merge into one shared-memory atomicOr (warp-aggregated by __match_any_sync).
-__device__ __forceinline__ void walk_mark(const MapParams &P, uint32_t *s_miss, double rate, int rho, int z) {
+__device__ __forceinline__ void walk_mark(const MapParams &P, uint32_t *s_miss, double rate, int rho, int z,
+                                          uint32_t *stamp_col, uint32_t t) {
   const int lane = lane_id();
   const double zd = (double)z;
   const int w_top = (rho - 1) >> 5;
@@ -496,12 +514,15 @@ __device__ __forceinline__ void walk_mark(const MapParams &P, uint32_t *s_miss, 
     // |v| < 2^31 on every valid lane of a sane ray; round_to_int_x86 handles the rest exactly as x86 would
     const int zc = round_to_int_x86(zd - diff * rate);
     valid = valid && zc >= 0 && zc < P.nZ;
+    // exploration mode: first-insert stamp of the miss cell = (point stamp, step along the ray: r = rho-1 first)
+    if (stamp_col && valid) atomicMin(&stamp_col[zc * P.nRho + r], t * (uint32_t)P.nRho + (uint32_t)(rho - 1 - r));
     const unsigned peers = __match_any_sync(0xffffffffu, valid ? zc : -1 - lane);
     if (valid && (peers & ((1u << lane) - 1)) == 0) atomicOr(&s_miss[zc * P.words_per_row + w], peers);
   }
 }
 // one prepared ray per lane (need = this lane has one); the warp marks them one after the other
-__device__ __forceinline__ void walk_batch(const MapParams &P, uint32_t *s_miss, bool need, int rho, int z) {
+__device__ __forceinline__ void walk_batch(const MapParams &P, uint32_t *s_miss, bool need, int rho, int z,
+                                           uint32_t *stamp_col = nullptr, uint32_t t = 0) {
   WalkStart ws;
   ws.rate = 0.0;
   ws.rho = 0;
@@ -514,7 +535,8 @@ __device__ __forceinline__ void walk_batch(const MapParams &P, uint32_t *s_miss,
     const double rate = __shfl_sync(0xffffffffu, ws.rate, src);
     const int r0 = __shfl_sync(0xffffffffu, ws.rho, src);
     const int z0 = __shfl_sync(0xffffffffu, ws.z, src);
-    walk_mark(P, s_miss, rate, r0, z0);
+    const uint32_t t0 = __shfl_sync(0xffffffffu, t, src);
+    walk_mark(P, s_miss, rate, r0, z0, stamp_col, t0);
   }
 }
 
@@ -637,6 +659,14 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   uint64_t *s_keys = reinterpret_cast<uint64_t *>(s_raw + col_smem_prefix_bytes(P.col_words, P.nRho));
   for (int i = tid; i < kOddsRows * P.nRho; i += blockDim.x) s_odds[i] = __ldg(&P.odds_table[i]);
   for (int i = tid; i < P.nRho; i += blockDim.x) s_reach[i] = __ldg(&P.k_reach[i]);
+  // exploration mode: per-column stamp arrays (earliest point stamp per end cell, first-insert stamp per miss cell)
+  uint32_t *end_t_col = P.explore ? D.end_t + (size_t)phi * P.nZ * P.nRho : nullptr;
+  uint32_t *stamp_col = P.explore ? D.miss_stamp + (size_t)phi * P.nZ * P.nRho : nullptr;
+  if (P.explore)
+    for (int i = tid; i < P.nZ * P.nRho; i += blockDim.x) {
+      end_t_col[i] = 0xffffffffu;
+      stamp_col[i] = 0xffffffffu;
+    }
   // ---- locate this column's records in the per-CTA windows k_project wrote (replaces a scatter pass):
   // s_map[k] = index into rec_lin of the column's k-th record
   __shared__ int s_warp[33];
@@ -744,6 +774,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
     const int rho = rc.rho, z = rc.z;
     const int reps = (int)((rc.phi_flags >> kRecCountShift) & kRecCountMask);
     if (P.visibility_check) atomicOr(&s_end[z * P.words_per_row + (rho >> 5)], 1u << (rho & 31));
+    if (P.explore) atomicMin(&end_t_col[z * P.nRho + rho], rc.t);
     const double rate = ray_rate(P, rho, z);
     const int dmax = min(s_reach[rho], P.nRho - 1 - rho);
     int pos = s_pos[i];
@@ -944,7 +975,8 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
             z = wi / P.words_per_row;
             rho = (wr << 5) + (int)(e & 31);
           }
-          walk_batch(P, s_miss, k < n_list, rho, z);
+          walk_batch(P, s_miss, k < n_list, rho, z, stamp_col,
+                     (P.explore && k < n_list) ? end_t_col[z * P.nRho + rho] : 0u);
         }
         group_bar(2, kHalf);
       }
@@ -959,7 +991,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
         rc.phi_flags = kRecInside;
         if (i < n_c) rc = REC_AT(i);
         bool need = !(rc.phi_flags & kRecInside);
-        if (need && rc.rho < 65536 && rc.z >= -32768 && rc.z < 32768) {
+        if (need && !P.explore && rc.rho < 65536 && rc.z >= -32768 && rc.z < 32768) {
           const uint32_t key = ((uint32_t)rc.rho << 16) | (uint32_t)(rc.z + 32768);
           uint32_t slot = (key * 2654435761u) >> 7;
           for (int probe = 0; probe < 8; probe++) {
@@ -973,7 +1005,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
             slot++;
           }
         }
-        walk_batch(P, s_miss, need, rc.rho, rc.z);
+        walk_batch(P, s_miss, need, rc.rho, rc.z, stamp_col, rc.t);
       }
     }
   }
@@ -1002,6 +1034,18 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
       if (lv < 0) {
         fc->error = kErrInternal;
         continue;
+      }
+      if (P.explore) {
+        // per-frame miss list for the ordered exploration passes
+        const int idx_cell = (z * P.nPhi + phi) * P.nRho + r;  // mapIdx
+        const uint32_t st = stamp_col[z * P.nRho + r];
+        const uint32_t bkt = (uint32_t)((uint64_t)(uint32_t)idx_cell % (uint64_t)F.bucket_count_miss);
+        atomicMin(&D.act_miss[F.parity][bkt], st);
+        const int j = agg_inc(&fc->n_miss_list);
+        D.miss_idx[j] = idx_cell;
+        D.miss_lv[j] = lv;
+        D.miss_t[j] = st;
+        D.miss_bucket[j] = bkt;
       }
       int old = atomicAdd(&D.lvg[lv].y, 1);
       if (old == 0) {
@@ -1046,12 +1090,15 @@ __device__ __forceinline__ void publish_counters(const DeviceBuffers &D, FrameCo
 
 // ---- K5: clamped log-odds fusion, one thread per touched cell (map_local.cpp:147-207) ---------------
 constexpr int kFuseLocal = 16;
+// kPhase 0: hits then misses (normal mode).  Exploration mode splits the pass so that update_observation can
+// look at the neighbours' state between them: kPhase 1 = hits only (LVG left intact), kPhase 2 = misses only.
+template <int kPhase>
 __global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D, FrameParams F) {
   FrameCounters *fc = D.fc[F.parity];
   const uint32_t *act = D.act[F.parity];
   const int n_hit_frame = fc->n_hit;
   // a frame that crosses a libstdc++ rehash needs the slow ordering pass first (host re-launches)
-  if (F.order_mode == 0 && n_hit_frame > (int)F.bucket_count) {
+  if (kPhase == 0 && F.order_mode == 0 && n_hit_frame > (int)F.bucket_count) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       fc->overflow = 1;
       publish_counters(D, fc);
@@ -1083,18 +1130,34 @@ __global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D, Fram
     // the claimed marker owns the cell (and gets head + miss count in one 64-bit exchange); the other
     // one only restores the empty marker.
     unsigned long long *slot = reinterpret_cast<unsigned long long *>(&D.lvg[lv]);
-    const unsigned long long old = atomicExch(slot, kClaimed64);
-    const int head = (int)(uint32_t)old, mc = (int)(old >> 32);
-    if (head == kLvgClaimed) {
-      *slot = kEmpty64;
-      continue;
+    int head, mc;
+    bool counted_by_hits = false;  // kPhase 2: the hits-only phase already counted this cell as touched
+    if (kPhase == 1) {
+      // hits-only phase: only the hit entry of a cell works, and the staging stays for the miss phase
+      if (!(e & kTouchedHitTag)) continue;
+      head = D.lvg[lv].x;
+      mc = 0;
+    } else {
+      const unsigned long long old = atomicExch(slot, kClaimed64);
+      head = (int)(uint32_t)old;
+      mc = (int)(old >> 32);
+      if (head == kLvgClaimed) {
+        *slot = kEmpty64;
+        continue;
+      }
+      if (!(head != kLvgEmpty && mc > 0)) *slot = kEmpty64;  // single entry: restore ourselves
+      if (kPhase == 2) {
+        counted_by_hits = head != kLvgEmpty;
+        head = kLvgEmpty;  // hits were applied by the hits-only phase
+        D.lvg_tkey[lv] = 0ull;
+      }
     }
-    if (!(head != kLvgEmpty && mc > 0)) *slot = kEmpty64;  // single entry: restore ourselves
     if (block < 0) continue;  // collapsed subbox (allocate_ram false) or pool error
     const size_t addr = (size_t)block * P.cell_stride + sub;
     float lo = D.pool_lo[addr];
     char occ = D.pool_occ[addr];
-    my_touched++;
+    if (!counted_by_hits) my_touched++;
+    bool became_o = false, became_f = false;
 
     // hits in the reference's unordered_map iteration order: descending (bucket activation, insert stamp).
     // Up to 4 hits per cell are ordered in registers; longer lists use selection by repeated traversal.
@@ -1121,6 +1184,7 @@ __global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D, Fram
         if (lo > P.lo_sh && occ != 'o') {
           occ = 'o';
           my_obs++;
+          became_o = true;
         }
       };
       if (cnt <= 4) {
@@ -1162,11 +1226,15 @@ __global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D, Fram
       if (lo < P.lo_sh && occ != 'f') {
         occ = 'f';
         changed = true;
+        became_f = true;
       }
       if (!changed) break;  // fixed point: the remaining identical steps are no-ops
     }
     D.pool_lo[addr] = lo;
     D.pool_occ[addr] = occ;
+    // frontier.erase(subbox_id) on either transition (src/map_local.cpp:167-168,200-201)
+    if (P.explore && (became_o || became_f))
+      atomicAnd(&D.pool_front[(size_t)block * P.front_words + (sub >> 5)], ~(1u << (sub & 31)));
   }
   // counters
   for (int ofs = 16; ofs > 0; ofs >>= 1) {
@@ -1177,6 +1245,7 @@ __global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D, Fram
     if (my_touched) atomicAdd(&fc->n_touched_voxels, my_touched);
     if (my_obs) atomicAdd(&fc->obs_delta, my_obs);
   }
+  if (kPhase == 1) return;  // the miss phase finishes the frame
   if (blockIdx.x == 0 && threadIdx.x == 0) fc->fused = 1;
   // the last block to get here publishes the frame counters to the host (no memcpy node in the graph)
   {
@@ -1204,6 +1273,15 @@ __global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D, Fram
       if (c_bucket_chain[c] == B) B = c_bucket_chain[c + 1];
     uint32_t *act_next = D.act[F.parity ^ 1];
     for (uint32_t i = gtid; i < B; i += nth) act_next[i] = 0xffffffffu;
+    if (P.explore) {
+      uint32_t Bm = F.bucket_count_miss;
+      const uint32_t n_miss = (uint32_t)fc->n_miss_list;
+      if (n_miss > 0 && Bm == 1) Bm = 13;
+      for (int c = 0; c + 1 < kBucketChainLen && n_miss > Bm; c++)
+        if (c_bucket_chain[c] == Bm) Bm = c_bucket_chain[c + 1];
+      uint32_t *am = D.act_miss[F.parity ^ 1];
+      for (uint32_t i = gtid; i < Bm; i += nth) am[i] = 0xffffffffu;
+    }
     for (int i = gtid; i < P.nPhi; i += nth) {
       D.phi_hist[i] = 0;
       D.phi_bound[i] = 0;

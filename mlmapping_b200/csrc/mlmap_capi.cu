@@ -17,6 +17,7 @@
 #include "../../include/mlmap_b200.h"
 #include "frame_kernels.cuh"
 #include "order_kernels.cuh"
+#include "explore_kernels.cuh"
 #include "query_kernels.cuh"
 
 using namespace mlm;
@@ -181,6 +182,8 @@ struct mlm_map {
   int *d_seq_a = nullptr, *d_seq_b = nullptr;
   int sort_cap = 0;
   uint32_t act_cap = 0;
+  uint32_t act_miss_cap = 0;
+  uint32_t bucket_count_miss = 1;  // emulated miss_idx_set.bucket_count() (exploration mode)
   uint32_t bucket_count = 1;  // emulated hit_idx_odds_hashmap.bucket_count()
   uint32_t last_order_B = 1;  // bucket count the last frame's stamps refer to
   int last_n_hit = 0;
@@ -322,40 +325,111 @@ void device_sort(mlm_map *h, uint64_t *keys, int n_pad) {
 // Slow ordering path: the frame's distinct hit keys exceed the emulated bucket count, so
 // libstdc++ would rehash mid-frame (possibly several times).  Produces virtual positions in
 // hit_t and bucket activations for the final bucket count.  Returns the final bucket count.
-int order_slow_path(mlm_map *h, int n, uint32_t *B_final_out) {
+// kind 0: the hit map (hit_key / hit_t / hit_bucket, act[parity]); kind 1: the miss set of exploration mode
+int order_slow_path(mlm_map *h, int n, int kind, uint32_t B_start, uint32_t *B_final_out) {
   cudaStream_t s = h->stream;
-  uint32_t *act = h->D.act[h->last_parity];
+  uint32_t *act = kind == 0 ? h->D.act[h->last_parity] : h->D.act_miss[h->last_parity];
+  const uint32_t act_cap = kind == 0 ? h->act_cap : h->act_miss_cap;
+  OrderArrays O;
+  O.key = kind == 0 ? h->D.hit_key : h->D.miss_idx;
+  O.stamp = kind == 0 ? h->D.hit_t : h->D.miss_t;
+  O.bucket = kind == 0 ? h->D.hit_bucket : h->D.miss_bucket;
+  O.kind = kind;
   const int T = 256;
   int n_pad = next_pow2(n);
-  k_order_seed<<<grid_for(n_pad, T), T, 0, s>>>(h->D, h->d_sort_a, n, n_pad);
+  k_order_seed<<<grid_for(n_pad, T), T, 0, s>>>(O, h->d_sort_a, n, n_pad);
   device_sort(h, h->d_sort_a, n_pad);
   k_order_take_seq<<<grid_for(n, T), T, 0, s>>>(h->d_sort_a, h->d_seq_a, n);
   h->launches += 2;
-  uint32_t B = h->bucket_count;
+  uint32_t B = B_start;
   while ((uint32_t)n > B) {
     int m = (int)std::min<uint32_t>(B, (uint32_t)n);
     if (m > 1) {
       int m_pad = next_pow2(m);
       k_fill_u32<<<grid_for(B, T), T, 0, s>>>(act, 0xffffffffu, (int)B);
-      k_stage_act<<<grid_for(m, T), T, 0, s>>>(h->P, h->D, act, h->d_seq_a, m, B);
-      k_stage_keys<<<grid_for(m_pad, T), T, 0, s>>>(h->P, h->D, act, h->d_seq_a, h->d_sort_b, m, m_pad, B);
+      k_stage_act<<<grid_for(m, T), T, 0, s>>>(h->P, O, act, h->d_seq_a, m, B);
+      k_stage_keys<<<grid_for(m_pad, T), T, 0, s>>>(h->P, O, act, h->d_seq_a, h->d_sort_b, m, m_pad, B);
       device_sort(h, h->d_sort_b, m_pad);
       k_stage_apply<<<grid_for(m, T), T, 0, s>>>(h->d_sort_b, h->d_seq_a, h->d_seq_b, m);
       k_copy_i32<<<grid_for(m, T), T, 0, s>>>(h->d_seq_a, h->d_seq_b, m);
       h->launches += 5;
     }
     uint32_t nb = chain_next(B);
-    if (nb == 0 || nb > h->act_cap) {
-      g_last_error = "hit map bucket chain exceeded";
+    if (nb == 0 || nb > act_cap) {
+      g_last_error = "bucket chain of the emulated container exceeded";
       return MLM_ERR_CAPACITY;
     }
     B = nb;
   }
   k_fill_u32<<<grid_for(B, T), T, 0, s>>>(act, 0xffffffffu, (int)B);
-  k_order_final<<<grid_for(n, T), T, 0, s>>>(h->P, h->D, act, h->d_seq_a, n, B);
+  k_order_final<<<grid_for(n, T), T, 0, s>>>(h->P, O, act, h->d_seq_a, n, B);
   h->launches += 2;
   *B_final_out = B;
   return MLM_OK;
+}
+
+int finish_frame(mlm_map *h, int slow, uint32_t order_B, mlm_frame_stats *stats);
+
+// Exploration mode (use_exploration_frontiers): the frame needs the neighbours' state between the hit and
+// the miss pass, and the miss-set iteration order, so it runs as direct launches with one host check of the
+// container sizes in the middle (rehash detection for both emulated containers).
+int run_frame_explore(mlm_map *h, int mode, int N, mlm_frame_stats *stats) {
+  const MapParams &P = h->P;
+  cudaStream_t s = h->stream;
+  FrameParams &F = *h->h_fp;
+  const int parity = F.parity;
+  const int proj_grid = grid_for((size_t)std::max(N, 1), 256);
+  F.order_mode = 1;  // rehash detection happens on the host below, not inside k_fuse
+  if (mode == 1)
+    k_project<1><<<proj_grid, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(P, h->D, F);
+  else if (mode == 2)
+    k_project<2><<<proj_grid, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(P, h->D, F);
+  else
+    k_project<0><<<proj_grid, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(P, h->D, F);
+  k_column<<<P.nPhi, kColThreads, h->col_smem_bytes, s>>>(P, h->D, F);
+  FrameCounters mid;
+  CUDA_TRY(cudaMemcpyAsync(&mid, h->D.fc[parity], sizeof(mid), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 2;
+  int slow = 0;
+  uint32_t order_B = h->bucket_count;
+  if (mid.error == 0) {
+    if (mid.n_hit > h->sort_cap || mid.n_miss_list > h->sort_cap) return MLM_ERR_CAPACITY;
+    if ((uint32_t)mid.n_hit > h->bucket_count) {
+      slow = 1;
+      int rc = order_slow_path(h, mid.n_hit, 0, h->bucket_count, &order_B);
+      if (rc != MLM_OK) return rc;
+      F.bucket_count = order_B;
+    }
+    if ((uint32_t)mid.n_miss_list > h->bucket_count_miss) {
+      slow = 1;
+      uint32_t Bm = 0;
+      int rc = order_slow_path(h, mid.n_miss_list, 1, h->bucket_count_miss, &Bm);
+      if (rc != MLM_OK) return rc;
+      F.bucket_count_miss = Bm;
+    }
+  }
+  const int g4 = h->sm_count * 4;
+  k_fuse<1><<<g4, 256, 0, s>>>(P, h->D, F);
+  k_miss_tkey<<<g4, 256, 0, s>>>(P, h->D, F);
+  k_explore_a<<<g4, 256, 0, s>>>(P, h->D, F);
+  k_explore_b<<<g4, 256, 0, s>>>(P, h->D, F);
+  k_fuse<2><<<g4, 256, 0, s>>>(P, h->D, F);
+  k_release<<<h->sm_count, 256, 0, s>>>(P, h->D, F);
+  h->launches += 6;
+  CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc[parity], sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  // bucket-count evolution of miss_idx_set (clear() keeps the buckets)
+  const int n_miss = h->h_fc->n_miss_list;
+  if (n_miss > 0 && h->bucket_count_miss == 1) h->bucket_count_miss = 13;
+  while ((uint32_t)n_miss > h->bucket_count_miss) {
+    uint32_t nb = chain_next(h->bucket_count_miss);
+    if (nb == 0) break;
+    h->bucket_count_miss = nb;
+  }
+  return finish_frame(h, slow, order_B, stats);
 }
 
 // mode: 0 = points, 1 = full depth image, 2 = sampled depth pixels (d_in = uint2 {pixel, raw} x n_points)
@@ -393,6 +467,7 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
   F.n_points = n_points;
   F.n_total = N;
   F.bucket_count = h->bucket_count;
+  F.bucket_count_miss = h->bucket_count_miss;
   const int parity = (int)(h->frame_idx & 1);
   h->frame_idx++;
   h->last_parity = parity;
@@ -407,6 +482,7 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
   F.lvg_base[2] = (int)floor((Twa.t[2] + P.z_border_min) / P.d_sub) - P.lvg_margin;
   for (int i = 0; i < 3; i++) F.lsg_base[i] = host_floor_div(F.lvg_base[i], P.n) - 1;
 
+  if (P.explore) return run_frame_explore(h, mode, N, stats);
   const bool prof = h->profiling != 0;
   const int full_grid = grid_for((size_t)P.max_points, 256);
   const int proj_grid = grid_for((size_t)std::max(N, 1), 256);
@@ -426,7 +502,7 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
     MLM_MARK(1);
     k_column<<<P.nPhi, kColThreads, h->col_smem_bytes, s>>>(Pk, Dk, Fk);
     MLM_MARK(2);
-    k_fuse<<<h->sm_count * 4, 256, 0, s>>>(Pk, Dk, Fk);
+    k_fuse<0><<<h->sm_count * 4, 256, 0, s>>>(Pk, Dk, Fk);
     MLM_MARK(3);
 #undef MLM_MARK
   } else {
@@ -441,7 +517,7 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
     np[1].gridDim = dim3(P.nPhi);
     np[1].blockDim = dim3(kColThreads);
     np[1].sharedMemBytes = (unsigned)h->col_smem_bytes;
-    np[2].func = (void *)k_fuse;
+    np[2].func = (void *)k_fuse<0>;
     np[2].gridDim = dim3(h->sm_count * 4);
     np[2].blockDim = dim3(256);
     np[2].sharedMemBytes = 0;
@@ -473,16 +549,20 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
       return MLM_ERR_CAPACITY;
     }
     uint32_t Bf = 0;
-    int rc = order_slow_path(h, n, &Bf);
+    int rc = order_slow_path(h, n, 0, h->bucket_count, &Bf);
     if (rc != MLM_OK) return rc;
     order_B = Bf;
     F.bucket_count = Bf;
     F.order_mode = 1;
-    k_fuse<<<h->sm_count * 4, 256, 0, s>>>(P, h->D, F);
+    k_fuse<0><<<h->sm_count * 4, 256, 0, s>>>(P, h->D, F);
     h->launches += 1;
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaGetLastError());
   }
+  return finish_frame(h, slow, order_B, stats);
+}
+
+int finish_frame(mlm_map *h, int slow, uint32_t order_B, mlm_frame_stats *stats) {
   const FrameCounters &C = *h->h_fc;
   if (C.fused) {
     h->cum_ram_expand += C.n_new_blocks;
@@ -617,10 +697,6 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
     g_last_error = why;
     return rc;
   }
-  if (cfg->use_exploration_frontiers) {
-    g_last_error = "use_exploration_frontiers=true (update_observation / release pass) is not implemented on the GPU path";
-    return MLM_ERR_UNSUPPORTED;
-  }
   if (cfg->sample_cnt < 0 || cfg->sample_cnt > cfg->max_points) {
     g_last_error = "sample_cnt must be in [0, max_points]";
     return MLM_ERR_INVALID_CONFIG;
@@ -688,6 +764,12 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   P.lo_max = cfg->log_odds_max;
   P.lo_miss = cfg->log_odds_miss;
   P.lo_sh = cfg->log_odds_occupied_sh;
+  P.explore = cfg->use_exploration_frontiers != 0;
+  P.front_words = (P.cells + 31) / 32;
+  {
+    const double bd[6] = {-30, 30, -30, 30, 0, 5};  // global_bd, hard-coded at src/map_local.cpp:124
+    for (int i = 0; i < 6; i++) P.bd[i] = bd[i];
+  }
   P.cx = cfg->cam_cx;
   P.cy = cfg->cam_cy;
   P.fx = cfg->cam_fx;
@@ -820,15 +902,49 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   TRY(dev_alloc(h, &D.pool_lo, (size_t)P.pool_blocks * P.cell_stride));
   TRY(dev_alloc(h, &D.pool_occ, (size_t)P.pool_blocks * P.cell_stride));
   TRY(dev_alloc(h, &D.pool_inf, (size_t)P.pool_blocks * P.cell_stride));
+  if (P.explore) {
+    if ((long long)P.max_points * P.nRho >= (1ll << 31)) {
+      g_last_error = "exploration mode needs max_points * n_Rho < 2^31 (miss-cell insert stamps)";
+      mlm_destroy(h);
+      return MLM_ERR_INVALID_CONFIG;
+    }
+    TRY(dev_alloc(h, &D.pool_front, (size_t)P.pool_blocks * P.front_words));
+    TRY(dev_alloc(h, &D.col_occ, (size_t)ht_cap));
+    TRY(dev_alloc(h, &D.col_inf, (size_t)ht_cap));
+    TRY(dev_alloc(h, &D.col_lo, (size_t)ht_cap));
+    TRY(dev_alloc(h, &D.end_t, (size_t)n_cells));
+    TRY(dev_alloc(h, &D.miss_stamp, (size_t)n_cells));
+    h->act_miss_cap = chain_cover((uint32_t)n_cells);
+    if (h->act_miss_cap == 0) {
+      g_last_error = "awareness cell count exceeds the bucket chain table";
+      mlm_destroy(h);
+      return MLM_ERR_INVALID_CONFIG;
+    }
+    TRY(dev_alloc(h, &D.act_miss[0], (size_t)h->act_miss_cap));
+    TRY(dev_alloc(h, &D.act_miss[1], (size_t)h->act_miss_cap));
+    TRY(dev_alloc(h, &D.miss_idx, (size_t)n_cells));
+    TRY(dev_alloc(h, &D.miss_lv, (size_t)n_cells));
+    TRY(dev_alloc(h, &D.miss_t, (size_t)n_cells));
+    TRY(dev_alloc(h, &D.miss_bucket, (size_t)n_cells));
+    TRY(dev_alloc(h, &D.miss_choice, (size_t)n_cells));
+    TRY(dev_alloc(h, &D.lvg_tkey, (size_t)lvg_cells));
+    TRY(dev_alloc(h, &D.obs_flag, (size_t)lsg_cells));
+    TRY(dev_alloc(h, &D.obs_list, (size_t)lsg_cells));
+    CUDA_TRY_H(cudaMemset(D.pool_front, 0, (size_t)P.pool_blocks * P.front_words * 4));
+    CUDA_TRY_H(cudaMemset(D.act_miss[0], 0xff, (size_t)h->act_miss_cap * 4));
+    CUDA_TRY_H(cudaMemset(D.act_miss[1], 0xff, (size_t)h->act_miss_cap * 4));
+    CUDA_TRY_H(cudaMemset(D.lvg_tkey, 0, (size_t)lvg_cells * 8));
+    CUDA_TRY_H(cudaMemset(D.obs_flag, 0, (size_t)lsg_cells * 4));
+  }
   TRY(dev_alloc(h, &D.cum, 4));
   TRY(dev_alloc(h, &D.debug_cycles, (size_t)P.nPhi * 16));
   CUDA_TRY_H(cudaMemset(D.debug_cycles, 0, (size_t)P.nPhi * 16 * sizeof(long long)));
-  h->sort_cap = P.max_hits;
-  const size_t sort_pad = (size_t)next_pow2(P.max_hits);
+  h->sort_cap = P.explore ? (int)n_cells : P.max_hits;
+  const size_t sort_pad = (size_t)next_pow2(h->sort_cap);
   TRY(dev_alloc(h, &h->d_sort_a, sort_pad));
   TRY(dev_alloc(h, &h->d_sort_b, sort_pad));
-  TRY(dev_alloc(h, &h->d_seq_a, (size_t)P.max_hits));
-  TRY(dev_alloc(h, &h->d_seq_b, (size_t)P.max_hits));
+  TRY(dev_alloc(h, &h->d_seq_a, (size_t)h->sort_cap));
+  TRY(dev_alloc(h, &h->d_seq_b, (size_t)h->sort_cap));
 
   // initial state
   {
@@ -1197,7 +1313,14 @@ int mlm_last_frame_hits(mlm_handle h, int32_t *keys3, float *p, size_t cap, size
   if (n == 0 || cap < (size_t)n || !keys3 || !p) return MLM_OK;
   cudaStream_t s = h->stream;
   const int T = 256, n_pad = next_pow2(n);
-  k_order_seed<<<grid_for(n_pad, T), T, 0, s>>>(h->D, h->d_sort_a, n, n_pad);
+  {
+    OrderArrays O;
+    O.key = h->D.hit_key;
+    O.stamp = h->D.hit_t;
+    O.bucket = h->D.hit_bucket;
+    O.kind = 0;
+    k_order_seed<<<grid_for(n_pad, T), T, 0, s>>>(O, h->d_sort_a, n, n_pad);
+  }
   device_sort(h, h->d_sort_a, n_pad);
   k_export_hit_keys<<<grid_for(n_pad, T), T, 0, s>>>(h->P, h->D, h->D.act[h->last_parity], h->d_sort_b, n, n_pad,
                                                       h->last_order_B);
@@ -1252,9 +1375,10 @@ int mlm_export_map_count(mlm_handle h, size_t *n_submaps) {
   return MLM_OK;
 }
 
-int mlm_export_map(mlm_handle h, size_t cap_submaps, int32_t *glb3, uint8_t *collapsed, char *occupancy,
-                   char *inflate_occupancy, float *log_odds, size_t *n_out) {
-  if (!h || !n_out || !glb3 || !collapsed || !occupancy || !inflate_occupancy || !log_odds) return MLM_ERR_INVALID_ARG;
+namespace {
+// shared by mlm_export_map / mlm_export_frontier: front == nullptr skips the frontier bitmasks
+int export_common(mlm_handle h, size_t cap_submaps, int32_t *glb3, uint8_t *collapsed, char *occupancy,
+                  char *inflate_occupancy, float *log_odds, uint32_t *front, size_t *n_out) {
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
   const MapParams &P = h->P;
@@ -1272,20 +1396,27 @@ int mlm_export_map(mlm_handle h, size_t cap_submaps, int32_t *glb3, uint8_t *col
   if (cnt > 0 && (size_t)cnt <= cap_submaps) {
     char *d_occ = nullptr, *d_inf = nullptr;
     float *d_lo = nullptr;
+    unsigned char *d_col = nullptr;
+    uint32_t *d_front = nullptr;
     const size_t cells = (size_t)cnt * P.cells;
     CUDA_TRY(cudaMallocAsync((void **)&d_occ, cells, s));
     CUDA_TRY(cudaMallocAsync((void **)&d_inf, cells, s));
     CUDA_TRY(cudaMallocAsync((void **)&d_lo, cells * 4, s));
-    k_export_blocks<<<cnt, 256, 0, s>>>(P, h->D, d_blk, cnt, d_occ, d_inf, d_lo);
+    CUDA_TRY(cudaMallocAsync((void **)&d_col, (size_t)cnt, s));
+    if (front) CUDA_TRY(cudaMallocAsync((void **)&d_front, (size_t)cnt * P.front_words * 4, s));
+    k_export_blocks<<<cnt, 256, 0, s>>>(P, h->D, d_blk, cnt, d_occ, d_inf, d_lo, d_col, d_front);
     CUDA_TRY(cudaMemcpyAsync(glb3, d_glb, (size_t)cnt * 12, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(occupancy, d_occ, cells, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(inflate_occupancy, d_inf, cells, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(log_odds, d_lo, cells * 4, cudaMemcpyDeviceToHost, s));
+    if (collapsed) CUDA_TRY(cudaMemcpyAsync(collapsed, d_col, (size_t)cnt, cudaMemcpyDeviceToHost, s));
+    if (occupancy) CUDA_TRY(cudaMemcpyAsync(occupancy, d_occ, cells, cudaMemcpyDeviceToHost, s));
+    if (inflate_occupancy) CUDA_TRY(cudaMemcpyAsync(inflate_occupancy, d_inf, cells, cudaMemcpyDeviceToHost, s));
+    if (log_odds) CUDA_TRY(cudaMemcpyAsync(log_odds, d_lo, cells * 4, cudaMemcpyDeviceToHost, s));
+    if (front) CUDA_TRY(cudaMemcpyAsync(front, d_front, (size_t)cnt * P.front_words * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaFreeAsync(d_occ, s));
     CUDA_TRY(cudaFreeAsync(d_inf, s));
     CUDA_TRY(cudaFreeAsync(d_lo, s));
+    CUDA_TRY(cudaFreeAsync(d_col, s));
+    if (d_front) CUDA_TRY(cudaFreeAsync(d_front, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    memset(collapsed, 0, (size_t)cnt);
     h->launches += 2;
   }
   CUDA_TRY(cudaFreeAsync(d_cnt, s));
@@ -1294,6 +1425,18 @@ int mlm_export_map(mlm_handle h, size_t cap_submaps, int32_t *glb3, uint8_t *col
   CUDA_TRY(cudaStreamSynchronize(s));
   CUDA_TRY(cudaGetLastError());
   return MLM_OK;
+}
+}  // namespace
+
+int mlm_export_map(mlm_handle h, size_t cap_submaps, int32_t *glb3, uint8_t *collapsed, char *occupancy,
+                   char *inflate_occupancy, float *log_odds, size_t *n_out) {
+  if (!h || !n_out || !glb3 || !collapsed || !occupancy || !inflate_occupancy || !log_odds) return MLM_ERR_INVALID_ARG;
+  return export_common(h, cap_submaps, glb3, collapsed, occupancy, inflate_occupancy, log_odds, nullptr, n_out);
+}
+
+int mlm_export_frontier(mlm_handle h, size_t cap_submaps, int32_t *glb3, uint32_t *frontier_words, size_t *n_out) {
+  if (!h || !n_out || !glb3 || !frontier_words) return MLM_ERR_INVALID_ARG;
+  return export_common(h, cap_submaps, glb3, nullptr, nullptr, nullptr, nullptr, frontier_words, n_out);
 }
 
 int mlm_debug_log10f(mlm_handle h, const float *x, size_t n, float *out) {

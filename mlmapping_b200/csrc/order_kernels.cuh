@@ -58,17 +58,27 @@ __global__ void __launch_bounds__(kSortThreads) k_bitonic_local(uint64_t *keys, 
 }
 
 // ---- stage kernels ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t hit_bucket(const MapParams &P, int key, uint32_t B) {
+// bucket of an awareness cell index in the emulated container:
+//   kind 0: hit_idx_odds_hashmap, key Vec3I(rho,phi,z), VectorHasher (include/map_awareness.h:31-41,56)
+//   kind 1: miss_idx_set, key size_t mapIdx, std::hash<size_t> = identity (include/map_awareness.h:57)
+__device__ __forceinline__ uint32_t cell_bucket(const MapParams &P, int key, uint32_t B, int kind) {
+  if (kind == 1) return (uint32_t)((uint64_t)(uint32_t)key % (uint64_t)B);
   int zk = key / (P.nRho * P.nPhi), rem = key - zk * (P.nRho * P.nPhi);
   int pk = rem / P.nRho, rk = rem - pk * P.nRho;
   return libstdcxx_bucket(vector_hash3(rk, pk, zk), B);
 }
+struct OrderArrays {
+  const int *key;      // awareness cell index of every element
+  uint32_t *stamp;     // in: first-insert stamps; out (slow path): virtual positions
+  uint32_t *bucket;    // out: bucket at the final bucket count
+  int kind;
+};
 
 // keys[i] = (first-insert stamp, hit index): ascending sort = real insertion sequence
-__global__ void k_order_seed(DeviceBuffers D, uint64_t *keys, int n, int n_pad) {
+__global__ void k_order_seed(OrderArrays O, uint64_t *keys, int n, int n_pad) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n)
-    keys[i] = ((uint64_t)D.hit_t[i] << 32) | (uint32_t)i;
+    keys[i] = ((uint64_t)O.stamp[i] << 32) | (uint32_t)i;
   else if (i < n_pad)
     keys[i] = ~0ull;
 }
@@ -81,16 +91,16 @@ __global__ void k_fill_u32(uint32_t *p, uint32_t v, int n) {
   if (i < n) p[i] = v;
 }
 // act[bucket] = earliest virtual position among the first m keys of the sequence
-__global__ void k_stage_act(MapParams P, DeviceBuffers D, uint32_t *act, const int *seq, int m, uint32_t B) {
+__global__ void k_stage_act(MapParams P, OrderArrays O, uint32_t *act, const int *seq, int m, uint32_t B) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < m) atomicMin(&act[hit_bucket(P, D.hit_key[seq[j]], B)], (uint32_t)j);
+  if (j < m) atomicMin(&act[cell_bucket(P, O.key[seq[j]], B, O.kind)], (uint32_t)j);
 }
 // sort key: descending (act, position)  ==  ascending 63-bit complement; padding sorts last
-__global__ void k_stage_keys(MapParams P, DeviceBuffers D, const uint32_t *act, const int *seq, uint64_t *keys, int m,
+__global__ void k_stage_keys(MapParams P, OrderArrays O, const uint32_t *act, const int *seq, uint64_t *keys, int m,
                              int m_pad, uint32_t B) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < m) {
-    uint64_t comp = ((uint64_t)act[hit_bucket(P, D.hit_key[seq[j]], B)] << 32) | (uint32_t)j;
+    uint64_t comp = ((uint64_t)act[cell_bucket(P, O.key[seq[j]], B, O.kind)] << 32) | (uint32_t)j;
     keys[j] = (~comp) & 0x7fffffffffffffffull;
   } else if (j < m_pad) {
     keys[j] = ~0ull;
@@ -108,13 +118,13 @@ __global__ void k_copy_i32(int *dst, const int *src, int n) {
   if (i < n) dst[i] = src[i];
 }
 // final: stamps become virtual positions; bucket activation over the whole sequence
-__global__ void k_order_final(MapParams P, DeviceBuffers D, uint32_t *act, const int *seq, int n, uint32_t B) {
+__global__ void k_order_final(MapParams P, OrderArrays O, uint32_t *act, const int *seq, int n, uint32_t B) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n) {
     int h = seq[j];
-    D.hit_t[h] = (uint32_t)j;
-    const uint32_t b = hit_bucket(P, D.hit_key[h], B);
-    D.hit_bucket[h] = b;
+    O.stamp[h] = (uint32_t)j;
+    const uint32_t b = cell_bucket(P, O.key[h], B, O.kind);
+    O.bucket[h] = b;
     atomicMin(&act[b], (uint32_t)j);
   }
 }
@@ -127,7 +137,7 @@ __global__ void k_export_hit_keys(MapParams P, DeviceBuffers D, const uint32_t *
                                   uint32_t B) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    uint64_t comp = ((uint64_t)act[hit_bucket(P, D.hit_key[i], B)] << 32) | D.hit_t[i];
+    uint64_t comp = ((uint64_t)act[cell_bucket(P, D.hit_key[i], B, 0)] << 32) | D.hit_t[i];
     keys_o[i] = (~comp) & 0x7fffffffffffffffull;
   } else if (i < n_pad) {
     keys_o[i] = ~0ull;

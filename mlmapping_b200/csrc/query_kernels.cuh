@@ -15,7 +15,9 @@ __device__ __forceinline__ float logit_inv_f(float lo) {
 
 // getOdd(glb, sub), include/mlmap.h:227-235
 __device__ __forceinline__ float odd_at(const MapParams &P, const DeviceBuffers &D, const int g[3], int sub) {
-  int block = ht_find(P, D, g);
+  uint32_t slot;
+  int block = ht_find_slot(P, D, g, slot);
+  if (block == kBlockCollapsed) return logit_inv_f(D.col_lo[slot]);  // log_odds.size() == 1 -> element 0
   if (block < 0) return 0.5f;
   return logit_inv_f(D.pool_lo[(size_t)block * P.cell_stride + sub]);
 }
@@ -23,9 +25,12 @@ __device__ __forceinline__ float odd_at(const MapParams &P, const DeviceBuffers 
 __device__ __forceinline__ int occupancy_at(const MapParams &P, const DeviceBuffers &D, double x, double y,
                                             double z) {  // include/mlmap.h:170-193
   CellRef c = locate_cell(P, x, y, z);
-  int block = ht_find(P, D, c.g);
-  if (block < 0) return -1;
-  char res = D.pool_occ[(size_t)block * P.cell_stride + c.sub];
+  uint32_t slot;
+  int block = ht_find_slot(P, D, c.g, slot);
+  char res;
+  if (block == kBlockCollapsed) res = D.col_occ[slot];  // occupancy.size() == 1 -> element 0
+  else if (block < 0) return -1;
+  else res = D.pool_occ[(size_t)block * P.cell_stride + c.sub];
   return res == 'o' ? 0 : (res == 'f' ? 1 : -1);
 }
 
@@ -93,10 +98,17 @@ __device__ __forceinline__ void neighbor_step(const MapParams &P, int dir, int g
 }
 
 // log-odds the reference's getOdd(glb, sub) would convert: absent subbox -> odds 0.5 == logit_inv(0.f)
-__device__ __forceinline__ float lo_at(const MapParams &P, const DeviceBuffers &D, const int g[3], int sub) {
-  int block = ht_find(P, D, g);
-  if (block < 0) return 0.0f;
-  return D.pool_lo[(size_t)block * P.cell_stride + sub];
+// block id for the gradient walk: >= 0 pool block, -1 absent, <= -16 collapsed subbox stored at slot -(id+16)
+__device__ __forceinline__ int grad_block(const MapParams &P, const DeviceBuffers &D, const int g[3]) {
+  uint32_t slot;
+  int block = ht_find_slot(P, D, g, slot);
+  if (block == kBlockCollapsed) return -16 - (int)slot;
+  return block < 0 ? -1 : block;
+}
+__device__ __forceinline__ float grad_lo(const MapParams &P, const DeviceBuffers &D, int blk, int sub) {
+  if (blk >= 0) return D.pool_lo[(size_t)blk * P.cell_stride + sub];
+  if (blk <= -16) return D.col_lo[-(blk + 16)];
+  return 0.0f;
 }
 
 __global__ void __launch_bounds__(256) k_get_odd_grad(MapParams P, DeviceBuffers D, const double *pos, size_t n,
@@ -109,8 +121,8 @@ __global__ void __launch_bounds__(256) k_get_odd_grad(MapParams P, DeviceBuffers
   // whose log-odds is not below the running minimum can never satisfy `tmp_odd < min_odd`: the double
   // pow() is only evaluated for the candidates that can win.  The sequence of accepted minima, and
   // therefore the result, is exactly the reference's.
-  const int blk0 = ht_find(P, D, c.g);
-  float min_lo = blk0 < 0 ? 0.0f : D.pool_lo[(size_t)blk0 * P.cell_stride + c.sub];
+  const int blk0 = grad_block(P, D, c.g);
+  float min_lo = grad_lo(P, D, blk0, c.sub);
   float min_odd = logit_inv_f(min_lo);
   const float ori_odd = min_odd;
   // The six probes walk along +z,-z,+y,-y,+x,-x (subbox_neighbors row order, src/map_local.cpp:78-120):
@@ -145,9 +157,9 @@ __global__ void __launch_bounds__(256) k_get_odd_grad(MapParams P, DeviceBuffers
       }
       int g[3] = {c.g[0], c.g[1], c.g[2]};
       g[axis] = ga[d];
-      if (crossed) blk[d] = ht_find(P, D, g);
+      if (crossed) blk[d] = grad_block(P, D, g);
       const int sub = c.sub + (ca[d] - cxyz[axis]) * stride[axis];
-      const float lo = blk[d] < 0 ? 0.0f : D.pool_lo[(size_t)blk[d] * P.cell_stride + sub];
+      const float lo = grad_lo(P, D, blk[d], sub);
       if (!(lo < min_lo)) continue;
       const float tmp = logit_inv_f(lo);
       if (tmp < min_odd) {
@@ -307,7 +319,7 @@ __global__ void k_export_list(MapParams P, DeviceBuffers D, int *out_glb3, int *
   uint64_t k = D.ht_key[slot];
   if (k == kEmptyKey) return;
   int block = D.ht_val[slot];
-  if (block < 0) return;
+  if (block < 0 && block != kBlockCollapsed) return;
   int idx = atomicAdd(counter, 1);
   if (idx >= cap) return;
   int g[3];
@@ -315,18 +327,38 @@ __global__ void k_export_list(MapParams P, DeviceBuffers D, int *out_glb3, int *
   out_glb3[3 * idx] = g[0];
   out_glb3[3 * idx + 1] = g[1];
   out_glb3[3 * idx + 2] = g[2];
-  out_block[idx] = block;
+  out_block[idx] = block == kBlockCollapsed ? -16 - (int)slot : block;
 }
+// collapsed subboxes export element 0 and zeros elsewhere (blocks[b] <= -16 encodes the hash slot);
+// front (optional) receives the frontier bitmask, cells/8 bytes per subbox rounded to front_words*4
 __global__ void k_export_blocks(MapParams P, DeviceBuffers D, const int *blocks, int n, char *occ, char *inf,
-                                float *lo) {
+                                float *lo, unsigned char *collapsed, uint32_t *front) {
   int b = blockIdx.x;
   if (b >= n) return;
-  size_t src = (size_t)blocks[b] * P.cell_stride, dst = (size_t)b * P.cells;
+  const int blk = blocks[b];
+  const size_t dst = (size_t)b * P.cells;
+  if (blk <= -16) {
+    const int slot = -(blk + 16);
+    for (int i = threadIdx.x; i < P.cells; i += blockDim.x) {
+      occ[dst + i] = i == 0 ? D.col_occ[slot] : 0;
+      inf[dst + i] = i == 0 ? D.col_inf[slot] : 0;
+      lo[dst + i] = i == 0 ? D.col_lo[slot] : 0.f;
+    }
+    if (threadIdx.x == 0) collapsed[b] = 1;
+    if (front)
+      for (int w = threadIdx.x; w < P.front_words; w += blockDim.x) front[(size_t)b * P.front_words + w] = 0;
+    return;
+  }
+  const size_t src = (size_t)blk * P.cell_stride;
   for (int i = threadIdx.x; i < P.cells; i += blockDim.x) {
     occ[dst + i] = D.pool_occ[src + i];
     inf[dst + i] = D.pool_inf[src + i];
     lo[dst + i] = D.pool_lo[src + i];
   }
+  if (threadIdx.x == 0) collapsed[b] = 0;
+  if (front)
+    for (int w = threadIdx.x; w < P.front_words; w += blockDim.x)
+      front[(size_t)b * P.front_words + w] = P.explore ? D.pool_front[(size_t)blk * P.front_words + w] : 0u;
 }
 // miss set export: ascending awareness indices from the per-column bitmaps
 __global__ void k_export_miss(MapParams P, DeviceBuffers D, unsigned long long *out, int *counter, int cap) {

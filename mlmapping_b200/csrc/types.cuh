@@ -11,6 +11,8 @@ constexpr int kOddsRows = 2 * kDiffRange + 1;
 constexpr int kMaxPhi = 4096;           // upper bound on nPhi for the shared-memory histogram
 constexpr uint64_t kEmptyKey = ~0ull;   // empty slot of the submap hash table
 constexpr int kBlockPending = -1;
+constexpr int kBlockCollapsed = -2;     // ht_val of a subbox collapsed by the release pass (map_local.cpp:208-232)
+constexpr int kBlockUnusable = -3;      // pool exhausted when the subbox was created
 constexpr int kLvgEmpty = -1;
 constexpr int kLvgClaimed = -2;
 // device-raised error codes (mapped to MLM_ERR_* by the host)
@@ -46,6 +48,9 @@ struct MapParams {
   int cells;              // cell_num_subbox
   int cell_stride;        // cells rounded up to 16: per-block stride of the pool arrays
   float lo_min, lo_max, lo_miss, lo_sh;
+  int explore;            // apply_explored_area (use_exploration_frontiers)
+  int front_words;        // 32-bit words of a subbox's frontier bitmask: ceil(cells/32)
+  double bd[6];           // global_bd = {-30,30,-30,30,0,5} (src/map_local.cpp:124)
   // camera (include/mlmap.h:85-86,92)
   float cx, cy, fx, fy;
   double inv_factor;
@@ -83,6 +88,7 @@ struct FrameParams {
   int lvg_base[3];  // global cell coordinate of local voxel grid origin
   int lsg_base[3];  // global subbox coordinate of local submap grid origin
   int tbits;        // bits needed for a point stamp this frame (ceil(log2(#points)))
+  uint32_t bucket_count_miss;  // emulated miss_idx_set.bucket_count() at frame start (exploration mode)
   int parity;       // frame & 1: selects the double-buffered counters / activation stamps
   int order_mode;   // 0: stamps are (bucket activation, first-insert time); 1: virtual sequence positions
 };
@@ -97,7 +103,9 @@ struct FrameCounters {
   int overflow;           // 1: n_hit > bucket_count -> fuse skipped, slow ordering path needed
   int obs_delta;          // occupancy 'o' transitions this frame
   int fused;              // set by k_fuse when it ran to completion
-  int pad[3];  // sizeof must stay a multiple of 4 (cleared word-wise by k_fuse)
+  int n_miss_list;        // exploration mode: entries of the per-frame miss list
+  int n_obs;              // exploration mode: subboxes handed to the release pass (observed_subboxes)
+  int n_released;         // subboxes collapsed by the release pass this frame
 };
 
 struct DeviceBuffers {
@@ -135,6 +143,21 @@ struct DeviceBuffers {
   char *pool_occ;         // [pool_blocks*cells]
   char *pool_inf;         // [pool_blocks*cells]
   int64_t *cum;           // [0]=ram_expand_cnt [1]=obs_cnt [2]=n_submaps
+  // ---- exploration-frontier mode (use_exploration_frontiers), allocated only when enabled ----
+  uint32_t *pool_front;   // [pool_blocks*front_words] frontier set of every subbox as a bitmask
+  char *col_occ, *col_inf; // [ht cap] element 0 of a collapsed subbox, by hash slot
+  float *col_lo;          // [ht cap]
+  uint32_t *end_t;        // [nPhi*nZ*nRho] earliest point stamp per inside end cell
+  uint32_t *miss_stamp;   // [nPhi*nZ*nRho] first-insert stamp of every miss cell (t*nRho + step)
+  uint32_t *act_miss[2];  // [bucket capacity] bucket activation stamps of miss_idx_set
+  int *miss_idx;          // [cells] per-frame miss list: awareness cell index
+  int *miss_lv;           // [cells]   its local voxel
+  uint32_t *miss_t;       // [cells]   its first-insert stamp (or virtual position)
+  uint32_t *miss_bucket;  // [cells]   its libstdc++ bucket
+  signed char *miss_choice; // [cells] neighbour picked by update_observation (-1 none)
+  unsigned long long *lvg_tkey; // [lvg cells] (bucket activation, stamp) of the voxel's first miss cell in iteration order
+  int *obs_flag;          // [lsg cells]
+  int *obs_list;          // [lsg cells]
   long long *debug_cycles; // [nPhi*16] per-column phase clocks (MLM_PHASE_TIMING builds only)
 };
 

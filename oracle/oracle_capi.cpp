@@ -161,6 +161,22 @@ size_t orc_export_map(void *h, size_t cap, int32_t *glb3, uint8_t *collapsed, ch
   return i;
 }
 
+// frontier sets (exploration mode): per exported subbox (same order as orc_export_map) a bitmask of cells/8 bytes
+size_t orc_export_frontier(void *h, size_t cap, uint8_t *bits) {
+  auto *m = static_cast<orc::mlmap *>(h);
+  size_t cells = m->local->cell_num_subbox, nb = (cells + 7) / 8;
+  size_t i = 0;
+  for (auto &kv : m->local->observed_group_map) {
+    if (i < cap) {
+      memset(bits + i * nb, 0, nb);
+      for (int c : kv.second.frontier) bits[i * nb + (size_t)c / 8] |= (uint8_t)(1u << (c & 7));
+    }
+    i++;
+  }
+  return i;
+}
+int orc_released_last(void *h) { return static_cast<orc::mlmap *>(h)->local->n_released_last; }
+
 // table / scalar probes used by known-answer tests
 float orc_odds_table(void *h, int diff, int r) {
   auto *m = static_cast<orc::mlmap *>(h);

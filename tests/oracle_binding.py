@@ -59,6 +59,8 @@ def load_oracle():
     lib.orc_get_odd_grad.argtypes = [vp, vp, sz, sz, vp]
     lib.orc_export_map_count.argtypes, lib.orc_export_map_count.restype = [vp], sz
     lib.orc_export_map.argtypes, lib.orc_export_map.restype = [vp, sz, vp, vp, vp, vp, vp], sz
+    lib.orc_export_frontier.argtypes, lib.orc_export_frontier.restype = [vp, sz, vp], sz
+    lib.orc_released_last.argtypes, lib.orc_released_last.restype = [vp], C.c_int
     lib.orc_odds_table.argtypes, lib.orc_odds_table.restype = [vp, C.c_int, C.c_int], C.c_float
     lib.orc_three_sigma.argtypes, lib.orc_three_sigma.restype = [vp, C.c_int], C.c_float
     lib.orc_fast_atan2.argtypes, lib.orc_fast_atan2.restype = [vp, C.c_double, C.c_double], C.c_double
@@ -193,6 +195,10 @@ class Oracle:
         if n:
             self.lib.orc_export_map(self.h, n, glb.ctypes.data, col.ctypes.data, occ.ctypes.data, inf.ctypes.data,
                                     lo.ctypes.data)
+        nb = (self.cells + 7) // 8
+        fr = np.zeros((n, nb), dtype=np.uint8)
+        if n:
+            self.lib.orc_export_frontier(self.h, n, fr.ctypes.data)
         order = np.lexsort((glb[:, 2], glb[:, 1], glb[:, 0]))
         return {"glb": glb[order], "collapsed": col[order], "occupancy": occ[order], "inflate": inf[order],
-                "log_odds": lo[order]}
+                "log_odds": lo[order], "frontier": fr[order]}

@@ -33,6 +33,9 @@ def assert_map_parity(gpu, orc, lo_tol=1e-6, tag=""):
     assert np.array_equal(g["occupancy"], o["occupancy"]), (
         tag, "occupancy states differ", int((g["occupancy"] != o["occupancy"]).sum()))
     assert np.array_equal(g["inflate"], o["inflate"]), (tag, "inflate states differ")
+    if "frontier" in g:
+        assert np.array_equal(g["frontier"], o["frontier"]), (
+            tag, "frontier sets differ", int((np.unpackbits(g["frontier"]) != np.unpackbits(o["frontier"])).sum()))
     d = np.abs(g["log_odds"].astype(np.float64) - o["log_odds"].astype(np.float64))
     assert d.max(initial=0.0) <= lo_tol, (tag, "log-odds differ", float(d.max()))
     exact = np.array_equal(g["log_odds"].view(np.uint32), o["log_odds"].view(np.uint32))

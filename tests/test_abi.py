@@ -61,9 +61,6 @@ def test_invalid_config_and_no_silent_cpu_fallback(lib):
     bad.max_points = 0
     assert lib.mlm_create(C.byref(bad), 0, C.byref(h)) == 2
     assert lib.mlm_create(None, 0, C.byref(h)) == 1           # MLM_ERR_INVALID_ARG
-    bad = cfg.copy()
-    bad.use_exploration_frontiers = 1
-    assert lib.mlm_create(C.byref(bad), 0, C.byref(h)) == 6   # MLM_ERR_UNSUPPORTED, never a CPU path
     if not torch.cuda.is_available():
         rc = lib.mlm_create(C.byref(cfg), 0, C.byref(h))
         assert rc == 7 and b"no CPU fallback" in lib.mlm_last_error()

@@ -255,3 +255,32 @@ def test_sampled_project_depth_matches_glibc_rand_stream():
         assert st_g.n_points == st_o.n_points and (st_g.n_points == 500 or k == 5)
         assert_frame_parity(gpu, orc, st_g, st_o, tag=f"sampled{k}")
     assert_map_parity(gpu, orc, LO_TOL)
+
+
+def test_exploration_frontiers_and_memory_release():
+    """use_exploration_frontiers = true (config2.yaml:36): update_observation in miss-set iteration order,
+    frontier sets, neighbour subbox allocation, release pass (collapse to element 0), queries on collapsed
+    subboxes — SURVEY §8a a14-a15"""
+    cfg = config_cfg_a()
+    cfg.use_exploration_frontiers = 1
+    gpu, orc = MLMap(cfg), Oracle(cfg)
+    for k in range(14):
+        pose = scenes.corridor_trajectory_pose(k * 10)
+        img = scenes.corridor_depth_frame(cfg, pose, frame_idx=k)
+        st_g, st_o = gpu.integrate_depth(img, pose), orc.integrate_depth(img, pose)
+        assert_frame_parity(gpu, orc, st_g, st_o, tag=f"explore{k}")
+        info = assert_map_parity(gpu, orc, LO_TOL, tag=f"explore{k}")
+    m = orc.export_map()
+    assert m["collapsed"].sum() >= 10 and np.unpackbits(m["frontier"]).sum() > 300
+    lo = m["glb"].min(0) * 1.0
+    hi = (m["glb"].max(0) + 1) * 1.0
+    pos = scenes.query_positions(200000, lo, hi, seed=9, inflate=1.0)
+    assert np.array_equal(gpu.getOccupancy(pos), orc.getOccupancy(pos))
+    assert np.abs(gpu.getOdd(pos).astype(np.float64) - orc.getOdd(pos)).max() <= 1.2e-7
+    assert np.abs(gpu.getOddGrad(pos[:50000]) - orc.getOddGrad(pos[:50000])).max() <= 1e-6
+    # box fill and inflation must skip collapsed subboxes like the reference
+    gpu.setFree_map_in_bound([5.0, -1.0, 0.2], [9.0, 1.0, 2.2])
+    orc.setFree_map_in_bound([5.0, -1.0, 0.2], [9.0, 1.0, 2.2])
+    gpu.inflate_map(pose[:3])
+    orc.inflate_map(pose[:3])
+    assert_map_parity(gpu, orc, LO_TOL, tag="explore-setfree-inflate")
