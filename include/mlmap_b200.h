@@ -214,6 +214,23 @@ int mlm_export_map(mlm_handle h, size_t cap_submaps, int32_t *glb3, uint8_t *col
  * bitmask of ceil(subbox_n^3 / 32) 32-bit words per subbox (bit c = cell id c), with its own glb3 list. */
 int mlm_export_frontier(mlm_handle h, size_t cap_submaps, int32_t *glb3, uint32_t *frontier_words, size_t *n_out);
 
+/* ---- one logical map sharded over `world` ranks (large LiDAR scans) -------------------------------
+ * Per scan, on every rank with the SAME points and pose:
+ *   1. mlm_shard_stage_points_f64   casts the rank's phi columns (phi % world == rank) into its voxel staging
+ *   2. mlm_shard_copy_hit_keys      -> all-gather the (key, stamp) lists of all ranks (caller, NCCL)
+ *   3. mlm_shard_order              every rank derives the same hit-map iteration order from the gathered list
+ *   4. mlm_shard_emit_counts / mlm_shard_emit_pack  24-byte update records grouped by owner rank
+ *      (owner = hash of the subbox index % world) -> all-to-all (caller, NCCL)
+ *   5. mlm_shard_ingest             the owner stages the received records, allocates its subboxes and fuses
+ * Each rank then holds the subboxes it owns; the union over ranks equals the single-GPU map bit for bit. */
+int mlm_shard_stage_points_f64(mlm_handle h, const double *xyz, int n, const double T_wb[7], int rank, int world,
+                               int32_t *n_hit_local, int32_t *n_miss_local);
+int mlm_shard_copy_hit_keys(mlm_handle h, int32_t *d_keys_out, uint32_t *d_stamps_out);
+int mlm_shard_order(mlm_handle h, const int32_t *d_keys_all, uint32_t *d_stamps_all, int n_total);
+int mlm_shard_emit_counts(mlm_handle h, int world, int32_t *counts);
+int mlm_shard_emit_pack(mlm_handle h, int world, const int32_t *counts, void *d_out);
+int mlm_shard_ingest(mlm_handle h, const void *d_records, int n, mlm_frame_stats *stats);
+
 /* glibc-2.39 log10f as evaluated on device (parity test hook, SURVEY §7 hard part 3) */
 int mlm_debug_log10f(mlm_handle h, const float *x, size_t n, float *out);
 

@@ -469,6 +469,7 @@ __device__ __forceinline__ void radix_pass(const uint64_t *src, uint64_t *dst, i
 
 __device__ __forceinline__ void touch_subbox(const MapParams &P, const FrameParams &F, DeviceBuffers &D,
                                              FrameCounters *fc, const int g[3]) {
+  if (F.stage_only) return;  // sharded staging: the subbox belongs to its owner rank
   int ls = lsg_index(P, F, g);
   if (ls < 0) {
     fc->error = kErrInternal;
@@ -633,7 +634,8 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   const int n_c = D.phi_hist[phi];
   uint32_t *g_miss = D.miss_bitmap + (size_t)phi * P.col_words;
   __shared__ int s_last;
-  if (n_c == 0) {
+  const bool not_mine = F.shard_world > 1 && (phi % F.shard_world) != F.shard_rank;  // another rank casts this column
+  if (n_c == 0 || not_mine) {
     for (int i = tid; i < P.col_words; i += blockDim.x) g_miss[i] = 0;
     if (tid == 0) {
       __threadfence();
@@ -643,7 +645,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
     if (s_last) {
       if (tid == 0) *D.col_ticket = 0;
       __threadfence();
-      resolve_subboxes(P, F, D, fc);
+      if (!F.stage_only) resolve_subboxes(P, F, D, fc);
     }
     return;
   }
@@ -1070,7 +1072,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   if (s_last) {
     if (tid == 0) *D.col_ticket = 0;
     __threadfence();
-    resolve_subboxes(P, F, D, fc);
+    if (!F.stage_only) resolve_subboxes(P, F, D, fc);
   }
 }
 

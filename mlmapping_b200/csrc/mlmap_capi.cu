@@ -19,6 +19,7 @@
 #include "order_kernels.cuh"
 #include "explore_kernels.cuh"
 #include "query_kernels.cuh"
+#include "shard_kernels.cuh"
 
 using namespace mlm;
 
@@ -169,6 +170,12 @@ struct mlm_map {
   uint32_t frame_idx = 0;
   int last_parity = 0;
   GlibcRand rng;  // project_depth's rand() stream (sampled mode)
+  // sharded operation (one logical map over several ranks)
+  uint32_t *d_key_stamp = nullptr;   // [cells] global ordering stamp per hit key of the frame
+  int *d_shard_cnt = nullptr;        // [3*64] counts / bases / cursors per destination
+  int shard_world = 1, shard_rank = 0;
+  int shard_n_local = 0;
+  bool shard_stage_pending = false;
   cudaGraphExec_t graph_exec[3] = {nullptr, nullptr, nullptr};  // by input mode: points, depth image, sampled pixels
   cudaGraph_t graph[3] = {nullptr, nullptr, nullptr};
   cudaGraphNode_t graph_nodes[3][3] = {};
@@ -473,6 +480,9 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
   h->last_parity = parity;
   F.parity = parity;
   F.order_mode = 0;
+  F.shard_rank = 0;
+  F.shard_world = 1;
+  F.stage_only = 0;
   F.tbits = 1;
   while ((1ll << F.tbits) < (long long)std::max(N, 2)) F.tbits++;
   // frame-local voxel grid origin: awareness bounding box around t_wa plus a margin
@@ -482,6 +492,21 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
   F.lvg_base[2] = (int)floor((Twa.t[2] + P.z_border_min) / P.d_sub) - P.lvg_margin;
   for (int i = 0; i < 3; i++) F.lsg_base[i] = host_floor_div(F.lvg_base[i], P.n) - 1;
 
+  if (h->shard_world > 0 && h->shard_stage_pending) {
+    // sharded staging: project + column only; records are emitted and fused by the mlm_shard_* calls
+    F.shard_rank = h->shard_rank;
+    F.shard_world = h->shard_world;
+    F.stage_only = 1;
+    F.order_mode = 1;
+    const int pg = grid_for((size_t)std::max(N, 1), 256);
+    k_project<0><<<pg, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(P, h->D, F);
+    k_column<<<P.nPhi, kColThreads, h->col_smem_bytes, s>>>(P, h->D, F);
+    h->launches += 2;
+    CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc[parity], sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaGetLastError());
+    return MLM_OK;
+  }
   if (P.explore) return run_frame_explore(h, mode, N, stats);
   const bool prof = h->profiling != 0;
   const int full_grid = grid_for((size_t)P.max_points, 256);
@@ -1437,6 +1462,161 @@ int mlm_export_map(mlm_handle h, size_t cap_submaps, int32_t *glb3, uint8_t *col
 int mlm_export_frontier(mlm_handle h, size_t cap_submaps, int32_t *glb3, uint32_t *frontier_words, size_t *n_out) {
   if (!h || !n_out || !glb3 || !frontier_words) return MLM_ERR_INVALID_ARG;
   return export_common(h, cap_submaps, glb3, nullptr, nullptr, nullptr, nullptr, frontier_words, n_out);
+}
+
+// ---- sharded map: stage / order / emit / ingest; collectives are the caller's (NCCL via torch.distributed)
+int mlm_shard_stage_points_f64(mlm_handle h, const double *xyz, int n, const double T_wb[7], int rank, int world,
+                               int32_t *n_hit_local, int32_t *n_miss_local) {
+  if (!h || (!xyz && n > 0) || !T_wb || n < 0 || world < 1 || world > 64 || rank < 0 || rank >= world) return MLM_ERR_INVALID_ARG;
+  if (h->P.explore || n > h->P.max_points) return n > h->P.max_points ? MLM_ERR_CAPACITY : MLM_ERR_UNSUPPORTED;
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->d_key_stamp) {
+    const size_t cells = (size_t)h->P.nZ * h->P.nPhi * h->P.nRho;
+    CUDA_TRY(cudaMalloc((void **)&h->d_key_stamp, cells * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc((void **)&h->d_shard_cnt, 3 * 64 * sizeof(int)));
+    h->allocs.push_back(h->d_key_stamp);
+    h->allocs.push_back(h->d_shard_cnt);
+  }
+  const size_t bytes = (size_t)std::max(n, 1) * 24;
+  int rc = ensure_input(h, bytes, (size_t)h->P.max_points * 24);
+  if (rc != MLM_OK) return rc;
+  if (n > 0) {
+    memcpy(h->h_stage, xyz, (size_t)n * 24);
+    CUDA_TRY(cudaMemcpyAsync(h->d_input, h->h_stage, (size_t)n * 24, cudaMemcpyHostToDevice, h->stream));
+  }
+  h->shard_rank = rank;
+  h->shard_world = world;
+  h->shard_stage_pending = true;
+  rc = run_frame(h, 0, h->d_input, 0, 0, n, T_wb, nullptr);
+  h->shard_stage_pending = false;
+  if (rc != MLM_OK) return rc;
+  if (h->h_fc->error) return map_device_error(h->h_fc->error);
+  h->shard_n_local = h->h_fc->n_hit;
+  if (n_hit_local) *n_hit_local = h->h_fc->n_hit;
+  if (n_miss_local) *n_miss_local = h->h_fc->n_miss;
+  return MLM_OK;
+}
+
+// copies the rank's distinct hit keys and first-insert stamps (n_hit_local each) into caller device buffers
+int mlm_shard_copy_hit_keys(mlm_handle h, int32_t *d_keys_out, uint32_t *d_stamps_out) {
+  if (!h || !d_keys_out || !d_stamps_out) return MLM_ERR_INVALID_ARG;
+  const size_t n = (size_t)h->shard_n_local;
+  if (n) {
+    CUDA_TRY(cudaMemcpyAsync(d_keys_out, h->D.hit_key, n * 4, cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_stamps_out, h->D.hit_t, n * 4, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return MLM_OK;
+}
+
+// global iteration order of the frame from the hit keys of ALL ranks (identical call on every rank)
+int mlm_shard_order(mlm_handle h, const int32_t *d_keys_all, uint32_t *d_stamps_all, int n_total) {
+  if (!h || n_total < 0 || (n_total && (!d_keys_all || !d_stamps_all))) return MLM_ERR_INVALID_ARG;
+  if (n_total > h->sort_cap) return MLM_ERR_CAPACITY;
+  cudaStream_t s = h->stream;
+  const int T = 256;
+  uint32_t *act = h->D.act[h->last_parity];
+  uint32_t B = h->bucket_count;
+  if (n_total > 0 && B == 1) B = 13;  // the first insert of an empty table allocates 13 buckets before anything is ordered
+  if ((uint32_t)n_total > B) {
+    // rehash frame: staged re-sequencing on the gathered list (stamps become virtual positions)
+    uint32_t *d_bucket = nullptr;
+    CUDA_TRY(cudaMallocAsync((void **)&d_bucket, (size_t)n_total * 4, s));
+    OrderArrays O;
+    O.key = d_keys_all;
+    O.stamp = d_stamps_all;
+    O.bucket = d_bucket;
+    O.kind = 0;
+    // same driver as order_slow_path, on caller arrays
+    int n_pad = next_pow2(n_total);
+    k_order_seed<<<grid_for(n_pad, T), T, 0, s>>>(O, h->d_sort_a, n_total, n_pad);
+    device_sort(h, h->d_sort_a, n_pad);
+    k_order_take_seq<<<grid_for(n_total, T), T, 0, s>>>(h->d_sort_a, h->d_seq_a, n_total);
+    uint32_t Bs = h->bucket_count;
+    while ((uint32_t)n_total > Bs) {
+      int m = (int)std::min<uint32_t>(Bs, (uint32_t)n_total);
+      if (m > 1) {
+        int m_pad = next_pow2(m);
+        k_fill_u32<<<grid_for(Bs, T), T, 0, s>>>(act, 0xffffffffu, (int)Bs);
+        k_stage_act<<<grid_for(m, T), T, 0, s>>>(h->P, O, act, h->d_seq_a, m, Bs);
+        k_stage_keys<<<grid_for(m_pad, T), T, 0, s>>>(h->P, O, act, h->d_seq_a, h->d_sort_b, m, m_pad, Bs);
+        device_sort(h, h->d_sort_b, m_pad);
+        k_stage_apply<<<grid_for(m, T), T, 0, s>>>(h->d_sort_b, h->d_seq_a, h->d_seq_b, m);
+        k_copy_i32<<<grid_for(m, T), T, 0, s>>>(h->d_seq_a, h->d_seq_b, m);
+      }
+      uint32_t nb = chain_next(Bs);
+      if (nb == 0 || nb > h->act_cap) return MLM_ERR_CAPACITY;
+      Bs = nb;
+    }
+    k_fill_u32<<<grid_for(Bs, T), T, 0, s>>>(act, 0xffffffffu, (int)Bs);
+    k_order_final<<<grid_for(n_total, T), T, 0, s>>>(h->P, O, act, h->d_seq_a, n_total, Bs);
+    CUDA_TRY(cudaFreeAsync(d_bucket, s));
+    B = Bs;
+  } else if (n_total > 0) {
+    k_fill_u32<<<grid_for(B, T), T, 0, s>>>(act, 0xffffffffu, (int)B);
+    k_shard_act<<<grid_for(n_total, T), T, 0, s>>>(h->P, d_keys_all, d_stamps_all, n_total, act, B);
+  }
+  if (n_total > 0) k_shard_scatter_stamps<<<grid_for(n_total, T), T, 0, s>>>(d_keys_all, d_stamps_all, n_total, h->d_key_stamp);
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  h->bucket_count = B;
+  h->last_order_B = B;
+  h->h_fp->bucket_count = B;
+  return MLM_OK;
+}
+
+int mlm_shard_emit_counts(mlm_handle h, int world, int32_t *counts) {
+  if (!h || !counts || world != h->shard_world) return MLM_ERR_INVALID_ARG;
+  cudaStream_t s = h->stream;
+  CUDA_TRY(cudaMemsetAsync(h->d_shard_cnt, 0, 3 * 64 * sizeof(int), s));
+  const int n = std::min(h->h_fc->n_touched, h->P.max_touched);
+  if (n > 0) k_shard_emit<0><<<grid_for(n, 256), 256, 0, s>>>(h->P, h->D, *h->h_fp, world, h->d_shard_cnt, nullptr, nullptr, nullptr);
+  CUDA_TRY(cudaMemcpyAsync(counts, h->d_shard_cnt, world * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  return MLM_OK;
+}
+
+// d_out: sum(counts) records of 24 bytes, grouped by destination rank in rank order
+int mlm_shard_emit_pack(mlm_handle h, int world, const int32_t *counts, void *d_out) {
+  if (!h || !counts || world != h->shard_world) return MLM_ERR_INVALID_ARG;
+  cudaStream_t s = h->stream;
+  int base[64], acc = 0;
+  for (int d = 0; d < world; d++) {
+    base[d] = acc;
+    acc += counts[d];
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->d_shard_cnt + 64, base, world * sizeof(int), cudaMemcpyHostToDevice, s));
+  const int n = std::min(h->h_fc->n_touched, h->P.max_touched);
+  if (n > 0)
+    k_shard_emit<1><<<grid_for(n, 256), 256, 0, s>>>(h->P, h->D, *h->h_fp, world, h->d_shard_cnt, h->d_shard_cnt + 64,
+                                                     h->d_shard_cnt + 128, reinterpret_cast<ShardRecord *>(d_out));
+  k_shard_reset_counters<<<1, 1, 0, s>>>(h->D, *h->h_fp);
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  return MLM_OK;
+}
+
+// owner side: received records -> voxel staging -> subbox resolve/allocate -> clamped log-odds fusion
+int mlm_shard_ingest(mlm_handle h, const void *d_records, int n, mlm_frame_stats *stats) {
+  if (!h || n < 0 || (n && !d_records)) return MLM_ERR_INVALID_ARG;
+  cudaStream_t s = h->stream;
+  FrameParams F = *h->h_fp;
+  F.stage_only = 0;
+  F.order_mode = 1;
+  F.shard_world = 1;
+  if (n > 0)
+    k_shard_ingest<<<grid_for(n, 256), 256, 0, s>>>(h->P, h->D, F, reinterpret_cast<const ShardRecord *>(d_records), n,
+                                                    h->d_key_stamp);
+  k_shard_resolve<<<1, 1024, 0, s>>>(h->P, h->D, F);
+  k_fuse<0><<<h->sm_count * 4, 256, 0, s>>>(h->P, h->D, F);
+  h->launches += 3;
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  const uint32_t B = h->bucket_count;
+  int rc = finish_frame(h, 0, B, stats);
+  h->bucket_count = B;  // finish_frame grows it from the LOCAL hit count; the global count already set it
+  return rc;
 }
 
 int mlm_debug_log10f(mlm_handle h, const float *x, size_t n, float *out) {

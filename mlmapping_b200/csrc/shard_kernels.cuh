@@ -1,0 +1,161 @@
+// One logical map sharded over several GPUs ("large LiDAR scans"): stage 1 by phi column
+// (rank r casts the columns phi % world == r: hit folds and miss bitmaps of different columns are
+// disjoint), stage 2 by subbox owner (hash(glb) % world).  Between the stages the ranks exchange
+//   * the distinct hit keys with their first-insert stamps (all-gather) so that every rank derives the same
+//     libstdc++ iteration order for the whole frame, and
+//   * fixed-size update records per touched voxel (all-to-all), consumed by the owner's k_fuse.
+// The collectives themselves are issued by the host side (torch.distributed / NCCL) on the device buffers
+// these kernels fill; with world == 1 the same code path runs on one GPU.
+#pragma once
+#include "frame_kernels.cuh"
+#include "order_kernels.cuh"
+
+namespace mlm {
+
+struct __align__(8) ShardRecord {  // 24 bytes
+  int c[3];     // canonical global cell coordinate of the voxel
+  int key;      // awareness cell index of a hit key, or -1 for a miss record
+  float p;      // hit: folded probability
+  int count;    // miss: number of miss cells mapping to the voxel
+};
+
+__device__ __forceinline__ int owner_of(const MapParams &P, const int c[3], int world) {
+  int g[3] = {floor_div(c[0], P.n), floor_div(c[1], P.n), floor_div(c[2], P.n)};
+  uint64_t key;
+  if (!pack_glb(g, key)) return 0;
+  return (int)(ht_hash(key) % (uint32_t)world);
+}
+
+// one thread per touched-list entry; pass 0 counts records per destination, pass 1 writes them at
+// cursor[dest] and clears the local staging.  A voxel with hits and misses has two list entries: the
+// hit entry handles both.
+template <int kPass>
+__global__ void __launch_bounds__(256) k_shard_emit(MapParams P, DeviceBuffers D, FrameParams F, int world,
+                                                    int *counts /*[world]*/, const int *base /*[world]*/,
+                                                    int *cursor /*[world]*/, ShardRecord *out) {
+  __shared__ int s_cnt[64];
+  __shared__ int s_base[64];
+  FrameCounters *fc = D.fc[F.parity];
+  for (int i = threadIdx.x; i < world; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  const int n = min(fc->n_touched, P.max_touched);
+  const int dxy = P.lvg_dim_xy;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int dest = -1, nrec = 0, head = kLvgEmpty, mc = 0, lv = 0, rank_in_cta = 0;
+  int c[3] = {0, 0, 0};
+  if (i < n) {
+    const uint32_t e = D.touched[i];
+    lv = (int)(e & ~kTouchedHitTag);
+    const int2 st = D.lvg[lv];
+    if ((e & kTouchedHitTag) || st.x == kLvgEmpty) {  // the entry that owns the voxel
+      head = st.x;
+      mc = st.y;
+      c[0] = lv % dxy + F.lvg_base[0];
+      c[1] = (lv / dxy) % dxy + F.lvg_base[1];
+      c[2] = lv / (dxy * dxy) + F.lvg_base[2];
+      dest = owner_of(P, c, world);
+      for (int h = head; h != kLvgEmpty; h = D.hit_next[h]) nrec++;
+      if (mc > 0) nrec++;
+      rank_in_cta = atomicAdd(&s_cnt[dest], nrec);
+    }
+  }
+  __syncthreads();
+  if (kPass == 0) {
+    for (int d = threadIdx.x; d < world; d += blockDim.x)
+      if (s_cnt[d]) atomicAdd(&counts[d], s_cnt[d]);
+    return;
+  }
+  for (int d = threadIdx.x; d < world; d += blockDim.x) s_base[d] = s_cnt[d] ? base[d] + atomicAdd(&cursor[d], s_cnt[d]) : 0;
+  __syncthreads();
+  if (dest >= 0) {
+    ShardRecord *o = out + s_base[dest] + rank_in_cta;
+    for (int h = head; h != kLvgEmpty; h = D.hit_next[h]) {
+      ShardRecord r;
+      r.c[0] = c[0];
+      r.c[1] = c[1];
+      r.c[2] = c[2];
+      r.key = D.hit_key[h];
+      r.p = D.hit_p[h];
+      r.count = 0;
+      *o++ = r;
+    }
+    if (mc > 0) {
+      ShardRecord r;
+      r.c[0] = c[0];
+      r.c[1] = c[1];
+      r.c[2] = c[2];
+      r.key = -1;
+      r.p = 0.f;
+      r.count = mc;
+      *o++ = r;
+    }
+  }
+  if (i < n) D.lvg[lv] = make_int2(kLvgEmpty, 0);  // staging consumed (both entries of a voxel write the same value)
+}
+
+// global ordering info per key: key_stamp[key] = first-insert stamp (or virtual position on a rehash frame)
+__global__ void k_shard_scatter_stamps(const int *keys, const uint32_t *stamps, int n, uint32_t *key_stamp) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) key_stamp[keys[i]] = stamps[i];
+}
+__global__ void k_shard_act(MapParams P, const int *keys, const uint32_t *stamps, int n, uint32_t *act, uint32_t B) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicMin(&act[cell_bucket(P, keys[i], B, 0)], stamps[i]);
+}
+
+// owner side: received records -> hit arrays + voxel-grid staging (the role k_column's staging plays on one GPU)
+__global__ void __launch_bounds__(256) k_shard_ingest(MapParams P, DeviceBuffers D, FrameParams F, const ShardRecord *rec,
+                                                      int n, const uint32_t *key_stamp) {
+  FrameCounters *fc = D.fc[F.parity];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const ShardRecord r = rec[i];
+  CellRef cr;
+  for (int a = 0; a < 3; a++) {
+    cr.c[a] = r.c[a];
+    cr.g[a] = floor_div(r.c[a], P.n);
+  }
+  const int lv = lvg_index(P, F, cr);
+  if (lv < 0) {
+    fc->error = kErrInternal;
+    return;
+  }
+  if (r.key >= 0) {
+    const int idx = agg_inc(&fc->n_hit);
+    if (idx >= P.max_hits) {
+      fc->error = kErrCapacity;
+      return;
+    }
+    D.hit_key[idx] = r.key;
+    D.hit_p[idx] = r.p;
+    D.hit_t[idx] = key_stamp[r.key];
+    D.hit_bucket[idx] = cell_bucket(P, r.key, F.bucket_count, 0);
+    const int old = atomicExch(&D.lvg[lv].x, idx);
+    D.hit_next[idx] = old;
+    if (old == kLvgEmpty) {
+      const int tp = agg_inc(&fc->n_touched);
+      if (tp < P.max_touched) D.touched[tp] = (uint32_t)lv | kTouchedHitTag; else fc->error = kErrCapacity;
+    }
+  } else {
+    const int old = atomicAdd(&D.lvg[lv].y, r.count);
+    if (old == 0) {
+      const int tp = agg_inc(&fc->n_touched);
+      if (tp < P.max_touched) D.touched[tp] = (uint32_t)lv; else fc->error = kErrCapacity;
+    }
+  }
+  touch_subbox(P, F, D, fc, cr.g);
+}
+
+// standalone resolve (on one GPU the last k_column CTA does this)
+__global__ void __launch_bounds__(1024) k_shard_resolve(MapParams P, DeviceBuffers D, FrameParams F) {
+  resolve_subboxes(P, F, D, D.fc[F.parity]);
+}
+
+__global__ void k_shard_reset_counters(DeviceBuffers D, FrameParams F) {
+  FrameCounters *fc = D.fc[F.parity];
+  fc->n_hit = 0;
+  fc->n_touched = 0;
+  fc->n_touched_sub = 0;
+}
+
+}  // namespace mlm

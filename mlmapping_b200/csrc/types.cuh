@@ -89,6 +89,8 @@ struct FrameParams {
   int lsg_base[3];  // global subbox coordinate of local submap grid origin
   int tbits;        // bits needed for a point stamp this frame (ceil(log2(#points)))
   uint32_t bucket_count_miss;  // emulated miss_idx_set.bucket_count() at frame start (exploration mode)
+  int shard_rank, shard_world;  // sharded staging: this rank casts the columns phi % world == rank
+  int stage_only;   // 1: k_column stages into the voxel grid only (no subbox resolve; records go to the owners)
   int parity;       // frame & 1: selects the double-buffered counters / activation stamps
   int order_mode;   // 0: stamps are (bucket activation, first-insert time); 1: virtual sequence positions
 };

@@ -1,0 +1,95 @@
+"""One logical map sharded over the GPUs of a node (large LiDAR scans).
+
+Every rank runs this class with the same scans.  Stage 1 is split by phi column, stage 2 by subbox owner;
+in between the ranks all-gather the frame's distinct hit keys (so each derives the same libstdc++ iteration
+order) and all-to-all the per-voxel update records.  torch.distributed (NCCL over NVLink) carries the two
+exchanges; the compute on both sides is the CUDA library.  With world_size 1 (or no process group) the same
+code path runs on one GPU, which is how the parity tests exercise it without a multi-GPU box."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .capi import FrameStats, MLMap, MlmConfig, _pose7
+
+
+class ShardedMLMap:
+    RECORD_INTS = 6  # 24-byte ShardRecord
+
+    def __init__(self, cfg: MlmConfig, rank: int = 0, world: int = 1, device: int | None = None):
+        import torch
+
+        self.torch = torch
+        self.rank, self.world = rank, world
+        self.map = MLMap(cfg, device=rank if device is None else device)
+        self.dev = torch.device("cuda", rank if device is None else device)
+        self.last = {}
+
+    def _dist(self):
+        import torch.distributed as dist
+        return dist if (self.world > 1) else None
+
+    def integrate_points(self, xyz: np.ndarray, T_wb) -> FrameStats:
+        torch, m, lib = self.torch, self.map, self.map._lib
+        dist = self._dist()
+        pts = np.ascontiguousarray(np.asarray(xyz, dtype=np.float64).reshape(-1, 3))
+        n_hit, n_miss = C.c_int32(), C.c_int32()
+        m._check(lib.mlm_shard_stage_points_f64(m._h, pts.ctypes.data, pts.shape[0], _pose7(T_wb), self.rank, self.world,
+                                                C.byref(n_hit), C.byref(n_miss)))
+        # ---- exchange 1: all-gather of the distinct hit keys + first-insert stamps ----
+        keys = torch.empty(max(n_hit.value, 1), dtype=torch.int32, device=self.dev)
+        stamps = torch.empty(max(n_hit.value, 1), dtype=torch.int32, device=self.dev)
+        m._check(lib.mlm_shard_copy_hit_keys(m._h, keys.data_ptr(), stamps.data_ptr()))
+        if dist:
+            cnt = torch.tensor([n_hit.value], dtype=torch.int64, device=self.dev)
+            all_cnt = torch.empty(self.world, dtype=torch.int64, device=self.dev)
+            dist.all_gather_into_tensor(all_cnt, cnt)
+            sizes = all_cnt.tolist()
+            mx = max(max(sizes), 1)
+            pad_k = torch.zeros(mx, dtype=torch.int32, device=self.dev)
+            pad_s = torch.zeros(mx, dtype=torch.int32, device=self.dev)
+            pad_k[:n_hit.value] = keys[:n_hit.value]
+            pad_s[:n_hit.value] = stamps[:n_hit.value]
+            gk = torch.empty(self.world * mx, dtype=torch.int32, device=self.dev)
+            gs = torch.empty(self.world * mx, dtype=torch.int32, device=self.dev)
+            dist.all_gather_into_tensor(gk, pad_k)
+            dist.all_gather_into_tensor(gs, pad_s)
+            keys_all = torch.cat([gk[r * mx:r * mx + sizes[r]] for r in range(self.world)]).contiguous()
+            stamps_all = torch.cat([gs[r * mx:r * mx + sizes[r]] for r in range(self.world)]).contiguous()
+        else:
+            keys_all, stamps_all = keys[:n_hit.value].contiguous(), stamps[:n_hit.value].contiguous()
+        n_total = int(keys_all.numel())
+        torch.cuda.synchronize(self.dev)
+        m._check(lib.mlm_shard_order(m._h, keys_all.data_ptr() if n_total else None,
+                                     stamps_all.data_ptr() if n_total else None, n_total))
+        # ---- exchange 2: all-to-all of the per-voxel update records, grouped by owner ----
+        send_counts = (C.c_int32 * self.world)()
+        m._check(lib.mlm_shard_emit_counts(m._h, self.world, send_counts))
+        sc = [int(v) for v in send_counts]
+        send = torch.empty((max(sum(sc), 1), self.RECORD_INTS), dtype=torch.int32, device=self.dev)
+        m._check(lib.mlm_shard_emit_pack(m._h, self.world, send_counts, send.data_ptr()))
+        if dist:
+            sct = torch.tensor(sc, dtype=torch.int64, device=self.dev)
+            rct = torch.empty(self.world, dtype=torch.int64, device=self.dev)
+            dist.all_to_all_single(rct, sct)
+            rc = rct.tolist()
+            recv = torch.empty((max(sum(rc), 1), self.RECORD_INTS), dtype=torch.int32, device=self.dev)
+            dist.all_to_all_single(recv[:sum(rc)], send[:sum(sc)], output_split_sizes=rc, input_split_sizes=sc)
+            n_recv = sum(rc)
+        else:
+            recv, n_recv = send, sum(sc)
+        torch.cuda.synchronize(self.dev)
+        st = FrameStats()
+        m._check(lib.mlm_shard_ingest(m._h, recv.data_ptr() if n_recv else None, n_recv, C.byref(st)))
+        self.last = {"n_hit_local": n_hit.value, "n_hit_total": n_total, "n_miss_local": n_miss.value,
+                     "records_sent": sum(sc), "records_received": n_recv,
+                     "a2a_bytes": 24 * sum(sc), "allgather_bytes": 8 * n_total}
+        return st
+
+    # queries / exports act on the subboxes this rank owns
+    def export_map(self):
+        return self.map.export_map()
+
+    def close(self):
+        self.map.close()
