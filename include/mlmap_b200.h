@@ -231,6 +231,13 @@ int mlm_shard_emit_counts(mlm_handle h, int world, int32_t *counts);
 int mlm_shard_emit_pack(mlm_handle h, int world, const int32_t *counts, void *d_out);
 int mlm_shard_ingest(mlm_handle h, const void *d_records, int n, mlm_frame_stats *stats);
 
+/* ---- replicated map for split query streams: after a frame the updating rank exports the subbox
+ * blocks that frame touched (mlm_dirty_count gives their number and the record size), the caller broadcasts the
+ * buffer (NCCL), replicas apply it with mlm_dirty_import; queries on a replica then equal the owner's. */
+int mlm_dirty_count(mlm_handle h, int32_t *n_blocks, size_t *record_bytes);
+int mlm_dirty_export(mlm_handle h, void *d_out, int32_t n_blocks);
+int mlm_dirty_import(mlm_handle h, const void *d_in, int32_t n_blocks);
+
 /* glibc-2.39 log10f as evaluated on device (parity test hook, SURVEY §7 hard part 3) */
 int mlm_debug_log10f(mlm_handle h, const float *x, size_t n, float *out);
 

@@ -109,7 +109,7 @@ ABI_SYMBOLS = [
     "mlm_last_frame_hits", "mlm_last_frame_misses", "mlm_export_map_count", "mlm_export_map",
     "mlm_debug_log10f", "mlm_set_profiling", "mlm_last_frame_kernel_ms", "mlm_sizeof_config",
     "mlm_sizeof_frame_stats", "mlm_debug_phase_cycles", "mlm_host_alloc", "mlm_host_free", "mlm_srand", "mlm_debug_rand", "mlm_export_frontier", "mlm_shard_stage_points_f64",
-    "mlm_shard_copy_hit_keys", "mlm_shard_order", "mlm_shard_emit_counts", "mlm_shard_emit_pack", "mlm_shard_ingest",
+    "mlm_shard_copy_hit_keys", "mlm_shard_order", "mlm_shard_emit_counts", "mlm_shard_emit_pack", "mlm_shard_ingest", "mlm_dirty_count", "mlm_dirty_export", "mlm_dirty_import",
 ]
 FRAME_KERNELS = ["k_project", "k_column", "k_fuse"]
 
@@ -186,6 +186,9 @@ def load_library() -> C.CDLL:
         "mlm_shard_emit_counts": ([vp, C.c_int, vp], C.c_int),
         "mlm_shard_emit_pack": ([vp, C.c_int, vp, vp], C.c_int),
         "mlm_shard_ingest": ([vp, vp, C.c_int, C.POINTER(FrameStats)], C.c_int),
+        "mlm_dirty_count": ([vp, ip, C.POINTER(sz)], C.c_int),
+        "mlm_dirty_export": ([vp, vp, C.c_int32], C.c_int),
+        "mlm_dirty_import": ([vp, vp, C.c_int32], C.c_int),
         "mlm_debug_log10f": ([vp, vp, sz, vp], C.c_int),
         "mlm_debug_phase_cycles": ([vp, vp, sz], C.c_int),
         "mlm_srand": ([vp, C.c_uint], C.c_int),

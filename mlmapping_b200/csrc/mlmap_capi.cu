@@ -1619,6 +1619,41 @@ int mlm_shard_ingest(mlm_handle h, const void *d_records, int n, mlm_frame_stats
   return rc;
 }
 
+// ---- replicated map: ship the subbox blocks touched by the last frame --------------------------------------
+int mlm_dirty_count(mlm_handle h, int32_t *n_blocks, size_t *record_bytes) {
+  if (!h || !n_blocks || !record_bytes) return MLM_ERR_INVALID_ARG;
+  if (h->P.explore) return MLM_ERR_UNSUPPORTED;
+  *n_blocks = h->h_fc->n_touched_sub;
+  *record_bytes = dirty_record_bytes(h->P.cells);
+  return MLM_OK;
+}
+int mlm_dirty_export(mlm_handle h, void *d_out, int32_t n_blocks) {
+  if (!h || (n_blocks && !d_out) || n_blocks < 0 || n_blocks > h->h_fc->n_touched_sub) return MLM_ERR_INVALID_ARG;
+  if (n_blocks) k_dirty_export<<<n_blocks, 256, 0, h->stream>>>(h->P, h->D, *h->h_fp, n_blocks, (unsigned char *)d_out);
+  h->launches++;
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaGetLastError());
+  return MLM_OK;
+}
+int mlm_dirty_import(mlm_handle h, const void *d_in, int32_t n_blocks) {
+  if (!h || (n_blocks && !d_in) || n_blocks < 0) return MLM_ERR_INVALID_ARG;
+  if (h->P.explore) return MLM_ERR_UNSUPPORTED;
+  cudaStream_t s = h->stream;
+  int *d_cnt = nullptr;
+  CUDA_TRY(cudaMallocAsync((void **)&d_cnt, 2 * sizeof(int), s));
+  CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), s));
+  if (n_blocks) k_dirty_import<<<n_blocks, 256, 0, s>>>(h->P, h->D, n_blocks, (const unsigned char *)d_in, d_cnt);
+  h->launches++;
+  int cnt[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaFreeAsync(d_cnt, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  h->cum_ram_expand += cnt[0];
+  h->n_submaps += cnt[0];
+  return cnt[1] ? map_device_error(cnt[1]) : MLM_OK;
+}
+
 int mlm_debug_log10f(mlm_handle h, const float *x, size_t n, float *out) {
   if (!h || (!x && n) || (!out && n)) return MLM_ERR_INVALID_ARG;
   if (n == 0) return MLM_OK;

@@ -158,4 +158,92 @@ __global__ void k_shard_reset_counters(DeviceBuffers D, FrameParams F) {
   fc->n_touched_sub = 0;
 }
 
+
+// ---- replicated map (query stream): after a frame the owner ships the subbox blocks the frame
+// touched ("dirty" blocks); replicas overwrite / create them.  Record = 16-byte header {g[3], cells} followed
+// by log_odds[cells] f32, occupancy[cells], inflate[cells] (padded to 16 bytes).
+__host__ __device__ inline size_t dirty_record_bytes(int cells) { return (16 + (size_t)cells * 6 + 15) & ~(size_t)15; }
+
+__global__ void __launch_bounds__(256) k_dirty_export(MapParams P, DeviceBuffers D, FrameParams F, int n, unsigned char *out) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const int ls = D.touched_sub[i];
+  const int block = D.lsg_block[ls];
+  unsigned char *rec = out + (size_t)i * dirty_record_bytes(P.cells);
+  int *hdr = reinterpret_cast<int *>(rec);
+  if (threadIdx.x == 0) {
+    int lx = ls % P.lsg_dim_xy, ly = (ls / P.lsg_dim_xy) % P.lsg_dim_xy, lz = ls / (P.lsg_dim_xy * P.lsg_dim_xy);
+    hdr[0] = lx + F.lsg_base[0];
+    hdr[1] = ly + F.lsg_base[1];
+    hdr[2] = lz + F.lsg_base[2];
+    hdr[3] = block >= 0 ? P.cells : 0;  // 0: nothing to ship (collapsed / unusable)
+  }
+  if (block < 0) return;
+  float *lo = reinterpret_cast<float *>(rec + 16);
+  char *occ = reinterpret_cast<char *>(rec + 16 + (size_t)P.cells * 4);
+  char *inf = occ + P.cells;
+  const size_t src = (size_t)block * P.cell_stride;
+  for (int c = threadIdx.x; c < P.cells; c += blockDim.x) {
+    lo[c] = D.pool_lo[src + c];
+    occ[c] = D.pool_occ[src + c];
+    inf[c] = D.pool_inf[src + c];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_dirty_import(MapParams P, DeviceBuffers D, int n, const unsigned char *in, int *counters) {
+  __shared__ int s_block;
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const unsigned char *rec = in + (size_t)i * dirty_record_bytes(P.cells);
+  const int *hdr = reinterpret_cast<const int *>(rec);
+  if (hdr[3] == 0) return;
+  if (threadIdx.x == 0) {
+    int g[3] = {hdr[0], hdr[1], hdr[2]};
+    uint64_t key;
+    int block = kBlockUnusable;
+    if (pack_glb(g, key)) {
+      uint32_t slot = ht_hash(key) & P.ht_mask;
+      for (uint32_t probe = 0; probe <= P.ht_mask; probe++) {
+        uint64_t k = D.ht_key[slot];
+        if (k == kEmptyKey) {
+          unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&D.ht_key[slot]),
+                                             (unsigned long long)kEmptyKey, (unsigned long long)key);
+          if (old == kEmptyKey) {
+            int top = atomicSub(D.free_top, 1) - 1;
+            if (top < 0) {
+              atomicAdd(D.free_top, 1);
+              D.ht_val[slot] = kBlockUnusable;
+              counters[1] = kErrPool;
+            } else {
+              block = D.free_stack[top];
+              D.ht_val[slot] = block;
+              atomicAdd(&counters[0], 1);
+            }
+            break;
+          }
+          k = (uint64_t)old;
+        }
+        if (k == key) {
+          block = D.ht_val[slot];
+          break;
+        }
+        slot = (slot + 1) & P.ht_mask;
+      }
+    }
+    s_block = block;
+  }
+  __syncthreads();
+  const int block = s_block;
+  if (block < 0) return;
+  const float *lo = reinterpret_cast<const float *>(rec + 16);
+  const char *occ = reinterpret_cast<const char *>(rec + 16 + (size_t)P.cells * 4);
+  const char *inf = occ + P.cells;
+  const size_t dst = (size_t)block * P.cell_stride;
+  for (int c = threadIdx.x; c < P.cells; c += blockDim.x) {
+    D.pool_lo[dst + c] = lo[c];
+    D.pool_occ[dst + c] = occ[c];
+    D.pool_inf[dst + c] = inf[c];
+  }
+}
+
 }  // namespace mlm

@@ -93,3 +93,47 @@ class ShardedMLMap:
 
     def close(self):
         self.map.close()
+
+
+class ReplicatedMLMap:
+    """One map updated on `src` rank and replicated on the others for split query streams: after each
+    frame the dirty subbox blocks (those the frame touched) are broadcast and applied on the replicas."""
+
+    def __init__(self, cfg: MlmConfig, rank: int = 0, world: int = 1, src: int = 0, device: int | None = None):
+        import torch
+
+        self.torch = torch
+        self.rank, self.world, self.src = rank, world, src
+        self.map = MLMap(cfg, device=rank if device is None else device)
+        self.dev = torch.device("cuda", rank if device is None else device)
+        self.last = {}
+
+    def integrate_depth(self, img, T_wb):
+        """call on every rank; only `src` needs the real image"""
+        torch, m, lib = self.torch, self.map, self.map._lib
+        st = None
+        n, rb = C.c_int32(0), C.c_size_t(0)
+        if self.rank == self.src:
+            st = m.integrate_depth(img, T_wb)
+            m._check(lib.mlm_dirty_count(m._h, C.byref(n), C.byref(rb)))
+        if self.world > 1:
+            import torch.distributed as dist
+            meta = torch.tensor([n.value, rb.value], dtype=torch.int64, device=self.dev)
+            dist.broadcast(meta, src=self.src)
+            nb, rbytes = int(meta[0]), int(meta[1])
+        else:
+            nb, rbytes = n.value, rb.value
+        buf = torch.empty(max(nb * rbytes, 16), dtype=torch.uint8, device=self.dev)
+        if self.rank == self.src:
+            m._check(lib.mlm_dirty_export(m._h, buf.data_ptr(), nb))
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.broadcast(buf, src=self.src)
+            torch.cuda.synchronize(self.dev)
+        if self.rank != self.src:
+            m._check(lib.mlm_dirty_import(m._h, buf.data_ptr(), nb))
+        self.last = {"dirty_blocks": nb, "broadcast_bytes": nb * rbytes}
+        return st
+
+    def import_from(self, buf_ptr: int, nb: int):
+        self.map._check(self.map._lib.mlm_dirty_import(self.map._h, buf_ptr, nb))

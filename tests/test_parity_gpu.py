@@ -318,3 +318,43 @@ def test_sharded_map_two_gpus_matches_oracle():
                           "--master-addr", "127.0.0.1", "--master-port", "29533", script], capture_output=True, text=True,
                          timeout=600)
     assert res.returncode == 0 and '"sharded_check": "ok"' in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+
+
+def test_replicated_map_dirty_block_shipping_single_gpu():
+    """replica kept coherent by shipping the subbox blocks each frame touched (two handles on one GPU stand in
+    for two ranks; the NCCL broadcast in between is exercised by tests/multi_gpu/replicated_check.py)"""
+    import ctypes as C
+    cfg = config_cfg_a()
+    owner, replica, orc = MLMap(cfg), MLMap(cfg), Oracle(cfg)
+    lib = owner._lib
+    for k in range(6):
+        pose = scenes.corridor_trajectory_pose(k * 15)
+        img = scenes.corridor_depth_frame(cfg, pose, frame_idx=k)
+        owner.integrate_depth(img, pose)
+        orc.integrate_depth(img, pose)
+        n, rb = C.c_int32(), C.c_size_t()
+        owner._check(lib.mlm_dirty_count(owner._h, C.byref(n), C.byref(rb)))
+        assert n.value > 0 and rb.value == 6016
+        buf = owner.device_alloc(n.value * rb.value)
+        owner._check(lib.mlm_dirty_export(owner._h, buf, n.value))
+        replica._check(lib.mlm_dirty_import(replica._h, buf, n.value))
+        owner.device_free(buf)
+    assert_map_parity(replica, orc, LO_TOL, tag="replica")
+    m = orc.export_map()
+    pos = scenes.query_positions(100000, m["glb"].min(0) * 1.0, (m["glb"].max(0) + 1) * 1.0, seed=3, inflate=2.0)
+    assert np.array_equal(replica.getOccupancy(pos), orc.getOccupancy(pos))
+    assert np.array_equal(replica.getOddGrad(pos[:20000]), owner.getOddGrad(pos[:20000]))
+
+
+def test_replicated_map_two_gpus_matches_oracle():
+    """dirty-block broadcast over NCCL + split query stream on 2 ranks.  Skipped on a single-GPU box."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = str(__import__("pathlib").Path(__file__).resolve().parent / "multi_gpu" / "replicated_check.py")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29537", script], capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0 and '"replicated_check": "ok"' in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
