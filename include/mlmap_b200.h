@@ -225,6 +225,12 @@ int mlm_export_frontier(mlm_handle h, size_t cap_submaps, int32_t *glb3, uint32_
  * Each rank then holds the subboxes it owns; the union over ranks equals the single-GPU map bit for bit. */
 int mlm_shard_stage_points_f64(mlm_handle h, const double *xyz, int n, const double T_wb[7], int rank, int world,
                                int32_t *n_hit_local, int32_t *n_miss_local);
+int mlm_shard_stage_points_f64_device(mlm_handle h, const double *d_xyz, int n, const double T_wb[7], int rank, int world,
+                                      int32_t *n_hit_local, int32_t *n_miss_local);
+/* frames without a rehash (sum of the ranks' hit counts <= bucket count): min-all-reduce the activation stamps
+ * (unsigned compare) instead of steps 2-3, then mlm_shard_order_fast; the stamps travel inside the records */
+int mlm_shard_act_buffer(mlm_handle h, void **d_act, uint32_t *bucket_count);
+int mlm_shard_order_fast(mlm_handle h, int n_total);
 int mlm_shard_copy_hit_keys(mlm_handle h, int32_t *d_keys_out, uint32_t *d_stamps_out);
 int mlm_shard_order(mlm_handle h, const int32_t *d_keys_all, uint32_t *d_stamps_all, int n_total);
 int mlm_shard_emit_counts(mlm_handle h, int world, int32_t *counts);

@@ -109,7 +109,7 @@ ABI_SYMBOLS = [
     "mlm_last_frame_hits", "mlm_last_frame_misses", "mlm_export_map_count", "mlm_export_map",
     "mlm_debug_log10f", "mlm_set_profiling", "mlm_last_frame_kernel_ms", "mlm_sizeof_config",
     "mlm_sizeof_frame_stats", "mlm_debug_phase_cycles", "mlm_host_alloc", "mlm_host_free", "mlm_srand", "mlm_debug_rand", "mlm_export_frontier", "mlm_shard_stage_points_f64",
-    "mlm_shard_copy_hit_keys", "mlm_shard_order", "mlm_shard_emit_counts", "mlm_shard_emit_pack", "mlm_shard_ingest", "mlm_dirty_count", "mlm_dirty_export", "mlm_dirty_import",
+    "mlm_shard_copy_hit_keys", "mlm_shard_stage_points_f64_device", "mlm_shard_act_buffer", "mlm_shard_order_fast", "mlm_shard_order", "mlm_shard_emit_counts", "mlm_shard_emit_pack", "mlm_shard_ingest", "mlm_dirty_count", "mlm_dirty_export", "mlm_dirty_import",
 ]
 FRAME_KERNELS = ["k_project", "k_column", "k_fuse"]
 
@@ -182,6 +182,9 @@ def load_library() -> C.CDLL:
         "mlm_export_frontier": ([vp, sz, vp, vp, C.POINTER(sz)], C.c_int),
         "mlm_shard_stage_points_f64": ([vp, vp, C.c_int, dp, C.c_int, C.c_int, ip, ip], C.c_int),
         "mlm_shard_copy_hit_keys": ([vp, vp, vp], C.c_int),
+        "mlm_shard_stage_points_f64_device": ([vp, vp, C.c_int, dp, C.c_int, C.c_int, ip, ip], C.c_int),
+        "mlm_shard_act_buffer": ([vp, C.POINTER(vp), C.POINTER(C.c_uint32)], C.c_int),
+        "mlm_shard_order_fast": ([vp, C.c_int], C.c_int),
         "mlm_shard_order": ([vp, vp, vp, C.c_int], C.c_int),
         "mlm_shard_emit_counts": ([vp, C.c_int, vp], C.c_int),
         "mlm_shard_emit_pack": ([vp, C.c_int, vp, vp], C.c_int),

@@ -175,6 +175,7 @@ struct mlm_map {
   int *d_shard_cnt = nullptr;        // [3*64] counts / bases / cursors per destination
   int shard_world = 1, shard_rank = 0;
   int shard_n_local = 0;
+  bool shard_record_stamps = false;  // ingest takes the stamps from the records (no-rehash frame)
   bool shard_stage_pending = false;
   cudaGraphExec_t graph_exec[3] = {nullptr, nullptr, nullptr};  // by input mode: points, depth image, sampled pixels
   cudaGraph_t graph[3] = {nullptr, nullptr, nullptr};
@@ -1465,29 +1466,13 @@ int mlm_export_frontier(mlm_handle h, size_t cap_submaps, int32_t *glb3, uint32_
 }
 
 // ---- sharded map: stage / order / emit / ingest; collectives are the caller's (NCCL via torch.distributed)
-int mlm_shard_stage_points_f64(mlm_handle h, const double *xyz, int n, const double T_wb[7], int rank, int world,
-                               int32_t *n_hit_local, int32_t *n_miss_local) {
-  if (!h || (!xyz && n > 0) || !T_wb || n < 0 || world < 1 || world > 64 || rank < 0 || rank >= world) return MLM_ERR_INVALID_ARG;
-  if (h->P.explore || n > h->P.max_points) return n > h->P.max_points ? MLM_ERR_CAPACITY : MLM_ERR_UNSUPPORTED;
-  CUDA_TRY(cudaSetDevice(h->device));
-  if (!h->d_key_stamp) {
-    const size_t cells = (size_t)h->P.nZ * h->P.nPhi * h->P.nRho;
-    CUDA_TRY(cudaMalloc((void **)&h->d_key_stamp, cells * sizeof(uint32_t)));
-    CUDA_TRY(cudaMalloc((void **)&h->d_shard_cnt, 3 * 64 * sizeof(int)));
-    h->allocs.push_back(h->d_key_stamp);
-    h->allocs.push_back(h->d_shard_cnt);
-  }
-  const size_t bytes = (size_t)std::max(n, 1) * 24;
-  int rc = ensure_input(h, bytes, (size_t)h->P.max_points * 24);
-  if (rc != MLM_OK) return rc;
-  if (n > 0) {
-    memcpy(h->h_stage, xyz, (size_t)n * 24);
-    CUDA_TRY(cudaMemcpyAsync(h->d_input, h->h_stage, (size_t)n * 24, cudaMemcpyHostToDevice, h->stream));
-  }
+namespace {
+int shard_stage_common(mlm_handle h, const double *d_xyz, int n, const double T_wb[7], int rank, int world,
+                       int32_t *n_hit_local, int32_t *n_miss_local) {
   h->shard_rank = rank;
   h->shard_world = world;
   h->shard_stage_pending = true;
-  rc = run_frame(h, 0, h->d_input, 0, 0, n, T_wb, nullptr);
+  int rc = run_frame(h, 0, d_xyz, 0, 0, n, T_wb, nullptr);
   h->shard_stage_pending = false;
   if (rc != MLM_OK) return rc;
   if (h->h_fc->error) return map_device_error(h->h_fc->error);
@@ -1495,6 +1480,51 @@ int mlm_shard_stage_points_f64(mlm_handle h, const double *xyz, int n, const dou
   if (n_hit_local) *n_hit_local = h->h_fc->n_hit;
   if (n_miss_local) *n_miss_local = h->h_fc->n_miss;
   return MLM_OK;
+}
+int shard_prepare(mlm_handle h) {
+  if (!h->d_key_stamp) {
+    const size_t cells = (size_t)h->P.nZ * h->P.nPhi * h->P.nRho;
+    CUDA_TRY(cudaMalloc((void **)&h->d_key_stamp, cells * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc((void **)&h->d_shard_cnt, 3 * 64 * sizeof(int)));
+    h->allocs.push_back(h->d_key_stamp);
+    h->allocs.push_back(h->d_shard_cnt);
+  }
+  return MLM_OK;
+}
+}  // namespace
+
+int mlm_shard_stage_points_f64_device(mlm_handle h, const double *d_xyz, int n, const double T_wb[7], int rank, int world,
+                                      int32_t *n_hit_local, int32_t *n_miss_local) {
+  if (!h || (!d_xyz && n > 0) || !T_wb || n < 0 || world < 1 || world > 64 || rank < 0 || rank >= world) return MLM_ERR_INVALID_ARG;
+  if (h->P.explore || n > h->P.max_points) return n > h->P.max_points ? MLM_ERR_CAPACITY : MLM_ERR_UNSUPPORTED;
+  CUDA_TRY(cudaSetDevice(h->device));
+  int rc = shard_prepare(h);
+  if (rc != MLM_OK) return rc;
+  return shard_stage_common(h, d_xyz, n, T_wb, rank, world, n_hit_local, n_miss_local);
+}
+
+int mlm_shard_stage_points_f64(mlm_handle h, const double *xyz, int n, const double T_wb[7], int rank, int world,
+                               int32_t *n_hit_local, int32_t *n_miss_local) {
+  if (!h || (!xyz && n > 0) || !T_wb || n < 0 || world < 1 || world > 64 || rank < 0 || rank >= world) return MLM_ERR_INVALID_ARG;
+  if (h->P.explore || n > h->P.max_points) return n > h->P.max_points ? MLM_ERR_CAPACITY : MLM_ERR_UNSUPPORTED;
+  CUDA_TRY(cudaSetDevice(h->device));
+  int rc = shard_prepare(h);
+  if (rc != MLM_OK) return rc;
+  const size_t bytes = (size_t)std::max(n, 1) * 24;
+  rc = ensure_input(h, bytes, (size_t)h->P.max_points * 24);
+  if (rc != MLM_OK) return rc;
+  if (n > 0) {
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, xyz) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const void *src = xyz;
+    if (!pinned) {
+      memcpy(h->h_stage, xyz, (size_t)n * 24);
+      src = h->h_stage;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_input, src, (size_t)n * 24, cudaMemcpyHostToDevice, h->stream));
+  }
+  return shard_stage_common(h, reinterpret_cast<const double *>(h->d_input), n, T_wb, rank, world, n_hit_local, n_miss_local);
 }
 
 // copies the rank's distinct hit keys and first-insert stamps (n_hit_local each) into caller device buffers
@@ -1562,6 +1592,24 @@ int mlm_shard_order(mlm_handle h, const int32_t *d_keys_all, uint32_t *d_stamps_
   h->bucket_count = B;
   h->last_order_B = B;
   h->h_fp->bucket_count = B;
+  h->shard_record_stamps = false;
+  return MLM_OK;
+}
+
+// No-rehash frames need no key gather: every key is cast by exactly one rank, so its stamp travels in its
+// record and only the bucket activation stamps must be combined: the caller min-all-reduces the array returned
+// here (B uint32 words; compare as unsigned) and then calls mlm_shard_order_fast.
+int mlm_shard_act_buffer(mlm_handle h, void **d_act, uint32_t *bucket_count) {
+  if (!h || !d_act || !bucket_count) return MLM_ERR_INVALID_ARG;
+  *d_act = h->D.act[h->last_parity];
+  *bucket_count = h->bucket_count;
+  return MLM_OK;
+}
+int mlm_shard_order_fast(mlm_handle h, int n_total) {
+  if (!h || n_total < 0 || h->bucket_count <= 1 || (uint32_t)n_total > h->bucket_count) return MLM_ERR_INVALID_ARG;
+  h->shard_record_stamps = true;
+  h->last_order_B = h->bucket_count;
+  h->h_fp->bucket_count = h->bucket_count;
   return MLM_OK;
 }
 
@@ -1607,7 +1655,7 @@ int mlm_shard_ingest(mlm_handle h, const void *d_records, int n, mlm_frame_stats
   F.shard_world = 1;
   if (n > 0)
     k_shard_ingest<<<grid_for(n, 256), 256, 0, s>>>(h->P, h->D, F, reinterpret_cast<const ShardRecord *>(d_records), n,
-                                                    h->d_key_stamp);
+                                                    h->shard_record_stamps ? nullptr : h->d_key_stamp);
   k_shard_resolve<<<1, 1024, 0, s>>>(h->P, h->D, F);
   k_fuse<0><<<h->sm_count * 4, 256, 0, s>>>(h->P, h->D, F);
   h->launches += 3;

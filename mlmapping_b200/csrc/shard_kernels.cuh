@@ -16,7 +16,7 @@ struct __align__(8) ShardRecord {  // 24 bytes
   int c[3];     // canonical global cell coordinate of the voxel
   int key;      // awareness cell index of a hit key, or -1 for a miss record
   float p;      // hit: folded probability
-  int count;    // miss: number of miss cells mapping to the voxel
+  int count;    // miss: number of miss cells mapping to the voxel; hit: first-insert stamp of the key
 };
 
 __device__ __forceinline__ int owner_of(const MapParams &P, const int c[3], int world) {
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) k_shard_emit(MapParams P, DeviceBuffers D
       r.c[2] = c[2];
       r.key = D.hit_key[h];
       r.p = D.hit_p[h];
-      r.count = 0;
+      r.count = (int)D.hit_t[h];  // every key is cast by exactly one rank, so its stamp travels with it
       *o++ = r;
     }
     if (mc > 0) {
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) k_shard_ingest(MapParams P, DeviceBuffers
     }
     D.hit_key[idx] = r.key;
     D.hit_p[idx] = r.p;
-    D.hit_t[idx] = key_stamp[r.key];
+    D.hit_t[idx] = key_stamp ? key_stamp[r.key] : (uint32_t)r.count;  // rehash frames: virtual position from the global order
     D.hit_bucket[idx] = cell_bucket(P, r.key, F.bucket_count, 0);
     const int old = atomicExch(&D.lvg[lv].x, idx);
     D.hit_next[idx] = old;

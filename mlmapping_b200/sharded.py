@@ -14,6 +14,13 @@ import numpy as np
 from .capi import FrameStats, MLMap, MlmConfig, _pose7
 
 
+class _DevArray:
+    """zero-copy view of library-owned device memory for torch (CUDA array interface, int32)"""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+
+
 class ShardedMLMap:
     RECORD_INTS = 6  # 24-byte ShardRecord
 
@@ -25,6 +32,8 @@ class ShardedMLMap:
         self.map = MLMap(cfg, device=rank if device is None else device)
         self.dev = torch.device("cuda", rank if device is None else device)
         self.last = {}
+        self._pinned = None
+        self._views = {}
 
     def _dist(self):
         import torch.distributed as dist
@@ -33,42 +42,79 @@ class ShardedMLMap:
     def integrate_points(self, xyz: np.ndarray, T_wb) -> FrameStats:
         torch, m, lib = self.torch, self.map, self.map._lib
         dist = self._dist()
+        import time
+        tm = {}
+        t_prev = time.perf_counter()
+
+        def lap(name):
+            nonlocal t_prev
+            torch.cuda.synchronize(self.dev)
+            now = time.perf_counter()
+            tm[name] = round(1e6 * (now - t_prev), 1)
+            t_prev = now
         pts = np.ascontiguousarray(np.asarray(xyz, dtype=np.float64).reshape(-1, 3))
+        if self._pinned is None or self._pinned.shape[0] < pts.shape[0]:
+            self._pinned = m.pinned_array((max(pts.shape[0], self.map.cfg.max_points), 3), np.float64)
+        self._pinned[:pts.shape[0]] = pts  # page-locked staging: the H2D copy runs without a second host copy
+        pts = self._pinned[:pts.shape[0]]
         n_hit, n_miss = C.c_int32(), C.c_int32()
         m._check(lib.mlm_shard_stage_points_f64(m._h, pts.ctypes.data, pts.shape[0], _pose7(T_wb), self.rank, self.world,
                                                 C.byref(n_hit), C.byref(n_miss)))
-        # ---- exchange 1: all-gather of the distinct hit keys + first-insert stamps ----
-        keys = torch.empty(max(n_hit.value, 1), dtype=torch.int32, device=self.dev)
-        stamps = torch.empty(max(n_hit.value, 1), dtype=torch.int32, device=self.dev)
-        m._check(lib.mlm_shard_copy_hit_keys(m._h, keys.data_ptr(), stamps.data_ptr()))
+        lap("stage_us")
+        # ---- exchange 1: make the hit-map iteration order global ----
+        n_total, fast = n_hit.value, False
         if dist:
-            cnt = torch.tensor([n_hit.value], dtype=torch.int64, device=self.dev)
-            all_cnt = torch.empty(self.world, dtype=torch.int64, device=self.dev)
-            dist.all_gather_into_tensor(all_cnt, cnt)
-            sizes = all_cnt.tolist()
-            mx = max(max(sizes), 1)
-            pad_k = torch.zeros(mx, dtype=torch.int32, device=self.dev)
-            pad_s = torch.zeros(mx, dtype=torch.int32, device=self.dev)
-            pad_k[:n_hit.value] = keys[:n_hit.value]
-            pad_s[:n_hit.value] = stamps[:n_hit.value]
-            gk = torch.empty(self.world * mx, dtype=torch.int32, device=self.dev)
-            gs = torch.empty(self.world * mx, dtype=torch.int32, device=self.dev)
-            dist.all_gather_into_tensor(gk, pad_k)
-            dist.all_gather_into_tensor(gs, pad_s)
-            keys_all = torch.cat([gk[r * mx:r * mx + sizes[r]] for r in range(self.world)]).contiguous()
-            stamps_all = torch.cat([gs[r * mx:r * mx + sizes[r]] for r in range(self.world)]).contiguous()
+            tot = torch.tensor([n_hit.value], dtype=torch.int64, device=self.dev)
+            dist.all_reduce(tot)
+            n_total = int(tot.item())
+        act_ptr, B = C.c_void_p(), C.c_uint32()
+        m._check(lib.mlm_shard_act_buffer(m._h, C.byref(act_ptr), C.byref(B)))
+        if B.value > 1 and n_total <= B.value:
+            # no rehash this frame: a key is cast by exactly one rank, so its stamp travels in its record and only
+            # the bucket activation stamps need a min-all-reduce (unsigned order == int32 order after flipping bit 31)
+            fast = True
+            if dist:
+                vk = (act_ptr.value, B.value)
+                act = self._views.get(vk)
+                if act is None:  # zero-copy torch view of the library's stamp array (one per parity / bucket count)
+                    act = self._views[vk] = torch.as_tensor(_DevArray(act_ptr.value, B.value), device=self.dev)
+                act.bitwise_xor_(-2 ** 31)
+                dist.all_reduce(act, op=dist.ReduceOp.MIN)
+                act.bitwise_xor_(-2 ** 31)
+            lap("allgather_us")
+            m._check(lib.mlm_shard_order_fast(m._h, n_total))
         else:
-            keys_all, stamps_all = keys[:n_hit.value].contiguous(), stamps[:n_hit.value].contiguous()
-        n_total = int(keys_all.numel())
-        torch.cuda.synchronize(self.dev)
-        m._check(lib.mlm_shard_order(m._h, keys_all.data_ptr() if n_total else None,
-                                     stamps_all.data_ptr() if n_total else None, n_total))
+            # rehash frame (map start / growth): gather every rank's (key, stamp) list; each rank re-sequences it
+            keys = torch.empty(max(n_hit.value, 1), dtype=torch.int32, device=self.dev)
+            stamps = torch.empty(max(n_hit.value, 1), dtype=torch.int32, device=self.dev)
+            m._check(lib.mlm_shard_copy_hit_keys(m._h, keys.data_ptr(), stamps.data_ptr()))
+            if dist:
+                cnt = torch.tensor([n_hit.value], dtype=torch.int64, device=self.dev)
+                all_cnt = torch.empty(self.world, dtype=torch.int64, device=self.dev)
+                dist.all_gather_into_tensor(all_cnt, cnt)
+                sizes = all_cnt.tolist()
+                mx = max(max(sizes), 1)
+                pad = torch.zeros((2, mx), dtype=torch.int32, device=self.dev)
+                pad[0, :n_hit.value] = keys[:n_hit.value]
+                pad[1, :n_hit.value] = stamps[:n_hit.value]
+                g = torch.empty((self.world, 2, mx), dtype=torch.int32, device=self.dev)
+                dist.all_gather_into_tensor(g, pad)
+                keys_all = torch.cat([g[r, 0, :sizes[r]] for r in range(self.world)]).contiguous()
+                stamps_all = torch.cat([g[r, 1, :sizes[r]] for r in range(self.world)]).contiguous()
+            else:
+                keys_all, stamps_all = keys[:n_hit.value].contiguous(), stamps[:n_hit.value].contiguous()
+            assert int(keys_all.numel()) == n_total
+            lap("allgather_us")
+            m._check(lib.mlm_shard_order(m._h, keys_all.data_ptr() if n_total else None,
+                                         stamps_all.data_ptr() if n_total else None, n_total))
+        lap("order_us")
         # ---- exchange 2: all-to-all of the per-voxel update records, grouped by owner ----
         send_counts = (C.c_int32 * self.world)()
         m._check(lib.mlm_shard_emit_counts(m._h, self.world, send_counts))
         sc = [int(v) for v in send_counts]
         send = torch.empty((max(sum(sc), 1), self.RECORD_INTS), dtype=torch.int32, device=self.dev)
         m._check(lib.mlm_shard_emit_pack(m._h, self.world, send_counts, send.data_ptr()))
+        lap("emit_us")
         if dist:
             sct = torch.tensor(sc, dtype=torch.int64, device=self.dev)
             rct = torch.empty(self.world, dtype=torch.int64, device=self.dev)
@@ -79,12 +125,13 @@ class ShardedMLMap:
             n_recv = sum(rc)
         else:
             recv, n_recv = send, sum(sc)
-        torch.cuda.synchronize(self.dev)
+        lap("alltoall_us")
         st = FrameStats()
         m._check(lib.mlm_shard_ingest(m._h, recv.data_ptr() if n_recv else None, n_recv, C.byref(st)))
-        self.last = {"n_hit_local": n_hit.value, "n_hit_total": n_total, "n_miss_local": n_miss.value,
+        lap("ingest_us")
+        self.last = {"timing": tm, "fast_order": fast, "n_hit_local": n_hit.value, "n_hit_total": n_total, "n_miss_local": n_miss.value,
                      "records_sent": sum(sc), "records_received": n_recv,
-                     "a2a_bytes": 24 * sum(sc), "allgather_bytes": 8 * n_total}
+                     "a2a_bytes": 24 * sum(sc), "order_exchange_bytes": 4 * B.value if fast else 8 * n_total}
         return st
 
     # queries / exports act on the subboxes this rank owns

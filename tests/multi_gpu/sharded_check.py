@@ -25,6 +25,8 @@ def main():
     full = "--full" in sys.argv
     cfg = config_cfg_c()
     beams, az, scans = (128, 2048, 3) if full else (32, 512, 4)
+    if "--scans" in sys.argv:
+        scans = int(sys.argv[sys.argv.index("--scans") + 1])
     if not full:
         cfg.am_n_rho, cfg.am_n_z_below, cfg.am_n_z_over = 120, 30, 30
         cfg.max_points = 32 * 512
@@ -65,7 +67,9 @@ def main():
             assert same, name
         print(json.dumps({"sharded_check": "ok", "world": world, "subboxes": int(glb.shape[0]),
                           "owned_per_rank": [int(g["glb"].shape[0]) for g in gathered],
-                          "ms_per_scan": [round(1e3 * t, 3) for t in times], "last": sh.last}))
+                          "ms_per_scan": [round(1e3 * t, 3) for t in times],
+                          "median_ms_after_warmup": round(1e3 * float(np.median(times[2:])), 3) if len(times) > 3 else None,
+                          "last": sh.last}))
     dist.barrier()
     dist.destroy_process_group()
     return 0 if ok else 1
