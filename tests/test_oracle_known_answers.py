@@ -184,3 +184,82 @@ def test_set_free_and_grad():
     assert np.all(after["occupancy"][changed] == b"f") and np.all(after["log_odds"][changed] == 0.0)
     g = o.getOddGrad([[100.0, 100.0, 100.0]])
     assert np.all(g == 0.0)   # unknown space everywhere: no lower neighbour -> zero vector (mlmap.h:293)
+
+
+def test_inflate_map_known_answer():
+    """one occupied cell in the middle of a subbox -> L1 ball of radius inflate_n in inflate_occupancy
+    (src/mlmap.cpp:286-309, include/map_local.h:233-264); cells at or below flate_height do not inflate"""
+    cfg = config_cfg_a()
+    cfg.inflate_n, cfg.inflate_global_n, cfg.inflate_height = 2, 1, 0.1
+    o = Oracle(cfg)
+    img = np.zeros((480, 640), dtype=np.uint16)
+    img[240, 320] = 1000
+    pose = scenes.pose_from_xyz_yaw(5.0, 0.0, 1.2, 0.0)
+    o.integrate_depth(img, pose)
+    o.integrate_depth(img, pose)          # second hit clamps to 4.2 and turns the cell 'o'
+    m = o.export_map()
+    assert (m["occupancy"] == b"o").sum() == 1 and (m["inflate"] == b"o").sum() == 0
+    o.inflate_map(pose[:3])
+    m = o.export_map()
+    assert (m["inflate"] == b"o").sum() == 25   # |dx|+|dy|+|dz| <= 2 has 25 lattice points
+    assert o.getInflateOccupancy([[6.15, 0.02, 1.25]])[0] == 0      # the occupied voxel itself (OCCUPIED)
+    assert o.getInflateOccupancy([[6.15, 0.02, 1.55]])[0] == -1     # 3 cells above: outside the ball
+    # the same scene 1.2 m lower: the hit cell centre is at z = 0.05 <= flate_height -> no inflation
+    o2 = Oracle(cfg)
+    low = scenes.pose_from_xyz_yaw(5.0, 0.0, 0.0, 0.0)
+    o2.integrate_depth(img, low)
+    o2.integrate_depth(img, low)
+    o2.inflate_map(low[:3])
+    assert (o2.export_map()["inflate"] == b"o").sum() == 0
+
+
+def test_exploration_frontier_known_answer():
+    """one free cell in unknown space inside the exploration bounds: update_observation puts exactly one
+    frontier cell on the first 'u' neighbour in the order +z,-z,+y,-y,+x,-x (src/map_local.cpp:7-33,78-83)"""
+    cfg = config_cfg_a()
+    cfg.use_exploration_frontiers = 1
+    o = Oracle(cfg)
+    img = np.zeros((480, 640), dtype=np.uint16)
+    img[240, 320] = 300                    # hit at rho 4 (0.42 m): the walk frees rho 3..1 along phi 0
+    pose = scenes.pose_from_xyz_yaw(5.0, 0.0, 1.2, 0.0)
+    st = o.integrate_depth(img, pose)
+    m = o.export_map()
+    n_free = int((m["occupancy"] == b"f").sum())
+    n_front = int(np.unpackbits(m["frontier"]).sum())
+    assert n_free == 3
+    assert 1 <= n_front <= 3               # every freed cell nominates its +z neighbour (still 'u')
+    # frontier cells are 'u' cells
+    bits = np.unpackbits(m["frontier"], axis=1, bitorder="little")[:, :1000].astype(bool)
+    assert np.all(m["occupancy"][bits] == b"u")
+    # outside the hard-coded bounds {-30,30,-30,30,0,5} nothing is observed
+    o2 = Oracle(cfg)
+    far = scenes.pose_from_xyz_yaw(100.0, 0.0, 1.2, 0.0)
+    o2.integrate_depth(img, far)
+    assert np.unpackbits(o2.export_map()["frontier"]).sum() == 0
+
+
+def test_sampled_projection_uses_libc_rand_stream():
+    """mlmapping_sample_cnt > 0: v = rand() % rows, u = rand() % cols, up to 2*cnt draws (src/mlmap.cpp:321-326)"""
+    import ctypes as C
+    cfg = config_cfg_a()
+    cfg.sample_cnt = 50
+    libc = C.CDLL("libc.so.6")
+    img = np.full((480, 640), 2000, dtype=np.uint16)
+    pose = scenes.pose_from_xyz_yaw(5.0, 0.0, 1.2, 0.0)
+    libc.srand(1)
+    o = Oracle(cfg)
+    st = o.integrate_depth(img, pose)
+    assert st.n_points == 50
+    pts = o.points()
+    libc.srand(1)
+    seq = [libc.rand() for _ in range(100)]
+    v0, u0 = seq[0] % 480, seq[1] % 640
+    fx = np.float32(347.99755859375)
+    assert pts[0, 2] == 2000 * (1.0 / 1000.0)
+    assert pts[0, 0] == float(np.float32(u0) - np.float32(320.0)) * pts[0, 2] / float(fx)
+    assert pts[0, 1] == float(np.float32(v0) - np.float32(240.0)) * pts[0, 2] / float(fx)
+    # three quarters of the image invalid: fewer than cnt points after 2*cnt draws
+    img[:, ::2] = 0
+    img[::2, :] = 0
+    st = o.integrate_depth(img, pose)
+    assert st.n_points < 50
