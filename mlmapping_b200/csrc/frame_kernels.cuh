@@ -258,121 +258,172 @@ __device__ __forceinline__ int block_exclusive_scan(int *data, int n, int *s_war
 
 // kMode: 0 = sensor-frame points (xyz doubles), 1 = full depth image (every pixel, row-major),
 //        2 = sampled depth pixels: input is uint2 {pixel index, raw depth} in sampling order (src/mlmap.cpp:321-346)
+// One CTA owns a tile of kProjTile consecutive points; warp w owns the 32*kProjPts consecutive points
+// of the tile and visits them in kProjPts rounds of 32 (64-byte depth-row loads),
+// so "point order" inside the tile is (warp, round, lane) and everything that has to follow point order is
+// warp-local except one exclusive scan over the 8 warps.
+constexpr int kProjThreads = 512;
+constexpr int kProjWarps = kProjThreads / 32;
+constexpr int kProjPts = 2;                          // points per thread
+constexpr int kProjTile = kProjThreads * kProjPts;   // points per CTA = slots of its rec_lin window
+__host__ __device__ inline size_t project_smem_bytes(int nPhi) { return (size_t)(kProjWarps + 3) * nPhi * sizeof(int); }
+
+// work column of a record: its phi column, or (phi, side) when the columns are split at the sensor row
+__device__ __forceinline__ int work_column(const MapParams &P, const RayRecord &rc) {
+  const int phi = (int)(rc.phi_flags & kRecPhiMask);
+  return P.split ? (phi << 1) | (rc.z >= P.n_below ? 1 : 0) : phi;
+}
+
 template <int kMode>
-__global__ void __launch_bounds__(256) k_project(MapParams P, DeviceBuffers D, FrameParams F) {
-  extern __shared__ int s_hist[];  // [nPhi] counts, [nPhi] offsets, [nPhi] contribution bounds
+__global__ void __launch_bounds__(kProjThreads) k_project(MapParams P, DeviceBuffers D, FrameParams F) {
+  extern __shared__ int s_proj[];  // [warps][nCol] per-warp counts -> exclusive prefix over warps, [nCol] totals, [nCol] offsets, [nCol] contribution bounds
   __shared__ int s_cnt[3];
   __shared__ int s_warp[33];
-  int *s_bnd = s_hist + 2 * P.nPhi;
-  for (int i = threadIdx.x; i < P.nPhi; i += blockDim.x) {
-    s_hist[i] = 0;
-    s_bnd[i] = 0;
-  }
-  if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
-  __syncthreads();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nPhi = P.nCol;  // work columns: phi, or (phi, side of the sensor row) when the columns are split
+  int *s_hist = s_proj + kProjWarps * nPhi;
+  int *s_off = s_hist + nPhi;
+  int *s_bnd = s_off + nPhi;
   const int N = F.n_total;
-  if (blockIdx.x * blockDim.x >= N) return;  // the grid is sized for cfg.max_points (graph replay)
+  const int tile0 = blockIdx.x * kProjTile;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (P.split && blockIdx.x == 0) {
+    // the one miss-bitmap row both half columns of a phi write (atomicOr in k_column) starts the frame empty
+    for (int i = tid; i < P.nPhi * P.words_per_row; i += kProjThreads) {
+      const int ph = i / P.words_per_row;
+      D.miss_bitmap[(size_t)ph * P.col_words + P.n_below * P.words_per_row + (i - ph * P.words_per_row)] = 0;
+    }
+  }
+  if (tile0 >= N) return;  // the grid is sized for cfg.max_points (graph replay)
+  for (int i = tid; i < kProjWarps * nPhi; i += kProjThreads) s_proj[i] = 0;
+  for (int i = tid; i < nPhi; i += kProjThreads) s_bnd[i] = 0;
+  if (tid < 3) s_cnt[tid] = 0;
   const void *input = F.input;
   const int cols = F.cols;
-  RayRecord rec;
-  rec.rho = 0;
-  rec.z = 0;
-  rec.t = 0;
-  rec.phi_flags = 0xffffffffu;
-  int valid = 0, inside = 0, cast = 0, rank = 0;
-  if (i < N) {
-    double xs, ys, zs;
-    if (kMode != 0) {
-      // project_depth, src/mlmap.cpp:329-346 (kMode 1: every pixel, v outer / u inner; kMode 2: the sampled pixels)
-      int pix = i;
-      uint16_t raw;
-      if (kMode == 1) {
-        raw = __ldg(reinterpret_cast<const uint16_t *>(input) + i);
+  const int warp0 = tile0 + warp * (32 * kProjPts);
+  // ---- the points of this thread: projection, transform, cylindrical index (independent chains) ----
+  RayRecord rec[kProjPts];
+  int n_valid = 0, n_inside = 0, n_cast = 0;
+#pragma unroll
+  for (int j = 0; j < kProjPts; j++) {
+    const int i = warp0 + j * 32 + lane;
+    rec[j].rho = 0;
+    rec[j].z = 0;
+    rec[j].t = (uint32_t)i;
+    rec[j].phi_flags = 0xffffffffu;
+    if (i < N) {
+      double xs = 0, ys = 0, zs = 0;
+      bool valid = false;
+      if (kMode != 0) {
+        // project_depth, src/mlmap.cpp:329-346 (kMode 1: every pixel, v outer / u inner; kMode 2: the sampled pixels)
+        int pix = i;
+        uint16_t raw;
+        if (kMode == 1) {
+          raw = __ldg(reinterpret_cast<const uint16_t *>(input) + i);
+        } else {
+          const uint2 sp = __ldg(reinterpret_cast<const uint2 *>(input) + i);
+          pix = (int)sp.x;
+          raw = (uint16_t)sp.y;
+        }
+        if (raw != 0) {
+          const int v = pix / cols, u = pix - v * cols;
+          const double depth = (double)(int)raw * P.inv_factor;
+          xs = (double)__fsub_rn((float)u, P.cx) * depth / (double)P.fx;
+          ys = (double)__fsub_rn((float)v, P.cy) * depth / (double)P.fy;
+          zs = depth;
+          valid = true;
+        }
       } else {
-        const uint2 sp = __ldg(reinterpret_cast<const uint2 *>(input) + i);
-        pix = (int)sp.x;
-        raw = (uint16_t)sp.y;
+        const double *xyz = reinterpret_cast<const double *>(input);
+        xs = xyz[3 * (size_t)i];
+        ys = xyz[3 * (size_t)i + 1];
+        zs = xyz[3 * (size_t)i + 2];
+        valid = true;
       }
-      if (raw != 0) {
-        int v = pix / cols, u = pix - v * cols;
-        double depth = (double)(int)raw * P.inv_factor;
-        xs = (double)__fsub_rn((float)u, P.cx) * depth / (double)P.fx;
-        ys = (double)__fsub_rn((float)v, P.cy) * depth / (double)P.fy;
-        zs = depth;
-        valid = 1;
+      if (valid) {
+        int inside = 0, cast = 0;
+        point_to_record(P, F, xs, ys, zs, (uint32_t)i, rec[j], inside, cast);
+        n_valid++;
+        n_inside += inside;
+        n_cast += cast;
       }
-    } else {
-      const double *xyz = reinterpret_cast<const double *>(input);
-      xs = xyz[3 * (size_t)i];
-      ys = xyz[3 * (size_t)i + 1];
-      zs = xyz[3 * (size_t)i + 2];
-      valid = 1;
     }
-    if (valid) point_to_record(P, F, xs, ys, zs, (uint32_t)i, rec, inside, cast);
   }
-  // Run-length merge: consecutive points (in input order) that land in the same awareness cell
-  // contribute the same (key, odd) list back to back, so for every key their contributions are
-  // adjacent in the key's insertion sequence.  One record with a repeat count is therefore exact
-  // for the ordered fold, the first-insert stamps and the (idempotent) ray walk.  Runs are cut at
-  // warp boundaries and at points without a record.
-  {
-    const int lane = lane_id();
-    const bool has = rec.phi_flags != 0xffffffffu;
-    int p_rho = __shfl_up_sync(0xffffffffu, rec.rho, 1);
-    int p_z = __shfl_up_sync(0xffffffffu, rec.z, 1);
-    uint32_t p_pf = __shfl_up_sync(0xffffffffu, rec.phi_flags, 1);
-    const bool same = has && lane > 0 && p_pf == rec.phi_flags && p_rho == rec.rho && p_z == rec.z;
+  __syncthreads();  // shared arrays cleared
+  // ---- run-length merge + stable rank inside the warp's 128 points ----
+  // Consecutive points (in input order) that land in the same awareness cell contribute the same
+  // (key, odd) list back to back, so for every key their contributions are adjacent in the key's
+  // insertion sequence.  One record with a repeat count is therefore exact for the ordered fold, the
+  // first-insert stamps and the (idempotent) ray walk.  Runs are cut at the 32-point rounds and at
+  // points without a record.
+  int *s_mine = s_proj + warp * nPhi;
+  int rank[kProjPts];
+#pragma unroll
+  for (int j = 0; j < kProjPts; j++) {
+    const bool has = rec[j].phi_flags != 0xffffffffu;
+    const int p_rho = __shfl_up_sync(0xffffffffu, rec[j].rho, 1);
+    const int p_z = __shfl_up_sync(0xffffffffu, rec[j].z, 1);
+    const uint32_t p_pf = __shfl_up_sync(0xffffffffu, rec[j].phi_flags, 1);
+    const bool same = has && lane > 0 && p_pf == rec[j].phi_flags && p_rho == rec[j].rho && p_z == rec[j].z;
     const unsigned sames = __ballot_sync(0xffffffffu, same);
     if (has && !same) {
-      unsigned follow = lane < 31 ? (sames >> (lane + 1)) : 0u;
-      int m = 1 + (__ffs(~follow) - 1);  // consecutive followers that repeat this cell
-      rec.phi_flags |= (uint32_t)m << kRecCountShift;
+      const unsigned follow = lane < 31 ? (sames >> (lane + 1)) : 0u;
+      const int m = 1 + (__ffs(~follow) - 1);  // consecutive followers that repeat this cell
+      rec[j].phi_flags |= (uint32_t)m << kRecCountShift;
       // upper bound of the hit contributions of this record: 1 + 2*min(K(rho), nRho-1-rho)
-      if (rec.phi_flags & kRecInside)
-        atomicAdd(&s_bnd[rec.phi_flags & kRecPhiMask], 1 + 2 * min(__ldg(&P.k_reach[rec.rho]), P.nRho - 1 - rec.rho));
+      if (rec[j].phi_flags & kRecInside)
+        atomicAdd(&s_bnd[work_column(P, rec[j])], 1 + 2 * min(__ldg(&P.k_reach[rec[j].rho]), P.nRho - 1 - rec[j].rho));
     } else {
-      rec.phi_flags = 0xffffffffu;
+      rec[j].phi_flags = 0xffffffffu;
     }
-    // stable rank of the record among the CTA's records of the same column: point order is kept, so
-    // k_column's record list of a column is ordered by point stamp without any sorting
-    const bool holds = rec.phi_flags != 0xffffffffu;
-    const int myphi = holds ? (int)(rec.phi_flags & kRecPhiMask) : -1 - lane;
+    // stable rank of the record among the warp's records of the same column (rounds are in point order)
+    const bool holds = rec[j].phi_flags != 0xffffffffu;
+    const int myphi = holds ? work_column(P, rec[j]) : -1 - lane;
     const unsigned peers = __match_any_sync(0xffffffffu, myphi);
     const int before = __popc(peers & ((1u << lane) - 1));
-    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5;
-    for (int w = 0; w < nwarps; w++) {
-      if (warp == w && holds) rank = s_hist[myphi] + before;
-      __syncwarp();
-      if (warp == w && holds && before == 0) s_hist[myphi] += __popc(peers);
-      __syncthreads();
-    }
+    rank[j] = holds ? s_mine[myphi] + before : 0;
+    __syncwarp();
+    if (holds && before == 0) s_mine[myphi] += __popc(peers);
+    __syncwarp();
   }
   // CTA-level counters
-  unsigned bv = __ballot_sync(0xffffffffu, valid), bi = __ballot_sync(0xffffffffu, inside),
-           bc = __ballot_sync(0xffffffffu, cast);
-  if (lane_id() == 0) {
-    if (bv) atomicAdd(&s_cnt[0], __popc(bv));
-    if (bi) atomicAdd(&s_cnt[1], __popc(bi));
-    if (bc) atomicAdd(&s_cnt[2], __popc(bc));
+  for (int ofs = 16; ofs > 0; ofs >>= 1) {
+    n_valid += __shfl_xor_sync(0xffffffffu, n_valid, ofs);
+    n_inside += __shfl_xor_sync(0xffffffffu, n_inside, ofs);
+    n_cast += __shfl_xor_sync(0xffffffffu, n_cast, ofs);
+  }
+  if (lane == 0) {
+    if (n_valid) atomicAdd(&s_cnt[0], n_valid);
+    if (n_inside) atomicAdd(&s_cnt[1], n_inside);
+    if (n_cast) atomicAdd(&s_cnt[2], n_cast);
   }
   __syncthreads();
-  // The CTA's records are written grouped by phi column into its own 256-slot window of rec_lin,
-  // with one directory word per (CTA, column): offset << 16 | count.  k_column gathers from there.
-  int *s_off = s_hist + P.nPhi;
-  for (int p = threadIdx.x; p < P.nPhi; p += blockDim.x) {
-    const int c = s_hist[p];
-    s_off[p] = c;
-    if (c) atomicAdd(&D.phi_hist[p], c);
+  // per column: exclusive prefix over the warps (warp order == point order) and the CTA total
+  for (int p = tid; p < nPhi; p += kProjThreads) {
+    int run = 0;
+#pragma unroll
+    for (int w = 0; w < kProjWarps; w++) {
+      const int c = s_proj[w * nPhi + p];
+      s_proj[w * nPhi + p] = run;
+      run += c;
+    }
+    s_hist[p] = run;
+    s_off[p] = run;
+    if (run) atomicAdd(&D.phi_hist[p], run);
     if (s_bnd[p]) atomicAdd(&D.phi_bound[p], s_bnd[p]);
   }
   __syncthreads();
-  block_exclusive_scan(s_off, P.nPhi, s_warp);
-  if (rec.phi_flags != 0xffffffffu)
-    D.rec_lin[(size_t)blockIdx.x * blockDim.x + s_off[rec.phi_flags & kRecPhiMask] + rank] = rec;
-  uint32_t *dir = D.rec_dir + (size_t)blockIdx.x * P.nPhi;
-  for (int p = threadIdx.x; p < P.nPhi; p += blockDim.x) dir[p] = ((uint32_t)s_off[p] << 16) | (uint32_t)s_hist[p];
-  if (threadIdx.x == 0) {
+  block_exclusive_scan(s_off, nPhi, s_warp);
+  // The CTA's records are written grouped by phi column into its own kProjTile-slot window of rec_lin,
+  // with one directory word per (CTA, column): offset << 16 | count.  k_column gathers from there.
+#pragma unroll
+  for (int j = 0; j < kProjPts; j++)
+    if (rec[j].phi_flags != 0xffffffffu) {
+      const int p = work_column(P, rec[j]);
+      D.rec_lin[(size_t)tile0 + s_off[p] + s_mine[p] + rank[j]] = rec[j];
+    }
+  uint32_t *dir = D.rec_dir + (size_t)blockIdx.x * nPhi;
+  for (int p = tid; p < nPhi; p += kProjThreads) dir[p] = ((uint32_t)s_off[p] << 16) | (uint32_t)s_hist[p];
+  if (tid == 0) {
     FrameCounters *fc = D.fc[F.parity];
     if (s_cnt[0]) atomicAdd(&fc->n_points, s_cnt[0]);
     if (s_cnt[1]) atomicAdd(&fc->n_inside, s_cnt[1]);
@@ -408,22 +459,24 @@ __device__ __forceinline__ uint64_t contrib_key(int cell, int k, int substep, in
 constexpr int kCntStride = kColWarps + 1;                 // +1: (digit, warp) counters of one warp hit 32 banks
 constexpr int kCntTotal = kRadixDigits * kCntStride;
 constexpr int kCntPerThread = (kCntTotal + kColThreads - 1) / kColThreads;
-__device__ __forceinline__ void radix_pass(const uint64_t *src, uint64_t *dst, int n, int shift, uint32_t *cnt,
+__device__ __forceinline__ void radix_pass(const uint64_t *src, uint64_t *dst, int n, int shift, int bits, uint32_t *cnt,
                                            uint32_t *warp_sums) {
   const int W = kColWarps, w = threadIdx.x >> 5, lane = lane_id(), tid = threadIdx.x;
   const int chunk = (((n + W - 1) / W) + 31) & ~31;
   const int beg = min(w * chunk, n), end = min(beg + chunk, n);
-  for (int i = tid; i < kCntTotal; i += kColThreads) cnt[i] = 0;
+  const int digits = 1 << bits;                 // <= kRadixDigits; narrower passes clear and scan fewer counters
+  const int total = digits * kCntStride;
+  for (int i = tid; i < total; i += kColThreads) cnt[i] = 0;
   __syncthreads();
   for (int i = beg + lane; i < end; i += 32)
-    atomicAdd(&cnt[(int)((src[i] >> shift) & (kRadixDigits - 1)) * kCntStride + w], 1u);
+    atomicAdd(&cnt[(int)((src[i] >> shift) & (digits - 1)) * kCntStride + w], 1u);
   __syncthreads();
   // exclusive scan over the counters in (digit, warp) order: kCntPerThread consecutive entries per thread
   uint32_t v[kCntPerThread], sum = 0;
 #pragma unroll
   for (int e = 0; e < kCntPerThread; e++) {
     const int idx = kCntPerThread * tid + e;
-    v[e] = idx < kCntTotal ? cnt[idx] : 0u;
+    v[e] = idx < total ? cnt[idx] : 0u;
     sum += v[e];
   }
   uint32_t incl = sum;
@@ -448,7 +501,7 @@ __device__ __forceinline__ void radix_pass(const uint64_t *src, uint64_t *dst, i
 #pragma unroll
   for (int e = 0; e < kCntPerThread; e++) {
     const int idx = kCntPerThread * tid + e;
-    if (idx < kCntTotal) cnt[idx] = run;
+    if (idx < total) cnt[idx] = run;
     run += v[e];
   }
   __syncthreads();
@@ -456,7 +509,7 @@ __device__ __forceinline__ void radix_pass(const uint64_t *src, uint64_t *dst, i
     const int i = base + lane;
     const bool ok = i < end;
     const uint64_t key = ok ? src[i] : 0;
-    const int d = ok ? (int)((key >> shift) & (kRadixDigits - 1)) : kRadixDigits + lane;
+    const int d = ok ? (int)((key >> shift) & (digits - 1)) : kRadixDigits + lane;
     const unsigned peers = __match_any_sync(0xffffffffu, d);
     const int rank = __popc(peers & ((1u << lane) - 1));
     if (ok) dst[cnt[d * kCntStride + w] + rank] = key;
@@ -492,7 +545,7 @@ struct WalkStart {
 };
 __device__ __forceinline__ WalkStart walk_prepare(const MapParams &P, int rho, int z) {
   WalkStart ws;
-  ws.rate = ray_rate(P, rho, z);
+  ws.rate = (rho < P.nRho && z >= 0 && z < P.nZ) ? __ldg(&P.rate_table[z * P.nRho + rho]) : ray_rate(P, rho, z);
   if (rho >= P.nRho) {
     z = round_to_int_x86((double)z - (double)(rho - P.nRho + 1) * ws.rate);
     rho = P.nRho - 1;
@@ -517,8 +570,18 @@ __device__ __forceinline__ void walk_mark(const MapParams &P, uint32_t *s_miss, 
     valid = valid && zc >= 0 && zc < P.nZ;
     // exploration mode: first-insert stamp of the miss cell = (point stamp, step along the ray: r = rho-1 first)
     if (stamp_col && valid) atomicMin(&stamp_col[zc * P.nRho + r], t * (uint32_t)P.nRho + (uint32_t)(rho - 1 - r));
-    const unsigned peers = __match_any_sync(0xffffffffu, valid ? zc : -1 - lane);
-    if (valid && (peers & ((1u << lane) - 1)) == 0) atomicOr(&s_miss[zc * P.words_per_row + w], peers);
+    // zc is monotone along the ray, so the lanes of one z row are consecutive: one shuffle + ballot finds the
+    // runs, the first lane of a run owns its mask, and the atomic is skipped when the bits are already there
+    const int key = valid ? zc : -1;
+    const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+    if (valid && (lane == 0 || key != prev)) {
+      const unsigned rest = lane < 31 ? heads >> (lane + 1) : 0u;
+      const int len = rest ? __ffs(rest) : 32 - lane;
+      const unsigned mask = (len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << lane;
+      uint32_t *wp = &s_miss[zc * P.words_per_row + w];
+      if ((*reinterpret_cast<volatile uint32_t *>(wp) & mask) != mask) atomicOr(wp, mask);
+    }
   }
 }
 // one prepared ray per lane (need = this lane has one); the warp marks them one after the other
@@ -615,41 +678,38 @@ __device__ __forceinline__ void resolve_subboxes(const MapParams &P, const Frame
 }
 
 // bytes of k_column's shared memory in front of the two key buffers
-__host__ __device__ inline size_t col_smem_prefix_bytes(int col_words, int nRho) {
-  return (((size_t)2 * col_words + kCntTotal + kColWarps + (size_t)kOddsRows * nRho + nRho + kMapCap) * 4 + 15) & ~(size_t)15;
+__host__ __device__ inline size_t col_smem_prefix_bytes(int col_words, int nRho, int nCol) {
+  return (((size_t)2 * col_words + kCntTotal + kColWarps + (size_t)kOddsRows * nRho + nRho + kMapCap) * 4 + (size_t)nCol * 2 + 15) & ~(size_t)15;
 }
 
 #ifdef MLM_PHASE_TIMING
-#define MLM_PHASE(i) do { __syncthreads(); if (threadIdx.x == 0) D.debug_cycles[blockIdx.x * 16 + (i)] = clock64(); } while (0)
+#define MLM_PHASE(i) do { __syncthreads(); if (threadIdx.x == 0) D.debug_cycles[vc * 16 + (i)] = clock64(); } while (0)
+#define MLM_PHASE_G(i, leader) do { if (threadIdx.x == (leader)) D.debug_cycles[vc * 16 + (i)] = clock64(); } while (0)
+#define MLM_WALL(i) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); D.debug_cycles[vc * 16 + (i)] = (long long)t_; } } while (0)
 #else
+#define MLM_WALL(i) do { } while (0)
 #define MLM_PHASE(i) do { } while (0)
+#define MLM_PHASE_G(i, leader) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBuffers D, FrameParams F) {
-  extern __shared__ __align__(16) unsigned char s_raw[];
+// One work column (a phi column or one of its halves), start to finish, by the whole CTA.
+__device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D, const FrameParams &F, const int vc,
+                                            unsigned char *s_raw) {
   FrameCounters *fc = D.fc[F.parity];
   uint32_t *act = D.act[F.parity];
-  const int phi = blockIdx.x;
+  // work column: a phi column, or one of its two halves (records below / at-or-above the sensor row n_below)
+  const int phi = P.split ? vc >> 1 : vc;
+  const int side = P.split ? (vc & 1) : -1;
+  // miss-bitmap rows this CTA owns outright, and the one row (n_below) both halves mark: rays of either half
+  // end at the sensor row, so that row goes to global memory with atomicOr and whoever sets a bit first stages it
+  const int z_own_lo = side == 1 ? P.n_below + 1 : 0;
+  const int z_own_hi = side == 0 ? P.n_below : P.nZ;
+  const int z_shared = side >= 0 ? P.n_below : -1;
   const int tid = threadIdx.x;
-  const int n_c = D.phi_hist[phi];
+  const int n_c = D.phi_hist[vc];
   uint32_t *g_miss = D.miss_bitmap + (size_t)phi * P.col_words;
-  __shared__ int s_last;
-  const bool not_mine = F.shard_world > 1 && (phi % F.shard_world) != F.shard_rank;  // another rank casts this column
-  if (n_c == 0 || not_mine) {
-    for (int i = tid; i < P.col_words; i += blockDim.x) g_miss[i] = 0;
-    if (tid == 0) {
-      __threadfence();
-      s_last = atomicAdd(D.col_ticket, 1) == (int)gridDim.x - 1;
-    }
-    __syncthreads();
-    if (s_last) {
-      if (tid == 0) *D.col_ticket = 0;
-      __threadfence();
-      if (!F.stage_only) resolve_subboxes(P, F, D, fc);
-    }
-    return;
-  }
   MLM_PHASE(15);
+  MLM_WALL(13);
   // shared memory: [miss bitmap][end-cell bitmap][radix counters][warp sums][odds table][k_reach][record index map][keys A][keys B]
   uint32_t *s_miss = reinterpret_cast<uint32_t *>(s_raw);
   uint32_t *s_end = s_miss + P.col_words;
@@ -658,9 +718,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   float *s_odds = reinterpret_cast<float *>(s_wsum + kColWarps);
   int *s_reach = reinterpret_cast<int *>(s_odds + kOddsRows * P.nRho);
   int *s_map = s_reach + P.nRho;
-  uint64_t *s_keys = reinterpret_cast<uint64_t *>(s_raw + col_smem_prefix_bytes(P.col_words, P.nRho));
-  for (int i = tid; i < kOddsRows * P.nRho; i += blockDim.x) s_odds[i] = __ldg(&P.odds_table[i]);
-  for (int i = tid; i < P.nRho; i += blockDim.x) s_reach[i] = __ldg(&P.k_reach[i]);
+  uint64_t *s_keys = reinterpret_cast<uint64_t *>(s_raw + col_smem_prefix_bytes(P.col_words, P.nRho, P.nCol));
   // exploration mode: per-column stamp arrays (earliest point stamp per end cell, first-insert stamp per miss cell)
   uint32_t *end_t_col = P.explore ? D.end_t + (size_t)phi * P.nZ * P.nRho : nullptr;
   uint32_t *stamp_col = P.explore ? D.miss_stamp + (size_t)phi * P.nZ * P.nRho : nullptr;
@@ -673,14 +731,14 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   // s_map[k] = index into rec_lin of the column's k-th record
   __shared__ int s_warp[33];
   __shared__ int s_off;
-  const int bound_c = D.phi_bound[phi];                  // upper bound of this column's hit contributions
+  const int bound_c = D.phi_bound[vc];                  // upper bound of this column's hit contributions
   const bool in_smem = bound_c <= P.sort_cap_smem;       // sort buffer in shared memory, else global spill (slow, exact)
   const bool big = n_c > P.map_cap;                      // more records than the shared-memory index map holds
   int off = 0;
   if (big || !in_smem) {
     // rare: first slot of this column in the global spill / record areas = records of the columns before it
     int part = 0;
-    for (int p = tid; p < phi; p += blockDim.x) part += D.phi_hist[p];
+    for (int p = tid; p < vc; p += blockDim.x) part += D.phi_hist[p];
     for (int ofs = 16; ofs > 0; ofs >>= 1) part += __shfl_xor_sync(0xffffffffu, part, ofs);
     if (tid == 0) s_off = 0;
     __syncthreads();
@@ -689,7 +747,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
     off = s_off;
   }
   {
-    const int nb = (F.n_total + 255) / 256;              // CTAs of k_project
+    const int nb = (F.n_total + kProjTile - 1) / kProjTile;   // CTAs of k_project
     const int per = (nb + (int)blockDim.x - 1) / (int)blockDim.x;
     const int b0 = min(tid * per, nb), b1 = min(b0 + per, nb);
     uint32_t dsave[4];
@@ -698,11 +756,11 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
     for (int q = 0; q < 4; q++) {
       dsave[q] = 0;
       if (b0 + q < b1) {
-        dsave[q] = __ldg(&D.rec_dir[(size_t)(b0 + q) * P.nPhi + phi]);
+        dsave[q] = __ldg(&D.rec_dir[(size_t)(b0 + q) * P.nCol + vc]);
         mine += (int)(dsave[q] & 0xffffu);
       }
     }
-    for (int b = b0 + 4; b < b1; b++) mine += (int)(__ldg(&D.rec_dir[(size_t)b * P.nPhi + phi]) & 0xffffu);
+    for (int b = b0 + 4; b < b1; b++) mine += (int)(__ldg(&D.rec_dir[(size_t)b * P.nCol + vc]) & 0xffffu);
     // exclusive scan of `mine` over threads (thread order == CTA order)
     int incl = mine;
     const int lane = lane_id(), w = tid >> 5, nw = blockDim.x >> 5;
@@ -725,9 +783,9 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
     __syncthreads();
     int dst = s_warp[w] + incl - mine;
     for (int b = b0; b < b1; b++) {
-      const uint32_t d = b - b0 < 4 ? dsave[b - b0] : __ldg(&D.rec_dir[(size_t)b * P.nPhi + phi]);
+      const uint32_t d = b - b0 < 4 ? dsave[b - b0] : __ldg(&D.rec_dir[(size_t)b * P.nCol + vc]);
       const int c = (int)(d & 0xffffu);
-      const int src = b * 256 + (int)(d >> 16);
+      const int src = b * kProjTile + (int)(d >> 16);
       for (int r = 0; r < c; r++) {
         if (big) D.rec_col[off + dst + r] = D.rec_lin[src + r];  // oversized column: materialise the records
         else s_map[dst + r] = src + r;
@@ -748,6 +806,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   if (tid == 0) {
     s_nk = 0;
     s_nmiss = 0;
+    s_nhead = 0;
   }
   __syncthreads();
   uint64_t *keys = in_smem ? s_keys : D.col_scratch + (size_t)2 * off * P.contrib_per_point;
@@ -777,15 +836,17 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
     const int reps = (int)((rc.phi_flags >> kRecCountShift) & kRecCountMask);
     if (P.visibility_check) atomicOr(&s_end[z * P.words_per_row + (rho >> 5)], 1u << (rho & 31));
     if (P.explore) atomicMin(&end_t_col[z * P.nRho + rho], rc.t);
-    const double rate = ray_rate(P, rho, z);
     const int dmax = min(s_reach[rho], P.nRho - 1 - rho);
     int pos = s_pos[i];
-    keys[pos++] = contrib_key(z * P.nRho + rho, i, 0, reps, cell_shift);
+    const int c0 = z * P.nRho + rho;
+    keys[pos++] = contrib_key(c0, i, 0, reps, cell_shift);
+    // z rows of the neighbour contributions: (int)round(z +/- d*rate), tabulated per end cell by the host
+    const short2 *dzr = P.dz_table + (size_t)c0 * P.maxK - 1;
     for (int d = 1; d <= dmax; d++) {
-      const int zp = round_to_int_x86((double)z + (double)d * rate);
-      const int zm = round_to_int_x86((double)z - (double)d * rate);
-      keys[pos++] = contrib_key(zp >= 0 && zp < P.nZ ? zp * P.nRho + rho + d : cell_sentinel, i, 2 * d - 1, reps, cell_shift);
-      keys[pos++] = contrib_key(zm >= 0 && zm < P.nZ ? zm * P.nRho + rho - d : cell_sentinel, i, 2 * d, reps, cell_shift);
+      const short2 e = __ldg(&dzr[d]);
+      const int zp = e.x, zm = e.y;
+      keys[pos++] = contrib_key(zp >= 0 ? zp * P.nRho + rho + d : cell_sentinel, i, 2 * d - 1, reps, cell_shift);
+      keys[pos++] = contrib_key(zm >= 0 ? zm * P.nRho + rho - d : cell_sentinel, i, 2 * d, reps, cell_shift);
     }
   }
   __syncthreads();
@@ -793,9 +854,13 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   MLM_PHASE(2);
   // (b) stable LSD radix sort by cell only: bits [cell_shift, cell_shift + cell_bits + 1)
   {
-    const int hi_bit = cell_shift + P.cell_bits + 1;
-    for (int shift = cell_shift; shift < hi_bit; shift += kRadixBits) {
-      radix_pass(keys, keys_alt, n_k, shift, s_cnt, s_wsum);
+    // cell_bits + 1 key bits (the sentinel sorts last) in the fewest passes of equal width
+    const int sort_bits = P.cell_bits + 1;
+    const int passes = (sort_bits + kRadixBits - 1) / kRadixBits;
+    const int pass_bits = (sort_bits + passes - 1) / passes;
+    const int hi_bit = cell_shift + sort_bits;
+    for (int shift = cell_shift; shift < hi_bit; shift += pass_bits) {
+      radix_pass(keys, keys_alt, n_k, shift, pass_bits, s_cnt, s_wsum);
       uint64_t *t = keys;
       keys = keys_alt;
       keys_alt = t;
@@ -816,52 +881,37 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
     uint32_t *s_head = reinterpret_cast<uint32_t *>(keys_alt);
     uint32_t *s_dec = s_head + n_k;
     {
-      const int W = kHalf / 32, w = tid >> 5, lane = lane_id();
-      const int chunk = (((n_k + W - 1) / W) + 31) & ~31;
-      const int beg = min(w * chunk, n_k), end = min(beg + chunk, n_k);
-      int cnt = 0;
-      for (int base = beg; base < end; base += 32) {
+      // one pass, heads compacted in any order (the fold and the staging do not care which thread gets which cell)
+      const int lane = lane_id();
+      for (int base = tid & ~31; base < n_k; base += kHalf) {
         const int i = base + lane;
         bool head = false;
-        if (i < end) {
+        if (i < n_k) {
           const uint64_t ki = keys[i];
           const int cell = (int)(ki >> cell_shift);
           if (cell != cell_sentinel) {
             head = i == 0 || (int)(keys[i - 1] >> cell_shift) != cell;
             const bool last = i + 1 >= n_k || (int)(keys[i + 1] >> cell_shift) != cell;
-            const int rk = cell - (cell / P.nRho) * P.nRho;
+            int zq = (int)__umulhi((uint32_t)cell, P.nRho_magic);
+            int rk = cell - zq * P.nRho;
+            if (rk >= P.nRho) rk -= P.nRho;  // never taken for cell < 2^20, nRho < 2^12; kept for safety
             const int sstep = (int)((ki >> 7) & 31);
             const int d = sstep == 0 ? 0 : ((sstep & 1) ? (sstep + 1) >> 1 : -(sstep >> 1));
             const uint32_t oi = (uint32_t)((kDiffRange + d) * P.nRho + (rk - d));
             s_dec[i] = oi | ((uint32_t)((ki & 127) - 1) << 25) | (last ? (1u << 30) : 0u);
           }
         }
-        cnt += __popc(__ballot_sync(0xffffffffu, head));
-      }
-      if (lane == 0) s_wsum[w] = (uint32_t)cnt;
-      group_bar(1, kHalf);
-      if (w == 0) {
-        uint32_t sv = lane < W ? s_wsum[lane] : 0, si = sv;
-  #pragma unroll
-        for (int ofs = 1; ofs < 32; ofs <<= 1) {
-          uint32_t t = __shfl_up_sync(0xffffffffu, si, ofs);
-          if (lane >= ofs) si += t;
+        const unsigned hb = __ballot_sync(0xffffffffu, head);
+        if (hb) {
+          int pos = 0;
+          if (lane == 0) pos = atomicAdd(&s_nhead, __popc(hb));
+          pos = __shfl_sync(0xffffffffu, pos, 0);
+          if (head) s_head[pos + __popc(hb & ((1u << lane) - 1))] = (uint32_t)i;
         }
-        if (lane < W) s_wsum[lane] = si - sv;
-        if (lane == W - 1) s_nhead = (int)si;
-      }
-      group_bar(1, kHalf);
-      int pos = (int)s_wsum[w];
-      for (int base = beg; base < end; base += 32) {
-        const int i = base + lane;
-        const bool head = i < end && (int)(keys[i] >> cell_shift) != cell_sentinel &&
-                          (i == 0 || (keys[i - 1] >> cell_shift) != (keys[i] >> cell_shift));
-        const unsigned b = __ballot_sync(0xffffffffu, head);
-        if (head) s_head[pos + __popc(b & ((1u << lane) - 1))] = (uint32_t)i;
-        pos += __popc(b);
       }
     }
     group_bar(1, kHalf);
+    MLM_PHASE_G(4, 0);
     // (c2) update_odds_hashmap fold, one thread per distinct cell (static: head h -> thread h, so the
     // lanes of a warp stay in one loop).  The chain p <- 1-(1-p)(1-odd) is inherently ordered; it is
     // flattened over (contribution, repeat) so that a lane never waits for another lane's run length,
@@ -904,6 +954,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
       }
     }
     group_bar(1, kHalf);
+    MLM_PHASE_G(5, 0);
     {
       const int n_head = s_nhead;
       int base_idx = 0;
@@ -947,7 +998,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
       }
     }
     group_bar(1, kHalf);
-
+    MLM_PHASE_G(8, 0);
   } else {
     // scratch of the walk group: the radix counters are idle now -> [hash set of outside rays][end-cell list]
     uint32_t *s_hash = s_cnt;
@@ -987,6 +1038,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
       // (walks are idempotent, so a missed duplicate only costs time).
       for (int i = gt; i < hcap; i += kHalf) s_hash[i] = 0xffffffffu;
       group_bar(2, kHalf);
+      MLM_PHASE_G(9, kHalf);
       for (int it = 0; it * 32 * nwarps < n_c; it++) {
         const int i = (it * 32 + lane_id()) * nwarps + warp;
         RayRecord rc;
@@ -1009,8 +1061,12 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
         }
         walk_batch(P, s_miss, need, rc.rho, rc.z, stamp_col, rc.t);
       }
+      group_bar(2, kHalf);
+      MLM_PHASE_G(12, kHalf);
     }
   }
+#ifdef MLM_PHASE_TIMING
+#endif
   __syncthreads();
 
   MLM_PHASE(6);
@@ -1019,11 +1075,22 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   uint32_t *s_list = reinterpret_cast<uint32_t *>(s_keys);
   const int list_cap = P.sort_cap_smem * 4;            // 32-bit entries in the two key buffers
   const int words_per_chunk = max(1, list_cap >> 5);   // a chunk of words can never overflow the list
-  for (int wi = tid; wi < P.col_words; wi += blockDim.x) g_miss[wi] = s_miss[wi];
-  for (int w0 = 0; w0 < P.col_words; w0 += words_per_chunk) {
+  for (int wi = z_own_lo * P.words_per_row + tid; wi < z_own_hi * P.words_per_row; wi += blockDim.x) g_miss[wi] = s_miss[wi];
+  if (z_shared >= 0) {
+    // cells of the shared row: only the half that sets a bit first keeps it for the staging below
+    if (tid < P.words_per_row) {
+      const int wi = z_shared * P.words_per_row + tid;
+      const uint32_t mine = s_miss[wi];
+      if (mine) s_miss[wi] = mine & ~atomicOr(&g_miss[wi], mine);
+    }
+    __syncthreads();
+  }
+  const int stage_w0 = min(z_own_lo, z_shared >= 0 ? z_shared : z_own_lo) * P.words_per_row;
+  const int stage_w1 = max(z_own_hi, z_shared + 1) * P.words_per_row;
+  for (int w0 = stage_w0; w0 < stage_w1; w0 += words_per_chunk) {
     if (tid == 0) s_nk = 0;
     __syncthreads();
-    compact_bits(s_miss, w0, min(w0 + words_per_chunk, P.col_words), s_list, &s_nk, tid >> 5, (int)blockDim.x >> 5);
+    compact_bits(s_miss, w0, min(w0 + words_per_chunk, stage_w1), s_list, &s_nk, tid >> 5, (int)blockDim.x >> 5);
     __syncthreads();
     const int n_list = s_nk;
     for (int k = tid; k < n_list; k += blockDim.x) {
@@ -1060,17 +1127,97 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
     __syncthreads();
   }
   MLM_PHASE(7);
+  MLM_WALL(14);
 #ifdef MLM_PHASE_TIMING
-  if (tid == 0) { D.debug_cycles[blockIdx.x * 16 + 10] = n_c; D.debug_cycles[blockIdx.x * 16 + 11] = n_k; }
+  if (tid == 0) { D.debug_cycles[vc * 16 + 10] = n_c; D.debug_cycles[vc * 16 + 11] = n_k; }
 #endif
   if (tid == 0 && s_nmiss) atomicAdd(&fc->n_miss, s_nmiss);
-  // the last column to finish resolves the touched subboxes for k_fuse
+}
+
+// weight of a work column for the longest-first queue (records dominate the walks, contributions the fold)
+__device__ __forceinline__ int column_weight(const DeviceBuffers &D, int vc) { return 4 * D.phi_hist[vc] + D.phi_bound[vc]; }
+
+// Persistent kernel: one CTA per SM pulls work columns, heaviest first, from a queue every CTA derives
+// identically (stable counting sort of the per-column weights k_project accumulated), so a depth camera's
+// ~80 lit columns (160 halves) spread over all SMs instead of one SM per column.
+__global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBuffers D, FrameParams F) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  FrameCounters *fc = D.fc[F.parity];
+  const int tid = threadIdx.x;
+  __shared__ int s_last, s_item, s_wmax, s_nactive;
+  // shared memory: [miss bitmap][end-cell bitmap][radix counters][warp sums][odds table][k_reach][record index map][queue order][keys A][keys B]
+  uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_raw) + 2 * P.col_words;
+  uint32_t *s_wsum = s_cnt + kCntTotal;
+  float *s_odds = reinterpret_cast<float *>(s_wsum + kColWarps);
+  int *s_reach = reinterpret_cast<int *>(s_odds + kOddsRows * P.nRho);
+  uint16_t *s_order = reinterpret_cast<uint16_t *>(s_reach + P.nRho + kMapCap);
+  uint64_t *s_keys = reinterpret_cast<uint64_t *>(s_raw + col_smem_prefix_bytes(P.col_words, P.nRho, P.nCol));
+  for (int i = tid; i < kOddsRows * P.nRho; i += blockDim.x) s_odds[i] = __ldg(&P.odds_table[i]);
+  for (int i = tid; i < P.nRho; i += blockDim.x) s_reach[i] = __ldg(&P.k_reach[i]);
+  if (tid == 0) {
+    s_wmax = 0;
+    s_nactive = 0;
+  }
+  __syncthreads();
+  auto is_active = [&](int vc) {
+    const int phi = P.split ? vc >> 1 : vc;
+    const bool not_mine = F.shard_world > 1 && (phi % F.shard_world) != F.shard_rank;  // another rank casts this column
+    return D.phi_hist[vc] > 0 && !not_mine;
+  };
+  // idle work columns: their own rows of the miss bitmap are empty this frame (spread over the CTAs)
+  for (int vc = blockIdx.x; vc < P.nCol; vc += gridDim.x) {
+    if (is_active(vc)) continue;
+    const int phi = P.split ? vc >> 1 : vc, side = P.split ? (vc & 1) : -1;
+    const int z_lo = side == 1 ? P.n_below + 1 : 0, z_hi = side == 0 ? P.n_below : P.nZ;
+    uint32_t *g_miss = D.miss_bitmap + (size_t)phi * P.col_words;
+    for (int i = z_lo * P.words_per_row + tid; i < z_hi * P.words_per_row; i += blockDim.x) g_miss[i] = 0;
+  }
+  // queue order: active work columns by descending weight bucket, ties by column index (deterministic, so
+  // every CTA holds the same list); one 7-bit radix pass over (63 - bucket | column)
+  const bool sorted = P.nCol <= P.sort_cap_smem;
+  int n_active = 0;
+  if (sorted) {
+    int my_active = 0;
+    for (int vc = tid; vc < P.nCol; vc += blockDim.x)
+      if (is_active(vc)) {
+        my_active++;
+        atomicMax(&s_wmax, column_weight(D, vc));
+      }
+    if (my_active) atomicAdd(&s_nactive, my_active);
+    __syncthreads();
+    n_active = s_nactive;
+    int sh = 0;
+    while ((s_wmax >> sh) > 63) sh++;
+    for (int vc = tid; vc < P.nCol; vc += blockDim.x) {
+      const uint64_t digit = is_active(vc) ? (uint64_t)(63 - (column_weight(D, vc) >> sh)) : 64ull;
+      s_keys[vc] = (digit << 16) | (uint64_t)vc;
+    }
+    __syncthreads();
+    radix_pass(s_keys, s_keys + P.sort_cap_smem, P.nCol, 16, 7, s_cnt, s_wsum);
+    for (int i = tid; i < n_active; i += blockDim.x) s_order[i] = (uint16_t)(s_keys[P.sort_cap_smem + i] & 0xffffu);
+  } else {
+    n_active = P.nCol;  // more work columns than the sort scratch holds: plain column order, idle ones skipped below
+  }
+  for (;;) {
+    __syncthreads();  // the previous item is done with shared memory; s_order is in place
+    if (tid == 0) s_item = atomicAdd(D.col_queue, 1);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= n_active) break;
+    const int vc = sorted ? (int)s_order[item] : item;
+    if (!sorted && !is_active(vc)) continue;
+    column_item(P, D, F, vc, s_raw);
+  }
+  // the last CTA to run dry resolves the touched subboxes for k_fuse and rearms the queue
   __threadfence();
   __syncthreads();
   if (tid == 0) s_last = atomicAdd(D.col_ticket, 1) == (int)gridDim.x - 1;
   __syncthreads();
   if (s_last) {
-    if (tid == 0) *D.col_ticket = 0;
+    if (tid == 0) {
+      *D.col_ticket = 0;
+      *D.col_queue = 0;
+    }
     __threadfence();
     if (!F.stage_only) resolve_subboxes(P, F, D, fc);
   }
@@ -1284,7 +1431,7 @@ __global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D, Fram
       uint32_t *am = D.act_miss[F.parity ^ 1];
       for (uint32_t i = gtid; i < Bm; i += nth) am[i] = 0xffffffffu;
     }
-    for (int i = gtid; i < P.nPhi; i += nth) {
+    for (int i = gtid; i < P.nCol; i += nth) {
       D.phi_hist[i] = 0;
       D.phi_bound[i] = 0;
     }

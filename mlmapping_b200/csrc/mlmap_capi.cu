@@ -181,6 +181,7 @@ struct mlm_map {
   cudaGraph_t graph[3] = {nullptr, nullptr, nullptr};
   cudaGraphNode_t graph_nodes[3][3] = {};
   int use_graph = 1;
+  int col_grid = 1;        // CTAs of the persistent k_column: one per SM, at most one per work column
   void *h_stage = nullptr;        // pinned input staging
   size_t stage_bytes = 0;
   void *d_input = nullptr;
@@ -224,6 +225,8 @@ struct AwarenessTables {
   std::vector<int> k_reach;
   std::vector<double2> centre_xy;
   std::vector<double> centre_z;
+  std::vector<double> rate;   // [nZ][nRho]
+  std::vector<short2> dz;     // [nZ][nRho][maxK]
   double dPhi, z_border_min;
   int nPhi, nZ;
 };
@@ -289,6 +292,7 @@ int validate_config(const mlm_config &c, std::string &why) {
   };
   if (!(c.am_d_rho > 0) || !(c.am_d_phi_deg > 0) || !(c.am_d_z > 0)) return bad("awareness resolutions must be > 0");
   if (c.am_n_rho < 2 || c.am_n_z_below < 0 || c.am_n_z_over < 0) return bad("awareness extents");
+  if (c.am_n_rho >= 4096) return bad("n_Rho must be < 4096");
   if (!(c.subbox_d_xyz > 0) || c.subbox_n < 1 || c.subbox_n > 64) return bad("subbox size");
   if (!(c.depth_noise_coe >= 0)) return bad("depth_noise_coe");
   if (c.max_points < 1 || c.max_points > (1 << 26)) return bad("max_points must be in [1, 2^26]");
@@ -386,15 +390,15 @@ int run_frame_explore(mlm_map *h, int mode, int N, mlm_frame_stats *stats) {
   cudaStream_t s = h->stream;
   FrameParams &F = *h->h_fp;
   const int parity = F.parity;
-  const int proj_grid = grid_for((size_t)std::max(N, 1), 256);
+  const int proj_grid = grid_for((size_t)std::max(N, 1), kProjTile);
   F.order_mode = 1;  // rehash detection happens on the host below, not inside k_fuse
   if (mode == 1)
-    k_project<1><<<proj_grid, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(P, h->D, F);
+    k_project<1><<<proj_grid, kProjThreads, project_smem_bytes(P.nCol), s>>>(P, h->D, F);
   else if (mode == 2)
-    k_project<2><<<proj_grid, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(P, h->D, F);
+    k_project<2><<<proj_grid, kProjThreads, project_smem_bytes(P.nCol), s>>>(P, h->D, F);
   else
-    k_project<0><<<proj_grid, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(P, h->D, F);
-  k_column<<<P.nPhi, kColThreads, h->col_smem_bytes, s>>>(P, h->D, F);
+    k_project<0><<<proj_grid, kProjThreads, project_smem_bytes(P.nCol), s>>>(P, h->D, F);
+  k_column<<<h->col_grid, kColThreads, h->col_smem_bytes, s>>>(P, h->D, F);
   FrameCounters mid;
   CUDA_TRY(cudaMemcpyAsync(&mid, h->D.fc[parity], sizeof(mid), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
@@ -499,9 +503,9 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
     F.shard_world = h->shard_world;
     F.stage_only = 1;
     F.order_mode = 1;
-    const int pg = grid_for((size_t)std::max(N, 1), 256);
-    k_project<0><<<pg, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(P, h->D, F);
-    k_column<<<P.nPhi, kColThreads, h->col_smem_bytes, s>>>(P, h->D, F);
+    const int pg = grid_for((size_t)std::max(N, 1), kProjTile);
+    k_project<0><<<pg, kProjThreads, project_smem_bytes(P.nCol), s>>>(P, h->D, F);
+    k_column<<<h->col_grid, kColThreads, h->col_smem_bytes, s>>>(P, h->D, F);
     h->launches += 2;
     CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc[parity], sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -510,8 +514,8 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
   }
   if (P.explore) return run_frame_explore(h, mode, N, stats);
   const bool prof = h->profiling != 0;
-  const int full_grid = grid_for((size_t)P.max_points, 256);
-  const int proj_grid = grid_for((size_t)std::max(N, 1), 256);
+  const int full_grid = grid_for((size_t)P.max_points, kProjTile);
+  const int proj_grid = grid_for((size_t)std::max(N, 1), kProjTile);
   MapParams Pk = P;
   DeviceBuffers Dk = h->D;
   FrameParams Fk = F;
@@ -520,13 +524,13 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
 #define MLM_MARK(i) do { if (prof) cudaEventRecord(h->kev[i], s); } while (0)
     MLM_MARK(0);
     if (mode == 1)
-      k_project<1><<<proj_grid, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(Pk, Dk, Fk);
+      k_project<1><<<proj_grid, kProjThreads, project_smem_bytes(P.nCol), s>>>(Pk, Dk, Fk);
     else if (mode == 2)
-      k_project<2><<<proj_grid, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(Pk, Dk, Fk);
+      k_project<2><<<proj_grid, kProjThreads, project_smem_bytes(P.nCol), s>>>(Pk, Dk, Fk);
     else
-      k_project<0><<<proj_grid, 256, (size_t)3 * P.nPhi * sizeof(int), s>>>(Pk, Dk, Fk);
+      k_project<0><<<proj_grid, kProjThreads, project_smem_bytes(P.nCol), s>>>(Pk, Dk, Fk);
     MLM_MARK(1);
-    k_column<<<P.nPhi, kColThreads, h->col_smem_bytes, s>>>(Pk, Dk, Fk);
+    k_column<<<h->col_grid, kColThreads, h->col_smem_bytes, s>>>(Pk, Dk, Fk);
     MLM_MARK(2);
     k_fuse<0><<<h->sm_count * 4, 256, 0, s>>>(Pk, Dk, Fk);
     MLM_MARK(3);
@@ -537,10 +541,10 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
     cudaKernelNodeParams np[3] = {};
     np[0].func = mode == 1 ? (void *)k_project<1> : (mode == 2 ? (void *)k_project<2> : (void *)k_project<0>);
     np[0].gridDim = dim3(full_grid);  // fixed grid: CTAs beyond this frame's point count return at once
-    np[0].blockDim = dim3(256);
-    np[0].sharedMemBytes = (unsigned)((size_t)3 * P.nPhi * sizeof(int));
+    np[0].blockDim = dim3(kProjThreads);
+    np[0].sharedMemBytes = (unsigned)(project_smem_bytes(P.nCol));
     np[1].func = (void *)k_column;
-    np[1].gridDim = dim3(P.nPhi);
+    np[1].gridDim = dim3(h->col_grid);
     np[1].blockDim = dim3(kColThreads);
     np[1].sharedMemBytes = (unsigned)h->col_smem_bytes;
     np[2].func = (void *)k_fuse<0>;
@@ -774,6 +778,34 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   P.col_words = P.nZ * P.words_per_row;
   P.cell_bits = 1;
   while ((1 << P.cell_bits) < P.nZ * P.nRho) P.cell_bits++;
+  P.nRho_magic = (uint32_t)(((1ull << 32) + (uint64_t)P.nRho - 1) / (uint64_t)P.nRho);
+  // Half-column split: records below the sensor row (z_idx < n_below) and at/above it never feed the same hit
+  // cell when every neighbour step stays on its side of the row, i.e. z - n_below and
+  // round(z -/+ d*rate) - n_below = round((z - n_below) * (1 -/+ d/rho)) have the same sign: 2*K(rho) < rho.
+  // Their ray walks share only the row n_below itself (arbitrated through the global miss bitmap).  The
+  // exploration mode needs per-cell first-insert stamps across both halves, so it keeps whole columns.
+  P.split = cfg->use_exploration_frontiers ? 0 : 1;
+  for (int r = 0; r < P.nRho; r++)
+    if (T.k_reach[r] > 0 && 2 * T.k_reach[r] >= r) P.split = 0;
+  if (P.n_below < 1 || P.n_below >= P.nZ - 1 || P.nRho >= 4096 || 2 * P.nPhi > kMaxPhi) P.split = 0;
+  if (const char *e = getenv("MLM_DEBUG_NO_SPLIT")) if (atoi(e)) P.split = 0;
+  P.nCol = P.nPhi * (P.split ? 2 : 1);
+  // per end cell: the ray's slope and the z rows of its neighbour contributions, with the reference's arithmetic
+  // (rate = (z - n_below) / (rho * 1.0); (int)round(z +/- d * rate)), src/map_awareness.cpp:64-71,151,161
+  T.rate.resize((size_t)P.nZ * P.nRho);
+  T.dz.resize((size_t)P.nZ * P.nRho * std::max(maxK, 1));
+  for (int z = 0; z < P.nZ; z++)
+    for (int rho = 0; rho < P.nRho; rho++) {
+      const double rate = rho > 0 ? (double)(z - P.n_below) / ((double)rho * 1.0) : 0.0;
+      T.rate[(size_t)z * P.nRho + rho] = rate;
+      for (int d = 1; d <= maxK; d++) {
+        const double vp = round((double)z + (double)d * rate), vm = round((double)z - (double)d * rate);
+        short2 e;
+        e.x = (vp >= 0 && vp < P.nZ) ? (short)vp : (short)-1;
+        e.y = (vm >= 0 && vm < P.nZ) ? (short)vm : (short)-1;
+        T.dz[((size_t)z * P.nRho + rho) * maxK + (d - 1)] = e;
+      }
+    }
   // local_map_cartesian::init_map, src/map_local.cpp:56-62
   P.d_sub = cfg->subbox_d_xyz;
   P.d_sub_half = P.d_sub * 0.5;
@@ -829,7 +861,7 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   // column kernel shared memory: two column bitmaps + the largest power-of-two sort buffer that fits
   int max_optin = 0;
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-  const size_t bm_bytes = col_smem_prefix_bytes(P.col_words, P.nRho);
+  const size_t bm_bytes = col_smem_prefix_bytes(P.col_words, P.nRho, P.nCol);
   long long avail = (long long)max_optin - 1024 - (long long)bm_bytes;
   if (avail < 32 * 1024) {
     delete h;
@@ -841,9 +873,11 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   P.sort_cap_smem = cap;
   P.map_cap = kMapCap;
   // test hooks: shrink the shared-memory capacities to force the global-memory fallback paths
+  if (const char *e = getenv("MLM_NO_GRAPH")) h->use_graph = atoi(e) ? 0 : 1;
   if (const char *e = getenv("MLM_DEBUG_SORT_CAP")) P.sort_cap_smem = std::max(128, std::min(cap, atoi(e)) & ~127);
   if (const char *e = getenv("MLM_DEBUG_MAP_CAP")) P.map_cap = std::max(1, std::min(kMapCap, atoi(e)));
   h->col_smem_bytes = (int)(bm_bytes + (size_t)cap * 16);
+  h->col_grid = std::max(1, std::min(P.nCol, h->sm_count));
 
 #define TRY(x)            \
   do {                    \
@@ -870,6 +904,12 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   CUDA_TRY_H(cudaHostAlloc((void **)&h->h_fc, sizeof(FrameCounters), cudaHostAllocMapped));
   memset(h->h_fc, 0, sizeof(FrameCounters));
   CUDA_TRY_H(cudaFuncSetAttribute(k_column, cudaFuncAttributeMaxDynamicSharedMemorySize, h->col_smem_bytes));
+  if (project_smem_bytes(P.nCol) > 48 * 1024) {
+    const int pb = (int)project_smem_bytes(P.nCol);
+    CUDA_TRY_H(cudaFuncSetAttribute(k_project<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
+    CUDA_TRY_H(cudaFuncSetAttribute(k_project<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
+    CUDA_TRY_H(cudaFuncSetAttribute(k_project<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
+  }
 
   DeviceBuffers &D = h->D;
   memset(&D, 0, sizeof(D));
@@ -885,6 +925,14 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   CUDA_TRY_H(cudaMemcpy(d_k, T.k_reach.data(), T.k_reach.size() * sizeof(int), cudaMemcpyHostToDevice));
   CUDA_TRY_H(cudaMemcpy(d_cxy, T.centre_xy.data(), T.centre_xy.size() * sizeof(double2), cudaMemcpyHostToDevice));
   CUDA_TRY_H(cudaMemcpy(d_cz, T.centre_z.data(), T.centre_z.size() * sizeof(double), cudaMemcpyHostToDevice));
+  double *d_rate;
+  short2 *d_dz;
+  TRY(dev_alloc(h, &d_rate, T.rate.size()));
+  TRY(dev_alloc(h, &d_dz, T.dz.size()));
+  CUDA_TRY_H(cudaMemcpy(d_rate, T.rate.data(), T.rate.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY_H(cudaMemcpy(d_dz, T.dz.data(), T.dz.size() * sizeof(short2), cudaMemcpyHostToDevice));
+  P.rate_table = d_rate;
+  P.dz_table = d_dz;
   P.odds_table = d_odds;
   P.k_reach = d_k;
   P.centre_xy = d_cxy;
@@ -896,11 +944,12 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   TRY(dev_alloc(h, &D.fc[0], 2));
   D.fc[1] = D.fc[0] + 1;
   TRY(dev_alloc(h, &D.col_ticket, 1));
+  TRY(dev_alloc(h, &D.col_queue, 1));
   TRY(dev_alloc(h, &D.rec_lin, (size_t)P.max_points));
   TRY(dev_alloc(h, &D.rec_col, (size_t)P.max_points));
-  TRY(dev_alloc(h, &D.rec_dir, (size_t)((P.max_points + 255) / 256) * P.nPhi));
-  TRY(dev_alloc(h, &D.phi_hist, (size_t)P.nPhi));
-  TRY(dev_alloc(h, &D.phi_bound, (size_t)P.nPhi));
+  TRY(dev_alloc(h, &D.rec_dir, (size_t)((P.max_points + kProjTile - 1) / kProjTile) * P.nCol));
+  TRY(dev_alloc(h, &D.phi_hist, (size_t)P.nCol));
+  TRY(dev_alloc(h, &D.phi_bound, (size_t)P.nCol));
   TRY(dev_alloc(h, &D.col_scratch, (size_t)2 * P.max_points * P.contrib_per_point));
   TRY(dev_alloc(h, &D.hit_key, (size_t)P.max_hits));
   TRY(dev_alloc(h, &D.hit_p, (size_t)P.max_hits));
@@ -963,8 +1012,8 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
     CUDA_TRY_H(cudaMemset(D.obs_flag, 0, (size_t)lsg_cells * 4));
   }
   TRY(dev_alloc(h, &D.cum, 4));
-  TRY(dev_alloc(h, &D.debug_cycles, (size_t)P.nPhi * 16));
-  CUDA_TRY_H(cudaMemset(D.debug_cycles, 0, (size_t)P.nPhi * 16 * sizeof(long long)));
+  TRY(dev_alloc(h, &D.debug_cycles, (size_t)P.nCol * 16));
+  CUDA_TRY_H(cudaMemset(D.debug_cycles, 0, (size_t)P.nCol * 16 * sizeof(long long)));
   h->sort_cap = P.explore ? (int)n_cells : P.max_hits;
   const size_t sort_pad = (size_t)next_pow2(h->sort_cap);
   TRY(dev_alloc(h, &h->d_sort_a, sort_pad));
@@ -983,11 +1032,12 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   CUDA_TRY_H(cudaMemset(D.ht_val, 0xff, (size_t)ht_cap * 4));
   CUDA_TRY_H(cudaMemset(D.cum, 0, 4 * sizeof(int64_t)));
   CUDA_TRY_H(cudaMemset(D.col_ticket, 0, sizeof(int)));
+  CUDA_TRY_H(cudaMemset(D.col_queue, 0, sizeof(int)));
   CUDA_TRY_H(cudaMemset(D.fc[0], 0, 2 * sizeof(FrameCounters)));
   CUDA_TRY_H(cudaMemset(D.act[0], 0xff, (size_t)h->act_cap * 4));
   CUDA_TRY_H(cudaMemset(D.act[1], 0xff, (size_t)h->act_cap * 4));
-  CUDA_TRY_H(cudaMemset(D.phi_hist, 0, (size_t)P.nPhi * 4));
-  CUDA_TRY_H(cudaMemset(D.phi_bound, 0, (size_t)P.nPhi * 4));
+  CUDA_TRY_H(cudaMemset(D.phi_hist, 0, (size_t)P.nCol * 4));
+  CUDA_TRY_H(cudaMemset(D.phi_bound, 0, (size_t)P.nCol * 4));
   // every block on the free stack is in the initial state of allocate_ram: 'u', 'u', 0.f
   CUDA_TRY_H(cudaMemset(D.pool_lo, 0, (size_t)P.pool_blocks * P.cell_stride * 4));
   CUDA_TRY_H(cudaMemset(D.pool_occ, 'u', (size_t)P.pool_blocks * P.cell_stride));
@@ -1308,7 +1358,7 @@ int mlm_last_frame_kernel_ms(mlm_handle h, float ms[MLM_NUM_FRAME_KERNELS]) {
 }
 int mlm_debug_phase_cycles(mlm_handle h, long long *out, size_t cap) {
   if (!h || !out) return MLM_ERR_INVALID_ARG;
-  size_t n = std::min(cap, (size_t)h->P.nPhi * 16);
+  size_t n = std::min(cap, (size_t)h->P.nCol * 16);
   CUDA_TRY(cudaMemcpy(out, h->D.debug_cycles, n * sizeof(long long), cudaMemcpyDeviceToHost));
   return MLM_OK;
 }

@@ -41,6 +41,9 @@ struct MapParams {
   int words_per_row;      // ceil(nRho / 32): bitmap words per (phi,z) row
   int col_words;          // nZ * words_per_row
   int cell_bits;          // bits of a cell id inside a column: ceil(log2(nZ*nRho))
+  int split;              // 1: every phi column is worked as two half columns (records below / at-or-above the sensor row n_below)
+  int nCol;               // work columns of k_column: nPhi * (split ? 2 : 1)
+  uint32_t nRho_magic;    // ceil(2^32 / nRho): cell / nRho by multiply-high (cells < 2^20, nRho < 2^12)
   // local_map_cartesian members (include/map_local.h:66-78)
   double d_sub, d_glb, d_sub_half;
   double inv_d_sub, inv_d_glb, inv_dRho, inv_dPhi, inv_dZ;  // fl(1/d): fast path of floor_quot_exact only
@@ -73,6 +76,8 @@ struct MapParams {
   const int *k_reach;         // [nRho]       number of diff_r >= 1 with diff_r < 3*sigma_in_dr(rho)
   const double2 *centre_xy;   // [nPhi*nRho]  cell centre x,y (map_awareness.cpp:58-61)
   const double *centre_z;     // [nZ]
+  const double *rate_table;   // [nZ*nRho]    raycasting_z_over_rho of cell (z,rho) (map_awareness.cpp:64-71)
+  const short2 *dz_table;     // [nZ*nRho*maxK] z row of the d-th outer / inner neighbour of an end cell (update_hits :151,:161), -1 = outside
 };
 
 // values that change every frame; lives in device memory so a captured graph can be replayed
@@ -115,11 +120,11 @@ struct DeviceBuffers {
   int *fuse_ticket;        // completion ticket of k_fuse
   FrameCounters *fc[2];   // double-buffered: frame f uses fc[f&1], k_fuse clears the other one
   // K1/K1b
-  RayRecord *rec_lin;     // [max_points] per k_project CTA: a 256-slot window, records grouped by column
-  uint32_t *rec_dir;      // [ceil(max_points/256)][nPhi] directory of those windows: offset << 16 | count
+  RayRecord *rec_lin;     // [max_points] per k_project CTA: a kProjTile-slot window, records grouped by column
+  uint32_t *rec_dir;      // [ceil(max_points/kProjTile)][nCol] directory of those windows: offset << 16 | count
   RayRecord *rec_col;     // [max_points] gathered by k_column: contiguous per phi column
-  int *phi_hist;          // [nPhi] records per column
-  int *phi_bound;         // [nPhi] upper bound of hit contributions per column
+  int *phi_hist;          // [nCol] records per work column
+  int *phi_bound;         // [nCol] upper bound of hit contributions per work column
   uint64_t *col_scratch;  // [max_points*contrib_per_point] sort spill for oversized columns
   // per-frame hit map / miss set
   int *hit_key;           // [max_hits] awareness linear index (mapIdx)
@@ -130,6 +135,7 @@ struct DeviceBuffers {
   uint32_t *miss_bitmap;  // [nPhi*col_words]
   uint32_t *act[2];       // [bucket capacity] bucket activation stamps, double-buffered like fc
   int *col_ticket;        // completion ticket of k_column (last CTA resolves the touched subboxes)
+  int *col_queue;         // next item of k_column's work queue (rearmed by the last CTA)
   // local voxel / submap grids
   int2 *lvg;              // [lvg cells] .x head of this frame's hit list (-1 empty), .y number of miss cells
   uint32_t *touched;      // [max_touched] local voxel index (| kTouchedHitTag)

@@ -22,5 +22,19 @@ print("columns", act.sum(), "cycles: total max", tot.max(), "mean", tot.mean())
 print("phase", names)
 print("mean  ", d.mean(0).astype(int))
 print("max   ", d.max(0).astype(int))
+# inside the overlapped phase (relative to its start, slot 3): fold half = heads, fold, hit staging; walk half = inside walks, outside walks
+ca = c[act]
+sub = np.stack([ca[:, 4] - ca[:, 3], ca[:, 5] - ca[:, 4], ca[:, 8] - ca[:, 5], ca[:, 9] - ca[:, 3], ca[:, 12] - ca[:, 9]], axis=1)
+print("fold half [heads, fold, hit-stage] | walk half [inside walks, outside walks]")
+print("mean  ", sub.mean(0).astype(int))
+print("max   ", sub.max(0).astype(int))
 for i in order[:6]:
-    print("col", np.nonzero(act)[0][i], "n_c", c[act][i, 10], "n_k", c[act][i, 11], "tot", tot[i], d[i])
+    print("col", np.nonzero(act)[0][i], "n_c", ca[i, 10], "n_k", ca[i, 11], "tot", tot[i], d[i], "sub", sub[i])
+t0 = ca[:, 13].min()
+st, en = (ca[:, 13] - t0) / 1e3, (ca[:, 14] - t0) / 1e3
+print("wall us: first start 0, last start %.1f, last end %.1f; starts>5us: %d" % (st.max(), en.max(), (st > 5).sum()))
+print("per-item duration us: mean %.1f max %.1f sum %.0f" % ((en - st).mean(), (en - st).max(), (en - st).sum()))
+late = np.argsort(-st)[:8]
+print("latest starters (col, start, end, n_c, n_k):", [(int(np.nonzero(act)[0][i]), round(float(st[i]), 1), round(float(en[i]), 1), int(ca[i, 10]), int(ca[i, 11])) for i in late])
+first = np.argsort(st)[:6]
+print("first starters:", [(int(np.nonzero(act)[0][i]), round(float(st[i]), 1), round(float(en[i]), 1), int(ca[i, 10]), int(ca[i, 11])) for i in first])
