@@ -219,6 +219,58 @@ __device__ __forceinline__ void point_to_record(const MapParams &P, const FrameP
   }
 }
 
+// Guarded fast path of point_to_record.  Only the three integer indices of a point reach the map, so the
+// point is first located with cheap arithmetic (FMA transform in double, then float sqrt / division /
+// polynomial): the float values are within 1e-6 relative of what the reference's double chain yields, and
+// an index is accepted only when its value (in cells) is farther than a 1000x larger guard band from the
+// next integer, where truncation cannot differ.  Anything inside a guard band, on the x == 0 quirk of
+// fast_atan2 or not finite is left to the exact path.  Returns false when the exact path has to run.
+__device__ __forceinline__ bool point_to_record_fast(const MapParams &P, const FrameParams &F, double xs, double ys,
+                                                     double zs, uint32_t t, RayRecord &rec, int &inside_out,
+                                                     int &cast_out) {
+  const double qw = F.q_ls[0], qx = F.q_ls[1], qy = F.q_ls[2], qz = F.q_ls[3];
+  double uvx = __fma_rn(qy, zs, -(qz * ys));
+  double uvy = __fma_rn(qz, xs, -(qx * zs));
+  double uvz = __fma_rn(qx, ys, -(qy * xs));
+  uvx += uvx;
+  uvy += uvy;
+  uvz += uvz;
+  const double x = __fma_rn(qw, uvx, xs) + __fma_rn(qy, uvz, -(qz * uvy)) + F.t_ls[0];
+  const double y = __fma_rn(qw, uvy, ys) + __fma_rn(qz, uvx, -(qx * uvz)) + F.t_ls[1];
+  const double z = __fma_rn(qw, uvz, zs) + __fma_rn(qx, uvy, -(qy * uvx)) + F.t_ls[2];
+  const float xf = (float)x, yf = (float)y, zf = (float)(z - P.z_border_min);
+  const float ax = fabsf(xf), ay = fabsf(yf);
+  if (!(ax > 1e-30f) || !(ax < 1e6f) || !(ay < 1e6f) || !(fabsf(zf) < 1e6f)) return false;  // x == 0 quirk, NaN, huge
+  const float rho_c = sqrtf(xf * xf + yf * yf) * P.fast_inv_dRho;
+  const float z_c = zf * P.fast_inv_dZ;
+  const bool steep = ay > ax;
+  const float tq = steep ? ax / ay : ay / ax;                       // a_input or 1 / a_input, in [0, 1]
+  const float f = tq * (45.0f - (tq - 1.0f) * (14.0f + 3.83f * tq));  // fast_atan, degrees
+  float deg = steep ? 90.0f - f : f;
+  if ((yf < 0.0f) != (xf < 0.0f)) deg = -deg;                        // copysign(., y / x)
+  if (!(xf > 0.0f)) deg += yf >= 0.0f ? 180.0f : -180.0f;
+  if (deg < 0.0f) deg += 360.0f;
+  const float phi_c = deg * P.fast_deg2cell;
+  // guard bands: 1e-3 cells + 4e-6 relative (float chain error < 1e-6 relative)
+  const float rr = rintf(rho_c), zr = rintf(z_c), pr = rintf(phi_c);
+  if (fabsf(rho_c - rr) < 1e-3f + 4e-6f * rho_c || fabsf(z_c - zr) < 1e-3f + 4e-6f * fabsf(z_c) ||
+      fabsf(phi_c - pr) < 1e-3f + 4e-6f * phi_c)
+    return false;
+  const int rho_idx = (int)rho_c, phi_idx = (int)phi_c, z_idx = (int)floorf(z_c);
+  const bool can = phi_idx < P.nPhi;  // rho_idx, phi_idx >= 0 by construction
+  const bool inside = can && z_idx >= 0 && rho_idx < P.nRho && z_idx < P.nZ;
+  const bool cast = can && P.visibility_check;
+  inside_out = inside;
+  cast_out = cast;
+  if (inside || cast) {
+    rec.rho = rho_idx;
+    rec.z = z_idx;
+    rec.phi_flags = (uint32_t)phi_idx | (inside ? kRecInside : 0u);
+    rec.t = t;
+  }
+  return true;
+}
+
 // CTA-wide exclusive scan of data[0,n) in shared memory (in place); returns the total.
 // Each thread scans a contiguous slice, slices are combined with warp shuffles.
 __device__ __forceinline__ int block_exclusive_scan(int *data, int n, int *s_warp /*[33]*/) {
@@ -276,13 +328,14 @@ __device__ __forceinline__ int work_column(const MapParams &P, const RayRecord &
 
 template <int kMode>
 __global__ void __launch_bounds__(kProjThreads) k_project(MapParams P, DeviceBuffers D, FrameParams F) {
-  extern __shared__ int s_proj[];  // [warps][nCol] per-warp counts -> exclusive prefix over warps, [nCol] totals, [nCol] offsets, [nCol] contribution bounds
+  // shared: [warps][W] per-warp counts -> exclusive prefix over warps, [W] totals, [W] offsets, [W] contribution bounds,
+  // where W is the span of work columns this tile touches (indices are relative to a per-tile base, modulo nCol,
+  // so a tile that straddles phi = 0 still has a short span); sized for the worst case W = nCol
+  extern __shared__ int s_proj[];
   __shared__ int s_cnt[3];
   __shared__ int s_warp[33];
-  const int nPhi = P.nCol;  // work columns: phi, or (phi, side of the sensor row) when the columns are split
-  int *s_hist = s_proj + kProjWarps * nPhi;
-  int *s_off = s_hist + nPhi;
-  int *s_bnd = s_off + nPhi;
+  __shared__ int s_base, s_rmin, s_rmax;
+  const int nCol = P.nCol;  // work columns: phi, or (phi, side of the sensor row) when the columns are split
   const int N = F.n_total;
   const int tile0 = blockIdx.x * kProjTile;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -294,9 +347,12 @@ __global__ void __launch_bounds__(kProjThreads) k_project(MapParams P, DeviceBuf
     }
   }
   if (tile0 >= N) return;  // the grid is sized for cfg.max_points (graph replay)
-  for (int i = tid; i < kProjWarps * nPhi; i += kProjThreads) s_proj[i] = 0;
-  for (int i = tid; i < nPhi; i += kProjThreads) s_bnd[i] = 0;
   if (tid < 3) s_cnt[tid] = 0;
+  if (tid == 0) {
+    s_base = -1;
+    s_rmin = 0x7fffffff;
+    s_rmax = -1;
+  }
   const void *input = F.input;
   const int cols = F.cols;
   const int warp0 = tile0 + warp * (32 * kProjPts);
@@ -312,7 +368,6 @@ __global__ void __launch_bounds__(kProjThreads) k_project(MapParams P, DeviceBuf
     rec[j].phi_flags = 0xffffffffu;
     if (i < N) {
       double xs = 0, ys = 0, zs = 0;
-      bool valid = false;
       if (kMode != 0) {
         // project_depth, src/mlmap.cpp:329-346 (kMode 1: every pixel, v outer / u inner; kMode 2: the sampled pixels)
         int pix = i;
@@ -327,35 +382,88 @@ __global__ void __launch_bounds__(kProjThreads) k_project(MapParams P, DeviceBuf
         if (raw != 0) {
           const int v = pix / cols, u = pix - v * cols;
           const double depth = (double)(int)raw * P.inv_factor;
-          xs = (double)__fsub_rn((float)u, P.cx) * depth / (double)P.fx;
-          ys = (double)__fsub_rn((float)v, P.cy) * depth / (double)P.fy;
+          const double du = (double)__fsub_rn((float)u, P.cx) * depth, dv = (double)__fsub_rn((float)v, P.cy) * depth;
           zs = depth;
-          valid = true;
+          int inside = 0, cast = 0;
+          if (!point_to_record_fast(P, F, du * P.inv_fx, dv * P.inv_fy, zs, (uint32_t)i, rec[j], inside, cast)) {
+            xs = du / (double)P.fx;  // the reference's own operation order
+            ys = dv / (double)P.fy;
+            point_to_record(P, F, xs, ys, zs, (uint32_t)i, rec[j], inside, cast);
+          }
+          n_valid++;
+          n_inside += inside;
+          n_cast += cast;
         }
       } else {
         const double *xyz = reinterpret_cast<const double *>(input);
         xs = xyz[3 * (size_t)i];
         ys = xyz[3 * (size_t)i + 1];
         zs = xyz[3 * (size_t)i + 2];
-        valid = true;
-      }
-      if (valid) {
         int inside = 0, cast = 0;
-        point_to_record(P, F, xs, ys, zs, (uint32_t)i, rec[j], inside, cast);
+        if (!point_to_record_fast(P, F, xs, ys, zs, (uint32_t)i, rec[j], inside, cast))
+          point_to_record(P, F, xs, ys, zs, (uint32_t)i, rec[j], inside, cast);
         n_valid++;
         n_inside += inside;
         n_cast += cast;
       }
     }
   }
-  __syncthreads();  // shared arrays cleared
-  // ---- run-length merge + stable rank inside the warp's 128 points ----
+  __syncthreads();
+  // span of the touched work columns, relative to the column of some record of the tile
+  int col[kProjPts];
+  bool any = false;
+#pragma unroll
+  for (int j = 0; j < kProjPts; j++) {
+    col[j] = rec[j].phi_flags != 0xffffffffu ? work_column(P, rec[j]) : -1;
+    any = any || col[j] >= 0;
+  }
+  if (any && s_base < 0) atomicCAS(&s_base, -1, col[0] >= 0 ? col[0] : col[kProjPts - 1]);
+  __syncthreads();
+  const int base = s_base;
+  const int half = nCol >> 1;
+  {
+    int rlo = 0x7fffffff, rhi = -1;
+#pragma unroll
+    for (int j = 0; j < kProjPts; j++)
+      if (col[j] >= 0) {
+        int r = col[j] - base + half;  // in (-nCol/2 .. 3*nCol/2)
+        r = r < 0 ? r + nCol : (r >= nCol ? r - nCol : r);
+        col[j] = r;
+        rlo = min(rlo, r);
+        rhi = max(rhi, r);
+      }
+    rlo = __reduce_min_sync(0xffffffffu, rlo);
+    rhi = __reduce_max_sync(0xffffffffu, rhi);
+    if (lane == 0 && rhi >= 0) {
+      atomicMin(&s_rmin, rlo);
+      atomicMax(&s_rmax, rhi);
+    }
+  }
+  __syncthreads();
+  const int rmin = s_rmin;
+  const int W = s_rmax >= 0 ? s_rmax - rmin + 1 : 0;
+  int *s_hist = s_proj + kProjWarps * W;
+  int *s_off = s_hist + W;
+  int *s_bnd = s_off + W;
+  for (int i = tid; i < (kProjWarps + 3) * W; i += kProjThreads) s_proj[i] = 0;
+  // directory row of this tile: zero outside the span (the span itself is written at the end)
+  uint32_t *dir = D.rec_dir + (size_t)blockIdx.x * nCol;
+  if (W < nCol) {
+    if ((nCol & 3) == 0) {
+      uint4 *d4 = reinterpret_cast<uint4 *>(dir);
+      for (int i = tid; i < (nCol >> 2); i += kProjThreads) d4[i] = make_uint4(0, 0, 0, 0);
+    } else {
+      for (int i = tid; i < nCol; i += kProjThreads) dir[i] = 0;
+    }
+  }
+  __syncthreads();
+  // ---- run-length merge + stable rank inside the warp's points ----
   // Consecutive points (in input order) that land in the same awareness cell contribute the same
   // (key, odd) list back to back, so for every key their contributions are adjacent in the key's
   // insertion sequence.  One record with a repeat count is therefore exact for the ordered fold, the
   // first-insert stamps and the (idempotent) ray walk.  Runs are cut at the 32-point rounds and at
   // points without a record.
-  int *s_mine = s_proj + warp * nPhi;
+  int *s_mine = s_proj + warp * W;
   int rank[kProjPts];
 #pragma unroll
   for (int j = 0; j < kProjPts; j++) {
@@ -371,13 +479,13 @@ __global__ void __launch_bounds__(kProjThreads) k_project(MapParams P, DeviceBuf
       rec[j].phi_flags |= (uint32_t)m << kRecCountShift;
       // upper bound of the hit contributions of this record: 1 + 2*min(K(rho), nRho-1-rho)
       if (rec[j].phi_flags & kRecInside)
-        atomicAdd(&s_bnd[work_column(P, rec[j])], 1 + 2 * min(__ldg(&P.k_reach[rec[j].rho]), P.nRho - 1 - rec[j].rho));
+        atomicAdd(&s_bnd[col[j] - rmin], 1 + 2 * min(__ldg(&P.k_reach[rec[j].rho]), P.nRho - 1 - rec[j].rho));
     } else {
       rec[j].phi_flags = 0xffffffffu;
     }
     // stable rank of the record among the warp's records of the same column (rounds are in point order)
     const bool holds = rec[j].phi_flags != 0xffffffffu;
-    const int myphi = holds ? work_column(P, rec[j]) : -1 - lane;
+    const int myphi = holds ? col[j] - rmin : -1 - lane;
     const unsigned peers = __match_any_sync(0xffffffffu, myphi);
     const int before = __popc(peers & ((1u << lane) - 1));
     rank[j] = holds ? s_mine[myphi] + before : 0;
@@ -397,32 +505,37 @@ __global__ void __launch_bounds__(kProjThreads) k_project(MapParams P, DeviceBuf
     if (n_cast) atomicAdd(&s_cnt[2], n_cast);
   }
   __syncthreads();
-  // per column: exclusive prefix over the warps (warp order == point order) and the CTA total
-  for (int p = tid; p < nPhi; p += kProjThreads) {
+  // per touched column: exclusive prefix over the warps (warp order == point order) and the tile's total
+  for (int p = tid; p < W; p += kProjThreads) {
     int run = 0;
 #pragma unroll
     for (int w = 0; w < kProjWarps; w++) {
-      const int c = s_proj[w * nPhi + p];
-      s_proj[w * nPhi + p] = run;
+      const int c = s_proj[w * W + p];
+      s_proj[w * W + p] = run;
       run += c;
     }
     s_hist[p] = run;
     s_off[p] = run;
-    if (run) atomicAdd(&D.phi_hist[p], run);
-    if (s_bnd[p]) atomicAdd(&D.phi_bound[p], s_bnd[p]);
+    int c = p + rmin + base - half;  // back to the work column
+    c = c < 0 ? c + nCol : (c >= nCol ? c - nCol : c);
+    if (run) atomicAdd(&D.phi_hist[c], run);
+    if (s_bnd[p]) atomicAdd(&D.phi_bound[c], s_bnd[p]);
   }
   __syncthreads();
-  block_exclusive_scan(s_off, nPhi, s_warp);
-  // The CTA's records are written grouped by phi column into its own kProjTile-slot window of rec_lin,
-  // with one directory word per (CTA, column): offset << 16 | count.  k_column gathers from there.
+  block_exclusive_scan(s_off, W, s_warp);
+  // The tile's records are written grouped by work column into its own kProjTile-slot window of rec_lin,
+  // with one directory word per (tile, column): offset << 16 | count.  k_column gathers from there.
 #pragma unroll
   for (int j = 0; j < kProjPts; j++)
     if (rec[j].phi_flags != 0xffffffffu) {
-      const int p = work_column(P, rec[j]);
+      const int p = col[j] - rmin;
       D.rec_lin[(size_t)tile0 + s_off[p] + s_mine[p] + rank[j]] = rec[j];
     }
-  uint32_t *dir = D.rec_dir + (size_t)blockIdx.x * nPhi;
-  for (int p = tid; p < nPhi; p += kProjThreads) dir[p] = ((uint32_t)s_off[p] << 16) | (uint32_t)s_hist[p];
+  for (int p = tid; p < W; p += kProjThreads) {
+    int c = p + rmin + base - half;
+    c = c < 0 ? c + nCol : (c >= nCol ? c - nCol : c);
+    dir[c] = ((uint32_t)s_off[p] << 16) | (uint32_t)s_hist[p];
+  }
   if (tid == 0) {
     FrameCounters *fc = D.fc[F.parity];
     if (s_cnt[0]) atomicAdd(&fc->n_points, s_cnt[0]);

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -537,6 +538,7 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
 #undef MLM_MARK
   } else {
     // the whole frame is one launch of a 3-kernel graph; the per-frame values travel as kernel arguments
+    const auto t0 = std::chrono::steady_clock::now();
     const int gi = mode;
     cudaKernelNodeParams np[3] = {};
     np[0].func = mode == 1 ? (void *)k_project<1> : (mode == 2 ? (void *)k_project<2> : (void *)k_project<0>);
@@ -561,7 +563,16 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
     } else {
       for (int i = 0; i < 3; i++) CUDA_TRY(cudaGraphExecKernelNodeSetParams(h->graph_exec[gi], h->graph_nodes[gi][i], &np[i]));
     }
+    const auto t1 = std::chrono::steady_clock::now();
     CUDA_TRY(cudaGraphLaunch(h->graph_exec[gi], s));
+    const auto t2 = std::chrono::steady_clock::now();
+    if (getenv("MLM_DEBUG_HOST_TIMING")) {
+      static double acc[2] = {0, 0};
+      static int cnt = 0;
+      acc[0] += std::chrono::duration<double, std::micro>(t1 - t0).count();
+      acc[1] += std::chrono::duration<double, std::micro>(t2 - t1).count();
+      if (++cnt % 50 == 0) fprintf(stderr, "host us: setparams %.2f launch %.2f\n", acc[0] / cnt, acc[1] / cnt);
+    }
   }
   h->launches += 3;
   CUDA_TRY(cudaStreamSynchronize(s));
@@ -833,6 +844,11 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   P.fx = cfg->cam_fx;
   P.fy = cfg->cam_fy;
   P.inv_factor = 1.0 / 1000.0;  // src/mlmap.h:85-86
+  P.inv_fx = 1.0 / (double)cfg->cam_fx;
+  P.inv_fy = 1.0 / (double)cfg->cam_fy;
+  P.fast_inv_dRho = (float)(1.0 / P.dRho);
+  P.fast_inv_dZ = (float)(1.0 / P.dZ);
+  P.fast_deg2cell = (float)((M_PI / 180) / P.dPhi);
   // glibc dispatches __logf to its FMA build when FMA and AVX2 are usable (ifunc-fma.h)
   P.log10f_fma = (__builtin_cpu_supports("fma") && __builtin_cpu_supports("avx2")) ? 1 : 0;
   P.lvg_margin = P.n + 1;

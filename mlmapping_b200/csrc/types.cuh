@@ -57,6 +57,8 @@ struct MapParams {
   // camera (include/mlmap.h:85-86,92)
   float cx, cy, fx, fy;
   double inv_factor;
+  double inv_fx, inv_fy;  // fl(1/fx), fl(1/fy): approximate projection of the guarded fast path only
+  float fast_inv_dRho, fast_inv_dZ, fast_deg2cell;  // float scale factors of the guarded fast path (cells per metre / per degree)
   int log10f_fma;         // which glibc __logf variant the host CPU dispatches to
   // local voxel grid (frame-local staging) geometry
   int lvg_dim_xy, lvg_dim_z;   // cells per axis
