@@ -437,7 +437,7 @@ class MLMap:
         return dict(zip(FRAME_KERNELS, [float(v) for v in ms]))
 
     def debug_phase_cycles(self) -> np.ndarray:
-        n = 2 * int(360 / self.cfg.am_d_phi_deg)  # work columns: up to two half columns per phi
+        n = 2 * int(360 / self.cfg.am_d_phi_deg) + 256  # work columns (up to two half columns per phi) + per-CTA rows of k_frame
         out = np.zeros((n, 16), dtype=np.int64)
         self._check(self._lib.mlm_debug_phase_cycles(self._h, out.ctypes.data, out.size))
         return out

@@ -310,15 +310,13 @@ __device__ __forceinline__ int block_exclusive_scan(int *data, int n, int *s_war
 
 // kMode: 0 = sensor-frame points (xyz doubles), 1 = full depth image (every pixel, row-major),
 //        2 = sampled depth pixels: input is uint2 {pixel index, raw depth} in sampling order (src/mlmap.cpp:321-346)
-// One CTA owns a tile of kProjTile consecutive points; warp w owns the 32*kProjPts consecutive points
-// of the tile and visits them in kProjPts rounds of 32 (64-byte depth-row loads),
+// One CTA owns a tile of F.tile_pts consecutive points (a multiple of 32); warp w owns a run of consecutive
+// 32-point rounds of the tile (at most kProjMaxPts, 64-byte depth-row loads each),
 // so "point order" inside the tile is (warp, round, lane) and everything that has to follow point order is
-// warp-local except one exclusive scan over the 8 warps.
-constexpr int kProjThreads = 512;
-constexpr int kProjWarps = kProjThreads / 32;
-constexpr int kProjPts = 2;                          // points per thread
-constexpr int kProjTile = kProjThreads * kProjPts;   // points per CTA = slots of its rec_lin window
-__host__ __device__ inline size_t project_smem_bytes(int nPhi) { return (size_t)(kProjWarps + 3) * nPhi * sizeof(int); }
+// warp-local except one exclusive scan over the warps.
+constexpr int kProjThreads = 512;                    // stand-alone k_project launch
+constexpr int kProjMaxPts = 4;                       // upper bound of rounds per warp: tile_pts <= 128 * warps
+__host__ __device__ inline size_t project_smem_bytes(int nCol, int threads) { return (size_t)(threads / 32 + 3) * nCol * sizeof(int); }
 
 // work column of a record: its phi column, or (phi, side) when the columns are split at the sensor row
 __device__ __forceinline__ int work_column(const MapParams &P, const RayRecord &rc) {
@@ -327,21 +325,26 @@ __device__ __forceinline__ int work_column(const MapParams &P, const RayRecord &
 }
 
 template <int kMode>
-__global__ void __launch_bounds__(kProjThreads) k_project(MapParams P, DeviceBuffers D, FrameParams F) {
+__device__ __forceinline__ void project_tile(const MapParams &P, DeviceBuffers &D, const FrameParams &F, const int tile,
+                                             int *s_proj) {
   // shared: [warps][W] per-warp counts -> exclusive prefix over warps, [W] totals, [W] offsets, [W] contribution bounds,
   // where W is the span of work columns this tile touches (indices are relative to a per-tile base, modulo nCol,
   // so a tile that straddles phi = 0 still has a short span); sized for the worst case W = nCol
-  extern __shared__ int s_proj[];
   __shared__ int s_cnt[3];
   __shared__ int s_warp[33];
   __shared__ int s_base, s_rmin, s_rmax;
   const int nCol = P.nCol;  // work columns: phi, or (phi, side of the sensor row) when the columns are split
   const int N = F.n_total;
-  const int tile0 = blockIdx.x * kProjTile;
+  const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+  // the tile's 32-point rounds are dealt to the warps in order, as evenly as they go (<= kProjMaxPts each)
+  const int rounds = F.tile_pts >> 5;
+  const int r0 = (int)(((long long)(threadIdx.x >> 5) * rounds) / nwarps), r1 = (int)(((long long)((threadIdx.x >> 5) + 1) * rounds) / nwarps);
+  const int pts = r1 - r0;
+  const int tile0 = tile * F.tile_pts;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (P.split && blockIdx.x == 0) {
+  if (P.split && tile == 0) {
     // the one miss-bitmap row both half columns of a phi write (atomicOr in k_column) starts the frame empty
-    for (int i = tid; i < P.nPhi * P.words_per_row; i += kProjThreads) {
+    for (int i = tid; i < P.nPhi * P.words_per_row; i += nthreads) {
       const int ph = i / P.words_per_row;
       D.miss_bitmap[(size_t)ph * P.col_words + P.n_below * P.words_per_row + (i - ph * P.words_per_row)] = 0;
     }
@@ -355,18 +358,18 @@ __global__ void __launch_bounds__(kProjThreads) k_project(MapParams P, DeviceBuf
   }
   const void *input = F.input;
   const int cols = F.cols;
-  const int warp0 = tile0 + warp * (32 * kProjPts);
+  const int warp0 = tile0 + r0 * 32;
   // ---- the points of this thread: projection, transform, cylindrical index (independent chains) ----
-  RayRecord rec[kProjPts];
+  RayRecord rec[kProjMaxPts];
   int n_valid = 0, n_inside = 0, n_cast = 0;
 #pragma unroll
-  for (int j = 0; j < kProjPts; j++) {
+  for (int j = 0; j < kProjMaxPts; j++) {
     const int i = warp0 + j * 32 + lane;
     rec[j].rho = 0;
     rec[j].z = 0;
     rec[j].t = (uint32_t)i;
     rec[j].phi_flags = 0xffffffffu;
-    if (i < N) {
+    if (j < pts && i < N) {
       double xs = 0, ys = 0, zs = 0;
       if (kMode != 0) {
         // project_depth, src/mlmap.cpp:329-346 (kMode 1: every pixel, v outer / u inner; kMode 2: the sampled pixels)
@@ -410,21 +413,26 @@ __global__ void __launch_bounds__(kProjThreads) k_project(MapParams P, DeviceBuf
   }
   __syncthreads();
   // span of the touched work columns, relative to the column of some record of the tile
-  int col[kProjPts];
+  int col[kProjMaxPts];
   bool any = false;
 #pragma unroll
-  for (int j = 0; j < kProjPts; j++) {
+  for (int j = 0; j < kProjMaxPts; j++) {
     col[j] = rec[j].phi_flags != 0xffffffffu ? work_column(P, rec[j]) : -1;
     any = any || col[j] >= 0;
   }
-  if (any && s_base < 0) atomicCAS(&s_base, -1, col[0] >= 0 ? col[0] : col[kProjPts - 1]);
+  if (any && s_base < 0) {
+    int c0 = -1;
+#pragma unroll
+    for (int j = kProjMaxPts - 1; j >= 0; j--) c0 = col[j] >= 0 ? col[j] : c0;
+    atomicCAS(&s_base, -1, c0);
+  }
   __syncthreads();
   const int base = s_base;
   const int half = nCol >> 1;
   {
     int rlo = 0x7fffffff, rhi = -1;
 #pragma unroll
-    for (int j = 0; j < kProjPts; j++)
+    for (int j = 0; j < kProjMaxPts; j++)
       if (col[j] >= 0) {
         int r = col[j] - base + half;  // in (-nCol/2 .. 3*nCol/2)
         r = r < 0 ? r + nCol : (r >= nCol ? r - nCol : r);
@@ -442,18 +450,18 @@ __global__ void __launch_bounds__(kProjThreads) k_project(MapParams P, DeviceBuf
   __syncthreads();
   const int rmin = s_rmin;
   const int W = s_rmax >= 0 ? s_rmax - rmin + 1 : 0;
-  int *s_hist = s_proj + kProjWarps * W;
+  int *s_hist = s_proj + nwarps * W;
   int *s_off = s_hist + W;
   int *s_bnd = s_off + W;
-  for (int i = tid; i < (kProjWarps + 3) * W; i += kProjThreads) s_proj[i] = 0;
+  for (int i = tid; i < (nwarps + 3) * W; i += nthreads) s_proj[i] = 0;
   // directory row of this tile: zero outside the span (the span itself is written at the end)
-  uint32_t *dir = D.rec_dir + (size_t)blockIdx.x * nCol;
+  uint32_t *dir = D.rec_dir + (size_t)tile * nCol;
   if (W < nCol) {
     if ((nCol & 3) == 0) {
       uint4 *d4 = reinterpret_cast<uint4 *>(dir);
-      for (int i = tid; i < (nCol >> 2); i += kProjThreads) d4[i] = make_uint4(0, 0, 0, 0);
+      for (int i = tid; i < (nCol >> 2); i += nthreads) d4[i] = make_uint4(0, 0, 0, 0);
     } else {
-      for (int i = tid; i < nCol; i += kProjThreads) dir[i] = 0;
+      for (int i = tid; i < nCol; i += nthreads) dir[i] = 0;
     }
   }
   __syncthreads();
@@ -464,9 +472,11 @@ __global__ void __launch_bounds__(kProjThreads) k_project(MapParams P, DeviceBuf
   // first-insert stamps and the (idempotent) ray walk.  Runs are cut at the 32-point rounds and at
   // points without a record.
   int *s_mine = s_proj + warp * W;
-  int rank[kProjPts];
+  int rank[kProjMaxPts];
 #pragma unroll
-  for (int j = 0; j < kProjPts; j++) {
+  for (int j = 0; j < kProjMaxPts; j++) {
+    rank[j] = 0;
+    if (j >= pts) continue;  // warp-uniform: this warp owns fewer rounds
     const bool has = rec[j].phi_flags != 0xffffffffu;
     const int p_rho = __shfl_up_sync(0xffffffffu, rec[j].rho, 1);
     const int p_z = __shfl_up_sync(0xffffffffu, rec[j].z, 1);
@@ -506,10 +516,9 @@ __global__ void __launch_bounds__(kProjThreads) k_project(MapParams P, DeviceBuf
   }
   __syncthreads();
   // per touched column: exclusive prefix over the warps (warp order == point order) and the tile's total
-  for (int p = tid; p < W; p += kProjThreads) {
+  for (int p = tid; p < W; p += nthreads) {
     int run = 0;
-#pragma unroll
-    for (int w = 0; w < kProjWarps; w++) {
+    for (int w = 0; w < nwarps; w++) {
       const int c = s_proj[w * W + p];
       s_proj[w * W + p] = run;
       run += c;
@@ -526,12 +535,12 @@ __global__ void __launch_bounds__(kProjThreads) k_project(MapParams P, DeviceBuf
   // The tile's records are written grouped by work column into its own kProjTile-slot window of rec_lin,
   // with one directory word per (tile, column): offset << 16 | count.  k_column gathers from there.
 #pragma unroll
-  for (int j = 0; j < kProjPts; j++)
+  for (int j = 0; j < kProjMaxPts; j++)
     if (rec[j].phi_flags != 0xffffffffu) {
       const int p = col[j] - rmin;
       D.rec_lin[(size_t)tile0 + s_off[p] + s_mine[p] + rank[j]] = rec[j];
     }
-  for (int p = tid; p < W; p += kProjThreads) {
+  for (int p = tid; p < W; p += nthreads) {
     int c = p + rmin + base - half;
     c = c < 0 ? c + nCol : (c >= nCol ? c - nCol : c);
     dir[c] = ((uint32_t)s_off[p] << 16) | (uint32_t)s_hist[p];
@@ -542,6 +551,12 @@ __global__ void __launch_bounds__(kProjThreads) k_project(MapParams P, DeviceBuf
     if (s_cnt[1]) atomicAdd(&fc->n_inside, s_cnt[1]);
     if (s_cnt[2]) atomicAdd(&fc->n_cast, s_cnt[2]);
   }
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(kProjThreads) k_project(MapParams P, DeviceBuffers D, FrameParams F) {
+  extern __shared__ int s_proj_dyn[];
+  project_tile<kMode>(P, D, F, (int)blockIdx.x, s_proj_dyn);  // the grid is sized for cfg.max_points (graph replay)
 }
 
 // ---- K2: one CTA per phi column ------------------------------------------------------------------------
@@ -633,6 +648,61 @@ __device__ __forceinline__ void radix_pass(const uint64_t *src, uint64_t *dst, i
   __syncthreads();
 }
 
+// ---- resolve / allocate a subbox touched this frame (allocate_ram, include/map_local.h:215-231) ----
+// Hash find-or-insert and, for a new subbox, a pop from the free stack.  Blocks on the free stack are
+// always in the initial state ('u','u',0.f) — they are initialised when the pool is created and when a
+// block is returned — so allocation writes nothing.  Safe to run from many threads at once (one per subbox).
+__device__ __forceinline__ void resolve_one(const MapParams &P, const FrameParams &F, DeviceBuffers &D, FrameCounters *fc,
+                                            const int ls, const bool rearm_flag) {
+  int block = -3;
+  int lx = ls % P.lsg_dim_xy, ly = (ls / P.lsg_dim_xy) % P.lsg_dim_xy, lz = ls / (P.lsg_dim_xy * P.lsg_dim_xy);
+  int g[3] = {lx + F.lsg_base[0], ly + F.lsg_base[1], lz + F.lsg_base[2]};
+  uint64_t key;
+  if (!pack_glb(g, key)) {
+    fc->error = kErrRange;
+  } else {
+    uint32_t slot = ht_hash(key) & P.ht_mask;
+    bool done = false;
+    for (uint32_t probe = 0; probe <= P.ht_mask && !done; probe++) {
+      uint64_t k = __ldcg(&D.ht_key[slot]);
+      if (k == kEmptyKey) {
+        unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&D.ht_key[slot]),
+                                           (unsigned long long)kEmptyKey, (unsigned long long)key);
+        if (old == kEmptyKey) {
+          int top = atomicSub(D.free_top, 1) - 1;
+          if (top < 0) {
+            atomicAdd(D.free_top, 1);
+            D.ht_val[slot] = -3;  // key stays so the table is consistent; the subbox is unusable
+            fc->error = kErrPool;
+          } else {
+            block = D.free_stack[top];
+            D.ht_val[slot] = block;
+            atomicAdd(&fc->n_new_blocks, 1);
+          }
+          done = true;
+          break;
+        }
+        k = (uint64_t)old;
+      }
+      if (k == key) {
+        block = __ldcg(&D.ht_val[slot]);
+        done = true;
+        break;
+      }
+      slot = (slot + 1) & P.ht_mask;
+    }
+    if (!done) fc->error = kErrPool;
+  }
+  D.lsg_block[ls] = block;
+  if (rearm_flag) D.lsg_flag[ls] = 0;
+}
+// all subboxes on the frame's touched list, one per thread of the given stride
+__device__ __forceinline__ void resolve_subboxes(const MapParams &P, const FrameParams &F, DeviceBuffers &D,
+                                                 FrameCounters *fc, int first, int stride) {
+  const int n = *reinterpret_cast<volatile int *>(&fc->n_touched_sub);
+  for (int i = first; i < n; i += stride) resolve_one(P, F, D, fc, __ldcg(&D.touched_sub[i]), true);
+}
+
 __device__ __forceinline__ void touch_subbox(const MapParams &P, const FrameParams &F, DeviceBuffers &D,
                                              FrameCounters *fc, const int g[3]) {
   if (F.stage_only) return;  // sharded staging: the subbox belongs to its owner rank
@@ -645,6 +715,9 @@ __device__ __forceinline__ void touch_subbox(const MapParams &P, const FramePara
     if (atomicExch(&D.lsg_flag[ls], 1) == 0) {
       int pos = atomicAdd(&fc->n_touched_sub, 1);
       D.touched_sub[pos] = ls;
+      // k_frame: the first toucher resolves the subbox on the spot (no resolve phase, one device barrier less);
+      // the flag stays up for the rest of the frame and is rearmed by the fusion's tail
+      if (F.inline_resolve) resolve_one(P, F, D, fc, ls, false);
     }
   }
 }
@@ -734,62 +807,6 @@ __device__ __forceinline__ void compact_bits(const uint32_t *bm, int w0, int w1,
   }
 }
 
-// ---- resolve / allocate the subboxes touched this frame (allocate_ram, include/map_local.h:215-231) ----
-// Run by the LAST k_column CTA to finish (ticket): one thread per touched subbox does the hash
-// find-or-insert and, for a new subbox, pops a block from the free stack.  Blocks on the free
-// stack are always in the initial state ('u','u',0.f) — they are initialised when the pool is
-// created and when a block is returned — so allocation writes nothing.
-__device__ __forceinline__ void resolve_subboxes(const MapParams &P, const FrameParams &F, DeviceBuffers &D,
-                                                 FrameCounters *fc) {
-  const int n = *reinterpret_cast<volatile int *>(&fc->n_touched_sub);
-  int n_new = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int ls = __ldcg(&D.touched_sub[i]);
-    int block = -3;
-    int lx = ls % P.lsg_dim_xy, ly = (ls / P.lsg_dim_xy) % P.lsg_dim_xy, lz = ls / (P.lsg_dim_xy * P.lsg_dim_xy);
-    int g[3] = {lx + F.lsg_base[0], ly + F.lsg_base[1], lz + F.lsg_base[2]};
-    uint64_t key;
-    if (!pack_glb(g, key)) {
-      fc->error = kErrRange;
-    } else {
-      uint32_t slot = ht_hash(key) & P.ht_mask;
-      bool done = false;
-      for (uint32_t probe = 0; probe <= P.ht_mask && !done; probe++) {
-        uint64_t k = D.ht_key[slot];
-        if (k == kEmptyKey) {
-          unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&D.ht_key[slot]),
-                                             (unsigned long long)kEmptyKey, (unsigned long long)key);
-          if (old == kEmptyKey) {
-            int top = atomicSub(D.free_top, 1) - 1;
-            if (top < 0) {
-              atomicAdd(D.free_top, 1);
-              D.ht_val[slot] = -3;  // key stays so the table is consistent; the subbox is unusable
-              fc->error = kErrPool;
-            } else {
-              block = D.free_stack[top];
-              D.ht_val[slot] = block;
-              n_new++;
-            }
-            done = true;
-            break;
-          }
-          k = (uint64_t)old;
-        }
-        if (k == key) {
-          block = D.ht_val[slot];
-          done = true;
-          break;
-        }
-        slot = (slot + 1) & P.ht_mask;
-      }
-      if (!done) fc->error = kErrPool;
-    }
-    D.lsg_block[ls] = block;
-    D.lsg_flag[ls] = 0;
-  }
-  if (n_new) atomicAdd(&fc->n_new_blocks, n_new);
-}
-
 // bytes of k_column's shared memory in front of the two key buffers
 __host__ __device__ inline size_t col_smem_prefix_bytes(int col_words, int nRho, int nCol) {
   return (((size_t)2 * col_words + kCntTotal + kColWarps + (size_t)kOddsRows * nRho + nRho + kMapCap) * 4 + (size_t)nCol * 2 + 15) & ~(size_t)15;
@@ -860,7 +877,7 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
     off = s_off;
   }
   {
-    const int nb = (F.n_total + kProjTile - 1) / kProjTile;   // CTAs of k_project
+    const int nb = (F.n_total + F.tile_pts - 1) / F.tile_pts;   // tiles of the projection
     const int per = (nb + (int)blockDim.x - 1) / (int)blockDim.x;
     const int b0 = min(tid * per, nb), b1 = min(b0 + per, nb);
     uint32_t dsave[4];
@@ -869,11 +886,11 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
     for (int q = 0; q < 4; q++) {
       dsave[q] = 0;
       if (b0 + q < b1) {
-        dsave[q] = __ldg(&D.rec_dir[(size_t)(b0 + q) * P.nCol + vc]);
+        dsave[q] = __ldcg(&D.rec_dir[(size_t)(b0 + q) * P.nCol + vc]);
         mine += (int)(dsave[q] & 0xffffu);
       }
     }
-    for (int b = b0 + 4; b < b1; b++) mine += (int)(__ldg(&D.rec_dir[(size_t)b * P.nCol + vc]) & 0xffffu);
+    for (int b = b0 + 4; b < b1; b++) mine += (int)(__ldcg(&D.rec_dir[(size_t)b * P.nCol + vc]) & 0xffffu);
     // exclusive scan of `mine` over threads (thread order == CTA order)
     int incl = mine;
     const int lane = lane_id(), w = tid >> 5, nw = blockDim.x >> 5;
@@ -896,9 +913,9 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
     __syncthreads();
     int dst = s_warp[w] + incl - mine;
     for (int b = b0; b < b1; b++) {
-      const uint32_t d = b - b0 < 4 ? dsave[b - b0] : __ldg(&D.rec_dir[(size_t)b * P.nCol + vc]);
+      const uint32_t d = b - b0 < 4 ? dsave[b - b0] : __ldcg(&D.rec_dir[(size_t)b * P.nCol + vc]);
       const int c = (int)(d & 0xffffu);
-      const int src = b * kProjTile + (int)(d >> 16);
+      const int src = b * F.tile_pts + (int)(d >> 16);
       for (int r = 0; r < c; r++) {
         if (big) D.rec_col[off + dst + r] = D.rec_lin[src + r];  // oversized column: materialise the records
         else s_map[dst + r] = src + r;
@@ -1253,11 +1270,9 @@ __device__ __forceinline__ int column_weight(const DeviceBuffers &D, int vc) { r
 // Persistent kernel: one CTA per SM pulls work columns, heaviest first, from a queue every CTA derives
 // identically (stable counting sort of the per-column weights k_project accumulated), so a depth camera's
 // ~80 lit columns (160 halves) spread over all SMs instead of one SM per column.
-__global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBuffers D, FrameParams F) {
-  extern __shared__ __align__(16) unsigned char s_raw[];
-  FrameCounters *fc = D.fc[F.parity];
+__device__ __forceinline__ void column_phase(const MapParams &P, DeviceBuffers &D, const FrameParams &F, unsigned char *s_raw) {
   const int tid = threadIdx.x;
-  __shared__ int s_last, s_item, s_wmax, s_nactive;
+  __shared__ int s_item, s_wmax, s_nactive;
   // shared memory: [miss bitmap][end-cell bitmap][radix counters][warp sums][odds table][k_reach][record index map][queue order][keys A][keys B]
   uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_raw) + 2 * P.col_words;
   uint32_t *s_wsum = s_cnt + kCntTotal;
@@ -1272,11 +1287,30 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
     s_nactive = 0;
   }
   __syncthreads();
-  auto is_active = [&](int vc) {
+  // per work column: records (0 = idle this frame or cast by another rank) and queue weight, loaded once
+  int *s_nrec = reinterpret_cast<int *>(s_keys);          // [nCol]; the key buffers are idle until the first item
+  int *s_wgt = s_nrec + P.nCol;
+  const bool sorted = P.nCol <= P.sort_cap_smem;  // 2 ints per column fit the first key buffer, the keys the second
+  auto not_mine = [&](int vc) {
     const int phi = P.split ? vc >> 1 : vc;
-    const bool not_mine = F.shard_world > 1 && (phi % F.shard_world) != F.shard_rank;  // another rank casts this column
-    return D.phi_hist[vc] > 0 && !not_mine;
+    return F.shard_world > 1 && (phi % F.shard_world) != F.shard_rank;  // another rank casts this column
   };
+  if (sorted) {
+    int my_active = 0;
+    for (int vc = tid; vc < P.nCol; vc += blockDim.x) {
+      const int n = not_mine(vc) ? 0 : D.phi_hist[vc];
+      const int w = n > 0 ? column_weight(D, vc) : 0;
+      s_nrec[vc] = n;
+      s_wgt[vc] = w;
+      if (n > 0) {
+        my_active++;
+        atomicMax(&s_wmax, w);
+      }
+    }
+    if (my_active) atomicAdd(&s_nactive, my_active);
+  }
+  __syncthreads();
+  auto is_active = [&](int vc) { return sorted ? s_nrec[vc] > 0 : (D.phi_hist[vc] > 0 && !not_mine(vc)); };
   // idle work columns: their own rows of the miss bitmap are empty this frame (spread over the CTAs)
   for (int vc = blockIdx.x; vc < P.nCol; vc += gridDim.x) {
     if (is_active(vc)) continue;
@@ -1287,30 +1321,28 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
   }
   // queue order: active work columns by descending weight bucket, ties by column index (deterministic, so
   // every CTA holds the same list); one 7-bit radix pass over (63 - bucket | column)
-  const bool sorted = P.nCol <= P.sort_cap_smem;
   int n_active = 0;
   if (sorted) {
-    int my_active = 0;
-    for (int vc = tid; vc < P.nCol; vc += blockDim.x)
-      if (is_active(vc)) {
-        my_active++;
-        atomicMax(&s_wmax, column_weight(D, vc));
-      }
-    if (my_active) atomicAdd(&s_nactive, my_active);
-    __syncthreads();
     n_active = s_nactive;
     int sh = 0;
     while ((s_wmax >> sh) > 63) sh++;
-    for (int vc = tid; vc < P.nCol; vc += blockDim.x) {
-      const uint64_t digit = is_active(vc) ? (uint64_t)(63 - (column_weight(D, vc) >> sh)) : 64ull;
-      s_keys[vc] = (digit << 16) | (uint64_t)vc;
-    }
+    uint64_t *q_src = s_keys + P.sort_cap_smem;           // second key buffer: sort input; output lands in the first
+    uint64_t kq[8];
+    int nk = 0;
+    for (int vc = tid; vc < P.nCol && nk < 8; vc += blockDim.x)
+      kq[nk++] = ((s_nrec[vc] > 0 ? (uint64_t)(63 - (s_wgt[vc] >> sh)) : 64ull) << 16) | (uint64_t)vc;
+    __syncthreads();                                        // s_nrec / s_wgt are dead from here on
+    nk = 0;
+    for (int vc = tid; vc < P.nCol && nk < 8; vc += blockDim.x) q_src[vc] = kq[nk++];
     __syncthreads();
-    radix_pass(s_keys, s_keys + P.sort_cap_smem, P.nCol, 16, 7, s_cnt, s_wsum);
-    for (int i = tid; i < n_active; i += blockDim.x) s_order[i] = (uint16_t)(s_keys[P.sort_cap_smem + i] & 0xffffu);
+    radix_pass(q_src, s_keys, P.nCol, 16, 7, s_cnt, s_wsum);
+    for (int i = tid; i < n_active; i += blockDim.x) s_order[i] = (uint16_t)(s_keys[i] & 0xffffu);
   } else {
     n_active = P.nCol;  // more work columns than the sort scratch holds: plain column order, idle ones skipped below
   }
+#ifdef MLM_PHASE_TIMING
+  if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); D.debug_cycles[(P.nCol + blockIdx.x) * 16 + 7] = (long long)t_; }
+#endif
   for (;;) {
     __syncthreads();  // the previous item is done with shared memory; s_order is in place
     if (tid == 0) s_item = atomicAdd(D.col_queue, 1);
@@ -1321,6 +1353,14 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
     if (!sorted && !is_active(vc)) continue;
     column_item(P, D, F, vc, s_raw);
   }
+}
+
+__global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBuffers D, FrameParams F) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  FrameCounters *fc = D.fc[F.parity];
+  const int tid = threadIdx.x;
+  __shared__ int s_last;
+  column_phase(P, D, F, s_raw);
   // the last CTA to run dry resolves the touched subboxes for k_fuse and rearms the queue
   __threadfence();
   __syncthreads();
@@ -1332,7 +1372,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_column(MapParams P, DeviceBu
       *D.col_queue = 0;
     }
     __threadfence();
-    if (!F.stage_only) resolve_subboxes(P, F, D, fc);
+    if (!F.stage_only) resolve_subboxes(P, F, D, fc, threadIdx.x, blockDim.x);
   }
 }
 
@@ -1344,10 +1384,11 @@ __device__ __constant__ uint32_t c_bucket_chain[kBucketChainLen] = {
 
 // frame counters -> mapped pinned host memory (zero-copy store; visible to the host after the stream sync)
 __device__ __forceinline__ void publish_counters(const DeviceBuffers &D, FrameCounters *fc) {
-  const volatile int *src = reinterpret_cast<const volatile int *>(fc);
-  volatile int *dst = reinterpret_cast<volatile int *>(D.host_fc);
-  for (int i = 0; i < (int)(sizeof(FrameCounters) / sizeof(int)); i++) dst[i] = src[i];
-  __threadfence_system();
+  // called by one whole warp: lane i moves word i (independent L2 reads and PCIe writes, not a serial chain)
+  const int lane = threadIdx.x & 31;
+  const int n = (int)(sizeof(FrameCounters) / sizeof(int));
+  for (int i = lane; i < n; i += 32) reinterpret_cast<volatile int *>(D.host_fc)[i] = __ldcg(reinterpret_cast<const int *>(fc) + i);
+  // no system-scope fence: the host reads the counters only after the stream has drained, which orders them
 }
 
 // ---- K5: clamped log-odds fusion, one thread per touched cell (map_local.cpp:147-207) ---------------
@@ -1355,16 +1396,25 @@ constexpr int kFuseLocal = 16;
 // kPhase 0: hits then misses (normal mode).  Exploration mode splits the pass so that update_observation can
 // look at the neighbours' state between them: kPhase 1 = hits only (LVG left intact), kPhase 2 = misses only.
 template <int kPhase>
-__global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D, FrameParams F) {
+__device__ __forceinline__ void fuse_body(const MapParams &P, DeviceBuffers &D, const FrameParams &F) {
   FrameCounters *fc = D.fc[F.parity];
   const uint32_t *act = D.act[F.parity];
   const int n_hit_frame = fc->n_hit;
   // a frame that crosses a libstdc++ rehash needs the slow ordering pass first (host re-launches)
   if (kPhase == 0 && F.order_mode == 0 && n_hit_frame > (int)F.bucket_count) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      fc->overflow = 1;
-      publish_counters(D, fc);
+    // every CTA takes a ticket so that the last one can rearm the launch-scoped counters safely
+    __shared__ int s_ovf_last;
+    if (threadIdx.x == 0) {
+      s_ovf_last = atomicAdd(D.fuse_ticket, 1) == (int)gridDim.x - 1;
+      if (s_ovf_last) {
+        *D.fuse_ticket = 0;
+        *D.grid_bar = 0;
+        fc->overflow = 1;
+        __threadfence();
+      }
     }
+    __syncthreads();
+    if (s_ovf_last && threadIdx.x < 32) publish_counters(D, fc);
     return;
   }
   const int n = min(fc->n_touched, P.max_touched);
@@ -1427,14 +1477,19 @@ __global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D, Fram
       uint64_t st0 = 0, st1 = 0, st2 = 0, st3 = 0;
       float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
       int cnt = 0;
+      // one walk over the list: only the next-pointer load is on the dependent chain, the node's stamp and
+      // probability loads overlap the following hop; entries 4..15 wait in a local array
+      uint64_t ls[kFuseLocal];
+      float lp[kFuseLocal];
       for (int h = head; h != kLvgEmpty; h = D.hit_next[h]) {
-        if (cnt < 4) {
+        if (cnt < kFuseLocal) {
           const uint64_t st = ((uint64_t)act[D.hit_bucket[h]] << 32) | D.hit_t[h];
           const float ph = D.hit_p[h];
           if (cnt == 0) { st0 = st; p0 = ph; }
           else if (cnt == 1) { st1 = st; p1 = ph; }
           else if (cnt == 2) { st2 = st; p2 = ph; }
-          else { st3 = st; p3 = ph; }
+          else if (cnt == 3) { st3 = st; p3 = ph; }
+          else { ls[cnt] = st; lp[cnt] = ph; }
         }
         cnt++;
       }
@@ -1459,6 +1514,26 @@ __global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D, Fram
         if (cnt > 1) apply_hit(p1);
         if (cnt > 2) apply_hit(p2);
         if (cnt > 3) apply_hit(p3);
+      } else if (cnt <= kFuseLocal) {
+        // 5..16 hits (near walls, where several thin cylindrical cells share a voxel): insertion sort of the
+        // collected entries by stamp, applied in descending order
+        ls[0] = st0; lp[0] = p0;
+        ls[1] = st1; lp[1] = p1;
+        ls[2] = st2; lp[2] = p2;
+        ls[3] = st3; lp[3] = p3;
+        for (int m = 1; m < cnt; m++) {
+          const uint64_t st = ls[m];
+          const float ph = lp[m];
+          int j = m;
+          while (j > 0 && ls[j - 1] < st) {
+            ls[j] = ls[j - 1];
+            lp[j] = lp[j - 1];
+            j--;
+          }
+          ls[j] = st;
+          lp[j] = ph;
+        }
+        for (int k = 0; k < cnt; k++) apply_hit(lp[k]);
       } else {
         uint64_t prev = ~0ull;
         for (int k = 0; k < cnt; k++) {
@@ -1514,12 +1589,19 @@ __global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D, Fram
     __shared__ int s_is_last;
     __threadfence();
     __syncthreads();
+#ifdef MLM_PHASE_TIMING
+    if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); D.debug_cycles[(P.nCol + blockIdx.x) * 16 + 8] = (long long)t_; }
+#endif
     if (threadIdx.x == 0) s_is_last = atomicAdd(D.fuse_ticket, 1) == (int)gridDim.x - 1;
     __syncthreads();
-    if (s_is_last && threadIdx.x == 0) {
-      *D.fuse_ticket = 0;
-      __threadfence();
-      fc->fused = 1;
+    if (s_is_last && threadIdx.x < 32) {
+      if (threadIdx.x == 0) {
+        *D.fuse_ticket = 0;
+        *D.grid_bar = 0;  // every CTA of a k_frame launch is past its last barrier once it has taken a ticket
+        fc->fused = 1;
+        __threadfence();
+      }
+      __syncwarp();
       publish_counters(D, fc);
     }
   }
@@ -1544,12 +1626,75 @@ __global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D, Fram
       uint32_t *am = D.act_miss[F.parity ^ 1];
       for (uint32_t i = gtid; i < Bm; i += nth) am[i] = 0xffffffffu;
     }
+    if (F.inline_resolve) {
+      const int nts = fc->n_touched_sub;
+      for (int i = gtid; i < nts; i += nth) D.lsg_flag[__ldcg(&D.touched_sub[i])] = 0;
+    }
     for (int i = gtid; i < P.nCol; i += nth) {
       D.phi_hist[i] = 0;
       D.phi_bound[i] = 0;
     }
     if (gtid < (int)(sizeof(FrameCounters) / sizeof(int))) reinterpret_cast<int *>(D.fc[F.parity ^ 1])[gtid] = 0;
   }
+}
+
+template <int kPhase>
+__global__ void __launch_bounds__(256) k_fuse(MapParams P, DeviceBuffers D, FrameParams F) {
+  fuse_body<kPhase>(P, D, F);
+}
+
+// ---- the whole frame as ONE cooperative launch: projection tiles, work columns, subbox resolve, fusion ----
+// One CTA per SM stays resident through the four phases; device-wide barriers replace three kernel
+// boundaries (each boundary costs a drain, a launch and a ramp-up that together outweigh the phase's own
+// tail on a ~70 us frame).  The barrier is a monotone counter in global memory: arrive with a release
+// add, spin on an acquire load; the last CTA through k_fuse's completion ticket rearms it.
+__device__ __forceinline__ void grid_barrier(int *counter, int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1);
+    int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+#ifdef MLM_PHASE_TIMING
+#define MLM_FRAME_WALL(i) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); D.debug_cycles[(P.nCol + blockIdx.x) * 16 + (i)] = (long long)t_; } } while (0)
+#else
+#define MLM_FRAME_WALL(i) do { } while (0)
+#endif
+template <int kMode>
+__global__ void __launch_bounds__(kColThreads, 1) k_frame(MapParams P, DeviceBuffers D, FrameParams F) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  FrameCounters *fc = D.fc[F.parity];
+  const int G = (int)gridDim.x;
+  MLM_FRAME_WALL(0);
+  // (1) projection: tile t of F.tile_pts points -> CTA t % G
+  {
+    const int n_tiles = (F.n_total + F.tile_pts - 1) / F.tile_pts;
+    for (int t = blockIdx.x; t < max(n_tiles, 1); t += G) {
+      project_tile<kMode>(P, D, F, t, reinterpret_cast<int *>(s_raw));
+      __syncthreads();
+    }
+  }
+  MLM_FRAME_WALL(1);
+  grid_barrier(D.grid_bar, G);
+  MLM_FRAME_WALL(2);
+  // (2) work columns (awareness update + staging into the frame-local voxel grid)
+  column_phase(P, D, F, s_raw);
+  MLM_FRAME_WALL(3);
+  grid_barrier(D.grid_bar, 2 * G);
+  MLM_FRAME_WALL(4);
+  MLM_FRAME_WALL(5);
+  // (3) the touched subboxes were resolved / allocated by their first toucher (F.inline_resolve)
+  if (blockIdx.x == 0 && threadIdx.x == 0) *D.col_queue = 0;
+  // (4) clamped log-odds fusion, next frame's resets, counters to the host
+  fuse_body<0>(P, D, F);
+  MLM_FRAME_WALL(6);
 }
 
 }  // namespace mlm

@@ -183,6 +183,11 @@ struct mlm_map {
   cudaGraphNode_t graph_nodes[3][3] = {};
   int use_graph = 1;
   int col_grid = 1;        // CTAs of the persistent k_column: one per SM, at most one per work column
+  int use_fused = 0;       // frames run as one cooperative k_frame launch
+  int frame_grid = 1;      // CTAs of k_frame (all co-resident)
+  cudaGraph_t fgraph[3] = {nullptr, nullptr, nullptr};
+  cudaGraphExec_t fgraph_exec[3] = {nullptr, nullptr, nullptr};
+  cudaGraphNode_t fgraph_node[3] = {nullptr, nullptr, nullptr};
   void *h_stage = nullptr;        // pinned input staging
   size_t stage_bytes = 0;
   void *d_input = nullptr;
@@ -391,14 +396,14 @@ int run_frame_explore(mlm_map *h, int mode, int N, mlm_frame_stats *stats) {
   cudaStream_t s = h->stream;
   FrameParams &F = *h->h_fp;
   const int parity = F.parity;
-  const int proj_grid = grid_for((size_t)std::max(N, 1), kProjTile);
+  const int proj_grid = grid_for((size_t)std::max(N, 1), kProjThreads * 2);
   F.order_mode = 1;  // rehash detection happens on the host below, not inside k_fuse
   if (mode == 1)
-    k_project<1><<<proj_grid, kProjThreads, project_smem_bytes(P.nCol), s>>>(P, h->D, F);
+    k_project<1><<<proj_grid, kProjThreads, project_smem_bytes(P.nCol, kProjThreads), s>>>(P, h->D, F);
   else if (mode == 2)
-    k_project<2><<<proj_grid, kProjThreads, project_smem_bytes(P.nCol), s>>>(P, h->D, F);
+    k_project<2><<<proj_grid, kProjThreads, project_smem_bytes(P.nCol, kProjThreads), s>>>(P, h->D, F);
   else
-    k_project<0><<<proj_grid, kProjThreads, project_smem_bytes(P.nCol), s>>>(P, h->D, F);
+    k_project<0><<<proj_grid, kProjThreads, project_smem_bytes(P.nCol, kProjThreads), s>>>(P, h->D, F);
   k_column<<<h->col_grid, kColThreads, h->col_smem_bytes, s>>>(P, h->D, F);
   FrameCounters mid;
   CUDA_TRY(cudaMemcpyAsync(&mid, h->D.fc[parity], sizeof(mid), cudaMemcpyDeviceToHost, s));
@@ -489,8 +494,10 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
   F.shard_rank = 0;
   F.shard_world = 1;
   F.stage_only = 0;
+  F.inline_resolve = 0;
   F.tbits = 1;
   while ((1ll << F.tbits) < (long long)std::max(N, 2)) F.tbits++;
+  F.tile_pts = kProjThreads * 2;  // stand-alone k_project: 512 threads x 2 rounds per warp
   // frame-local voxel grid origin: awareness bounding box around t_wa plus a margin
   const double R = P.nRho * P.dRho;
   F.lvg_base[0] = (int)floor((Twa.t[0] - R) / P.d_sub) - P.lvg_margin;
@@ -504,8 +511,8 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
     F.shard_world = h->shard_world;
     F.stage_only = 1;
     F.order_mode = 1;
-    const int pg = grid_for((size_t)std::max(N, 1), kProjTile);
-    k_project<0><<<pg, kProjThreads, project_smem_bytes(P.nCol), s>>>(P, h->D, F);
+    const int pg = grid_for((size_t)std::max(N, 1), kProjThreads * 2);
+    k_project<0><<<pg, kProjThreads, project_smem_bytes(P.nCol, kProjThreads), s>>>(P, h->D, F);
     k_column<<<h->col_grid, kColThreads, h->col_smem_bytes, s>>>(P, h->D, F);
     h->launches += 2;
     CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc[parity], sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
@@ -515,8 +522,8 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
   }
   if (P.explore) return run_frame_explore(h, mode, N, stats);
   const bool prof = h->profiling != 0;
-  const int full_grid = grid_for((size_t)P.max_points, kProjTile);
-  const int proj_grid = grid_for((size_t)std::max(N, 1), kProjTile);
+  const int full_grid = grid_for((size_t)P.max_points, kProjThreads * 2);
+  const int proj_grid = grid_for((size_t)std::max(N, 1), kProjThreads * 2);
   MapParams Pk = P;
   DeviceBuffers Dk = h->D;
   FrameParams Fk = F;
@@ -525,17 +532,45 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
 #define MLM_MARK(i) do { if (prof) cudaEventRecord(h->kev[i], s); } while (0)
     MLM_MARK(0);
     if (mode == 1)
-      k_project<1><<<proj_grid, kProjThreads, project_smem_bytes(P.nCol), s>>>(Pk, Dk, Fk);
+      k_project<1><<<proj_grid, kProjThreads, project_smem_bytes(P.nCol, kProjThreads), s>>>(Pk, Dk, Fk);
     else if (mode == 2)
-      k_project<2><<<proj_grid, kProjThreads, project_smem_bytes(P.nCol), s>>>(Pk, Dk, Fk);
+      k_project<2><<<proj_grid, kProjThreads, project_smem_bytes(P.nCol, kProjThreads), s>>>(Pk, Dk, Fk);
     else
-      k_project<0><<<proj_grid, kProjThreads, project_smem_bytes(P.nCol), s>>>(Pk, Dk, Fk);
+      k_project<0><<<proj_grid, kProjThreads, project_smem_bytes(P.nCol, kProjThreads), s>>>(Pk, Dk, Fk);
     MLM_MARK(1);
     k_column<<<h->col_grid, kColThreads, h->col_smem_bytes, s>>>(Pk, Dk, Fk);
     MLM_MARK(2);
     k_fuse<0><<<h->sm_count * 4, 256, 0, s>>>(Pk, Dk, Fk);
     MLM_MARK(3);
 #undef MLM_MARK
+  } else if (h->use_fused) {
+    // the whole frame is ONE cooperative kernel (k_frame), replayed as a single-node graph
+    const int G = h->frame_grid;
+    // one tile per CTA when the frame allows it: N points dealt evenly, in 32-point rounds, at most 128 per warp
+    Fk.tile_pts = std::min(kProjMaxPts * kColThreads, std::max(32, (((N + G - 1) / G) + 31) & ~31));
+    F.tile_pts = Fk.tile_pts;
+    Fk.inline_resolve = F.inline_resolve = 1;
+    const int gi = mode;
+    cudaKernelNodeParams np = {};
+    np.func = mode == 1 ? (void *)k_frame<1> : (mode == 2 ? (void *)k_frame<2> : (void *)k_frame<0>);
+    np.gridDim = dim3(G);
+    np.blockDim = dim3(kColThreads);
+    np.sharedMemBytes = (unsigned)h->col_smem_bytes;
+    np.kernelParams = kargs;
+    static const int direct = getenv("MLM_FUSED_DIRECT") ? atoi(getenv("MLM_FUSED_DIRECT")) : 0;
+    if (direct) {
+      CUDA_TRY(cudaLaunchCooperativeKernel(np.func, np.gridDim, np.blockDim, kargs, np.sharedMemBytes, s));
+    } else if (!h->fgraph_exec[gi]) {
+      CUDA_TRY(cudaGraphCreate(&h->fgraph[gi], 0));
+      CUDA_TRY(cudaGraphAddKernelNode(&h->fgraph_node[gi], h->fgraph[gi], nullptr, 0, &np));
+      cudaKernelNodeAttrValue av = {};
+      av.cooperative = 1;
+      CUDA_TRY(cudaGraphKernelNodeSetAttribute(h->fgraph_node[gi], cudaKernelNodeAttributeCooperative, &av));
+      CUDA_TRY(cudaGraphInstantiate(&h->fgraph_exec[gi], h->fgraph[gi], 0));
+    } else {
+      CUDA_TRY(cudaGraphExecKernelNodeSetParams(h->fgraph_exec[gi], h->fgraph_node[gi], &np));
+    }
+    if (!direct) CUDA_TRY(cudaGraphLaunch(h->fgraph_exec[gi], s));
   } else {
     // the whole frame is one launch of a 3-kernel graph; the per-frame values travel as kernel arguments
     const auto t0 = std::chrono::steady_clock::now();
@@ -544,7 +579,7 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
     np[0].func = mode == 1 ? (void *)k_project<1> : (mode == 2 ? (void *)k_project<2> : (void *)k_project<0>);
     np[0].gridDim = dim3(full_grid);  // fixed grid: CTAs beyond this frame's point count return at once
     np[0].blockDim = dim3(kProjThreads);
-    np[0].sharedMemBytes = (unsigned)(project_smem_bytes(P.nCol));
+    np[0].sharedMemBytes = (unsigned)(project_smem_bytes(P.nCol, kProjThreads));
     np[1].func = (void *)k_column;
     np[1].gridDim = dim3(h->col_grid);
     np[1].blockDim = dim3(kColThreads);
@@ -920,8 +955,27 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   CUDA_TRY_H(cudaHostAlloc((void **)&h->h_fc, sizeof(FrameCounters), cudaHostAllocMapped));
   memset(h->h_fc, 0, sizeof(FrameCounters));
   CUDA_TRY_H(cudaFuncSetAttribute(k_column, cudaFuncAttributeMaxDynamicSharedMemorySize, h->col_smem_bytes));
-  if (project_smem_bytes(P.nCol) > 48 * 1024) {
-    const int pb = (int)project_smem_bytes(P.nCol);
+  if ((long long)project_smem_bytes(P.nCol, kProjThreads) > (long long)max_optin - 1024) {
+    delete h;
+    g_last_error = "n_Phi too large for the projection's shared-memory histogram";
+    return MLM_ERR_INVALID_CONFIG;
+  }
+  // one cooperative launch per frame when every phase fits the resident CTA (not in exploration mode, whose
+  // ordered passes need extra kernels between the phases)
+  {
+    CUDA_TRY_H(cudaFuncSetAttribute(k_frame<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->col_smem_bytes));
+    CUDA_TRY_H(cudaFuncSetAttribute(k_frame<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->col_smem_bytes));
+    CUDA_TRY_H(cudaFuncSetAttribute(k_frame<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->col_smem_bytes));
+    int per_sm = 0, coop = 0;
+    CUDA_TRY_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame<1>, kColThreads, h->col_smem_bytes));
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    h->frame_grid = h->sm_count * std::min(per_sm, 1);
+    h->use_fused = coop && per_sm >= 1 && !P.explore &&
+                   project_smem_bytes(P.nCol, kColThreads) <= (size_t)h->col_smem_bytes;
+    if (const char *e = getenv("MLM_NO_FUSED")) if (atoi(e)) h->use_fused = 0;
+  }
+  if (project_smem_bytes(P.nCol, kProjThreads) > 48 * 1024) {
+    const int pb = (int)project_smem_bytes(P.nCol, kProjThreads);
     CUDA_TRY_H(cudaFuncSetAttribute(k_project<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
     CUDA_TRY_H(cudaFuncSetAttribute(k_project<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
     CUDA_TRY_H(cudaFuncSetAttribute(k_project<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
@@ -961,9 +1015,10 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   D.fc[1] = D.fc[0] + 1;
   TRY(dev_alloc(h, &D.col_ticket, 1));
   TRY(dev_alloc(h, &D.col_queue, 1));
+  TRY(dev_alloc(h, &D.grid_bar, 1));
   TRY(dev_alloc(h, &D.rec_lin, (size_t)P.max_points));
   TRY(dev_alloc(h, &D.rec_col, (size_t)P.max_points));
-  TRY(dev_alloc(h, &D.rec_dir, (size_t)((P.max_points + kProjTile - 1) / kProjTile) * P.nCol));
+  TRY(dev_alloc(h, &D.rec_dir, (size_t)(std::max((P.max_points + 1023) / 1024, h->sm_count + 1)) * P.nCol));
   TRY(dev_alloc(h, &D.phi_hist, (size_t)P.nCol));
   TRY(dev_alloc(h, &D.phi_bound, (size_t)P.nCol));
   TRY(dev_alloc(h, &D.col_scratch, (size_t)2 * P.max_points * P.contrib_per_point));
@@ -1028,8 +1083,8 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
     CUDA_TRY_H(cudaMemset(D.obs_flag, 0, (size_t)lsg_cells * 4));
   }
   TRY(dev_alloc(h, &D.cum, 4));
-  TRY(dev_alloc(h, &D.debug_cycles, (size_t)P.nCol * 16));
-  CUDA_TRY_H(cudaMemset(D.debug_cycles, 0, (size_t)P.nCol * 16 * sizeof(long long)));
+  TRY(dev_alloc(h, &D.debug_cycles, (size_t)(P.nCol + 256) * 16));
+  CUDA_TRY_H(cudaMemset(D.debug_cycles, 0, (size_t)(P.nCol + 256) * 16 * sizeof(long long)));
   h->sort_cap = P.explore ? (int)n_cells : P.max_hits;
   const size_t sort_pad = (size_t)next_pow2(h->sort_cap);
   TRY(dev_alloc(h, &h->d_sort_a, sort_pad));
@@ -1049,6 +1104,7 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   CUDA_TRY_H(cudaMemset(D.cum, 0, 4 * sizeof(int64_t)));
   CUDA_TRY_H(cudaMemset(D.col_ticket, 0, sizeof(int)));
   CUDA_TRY_H(cudaMemset(D.col_queue, 0, sizeof(int)));
+  CUDA_TRY_H(cudaMemset(D.grid_bar, 0, sizeof(int)));
   CUDA_TRY_H(cudaMemset(D.fc[0], 0, 2 * sizeof(FrameCounters)));
   CUDA_TRY_H(cudaMemset(D.act[0], 0xff, (size_t)h->act_cap * 4));
   CUDA_TRY_H(cudaMemset(D.act[1], 0xff, (size_t)h->act_cap * 4));
@@ -1080,6 +1136,8 @@ int mlm_destroy(mlm_handle h) {
   for (int i = 0; i < 3; i++) {
     if (h->graph_exec[i]) cudaGraphExecDestroy(h->graph_exec[i]);
     if (h->graph[i]) cudaGraphDestroy(h->graph[i]);
+    if (h->fgraph_exec[i]) cudaGraphExecDestroy(h->fgraph_exec[i]);
+    if (h->fgraph[i]) cudaGraphDestroy(h->fgraph[i]);
   }
   for (void *p : h->allocs) cudaFree(p);
   if (h->d_input) cudaFree(h->d_input);
@@ -1374,7 +1432,7 @@ int mlm_last_frame_kernel_ms(mlm_handle h, float ms[MLM_NUM_FRAME_KERNELS]) {
 }
 int mlm_debug_phase_cycles(mlm_handle h, long long *out, size_t cap) {
   if (!h || !out) return MLM_ERR_INVALID_ARG;
-  size_t n = std::min(cap, (size_t)h->P.nCol * 16);
+  size_t n = std::min(cap, (size_t)(h->P.nCol + 256) * 16);
   CUDA_TRY(cudaMemcpy(out, h->D.debug_cycles, n * sizeof(long long), cudaMemcpyDeviceToHost));
   return MLM_OK;
 }

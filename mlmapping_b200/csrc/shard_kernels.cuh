@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) k_shard_ingest(MapParams P, DeviceBuffers
 
 // standalone resolve (on one GPU the last k_column CTA does this)
 __global__ void __launch_bounds__(1024) k_shard_resolve(MapParams P, DeviceBuffers D, FrameParams F) {
-  resolve_subboxes(P, F, D, D.fc[F.parity]);
+  resolve_subboxes(P, F, D, D.fc[F.parity], threadIdx.x, blockDim.x);
 }
 
 __global__ void k_shard_reset_counters(DeviceBuffers D, FrameParams F) {

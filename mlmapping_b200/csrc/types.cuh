@@ -95,9 +95,11 @@ struct FrameParams {
   int lvg_base[3];  // global cell coordinate of local voxel grid origin
   int lsg_base[3];  // global subbox coordinate of local submap grid origin
   int tbits;        // bits needed for a point stamp this frame (ceil(log2(#points)))
+  int tile_pts;     // points per projection tile (multiple of 32, <= 128 per warp of the projecting CTA) = slots of its rec_lin window
   uint32_t bucket_count_miss;  // emulated miss_idx_set.bucket_count() at frame start (exploration mode)
   int shard_rank, shard_world;  // sharded staging: this rank casts the columns phi % world == rank
   int stage_only;   // 1: k_column stages into the voxel grid only (no subbox resolve; records go to the owners)
+  int inline_resolve; // 1 (k_frame): the first thread to touch a subbox resolves / allocates it right away
   int parity;       // frame & 1: selects the double-buffered counters / activation stamps
   int order_mode;   // 0: stamps are (bucket activation, first-insert time); 1: virtual sequence positions
 };
@@ -122,8 +124,8 @@ struct DeviceBuffers {
   int *fuse_ticket;        // completion ticket of k_fuse
   FrameCounters *fc[2];   // double-buffered: frame f uses fc[f&1], k_fuse clears the other one
   // K1/K1b
-  RayRecord *rec_lin;     // [max_points] per k_project CTA: a kProjTile-slot window, records grouped by column
-  uint32_t *rec_dir;      // [ceil(max_points/kProjTile)][nCol] directory of those windows: offset << 16 | count
+  RayRecord *rec_lin;     // [max_points] per projection tile: a tile_pts-slot window, records grouped by column
+  uint32_t *rec_dir;      // [tiles][nCol] directory of those windows: offset << 16 | count
   RayRecord *rec_col;     // [max_points] gathered by k_column: contiguous per phi column
   int *phi_hist;          // [nCol] records per work column
   int *phi_bound;         // [nCol] upper bound of hit contributions per work column
@@ -138,6 +140,7 @@ struct DeviceBuffers {
   uint32_t *act[2];       // [bucket capacity] bucket activation stamps, double-buffered like fc
   int *col_ticket;        // completion ticket of k_column (last CTA resolves the touched subboxes)
   int *col_queue;         // next item of k_column's work queue (rearmed by the last CTA)
+  int *grid_bar;          // arrival counter of k_frame's device-wide barriers (rearmed by the last CTA)
   // local voxel / submap grids
   int2 *lvg;              // [lvg cells] .x head of this frame's hit list (-1 empty), .y number of miss cells
   uint32_t *touched;      // [max_touched] local voxel index (| kTouchedHitTag)

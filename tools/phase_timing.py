@@ -12,6 +12,9 @@ for k in range(6):
     img = scenes.corridor_depth_frame(cfg, pose, frame_idx=100 + k)
     m.integrate_depth(img, pose)
 c = m.debug_phase_cycles()
+nc = c.shape[0] - 256
+fr = c[nc:]
+c = c[:nc]
 act = c[:, 10] > 0
 names = ["gather", "bound", "contrib", "radix", "fold||walks", "miss-stage"]
 cc = np.concatenate([c[:, 15:16], c[:, :4], c[:, 6:8]], axis=1)
@@ -38,3 +41,14 @@ late = np.argsort(-st)[:8]
 print("latest starters (col, start, end, n_c, n_k):", [(int(np.nonzero(act)[0][i]), round(float(st[i]), 1), round(float(en[i]), 1), int(ca[i, 10]), int(ca[i, 11])) for i in late])
 first = np.argsort(st)[:6]
 print("first starters:", [(int(np.nonzero(act)[0][i]), round(float(st[i]), 1), round(float(en[i]), 1), int(ca[i, 10]), int(ca[i, 11])) for i in first])
+fa = fr[fr[:, 0] > 0]
+if len(fa):
+    t0 = fa[:, 0].min()
+    rel = (fa[:, :9] - t0) / 1e3
+    names = ["start", "proj done", "bar1 out", "cols done", "bar2 out", "bar3 out", "end", "col prologue", "fuse ticket"]
+    for i, n in enumerate(names):
+        print(f"k_frame {n:10s}: min {rel[:, i].min():6.1f}  mean {rel[:, i].mean():6.1f}  max {rel[:, i].max():6.1f} us")
+    ids = np.nonzero(fr[:, 0] > 0)[0]
+    o = np.argsort(-rel[:, 8])
+    print("fuse ticket times, slowest 12 (cta, bar2 out, ticket):", [(int(ids[i]), round(float(rel[i, 4]), 1), round(float(rel[i, 8]), 1)) for i in o[:12]])
+    print("fuse ticket percentiles:", np.percentile(rel[:, 8], [0, 25, 50, 75, 90, 100]).round(1))
