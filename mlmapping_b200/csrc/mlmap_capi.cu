@@ -1202,6 +1202,15 @@ int mlm_integrate_depth_u16(mlm_handle h, const uint16_t *img, int rows, int col
     }
     src = h->h_stage;
   }
+  // The projection reads every pixel exactly once, so page-locked input is read in place over PCIe by the
+  // kernel itself (zero-copy): the transfer overlaps the projection instead of preceding it as a separate copy.
+  static const int zero_copy = getenv("MLM_ZERO_COPY") ? atoi(getenv("MLM_ZERO_COPY")) : 0;  // opt-in: measured equal to the staged copy on this box
+  if (zero_copy) {
+    cudaPointerAttributes a2;
+    if (cudaPointerGetAttributes(&a2, src) == cudaSuccess && a2.type == cudaMemoryTypeHost && a2.devicePointer)
+      return run_frame(h, 1, a2.devicePointer, rows, cols, 0, T_wb, stats);
+    cudaGetLastError();
+  }
   CUDA_TRY(cudaMemcpyAsync(h->d_input, src, bytes, cudaMemcpyHostToDevice, h->stream));
   return run_frame(h, 1, h->d_input, rows, cols, 0, T_wb, stats);
 }

@@ -90,7 +90,9 @@ __global__ void __launch_bounds__(256) k_shard_emit(MapParams P, DeviceBuffers D
       *o++ = r;
     }
   }
-  if (i < n) D.lvg[lv] = make_int2(kLvgEmpty, 0);  // staging consumed (both entries of a voxel write the same value)
+  // staging consumed.  Only the entry that owns the voxel clears it: the other entry of a voxel with hits and
+  // misses may sit anywhere in the list, and clearing from there could empty the voxel before its owner reads it
+  if (dest >= 0) D.lvg[lv] = make_int2(kLvgEmpty, 0);
 }
 
 // global ordering info per key: key_stamp[key] = first-insert stamp (or virtual position on a rehash frame)
