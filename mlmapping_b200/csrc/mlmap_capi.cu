@@ -609,7 +609,7 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
       if (++cnt % 50 == 0) fprintf(stderr, "host us: setparams %.2f launch %.2f\n", acc[0] / cnt, acc[1] / cnt);
     }
   }
-  h->launches += 3;
+  h->launches += (prof || !h->use_graph || !h->use_fused) ? 3 : 1;
   CUDA_TRY(cudaStreamSynchronize(s));
   CUDA_TRY(cudaGetLastError());
 

@@ -10,6 +10,9 @@ m = MLMap(cfg)
 for k in range(6):
     pose = scenes.corridor_trajectory_pose(100 + k)
     img = scenes.corridor_depth_frame(cfg, pose, frame_idx=100 + k)
+    if "--flush" in sys.argv:
+        m.flush_l2()
+        m.sync()
     m.integrate_depth(img, pose)
 c = m.debug_phase_cycles()
 nc = c.shape[0] - 256
