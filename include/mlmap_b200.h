@@ -214,6 +214,23 @@ int mlm_export_map(mlm_handle h, size_t cap_submaps, int32_t *glb3, uint8_t *col
  * bitmask of ceil(subbox_n^3 / 32) 32-bit words per subbox (bit c = cell id c), with its own glb3 list. */
 int mlm_export_frontier(mlm_handle h, size_t cap_submaps, int32_t *glb3, uint32_t *frontier_words, size_t *n_out);
 
+/* ---- map clouds for consumers ---------------------------------------------------------------------
+ * Whole-map compaction on the device into float4 points {x, y, z, w} (16-byte stride = pcl::PointXYZ, the wire format
+ * of the reference's PointCloud2 topics, include/common.h:53):
+ *   MLM_CLOUD_INFLATED  cells with inflate_occupancy == 'o'  (rviz_vis::pub_global_local_map, src/rviz_vis.cpp:296-327)
+ *   MLM_CLOUD_OCCUPIED  cells with occupancy == 'o'
+ *   MLM_CLOUD_FRONTIER  the frontier sets                     (rviz_vis::pub_frontier, src/rviz_vis.cpp:267-294)
+ * w is 1.0f.  mlm_export_odds_slice writes the cells whose centre height is within 1e-3 of `height` as
+ * {x, y, z, odd}, odd = logit_inv(log_odds)  (mlmap::visualize_odds, src/mlmap.cpp:200-284).
+ * `xyzw` holds `cap` points (host memory for the plain calls, device memory for *_device); *n_out is the number of
+ * points the map has, which may exceed cap (then only cap points were written).  Point order is unspecified. */
+#define MLM_CLOUD_INFLATED 0
+#define MLM_CLOUD_OCCUPIED 1
+#define MLM_CLOUD_FRONTIER 2
+int mlm_export_cloud(mlm_handle h, int kind, float *xyzw, size_t cap, size_t *n_out);
+int mlm_export_cloud_device(mlm_handle h, int kind, float *d_xyzw, size_t cap, size_t *n_out);
+int mlm_export_odds_slice(mlm_handle h, double height, float *xyzw, size_t cap, size_t *n_out);
+
 /* ---- one logical map sharded over `world` ranks (large LiDAR scans) -------------------------------
  * Per scan, on every rank with the SAME points and pose:
  *   1. mlm_shard_stage_points_f64   casts the rank's phi columns (phi % world == rank) into its voxel staging

@@ -110,6 +110,8 @@ ABI_SYMBOLS = [
     "mlm_debug_log10f", "mlm_set_profiling", "mlm_last_frame_kernel_ms", "mlm_sizeof_config",
     "mlm_sizeof_frame_stats", "mlm_debug_phase_cycles", "mlm_host_alloc", "mlm_host_free", "mlm_srand", "mlm_debug_rand", "mlm_export_frontier", "mlm_shard_stage_points_f64",
     "mlm_shard_copy_hit_keys", "mlm_shard_stage_points_f64_device", "mlm_shard_act_buffer", "mlm_shard_order_fast", "mlm_shard_order", "mlm_shard_emit_counts", "mlm_shard_emit_pack", "mlm_shard_ingest", "mlm_dirty_count", "mlm_dirty_export", "mlm_dirty_import",
+    "mlm_export_cloud", "mlm_export_cloud_device", "mlm_export_odds_slice",
+    "mlm_export_cloud", "mlm_export_cloud_device", "mlm_export_odds_slice",
 ]
 FRAME_KERNELS = ["k_project", "k_column", "k_fuse"]
 
@@ -180,6 +182,9 @@ def load_library() -> C.CDLL:
         "mlm_export_map_count": ([vp, C.POINTER(sz)], C.c_int),
         "mlm_export_map": ([vp, sz, vp, vp, vp, vp, vp, C.POINTER(sz)], C.c_int),
         "mlm_export_frontier": ([vp, sz, vp, vp, C.POINTER(sz)], C.c_int),
+        "mlm_export_cloud": ([vp, C.c_int, vp, sz, C.POINTER(sz)], C.c_int),
+        "mlm_export_cloud_device": ([vp, C.c_int, vp, sz, C.POINTER(sz)], C.c_int),
+        "mlm_export_odds_slice": ([vp, C.c_double, vp, sz, C.POINTER(sz)], C.c_int),
         "mlm_shard_stage_points_f64": ([vp, vp, C.c_int, dp, C.c_int, C.c_int, ip, ip], C.c_int),
         "mlm_shard_copy_hit_keys": ([vp, vp, vp], C.c_int),
         "mlm_shard_stage_points_f64_device": ([vp, vp, C.c_int, dp, C.c_int, C.c_int, ip, ip], C.c_int),
@@ -478,6 +483,34 @@ class MLMap:
         if n.value:
             self._check(self._lib.mlm_last_frame_misses(self._h, idx.ctypes.data, n.value, C.byref(n)))
         return idx
+
+    CLOUD_INFLATED, CLOUD_OCCUPIED, CLOUD_FRONTIER = 0, 1, 2
+
+    def export_cloud(self, kind: int = 0) -> np.ndarray:
+        """[n,4] float32 points x,y,z,1 (pcl::PointXYZ layout) of the cells the reference's map / frontier topics
+        carry (rviz_vis.cpp:267-327); compacted on the device, order unspecified"""
+        n = C.c_size_t()
+        self._check(self._lib.mlm_export_cloud(self._h, kind, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 4), dtype=np.float32)
+        if n.value:
+            self._check(self._lib.mlm_export_cloud(self._h, kind, out.ctypes.data, n.value, C.byref(n)))
+            assert n.value == out.shape[0]
+        return out
+
+    def export_cloud_device(self, kind: int, d_ptr: int, cap: int) -> int:
+        """same compaction into caller device memory (cap float4 points); returns the number of points in the map"""
+        n = C.c_size_t()
+        self._check(self._lib.mlm_export_cloud_device(self._h, kind, d_ptr, cap, C.byref(n)))
+        return n.value
+
+    def export_odds_slice(self, height: float) -> np.ndarray:
+        """[n,4] float32 x,y,z,odd of the cells at `height` (mlmap::visualize_odds, mlmap.cpp:200-284)"""
+        n = C.c_size_t()
+        self._check(self._lib.mlm_export_odds_slice(self._h, float(height), None, 0, C.byref(n)))
+        out = np.zeros((n.value, 4), dtype=np.float32)
+        if n.value:
+            self._check(self._lib.mlm_export_odds_slice(self._h, float(height), out.ctypes.data, n.value, C.byref(n)))
+        return out
 
     def export_map(self):
         """dict with glb[n,3], collapsed[n], occupancy[n,cells] (S1), inflate[n,cells], log_odds[n,cells],

@@ -1600,6 +1600,51 @@ int mlm_export_frontier(mlm_handle h, size_t cap_submaps, int32_t *glb3, uint32_
 
 // ---- sharded map: stage / order / emit / ingest; collectives are the caller's (NCCL via torch.distributed)
 namespace {
+// kind >= 0: k_export_cloud, kind < 0: odds slice at `height`; device_out: xyzw is device memory
+int export_points(mlm_handle h, int kind, double height, float *xyzw, size_t cap, size_t *n_out, bool device_out) {
+  if (!h || !n_out || (cap && !xyzw) || kind > MLM_CLOUD_FRONTIER) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  unsigned long long *d_cnt = nullptr;
+  float4 *d_out = device_out ? reinterpret_cast<float4 *>(xyzw) : nullptr;
+  CUDA_TRY(cudaMallocAsync((void **)&d_cnt, sizeof(unsigned long long), s));
+  CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));
+  if (!device_out && cap) CUDA_TRY(cudaMallocAsync((void **)&d_out, cap * sizeof(float4), s));
+  const int grid = h->sm_count * 8;  // 8 resident CTAs of 256 threads per SM: one full wave, grid-stride over the slots
+  if (kind >= 0)
+    k_export_cloud<<<grid, 256, 0, s>>>(h->P, h->D, kind, d_out, d_cnt, (unsigned long long)cap);
+  else
+    k_export_odds_slice<<<grid, 256, 0, s>>>(h->P, h->D, height, d_out, d_cnt, (unsigned long long)cap);
+  h->launches++;
+  unsigned long long cnt = 0;
+  CUDA_TRY(cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  *n_out = (size_t)cnt;
+  if (!device_out && cap) {
+    const size_t n_copy = std::min<size_t>((size_t)cnt, cap);
+    if (n_copy) CUDA_TRY(cudaMemcpyAsync(xyzw, d_out, n_copy * sizeof(float4), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaFreeAsync(d_out, s));
+  }
+  CUDA_TRY(cudaFreeAsync(d_cnt, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  return MLM_OK;
+}
+}  // namespace
+
+int mlm_export_cloud(mlm_handle h, int kind, float *xyzw, size_t cap, size_t *n_out) {
+  if (kind < 0) return MLM_ERR_INVALID_ARG;
+  return export_points(h, kind, 0.0, xyzw, cap, n_out, false);
+}
+int mlm_export_cloud_device(mlm_handle h, int kind, float *d_xyzw, size_t cap, size_t *n_out) {
+  if (kind < 0) return MLM_ERR_INVALID_ARG;
+  return export_points(h, kind, 0.0, d_xyzw, cap, n_out, true);
+}
+int mlm_export_odds_slice(mlm_handle h, double height, float *xyzw, size_t cap, size_t *n_out) {
+  return export_points(h, -1, height, xyzw, cap, n_out, false);
+}
+
+namespace {
 int shard_stage_common(mlm_handle h, const double *d_xyz, int n, const double T_wb[7], int rank, int world,
                        int32_t *n_hit_local, int32_t *n_miss_local) {
   h->shard_rank = rank;

@@ -312,6 +312,118 @@ __global__ void __launch_bounds__(256) k_inflate_sources(MapParams P, DeviceBuff
   }
 }
 
+// ---- map clouds for consumers (reference src/rviz_vis.cpp:267-327, src/mlmap.cpp:200-284) ----------------------
+// Whole-map stream compaction: one warp per hash slot; a live subbox is scanned 16 cells per lane and load, the
+// selected cells are ranked inside the warp, space for them is reserved with ONE atomicAdd per warp and round,
+// and the points go out as float4 {x, y, z, w} = the memory layout of pcl::PointXYZ (include/common.h:53).
+//   kind 0: inflate_occupancy == 'o'  (rviz_vis::pub_global_local_map, the map cloud the reference publishes)
+//   kind 1: occupancy == 'o'
+//   kind 2: the frontier sets         (rviz_vis::pub_frontier)
+// A collapsed subbox holds one element per array, so only its cell 0 can qualify (the reference loops over
+// vectors of size 1 there).  Point order is unspecified (the reference's is its unordered_map iteration order).
+__device__ __forceinline__ float4 cell_point(const MapParams &P, const int g[3], int sub, float w) {
+  const int x = sub % P.n, y = (sub / P.n) % P.n, z = sub / (P.n * P.n);
+  // subbox_id2xyz_glb, include/map_local.h:201-206: origin*d_glb + xyz*d_sub + d_sub/2 in double, then float
+  return make_float4((float)(((double)g[0] * P.d_glb + (double)x * P.d_sub) + P.d_sub_half),
+                     (float)(((double)g[1] * P.d_glb + (double)y * P.d_sub) + P.d_sub_half),
+                     (float)(((double)g[2] * P.d_glb + (double)z * P.d_sub) + P.d_sub_half), w);
+}
+__global__ void __launch_bounds__(256) k_export_cloud(MapParams P, DeviceBuffers D, int kind, float4 *out,
+                                                      unsigned long long *counter, unsigned long long cap) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t slot = warp; slot <= P.ht_mask; slot += nwarps) {
+    const uint64_t k = D.ht_key[slot];
+    if (k == kEmptyKey) continue;
+    const int block = D.ht_val[slot];
+    int g[3];
+    unpack_glb(k, g);
+    if (block == kBlockCollapsed) {
+      const bool sel = kind == 0 ? D.col_inf[slot] == 'o' : (kind == 1 ? D.col_occ[slot] == 'o' : false);
+      if (sel && lane == 0) {
+        const unsigned long long at = atomicAdd(counter, 1ull);
+        if (at < cap) out[at] = cell_point(P, g, 0, 1.0f);
+      }
+      continue;
+    }
+    if (block < 0) continue;
+    if (kind == 2 && !P.explore) continue;
+    const char *src = (kind == 0 ? D.pool_inf : D.pool_occ) + (size_t)block * P.cell_stride;
+    for (int c0 = 0; c0 < P.cell_stride; c0 += 32 * 16) {
+      const int c = c0 + lane * 16;
+      uint32_t m = 0;  // bit i: cell c + i selected
+      if (c < P.cell_stride) {
+        if (kind == 2) {
+          // 16 frontier bits of this lane: cells c .. c+15 live in word c/32, half (c/16)&1
+          const uint32_t w = D.pool_front[(size_t)block * P.front_words + (c >> 5)];
+          m = (w >> (c & 16)) & 0xffffu;
+        } else {
+          const uint4 v = *reinterpret_cast<const uint4 *>(src + c);
+          const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+              if (((wv[q] >> (8 * b)) & 0xffu) == (uint32_t)'o') m |= 1u << (4 * q + b);
+        }
+        if (c + 16 > P.cells) m &= (c < P.cells) ? ((1u << (P.cells - c)) - 1u) : 0u;  // padding cells of the block
+      }
+      const int cnt = __popc(m);
+      int incl = cnt;
+#pragma unroll
+      for (int ofs = 1; ofs < 32; ofs <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, ofs);
+        if (lane >= ofs) incl += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if (total == 0) continue;
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(counter, (unsigned long long)total);
+      base = __shfl_sync(0xffffffffu, base, 0) + (unsigned long long)(incl - cnt);
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        if (base < cap) out[base] = cell_point(P, g, c + b, 1.0f);
+        base++;
+      }
+    }
+  }
+}
+// Horizontal slice of the odds field (mlmap::visualize_odds, src/mlmap.cpp:200-284): every cell whose centre height
+// is within 1e-3 of `height` goes out as {x, y, z, odd} with odd = logit_inv(log_odds) (the reference colours the
+// marker by it; its gradient lines are getOddGrad at the same points, available through mlm_get_odd_grad).
+__global__ void __launch_bounds__(256) k_export_odds_slice(MapParams P, DeviceBuffers D, double height, float4 *out,
+                                                           unsigned long long *counter, unsigned long long cap) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t slot = warp; slot <= P.ht_mask; slot += nwarps) {
+    const uint64_t k = D.ht_key[slot];
+    if (k == kEmptyKey) continue;
+    const int block = D.ht_val[slot];
+    if (block < 0 && block != kBlockCollapsed) continue;
+    int g[3];
+    unpack_glb(k, g);
+    for (int z = 0; z < P.n; z++) {
+      const double pz = ((double)g[2] * P.d_glb + (double)z * P.d_sub) + P.d_sub_half;
+      if (!(pz < height + 1e-3 && pz > height - 1e-3)) continue;
+      const int layer = P.n * P.n;
+      for (int i0 = 0; i0 < layer; i0 += 32) {
+        const int i = i0 + lane, sub = z * layer + i;
+        const bool sel = i < layer && (block != kBlockCollapsed || sub == 0);
+        const unsigned sm = __ballot_sync(0xffffffffu, sel);
+        if (!sm) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)__popc(sm));
+        base = __shfl_sync(0xffffffffu, base, 0) + (unsigned long long)__popc(sm & ((1u << lane) - 1));
+        if (sel && base < cap) {
+          const float lo = block == kBlockCollapsed ? D.col_lo[slot] : D.pool_lo[(size_t)block * P.cell_stride + sub];
+          out[base] = cell_point(P, g, sub, logit_inv_f(lo));
+        }
+      }
+    }
+  }
+}
+
 // ---- export -----------------------------------------------------------------------------------------
 __global__ void k_export_list(MapParams P, DeviceBuffers D, int *out_glb3, int *out_block, int *counter, int cap) {
   uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;

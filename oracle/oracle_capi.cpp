@@ -175,6 +175,54 @@ size_t orc_export_frontier(void *h, size_t cap, uint8_t *bits) {
   }
   return i;
 }
+// map clouds, reference src/rviz_vis.cpp:267-327 (pub_frontier, pub_global_local_map) and the same loop over
+// `occupancy`; points as float x,y,z,1 (pcl::PointXYZ).  kind 0 inflate_occupancy == 'o', 1 occupancy == 'o', 2 frontier
+size_t orc_export_cloud(void *h, int kind, float *xyzw, size_t cap) {
+  auto *m = static_cast<orc::mlmap *>(h);
+  size_t n = 0;
+  auto emit = [&](const Vec3I &g, int id) {
+    Vec3 p = m->local->subbox_id2xyz_glb_vec(g, id);  // same expression as subbox_id2xyz_glb, converted to float by PointP
+    if (n < cap) {
+      xyzw[4 * n] = (float)p[0];
+      xyzw[4 * n + 1] = (float)p[1];
+      xyzw[4 * n + 2] = (float)p[2];
+      xyzw[4 * n + 3] = 1.0f;
+    }
+    n++;
+  };
+  for (auto &kv : m->local->observed_group_map) {
+    if (kind == 2) {
+      for (int c : kv.second.frontier) emit(kv.first, c);
+      continue;
+    }
+    const auto &v = kind == 0 ? kv.second.inflate_occupancy : kv.second.occupancy;
+    int id = 0;
+    for (auto it = v.begin(); it != v.end(); it++, id++)
+      if (*it == 'o') emit(kv.first, id);
+  }
+  return n;
+}
+// odds slice, reference mlmap::visualize_odds src/mlmap.cpp:200-284: x,y,z of the cell and logit_inv(log_odds)
+size_t orc_export_odds_slice(void *h, double height, float *xyzw, size_t cap) {
+  auto *m = static_cast<orc::mlmap *>(h);
+  size_t n = 0;
+  for (auto &kv : m->local->observed_group_map) {
+    int id = 0;
+    for (auto it = kv.second.log_odds.begin(); it != kv.second.log_odds.end(); it++, id++) {
+      Vec3 pt = m->local->subbox_id2xyz_glb_vec(kv.first, id);
+      if (pt[2] < height + 1e-3 && pt[2] > height - 1e-3) {
+        if (n < cap) {
+          xyzw[4 * n] = (float)pt[0];
+          xyzw[4 * n + 1] = (float)pt[1];
+          xyzw[4 * n + 2] = (float)pt[2];
+          xyzw[4 * n + 3] = (float)ORC_logit_inv(*it);
+        }
+        n++;
+      }
+    }
+  }
+  return n;
+}
 int orc_released_last(void *h) { return static_cast<orc::mlmap *>(h)->local->n_released_last; }
 
 // table / scalar probes used by known-answer tests

@@ -61,6 +61,8 @@ def load_oracle():
     lib.orc_export_map.argtypes, lib.orc_export_map.restype = [vp, sz, vp, vp, vp, vp, vp], sz
     lib.orc_export_frontier.argtypes, lib.orc_export_frontier.restype = [vp, sz, vp], sz
     lib.orc_released_last.argtypes, lib.orc_released_last.restype = [vp], C.c_int
+    lib.orc_export_cloud.argtypes, lib.orc_export_cloud.restype = [vp, C.c_int, vp, sz], sz
+    lib.orc_export_odds_slice.argtypes, lib.orc_export_odds_slice.restype = [vp, C.c_double, vp, sz], sz
     lib.orc_odds_table.argtypes, lib.orc_odds_table.restype = [vp, C.c_int, C.c_int], C.c_float
     lib.orc_three_sigma.argtypes, lib.orc_three_sigma.restype = [vp, C.c_int], C.c_float
     lib.orc_fast_atan2.argtypes, lib.orc_fast_atan2.restype = [vp, C.c_double, C.c_double], C.c_double
@@ -183,6 +185,21 @@ class Oracle:
         p = self._pos(pos_w)
         out = np.empty((p.shape[0], 3), dtype=np.float64)
         self.lib.orc_get_odd_grad(self.h, p.ctypes.data, p.shape[0], max_iter, out.ctypes.data)
+        return out
+
+    def export_cloud(self, kind: int) -> np.ndarray:
+        """[n,4] float32 x,y,z,1 of the cells the reference would publish (0 inflated, 1 occupied, 2 frontier)"""
+        n = self.lib.orc_export_cloud(self.h, kind, None, 0)
+        out = np.zeros((n, 4), dtype=np.float32)
+        if n:
+            self.lib.orc_export_cloud(self.h, kind, out.ctypes.data, n)
+        return out
+
+    def export_odds_slice(self, height: float) -> np.ndarray:
+        n = self.lib.orc_export_odds_slice(self.h, float(height), None, 0)
+        out = np.zeros((n, 4), dtype=np.float32)
+        if n:
+            self.lib.orc_export_odds_slice(self.h, float(height), out.ctypes.data, n)
         return out
 
     def export_map(self):

@@ -40,3 +40,31 @@ def assert_map_parity(gpu, orc, lo_tol=1e-6, tag=""):
     assert d.max(initial=0.0) <= lo_tol, (tag, "log-odds differ", float(d.max()))
     exact = np.array_equal(g["log_odds"].view(np.uint32), o["log_odds"].view(np.uint32))
     return {"subboxes": int(g["glb"].shape[0]), "log_odds_bit_exact": bool(exact), "max_abs_diff": float(d.max(initial=0.0))}
+
+
+def _sorted_rows(a):
+    a = np.ascontiguousarray(a)
+    v = a.view(np.uint32).reshape(a.shape[0], -1)
+    return a[np.lexsort(tuple(v[:, c] for c in range(v.shape[1] - 1, -1, -1)))]
+
+
+def assert_cloud_parity(gpu, orc, kinds=(0, 1), heights=(0.75, 1.25), tag=""):
+    """map clouds for consumers (rviz_vis.cpp:267-327, mlmap.cpp:200-284): same point SETS bit for bit (the order
+    of the reference's clouds is its unordered_map iteration order, which no consumer can rely on); the slice's
+    odd within one float ulp like getOdd"""
+    sizes = {}
+    for kind in kinds:
+        g, o = _sorted_rows(gpu.export_cloud(kind)), _sorted_rows(orc.export_cloud(kind))
+        assert g.shape == o.shape, (tag, kind, g.shape, o.shape)
+        assert np.array_equal(g.view(np.uint32), o.view(np.uint32)), (tag, "cloud", kind)
+        sizes[kind] = g.shape[0]
+    for hgt in heights:
+        g, o = gpu.export_odds_slice(hgt), orc.export_odds_slice(hgt)
+        assert g.shape == o.shape, (tag, "slice", hgt, g.shape, o.shape)
+        gi = np.lexsort((g[:, 2], g[:, 1], g[:, 0]))
+        oi = np.lexsort((o[:, 2], o[:, 1], o[:, 0]))
+        g, o = g[gi], o[oi]
+        assert np.array_equal(g[:, :3].view(np.uint32), o[:, :3].view(np.uint32)), (tag, "slice xyz", hgt)
+        assert np.abs(g[:, 3].astype(np.float64) - o[:, 3]).max(initial=0.0) <= 1.2e-7, (tag, "slice odd", hgt)
+        sizes[("slice", hgt)] = g.shape[0]
+    return sizes

@@ -263,3 +263,33 @@ def test_sampled_projection_uses_libc_rand_stream():
     img[::2, :] = 0
     st = o.integrate_depth(img, pose)
     assert st.n_points < 50
+
+
+def test_map_clouds_follow_subbox_id2xyz_glb():
+    """map clouds (rviz_vis.cpp:267-327): one float point per selected cell at origin*d_glb + xyz*d_sub + d_sub/2
+    (map_local.h:201-206), cell ids x-fastest; the odds slice (mlmap.cpp:200-284) keeps the cells within 1e-3 of the height"""
+    cfg = config_cfg_a()
+    orc = Oracle(cfg)
+    pose = scenes.corridor_trajectory_pose(0)
+    for k in range(3):
+        orc.integrate_depth(scenes.corridor_depth_frame(cfg, pose, frame_idx=k), pose)
+    m = orc.export_map()
+    n = cfg.subbox_n
+    occ = orc.export_cloud(1)
+    assert occ.shape[0] == int((m["occupancy"] == b"o").sum()) > 100 and np.all(occ[:, 3] == 1.0)
+    # rebuild the expected set from the exported arrays
+    sb, cell = np.nonzero(m["occupancy"] == b"o")
+    xyz = np.stack([cell % n, (cell // n) % n, cell // (n * n)], 1)
+    d_sub, d_glb = cfg.subbox_d_xyz, cfg.subbox_d_xyz * n
+    exp = (m["glb"][sb] * d_glb + xyz * d_sub + d_sub / 2).astype(np.float32)
+    key = lambda a: a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))]
+    assert np.array_equal(key(occ[:, :3]), key(exp))
+    assert orc.export_cloud(0).shape[0] == int((m["inflate"] == b"o").sum())
+    assert orc.export_cloud(2).shape[0] == 0  # frontiers are off in this configuration
+    sl = orc.export_odds_slice(0.75)
+    assert sl.shape[0] > 0 and np.all(np.abs(sl[:, 2] - 0.75) < 1e-3)
+    assert orc.export_odds_slice(0.7).shape[0] == 0  # cell centres sit at k*0.1 + 0.05: nothing within 1e-3 of 0.7
+    lo = m["log_odds"][(m["glb"][:, 2] == 0)][:, 7 * n * n:8 * n * n]
+    assert sl.shape[0] == lo.size
+    assert np.all((sl[:, 3] > 0) & (sl[:, 3] < 1))
+    orc.close()

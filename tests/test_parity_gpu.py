@@ -7,7 +7,7 @@ import pytest
 from mlmapping_b200 import MLMap, config_cfg_a, config_cfg_c, scenes
 from mlmapping_b200.capi import MlmError
 from oracle_binding import Oracle
-from parity_utils import assert_frame_parity, assert_map_parity
+from parity_utils import assert_cloud_parity, assert_frame_parity, assert_map_parity
 
 pytestmark = pytest.mark.gpu
 LO_TOL = 1e-6
@@ -234,6 +234,13 @@ def test_inflate_map_and_inflate_occupancy():
     gpu.inflate_map([100.0, 0.0, 0.0])
     orc.inflate_map([100.0, 0.0, 0.0])
     assert_map_parity(gpu, orc, LO_TOL, tag="inflate-empty-window")
+    # the clouds the reference publishes from this map: inflated / occupied cells and two odds slices
+    sizes = assert_cloud_parity(gpu, orc, kinds=(0, 1), tag="inflate")
+    assert sizes[0] > 1000 and sizes[1] > 100 and sizes[("slice", 0.75)] > 1000
+    cap = 64  # truncated export reports the full count and writes only `cap` points
+    dptr = gpu.device_alloc(16 * cap)
+    assert gpu.export_cloud_device(0, dptr, cap) == sizes[0]
+    gpu.device_free(dptr)
 
 
 def test_sampled_project_depth_matches_glibc_rand_stream():
@@ -284,6 +291,8 @@ def test_exploration_frontiers_and_memory_release():
     gpu.inflate_map(pose[:3])
     orc.inflate_map(pose[:3])
     assert_map_parity(gpu, orc, LO_TOL, tag="explore-setfree-inflate")
+    sizes = assert_cloud_parity(gpu, orc, kinds=(0, 1, 2), tag="explore")   # incl. the frontier cloud and collapsed subboxes
+    assert sizes[2] > 100
 
 
 def test_sharded_pipeline_world_1_matches_oracle():
