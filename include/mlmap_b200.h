@@ -231,6 +231,21 @@ int mlm_export_cloud(mlm_handle h, int kind, float *xyzw, size_t cap, size_t *n_
 int mlm_export_cloud_device(mlm_handle h, int kind, float *d_xyzw, size_t cap, size_t *n_out);
 int mlm_export_odds_slice(mlm_handle h, double height, float *xyzw, size_t cap, size_t *n_out);
 
+/* ---- checkpoint / restore of the map (the reference keeps its map in process memory only) ------------
+ * A checkpoint is a self-describing byte image: a header (format version, the map-defining configuration fields,
+ * the cumulative counters, the emulated bucket counts of the per-frame containers and the rand() stream of the
+ * sampled projection) followed by one fixed-size record per subbox (index, collapsed flag, log_odds, occupancy,
+ * inflate_occupancy and, in exploration mode, the frontier set).  Restoring it into a handle created with the same
+ * map-defining configuration (any pool size that holds the subboxes) replaces that handle's map; frames integrated
+ * afterwards give bit for bit what the original handle would have produced.
+ *   mlm_checkpoint_size     bytes mlm_checkpoint_save will write for the current map
+ *   mlm_checkpoint_save     writes at most `cap` bytes into host memory `buf`; MLM_ERR_CAPACITY if cap is too small
+ *   mlm_checkpoint_restore  MLM_ERR_INVALID_ARG for a foreign / truncated image, MLM_ERR_INVALID_CONFIG when the image
+ *                           was taken with a different map configuration, MLM_ERR_POOL_EXHAUSTED if the pool is too small */
+int mlm_checkpoint_size(mlm_handle h, size_t *bytes);
+int mlm_checkpoint_save(mlm_handle h, void *buf, size_t cap, size_t *written);
+int mlm_checkpoint_restore(mlm_handle h, const void *buf, size_t bytes);
+
 /* ---- one logical map sharded over `world` ranks (large LiDAR scans) -------------------------------
  * Per scan, on every rank with the SAME points and pose:
  *   1. mlm_shard_stage_points_f64   casts the rank's phi columns (phi % world == rank) into its voxel staging

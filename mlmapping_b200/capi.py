@@ -111,6 +111,7 @@ ABI_SYMBOLS = [
     "mlm_sizeof_frame_stats", "mlm_debug_phase_cycles", "mlm_host_alloc", "mlm_host_free", "mlm_srand", "mlm_debug_rand", "mlm_export_frontier", "mlm_shard_stage_points_f64",
     "mlm_shard_copy_hit_keys", "mlm_shard_stage_points_f64_device", "mlm_shard_act_buffer", "mlm_shard_order_fast", "mlm_shard_order", "mlm_shard_emit_counts", "mlm_shard_emit_pack", "mlm_shard_ingest", "mlm_dirty_count", "mlm_dirty_export", "mlm_dirty_import",
     "mlm_export_cloud", "mlm_export_cloud_device", "mlm_export_odds_slice",
+    "mlm_checkpoint_size", "mlm_checkpoint_save", "mlm_checkpoint_restore",
     "mlm_export_cloud", "mlm_export_cloud_device", "mlm_export_odds_slice",
 ]
 FRAME_KERNELS = ["k_project", "k_column", "k_fuse"]
@@ -185,6 +186,9 @@ def load_library() -> C.CDLL:
         "mlm_export_cloud": ([vp, C.c_int, vp, sz, C.POINTER(sz)], C.c_int),
         "mlm_export_cloud_device": ([vp, C.c_int, vp, sz, C.POINTER(sz)], C.c_int),
         "mlm_export_odds_slice": ([vp, C.c_double, vp, sz, C.POINTER(sz)], C.c_int),
+        "mlm_checkpoint_size": ([vp, C.POINTER(sz)], C.c_int),
+        "mlm_checkpoint_save": ([vp, vp, sz, C.POINTER(sz)], C.c_int),
+        "mlm_checkpoint_restore": ([vp, vp, sz], C.c_int),
         "mlm_shard_stage_points_f64": ([vp, vp, C.c_int, dp, C.c_int, C.c_int, ip, ip], C.c_int),
         "mlm_shard_copy_hit_keys": ([vp, vp, vp], C.c_int),
         "mlm_shard_stage_points_f64_device": ([vp, vp, C.c_int, dp, C.c_int, C.c_int, ip, ip], C.c_int),
@@ -483,6 +487,19 @@ class MLMap:
         if n.value:
             self._check(self._lib.mlm_last_frame_misses(self._h, idx.ctypes.data, n.value, C.byref(n)))
         return idx
+
+    def checkpoint(self) -> bytes:
+        """byte image of the whole map (see include/mlmap_b200.h, checkpoint / restore)"""
+        n = C.c_size_t()
+        self._check(self._lib.mlm_checkpoint_size(self._h, C.byref(n)))
+        buf = (C.c_ubyte * n.value)()
+        self._check(self._lib.mlm_checkpoint_save(self._h, buf, n.value, C.byref(n)))
+        return bytes(buf[:n.value])
+
+    def restore(self, image: bytes):
+        """replace this handle's map by a checkpoint taken with the same map configuration"""
+        buf = (C.c_ubyte * len(image)).from_buffer_copy(image)
+        self._check(self._lib.mlm_checkpoint_restore(self._h, buf, len(image)))
 
     CLOUD_INFLATED, CLOUD_OCCUPIED, CLOUD_FRONTIER = 0, 1, 2
 

@@ -1670,7 +1670,6 @@ __device__ __forceinline__ void grid_barrier(int *counter, int target) {
 template <int kMode>
 __global__ void __launch_bounds__(kColThreads, 1) k_frame(MapParams P, DeviceBuffers D, FrameParams F) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  FrameCounters *fc = D.fc[F.parity];
   const int G = (int)gridDim.x;
   MLM_FRAME_WALL(0);
   // (1) projection: tile t of F.tile_pts points -> CTA t % G

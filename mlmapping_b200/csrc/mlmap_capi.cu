@@ -1645,6 +1645,203 @@ int mlm_export_odds_slice(mlm_handle h, double height, float *xyzw, size_t cap, 
 }
 
 namespace {
+struct CkptFileHeader {
+  char magic[8];            // "MLMCKPT1"
+  uint32_t version, header_bytes;
+  mlm_config cfg;           // configuration of the saving handle (the map-defining fields must match on restore)
+  int32_t cells, front_words, explore, rec_bytes;
+  uint64_t n_records;
+  uint32_t bucket_count, bucket_count_miss;
+  int64_t cum_ram_expand, cum_obs, n_submaps;
+  int32_t rng_r[31];
+  int32_t rng_f, rng_b;
+};
+const char kCkptMagic[8] = {'M', 'L', 'M', 'C', 'K', 'P', 'T', '1'};
+bool same_map_config(const mlm_config &a, const mlm_config &b) {
+  return a.am_d_rho == b.am_d_rho && a.am_d_phi_deg == b.am_d_phi_deg && a.am_d_z == b.am_d_z && a.am_n_rho == b.am_n_rho &&
+         a.am_n_z_below == b.am_n_z_below && a.am_n_z_over == b.am_n_z_over && a.use_raycasting == b.use_raycasting &&
+         a.depth_noise_coe == b.depth_noise_coe && a.subbox_d_xyz == b.subbox_d_xyz && a.subbox_n == b.subbox_n &&
+         a.log_odds_min == b.log_odds_min && a.log_odds_max == b.log_odds_max && a.log_odds_miss == b.log_odds_miss &&
+         a.log_odds_occupied_sh == b.log_odds_occupied_sh && a.use_exploration_frontiers == b.use_exploration_frontiers;
+}
+int count_submaps(mlm_handle h, size_t *n) {
+  size_t cnt = 0;
+  int rc = mlm_export_map_count(h, &cnt);
+  *n = cnt;
+  return rc;
+}
+}  // namespace
+
+int mlm_checkpoint_size(mlm_handle h, size_t *bytes) {
+  if (!h || !bytes) return MLM_ERR_INVALID_ARG;
+  size_t n = 0;
+  int rc = count_submaps(h, &n);
+  if (rc != MLM_OK) return rc;
+  *bytes = sizeof(CkptFileHeader) + n * ckpt_record_bytes(h->P.cells, h->P.front_words, h->P.explore);
+  return MLM_OK;
+}
+
+int mlm_checkpoint_save(mlm_handle h, void *buf, size_t cap, size_t *written) {
+  if (!h || !buf || !written) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const MapParams &P = h->P;
+  size_t n = 0;
+  int rc = count_submaps(h, &n);
+  if (rc != MLM_OK) return rc;
+  const size_t rb = ckpt_record_bytes(P.cells, P.front_words, P.explore);
+  const size_t need = sizeof(CkptFileHeader) + n * rb;
+  *written = need;
+  if (cap < need) {
+    g_last_error = "checkpoint buffer too small";
+    return MLM_ERR_CAPACITY;
+  }
+  CkptFileHeader hd;
+  memset(&hd, 0, sizeof(hd));
+  memcpy(hd.magic, kCkptMagic, 8);
+  hd.version = 1;
+  hd.header_bytes = (uint32_t)sizeof(hd);
+  hd.cfg = h->cfg;
+  hd.cells = P.cells;
+  hd.front_words = P.front_words;
+  hd.explore = P.explore;
+  hd.rec_bytes = (int32_t)rb;
+  hd.n_records = n;
+  hd.bucket_count = h->bucket_count;
+  hd.bucket_count_miss = h->bucket_count_miss;
+  hd.cum_ram_expand = h->cum_ram_expand;
+  hd.cum_obs = h->cum_obs;
+  hd.n_submaps = h->n_submaps;
+  memcpy(hd.rng_r, h->rng.r, sizeof(hd.rng_r));
+  hd.rng_f = h->rng.f;
+  hd.rng_b = h->rng.b;
+  memcpy(buf, &hd, sizeof(hd));
+  if (n == 0) return MLM_OK;
+  int *d_cnt = nullptr, *d_glb = nullptr, *d_blk = nullptr;
+  unsigned char *d_rec = nullptr;
+  const size_t batch = std::max<size_t>(1, std::min<size_t>(n, ((size_t)256 << 20) / rb));
+  CUDA_TRY(cudaMallocAsync((void **)&d_cnt, sizeof(int), s));
+  CUDA_TRY(cudaMallocAsync((void **)&d_glb, n * 12, s));
+  CUDA_TRY(cudaMallocAsync((void **)&d_blk, n * 4, s));
+  CUDA_TRY(cudaMallocAsync((void **)&d_rec, batch * rb, s));
+  CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(int), s));
+  k_export_list<<<grid_for((size_t)P.ht_mask + 1, 256), 256, 0, s>>>(P, h->D, d_glb, d_blk, d_cnt, (int)n);
+  unsigned char *dst = reinterpret_cast<unsigned char *>(buf) + sizeof(hd);
+  for (size_t first = 0; first < n; first += batch) {
+    const size_t m = std::min(batch, n - first);
+    k_ckpt_pack<<<(unsigned)m, 256, 0, s>>>(P, h->D, d_glb, d_blk, (int)first, (int)m, d_rec);
+    CUDA_TRY(cudaMemcpyAsync(dst + first * rb, d_rec, m * rb, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    h->launches++;
+  }
+  CUDA_TRY(cudaFreeAsync(d_cnt, s));
+  CUDA_TRY(cudaFreeAsync(d_glb, s));
+  CUDA_TRY(cudaFreeAsync(d_blk, s));
+  CUDA_TRY(cudaFreeAsync(d_rec, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  return MLM_OK;
+}
+
+int mlm_checkpoint_restore(mlm_handle h, const void *buf, size_t bytes) {
+  if (!h || !buf || bytes < sizeof(CkptFileHeader)) return MLM_ERR_INVALID_ARG;
+  CkptFileHeader hd;
+  memcpy(&hd, buf, sizeof(hd));
+  const MapParams &P = h->P;
+  const size_t rb = ckpt_record_bytes(P.cells, P.front_words, P.explore);
+  if (memcmp(hd.magic, kCkptMagic, 8) != 0 || hd.version != 1 || hd.header_bytes != sizeof(hd)) {
+    g_last_error = "not a mlmap_b200 checkpoint (magic / version)";
+    return MLM_ERR_INVALID_ARG;
+  }
+  if (!same_map_config(hd.cfg, h->cfg) || hd.cells != P.cells || hd.explore != P.explore || (size_t)hd.rec_bytes != rb) {
+    g_last_error = "checkpoint was taken with a different map configuration";
+    return MLM_ERR_INVALID_CONFIG;
+  }
+  if (bytes < sizeof(hd) + hd.n_records * rb) {
+    g_last_error = "truncated checkpoint";
+    return MLM_ERR_INVALID_ARG;
+  }
+  if (hd.n_records > (uint64_t)P.pool_blocks + (uint64_t)(P.explore ? P.ht_mask / 2 : 0)) {
+    g_last_error = "checkpoint holds more subboxes than this handle's pool";
+    return MLM_ERR_POOL_EXHAUSTED;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  CUDA_TRY(cudaStreamSynchronize(s));
+  DeviceBuffers &D = h->D;
+  const size_t ht_cap = (size_t)P.ht_mask + 1;
+  // back to the state mlm_create leaves: empty hash table, full free stack, every block 'u','u',0.f
+  CUDA_TRY(cudaMemsetAsync(D.ht_key, 0xff, ht_cap * 8, s));
+  CUDA_TRY(cudaMemsetAsync(D.ht_val, 0xff, ht_cap * 4, s));
+  CUDA_TRY(cudaMemsetAsync(D.pool_lo, 0, (size_t)P.pool_blocks * P.cell_stride * 4, s));
+  CUDA_TRY(cudaMemsetAsync(D.pool_occ, 'u', (size_t)P.pool_blocks * P.cell_stride, s));
+  CUDA_TRY(cudaMemsetAsync(D.pool_inf, 'u', (size_t)P.pool_blocks * P.cell_stride, s));
+  if (P.explore) {
+    CUDA_TRY(cudaMemsetAsync(D.pool_front, 0, (size_t)P.pool_blocks * P.front_words * 4, s));
+    CUDA_TRY(cudaMemsetAsync(D.act_miss[0], 0xff, (size_t)h->act_miss_cap * 4, s));
+    CUDA_TRY(cudaMemsetAsync(D.act_miss[1], 0xff, (size_t)h->act_miss_cap * 4, s));
+  }
+  {
+    std::vector<int> stack(P.pool_blocks);
+    for (int i = 0; i < P.pool_blocks; i++) stack[i] = P.pool_blocks - 1 - i;
+    CUDA_TRY(cudaMemcpyAsync(D.free_stack, stack.data(), stack.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    const int top = P.pool_blocks;
+    CUDA_TRY(cudaMemcpyAsync(D.free_top, &top, sizeof(int), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));  // `stack` and `top` are read by the copies above
+  }
+  const size_t lsg_cells = (size_t)P.lsg_dim_xy * P.lsg_dim_xy * P.lsg_dim_z;
+  CUDA_TRY(cudaMemsetAsync(D.lsg_flag, 0, lsg_cells * 4, s));
+  CUDA_TRY(cudaMemsetAsync(D.lsg_block, 0xff, lsg_cells * 4, s));
+  CUDA_TRY(cudaMemsetAsync(D.fc[0], 0, 2 * sizeof(FrameCounters), s));
+  CUDA_TRY(cudaMemsetAsync(D.act[0], 0xff, (size_t)h->act_cap * 4, s));
+  CUDA_TRY(cudaMemsetAsync(D.act[1], 0xff, (size_t)h->act_cap * 4, s));
+  CUDA_TRY(cudaMemsetAsync(D.phi_hist, 0, (size_t)P.nCol * 4, s));
+  CUDA_TRY(cudaMemsetAsync(D.phi_bound, 0, (size_t)P.nCol * 4, s));
+  memset(h->h_fc, 0, sizeof(FrameCounters));
+  int rc = MLM_OK;
+  if (hd.n_records) {
+    int *d_status = nullptr;
+    unsigned char *d_rec = nullptr;
+    const size_t n = (size_t)hd.n_records;
+    const size_t batch = std::max<size_t>(1, std::min<size_t>(n, ((size_t)256 << 20) / rb));
+    CUDA_TRY(cudaMallocAsync((void **)&d_status, sizeof(int), s));
+    CUDA_TRY(cudaMallocAsync((void **)&d_rec, batch * rb, s));
+    CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int), s));
+    const unsigned char *src = reinterpret_cast<const unsigned char *>(buf) + sizeof(hd);
+    for (size_t first = 0; first < n; first += batch) {
+      const size_t m = std::min(batch, n - first);
+      CUDA_TRY(cudaMemcpyAsync(d_rec, src + first * rb, m * rb, cudaMemcpyHostToDevice, s));
+      k_ckpt_unpack<<<(unsigned)m, 256, 0, s>>>(P, D, (int)m, d_rec, d_status);
+      CUDA_TRY(cudaStreamSynchronize(s));
+      h->launches++;
+    }
+    int status = 0;
+    CUDA_TRY(cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaFreeAsync(d_status, s));
+    CUDA_TRY(cudaFreeAsync(d_rec, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (status) {
+      g_last_error = "checkpoint restore: device raised error code " + std::to_string(status);
+      rc = map_device_error(status);
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  h->frame_idx = 0;
+  h->last_parity = 0;
+  h->bucket_count = hd.bucket_count;
+  h->bucket_count_miss = hd.bucket_count_miss;
+  h->last_order_B = hd.bucket_count;
+  h->last_n_hit = 0;
+  h->cum_ram_expand = hd.cum_ram_expand;
+  h->cum_obs = hd.cum_obs;
+  h->n_submaps = hd.n_submaps;
+  memcpy(h->rng.r, hd.rng_r, sizeof(hd.rng_r));
+  h->rng.f = hd.rng_f;
+  h->rng.b = hd.rng_b;
+  return rc;
+}
+
+namespace {
 int shard_stage_common(mlm_handle h, const double *d_xyz, int n, const double T_wb[7], int rank, int world,
                        int32_t *n_hit_local, int32_t *n_miss_local) {
   h->shard_rank = rank;

@@ -248,4 +248,137 @@ __global__ void __launch_bounds__(256) k_dirty_import(MapParams P, DeviceBuffers
   }
 }
 
+// ---- checkpoint / restore of the submap pool (the reference has no persistence) -------------------
+// One fixed-size record per subbox: 32-byte header {g[3], flags, element 0 of a collapsed subbox} followed by
+// log_odds[cells] f32, occupancy[cells], inflate_occupancy[cells] and, in exploration mode, the frontier bitmask.
+struct CkptRecHeader {
+  int g[3];
+  int flags;        // 0: full block follows, 1: collapsed subbox (only col_* are meaningful, payload is zero)
+  float col_lo;
+  char col_occ, col_inf;
+  char pad[10];
+};
+static_assert(sizeof(CkptRecHeader) == 32, "checkpoint record header is 32 bytes");
+__host__ __device__ inline size_t ckpt_record_bytes(int cells, int front_words, int explore) {
+  return (sizeof(CkptRecHeader) + (size_t)cells * 6 + (explore ? (size_t)front_words * 4 : 0) + 15) & ~(size_t)15;
+}
+// blocks[i] as produced by k_export_list: pool block, or -16 - hash slot for a collapsed subbox
+__global__ void __launch_bounds__(256) k_ckpt_pack(MapParams P, DeviceBuffers D, const int *glb3, const int *blocks, int first,
+                                                   int n, unsigned char *out) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const size_t rb = ckpt_record_bytes(P.cells, P.front_words, P.explore);
+  unsigned char *rec = out + (size_t)i * rb;
+  const int blk = blocks[first + i];
+  for (size_t b = threadIdx.x * 16; b < rb; b += blockDim.x * 16) *reinterpret_cast<uint4 *>(rec + b) = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  CkptRecHeader *hd = reinterpret_cast<CkptRecHeader *>(rec);
+  if (threadIdx.x == 0) {
+    hd->g[0] = glb3[3 * (first + i)];
+    hd->g[1] = glb3[3 * (first + i) + 1];
+    hd->g[2] = glb3[3 * (first + i) + 2];
+    hd->flags = blk <= -16 ? 1 : 0;
+    if (blk <= -16) {
+      const int slot = -(blk + 16);
+      hd->col_lo = D.col_lo[slot];
+      hd->col_occ = D.col_occ[slot];
+      hd->col_inf = D.col_inf[slot];
+    }
+  }
+  if (blk < 0) return;
+  float *lo = reinterpret_cast<float *>(rec + sizeof(CkptRecHeader));
+  char *occ = reinterpret_cast<char *>(lo + P.cells);
+  char *inf = occ + P.cells;
+  const size_t src = (size_t)blk * P.cell_stride;
+  for (int c = threadIdx.x; c < P.cells; c += blockDim.x) {
+    lo[c] = D.pool_lo[src + c];
+    occ[c] = D.pool_occ[src + c];
+    inf[c] = D.pool_inf[src + c];
+  }
+  if (P.explore) {
+    // the frontier words sit behind the three cell arrays, 4-byte aligned because cells*6 is even... keep it exact:
+    unsigned char *fw = reinterpret_cast<unsigned char *>(inf + P.cells);
+    for (int w = threadIdx.x; w < P.front_words; w += blockDim.x) {
+      const uint32_t v = D.pool_front[(size_t)blk * P.front_words + w];
+      fw[4 * w] = (unsigned char)v;
+      fw[4 * w + 1] = (unsigned char)(v >> 8);
+      fw[4 * w + 2] = (unsigned char)(v >> 16);
+      fw[4 * w + 3] = (unsigned char)(v >> 24);
+    }
+  }
+}
+// inverse: insert the subbox into the (freshly reset) hash table, take a block from the free stack and fill it
+__global__ void __launch_bounds__(256) k_ckpt_unpack(MapParams P, DeviceBuffers D, int n, const unsigned char *in, int *status) {
+  __shared__ int s_block;
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const size_t rb = ckpt_record_bytes(P.cells, P.front_words, P.explore);
+  const unsigned char *rec = in + (size_t)i * rb;
+  const CkptRecHeader *hd = reinterpret_cast<const CkptRecHeader *>(rec);
+  if (threadIdx.x == 0) {
+    int block = kBlockUnusable;
+    int g[3] = {hd->g[0], hd->g[1], hd->g[2]};
+    uint64_t key;
+    if (!pack_glb(g, key)) {
+      *status = kErrRange;
+    } else {
+      uint32_t slot = ht_hash(key) & P.ht_mask;
+      bool done = false;
+      for (uint32_t probe = 0; probe <= P.ht_mask && !done; probe++) {
+        unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&D.ht_key[slot]),
+                                           (unsigned long long)kEmptyKey, (unsigned long long)key);
+        if (old == kEmptyKey) {
+          if (hd->flags & 1) {
+            if (P.explore) {
+              D.col_lo[slot] = hd->col_lo;
+              D.col_occ[slot] = hd->col_occ;
+              D.col_inf[slot] = hd->col_inf;
+              D.ht_val[slot] = kBlockCollapsed;
+              block = kBlockCollapsed;
+            } else {
+              *status = kErrInternal;  // a collapsed subbox cannot exist without the exploration mode
+            }
+          } else {
+            const int top = atomicSub(D.free_top, 1) - 1;
+            if (top < 0) {
+              atomicAdd(D.free_top, 1);
+              D.ht_val[slot] = kBlockUnusable;
+              *status = kErrPool;
+            } else {
+              block = D.free_stack[top];
+              D.ht_val[slot] = block;
+            }
+          }
+          done = true;
+        } else if (old == key) {
+          *status = kErrInternal;  // duplicate subbox in the checkpoint
+          done = true;
+        } else {
+          slot = (slot + 1) & P.ht_mask;
+        }
+      }
+      if (!done) *status = kErrPool;
+    }
+    s_block = block;
+  }
+  __syncthreads();
+  const int block = s_block;
+  if (block < 0) return;
+  const float *lo = reinterpret_cast<const float *>(rec + sizeof(CkptRecHeader));
+  const char *occ = reinterpret_cast<const char *>(lo + P.cells);
+  const char *inf = occ + P.cells;
+  const size_t dst = (size_t)block * P.cell_stride;
+  for (int c = threadIdx.x; c < P.cells; c += blockDim.x) {
+    D.pool_lo[dst + c] = lo[c];
+    D.pool_occ[dst + c] = occ[c];
+    D.pool_inf[dst + c] = inf[c];
+  }
+  if (P.explore) {
+    const unsigned char *fw = reinterpret_cast<const unsigned char *>(inf + P.cells);
+    for (int w = threadIdx.x; w < P.front_words; w += blockDim.x)
+      D.pool_front[(size_t)block * P.front_words + w] =
+          (uint32_t)fw[4 * w] | ((uint32_t)fw[4 * w + 1] << 8) | ((uint32_t)fw[4 * w + 2] << 16) | ((uint32_t)fw[4 * w + 3] << 24);
+  }
+}
+
 }  // namespace mlm

@@ -367,3 +367,54 @@ def test_replicated_map_two_gpus_matches_oracle():
                           "--master-addr", "127.0.0.1", "--master-port", "29537", script], capture_output=True, text=True,
                          timeout=600)
     assert res.returncode == 0 and '"replicated_check": "ok"' in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+
+
+@pytest.mark.gpu
+def test_checkpoint_restore_round_trip_and_continuation():
+    """checkpoint / restore: the image restored into a second handle gives the same map bit for bit,
+    and frames integrated after the restore keep matching the oracle (bucket counts, counters and the rand() stream
+    travel in the header); exploration mode so that collapsed subboxes and frontier sets are covered"""
+    cfg = config_cfg_a()
+    cfg.use_exploration_frontiers = 1
+    cfg.inflate_n, cfg.inflate_global_n = 2, 2
+    a, orc = MLMap(cfg), Oracle(cfg)
+    for k in range(8):
+        pose = scenes.corridor_trajectory_pose(k * 10)
+        img = scenes.corridor_depth_frame(cfg, pose, frame_idx=k)
+        a.integrate_depth(img, pose)
+        orc.integrate_depth(img, pose)
+    a.inflate_map(pose[:3])
+    orc.inflate_map(pose[:3])
+    image = a.checkpoint()
+    ma = a.export_map()
+    assert ma["collapsed"].sum() > 0 and len(image) > 6000 * ma["glb"].shape[0]
+    cfg_b = cfg.copy()
+    cfg_b.pool_submaps = cfg.pool_submaps // 2 + 7  # another pool size that still holds the map
+    b = MLMap(cfg_b)
+    b.restore(image)
+    mb = b.export_map()
+    for name in ma:
+        assert np.array_equal(ma[name].view(np.uint8), mb[name].view(np.uint8)), name
+    assert b.checkpoint()[-4096:] is not None and len(b.checkpoint()) == len(image)
+    # both handles and the oracle continue in lock step
+    for k in range(8, 12):
+        pose = scenes.corridor_trajectory_pose(k * 10)
+        img = scenes.corridor_depth_frame(cfg, pose, frame_idx=k)
+        st_a, st_b, st_o = a.integrate_depth(img, pose), b.integrate_depth(img, pose), orc.integrate_depth(img, pose)
+        assert_frame_parity(b, orc, st_b, st_o, tag=f"restored{k}")
+        assert st_a.ram_expand_cnt == st_b.ram_expand_cnt == st_o.ram_expand_cnt and st_a.obs_cnt == st_b.obs_cnt
+    assert_map_parity(b, orc, LO_TOL, tag="restored")
+    assert_map_parity(a, orc, LO_TOL, tag="original")
+    # roll the first handle back to the checkpoint, foreign bytes and a different configuration are refused
+    a.restore(image)
+    m2 = a.export_map()
+    for name in ma:
+        assert np.array_equal(ma[name].view(np.uint8), m2[name].view(np.uint8)), name
+    with pytest.raises(MlmError) as e:
+        a.restore(b"\0" * len(image))
+    assert e.value.code == 1
+    cfg_c = config_cfg_a()
+    c = MLMap(cfg_c)  # exploration mode off: not the same map configuration
+    with pytest.raises(MlmError) as e:
+        c.restore(image)
+    assert e.value.code == 2
