@@ -180,6 +180,63 @@ def run_reference(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
+def run_lidar(rank, world, local_rank, barrier, scans=10, warm=3):
+    import torch
+    from mlmapping_b200 import MLMap, config_cfg_c, scenes
+    cfg = config_cfg_c()
+    data = []
+    for k in range(scans):
+        pose = scenes.lidar_loop_pose(k)
+        data.append((scenes.lidar_scan(pose, frame_idx=k), pose))
+    out = {"workload": "cfg_c_128beam_lidar_2048az_d0.2m_50m (BASELINE config 4)", "scans": scans - warm, "n_gpus": world}
+    if world == 1:
+        m = MLMap(cfg, device=local_rank)
+        dev = [(m.to_device(p), p.shape[0], pose) for p, pose in data]
+        ms, rays, touched, new = 0.0, 0, 0, 0
+        for k, (dp, n, pose) in enumerate(dev):
+            m.flush_l2()
+            m.timer_start()
+            st = m.integrate_points_device(dp, n, pose)
+            t = m.timer_stop_ms()
+            if k >= warm:
+                ms += t
+                rays += st.n_points
+                touched += st.n_touched_voxels
+                new += st.n_new_submaps
+        alg = 24 * rays + 56 * (scans - warm) + 10 * touched + 6000 * new  # SURVEY 8d frame bytes with point input
+        peak, _ = measured_peak_gbs()
+        out.update({"mode": "one map on one GPU, points resident in HBM, L2 flushed between scans",
+                    "rays_per_s": rays / (ms * 1e-3), "us_per_scan": 1e3 * ms / (scans - warm),
+                    "alg_GB_per_s": alg / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak})
+        m.close()
+        return out
+    from mlmapping_b200.sharded import ShardedMLMap
+    sh = ShardedMLMap(cfg, rank=rank, world=world, device=local_rank)
+    sh.timing = False
+    secs, rays = 0.0, 0
+    for k, (pts, pose) in enumerate(data):
+        buf = sh.pinned_points(pts.shape[0])
+        buf[...] = pts
+        barrier()
+        t0 = time.perf_counter()
+        sh.integrate_points(buf, pose)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if k >= warm:
+            secs += dt
+            rays += pts.shape[0]
+    t = torch.tensor([secs], dtype=torch.float64, device="cuda")
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    secs = float(t.item())
+    owned = sh.export_map()["glb"].shape[0]
+    out.update({"mode": "ONE map sharded by subbox ownership over the ranks (host scan in pinned memory, H2D + NCCL "
+                        "exchanges inside the timed region, wall clock, max over ranks)",
+                "rays_per_s": rays / secs, "us_per_scan": 1e6 * secs / (scans - warm), "scaling": "strong",
+                "subboxes_owned_rank0": owned, "last_exchange": {k_: v_ for k_, v_ in sh.last.items() if k_ != "timing"}})
+    sh.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -189,6 +246,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=60, help="frames of the workload timed on the CPU oracle")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-queries", action="store_true")
+    ap.add_argument("--no-lidar", action="store_true")
     ap.add_argument("--queries", type=int, default=10_000_000, help="planner queries per step (4:4:2 odd/occupancy/grad)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -284,6 +342,13 @@ def main():
         queries = {"n_local": len(pos), "ms": acc, "total_ms": q_ms, "alg_bytes": q_bytes}
         for pp in (d_pos, d_o1, d_o2, d_o3):
             m.device_free(pp)
+
+    # ---------------- LiDAR-scale integration (BASELINE config 4, CFG-C): 128 x 2048 scans ----------------
+    # N = 1: one map on one GPU.  N > 1: ONE logical map sharded over the ranks by subbox ownership (stage by phi
+    # column, NCCL min-all-reduce / all-gather for the global iteration order, all-to-all of the update records).
+    lidar = None
+    if not args.no_lidar:
+        lidar = run_lidar(rank, world, local_rank, barrier)
 
     # ---------------- pass 2: per-kernel events on the same frames (roofline share) ----------------
     m.close()
@@ -383,6 +448,8 @@ def main():
                               "n_queries": args.queries, "mix": "40% getOdd, 40% getOccupancy, 20% getOddGrad(max_iter=5)",
                               "ms_per_step": q_ms_max, "per_kernel_rank0": per, "inputs": "device-resident, L2 flushed",
                               "split": "evenly over ranks, each rank queries its own agent map"}
+        if lidar:
+            out["lidar"] = lidar
         if not args.no_cpu:
             nf = min(args.cpu_frames, total)
             c_rays, c_s = run_cpu_sample(cfg, frames, poses, nf)
@@ -400,6 +467,21 @@ def main():
                 out["queries"]["cpu_baseline"] = {"value": 300000 / tq, "unit": "queries/s", "cores": 1, "kind": "port",
                                                   "sample": "300k queries (same 4:4:2 mix) on a 20-frame oracle map"}
                 orc.close()
+            if lidar:
+                from mlmapping_b200 import config_cfg_c, scenes as _sc2
+                from oracle_binding import Oracle as _Orc
+                cfg_c = config_cfg_c()
+                oc = _Orc(cfg_c, bookkeeping=False)
+                l_rays, l_s = 0, 0.0
+                for k in range(3):
+                    pose = _sc2.lidar_loop_pose(k)
+                    st_l = oc.integrate_points(_sc2.lidar_scan(pose, frame_idx=k), pose)
+                    if k >= 1:
+                        l_rays += st_l.n_points
+                        l_s += oc.last_seconds
+                oc.close()
+                out["lidar"]["cpu_baseline"] = {"value": l_rays / l_s, "unit": UNIT, "cores": 1, "kind": "port",
+                                                "sample": "scans 1-2 of the same loop on the CPU oracle, single thread"}
             out["cpu_baseline"] = {"value": c_rays / c_s, "unit": UNIT, "cores": 1, "kind": "port",
                                    "sample": f"first {nf} frames of {WORKLOAD} on the CPU oracle, single thread "
                                              f"({os.cpu_count()} host cores present)",

@@ -61,5 +61,14 @@ int main() {
               map.getOccupancy(far), map.getOdd(wall));
   Vec3 g = map.getOddGrad(Vec3(7.0, 1.12, 1.2));
   std::printf("getOddGrad near wall = (%.4f, %.4f, %.4f)\n", g[0], g[1], g[2]);
+  // what the reference publishes after an update (occupied-cell cloud, odds slice) and a checkpoint round trip
+  const auto cloud = map.map_cloud(MLM_CLOUD_OCCUPIED);
+  const auto slice = map.odds_slice(1.25);
+  const auto image = map.checkpoint();
+  mlmap copy;
+  copy.init_map(cfg);
+  copy.restore(image);
+  std::printf("occupied cloud %zu points, odds slice %zu cells, checkpoint %zu bytes, restored copy: wall=%d (%zu points)\n",
+              cloud.size(), slice.size(), image.size(), copy.getOccupancy(wall), copy.map_cloud(MLM_CLOUD_OCCUPIED).size());
   return 0;
 }

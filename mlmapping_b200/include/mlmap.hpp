@@ -8,6 +8,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -128,6 +129,40 @@ class mlmap {
   void getOdd(const Vec3 *pos_w, size_t n, float *out) { check(mlm_get_odd(h_, pos_w->v, n, out), "mlm_get_odd"); }
   void getOddGrad(const Vec3 *pos_w, size_t n, Vec3 *out, size_t max_iter = 5) {
     check(mlm_get_odd_grad(h_, pos_w->v, n, max_iter, out->v), "mlm_get_odd_grad");
+  }
+
+  // map clouds for consumers: what rviz_vis::pub_global_local_map / pub_frontier put on the wire
+  // (src/rviz_vis.cpp:267-327) and mlmap::visualize_odds' slice (src/mlmap.cpp:200-284), compacted on the device.
+  // Points are {x, y, z, w} floats, the layout of pcl::PointXYZ.
+  struct PointXYZW { float x, y, z, w; };
+  std::vector<PointXYZW> map_cloud(int kind = MLM_CLOUD_INFLATED) {
+    size_t n = 0;
+    check(mlm_export_cloud(h_, kind, nullptr, 0, &n), "mlm_export_cloud");
+    std::vector<PointXYZW> pts(n);
+    if (n) check(mlm_export_cloud(h_, kind, &pts[0].x, n, &n), "mlm_export_cloud");
+    pts.resize(std::min(n, pts.size()));
+    return pts;
+  }
+  std::vector<PointXYZW> frontier_cloud() { return map_cloud(MLM_CLOUD_FRONTIER); }
+  std::vector<PointXYZW> odds_slice(double height = 0.7) {  // w = logit_inv(log_odds) of the cell
+    size_t n = 0;
+    check(mlm_export_odds_slice(h_, height, nullptr, 0, &n), "mlm_export_odds_slice");
+    std::vector<PointXYZW> pts(n);
+    if (n) check(mlm_export_odds_slice(h_, height, &pts[0].x, n, &n), "mlm_export_odds_slice");
+    pts.resize(std::min(n, pts.size()));
+    return pts;
+  }
+  // checkpoint / restore of the whole map (no counterpart in the reference, which keeps its map in process memory)
+  std::vector<unsigned char> checkpoint() {
+    size_t n = 0;
+    check(mlm_checkpoint_size(h_, &n), "mlm_checkpoint_size");
+    std::vector<unsigned char> image(n);
+    check(mlm_checkpoint_save(h_, image.data(), image.size(), &n), "mlm_checkpoint_save");
+    image.resize(n);
+    return image;
+  }
+  void restore(const std::vector<unsigned char> &image) {
+    check(mlm_checkpoint_restore(h_, image.data(), image.size()), "mlm_checkpoint_restore");
   }
 
   const mlm_frame_stats &last_stats() const { return stats_; }

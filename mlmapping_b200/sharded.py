@@ -34,6 +34,13 @@ class ShardedMLMap:
         self.last = {}
         self._pinned = None
         self._views = {}
+        self.timing = True  # per-stage wall times in self.last (one device sync per stage); switch off for throughput runs
+
+    def pinned_points(self, n: int) -> np.ndarray:
+        """(n,3) float64 view of the page-locked scan buffer: fill it in place and pass it to integrate_points"""
+        if self._pinned is None:
+            self._pinned = self.map.pinned_array((max(n, self.map.cfg.max_points), 3), np.float64)
+        return self._pinned[:n]
 
     def _dist(self):
         import torch.distributed as dist
@@ -48,6 +55,8 @@ class ShardedMLMap:
 
         def lap(name):
             nonlocal t_prev
+            if not self.timing:
+                return
             torch.cuda.synchronize(self.dev)
             now = time.perf_counter()
             tm[name] = round(1e6 * (now - t_prev), 1)
@@ -55,7 +64,8 @@ class ShardedMLMap:
         pts = np.ascontiguousarray(np.asarray(xyz, dtype=np.float64).reshape(-1, 3))
         if self._pinned is None or self._pinned.shape[0] < pts.shape[0]:
             self._pinned = m.pinned_array((max(pts.shape[0], self.map.cfg.max_points), 3), np.float64)
-        self._pinned[:pts.shape[0]] = pts  # page-locked staging: the H2D copy runs without a second host copy
+        if pts.ctypes.data != self._pinned.ctypes.data:  # a scan produced in place (pinned_points) needs no host copy
+            self._pinned[:pts.shape[0]] = pts  # page-locked staging: the H2D copy runs without a second host copy
         pts = self._pinned[:pts.shape[0]]
         n_hit, n_miss = C.c_int32(), C.c_int32()
         m._check(lib.mlm_shard_stage_points_f64(m._h, pts.ctypes.data, pts.shape[0], _pose7(T_wb), self.rank, self.world,
