@@ -214,6 +214,16 @@ int mlm_export_map(mlm_handle h, size_t cap_submaps, int32_t *glb3, uint8_t *col
  * bitmask of ceil(subbox_n^3 / 32) 32-bit words per subbox (bit c = cell id c), with its own glb3 list. */
 int mlm_export_frontier(mlm_handle h, size_t cap_submaps, int32_t *glb3, uint32_t *frontier_words, size_t *n_out);
 
+/* ---- pose forwarding of the ROS callback, host-only, no handle ---------------------------------------
+ * mlmap::depth_odom_input_callback (src/mlmap.cpp:470-498) forwards the odometry pose to the image stamp with a linear
+ * model before the update:  time_gap = gap_imu - latency;  rot_cp = log(R) + time_gap * (R * omega);
+ * T_wb = (exp(rot_cp), p + (gap_odom - latency) * v), with Sophus' SO3::log / SO3::exp (so3.cpp:127-199).
+ * gap_* = image stamp - odometry / IMU stamp in seconds; quaternion order w,x,y,z; T_wb_out = {x,y,z,qw,qx,qy,qz},
+ * ready for mlm_integrate_*. */
+int mlm_compensate_pose(const double odom_pos[3], const double odom_quat_wxyz[4], const double odom_lin_vel[3],
+                        const double imu_ang_vel[3], double gap_odom_s, double gap_imu_s, double camera2odom_latency_s,
+                        double T_wb_out[7]);
+
 /* ---- map clouds for consumers ---------------------------------------------------------------------
  * Whole-map compaction on the device into float4 points {x, y, z, w} (16-byte stride = pcl::PointXYZ, the wire format
  * of the reference's PointCloud2 topics, include/common.h:53):

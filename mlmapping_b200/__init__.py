@@ -17,4 +17,5 @@ from .capi import (  # noqa: F401
     config_cfg_a,
     config_cfg_b,
     config_cfg_c,
+    compensate_pose,
 )

@@ -111,7 +111,7 @@ ABI_SYMBOLS = [
     "mlm_sizeof_frame_stats", "mlm_debug_phase_cycles", "mlm_host_alloc", "mlm_host_free", "mlm_srand", "mlm_debug_rand", "mlm_export_frontier", "mlm_shard_stage_points_f64",
     "mlm_shard_copy_hit_keys", "mlm_shard_stage_points_f64_device", "mlm_shard_act_buffer", "mlm_shard_order_fast", "mlm_shard_order", "mlm_shard_emit_counts", "mlm_shard_emit_pack", "mlm_shard_ingest", "mlm_dirty_count", "mlm_dirty_export", "mlm_dirty_import",
     "mlm_export_cloud", "mlm_export_cloud_device", "mlm_export_odds_slice",
-    "mlm_checkpoint_size", "mlm_checkpoint_save", "mlm_checkpoint_restore",
+    "mlm_checkpoint_size", "mlm_checkpoint_save", "mlm_checkpoint_restore", "mlm_compensate_pose",
     "mlm_export_cloud", "mlm_export_cloud_device", "mlm_export_odds_slice",
 ]
 FRAME_KERNELS = ["k_project", "k_column", "k_fuse"]
@@ -189,6 +189,7 @@ def load_library() -> C.CDLL:
         "mlm_checkpoint_size": ([vp, C.POINTER(sz)], C.c_int),
         "mlm_checkpoint_save": ([vp, vp, sz, C.POINTER(sz)], C.c_int),
         "mlm_checkpoint_restore": ([vp, vp, sz], C.c_int),
+        "mlm_compensate_pose": ([dp, dp, dp, dp, C.c_double, C.c_double, C.c_double, dp], C.c_int),
         "mlm_shard_stage_points_f64": ([vp, vp, C.c_int, dp, C.c_int, C.c_int, ip, ip], C.c_int),
         "mlm_shard_copy_hit_keys": ([vp, vp, vp], C.c_int),
         "mlm_shard_stage_points_f64_device": ([vp, vp, C.c_int, dp, C.c_int, C.c_int, ip, ip], C.c_int),
@@ -284,6 +285,17 @@ def config_cfg_c() -> MlmConfig:
 def _pose7(T_wb) -> "C.Array":
     a = np.ascontiguousarray(np.asarray(T_wb, dtype=np.float64).reshape(7))
     return (C.c_double * 7)(*a.tolist())
+
+
+def compensate_pose(pos, quat_wxyz, lin_vel, ang_vel, gap_odom_s, gap_imu_s, latency_s) -> np.ndarray:
+    """pose forwarded to the image stamp as in depth_odom_input_callback (src/mlmap.cpp:470-498): pose7 for integrate_*"""
+    lib = load_library()
+    a = [(C.c_double * len(v))(*[float(x) for x in v]) for v in (pos, quat_wxyz, lin_vel, ang_vel)]
+    out = (C.c_double * 7)()
+    rc = lib.mlm_compensate_pose(a[0], a[1], a[2], a[3], float(gap_odom_s), float(gap_imu_s), float(latency_s), out)
+    if rc != MLM_OK:
+        raise MlmError(rc, "mlm_compensate_pose")
+    return np.array(out[:], dtype=np.float64)
 
 
 class MLMap:

@@ -717,6 +717,55 @@ int host_query(mlm_handle h, const double *pos, size_t n, OutT *out, size_t out_
 
 extern "C" {
 
+// depth_odom_input_callback's pose forwarding, src/mlmap.cpp:470-498: host-side, once per frame, no device work.
+// SO3::log / SO3::exp as in 3rdPartLib/Sophus/sophus/so3.cpp:127-199 (SMALL_EPS 1e-10, so3.h:35), rot_og.matrix()
+// as Eigen's Quaternion::toRotationMatrix.
+int mlm_compensate_pose(const double odom_pos[3], const double odom_quat_wxyz[4], const double odom_lin_vel[3],
+                        const double imu_ang_vel[3], double gap_odom_s, double gap_imu_s, double camera2odom_latency_s,
+                        double T_wb_out[7]) {
+  if (!odom_pos || !odom_quat_wxyz || !odom_lin_vel || !imu_ang_vel || !T_wb_out) return MLM_ERR_INVALID_ARG;
+  const double time_gap = gap_imu_s - camera2odom_latency_s;
+  const HQuat q = h_normalized(HQuat{odom_quat_wxyz[0], odom_quat_wxyz[1], odom_quat_wxyz[2], odom_quat_wxyz[3]});
+  // rot_dot = rot_og.matrix() * angular velocity
+  const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+  const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+  const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  const double m[3][3] = {{1 - (tyy + tzz), txy - twz, txz + twy}, {txy + twz, 1 - (txx + tzz), tyz - twx}, {txz - twy, tyz + twx, 1 - (txx + tyy)}};
+  double rot_dot[3];
+  for (int i = 0; i < 3; i++) rot_dot[i] = m[i][0] * imu_ang_vel[0] + m[i][1] * imu_ang_vel[1] + m[i][2] * imu_ang_vel[2];
+  // rot_cp = rot_og.log() + time_gap * rot_dot
+  const double n = sqrt(q.x * q.x + q.y * q.y + q.z * q.z);
+  const double w = q.w, squared_w = w * w;
+  double k;
+  if (n < 1e-10)
+    k = 2. / w - 2. * (n * n) / (w * squared_w);
+  else
+    k = 2 * atan(n / w) / n;  // the reference's |w| < SMALL_EPS branch is overwritten by this statement (so3.cpp:152-165)
+  const double lg[3] = {k * q.x, k * q.y, k * q.z};
+  double rc[3];
+  for (int i = 0; i < 3; i++) rc[i] = lg[i] + rot_dot[i] * time_gap;
+  // SO3::exp(rot_cp)
+  const double theta = sqrt(rc[0] * rc[0] + rc[1] * rc[1] + rc[2] * rc[2]);
+  const double half_theta = 0.5 * theta;
+  const double real_factor = cos(half_theta);
+  double imag_factor;
+  if (theta < 1e-10) {
+    const double theta_sq = theta * theta, theta_po4 = theta_sq * theta_sq;
+    imag_factor = 0.5 - 0.0208333 * theta_sq + 0.000260417 * theta_po4;
+  } else {
+    imag_factor = sin(half_theta) / theta;
+  }
+  const HQuat e = h_normalized(HQuat{real_factor, imag_factor * rc[0], imag_factor * rc[1], imag_factor * rc[2]});
+  const double dt = gap_odom_s - camera2odom_latency_s;
+  for (int i = 0; i < 3; i++) T_wb_out[i] = odom_pos[i] + odom_lin_vel[i] * dt;
+  T_wb_out[3] = e.w;
+  T_wb_out[4] = e.x;
+  T_wb_out[5] = e.y;
+  T_wb_out[6] = e.z;
+  return MLM_OK;
+}
+
 int mlm_abi_version(void) { return MLM_ABI_VERSION; }
 size_t mlm_sizeof_config(void) { return sizeof(mlm_config); }
 size_t mlm_sizeof_frame_stats(void) { return sizeof(mlm_frame_stats); }

@@ -77,6 +77,16 @@ class mlmap {
   }
   void set_pose(const SE3 &T_wb) { T_wb_ = T_wb; }
 
+  // the callback's linear pose forwarding to the image stamp (src/mlmap.cpp:470-498); gaps in seconds
+  static SE3 compensate_pose(const Vec3 &pos, double qw, double qx, double qy, double qz, const Vec3 &lin_vel,
+                             const Vec3 &ang_vel, double gap_odom, double gap_imu, double camera2odom_latency) {
+    const double q[4] = {qw, qx, qy, qz};
+    SE3 T;
+    if (mlm_compensate_pose(pos.v, q, lin_vel.v, ang_vel.v, gap_odom, gap_imu, camera2odom_latency, T.p) != MLM_OK)
+      throw std::runtime_error("mlm_compensate_pose failed");
+    return T;
+  }
+
   // project_depth() + update_map() (src/mlmap.cpp:311-349,382-386).  Back-projection runs inside the
   // same device pass as the awareness/local update, so project_depth() only arms the frame.
   void project_depth() { projected_ = img_ != nullptr; }

@@ -134,6 +134,56 @@ inline SE3 se3_from_pose7(const double p[7]) {
   return SE3(SO3(Quat{p[3], p[4], p[5], p[6]}), Vec3(p[0], p[1], p[2]));
 }
 
+// Sophus SO3::log / SO3::exp (3rdPartLib/Sophus/sophus/so3.cpp:127-199), SMALL_EPS = 1e-10 (so3.h:35)
+inline Vec3 so3_log(const SO3 &r) {
+  const double n = sqrt(r.q.x * r.q.x + r.q.y * r.q.y + r.q.z * r.q.z);
+  const double w = r.q.w;
+  const double squared_w = w * w;
+  double two_atan_nbyw_by_n;
+  if (n < 1e-10) {
+    two_atan_nbyw_by_n = 2. / w - 2. * (n * n) / (w * squared_w);
+  } else {
+    // the |w| < SMALL_EPS branch of the reference is overwritten by the next statement (so3.cpp:152-165)
+    two_atan_nbyw_by_n = 2 * atan(n / w) / n;
+  }
+  return Vec3(two_atan_nbyw_by_n * r.q.x, two_atan_nbyw_by_n * r.q.y, two_atan_nbyw_by_n * r.q.z);
+}
+inline SO3 so3_exp(const Vec3 &omega) {
+  const double theta = sqrt(omega[0] * omega[0] + omega[1] * omega[1] + omega[2] * omega[2]);
+  const double half_theta = 0.5 * theta;
+  double imag_factor;
+  const double real_factor = cos(half_theta);
+  if (theta < 1e-10) {
+    const double theta_sq = theta * theta;
+    const double theta_po4 = theta_sq * theta_sq;
+    imag_factor = 0.5 - 0.0208333 * theta_sq + 0.000260417 * theta_po4;
+  } else {
+    imag_factor = sin(half_theta) / theta;
+  }
+  return SO3(Quat{real_factor, imag_factor * omega[0], imag_factor * omega[1], imag_factor * omega[2]});
+}
+// Eigen Quaternion::toRotationMatrix() times a vector (rot_og.matrix() * w), src/mlmap.cpp:492
+inline Vec3 quat_matrix_times(const Quat &q, const Vec3 &v) {
+  const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+  const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+  const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  const double m00 = 1 - (tyy + tzz), m01 = txy - twz, m02 = txz + twy;
+  const double m10 = txy + twz, m11 = 1 - (txx + tzz), m12 = tyz - twx;
+  const double m20 = txz - twy, m21 = tyz + twx, m22 = 1 - (txx + tyy);
+  return Vec3(m00 * v[0] + m01 * v[1] + m02 * v[2], m10 * v[0] + m11 * v[1] + m12 * v[2], m20 * v[0] + m21 * v[1] + m22 * v[2]);
+}
+// pose forwarded to the image stamp, mlmap::depth_odom_input_callback src/mlmap.cpp:470-498:
+// time_gap = gap_imu - latency; rot_cp = log(R) + time_gap * (R * omega); T_wb = (exp(rot_cp), p + (gap_odom - latency) * v)
+inline SE3 compensate_pose(const Vec3 &pos, const Quat &quat, const Vec3 &lin_vel, const Vec3 &ang_vel, double gap_odom,
+                           double gap_imu, double camera2odom_latency) {
+  const double time_gap = gap_imu - camera2odom_latency;
+  const SO3 rot_og(quat);
+  const Vec3 rot_dot = quat_matrix_times(rot_og.q, ang_vel);
+  const Vec3 rot_cp = so3_log(rot_og) + rot_dot * time_gap;
+  return SE3(so3_exp(rot_cp), pos + lin_vel * (gap_odom - camera2odom_latency));
+}
+
 // ---- awareness_map_cylindrical (include/map_awareness.h, src/map_awareness.cpp) ------------------
 #define ORC_deg2rad M_PI / 180 /* unparenthesised on purpose, map_awareness.h:7 */
 class awareness_map {

@@ -262,6 +262,19 @@ void orc_T_ls(const double T_wb[7], const double T_bs[7], double out7[7]) {
   out7[5] = T_ls.so3.q.y;
   out7[6] = T_ls.so3.q.z;
 }
+void orc_compensate_pose(const double pos[3], const double quat_wxyz[4], const double lin_vel[3], const double ang_vel[3],
+                         double gap_odom, double gap_imu, double latency, double out7[7]) {
+  SE3 T = compensate_pose(Vec3(pos[0], pos[1], pos[2]), Quat{quat_wxyz[0], quat_wxyz[1], quat_wxyz[2], quat_wxyz[3]},
+                          Vec3(lin_vel[0], lin_vel[1], lin_vel[2]), Vec3(ang_vel[0], ang_vel[1], ang_vel[2]), gap_odom, gap_imu,
+                          latency);
+  out7[0] = T.t[0];
+  out7[1] = T.t[1];
+  out7[2] = T.t[2];
+  out7[3] = T.so3.q.w;
+  out7[4] = T.so3.q.x;
+  out7[5] = T.so3.q.y;
+  out7[6] = T.so3.q.z;
+}
 // libstdc++ growth chain probe: bucket_count of an empty unordered_set after rehash(n)
 size_t orc_next_bucket_count(size_t n) {
   std::unordered_set<size_t> s;

@@ -74,6 +74,7 @@ def load_oracle():
     lib.orc_transform_point.argtypes = [dp, dp, dp, dp]
     lib.orc_T_ls.argtypes = [dp, dp, dp]
     lib.orc_next_bucket_count.argtypes, lib.orc_next_bucket_count.restype = [sz], sz
+    lib.orc_compensate_pose.argtypes = [dp, dp, dp, dp, C.c_double, C.c_double, C.c_double, dp]
     _lib = lib
     return lib
 

@@ -46,3 +46,43 @@ def test_oracle_matches_golden_fixtures():
     for name, want in meta["cases"].items():
         got = run_case(name)
         assert got == want, name
+
+
+def test_pose_forwarding_matches_the_callback_and_the_oracle():
+    """mlm_compensate_pose = depth_odom_input_callback's linear pose forwarding (src/mlmap.cpp:470-498) with Sophus'
+    SO3::log / SO3::exp (so3.cpp:127-199): known answers, then the product (host code of the C ABI) against the oracle"""
+    import ctypes as C
+    from mlmapping_b200 import compensate_pose
+    from oracle_binding import load_oracle
+    lib = load_oracle()
+
+    def oracle(pos, q, v, w, go, gi, lat):
+        arr = [(C.c_double * len(a))(*a) for a in (pos, q, v, w)]
+        out = (C.c_double * 7)()
+        lib.orc_compensate_pose(arr[0], arr[1], arr[2], arr[3], go, gi, lat, out)
+        return np.array(out[:])
+
+    # zero gaps: the odometry pose itself (log followed by exp returns the unit quaternion up to rounding)
+    q0 = np.array([np.cos(0.3), 0.0, 0.0, np.sin(0.3)])
+    T = compensate_pose([1, 2, 3], q0, [0.5, 0, 0], [0, 0, 1.0], 0.0, 0.0, 0.0)
+    assert np.allclose(T[:3], [1, 2, 3]) and np.allclose(T[3:], q0, atol=1e-15)
+    # pure yaw rate 1 rad/s for 0.1 s after a 20 ms latency: yaw grows by 0.08 rad; position moves 0.03 * v
+    T = compensate_pose([1, 2, 3], q0, [0.5, -1.0, 0.25], [0, 0, 1.0], 0.05, 0.1, 0.02)
+    assert np.allclose(T[:3], [1 + 0.03 * 0.5, 2 - 0.03, 3 + 0.03 * 0.25], atol=1e-15)
+    yaw = 2 * np.arctan2(T[6], T[3])
+    assert abs(yaw - (0.6 + 0.08)) < 1e-12 and abs(T[4]) < 1e-15 and abs(T[5]) < 1e-15
+    # body-frame rate: rot_dot = R * omega (a roll rate seen from a yawed body turns about the rotated axis)
+    T = compensate_pose([0, 0, 0], [np.cos(np.pi / 4), 0, 0, np.sin(np.pi / 4)], [0, 0, 0], [1.0, 0, 0], 0.0, 1e-3, 0.0)
+    lg = 2 * np.arccos(T[3]) * T[4:7] / np.linalg.norm(T[4:7])
+    assert np.allclose(lg, [0.0, 1e-3, np.pi / 2], atol=1e-12)
+    # random cases incl. the small-angle branches: bit-identical to the oracle restatement
+    rs = np.random.RandomState(11)
+    for i in range(200):
+        q = rs.normal(size=4)
+        if i % 10 == 0:
+            q = np.array([1.0, 0, 0, 0]) + rs.normal(size=4) * 1e-12  # n < SMALL_EPS branch of log
+        pos, v, w = rs.normal(size=3) * 5, rs.normal(size=3), rs.normal(size=3) * (0.0 if i % 25 == 0 else 1.0)
+        go, gi, lat = rs.uniform(-0.05, 0.05), rs.uniform(-0.05, 0.05), rs.uniform(0, 0.03)
+        a, b = compensate_pose(pos, q, v, w, go, gi, lat), oracle(list(pos), list(q), list(v), list(w), go, gi, lat)
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), (i, a, b)
+        assert abs(np.linalg.norm(a[3:]) - 1) < 1e-15

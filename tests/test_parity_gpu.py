@@ -181,6 +181,29 @@ def test_fallback_paths_global_sort_spill_and_oversized_columns(monkeypatch):
         assert_map_parity(gpu, orc, LO_TOL)
 
 
+def test_alternative_launch_paths_give_the_same_map(monkeypatch):
+    """the frame runs as one cooperative k_frame launch by default; the three stand-alone kernels (graph or direct
+    launches) and whole-column work items (no split at the sensor row) must give the same cell sets and map"""
+    cfg = config_cfg_a()
+    frames = []
+    for k in range(3):
+        pose = scenes.corridor_trajectory_pose(35 * k)
+        frames.append((scenes.corridor_depth_frame(cfg, pose, frame_idx=k), pose))
+    for env in ({"MLM_NO_FUSED": "1"}, {"MLM_DEBUG_NO_SPLIT": "1"}, {"MLM_NO_FUSED": "1", "MLM_NO_GRAPH": "1"},
+                {"MLM_NO_FUSED": "1", "MLM_DEBUG_NO_SPLIT": "1"}):
+        for k_, v_ in env.items():
+            monkeypatch.setenv(k_, v_)
+        gpu, orc = MLMap(cfg), Oracle(cfg)
+        for k_ in env:
+            monkeypatch.delenv(k_)
+        for i, (img, pose) in enumerate(frames):
+            st_g, st_o = gpu.integrate_depth(img, pose), orc.integrate_depth(img, pose)
+            assert_frame_parity(gpu, orc, st_g, st_o, tag=f"{env} frame{i}")
+        expected_launches = 3 * len(frames) if "MLM_NO_FUSED" in env else len(frames)
+        assert gpu.kernel_launch_count() >= expected_launches
+        assert_map_parity(gpu, orc, LO_TOL)
+
+
 def test_full_size_cfg_b_l515_like():
     """BASELINE config 3 geometry at full size: 1024x768 @ 0.05 m, n_Rho 180, n_Z 81 (3 frames)"""
     from mlmapping_b200 import config_cfg_b
