@@ -1202,8 +1202,13 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
   MLM_PHASE(6);
   // (e) distinct miss cells -> voxel grid staging (one cell per thread); bitmap to global for export.
   // The sorted keys are dead now: the key area is the scratch for the compacted cell list.
+  // First key buffer: the compacted cell list of a chunk; second: the voxels the chunk touches first, which go to
+  // the frame's touched list with ONE global reservation per chunk (a per-voxel append would put a contended
+  // same-address atomic with return on every thread's dependent chain).
   uint32_t *s_list = reinterpret_cast<uint32_t *>(s_keys);
-  const int list_cap = P.sort_cap_smem * 4;            // 32-bit entries in the two key buffers
+  uint32_t *s_tout = s_list + P.sort_cap_smem * 2;
+  __shared__ int s_tcnt, s_tbase;
+  const int list_cap = P.sort_cap_smem * 2;            // 32-bit entries in one key buffer
   const int words_per_chunk = max(1, list_cap >> 5);   // a chunk of words can never overflow the list
   for (int wi = z_own_lo * P.words_per_row + tid; wi < z_own_hi * P.words_per_row; wi += blockDim.x) g_miss[wi] = s_miss[wi];
   if (z_shared >= 0) {
@@ -1218,7 +1223,10 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
   const int stage_w0 = min(z_own_lo, z_shared >= 0 ? z_shared : z_own_lo) * P.words_per_row;
   const int stage_w1 = max(z_own_hi, z_shared + 1) * P.words_per_row;
   for (int w0 = stage_w0; w0 < stage_w1; w0 += words_per_chunk) {
-    if (tid == 0) s_nk = 0;
+    if (tid == 0) {
+      s_nk = 0;
+      s_tcnt = 0;
+    }
     __syncthreads();
     compact_bits(s_miss, w0, min(w0 + words_per_chunk, stage_w1), s_list, &s_nk, tid >> 5, (int)blockDim.x >> 5);
     __syncthreads();
@@ -1247,13 +1255,21 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
         D.miss_bucket[j] = bkt;
       }
       int old = atomicAdd(&D.lvg[lv].y, 1);
-      if (old == 0) {
-        int tp = agg_inc(&fc->n_touched);
-        if (tp < P.max_touched) D.touched[tp] = (uint32_t)lv; else fc->error = kErrCapacity;
-      }
+      if (old == 0) s_tout[agg_inc(&s_tcnt)] = (uint32_t)lv;
       touch_subbox(P, F, D, fc, cr.g);
     }
-    if (tid == 0) s_nmiss += n_list;
+    __syncthreads();
+    const int n_t = s_tcnt;
+    if (tid == 0) {
+      s_nmiss += n_list;
+      if (n_t) s_tbase = atomicAdd(&fc->n_touched, n_t);
+    }
+    __syncthreads();
+    if (n_t) {
+      const int tb = s_tbase;
+      if (tb + n_t > P.max_touched) fc->error = kErrCapacity;
+      for (int i = tid; i < n_t && tb + i < P.max_touched; i += blockDim.x) D.touched[tb + i] = s_tout[i];
+    }
     __syncthreads();
   }
   MLM_PHASE(7);
