@@ -372,14 +372,15 @@ def main():
         pf = m.pinned_array(f.shape, np.uint16)
         pf[...] = f
         pinned.append(pf)
+    ptrs = [pf.ctypes.data for pf in pinned]  # the C-ABI call takes the host address, as a C/C++ caller passes it
     for k in range(args.warmup):
-        m.integrate_depth(pinned[k], poses[k])
+        m.integrate_depth_ptr(ptrs[k], ROWS, COLS, 2 * COLS, poses[k])
     barrier()
     e2e_s, e2e_rays = 0.0, 0
     for k in range(args.warmup, total):
-        m.flush_l2()
+        m.flush_l2()  # synchronous: the flush is not part of the step
         t0 = time.perf_counter()
-        st = m.integrate_depth(pinned[k], poses[k])
+        st = m.integrate_depth_ptr(ptrs[k], ROWS, COLS, 2 * COLS, poses[k])
         e2e_s += time.perf_counter() - t0
         e2e_rays += st.n_points
     barrier()

@@ -341,14 +341,30 @@ class MLMap:
         if img.strides[1] != 2:
             img = np.ascontiguousarray(img)
         st = FrameStats()
+        # the binding itself is on the end-to-end path: a reused pose buffer instead of fresh ctypes objects
         self._check(self._lib.mlm_integrate_depth_u16(self._h, img.ctypes.data, img.shape[0], img.shape[1],
-                                                      img.strides[0], _pose7(T_wb), C.byref(st)))
+                                                      img.strides[0], self._pose(T_wb), C.byref(st)))
         self.has_data = self.map_updated = True
         return st
 
+    def integrate_depth_ptr(self, host_ptr: int, rows: int, cols: int, stride_bytes: int, T_wb) -> FrameStats:
+        """mlm_integrate_depth_u16 on a raw host address (what a C/C++ caller passes): no numpy work on the call path"""
+        st = FrameStats()
+        self._check(self._lib.mlm_integrate_depth_u16(self._h, host_ptr, rows, cols, stride_bytes, self._pose(T_wb), C.byref(st)))
+        self.has_data = self.map_updated = True
+        return st
+
+    def _pose(self, T_wb):
+        buf = self.__dict__.get("_pose_buf")
+        if buf is None:
+            buf = self._pose_buf = (C.c_double * 7)()
+            self._pose_np = np.frombuffer(buf, dtype=np.float64)
+        self._pose_np[:] = T_wb
+        return buf
+
     def integrate_depth_device(self, d_img: int, rows: int, cols: int, T_wb) -> FrameStats:
         st = FrameStats()
-        self._check(self._lib.mlm_integrate_depth_u16_device(self._h, d_img, rows, cols, _pose7(T_wb), C.byref(st)))
+        self._check(self._lib.mlm_integrate_depth_u16_device(self._h, d_img, rows, cols, self._pose(T_wb), C.byref(st)))
         return st
 
     def integrate_points(self, xyz: np.ndarray, T_wb) -> FrameStats:
@@ -361,7 +377,7 @@ class MLMap:
 
     def integrate_points_device(self, d_xyz: int, n: int, T_wb) -> FrameStats:
         st = FrameStats()
-        self._check(self._lib.mlm_integrate_points_f64_device(self._h, d_xyz, n, _pose7(T_wb), C.byref(st)))
+        self._check(self._lib.mlm_integrate_points_f64_device(self._h, d_xyz, n, self._pose(T_wb), C.byref(st)))
         return st
 
     def setFree_map_in_bound(self, box_min, box_max):
