@@ -12,7 +12,7 @@ from pathlib import Path
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
-_LIB_PATH = _PKG / "lib" / "libmlmap_b200.so"
+_LIB_PATH = Path(os.environ["MLM_LIB_PATH"]) if os.environ.get("MLM_LIB_PATH") else _PKG / "lib" / "libmlmap_b200.so"  # override: A/B builds
 
 MLM_OK = 0
 ERR_NAMES = {

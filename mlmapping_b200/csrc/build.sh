@@ -8,4 +8,4 @@ mkdir -p "$OUT"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false \
   -Xcompiler -fPIC,-O3,-Wall,-fvisibility=hidden -Xptxas -v -shared -cudart static \
-  -o "$OUT/libmlmap_b200.so" "$HERE/mlmap_capi.cu" "$@"
+  -o "${MLM_OUT:-$OUT/libmlmap_b200.so}" "$HERE/mlmap_capi.cu" "$@"
