@@ -1002,7 +1002,9 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
   // From here the CTA works as two halves with their own named barriers: warps 0-15 detect the cell
   // segments, fold them and stage the hit keys; warps 16-31 run the ray walks (which only need the
   // records and the end-cell bitmap).  They meet again before the miss staging.
-  if (tid < kHalf) {
+  const int nFold = kHalf;  // an adaptive split (768/256 by contributions per record) was measured: no gain at CFG-A, slower LiDAR scans
+  const int nWalk = kColThreads - nFold;
+  if (tid < nFold) {
     // (c1) ordered list of segment heads (first contribution of every distinct cell) and a compact decode
     // of every contribution, both in the idle ping-pong buffer:
     //   s_head[h]  = index into keys of the h-th cell's first contribution
@@ -1013,7 +1015,7 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
     {
       // one pass, heads compacted in any order (the fold and the staging do not care which thread gets which cell)
       const int lane = lane_id();
-      for (int base = tid & ~31; base < n_k; base += kHalf) {
+      for (int base = tid & ~31; base < n_k; base += nFold) {
         const int i = base + lane;
         bool head = false;
         if (i < n_k) {
@@ -1040,7 +1042,7 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
         }
       }
     }
-    group_bar(1, kHalf);
+    group_bar(1, nFold);
     MLM_PHASE_G(4, 0);
     // (c2) update_odds_hashmap fold, one thread per distinct cell (static: head h -> thread h, so the
     // lanes of a warp stay in one loop).  The chain p <- 1-(1-p)(1-odd) is inherently ordered; it is
@@ -1053,7 +1055,7 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
       // instruction costs ~5 cycles, so the loop is written for instruction count: a tight 3-op repeat
       // loop per contribution, entries pre-decoded (s_dec), the next entry and its odds fetched ahead.
       auto fold_chain = [&](const uint32_t *heads, uint32_t *dec) {
-        for (int h = tid; h < n_head; h += kHalf) {
+        for (int h = tid; h < n_head; h += nFold) {
           const int i0 = (int)heads[h];
           int i = i0;
           uint32_t e = dec[i];
@@ -1083,15 +1085,15 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
         fold_chain(s_head, s_dec);
       }
     }
-    group_bar(1, kHalf);
+    group_bar(1, nFold);
     MLM_PHASE_G(5, 0);
     {
       const int n_head = s_nhead;
       int base_idx = 0;
       if (tid == 0) s_nk = atomicAdd(&fc->n_hit, n_head);  // one global reservation per column
-      group_bar(1, kHalf);
+      group_bar(1, nFold);
       base_idx = s_nk;
-      for (int k = tid; k < n_head; k += kHalf) {
+      for (int k = tid; k < n_head; k += nFold) {
         const uint64_t k0 = keys[s_head[k]];
         const int cell = (int)(k0 >> cell_shift);
         const int zk = cell / P.nRho, rk = cell - zk * P.nRho;
@@ -1127,7 +1129,7 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
         touch_subbox(P, F, D, fc, cr.g);
       }
     }
-    group_bar(1, kHalf);
+    group_bar(1, nFold);
     MLM_PHASE_G(8, 0);
   } else {
     // scratch of the walk group: the radix counters are idle now -> [hash set of outside rays][end-cell list]
@@ -1136,17 +1138,17 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
     uint32_t *s_list = s_cnt + hcap;
     const int list_cap = kCntTotal - hcap;
     const int words_per_chunk = max(1, list_cap >> 5);   // a chunk of words can never overflow the list
-    const int gt = tid - kHalf;                          // thread index inside the walk group
+    const int gt = tid - nFold;                          // thread index inside the walk group
 
     // (d) ray walks, src/map_awareness.cpp:241-275
     if (P.visibility_check) {
-      const int warp = gt >> 5, nwarps = kHalf >> 5;
+      const int warp = gt >> 5, nwarps = nWalk >> 5;
       // distinct inside end cells: each walks once (the walk depends only on (rho,phi,z))
       for (int w0 = 0; w0 < P.col_words; w0 += words_per_chunk) {
         if (gt == 0) s_nlist = 0;
-        group_bar(2, kHalf);
+        group_bar(2, nWalk);
         compact_bits(s_end, w0, min(w0 + words_per_chunk, P.col_words), s_list, &s_nlist, warp, nwarps);
-        group_bar(2, kHalf);
+        group_bar(2, nWalk);
         const int n_list = s_nlist;
         // entry (it*32 + lane)*nwarps + warp: every warp gets the same share of the list
         for (int it = 0; it * 32 * nwarps < n_list; it++) {
@@ -1161,14 +1163,14 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
           walk_batch(P, s_miss, k < n_list, rho, z, stamp_col,
                      (P.explore && k < n_list) ? end_t_col[z * P.nRho + rho] : 0u);
         }
-        group_bar(2, kHalf);
+        group_bar(2, nWalk);
       }
       // castable points outside the awareness range walk from the clamped cell (:261-265).  Records
       // with identical (rho,z) repeat the same walk: drop them through a small shared-memory set
       // (walks are idempotent, so a missed duplicate only costs time).
-      for (int i = gt; i < hcap; i += kHalf) s_hash[i] = 0xffffffffu;
-      group_bar(2, kHalf);
-      MLM_PHASE_G(9, kHalf);
+      for (int i = gt; i < hcap; i += nWalk) s_hash[i] = 0xffffffffu;
+      group_bar(2, nWalk);
+      MLM_PHASE_G(9, nFold);
       for (int it = 0; it * 32 * nwarps < n_c; it++) {
         const int i = (it * 32 + lane_id()) * nwarps + warp;
         RayRecord rc;
@@ -1191,8 +1193,8 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
         }
         walk_batch(P, s_miss, need, rc.rho, rc.z, stamp_col, rc.t);
       }
-      group_bar(2, kHalf);
-      MLM_PHASE_G(12, kHalf);
+      group_bar(2, nWalk);
+      MLM_PHASE_G(12, nFold);
     }
   }
 #ifdef MLM_PHASE_TIMING
@@ -1359,9 +1361,12 @@ __device__ __forceinline__ void column_phase(const MapParams &P, DeviceBuffers &
 #ifdef MLM_PHASE_TIMING
   if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); D.debug_cycles[(P.nCol + blockIdx.x) * 16 + 7] = (long long)t_; }
 #endif
+  bool first_round = true;
   for (;;) {
     __syncthreads();  // the previous item is done with shared memory; s_order is in place
-    if (tid == 0) s_item = atomicAdd(D.col_queue, 1);
+    // the first item of every CTA needs no ticket: items [0, gridDim) are dealt by block index, the queue continues after them
+    if (tid == 0) s_item = first_round ? (int)blockIdx.x : atomicAdd(D.col_queue, 1) + (int)gridDim.x;
+    first_round = false;
     __syncthreads();
     const int item = s_item;
     if (item >= n_active) break;
