@@ -358,6 +358,8 @@ __device__ __forceinline__ void project_tile(const MapParams &P, DeviceBuffers &
   }
   const void *input = F.input;
   const int cols = F.cols;
+  const uint32_t cols_magic = F.cols_magic;
+  const int cols_shift = F.cols_shift;
   const int warp0 = tile0 + r0 * 32;
   // ---- the points of this thread: projection, transform, cylindrical index (independent chains) ----
   RayRecord rec[kProjMaxPts];
@@ -383,7 +385,8 @@ __device__ __forceinline__ void project_tile(const MapParams &P, DeviceBuffers &
           raw = (uint16_t)sp.y;
         }
         if (raw != 0) {
-          const int v = pix / cols, u = pix - v * cols;
+          // row / column of the pixel by multiply-high (host-built magic, exact for pixel indices < 2^31)
+          const int v = cols_magic ? (int)(__umulhi((uint32_t)pix, cols_magic) >> cols_shift) : pix / cols, u = pix - v * cols;
           const double depth = (double)(int)raw * P.inv_factor;
           const double du = (double)__fsub_rn((float)u, P.cx) * depth, dv = (double)__fsub_rn((float)v, P.cy) * depth;
           zs = depth;
@@ -1443,7 +1446,10 @@ __device__ __forceinline__ void fuse_body(const MapParams &P, DeviceBuffers &D, 
   const unsigned long long kClaimed64 = (unsigned long long)(uint32_t)kLvgClaimed;  // {head = claimed, miss = 0}
   const unsigned long long kEmpty64 = (unsigned long long)(uint32_t)kLvgEmpty;      // {head = empty,   miss = 0}
   int my_touched = 0, my_obs = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  // entries are dealt warp by warp round-robin over the CTAs: every SM gets its share of the dependent chains
+  // (with contiguous blocks only the first ~40 % of the SMs had work: 82.6 -> 76.6 us per CFG-A frame)
+  const int fw_ = (int)(threadIdx.x >> 5), fl_ = (int)(threadIdx.x & 31);
+  for (int i = ((fw_ * (int)gridDim.x + (int)blockIdx.x) << 5) + fl_; i < n; i += (int)gridDim.x * (int)blockDim.x) {
     const uint32_t e = D.touched[i];
     const int lv = (int)(e & ~kTouchedHitTag);
     // subbox of this cell (independent of the claim below, so its load overlaps the atomic)

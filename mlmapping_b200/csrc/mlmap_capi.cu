@@ -482,6 +482,9 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
   F.input = d_in;
   F.rows = rows;
   F.cols = cols;
+  F.cols_shift = 0;
+  while ((2 << F.cols_shift) <= std::max(cols - 1, 1)) F.cols_shift++;  // floor(log2(cols - 1))
+  F.cols_magic = cols >= 2 ? (uint32_t)(((1ull << (32 + F.cols_shift)) / (uint64_t)cols) + 1) : 0u;  // 0: plain division
   F.n_points = n_points;
   F.n_total = N;
   F.bucket_count = h->bucket_count;

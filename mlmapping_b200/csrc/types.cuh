@@ -89,6 +89,8 @@ struct FrameParams {
   double t_wa[3];   // T_wa translation (= t_wb)
   const void *input; // device pointer: uint16 depth image (rows*cols) or xyz doubles (n_points*3)
   int rows, cols;
+  uint32_t cols_magic;  // pixel index / cols == umulhi(index, cols_magic) >> cols_shift for index < 2^31
+  int cols_shift;
   int n_points;     // point-cloud input
   int n_total;      // rows*cols or n_points: number of input slots this frame
   uint32_t bucket_count;  // emulated hit_idx_odds_hashmap.bucket_count() at frame start
