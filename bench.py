@@ -247,6 +247,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-queries", action="store_true")
     ap.add_argument("--no-lidar", action="store_true")
+    ap.add_argument("--lidar-sharded-any-n", action="store_true", help="run the sharded LiDAR section above 2 ranks too")
     ap.add_argument("--queries", type=int, default=10_000_000, help="planner queries per step (4:4:2 odd/occupancy/grad)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -348,7 +349,20 @@ def main():
     # column, NCCL min-all-reduce / all-gather for the global iteration order, all-to-all of the update records).
     lidar = None
     if not args.no_lidar:
-        lidar = run_lidar(rank, world, local_rank, barrier)
+        if world > 2 and not args.lidar_sharded_any_n:
+            # The sharded exchange is verified on 2 GPUs (tests/multi_gpu/sharded_check.py, this section at N = 2).
+            # A 4-GPU run of this script stopped making progress in round 1 and could not be re-run within the GPU
+            # budget, so until that is understood the section is opt-in above 2 ranks: a hang would cost the
+            # headline line of the whole scaling run.
+            lidar = {"skipped": "sharded LiDAR section runs at N <= 2 by default (--lidar-sharded-any-n to force); "
+                                "unverified above 2 ranks in round 1"}
+        elif world == 1:
+            try:
+                lidar = run_lidar(rank, world, local_rank, barrier)
+            except Exception as e:  # no collectives at N = 1: an error here must not cost the headline line
+                lidar = {"error": f"{type(e).__name__}: {e}"[:300]}
+        else:
+            lidar = run_lidar(rank, world, local_rank, barrier)
 
     # ---------------- pass 2: per-kernel events on the same frames (roofline share) ----------------
     m.close()
@@ -468,7 +482,7 @@ def main():
                 out["queries"]["cpu_baseline"] = {"value": 300000 / tq, "unit": "queries/s", "cores": 1, "kind": "port",
                                                   "sample": "300k queries (same 4:4:2 mix) on a 20-frame oracle map"}
                 orc.close()
-            if lidar:
+            if lidar and "error" not in lidar and "skipped" not in lidar:
                 from mlmapping_b200 import config_cfg_c, scenes as _sc2
                 from oracle_binding import Oracle as _Orc
                 cfg_c = config_cfg_c()
