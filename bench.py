@@ -351,9 +351,10 @@ def main():
     if not args.no_lidar:
         if world > 2 and not args.lidar_sharded_any_n:
             # The sharded exchange is verified on 2 GPUs (tests/multi_gpu/sharded_check.py, this section at N = 2).
-            # A 4-GPU run of this script stopped making progress in round 1 and could not be re-run within the GPU
-            # budget, so until that is understood the section is opt-in above 2 ranks: a hang would cost the
-            # headline line of the whole scaling run.
+            # A 4-GPU run of this script stopped making progress in round 1.  The likely cause was found afterwards
+            # (with the per-stage timing syncs off, the library's ingest kernels could start before torch's
+            # all-to-all had finished; fixed in ShardedMLMap._join_torch_stream) but could not be re-run within the
+            # GPU budget, so the section stays opt-in above 2 ranks: a hang would cost the whole scaling run.
             lidar = {"skipped": "sharded LiDAR section runs at N <= 2 by default (--lidar-sharded-any-n to force); "
                                 "unverified above 2 ranks in round 1"}
         elif world == 1:

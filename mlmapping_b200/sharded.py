@@ -42,6 +42,11 @@ class ShardedMLMap:
             self._pinned = self.map.pinned_array((max(n, self.map.cfg.max_points), 3), np.float64)
         return self._pinned[:n]
 
+    def _join_torch_stream(self):
+        """torch / NCCL work is enqueued on torch's current stream, the library runs on its own stream: results of
+        the former must be complete before the library's kernels read them (the C ABI synchronises the other way)"""
+        self.torch.cuda.current_stream(self.dev).synchronize()
+
     def _dist(self):
         import torch.distributed as dist
         return dist if (self.world > 1) else None
@@ -92,6 +97,7 @@ class ShardedMLMap:
                 dist.all_reduce(act, op=dist.ReduceOp.MIN)
                 act.bitwise_xor_(-2 ** 31)
             lap("allgather_us")
+            self._join_torch_stream()  # the min-all-reduce ran on torch's stream; the library's kernels must see its result
             m._check(lib.mlm_shard_order_fast(m._h, n_total))
         else:
             # rehash frame (map start / growth): gather every rank's (key, stamp) list; each rank re-sequences it
@@ -115,6 +121,7 @@ class ShardedMLMap:
                 keys_all, stamps_all = keys[:n_hit.value].contiguous(), stamps[:n_hit.value].contiguous()
             assert int(keys_all.numel()) == n_total
             lap("allgather_us")
+            self._join_torch_stream()  # gathered keys / stamps are consumed by kernels on the library's stream
             m._check(lib.mlm_shard_order(m._h, keys_all.data_ptr() if n_total else None,
                                          stamps_all.data_ptr() if n_total else None, n_total))
         lap("order_us")
@@ -136,6 +143,7 @@ class ShardedMLMap:
         else:
             recv, n_recv = send, sum(sc)
         lap("alltoall_us")
+        self._join_torch_stream()  # the received records are consumed by kernels on the library's stream
         st = FrameStats()
         m._check(lib.mlm_shard_ingest(m._h, recv.data_ptr() if n_recv else None, n_recv, C.byref(st)))
         lap("ingest_us")
