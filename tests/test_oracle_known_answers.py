@@ -293,3 +293,61 @@ def test_map_clouds_follow_subbox_id2xyz_glb():
     assert sl.shape[0] == lo.size
     assert np.all((sl[:, 3] > 0) & (sl[:, 3] < 1))
     orc.close()
+
+
+def test_far_hit_spreads_over_neighbours_along_the_ray(lib):
+    """update_hits (map_awareness.cpp:135-171): at 5.8 m the depth noise reaches 3*sigma = 0.001125*rho^2 > 3 cells, so one
+    point marks the centre cell and, for d = 1..K, the cells (rho+d, round(z + d*rate)) and (rho-d, round(z - d*rate))
+    with rate = (z - n_below) / rho, each with the tabulated odds of its offset; a second identical point folds
+    p <- 1 - (1-p)(1-odd) in float"""
+    import ctypes as C
+    cfg = config_cfg_a()
+    o = Oracle(cfg)
+    img = np.zeros((480, 640), dtype=np.uint16)
+    v, u = 200, 400
+    img[v, u] = 5500
+    pose = scenes.pose_from_xyz_yaw(5.0, 0.0, 1.2, 0.1)
+    st = o.integrate_depth(img, pose)
+    assert (st.n_points, st.n_inside) == (1, 1)
+    # the point in the awareness frame, from the documented projection + T_ls (checked separately above)
+    fx = np.float32(cfg.cam_fx)
+    d = 5500 * (1.0 / 1000.0)
+    ps = (C.c_double * 3)(float(np.float32(u) - np.float32(cfg.cam_cx)) * d / float(fx),
+                          float(np.float32(v) - np.float32(cfg.cam_cy)) * d / float(np.float32(cfg.cam_fy)), d)
+    pl = (C.c_double * 3)()
+    lib.orc_transform_point((C.c_double * 7)(*pose), (C.c_double * 7)(*cfg.T_bs), ps, pl)
+    x, y, z = pl[0], pl[1], pl[2]
+    rho0 = int(math.sqrt(x * x + y * y) / cfg.am_d_rho)
+    phi = math.degrees(math.atan2(y, x)) % 360.0
+    z0 = int(math.floor((z + cfg.am_n_z_below * cfg.am_d_z + 0.5 * cfg.am_d_z) / cfg.am_d_z))
+    keys, p = o.last_frame_hits()
+    got = {tuple(k): float(pp) for k, pp in zip(keys.tolist(), p)}
+    phis = {k[1] for k in got}
+    assert len(phis) == 1 and abs(phis.pop() + 0.5 - phi) < 0.6           # fast_atan2 is within 0.09 deg of atan2
+    phi0 = keys[0][1]
+    K = 0
+    while K + 1 < 3 * float(lib.orc_three_sigma(o.h, rho0)) / 3 and rho0 + K + 1 < cfg.am_n_rho:
+        K += 1
+    assert K >= 3
+    rate = (z0 - cfg.am_n_z_below) / (rho0 * 1.0)
+    rnd = lambda t: int(math.floor(abs(t) + 0.5) * (1 if t >= 0 else -1))   # std::round: half away from zero
+    expect = {(rho0, phi0, z0): np.float32(lib.orc_odds_table(o.h, 0, rho0))}
+    for dd in range(1, K + 1):
+        expect[(rho0 + dd, phi0, rnd(z0 + dd * rate))] = np.float32(lib.orc_odds_table(o.h, dd, rho0))
+        expect[(rho0 - dd, phi0, rnd(z0 - dd * rate))] = np.float32(lib.orc_odds_table(o.h, -dd, rho0))
+    assert set(got) == set(expect), (sorted(got), sorted(expect))
+    for k, pp in expect.items():
+        assert np.float32(got[k]) == pp, (k, got[k], pp)
+    assert abs(sum(got.values()) - 1.0) < 0.02                               # the offsets' odds are a discretised Gaussian
+    # two identical points in one frame: every key folds once more, in float
+    img[v, u + 1] = 0
+    o2 = Oracle(cfg)
+    pts = np.array([[ps[0], ps[1], ps[2]], [ps[0], ps[1], ps[2]]])
+    o2.integrate_points(pts, pose)
+    keys2, p2 = o2.last_frame_hits()
+    got2 = {tuple(k): np.float32(pp) for k, pp in zip(keys2.tolist(), p2)}
+    one = np.float32(1.0)
+    for k, pp in expect.items():
+        assert got2[k] == one - (one - pp) * (one - pp), k
+    o.close()
+    o2.close()
