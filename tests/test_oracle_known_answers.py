@@ -351,3 +351,64 @@ def test_far_hit_spreads_over_neighbours_along_the_ray(lib):
         assert got2[k] == one - (one - pp) * (one - pp), k
     o.close()
     o2.close()
+
+
+def test_inflated_occupancy_query_probes_19_points():
+    """getOccupancy(pos, inflate) (mlmap.h:142-169): OCCUPIED iff the point itself, one of the 6 axis offsets or one of
+    the 12 planar diagonals (+-inflate on two axes) is occupied; never UNKNOWN; the 8 space diagonals are not probed"""
+    cfg = config_cfg_a()
+    o = Oracle(cfg)
+    img = np.zeros((480, 640), dtype=np.uint16)
+    img[240, 320] = 1000
+    pose = scenes.pose_from_xyz_yaw(5.0, 0.0, 1.2, 0.0)
+    o.integrate_depth(img, pose)
+    o.integrate_depth(img, pose)                       # second frame turns the hit voxel 'o' (see the single-point test)
+    m = o.export_map()
+    si, ci = np.argwhere(m["occupancy"] == b"o")[0]
+    c = m["glb"][si] * 1.0 + np.array([ci % 10, (ci // 10) % 10, ci // 100]) * 0.1 + 0.05
+    r = 0.3
+    assert o.getOccupancy([c])[0] == 0 and o.getOccupancy([c], inflate=r)[0] == 0
+    probes, expect = [], []
+    for dx in (-r, 0.0, r):
+        for dy in (-r, 0.0, r):
+            for dz in (-r, 0.0, r):
+                probes.append(c + [dx, dy, dz])        # querying from here, the occupied cell sits at offset (-dx,-dy,-dz)
+                expect.append(0 if (dx == 0) + (dy == 0) + (dz == 0) >= 1 else 1)
+    got = o.getOccupancy(np.array(probes), inflate=r)
+    assert got.tolist() == expect
+    assert o.getOccupancy([c + [0.0, 0.0, r]])[0] != 0                      # the plain query there is not occupied
+    assert o.getOccupancy([[100.0, 0.0, 0.0]], inflate=r)[0] == 1           # unknown everywhere -> FREE, never UNKNOWN
+    o.close()
+
+
+def test_odd_gradient_picks_the_strictly_lowest_neighbour():
+    """getOddGrad (mlmap.h:237-295): the six axis probes are compared in the order +z,-z,+y,-y,+x,-x and a probe wins only
+    if it is strictly lower than the running minimum; the result is (centre(best) - pos) * (float)(ori - min)"""
+    cfg = config_cfg_a()
+    o = Oracle(cfg)
+    img = np.zeros((480, 640), dtype=np.uint16)
+    img[240, 320] = 1000
+    pose = scenes.pose_from_xyz_yaw(5.0, 0.0, 1.2, 0.0)
+    o.integrate_depth(img, pose)
+    o.integrate_depth(img, pose)     # hit voxel: lo 4.2 'o'; the ten voxels of the ray in front of it: lo -1.8 'f'
+    m = o.export_map()
+    si, ci = np.argwhere(m["occupancy"] == b"o")[0]
+    c = m["glb"][si] * 1.0 + np.array([ci % 10, (ci // 10) % 10, ci // 100]) * 0.1 + 0.05
+    ori = np.float32(10.0 ** float(np.float32(4.2)) / (1 + 10.0 ** float(np.float32(4.2))))
+    free = np.float32(10.0 ** float(np.float32(-1.8)) / (1 + 10.0 ** float(np.float32(-1.8))))
+    assert o.getOdd([c])[0] == ori and o.getOdd([c - [0.1, 0, 0]])[0] == pytest.approx(float(free), abs=1e-7)
+    # at the occupied cell: +z is unknown (0.5 < ori) and becomes the minimum first, ..., -x (free, 0.0156) wins at the end
+    g = o.getOddGrad([c])[0]
+    assert g[0] == pytest.approx(-0.1 * float(ori - o.getOdd([c - [0.1, 0, 0]])[0]), abs=1e-9) and abs(g[1]) < 1e-12 and abs(g[2]) < 1e-12
+    # two cells above it everything within one step is unknown (0.5) except nothing lower: the search widens; the occupied
+    # cell below has HIGHER odds, so the first strictly lower value is found only where the free ray cells come into reach
+    up = c + [0.0, 0.0, 0.2]
+    assert o.getOdd([up])[0] == 0.5
+    g_up = o.getOddGrad([up], max_iter=1)[0]
+    assert np.all(g_up == 0.0)                        # one step: all six neighbours are unknown, none is lower than 0.5
+    # from a free ray cell, the cell behind it (towards the sensor) is equally free and the occupied one is higher:
+    # no strictly lower neighbour within 5 steps along the axes except none -> zero vector at the second ray cell
+    mid = c - [0.5, 0.0, 0.0]
+    g_mid = o.getOddGrad([mid])[0]
+    assert np.all(g_mid == 0.0)
+    o.close()
