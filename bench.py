@@ -267,7 +267,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the mlmap_b200 hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a stuck collective should fail the run in minutes, not hold the box for NCCL's default ten
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
 
     from mlmapping_b200 import MLMap, config_cfg_a
     import ctypes as C
