@@ -69,6 +69,14 @@ def test_invalid_config_and_no_silent_cpu_fallback(lib):
     # null handles are rejected, not dereferenced
     assert lib.mlm_sync(None) == 1
     assert lib.mlm_destroy(None) == 1
+    n = C.c_size_t()
+    assert lib.mlm_export_cloud(None, 0, None, 0, C.byref(n)) == 1
+    assert lib.mlm_export_odds_slice(None, 0.7, None, 0, C.byref(n)) == 1
+    assert lib.mlm_checkpoint_size(None, C.byref(n)) == 1
+    assert lib.mlm_checkpoint_save(None, None, 0, C.byref(n)) == 1
+    assert lib.mlm_checkpoint_restore(None, None, 0) == 1
+    out7 = (C.c_double * 7)()
+    assert lib.mlm_compensate_pose(None, None, None, None, 0.0, 0.0, 0.0, out7) == 1
 
 
 def test_rand_stream_is_glibc_rand(lib):
