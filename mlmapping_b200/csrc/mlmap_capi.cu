@@ -45,17 +45,21 @@ struct HPose {
   HQuat q;
   double t[3];
 };
-HQuat h_normalized(const HQuat &q) {  // Eigen normalize(): coeffs / sqrt(squaredNorm), storage x,y,z,w
-  double n2 = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+// Evaluation order as Eigen's x86-64 SSE2 build of the reference has it (packets of 2 doubles; CMakeLists.txt:4 sets no
+// -march): squaredNorm of the 4 coefficients x,y,z,w adds the two packets first, the quaternion product is the kernel
+// of Eigen/src/Geometry/arch/Geometry_SSE.h.  Checked bit for bit against oracle/_ref in tests/test_reference_pin.py.
+HQuat h_normalized(const HQuat &q) {  // MatrixBase::normalize(): z = squaredNorm(); if (z > 0) coeffs /= sqrt(z)
+  double n2 = (q.x * q.x + q.z * q.z) + (q.y * q.y + q.w * q.w);
+  if (!(n2 > 0)) return q;
   double n = sqrt(n2);
   return HQuat{q.w / n, q.x / n, q.y / n, q.z / n};
 }
 HQuat h_mul(const HQuat &a, const HQuat &b) {
   HQuat r;
-  r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
-  r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
-  r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
-  r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+  r.x = (a.w * b.x + a.y * b.z) - (a.z * b.y - a.x * b.w);
+  r.y = (a.w * b.y + a.y * b.w) + (a.z * b.x - a.x * b.z);
+  r.z = (a.w * b.z - a.y * b.x) + (a.z * b.w + a.x * b.y);
+  r.w = (a.w * b.w - a.y * b.y) - (a.z * b.z + a.x * b.x);
   return r;
 }
 void h_rotate(const HQuat &q, const double v[3], double out[3]) {  // Eigen _transformVector
@@ -736,7 +740,10 @@ int mlm_compensate_pose(const double odom_pos[3], const double odom_quat_wxyz[4]
   const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
   const double m[3][3] = {{1 - (tyy + tzz), txy - twz, txz + twy}, {txy + twz, 1 - (txx + tzz), tyz - twx}, {txz - twy, tyz + twx, 1 - (txx + tyy)}};
   double rot_dot[3];
-  for (int i = 0; i < 3; i++) rot_dot[i] = m[i][0] * imu_ang_vel[0] + m[i][1] * imu_ang_vel[1] + m[i][2] * imu_ang_vel[2];
+  // Matrix3d * Vector3d as Eigen's coefficient-based product evaluates it: rows 0-1 are one packet accumulated in
+  // order, the odd last row is a scalar dot product reduced as a halving tree
+  for (int i = 0; i < 2; i++) rot_dot[i] = (imu_ang_vel[0] * m[i][0] + imu_ang_vel[1] * m[i][1]) + imu_ang_vel[2] * m[i][2];
+  rot_dot[2] = m[2][0] * imu_ang_vel[0] + (m[2][1] * imu_ang_vel[1] + m[2][2] * imu_ang_vel[2]);
   // rot_cp = rot_og.log() + time_gap * rot_dot
   const double n = sqrt(q.x * q.x + q.y * q.y + q.z * q.z);
   const double w = q.w, squared_w = w * w;

@@ -6,17 +6,20 @@
 // and bench.py's cpu_baseline / --impl reference legs may build, load or call this code; the
 // product (mlmapping_b200/csrc) never links or includes anything from oracle/.
 //
-// PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for any mapping
-// function and cannot be compiled here (Eigen, PCL, OpenCV, ROS, Boost absent),
-// so this restatement is pinned only by (a) first-principles known answers in tests/ and
-// (b) golden dumps of itself under tests/golden/.  It keeps the reference's own containers
-// (std::unordered_map / std::unordered_set with the reference's hashers, same insert/clear
-// sequence) so libstdc++ iteration order is inherited, and is compiled with the reference's
-// flags (-std=c++17 -O3, no -march, no fast-math; reference CMakeLists.txt:4).
+// PINNED AGAINST THE REFERENCE ITSELF: the reference ships no tests, golden vectors or fixtures for any mapping
+// function, but its mapping sources compile unmodified against a small Eigen subset and inert
+// ROS/PCL/OpenCV stand-ins (oracle/ref_build -> oracle/_ref/libmlmap_ref.so).  tests/test_reference_pin.py and the
+// known-answer tests run this restatement and that library on the same seeded inputs and require identical bits
+// (hit map in iteration order, miss set in iteration order, map, queries, clouds, forwarded pose);
+// tests/golden/golden.json is generated from that library.  This restatement keeps the reference's own containers
+// (std::unordered_map / std::unordered_set with the reference's hashers, same insert/clear sequence) so libstdc++
+// iteration order is inherited, and is compiled with the reference's flags (-std=c++17 -O3, no -march, no
+// fast-math; reference CMakeLists.txt:4).
 //
-// Third-party arithmetic restated from published formulas (un-vendored dependency):
-//   Eigen3 (unpinned system package): Quaternion product / normalize / conjugate /
-//   _transformVector (v + w*uv + qv x uv with uv = 2*(qv x v)), fixed-size vector +,-,*.
+// What stays a restatement on BOTH sides is Eigen3 (the reference's un-vendored, unpinned system dependency, absent
+// from this image): Quaternion product / normalize / conjugate / _transformVector and fixed-size vector +,-,* follow
+// Eigen 3.3's evaluation order for an x86-64 SSE2 build (see the notes at quat_mul below and in
+// oracle/ref_build/shim/mini_eigen/mini_eigen.hpp).
 // =================================================================================================
 #ifndef MLMAP_ORACLE_HPP
 #define MLMAP_ORACLE_HPP
@@ -71,16 +74,21 @@ inline Vec3I operator+(const Vec3I &a, const Vec3I &b) { return Vec3I(a[0] + b[0
 struct Quat {
   double w, x, y, z;
 };
-inline Quat quat_mul(const Quat &a, const Quat &b) {  // Eigen generic quaternion product
+// Eigen evaluates these as an x86-64 SSE2 build does (the reference's flags: -O3, no -march; packets of 2 doubles):
+// the quaternion product is the kernel of Eigen/src/Geometry/arch/Geometry_SSE.h, a 4-coefficient squaredNorm
+// adds the two packets first, (x^2 + z^2) + (y^2 + w^2), a 3-coefficient one is (a0^2 + a1^2) + a2^2.
+// oracle/ref_build/shim/mini_eigen/mini_eigen.hpp states the same rules for the build of the reference's own sources.
+inline Quat quat_mul(const Quat &a, const Quat &b) {
   Quat r;
-  r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
-  r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
-  r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
-  r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+  r.x = (a.w * b.x + a.y * b.z) - (a.z * b.y - a.x * b.w);
+  r.y = (a.w * b.y + a.y * b.w) + (a.z * b.x - a.x * b.z);
+  r.z = (a.w * b.z - a.y * b.x) + (a.z * b.w + a.x * b.y);
+  r.w = (a.w * b.w - a.y * b.y) - (a.z * b.z + a.x * b.x);
   return r;
 }
-inline Quat quat_normalized(const Quat &q) {  // coeffs / sqrt(squaredNorm), storage order x,y,z,w
-  double n2 = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+inline Quat quat_normalized(const Quat &q) {  // MatrixBase::normalize(): z = squaredNorm(); if (z > 0) coeffs /= sqrt(z)
+  double n2 = (q.x * q.x + q.z * q.z) + (q.y * q.y + q.w * q.w);
+  if (!(n2 > 0)) return q;
   double n = sqrt(n2);
   return Quat{q.w / n, q.x / n, q.y / n, q.z / n};
 }
@@ -171,7 +179,9 @@ inline Vec3 quat_matrix_times(const Quat &q, const Vec3 &v) {
   const double m00 = 1 - (tyy + tzz), m01 = txy - twz, m02 = txz + twy;
   const double m10 = txy + twz, m11 = 1 - (txx + tzz), m12 = tyz - twx;
   const double m20 = txz - twy, m21 = tyz + twx, m22 = 1 - (txx + tyy);
-  return Vec3(m00 * v[0] + m01 * v[1] + m02 * v[2], m10 * v[0] + m11 * v[1] + m12 * v[2], m20 * v[0] + m21 * v[1] + m22 * v[2]);
+  // coefficient-based product into a column vector: rows 0-1 form one packet and accumulate in order, the odd last
+  // row is a scalar dot product reduced as a halving tree
+  return Vec3((v[0] * m00 + v[1] * m01) + v[2] * m02, (v[0] * m10 + v[1] * m11) + v[2] * m12, m20 * v[0] + (m21 * v[1] + m22 * v[2]));
 }
 // pose forwarded to the image stamp, mlmap::depth_odom_input_callback src/mlmap.cpp:470-498:
 // time_gap = gap_imu - latency; rot_cp = log(R) + time_gap * (R * omega); T_wb = (exp(rot_cp), p + (gap_odom - latency) * v)

@@ -1,6 +1,6 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see mlmap_oracle.hpp header).  C ABI over the CPU
 // restatement so tests/ and bench.py's cpu_baseline leg can drive it through ctypes.
-// PARITY UNPINNED (no reference tests or golden vectors exist).
+// Pinned against oracle/_ref (the reference's own sources, oracle/ref_build) by tests/test_reference_pin.py.
 #include "mlmap_oracle.hpp"
 
 #include <chrono>

@@ -1,7 +1,9 @@
-"""Generates tests/golden/golden.json: digests + counters of the CPU oracle on the seeded inputs of
-SURVEY §8d.  The reference itself cannot run here (no Eigen/PCL/ROS), so these fixtures pin the
-ORACLE (regression guard for the restatement), not the reference: parity stays 'unpinned'.
-Run:  python tests/golden/make_golden.py"""
+"""Generates tests/golden/golden.json: digests + counters on the seeded inputs of SURVEY §8d, produced by
+the REFERENCE ITSELF: the unmodified sources of /root/reference compiled into oracle/_ref/libmlmap_ref.so
+(oracle/ref_build/Makefile; Eigen / ROS / PCL / OpenCV replaced by the stand-ins of oracle/ref_build/shim).
+tests/test_host_logic.py checks the restatement (oracle/mlmap_oracle.hpp) against these digests, so the
+restatement stays pinned to the reference on boxes where /root/reference does not exist.
+Run where the reference exists:  python tests/golden/make_golden.py"""
 import hashlib
 import json
 import sys
@@ -36,7 +38,17 @@ def _summ(o, st, extra=None):
     return out
 
 
-def run_case(name):
+def run_case(name, impl="port"):
+    global Oracle
+    base = Oracle
+    Oracle = lambda cfg: base(cfg, impl=impl)  # noqa: E731
+    try:
+        return _run_case(name)
+    finally:
+        Oracle = base
+
+
+def _run_case(name):
     if name == "cfg_a_config1_single_frame":
         cfg = config_cfg_a()
         pose = scenes.pose_from_xyz_yaw(5.0, 0.0, 1.2, 0.0)
@@ -64,13 +76,52 @@ def run_case(name):
             pose = scenes.lidar_loop_pose(3 * k)
             st = o.integrate_points(scenes.lidar_scan(pose, frame_idx=k, beams=32, azimuths=512), pose)
         return _summ(o, st)
+    if name == "cfg_a_exploration_6_frames_rolled_poses":
+        # exploration mode (update_observation + release pass), poses with roll / pitch, inflation, box fill and the
+        # map clouds: the rows of SURVEY 8a a14-a16 and 8f-1/2 in one case
+        cfg = config_cfg_a()
+        cfg.use_exploration_frontiers = 1
+        cfg.inflate_n, cfg.inflate_global_n = 2, 2
+        o = Oracle(cfg)
+        for k in range(6):
+            pose = scenes.corridor_trajectory_pose(40 * k)
+            a = 0.05 * np.sin(0.7 * k)
+            b = 0.04 * np.cos(0.9 * k)
+            q = _quat_mul(pose[3:7], _quat_mul([np.cos(a / 2), np.sin(a / 2), 0, 0], [np.cos(b / 2), 0, np.sin(b / 2), 0]))
+            pose = np.r_[pose[:3], q]
+            st = o.integrate_depth(scenes.corridor_depth_frame(cfg, pose, rows=240, cols=320, frame_idx=k), pose)
+        o.inflate_map(pose[:3])
+        o.setFree_map_in_bound([pose[0] + 0.5, -0.4, 0.8], [pose[0] + 1.5, 0.4, 1.6])
+        m = o.export_map()
+
+        def rows(a):
+            a = np.ascontiguousarray(a).view(np.uint32).reshape(a.shape[0], -1)
+            return a[np.lexsort(tuple(a[:, c] for c in range(a.shape[1] - 1, -1, -1)))]
+        return _summ(o, st, {"frontier": _d(m["frontier"]), "inflate": _d(m["inflate"]), "collapsed": int(m["collapsed"].sum()),
+                             "cloud_inflated": _d(rows(o.export_cloud(0))), "cloud_occupied": _d(rows(o.export_cloud(1))),
+                             "cloud_frontier": _d(rows(o.export_cloud(2))), "slice_1.25": _d(rows(o.export_odds_slice(1.25)))})
     raise KeyError(name)
 
 
-CASES = ["cfg_a_config1_single_frame", "cfg_a_config2_first_8_frames_stride_25", "cfg_c_small_lidar_3_scans"]
+def _quat_mul(a, b):
+    aw, ax, ay, az = a
+    bw, bx, by, bz = b
+    return np.array([aw * bw - ax * bx - ay * by - az * bz, aw * bx + ax * bw + ay * bz - az * by,
+                     aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw])
+
+
+CASES = ["cfg_a_config1_single_frame", "cfg_a_config2_first_8_frames_stride_25", "cfg_c_small_lidar_3_scans",
+         "cfg_a_exploration_6_frames_rolled_poses"]
 
 if __name__ == "__main__":
-    out = {"generator": "tests/golden/make_golden.py", "note": "pins the oracle restatement, not the reference",
-           "cases": {c: run_case(c) for c in CASES}}
+    from oracle_binding import _REFERENCE
+    if not _REFERENCE.exists():
+        raise SystemExit("the golden vectors are generated from the reference's own sources: /root/reference is needed")
+    out = {"generator": "tests/golden/make_golden.py",
+           "provenance": "outputs of the UNMODIFIED reference sources (/root/reference src/map_awareness.cpp, src/map_local.cpp, "
+                         "src/mlmap.cpp, src/rviz_vis.cpp, include/*.h, 3rdPartLib/Sophus/sophus/{so3,se3}.cpp) built by "
+                         "oracle/ref_build/Makefile into oracle/_ref/libmlmap_ref.so with g++ -std=c++17 -O3 (reference "
+                         "CMakeLists.txt:4) against the Eigen subset / inert ROS-PCL-OpenCV stand-ins of oracle/ref_build/shim",
+           "cases": {c: run_case(c, impl="reference") for c in CASES}}
     (HERE / "golden.json").write_text(json.dumps(out, indent=1))
     print(json.dumps(out, indent=1))

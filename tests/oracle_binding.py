@@ -16,7 +16,10 @@ from mlmapping_b200.capi import FrameStats, MlmConfig  # noqa: E402  (struct lay
 
 _ORACLE_DIR = ROOT / "oracle"
 _LIB = _ORACLE_DIR / "liboracle.so"
+_REF_LIB = _ORACLE_DIR / "_ref" / "libmlmap_ref.so"  # the UNMODIFIED reference sources (oracle/ref_build/Makefile)
+_REFERENCE = Path("/root/reference")
 _lib = None
+_ref_lib = None
 
 
 def build_oracle():
@@ -24,6 +27,32 @@ def build_oracle():
     if res.returncode != 0:
         raise RuntimeError("oracle build failed:\n" + res.stdout + res.stderr)
     return _LIB
+
+
+def build_reference():
+    """compile the reference's own mapping sources into oracle/_ref (only possible where /root/reference exists)"""
+    res = subprocess.run(["make", "-C", str(_ORACLE_DIR / "ref_build"), "-j8"], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("oracle/_ref build failed:\n" + res.stdout[-3000:] + res.stderr[-3000:])
+    return _REF_LIB
+
+
+def reference_available() -> bool:
+    """the prebuilt library travels to the GPU box; the sources do not"""
+    return _REF_LIB.exists() or _REFERENCE.exists()
+
+
+def load_reference():
+    global _ref_lib
+    if _ref_lib is not None:
+        return _ref_lib
+    if _REFERENCE.exists():
+        build_reference()  # make: a no-op when up to date
+    if not _REF_LIB.exists():
+        raise FileNotFoundError(f"{_REF_LIB} missing and /root/reference absent: build it where the reference exists")
+    _ref_lib = _prototypes(C.CDLL(str(_REF_LIB)))
+    _ref_lib.orc_get_odd_at.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    return _ref_lib
 
 
 def load_oracle():
@@ -34,7 +63,11 @@ def load_oracle():
         p.stat().st_mtime > _LIB.stat().st_mtime for p in [_ORACLE_DIR / "mlmap_oracle.hpp", _ORACLE_DIR / "oracle_capi.cpp"])
     if src_newer:
         build_oracle()
-    lib = C.CDLL(str(_LIB))
+    _lib = _prototypes(C.CDLL(str(_LIB)))
+    return _lib
+
+
+def _prototypes(lib):
     vp, sz, dp = C.c_void_p, C.c_size_t, C.POINTER(C.c_double)
     lib.orc_create.argtypes, lib.orc_create.restype = [C.POINTER(MlmConfig)], vp
     lib.orc_destroy.argtypes = [vp]
@@ -75,7 +108,6 @@ def load_oracle():
     lib.orc_T_ls.argtypes = [dp, dp, dp]
     lib.orc_next_bucket_count.argtypes, lib.orc_next_bucket_count.restype = [sz], sz
     lib.orc_compensate_pose.argtypes = [dp, dp, dp, dp, C.c_double, C.c_double, C.c_double, dp]
-    _lib = lib
     return lib
 
 
@@ -88,8 +120,10 @@ class Oracle:
     """CPU restatement of the reference's mlmap (oracle/mlmap_oracle.hpp) with the same surface as
     mlmapping_b200.MLMap so parity tests read symmetrically."""
 
-    def __init__(self, cfg: MlmConfig, bookkeeping: bool = True):
-        self.lib = load_oracle()
+    def __init__(self, cfg: MlmConfig, bookkeeping: bool = True, impl: str = "port"):
+        """impl "port": the restatement (oracle/mlmap_oracle.hpp); "reference": the reference's own sources (oracle/_ref)"""
+        self.impl = impl
+        self.lib = load_reference() if impl == "reference" else load_oracle()
         self.cfg = cfg.copy()
         self.h = C.c_void_p(self.lib.orc_create(C.byref(self.cfg)))
         self.lib.orc_set_bookkeeping(self.h, 1 if bookkeeping else 0)

@@ -1,23 +1,37 @@
-"""CPU: pins for the oracle (oracle/mlmap_oracle.hpp).  The reference has no tests or golden vectors
-(SURVEY §4), so these are first-principles known answers for the reference's formulas, quirks the
-SURVEY derived from the cited lines, and the libstdc++ container model the CUDA path emulates."""
+"""CPU: pins for the oracle.  The reference has no tests or golden vectors, so these are
+first-principles known answers for the reference's formulas, quirks the SURVEY derived from the cited
+lines, and the libstdc++ container model the CUDA path emulates.  Every test runs twice: on the
+restatement (oracle/mlmap_oracle.hpp, "port") and on the reference's OWN sources compiled into
+oracle/_ref ("reference", oracle/ref_build/Makefile)."""
 import math
 
 import numpy as np
 import pytest
 
 from mlmapping_b200 import config_cfg_a, scenes
-from oracle_binding import Oracle, load_oracle
+from oracle_binding import Oracle as _Oracle, load_oracle, load_reference, reference_available
 from order_model import BUCKET_CHAIN, iteration_order, vector_hash
 
 
-@pytest.fixture(scope="module")
-def lib():
-    return load_oracle()
+@pytest.fixture(scope="module", params=["port", "reference"])
+def impl(request):
+    if request.param == "reference" and not reference_available():
+        pytest.skip("oracle/_ref/libmlmap_ref.so not built and /root/reference absent")
+    return request.param
 
 
 @pytest.fixture(scope="module")
-def orc():
+def Oracle(impl):
+    return lambda cfg, **kw: _Oracle(cfg, impl=impl, **kw)
+
+
+@pytest.fixture(scope="module")
+def lib(impl):
+    return load_reference() if impl == "reference" else load_oracle()
+
+
+@pytest.fixture(scope="module")
+def orc(Oracle):
     return Oracle(config_cfg_a())
 
 
@@ -92,7 +106,7 @@ def test_T_ls_prologue(lib):
     assert list(out) == pytest.approx([0.0, 1.12, 0.0], abs=1e-12)
 
 
-def test_single_point_hit_miss_sets():
+def test_single_point_hit_miss_sets(Oracle):
     """one pixel, straight ahead at 1.0 m: hit cell + ray walk follow map_awareness.cpp:135-171,241-275"""
     cfg = config_cfg_a()
     o = Oracle(cfg)
@@ -139,7 +153,7 @@ def test_single_point_hit_miss_sets():
     assert o.export_map()["log_odds"].min() == np.float32(-2.0)
 
 
-def test_out_of_range_ray_is_clamped_not_dropped():
+def test_out_of_range_ray_is_clamped_not_dropped(Oracle):
     """rho beyond n_Rho: no hit, ray cast from rho = n_Rho-1 with the stale rate (map_awareness.cpp:261-265)"""
     cfg = config_cfg_a()
     o = Oracle(cfg)
@@ -150,9 +164,11 @@ def test_out_of_range_ray_is_clamped_not_dropped():
     assert st.n_miss_cells == cfg.am_n_rho - 2   # r = 63..1
 
 
-def test_iteration_order_model_with_rehashes():
+def test_iteration_order_model_with_rehashes(Oracle, impl):
     """the data-parallel ordering scheme (stamp -> sort -> re-sequence per rehash) reproduces
     std::unordered_map's iteration order, including frames that cross several rehashes"""
+    if impl == "reference":
+        pytest.skip("needs the insert log, an instrumentation of the restatement")
     cfg = config_cfg_a()
     o = Oracle(cfg)
     o.set_log_inserts(True)
@@ -168,7 +184,7 @@ def test_iteration_order_model_with_rehashes():
         assert B == st.hit_bucket_count
 
 
-def test_set_free_and_grad():
+def test_set_free_and_grad(Oracle):
     cfg = config_cfg_a()
     o = Oracle(cfg)
     pose = scenes.pose_from_xyz_yaw(5.0, 0.0, 1.2, 0.0)
@@ -186,7 +202,7 @@ def test_set_free_and_grad():
     assert np.all(g == 0.0)   # unknown space everywhere: no lower neighbour -> zero vector (mlmap.h:293)
 
 
-def test_inflate_map_known_answer():
+def test_inflate_map_known_answer(Oracle):
     """one occupied cell in the middle of a subbox -> L1 ball of radius inflate_n in inflate_occupancy
     (src/mlmap.cpp:286-309, include/map_local.h:233-264); cells at or below flate_height do not inflate"""
     cfg = config_cfg_a()
@@ -213,7 +229,7 @@ def test_inflate_map_known_answer():
     assert (o2.export_map()["inflate"] == b"o").sum() == 0
 
 
-def test_exploration_frontier_known_answer():
+def test_exploration_frontier_known_answer(Oracle):
     """one free cell in unknown space inside the exploration bounds: update_observation puts exactly one
     frontier cell on the first 'u' neighbour in the order +z,-z,+y,-y,+x,-x (src/map_local.cpp:7-33,78-83)"""
     cfg = config_cfg_a()
@@ -238,7 +254,7 @@ def test_exploration_frontier_known_answer():
     assert np.unpackbits(o2.export_map()["frontier"]).sum() == 0
 
 
-def test_sampled_projection_uses_libc_rand_stream():
+def test_sampled_projection_uses_libc_rand_stream(Oracle):
     """mlmapping_sample_cnt > 0: v = rand() % rows, u = rand() % cols, up to 2*cnt draws (src/mlmap.cpp:321-326)"""
     import ctypes as C
     cfg = config_cfg_a()
@@ -265,7 +281,7 @@ def test_sampled_projection_uses_libc_rand_stream():
     assert st.n_points < 50
 
 
-def test_map_clouds_follow_subbox_id2xyz_glb():
+def test_map_clouds_follow_subbox_id2xyz_glb(Oracle):
     """map clouds (rviz_vis.cpp:267-327): one float point per selected cell at origin*d_glb + xyz*d_sub + d_sub/2
     (map_local.h:201-206), cell ids x-fastest; the odds slice (mlmap.cpp:200-284) keeps the cells within 1e-3 of the height"""
     cfg = config_cfg_a()
@@ -295,7 +311,7 @@ def test_map_clouds_follow_subbox_id2xyz_glb():
     orc.close()
 
 
-def test_far_hit_spreads_over_neighbours_along_the_ray(lib):
+def test_far_hit_spreads_over_neighbours_along_the_ray(lib, Oracle):
     """update_hits (map_awareness.cpp:135-171): at 5.8 m the depth noise reaches 3*sigma = 0.001125*rho^2 > 3 cells, so one
     point marks the centre cell and, for d = 1..K, the cells (rho+d, round(z + d*rate)) and (rho-d, round(z - d*rate))
     with rate = (z - n_below) / rho, each with the tabulated odds of its offset; a second identical point folds
@@ -353,7 +369,7 @@ def test_far_hit_spreads_over_neighbours_along_the_ray(lib):
     o2.close()
 
 
-def test_inflated_occupancy_query_probes_19_points():
+def test_inflated_occupancy_query_probes_19_points(Oracle):
     """getOccupancy(pos, inflate) (mlmap.h:142-169): OCCUPIED iff the point itself, one of the 6 axis offsets or one of
     the 12 planar diagonals (+-inflate on two axes) is occupied; never UNKNOWN; the 8 space diagonals are not probed"""
     cfg = config_cfg_a()
@@ -381,7 +397,7 @@ def test_inflated_occupancy_query_probes_19_points():
     o.close()
 
 
-def test_odd_gradient_picks_the_strictly_lowest_neighbour():
+def test_odd_gradient_picks_the_strictly_lowest_neighbour(Oracle):
     """getOddGrad (mlmap.h:237-295): the six axis probes are compared in the order +z,-z,+y,-y,+x,-x and a probe wins only
     if it is strictly lower than the running minimum; the result is (centre(best) - pos) * (float)(ori - min)"""
     cfg = config_cfg_a()
