@@ -256,28 +256,45 @@ int mlm_checkpoint_size(mlm_handle h, size_t *bytes);
 int mlm_checkpoint_save(mlm_handle h, void *buf, size_t cap, size_t *written);
 int mlm_checkpoint_restore(mlm_handle h, const void *buf, size_t bytes);
 
-/* ---- one logical map sharded over `world` ranks (large LiDAR scans) -------------------------------
- * Per scan, on every rank with the SAME points and pose:
- *   1. mlm_shard_stage_points_f64   casts the rank's phi columns (phi % world == rank) into its voxel staging
- *   2. mlm_shard_copy_hit_keys      -> all-gather the (key, stamp) lists of all ranks (caller, NCCL)
- *   3. mlm_shard_order              every rank derives the same hit-map iteration order from the gathered list
- *   4. mlm_shard_emit_counts / mlm_shard_emit_pack  24-byte update records grouped by owner rank
- *      (owner = hash of the subbox index % world) -> all-to-all (caller, NCCL)
- *   5. mlm_shard_ingest             the owner stages the received records, allocates its subboxes and fuses
- * Each rank then holds the subboxes it owns; the union over ranks equals the single-GPU map bit for bit. */
-int mlm_shard_stage_points_f64(mlm_handle h, const double *xyz, int n, const double T_wb[7], int rank, int world,
-                               int32_t *n_hit_local, int32_t *n_miss_local);
-int mlm_shard_stage_points_f64_device(mlm_handle h, const double *d_xyz, int n, const double T_wb[7], int rank, int world,
-                                      int32_t *n_hit_local, int32_t *n_miss_local);
-/* frames without a rehash (sum of the ranks' hit counts <= bucket count): min-all-reduce the activation stamps
- * (unsigned compare) instead of steps 2-3, then mlm_shard_order_fast; the stamps travel inside the records */
-int mlm_shard_act_buffer(mlm_handle h, void **d_act, uint32_t *bucket_count);
-int mlm_shard_order_fast(mlm_handle h, int n_total);
-int mlm_shard_copy_hit_keys(mlm_handle h, int32_t *d_keys_out, uint32_t *d_stamps_out);
-int mlm_shard_order(mlm_handle h, const int32_t *d_keys_all, uint32_t *d_stamps_all, int n_total);
-int mlm_shard_emit_counts(mlm_handle h, int world, int32_t *counts);
-int mlm_shard_emit_pack(mlm_handle h, int world, const int32_t *counts, void *d_out);
-int mlm_shard_ingest(mlm_handle h, const void *d_records, int n, mlm_frame_stats *stats);
+/* ---- one logical map sharded over `world` ranks (large LiDAR scans) -------------------------------------
+ * The sharded form of awareness_map_cylindrical::input_pc_pose + local_map_cartesian::input_pc_pose_direct
+ * (reference src/map_awareness.cpp:173-282, src/map_local.cpp:143-207) for scans too large / too frequent for one GPU:
+ * every rank gets the SAME points and pose, casts the phi columns `phi % world == rank`, and owns the subboxes whose
+ * index hashes to it.  Between the two stages the library itself exchanges (a) every rank's distinct hit keys with
+ * their first-insert stamps (all-gather, so that all ranks derive the same unordered_map iteration order) and (b) one
+ * 24-byte update record per touched voxel and hit key, sent to the voxel's owner (all-to-all).  Both exchanges are
+ * plain stores into the destination's exchange arena over NVLink peer memory followed by a system-scope flag; the
+ * owner waits on device.  There is no host synchronisation between mlm_shard_submit_* and mlm_shard_finish and no
+ * collective-library call on the path.  The union of the ranks' subboxes equals the single-GPU map bit for bit.
+ *
+ * Setup (once):  mlm_shard_open on every rank -> exchange the MLM_SHARD_BLOB_BYTES blobs by any means (MPI_Allgather,
+ * torch.distributed.all_gather, a file) -> mlm_shard_connect with all `world` blobs in rank order.  Ranks may be
+ * processes (one GPU each; arenas mapped with CUDA IPC) or handles of one process (peer access / same device).
+ * Per scan:  mlm_shard_submit_points_f64[_device] enqueues the whole scan on the handle's stream and returns;
+ * mlm_shard_finish waits for it, runs the rare rehash path (a scan whose distinct hit keys exceed the emulated bucket
+ * count: each rank re-sequences the gathered list on its own) and returns the counters.  One process driving several
+ * handles must submit on ALL of them before finishing any.  mlm_shard_integrate_points_f64 = submit + finish.
+ * A peer that fails or does not signal within MLM_SHARD_TIMEOUT_MS (default 10000) makes finish return MLM_ERR_CUDA. */
+#define MLM_SHARD_BLOB_BYTES 128
+#define MLM_SHARD_MAX_WORLD 16
+typedef struct mlm_shard_exchange {
+  int32_t world;
+  int32_t n_hit_total;      /* distinct hit keys of the scan over all ranks */
+  int32_t n_hit_local;      /* ... cast by this rank */
+  int32_t records_received; /* update records this rank ingested (all sources) */
+  int32_t records_from_self;
+  int32_t rehash_path;      /* 1: the scan took the rehash path */
+  int64_t wait_ns;          /* time this rank's wait kernel spun for its peers */
+  int64_t arena_bytes;      /* size of this rank's exchange arena */
+} mlm_shard_exchange;
+int mlm_shard_open(mlm_handle h, int rank, int world, void *blob_out /* MLM_SHARD_BLOB_BYTES */);
+int mlm_shard_connect(mlm_handle h, const void *blobs /* world * MLM_SHARD_BLOB_BYTES, rank order */);
+int mlm_shard_submit_points_f64(mlm_handle h, const double *xyz, int n, const double T_wb[7]);
+int mlm_shard_submit_points_f64_device(mlm_handle h, const double *d_xyz, int n, const double T_wb[7]);
+int mlm_shard_finish(mlm_handle h, mlm_frame_stats *stats /* may be NULL */);
+int mlm_shard_integrate_points_f64(mlm_handle h, const double *xyz, int n, const double T_wb[7], mlm_frame_stats *stats);
+int mlm_shard_last_exchange(mlm_handle h, mlm_shard_exchange *out);
+int mlm_shard_close(mlm_handle h); /* unmaps the peers' arenas; call on every rank before any rank is destroyed */
 
 /* ---- replicated map for split query streams: after a frame the updating rank exports the subbox
  * blocks that frame touched (mlm_dirty_count gives their number and the record size), the caller broadcasts the

@@ -97,6 +97,18 @@ class FrameStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+SHARD_BLOB_BYTES = 128  # MLM_SHARD_BLOB_BYTES
+
+
+class ShardExchange(C.Structure):
+    """mirror of mlm_shard_exchange (include/mlmap_b200.h)"""
+    _fields_ = [("world", C.c_int32), ("n_hit_total", C.c_int32), ("n_hit_local", C.c_int32), ("records_received", C.c_int32),
+                ("records_from_self", C.c_int32), ("rehash_path", C.c_int32), ("wait_ns", C.c_int64), ("arena_bytes", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 # every symbol include/mlmap_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "mlm_default_config", "mlm_create", "mlm_destroy", "mlm_last_error", "mlm_abi_version",
@@ -108,8 +120,9 @@ ABI_SYMBOLS = [
     "mlm_copy_to_device", "mlm_copy_to_host", "mlm_flush_l2", "mlm_kernel_launch_count",
     "mlm_last_frame_hits", "mlm_last_frame_misses", "mlm_export_map_count", "mlm_export_map",
     "mlm_debug_log10f", "mlm_set_profiling", "mlm_last_frame_kernel_ms", "mlm_sizeof_config",
-    "mlm_sizeof_frame_stats", "mlm_debug_phase_cycles", "mlm_host_alloc", "mlm_host_free", "mlm_srand", "mlm_debug_rand", "mlm_export_frontier", "mlm_shard_stage_points_f64",
-    "mlm_shard_copy_hit_keys", "mlm_shard_stage_points_f64_device", "mlm_shard_act_buffer", "mlm_shard_order_fast", "mlm_shard_order", "mlm_shard_emit_counts", "mlm_shard_emit_pack", "mlm_shard_ingest", "mlm_dirty_count", "mlm_dirty_export", "mlm_dirty_import",
+    "mlm_sizeof_frame_stats", "mlm_debug_phase_cycles", "mlm_host_alloc", "mlm_host_free", "mlm_srand", "mlm_debug_rand", "mlm_export_frontier", 
+    "mlm_shard_open", "mlm_shard_connect", "mlm_shard_submit_points_f64", "mlm_shard_submit_points_f64_device", "mlm_shard_finish",
+    "mlm_shard_integrate_points_f64", "mlm_shard_last_exchange", "mlm_shard_close", "mlm_dirty_count", "mlm_dirty_export", "mlm_dirty_import",
     "mlm_export_cloud", "mlm_export_cloud_device", "mlm_export_odds_slice",
     "mlm_checkpoint_size", "mlm_checkpoint_save", "mlm_checkpoint_restore", "mlm_compensate_pose",
     "mlm_export_cloud", "mlm_export_cloud_device", "mlm_export_odds_slice",
@@ -190,15 +203,14 @@ def load_library() -> C.CDLL:
         "mlm_checkpoint_save": ([vp, vp, sz, C.POINTER(sz)], C.c_int),
         "mlm_checkpoint_restore": ([vp, vp, sz], C.c_int),
         "mlm_compensate_pose": ([dp, dp, dp, dp, C.c_double, C.c_double, C.c_double, dp], C.c_int),
-        "mlm_shard_stage_points_f64": ([vp, vp, C.c_int, dp, C.c_int, C.c_int, ip, ip], C.c_int),
-        "mlm_shard_copy_hit_keys": ([vp, vp, vp], C.c_int),
-        "mlm_shard_stage_points_f64_device": ([vp, vp, C.c_int, dp, C.c_int, C.c_int, ip, ip], C.c_int),
-        "mlm_shard_act_buffer": ([vp, C.POINTER(vp), C.POINTER(C.c_uint32)], C.c_int),
-        "mlm_shard_order_fast": ([vp, C.c_int], C.c_int),
-        "mlm_shard_order": ([vp, vp, vp, C.c_int], C.c_int),
-        "mlm_shard_emit_counts": ([vp, C.c_int, vp], C.c_int),
-        "mlm_shard_emit_pack": ([vp, C.c_int, vp, vp], C.c_int),
-        "mlm_shard_ingest": ([vp, vp, C.c_int, C.POINTER(FrameStats)], C.c_int),
+        "mlm_shard_open": ([vp, C.c_int, C.c_int, vp], C.c_int),
+        "mlm_shard_connect": ([vp, vp], C.c_int),
+        "mlm_shard_submit_points_f64": ([vp, vp, C.c_int, dp], C.c_int),
+        "mlm_shard_submit_points_f64_device": ([vp, vp, C.c_int, dp], C.c_int),
+        "mlm_shard_finish": ([vp, C.POINTER(FrameStats)], C.c_int),
+        "mlm_shard_integrate_points_f64": ([vp, vp, C.c_int, dp, C.POINTER(FrameStats)], C.c_int),
+        "mlm_shard_last_exchange": ([vp, C.POINTER(ShardExchange)], C.c_int),
+        "mlm_shard_close": ([vp], C.c_int),
         "mlm_dirty_count": ([vp, ip, C.POINTER(sz)], C.c_int),
         "mlm_dirty_export": ([vp, vp, C.c_int32], C.c_int),
         "mlm_dirty_import": ([vp, vp, C.c_int32], C.c_int),
@@ -314,6 +326,7 @@ class MLMap:
         rc = self._lib.mlm_create(C.byref(self.cfg), device, C.byref(self._h))
         if rc != MLM_OK:
             raise MlmError(rc, self._lib.mlm_last_error().decode())
+        self.device = device
         self.has_data = False
         self.map_updated = False
         self.cells = self.cfg.subbox_n ** 3

@@ -1421,6 +1421,7 @@ constexpr int kFuseLocal = 16;
 // look at the neighbours' state between them: kPhase 1 = hits only (LVG left intact), kPhase 2 = misses only.
 template <int kPhase>
 __device__ __forceinline__ void fuse_body(const MapParams &P, DeviceBuffers &D, const FrameParams &F) {
+  if (F.skip_flag && __ldcg(F.skip_flag)) return;  // sharded scan that needs the rehash path: nothing may be consumed yet
   FrameCounters *fc = D.fc[F.parity];
   const uint32_t *act = D.act[F.parity];
   const int n_hit_frame = fc->n_hit;

@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>
@@ -175,12 +176,20 @@ struct mlm_map {
   uint32_t frame_idx = 0;
   int last_parity = 0;
   GlibcRand rng;  // project_depth's rand() stream (sampled mode)
-  // sharded operation (one logical map over several ranks)
-  uint32_t *d_key_stamp = nullptr;   // [cells] global ordering stamp per hit key of the frame
-  int *d_shard_cnt = nullptr;        // [3*64] counts / bases / cursors per destination
+  // sharded operation (one logical map over several ranks, exchange over peer memory)
+  uint32_t *d_key_stamp = nullptr;   // [cells] global ordering stamp per hit key of a rehash scan
+  int *d_shard_cursor = nullptr;     // [kMaxWorld] records written per destination this scan; [kMaxWorld] = skip flag
+  ShardState *d_shard_state = nullptr, *h_shard_state = nullptr;  // device copy / pinned host copy
+  int *d_keys_all = nullptr;         // [sort_cap] gathered keys, contiguous (rehash path)
+  uint32_t *d_stamps_all = nullptr, *d_bucket_all = nullptr;
+  void *shard_arena = nullptr;       // this rank's exchange arena (exported to the peers)
+  size_t shard_arena_bytes = 0;
+  ShardPeers shard_peers;            // every rank's arena as mapped here
+  void *shard_mapped[kMaxWorld] = {};  // cudaIpcOpenMemHandle results to close
+  bool shard_open = false, shard_connected = false, shard_pending = false;
+  uint32_t shard_epoch = 0;
+  unsigned long long shard_timeout_ns = 10ull * 1000 * 1000 * 1000;
   int shard_world = 1, shard_rank = 0;
-  int shard_n_local = 0;
-  bool shard_record_stamps = false;  // ingest takes the stamps from the records (no-rehash frame)
   bool shard_stage_pending = false;
   cudaGraphExec_t graph_exec[3] = {nullptr, nullptr, nullptr};  // by input mode: points, depth image, sampled pixels
   cudaGraph_t graph[3] = {nullptr, nullptr, nullptr};
@@ -502,6 +511,7 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
   F.shard_world = 1;
   F.stage_only = 0;
   F.inline_resolve = 0;
+  F.skip_flag = nullptr;
   F.tbits = 1;
   while ((1ll << F.tbits) < (long long)std::max(N, 2)) F.tbits++;
   F.tile_pts = kProjThreads * 2;  // stand-alone k_project: 512 threads x 2 rounds per warp
@@ -519,13 +529,11 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
     F.stage_only = 1;
     F.order_mode = 1;
     const int pg = grid_for((size_t)std::max(N, 1), kProjThreads * 2);
+    if (F.bucket_count == 1) F.bucket_count = 13;  // the first insert of an empty table allocates 13 buckets before anything is ordered
     k_project<0><<<pg, kProjThreads, project_smem_bytes(P.nCol, kProjThreads), s>>>(P, h->D, F);
     k_column<<<h->col_grid, kColThreads, h->col_smem_bytes, s>>>(P, h->D, F);
     h->launches += 2;
-    CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc[parity], sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    CUDA_TRY(cudaGetLastError());
-    return MLM_OK;
+    return MLM_OK;  // no host sync: the exchange and the owner-side kernels follow on the stream (mlm_shard_submit_*)
   }
   if (P.explore) return run_frame_explore(h, mode, N, stats);
   const bool prof = h->profiling != 0;
@@ -1198,6 +1206,8 @@ int mlm_destroy(mlm_handle h) {
     if (h->fgraph_exec[i]) cudaGraphExecDestroy(h->fgraph_exec[i]);
     if (h->fgraph[i]) cudaGraphDestroy(h->fgraph[i]);
   }
+  mlm_shard_close(h);
+  if (h->h_shard_state) cudaFreeHost(h->h_shard_state);
   for (void *p : h->allocs) cudaFree(p);
   if (h->d_input) cudaFree(h->d_input);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -1900,50 +1910,313 @@ int mlm_checkpoint_restore(mlm_handle h, const void *buf, size_t bytes) {
   return rc;
 }
 
+// ---- one logical map sharded over `world` ranks; the exchanges run over NVLink peer memory (shard_kernels.cuh) ------
 namespace {
-int shard_stage_common(mlm_handle h, const double *d_xyz, int n, const double T_wb[7], int rank, int world,
-                       int32_t *n_hit_local, int32_t *n_miss_local) {
-  h->shard_rank = rank;
-  h->shard_world = world;
+struct ShardBlob {  // what a rank publishes so that its peers can map its exchange arena (fits MLM_SHARD_BLOB_BYTES)
+  uint32_t magic;
+  int32_t rank, world, device;
+  int32_t hit_cap, rec_cap;
+  int64_t pid;
+  uint64_t ptr;  // arena address in the exporting process (used directly by handles of the same process)
+  cudaIpcMemHandle_t ipc;
+};
+static_assert(sizeof(ShardBlob) <= MLM_SHARD_BLOB_BYTES, "blob must fit the ABI constant");
+constexpr uint32_t kShardMagic = 0x4d4c5342u;  // "MLSB"
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+// carve the arena of one rank: flags | mailboxes | cursors | gathered keys | gathered stamps | inboxes
+ShardArena carve_arena(void *base, int world, int hit_cap, int rec_cap, size_t *total) {
+  unsigned char *p = reinterpret_cast<unsigned char *>(base);
+  size_t off = 0;
+  ShardArena a;
+  a.flags = reinterpret_cast<uint32_t *>(p + off);
+  off = align256(off + kMaxWorld * sizeof(uint32_t));
+  a.mbox = reinterpret_cast<int2 *>(p + off);
+  off = align256(off + 2 * kMaxWorld * sizeof(int2));
+  a.cursor = reinterpret_cast<int *>(p + off);
+  off = align256(off + 2 * sizeof(int));
+  a.gather_key = reinterpret_cast<int *>(p + off);
+  off = align256(off + (size_t)2 * world * hit_cap * sizeof(int));
+  a.gather_stamp = reinterpret_cast<uint32_t *>(p + off);
+  off = align256(off + (size_t)2 * world * hit_cap * sizeof(uint32_t));
+  a.inbox = reinterpret_cast<ShardRecord *>(p + off);
+  off = align256(off + (size_t)2 * rec_cap * sizeof(ShardRecord));
+  if (total) *total = off;
+  return a;
+}
+
+int shard_check(mlm_handle h, bool need_connected) {
+  if (!h) return MLM_ERR_INVALID_ARG;
+  if (!h->shard_open || (need_connected && !h->shard_connected)) {
+    g_last_error = "mlm_shard_open / mlm_shard_connect must come first";
+    return MLM_ERR_INVALID_ARG;
+  }
+  return MLM_OK;
+}
+
+// everything of one scan after the input is on the device: stage the rank's columns, push keys and records to the
+// owners, signal, wait for every source, then the owner-side kernels; no host synchronisation
+int shard_enqueue(mlm_handle h, const double *d_xyz, int n, const double T_wb[7]) {
+  cudaStream_t s = h->stream;
+  const ShardPeers &X = h->shard_peers;
+  const uint32_t epoch = ++h->shard_epoch;
+  const int par = (int)(epoch & 1);
+  const int parity_next = (int)(h->frame_idx & 1);
+  // stale activation stamps of earlier scans must not survive: the staging kernels atomicMin into this buffer
+  CUDA_TRY(cudaMemsetAsync(h->D.act[parity_next], 0xff, (size_t)h->act_cap * 4, s));
+  CUDA_TRY(cudaMemsetAsync(h->d_shard_cursor, 0, (kMaxWorld + 1) * sizeof(int), s));
+  // the inbox cursor of the PREVIOUS scan's parity: its records are ingested, and no source can reserve in it again before
+  // it has seen this scan's flag (raised further down this stream)
+  CUDA_TRY(cudaMemsetAsync(X.a[X.rank].cursor + (par ^ 1), 0, sizeof(int), s));
   h->shard_stage_pending = true;
   int rc = run_frame(h, 0, d_xyz, 0, 0, n, T_wb, nullptr);
   h->shard_stage_pending = false;
   if (rc != MLM_OK) return rc;
-  if (h->h_fc->error) return map_device_error(h->h_fc->error);
-  h->shard_n_local = h->h_fc->n_hit;
-  if (n_hit_local) *n_hit_local = h->h_fc->n_hit;
-  if (n_miss_local) *n_miss_local = h->h_fc->n_miss;
+  FrameParams F = *h->h_fp;  // as the staging kernels saw it (bucket_count already lifted from 1 to 13)
+  int *skip = h->d_shard_cursor + kMaxWorld;
+  const int G = h->sm_count * 2;
+  k_shard_push_hits<<<G, 256, 0, s>>>(X, h->D, F, par);
+  k_shard_emit<<<G * 2, 256, 0, s>>>(X, h->P, h->D, F, par, h->d_shard_cursor);
+  k_shard_signal<<<1, 32, 0, s>>>(X, h->D, F, par, h->d_shard_cursor, epoch);
+  k_shard_wait<<<1, 32, 0, s>>>(X, h->D, F, par, epoch, h->d_shard_state, skip, h->shard_timeout_ns);
+  // owner side (all of it returns at once when the wait kernel found a rehash scan or an error)
+  F.stage_only = 0;
+  F.order_mode = 1;  // stamps are complete: first-insert stamps travel in the records, activations come from the gathered keys
+  F.shard_world = 1;
+  F.skip_flag = skip;
+  k_shard_act<<<G, 256, 0, s>>>(X, h->P, par, h->d_shard_state, skip, h->D.act[F.parity], F.bucket_count);
+  k_shard_ingest<<<G * 2, 256, 0, s>>>(X, h->P, h->D, F, par, h->d_shard_state, skip, nullptr);
+  k_shard_resolve<<<1, 1024, 0, s>>>(h->P, h->D, F);
+  k_fuse<0><<<h->sm_count * 4, 256, 0, s>>>(h->P, h->D, F);
+  h->launches += 8;
+  CUDA_TRY(cudaMemcpyAsync(h->h_shard_state, h->d_shard_state, sizeof(ShardState), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc[F.parity], sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaGetLastError());
+  h->shard_pending = true;
   return MLM_OK;
 }
-int shard_prepare(mlm_handle h) {
-  if (!h->d_key_stamp) {
-    const size_t cells = (size_t)h->P.nZ * h->P.nPhi * h->P.nRho;
-    CUDA_TRY(cudaMalloc((void **)&h->d_key_stamp, cells * sizeof(uint32_t)));
-    CUDA_TRY(cudaMalloc((void **)&h->d_shard_cnt, 3 * 64 * sizeof(int)));
-    h->allocs.push_back(h->d_key_stamp);
-    h->allocs.push_back(h->d_shard_cnt);
+
+// a scan whose distinct hit keys (over all ranks) exceed the emulated bucket count: libstdc++ would rehash mid-frame.
+// Every rank holds the full gathered (key, stamp) list, so each re-sequences it on its own (same result everywhere),
+// then ingests its records with the virtual positions and fuses.  Host-driven like order_slow_path; only the first
+// scans of a map take this path (the bucket array keeps its size across clear()).
+int shard_rehash_path(mlm_handle h, const ShardState &st, uint32_t *B_out) {
+  cudaStream_t s = h->stream;
+  const ShardPeers &X = h->shard_peers;
+  const int par = (int)(h->shard_epoch & 1);
+  const int n_total = st.n_total;
+  if (n_total > h->sort_cap) {
+    g_last_error = "hit count exceeds ordering scratch";
+    return MLM_ERR_CAPACITY;
   }
+  const ShardArena &A = X.a[X.rank];
+  int off = 0;
+  for (int r = 0; r < X.world; r++) {
+    const size_t region = ((size_t)par * X.world + r) * X.hit_cap;
+    if (st.cnt_hits[r] > 0) {
+      CUDA_TRY(cudaMemcpyAsync(h->d_keys_all + off, A.gather_key + region, (size_t)st.cnt_hits[r] * 4, cudaMemcpyDeviceToDevice, s));
+      CUDA_TRY(cudaMemcpyAsync(h->d_stamps_all + off, A.gather_stamp + region, (size_t)st.cnt_hits[r] * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    off += st.cnt_hits[r];
+  }
+  const int T = 256;
+  FrameParams F = *h->h_fp;
+  uint32_t *act = h->D.act[F.parity];
+  OrderArrays O;
+  O.key = h->d_keys_all;
+  O.stamp = h->d_stamps_all;
+  O.bucket = h->d_bucket_all;
+  O.kind = 0;
+  int n_pad = next_pow2(n_total);
+  k_order_seed<<<grid_for(n_pad, T), T, 0, s>>>(O, h->d_sort_a, n_total, n_pad);
+  device_sort(h, h->d_sort_a, n_pad);
+  k_order_take_seq<<<grid_for(n_total, T), T, 0, s>>>(h->d_sort_a, h->d_seq_a, n_total);
+  uint32_t Bs = h->bucket_count;
+  while ((uint32_t)n_total > Bs) {
+    int m = (int)std::min<uint32_t>(Bs, (uint32_t)n_total);
+    if (m > 1) {
+      int m_pad = next_pow2(m);
+      k_fill_u32<<<grid_for(Bs, T), T, 0, s>>>(act, 0xffffffffu, (int)Bs);
+      k_stage_act<<<grid_for(m, T), T, 0, s>>>(h->P, O, act, h->d_seq_a, m, Bs);
+      k_stage_keys<<<grid_for(m_pad, T), T, 0, s>>>(h->P, O, act, h->d_seq_a, h->d_sort_b, m, m_pad, Bs);
+      device_sort(h, h->d_sort_b, m_pad);
+      k_stage_apply<<<grid_for(m, T), T, 0, s>>>(h->d_sort_b, h->d_seq_a, h->d_seq_b, m);
+      k_copy_i32<<<grid_for(m, T), T, 0, s>>>(h->d_seq_a, h->d_seq_b, m);
+    }
+    uint32_t nb = chain_next(Bs);
+    if (nb == 0 || nb > h->act_cap) {
+      g_last_error = "bucket chain of the emulated container exceeded";
+      return MLM_ERR_CAPACITY;
+    }
+    Bs = nb;
+  }
+  k_fill_u32<<<grid_for(Bs, T), T, 0, s>>>(act, 0xffffffffu, (int)Bs);
+  k_order_final<<<grid_for(n_total, T), T, 0, s>>>(h->P, O, act, h->d_seq_a, n_total, Bs);
+  k_shard_scatter_stamps<<<grid_for(n_total, T), T, 0, s>>>(h->d_keys_all, h->d_stamps_all, n_total, h->d_key_stamp);
+  F.stage_only = 0;
+  F.order_mode = 1;
+  F.shard_world = 1;
+  F.skip_flag = nullptr;
+  F.bucket_count = Bs;
+  const int G = h->sm_count * 2;
+  k_shard_ingest<<<G * 2, 256, 0, s>>>(X, h->P, h->D, F, par, h->d_shard_state, nullptr, h->d_key_stamp);
+  k_shard_resolve<<<1, 1024, 0, s>>>(h->P, h->D, F);
+  k_fuse<0><<<h->sm_count * 4, 256, 0, s>>>(h->P, h->D, F);
+  h->launches += 8;
+  CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc[F.parity], sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  *B_out = Bs;
   return MLM_OK;
 }
 }  // namespace
 
-int mlm_shard_stage_points_f64_device(mlm_handle h, const double *d_xyz, int n, const double T_wb[7], int rank, int world,
-                                      int32_t *n_hit_local, int32_t *n_miss_local) {
-  if (!h || (!d_xyz && n > 0) || !T_wb || n < 0 || world < 1 || world > 64 || rank < 0 || rank >= world) return MLM_ERR_INVALID_ARG;
-  if (h->P.explore || n > h->P.max_points) return n > h->P.max_points ? MLM_ERR_CAPACITY : MLM_ERR_UNSUPPORTED;
+int mlm_shard_open(mlm_handle h, int rank, int world, void *blob_out) {
+  if (!h || !blob_out || world < 1 || world > kMaxWorld || rank < 0 || rank >= world) return MLM_ERR_INVALID_ARG;
+  if (h->P.explore) return MLM_ERR_UNSUPPORTED;
+  if (h->shard_open) {
+    g_last_error = "handle is already part of a sharded map";
+    return MLM_ERR_INVALID_ARG;
+  }
   CUDA_TRY(cudaSetDevice(h->device));
-  int rc = shard_prepare(h);
-  if (rc != MLM_OK) return rc;
-  return shard_stage_common(h, d_xyz, n, T_wb, rank, world, n_hit_local, n_miss_local);
+  const MapParams &P = h->P;
+  const int hit_cap = P.max_hits;
+  // records an owner can receive in a scan: one per hit key plus one per voxel with misses; a ray frees at most n_Rho
+  // cells and the voxels lie inside the frame-local grid.  MLM_SHARD_REC_CAP overrides (overflow -> MLM_ERR_CAPACITY)
+  const long long lvg_cells = (long long)P.lvg_dim_xy * P.lvg_dim_xy * P.lvg_dim_z;
+  long long rc_ll = std::min<long long>(lvg_cells, (long long)P.max_points * P.nRho) + P.max_hits;
+  if (const char *e = getenv("MLM_SHARD_REC_CAP")) rc_ll = std::max(1ll, atoll(e));
+  const int rec_cap = (int)std::min<long long>(rc_ll, (1ll << 30));
+  size_t bytes = 0;
+  carve_arena(nullptr, world, hit_cap, rec_cap, &bytes);
+  CUDA_TRY(cudaMalloc(&h->shard_arena, bytes));
+  h->allocs.push_back(h->shard_arena);
+  h->shard_arena_bytes = bytes;
+  CUDA_TRY(cudaMemset(h->shard_arena, 0, align256(kMaxWorld * 4) + align256(2 * kMaxWorld * sizeof(int2)) + align256(8)));
+  if (!h->d_key_stamp) {
+    const size_t cells = (size_t)P.nZ * P.nPhi * P.nRho;
+    CUDA_TRY(cudaMalloc((void **)&h->d_key_stamp, cells * sizeof(uint32_t)));
+    h->allocs.push_back(h->d_key_stamp);
+    CUDA_TRY(cudaMalloc((void **)&h->d_shard_cursor, (kMaxWorld + 1) * sizeof(int)));
+    h->allocs.push_back(h->d_shard_cursor);
+    CUDA_TRY(cudaMalloc((void **)&h->d_shard_state, sizeof(ShardState)));
+    h->allocs.push_back(h->d_shard_state);
+    CUDA_TRY(cudaMemset(h->d_shard_state, 0, sizeof(ShardState)));
+    CUDA_TRY(cudaMallocHost((void **)&h->h_shard_state, sizeof(ShardState)));
+    memset(h->h_shard_state, 0, sizeof(ShardState));
+    CUDA_TRY(cudaMalloc((void **)&h->d_keys_all, (size_t)std::max(h->sort_cap, 1) * 4));
+    h->allocs.push_back(h->d_keys_all);
+    CUDA_TRY(cudaMalloc((void **)&h->d_stamps_all, (size_t)std::max(h->sort_cap, 1) * 4));
+    h->allocs.push_back(h->d_stamps_all);
+    CUDA_TRY(cudaMalloc((void **)&h->d_bucket_all, (size_t)std::max(h->sort_cap, 1) * 4));
+    h->allocs.push_back(h->d_bucket_all);
+  }
+  if (const char *e = getenv("MLM_SHARD_TIMEOUT_MS")) h->shard_timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
+  memset(&h->shard_peers, 0, sizeof(h->shard_peers));
+  h->shard_peers.rank = rank;
+  h->shard_peers.world = world;
+  h->shard_peers.hit_cap = hit_cap;
+  h->shard_peers.rec_cap = rec_cap;
+  h->shard_peers.a[rank] = carve_arena(h->shard_arena, world, hit_cap, rec_cap, nullptr);
+  h->shard_rank = rank;
+  h->shard_world = world;
+  h->shard_epoch = 0;
+  ShardBlob b;
+  memset(&b, 0, sizeof(b));
+  b.magic = kShardMagic;
+  b.rank = rank;
+  b.world = world;
+  b.device = h->device;
+  b.hit_cap = hit_cap;
+  b.rec_cap = rec_cap;
+  b.pid = (int64_t)getpid();
+  b.ptr = (uint64_t)(uintptr_t)h->shard_arena;
+  if (world > 1) CUDA_TRY(cudaIpcGetMemHandle(&b.ipc, h->shard_arena));
+  memset(blob_out, 0, MLM_SHARD_BLOB_BYTES);
+  memcpy(blob_out, &b, sizeof(b));
+  h->shard_open = true;
+  h->shard_connected = world == 1;
+  return MLM_OK;
 }
 
-int mlm_shard_stage_points_f64(mlm_handle h, const double *xyz, int n, const double T_wb[7], int rank, int world,
-                               int32_t *n_hit_local, int32_t *n_miss_local) {
-  if (!h || (!xyz && n > 0) || !T_wb || n < 0 || world < 1 || world > 64 || rank < 0 || rank >= world) return MLM_ERR_INVALID_ARG;
-  if (h->P.explore || n > h->P.max_points) return n > h->P.max_points ? MLM_ERR_CAPACITY : MLM_ERR_UNSUPPORTED;
-  CUDA_TRY(cudaSetDevice(h->device));
-  int rc = shard_prepare(h);
+int mlm_shard_connect(mlm_handle h, const void *blobs) {
+  int rc = shard_check(h, false);
   if (rc != MLM_OK) return rc;
+  if (!blobs) return MLM_ERR_INVALID_ARG;
+  if (h->shard_connected) return MLM_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  ShardPeers &X = h->shard_peers;
+  for (int r = 0; r < X.world; r++) {
+    ShardBlob b;
+    memcpy(&b, reinterpret_cast<const unsigned char *>(blobs) + (size_t)r * MLM_SHARD_BLOB_BYTES, sizeof(b));
+    if (b.magic != kShardMagic || b.rank != r || b.world != X.world || b.hit_cap != X.hit_cap || b.rec_cap != X.rec_cap) {
+      g_last_error = "shard blob " + std::to_string(r) + " does not describe a rank of this sharded map (same configuration on every rank?)";
+      return MLM_ERR_INVALID_ARG;
+    }
+    if (r == X.rank) continue;
+    void *base = nullptr;
+    if (b.pid == (int64_t)getpid()) {
+      // a handle of this process (several GPUs driven by one process, or several ranks on one GPU in the tests)
+      base = reinterpret_cast<void *>((uintptr_t)b.ptr);
+      if (b.device != h->device) {
+        int can = 0;
+        CUDA_TRY(cudaDeviceCanAccessPeer(&can, h->device, b.device));
+        if (!can) {
+          g_last_error = "no peer access between devices " + std::to_string(h->device) + " and " + std::to_string(b.device);
+          return MLM_ERR_UNSUPPORTED;
+        }
+        cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_TRY(e);
+        cudaGetLastError();
+      }
+    } else {
+      CUDA_TRY(cudaIpcOpenMemHandle(&base, b.ipc, cudaIpcMemLazyEnablePeerAccess));
+      h->shard_mapped[r] = base;
+    }
+    X.a[r] = carve_arena(base, X.world, X.hit_cap, X.rec_cap, nullptr);
+  }
+  h->shard_connected = true;
+  return MLM_OK;
+}
+
+int mlm_shard_close(mlm_handle h) {
+  if (!h) return MLM_ERR_INVALID_ARG;
+  if (!h->shard_open) return MLM_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (int r = 0; r < kMaxWorld; r++)
+    if (h->shard_mapped[r]) {
+      cudaIpcCloseMemHandle(h->shard_mapped[r]);
+      h->shard_mapped[r] = nullptr;
+    }
+  cudaGetLastError();
+  h->shard_connected = false;  // the arena itself is released by mlm_destroy (peers must have closed by then)
+  return MLM_OK;
+}
+
+int mlm_shard_submit_points_f64_device(mlm_handle h, const double *d_xyz, int n, const double T_wb[7]) {
+  int rc = shard_check(h, true);
+  if (rc != MLM_OK) return rc;
+  if ((!d_xyz && n > 0) || !T_wb || n < 0) return MLM_ERR_INVALID_ARG;
+  if (n > h->P.max_points) return MLM_ERR_CAPACITY;
+  if (h->shard_pending) {
+    g_last_error = "mlm_shard_finish of the previous scan is missing";
+    return MLM_ERR_INVALID_ARG;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  return shard_enqueue(h, d_xyz, n, T_wb);
+}
+
+int mlm_shard_submit_points_f64(mlm_handle h, const double *xyz, int n, const double T_wb[7]) {
+  int rc = shard_check(h, true);
+  if (rc != MLM_OK) return rc;
+  if ((!xyz && n > 0) || !T_wb || n < 0) return MLM_ERR_INVALID_ARG;
+  if (n > h->P.max_points) return MLM_ERR_CAPACITY;
+  if (h->shard_pending) {
+    g_last_error = "mlm_shard_finish of the previous scan is missing";
+    return MLM_ERR_INVALID_ARG;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
   const size_t bytes = (size_t)std::max(n, 1) * 24;
   rc = ensure_input(h, bytes, (size_t)h->P.max_points * 24);
   if (rc != MLM_OK) return rc;
@@ -1958,147 +2231,64 @@ int mlm_shard_stage_points_f64(mlm_handle h, const double *xyz, int n, const dou
     }
     CUDA_TRY(cudaMemcpyAsync(h->d_input, src, (size_t)n * 24, cudaMemcpyHostToDevice, h->stream));
   }
-  return shard_stage_common(h, reinterpret_cast<const double *>(h->d_input), n, T_wb, rank, world, n_hit_local, n_miss_local);
+  return shard_enqueue(h, reinterpret_cast<const double *>(h->d_input), n, T_wb);
 }
 
-// copies the rank's distinct hit keys and first-insert stamps (n_hit_local each) into caller device buffers
-int mlm_shard_copy_hit_keys(mlm_handle h, int32_t *d_keys_out, uint32_t *d_stamps_out) {
-  if (!h || !d_keys_out || !d_stamps_out) return MLM_ERR_INVALID_ARG;
-  const size_t n = (size_t)h->shard_n_local;
-  if (n) {
-    CUDA_TRY(cudaMemcpyAsync(d_keys_out, h->D.hit_key, n * 4, cudaMemcpyDeviceToDevice, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_stamps_out, h->D.hit_t, n * 4, cudaMemcpyDeviceToDevice, h->stream));
+int mlm_shard_finish(mlm_handle h, mlm_frame_stats *stats) {
+  int rc = shard_check(h, true);
+  if (rc != MLM_OK) return rc;
+  if (!h->shard_pending) {
+    g_last_error = "no submitted scan";
+    return MLM_ERR_INVALID_ARG;
   }
+  CUDA_TRY(cudaSetDevice(h->device));
+  h->shard_pending = false;
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  return MLM_OK;
-}
-
-// global iteration order of the frame from the hit keys of ALL ranks (identical call on every rank)
-int mlm_shard_order(mlm_handle h, const int32_t *d_keys_all, uint32_t *d_stamps_all, int n_total) {
-  if (!h || n_total < 0 || (n_total && (!d_keys_all || !d_stamps_all))) return MLM_ERR_INVALID_ARG;
-  if (n_total > h->sort_cap) return MLM_ERR_CAPACITY;
-  cudaStream_t s = h->stream;
-  const int T = 256;
-  uint32_t *act = h->D.act[h->last_parity];
+  CUDA_TRY(cudaGetLastError());
+  const ShardState st = *h->h_shard_state;
+  if (st.error) {
+    g_last_error = st.error == kErrPeer ? "sharded scan: a peer rank failed or did not signal within the timeout"
+                                        : "device raised error code " + std::to_string(st.error);
+    return st.error == kErrPeer ? MLM_ERR_CUDA : map_device_error(st.error);
+  }
   uint32_t B = h->bucket_count;
-  if (n_total > 0 && B == 1) B = 13;  // the first insert of an empty table allocates 13 buckets before anything is ordered
-  if ((uint32_t)n_total > B) {
-    // rehash frame: staged re-sequencing on the gathered list (stamps become virtual positions)
-    uint32_t *d_bucket = nullptr;
-    CUDA_TRY(cudaMallocAsync((void **)&d_bucket, (size_t)n_total * 4, s));
-    OrderArrays O;
-    O.key = d_keys_all;
-    O.stamp = d_stamps_all;
-    O.bucket = d_bucket;
-    O.kind = 0;
-    // same driver as order_slow_path, on caller arrays
-    int n_pad = next_pow2(n_total);
-    k_order_seed<<<grid_for(n_pad, T), T, 0, s>>>(O, h->d_sort_a, n_total, n_pad);
-    device_sort(h, h->d_sort_a, n_pad);
-    k_order_take_seq<<<grid_for(n_total, T), T, 0, s>>>(h->d_sort_a, h->d_seq_a, n_total);
-    uint32_t Bs = h->bucket_count;
-    while ((uint32_t)n_total > Bs) {
-      int m = (int)std::min<uint32_t>(Bs, (uint32_t)n_total);
-      if (m > 1) {
-        int m_pad = next_pow2(m);
-        k_fill_u32<<<grid_for(Bs, T), T, 0, s>>>(act, 0xffffffffu, (int)Bs);
-        k_stage_act<<<grid_for(m, T), T, 0, s>>>(h->P, O, act, h->d_seq_a, m, Bs);
-        k_stage_keys<<<grid_for(m_pad, T), T, 0, s>>>(h->P, O, act, h->d_seq_a, h->d_sort_b, m, m_pad, Bs);
-        device_sort(h, h->d_sort_b, m_pad);
-        k_stage_apply<<<grid_for(m, T), T, 0, s>>>(h->d_sort_b, h->d_seq_a, h->d_seq_b, m);
-        k_copy_i32<<<grid_for(m, T), T, 0, s>>>(h->d_seq_a, h->d_seq_b, m);
-      }
-      uint32_t nb = chain_next(Bs);
-      if (nb == 0 || nb > h->act_cap) return MLM_ERR_CAPACITY;
-      Bs = nb;
-    }
-    k_fill_u32<<<grid_for(Bs, T), T, 0, s>>>(act, 0xffffffffu, (int)Bs);
-    k_order_final<<<grid_for(n_total, T), T, 0, s>>>(h->P, O, act, h->d_seq_a, n_total, Bs);
-    CUDA_TRY(cudaFreeAsync(d_bucket, s));
-    B = Bs;
-  } else if (n_total > 0) {
-    k_fill_u32<<<grid_for(B, T), T, 0, s>>>(act, 0xffffffffu, (int)B);
-    k_shard_act<<<grid_for(n_total, T), T, 0, s>>>(h->P, d_keys_all, d_stamps_all, n_total, act, B);
+  if (st.n_total > 0 && B == 1) B = 13;
+  int slow = 0;
+  if (st.rehash) {
+    slow = 1;
+    h->bucket_count = B;
+    rc = shard_rehash_path(h, st, &B);
+    if (rc != MLM_OK) return rc;
   }
-  if (n_total > 0) k_shard_scatter_stamps<<<grid_for(n_total, T), T, 0, s>>>(d_keys_all, d_stamps_all, n_total, h->d_key_stamp);
-  CUDA_TRY(cudaStreamSynchronize(s));
-  CUDA_TRY(cudaGetLastError());
-  h->bucket_count = B;
+  rc = finish_frame(h, slow, B, stats);
+  h->bucket_count = B;  // finish_frame grows it from the LOCAL record count; the gathered count decides
   h->last_order_B = B;
-  h->h_fp->bucket_count = B;
-  h->shard_record_stamps = false;
-  return MLM_OK;
-}
-
-// No-rehash frames need no key gather: every key is cast by exactly one rank, so its stamp travels in its
-// record and only the bucket activation stamps must be combined: the caller min-all-reduces the array returned
-// here (B uint32 words; compare as unsigned) and then calls mlm_shard_order_fast.
-int mlm_shard_act_buffer(mlm_handle h, void **d_act, uint32_t *bucket_count) {
-  if (!h || !d_act || !bucket_count) return MLM_ERR_INVALID_ARG;
-  *d_act = h->D.act[h->last_parity];
-  *bucket_count = h->bucket_count;
-  return MLM_OK;
-}
-int mlm_shard_order_fast(mlm_handle h, int n_total) {
-  if (!h || n_total < 0 || h->bucket_count <= 1 || (uint32_t)n_total > h->bucket_count) return MLM_ERR_INVALID_ARG;
-  h->shard_record_stamps = true;
-  h->last_order_B = h->bucket_count;
-  h->h_fp->bucket_count = h->bucket_count;
-  return MLM_OK;
-}
-
-int mlm_shard_emit_counts(mlm_handle h, int world, int32_t *counts) {
-  if (!h || !counts || world != h->shard_world) return MLM_ERR_INVALID_ARG;
-  cudaStream_t s = h->stream;
-  CUDA_TRY(cudaMemsetAsync(h->d_shard_cnt, 0, 3 * 64 * sizeof(int), s));
-  const int n = std::min(h->h_fc->n_touched, h->P.max_touched);
-  if (n > 0) k_shard_emit<0><<<grid_for(n, 256), 256, 0, s>>>(h->P, h->D, *h->h_fp, world, h->d_shard_cnt, nullptr, nullptr, nullptr);
-  CUDA_TRY(cudaMemcpyAsync(counts, h->d_shard_cnt, world * sizeof(int), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
-  CUDA_TRY(cudaGetLastError());
-  return MLM_OK;
-}
-
-// d_out: sum(counts) records of 24 bytes, grouped by destination rank in rank order
-int mlm_shard_emit_pack(mlm_handle h, int world, const int32_t *counts, void *d_out) {
-  if (!h || !counts || world != h->shard_world) return MLM_ERR_INVALID_ARG;
-  cudaStream_t s = h->stream;
-  int base[64], acc = 0;
-  for (int d = 0; d < world; d++) {
-    base[d] = acc;
-    acc += counts[d];
+  if (stats) {
+    stats->n_hit_cells = st.n_total;  // distinct hit keys of the whole scan (identical on every rank)
+    stats->hit_bucket_count = (int32_t)B;
   }
-  CUDA_TRY(cudaMemcpyAsync(h->d_shard_cnt + 64, base, world * sizeof(int), cudaMemcpyHostToDevice, s));
-  const int n = std::min(h->h_fc->n_touched, h->P.max_touched);
-  if (n > 0)
-    k_shard_emit<1><<<grid_for(n, 256), 256, 0, s>>>(h->P, h->D, *h->h_fp, world, h->d_shard_cnt, h->d_shard_cnt + 64,
-                                                     h->d_shard_cnt + 128, reinterpret_cast<ShardRecord *>(d_out));
-  k_shard_reset_counters<<<1, 1, 0, s>>>(h->D, *h->h_fp);
-  CUDA_TRY(cudaStreamSynchronize(s));
-  CUDA_TRY(cudaGetLastError());
-  return MLM_OK;
+  return rc;
 }
 
-// owner side: received records -> voxel staging -> subbox resolve/allocate -> clamped log-odds fusion
-int mlm_shard_ingest(mlm_handle h, const void *d_records, int n, mlm_frame_stats *stats) {
-  if (!h || n < 0 || (n && !d_records)) return MLM_ERR_INVALID_ARG;
-  cudaStream_t s = h->stream;
-  FrameParams F = *h->h_fp;
-  F.stage_only = 0;
-  F.order_mode = 1;
-  F.shard_world = 1;
-  if (n > 0)
-    k_shard_ingest<<<grid_for(n, 256), 256, 0, s>>>(h->P, h->D, F, reinterpret_cast<const ShardRecord *>(d_records), n,
-                                                    h->shard_record_stamps ? nullptr : h->d_key_stamp);
-  k_shard_resolve<<<1, 1024, 0, s>>>(h->P, h->D, F);
-  k_fuse<0><<<h->sm_count * 4, 256, 0, s>>>(h->P, h->D, F);
-  h->launches += 3;
-  CUDA_TRY(cudaStreamSynchronize(s));
-  CUDA_TRY(cudaGetLastError());
-  const uint32_t B = h->bucket_count;
-  int rc = finish_frame(h, 0, B, stats);
-  h->bucket_count = B;  // finish_frame grows it from the LOCAL hit count; the global count already set it
-  return rc;
+int mlm_shard_integrate_points_f64(mlm_handle h, const double *xyz, int n, const double T_wb[7], mlm_frame_stats *stats) {
+  int rc = mlm_shard_submit_points_f64(h, xyz, n, T_wb);
+  if (rc != MLM_OK) return rc;
+  return mlm_shard_finish(h, stats);
+}
+
+int mlm_shard_last_exchange(mlm_handle h, mlm_shard_exchange *out) {
+  if (!h || !out || !h->h_shard_state) return MLM_ERR_INVALID_ARG;
+  const ShardState &st = *h->h_shard_state;
+  memset(out, 0, sizeof(*out));
+  out->n_hit_total = st.n_total;
+  out->n_hit_local = st.cnt_hits[h->shard_rank];
+  out->records_received = st.n_rec_total;
+  out->records_from_self = st.cnt_recs[h->shard_rank];
+  out->rehash_path = st.rehash;
+  out->wait_ns = (int64_t)st.wait_ns;
+  out->world = h->shard_world;
+  out->arena_bytes = (int64_t)h->shard_arena_bytes;
+  return MLM_OK;
 }
 
 // ---- replicated map: ship the subbox blocks touched by the last frame --------------------------------------

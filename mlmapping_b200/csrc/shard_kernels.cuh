@@ -1,11 +1,16 @@
 // One logical map sharded over several GPUs ("large LiDAR scans"): stage 1 by phi column
 // (rank r casts the columns phi % world == r: hit folds and miss bitmaps of different columns are
 // disjoint), stage 2 by subbox owner (hash(glb) % world).  Between the stages the ranks exchange
-//   * the distinct hit keys with their first-insert stamps (all-gather) so that every rank derives the same
+//   * the distinct hit keys with their first-insert stamps (an all-gather) so that every rank derives the same
 //     libstdc++ iteration order for the whole frame, and
-//   * fixed-size update records per touched voxel (all-to-all), consumed by the owner's k_fuse.
-// The collectives themselves are issued by the host side (torch.distributed / NCCL) on the device buffers
-// these kernels fill; with world == 1 the same code path runs on one GPU.
+//   * fixed-size update records per touched voxel (an all-to-all), consumed by the owner's k_fuse.
+// Both exchanges are done BY THESE KERNELS over NVLink peer memory: every rank owns an exchange arena
+// (cudaMalloc, exported with cudaIpcGetMemHandle and mapped by its peers); a source writes its keys and records
+// straight into the region reserved for it in the destination's arena, then publishes its counts and raises an
+// epoch flag with a system-scope release; the destination's wait kernel acquires all flags before the owner-side
+// kernels run.  No host round trip, no library collective and no remote atomic on the data path; the arenas are
+// double-buffered by scan parity (a source can be at most one scan ahead of a destination, because its own wait
+// needs the destination's flag of the scan before).  With world == 1 the same kernels run on one GPU.
 #pragma once
 #include "frame_kernels.cuh"
 #include "order_kernels.cuh"
@@ -19,6 +24,33 @@ struct __align__(8) ShardRecord {  // 24 bytes
   int count;    // miss: number of miss cells mapping to the voxel; hit: first-insert stamp of the key
 };
 
+constexpr int kMaxWorld = 16;
+// one rank's exchange arena as seen from this rank (peer-mapped addresses for the other ranks)
+struct ShardArena {
+  uint32_t *flags;        // [kMaxWorld] epoch of the last complete scan of every source
+  int2 *mbox;             // [2][kMaxWorld] by parity, source: {distinct hit keys cast, records sent} (-1: the source failed)
+  int *gather_key;        // [2][world][hit_cap] by parity, source: the source's distinct hit keys ...
+  uint32_t *gather_stamp; // [2][world][hit_cap] ... and their first-insert stamps
+  int *cursor;            // [2] by parity: records reserved in the inbox so far (sources reserve with a remote atomicAdd)
+  ShardRecord *inbox;     // [2][rec_cap] by parity: update records for voxels this rank owns, all sources interleaved
+};
+struct ShardPeers {
+  ShardArena a[kMaxWorld];
+  int rank, world;
+  int hit_cap, rec_cap;
+};
+// what the wait kernel found (device copy read by the owner-side kernels, pinned host copy read by the caller)
+struct ShardState {
+  int n_total;            // distinct hit keys of the scan over all ranks
+  int n_rec_total;        // records received
+  int rehash;             // 1: n_total exceeds the bucket count -> the owner-side kernels skipped, host runs the rehash path
+  int error;              // device error code (peer failure, timeout, capacity)
+  int cnt_hits[kMaxWorld];
+  int cnt_recs[kMaxWorld];
+  unsigned long long wait_ns;  // time the wait kernel spent spinning (exchange skew seen by this rank)
+};
+constexpr int kErrPeer = 101;  // a peer did not signal in time / reported a failure
+
 __device__ __forceinline__ int owner_of(const MapParams &P, const int c[3], int world) {
   int g[3] = {floor_div(c[0], P.n), floor_div(c[1], P.n), floor_div(c[2], P.n)};
   uint64_t key;
@@ -26,73 +58,172 @@ __device__ __forceinline__ int owner_of(const MapParams &P, const int c[3], int 
   return (int)(ht_hash(key) % (uint32_t)world);
 }
 
-// one thread per touched-list entry; pass 0 counts records per destination, pass 1 writes them at
-// cursor[dest] and clears the local staging.  A voxel with hits and misses has two list entries: the
-// hit entry handles both.
-template <int kPass>
-__global__ void __launch_bounds__(256) k_shard_emit(MapParams P, DeviceBuffers D, FrameParams F, int world,
-                                                    int *counts /*[world]*/, const int *base /*[world]*/,
-                                                    int *cursor /*[world]*/, ShardRecord *out) {
-  __shared__ int s_cnt[64];
-  __shared__ int s_base[64];
+// all-gather of the rank's distinct hit keys + stamps: written into every rank's gather region for this source
+__global__ void __launch_bounds__(256) k_shard_push_hits(ShardPeers X, DeviceBuffers D, FrameParams F, int par) {
   FrameCounters *fc = D.fc[F.parity];
-  for (int i = threadIdx.x; i < world; i += blockDim.x) s_cnt[i] = 0;
-  __syncthreads();
-  const int n = min(fc->n_touched, P.max_touched);
-  const int dxy = P.lvg_dim_xy;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int dest = -1, nrec = 0, head = kLvgEmpty, mc = 0, lv = 0, rank_in_cta = 0;
-  int c[3] = {0, 0, 0};
-  if (i < n) {
-    const uint32_t e = D.touched[i];
-    lv = (int)(e & ~kTouchedHitTag);
-    const int2 st = D.lvg[lv];
-    if ((e & kTouchedHitTag) || st.x == kLvgEmpty) {  // the entry that owns the voxel
-      head = st.x;
-      mc = st.y;
-      c[0] = lv % dxy + F.lvg_base[0];
-      c[1] = (lv / dxy) % dxy + F.lvg_base[1];
-      c[2] = lv / (dxy * dxy) + F.lvg_base[2];
-      dest = owner_of(P, c, world);
-      for (int h = head; h != kLvgEmpty; h = D.hit_next[h]) nrec++;
-      if (mc > 0) nrec++;
-      rank_in_cta = atomicAdd(&s_cnt[dest], nrec);
-    }
-  }
-  __syncthreads();
-  if (kPass == 0) {
-    for (int d = threadIdx.x; d < world; d += blockDim.x)
-      if (s_cnt[d]) atomicAdd(&counts[d], s_cnt[d]);
+  const int n = fc->n_hit;
+  if (n > X.hit_cap) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) fc->error = kErrCapacity;
     return;
   }
-  for (int d = threadIdx.x; d < world; d += blockDim.x) s_base[d] = s_cnt[d] ? base[d] + atomicAdd(&cursor[d], s_cnt[d]) : 0;
-  __syncthreads();
-  if (dest >= 0) {
-    ShardRecord *o = out + s_base[dest] + rank_in_cta;
-    for (int h = head; h != kLvgEmpty; h = D.hit_next[h]) {
-      ShardRecord r;
-      r.c[0] = c[0];
-      r.c[1] = c[1];
-      r.c[2] = c[2];
-      r.key = D.hit_key[h];
-      r.p = D.hit_p[h];
-      r.count = (int)D.hit_t[h];  // every key is cast by exactly one rank, so its stamp travels with it
-      *o++ = r;
-    }
-    if (mc > 0) {
-      ShardRecord r;
-      r.c[0] = c[0];
-      r.c[1] = c[1];
-      r.c[2] = c[2];
-      r.key = -1;
-      r.p = 0.f;
-      r.count = mc;
-      *o++ = r;
+  const size_t region = ((size_t)par * X.world + X.rank) * X.hit_cap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int key = D.hit_key[i];
+    const uint32_t st = D.hit_t[i];
+    for (int d = 0; d < X.world; d++) {
+      X.a[d].gather_key[region + i] = key;
+      X.a[d].gather_stamp[region + i] = st;
     }
   }
-  // staging consumed.  Only the entry that owns the voxel clears it: the other entry of a voxel with hits and
-  // misses may sit anywhere in the list, and clearing from there could empty the voxel before its owner reads it
-  if (dest >= 0) D.lvg[lv] = make_int2(kLvgEmpty, 0);
+}
+
+// all-to-all of the update records: one thread per touched-list entry; records of a CTA chunk are grouped by
+// destination in shared memory, each group reserves its slots in the DESTINATION's inbox with one atomicAdd on that
+// rank's cursor (a remote atomic over NVLink for a peer: one per 256 list entries and destination) and is then
+// written there with plain stores.  `sent` counts what this source sent to each destination.  A voxel with hits and
+// misses has two list entries: the hit entry handles both.  Clears the local staging it consumes.
+__global__ void __launch_bounds__(256) k_shard_emit(ShardPeers X, MapParams P, DeviceBuffers D, FrameParams F, int par,
+                                                    int *sent /*[kMaxWorld]*/) {
+  __shared__ int s_cnt[kMaxWorld];
+  __shared__ int s_base[kMaxWorld];
+  FrameCounters *fc = D.fc[F.parity];
+  const int world = X.world;
+  const int n = min(fc->n_touched, P.max_touched);
+  const int dxy = P.lvg_dim_xy;
+  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    if (threadIdx.x < world) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int i = base + threadIdx.x;
+    int dest = -1, nrec = 0, head = kLvgEmpty, mc = 0, lv = 0, rank_in_cta = 0;
+    int c[3] = {0, 0, 0};
+    if (i < n) {
+      const uint32_t e = D.touched[i];
+      lv = (int)(e & ~kTouchedHitTag);
+      const int2 st = D.lvg[lv];
+      if ((e & kTouchedHitTag) || st.x == kLvgEmpty) {  // the entry that owns the voxel
+        head = st.x;
+        mc = st.y;
+        c[0] = lv % dxy + F.lvg_base[0];
+        c[1] = (lv / dxy) % dxy + F.lvg_base[1];
+        c[2] = lv / (dxy * dxy) + F.lvg_base[2];
+        dest = owner_of(P, c, world);
+        for (int h = head; h != kLvgEmpty; h = D.hit_next[h]) nrec++;
+        if (mc > 0) nrec++;
+        rank_in_cta = atomicAdd(&s_cnt[dest], nrec);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < world && s_cnt[threadIdx.x]) {
+      s_base[threadIdx.x] = atomicAdd(X.a[threadIdx.x].cursor + par, s_cnt[threadIdx.x]);
+      atomicAdd(&sent[threadIdx.x], s_cnt[threadIdx.x]);
+    }
+    __syncthreads();
+    if (dest >= 0) {
+      const int first = s_base[dest] + rank_in_cta;
+      if (first + nrec > X.rec_cap) {
+        fc->error = kErrCapacity;
+      } else {
+        ShardRecord *o = X.a[dest].inbox + (size_t)par * X.rec_cap + first;
+        for (int h = head; h != kLvgEmpty; h = D.hit_next[h]) {
+          ShardRecord r;
+          r.c[0] = c[0];
+          r.c[1] = c[1];
+          r.c[2] = c[2];
+          r.key = D.hit_key[h];
+          r.p = D.hit_p[h];
+          r.count = (int)D.hit_t[h];  // every key is cast by exactly one rank, so its stamp travels with it
+          *o++ = r;
+        }
+        if (mc > 0) {
+          ShardRecord r;
+          r.c[0] = c[0];
+          r.c[1] = c[1];
+          r.c[2] = c[2];
+          r.key = -1;
+          r.p = 0.f;
+          r.count = mc;
+          *o++ = r;
+        }
+      }
+      // staging consumed.  Only the entry that owns the voxel clears it: the other entry of a voxel with hits and
+      // misses may sit anywhere in the list, and clearing from there could empty the voxel before its owner reads it
+      D.lvg[lv] = make_int2(kLvgEmpty, 0);
+    }
+    __syncthreads();
+  }
+}
+
+// after the pushes of this scan have completed (stream order): publish the counts to every destination's mailbox,
+// make everything visible system-wide, raise this source's epoch flag in every arena; then rearm the local staging
+// counters for the owner-side ingest
+__global__ void k_shard_signal(ShardPeers X, DeviceBuffers D, FrameParams F, int par, const int *cursor, uint32_t epoch) {
+  FrameCounters *fc = D.fc[F.parity];
+  const int d = threadIdx.x;
+  if (d < X.world) {
+    const bool failed = fc->error != 0;
+    X.a[d].mbox[par * kMaxWorld + X.rank] = make_int2(failed ? -1 : fc->n_hit, failed ? -1 : cursor[d]);
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(X.a[d].flags + X.rank), "r"(epoch) : "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    fc->n_hit = 0;
+    fc->n_touched = 0;
+    fc->n_touched_sub = 0;
+  }
+}
+
+// owner side: wait until every source has raised its flag for this epoch, then total the counts and decide
+// whether the scan crosses a libstdc++ rehash (same decision on every rank: they all see the same counts)
+__global__ void k_shard_wait(ShardPeers X, DeviceBuffers D, FrameParams F, int par, uint32_t epoch, ShardState *st, int *skip,
+                             unsigned long long timeout_ns) {
+  __shared__ int s_fail;
+  const int s = threadIdx.x;
+  if (s == 0) s_fail = 0;
+  __syncthreads();
+  unsigned long long t0, t1 = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  if (s < X.world) {
+    const uint32_t *flag = X.a[X.rank].flags + s;
+    for (;;) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+      if ((int)(v - epoch) >= 0) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > timeout_ns) {
+        s_fail = 1;
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  if (s == 0) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    FrameCounters *fc = D.fc[F.parity];
+    int n_total = 0, n_rec = 0, err = s_fail ? kErrPeer : 0;
+    for (int r = 0; r < X.world; r++) {
+      int2 m = s_fail ? make_int2(0, 0) : X.a[X.rank].mbox[par * kMaxWorld + r];
+      if (m.x < 0 || m.y < 0) {
+        err = kErrPeer;
+        m = make_int2(0, 0);
+      }
+      st->cnt_hits[r] = m.x;
+      st->cnt_recs[r] = m.y;
+      n_total += m.x;
+      n_rec += m.y;
+    }
+    // every source has reserved and written all its records: the cursor is the number of records to ingest
+    if (!err && __ldcg(X.a[X.rank].cursor + par) != n_rec) err = kErrCapacity;  // a source ran past rec_cap
+    if (fc->error) err = fc->error;
+    st->n_total = n_total;
+    st->n_rec_total = n_rec;
+    st->rehash = (err == 0 && (uint32_t)n_total > F.bucket_count) ? 1 : 0;
+    st->error = err;
+    st->wait_ns = t1 - t0;
+    if (err) fc->error = err;
+    *skip = (err != 0 || st->rehash) ? 1 : 0;
+  }
 }
 
 // global ordering info per key: key_stamp[key] = first-insert stamp (or virtual position on a rehash frame)
@@ -100,18 +231,22 @@ __global__ void k_shard_scatter_stamps(const int *keys, const uint32_t *stamps, 
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) key_stamp[keys[i]] = stamps[i];
 }
-__global__ void k_shard_act(MapParams P, const int *keys, const uint32_t *stamps, int n, uint32_t *act, uint32_t B) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) atomicMin(&act[cell_bucket(P, keys[i], B, 0)], stamps[i]);
+// bucket activation stamps of a no-rehash scan from the gathered (key, stamp) lists of all sources
+__global__ void __launch_bounds__(256) k_shard_act(ShardPeers X, MapParams P, int par, const ShardState *st, const int *skip,
+                                                   uint32_t *act, uint32_t B) {
+  if (*skip) return;
+  const ShardArena &A = X.a[X.rank];
+  for (int src = 0; src < X.world; src++) {
+    const int n = st->cnt_hits[src];
+    const size_t region = ((size_t)par * X.world + src) * X.hit_cap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+      atomicMin(&act[cell_bucket(P, A.gather_key[region + i], B, 0)], A.gather_stamp[region + i]);
+  }
 }
 
-// owner side: received records -> hit arrays + voxel-grid staging (the role k_column's staging plays on one GPU)
-__global__ void __launch_bounds__(256) k_shard_ingest(MapParams P, DeviceBuffers D, FrameParams F, const ShardRecord *rec,
-                                                      int n, const uint32_t *key_stamp) {
-  FrameCounters *fc = D.fc[F.parity];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const ShardRecord r = rec[i];
+// owner side: one received record -> hit arrays + voxel-grid staging (the role k_column's staging plays on one GPU)
+__device__ __forceinline__ void ingest_record(const MapParams &P, DeviceBuffers &D, const FrameParams &F, FrameCounters *fc,
+                                              const ShardRecord &r, const uint32_t *key_stamp) {
   CellRef cr;
   for (int a = 0; a < 3; a++) {
     cr.c[a] = r.c[a];
@@ -147,17 +282,19 @@ __global__ void __launch_bounds__(256) k_shard_ingest(MapParams P, DeviceBuffers
   }
   touch_subbox(P, F, D, fc, cr.g);
 }
+__global__ void __launch_bounds__(256) k_shard_ingest(ShardPeers X, MapParams P, DeviceBuffers D, FrameParams F, int par,
+                                                      const ShardState *st, const int *skip, const uint32_t *key_stamp) {
+  if (skip && *skip) return;
+  FrameCounters *fc = D.fc[F.parity];
+  const int n = st->n_rec_total;
+  const ShardRecord *rec = X.a[X.rank].inbox + (size_t)par * X.rec_cap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) ingest_record(P, D, F, fc, rec[i], key_stamp);
+}
 
 // standalone resolve (on one GPU the last k_column CTA does this)
 __global__ void __launch_bounds__(1024) k_shard_resolve(MapParams P, DeviceBuffers D, FrameParams F) {
+  if (F.skip_flag && *F.skip_flag) return;
   resolve_subboxes(P, F, D, D.fc[F.parity], threadIdx.x, blockDim.x);
-}
-
-__global__ void k_shard_reset_counters(DeviceBuffers D, FrameParams F) {
-  FrameCounters *fc = D.fc[F.parity];
-  fc->n_hit = 0;
-  fc->n_touched = 0;
-  fc->n_touched_sub = 0;
 }
 
 

@@ -104,6 +104,8 @@ struct FrameParams {
   int inline_resolve; // 1 (k_frame): the first thread to touch a subbox resolves / allocates it right away
   int parity;       // frame & 1: selects the double-buffered counters / activation stamps
   int order_mode;   // 0: stamps are (bucket activation, first-insert time); 1: virtual sequence positions
+  const int *skip_flag;  // sharded scans: when non-null and *skip_flag != 0 the owner-side kernels (resolve, fuse) return at
+                         // once; set on device when the gathered hit count calls for the rehash path (the host re-launches)
 };
 
 // per-frame counters + error word, reset by k_frame_begin

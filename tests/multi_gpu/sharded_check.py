@@ -44,11 +44,10 @@ def main():
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         st = sh.integrate_points(pts, pose)
-        torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
         if orc is not None:
             st_o = orc.integrate_points(pts, pose)
-            assert sh.last["n_hit_total"] == st_o.n_hit_cells, (sh.last, st_o.n_hit_cells)
+            assert st.n_hit_cells == st_o.n_hit_cells, (sh.last, st_o.n_hit_cells)
     mine = sh.export_map()
     gathered = [None] * world
     dist.all_gather_object(gathered, {k: v for k, v in mine.items()})
@@ -70,6 +69,8 @@ def main():
                           "ms_per_scan": [round(1e3 * t, 3) for t in times],
                           "median_ms_after_warmup": round(1e3 * float(np.median(times[2:])), 3) if len(times) > 3 else None,
                           "last": sh.last}))
+    dist.barrier()
+    sh.close()
     dist.barrier()
     dist.destroy_process_group()
     return 0 if ok else 1
