@@ -180,15 +180,33 @@ def run_reference(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
-def run_lidar(rank, world, local_rank, barrier, scans=10, warm=3):
+def run_lidar(rank, world, local_rank, barrier, scans=12, warm=4):
+    """BASELINE config 4 (CFG-C): 128 x 2048 LiDAR scans into ONE map.  At every N the scan goes through the sharded
+    path (stage by phi column, keys + update records stored into the owners' arenas over NVLink peer memory, owner-side
+    fusion; world 1 = the same kernels without peers); at N = 1 the fused single-GPU frame (k_frame) is timed beside it
+    and is the N = 1 figure.  Timed on the device: CUDA events on the library's stream around submit..finish, barrier
+    before every scan, sum over the timed scans, max over ranks.  The first two scans are checked against the CPU
+    oracle (union of the ranks' subboxes == the oracle map, bit for bit)."""
     import torch
     from mlmapping_b200 import MLMap, config_cfg_c, scenes
+    from mlmapping_b200.sharded import ShardedMLMap
     cfg = config_cfg_c()
     data = []
     for k in range(scans):
         pose = scenes.lidar_loop_pose(k)
         data.append((scenes.lidar_scan(pose, frame_idx=k), pose))
-    out = {"workload": "cfg_c_128beam_lidar_2048az_d0.2m_50m (BASELINE config 4)", "scans": scans - warm, "n_gpus": world}
+    out = {"workload": "cfg_c_128beam_lidar_2048az_d0.2m_50m (BASELINE config 4)", "scans": scans - warm, "n_gpus": world,
+           "scaling": "strong"}
+    peak, _ = measured_peak_gbs()
+
+    def reduce_max(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    fused = None
     if world == 1:
         m = MLMap(cfg, device=local_rank)
         dev = [(m.to_device(p), p.shape[0], pose) for p, pose in data]
@@ -204,36 +222,100 @@ def run_lidar(rank, world, local_rank, barrier, scans=10, warm=3):
                 touched += st.n_touched_voxels
                 new += st.n_new_submaps
         alg = 24 * rays + 56 * (scans - warm) + 10 * touched + 6000 * new  # SURVEY 8d frame bytes with point input
-        peak, _ = measured_peak_gbs()
-        out.update({"mode": "one map on one GPU, points resident in HBM, L2 flushed between scans",
-                    "rays_per_s": rays / (ms * 1e-3), "us_per_scan": 1e3 * ms / (scans - warm),
-                    "alg_GB_per_s": alg / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak})
+        fused = {"mode": "one map on one GPU, ONE cooperative launch per scan (k_frame), points resident in HBM, L2 flushed",
+                 "rays_per_s": rays / (ms * 1e-3), "us_per_scan": 1e3 * ms / (scans - warm),
+                 "alg_GB_per_s": alg / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak}
         m.close()
-        return out
-    from mlmapping_b200.sharded import ShardedMLMap
+
     sh = ShardedMLMap(cfg, rank=rank, world=world, device=local_rank)
-    sh.timing = False
-    secs, rays = 0.0, 0
-    for k, (pts, pose) in enumerate(data):
-        buf = sh.pinned_points(pts.shape[0])
-        buf[...] = pts
+    dev = [(sh.map.to_device(p), p.shape[0], pose) for p, pose in data]
+    parity = "not checked"
+    ms, rays, wait_ns, rehash = 0.0, 0, 0, 0
+    for k, (dp, n, pose) in enumerate(dev):
+        sh.map.flush_l2()
+        barrier()
+        sh.map.timer_start()
+        sh.submit_device(dp, n, pose)
+        sh.finish()
+        t = sh.map.timer_stop_ms()
+        rehash += sh.last["rehash_path"]
+        if k >= warm:
+            ms += t
+            rays += n
+            wait_ns += sh.last["wait_ns"]
+        if k == 1:  # parity of the sharded map against the CPU oracle after two scans
+            mine = sh.export_map()
+            gathered = [mine]
+            if world > 1:
+                gathered = [None] * world
+                torch.distributed.all_gather_object(gathered, mine)
+            if rank == 0:
+                from oracle_binding import Oracle
+                oc = Oracle(cfg, bookkeeping=False)
+                for p, ps in data[:2]:
+                    oc.integrate_points(p, ps)
+                o = oc.export_map()
+                oc.close()
+                glb = np.concatenate([g["glb"] for g in gathered])
+                order = np.lexsort((glb[:, 2], glb[:, 1], glb[:, 0]))
+                ok = np.array_equal(glb[order], o["glb"])
+                for name in ("occupancy", "log_odds", "collapsed"):
+                    u = np.concatenate([g[name] for g in gathered])[order]
+                    ok = ok and u.shape == o[name].shape and np.array_equal(u.view(np.uint8), o[name].view(np.uint8))
+                parity = "ok" if ok else "MISMATCH"
+                out["parity_subboxes"] = int(glb.shape[0])
+                out["subboxes_owned_per_rank"] = [int(g["glb"].shape[0]) for g in gathered]
+    ms = reduce_max(ms)
+    sharded = {"mode": "ONE map sharded by subbox ownership over the ranks: keys and update records stored into the owners' "
+                       "arenas over NVLink peer memory by the library's kernels, device-side wait; points resident in HBM, "
+                       "L2 flushed, CUDA events around submit..finish, max over ranks",
+               "rays_per_s": rays / (ms * 1e-3), "us_per_scan": 1e3 * ms / (scans - warm),
+               "wait_us_per_scan_this_rank": 1e-3 * wait_ns / (scans - warm), "rehash_scans": rehash,
+               "last_exchange": sh.last}
+    # per-stage device times (events between the launches; a separate pass so that the events do not sit in the timed one)
+    sh.map.set_profiling(True)
+    acc = {}
+    for k, (dp, n, pose) in enumerate(dev[warm:]):
+        sh.map.flush_l2()
+        barrier()
+        sh.submit_device(dp, n, pose)
+        sh.finish()
+        for k_, v_ in sh.last_kernel_us().items():
+            acc[k_] = acc.get(k_, 0.0) + v_ / (scans - warm)
+    sh.map.set_profiling(False)
+    sharded["stage_us_this_rank"] = {k_: round(v_, 1) for k_, v_ in acc.items()}
+    # e2e: the scan starts in pinned host memory, the H2D copy is inside the timed region (wall clock, max over ranks)
+    buf = sh.pinned_points(max(p.shape[0] for p, _ in data))
+    secs, e_rays, h2d_us, t_submit = 0.0, 0, 0.0, 0.0
+    sh.map.set_profiling(True)
+    for k, (pts, pose) in enumerate(data[warm:]):
+        b = buf[:pts.shape[0]]
+        b[...] = pts
+        sh.map.flush_l2()
         barrier()
         t0 = time.perf_counter()
-        sh.integrate_points(buf, pose)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if k >= warm:
-            secs += dt
-            rays += pts.shape[0]
-    t = torch.tensor([secs], dtype=torch.float64, device="cuda")
-    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    secs = float(t.item())
-    owned = sh.export_map()["glb"].shape[0]
-    out.update({"mode": "ONE map sharded by subbox ownership over the ranks (host scan in pinned memory, H2D + NCCL "
-                        "exchanges inside the timed region, wall clock, max over ranks)",
-                "rays_per_s": rays / secs, "us_per_scan": 1e6 * secs / (scans - warm), "scaling": "strong",
-                "subboxes_owned_rank0": owned, "last_exchange": {k_: v_ for k_, v_ in sh.last.items() if k_ != "timing"}})
+        sh.submit(b, pose)
+        t1 = time.perf_counter()
+        sh.finish()
+        secs += time.perf_counter() - t0
+        t_submit += t1 - t0
+        e_rays += pts.shape[0]
+        h2d_us += sh.last_kernel_us()["resets_h2d"] / (scans - warm)
+    sh.map.set_profiling(False)
+    secs = reduce_max(secs)
+    sharded["e2e"] = {"rays_per_s": e_rays / secs, "us_per_scan": 1e6 * secs / (scans - warm),
+                      "h2d_bytes_per_scan": int(24 * e_rays / (scans - warm)), "resets_and_h2d_us_this_rank": round(h2d_us, 1),
+                      "host_submit_us_this_rank": round(1e6 * t_submit / (scans - warm), 1),
+                      "note": "every rank copies the whole scan (it casts its own phi columns of it)"}
+    if world > 1:
+        barrier()
     sh.close()
+    if world > 1:
+        barrier()
+    best = fused if fused is not None and fused["us_per_scan"] <= sharded["us_per_scan"] else sharded
+    out.update({"parity": parity, "rays_per_s": best["rays_per_s"], "us_per_scan": best["us_per_scan"], "sharded": sharded})
+    if fused is not None:
+        out["fused_single_gpu"] = fused
     return out
 
 
@@ -247,7 +329,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-queries", action="store_true")
     ap.add_argument("--no-lidar", action="store_true")
-    ap.add_argument("--lidar-sharded-any-n", action="store_true", help="run the sharded LiDAR section above 2 ranks too")
+    ap.add_argument("--lidar-only", action="store_true", help="run only the LiDAR section and print its JSON (tooling)")
     ap.add_argument("--queries", type=int, default=10_000_000, help="planner queries per step (4:4:2 odd/occupancy/grad)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -275,14 +357,22 @@ def main():
     import ctypes as C
     from mlmapping_b200.capi import FrameStats
 
-    cfg = config_cfg_a()
-    total = args.steps + args.warmup
-    frames, poses = gen_frames(cfg, total, agent=rank)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.lidar_only:
+        res = run_lidar(rank, world, local_rank, barrier)
+        if rank == 0:
+            print(json.dumps({"lidar": res}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cfg = config_cfg_a()
+    total = args.steps + args.warmup
+    frames, poses = gen_frames(cfg, total, agent=rank)
 
     # ---------------- pass 1: device-resident inputs ("value") ----------------
     m = MLMap(cfg, device=local_rank)
@@ -347,22 +437,14 @@ def main():
             m.device_free(pp)
 
     # ---------------- LiDAR-scale integration (BASELINE config 4, CFG-C): 128 x 2048 scans ----------------
-    # N = 1: one map on one GPU.  N > 1: ONE logical map sharded over the ranks by subbox ownership (stage by phi
-    # column, NCCL min-all-reduce / all-gather for the global iteration order, all-to-all of the update records).
+    # ONE logical map sharded over the ranks by subbox ownership (stage by phi column; hit keys all-gathered and update
+    # records sent to their owners by the library's kernels over NVLink peer memory); N = 1 also times the fused frame.
     lidar = None
     if not args.no_lidar:
-        if world > 2 and not args.lidar_sharded_any_n:
-            # The sharded exchange is verified on 2 GPUs (tests/multi_gpu/sharded_check.py, this section at N = 2).
-            # A 4-GPU run of this script stopped making progress in round 1.  The likely cause was found afterwards
-            # (with the per-stage timing syncs off, the library's ingest kernels could start before torch's
-            # all-to-all had finished; fixed in ShardedMLMap._join_torch_stream) but could not be re-run within the
-            # GPU budget, so the section stays opt-in above 2 ranks: a hang would cost the whole scaling run.
-            lidar = {"skipped": "sharded LiDAR section runs at N <= 2 by default (--lidar-sharded-any-n to force); "
-                                "unverified above 2 ranks in round 1"}
-        elif world == 1:
+        if world == 1:
             try:
                 lidar = run_lidar(rank, world, local_rank, barrier)
-            except Exception as e:  # no collectives at N = 1: an error here must not cost the headline line
+            except Exception as e:  # no peers at N = 1: an error here must not cost the headline line
                 lidar = {"error": f"{type(e).__name__}: {e}"[:300]}
         else:
             lidar = run_lidar(rank, world, local_rank, barrier)
@@ -485,7 +567,7 @@ def main():
                 out["queries"]["cpu_baseline"] = {"value": 300000 / tq, "unit": "queries/s", "cores": 1, "kind": "port",
                                                   "sample": "300k queries (same 4:4:2 mix) on a 20-frame oracle map"}
                 orc.close()
-            if lidar and "error" not in lidar and "skipped" not in lidar:
+            if lidar and "error" not in lidar:
                 from mlmapping_b200 import config_cfg_c, scenes as _sc2
                 from oracle_binding import Oracle as _Orc
                 cfg_c = config_cfg_c()

@@ -122,7 +122,7 @@ ABI_SYMBOLS = [
     "mlm_debug_log10f", "mlm_set_profiling", "mlm_last_frame_kernel_ms", "mlm_sizeof_config",
     "mlm_sizeof_frame_stats", "mlm_debug_phase_cycles", "mlm_host_alloc", "mlm_host_free", "mlm_srand", "mlm_debug_rand", "mlm_export_frontier", 
     "mlm_shard_open", "mlm_shard_connect", "mlm_shard_submit_points_f64", "mlm_shard_submit_points_f64_device", "mlm_shard_finish",
-    "mlm_shard_integrate_points_f64", "mlm_shard_last_exchange", "mlm_shard_close", "mlm_dirty_count", "mlm_dirty_export", "mlm_dirty_import",
+    "mlm_shard_integrate_points_f64", "mlm_shard_last_exchange", "mlm_shard_last_kernel_ms", "mlm_shard_close", "mlm_dirty_count", "mlm_dirty_export", "mlm_dirty_import",
     "mlm_export_cloud", "mlm_export_cloud_device", "mlm_export_odds_slice",
     "mlm_checkpoint_size", "mlm_checkpoint_save", "mlm_checkpoint_restore", "mlm_compensate_pose",
     "mlm_export_cloud", "mlm_export_cloud_device", "mlm_export_odds_slice",
@@ -211,6 +211,7 @@ def load_library() -> C.CDLL:
         "mlm_shard_integrate_points_f64": ([vp, vp, C.c_int, dp, C.POINTER(FrameStats)], C.c_int),
         "mlm_shard_last_exchange": ([vp, C.POINTER(ShardExchange)], C.c_int),
         "mlm_shard_close": ([vp], C.c_int),
+        "mlm_shard_last_kernel_ms": ([vp, fp], C.c_int),
         "mlm_dirty_count": ([vp, ip, C.POINTER(sz)], C.c_int),
         "mlm_dirty_export": ([vp, vp, C.c_int32], C.c_int),
         "mlm_dirty_import": ([vp, vp, C.c_int32], C.c_int),

@@ -178,7 +178,7 @@ struct mlm_map {
   GlibcRand rng;  // project_depth's rand() stream (sampled mode)
   // sharded operation (one logical map over several ranks, exchange over peer memory)
   uint32_t *d_key_stamp = nullptr;   // [cells] global ordering stamp per hit key of a rehash scan
-  int *d_shard_cursor = nullptr;     // [kMaxWorld] records written per destination this scan; [kMaxWorld] = skip flag
+  int *d_shard_cursor = nullptr;     // [kMaxWorld] records sent per destination this scan; [kMaxWorld] skip flag; [kMaxWorld + 1] push ticket
   ShardState *d_shard_state = nullptr, *h_shard_state = nullptr;  // device copy / pinned host copy
   int *d_keys_all = nullptr;         // [sort_cap] gathered keys, contiguous (rehash path)
   uint32_t *d_stamps_all = nullptr, *d_bucket_all = nullptr;
@@ -187,6 +187,9 @@ struct mlm_map {
   ShardPeers shard_peers;            // every rank's arena as mapped here
   void *shard_mapped[kMaxWorld] = {};  // cudaIpcOpenMemHandle results to close
   bool shard_open = false, shard_connected = false, shard_pending = false;
+  cudaEvent_t sev[MLM_NUM_SHARD_KERNELS + 1] = {};
+  float skms[MLM_NUM_SHARD_KERNELS] = {};
+  bool shard_shares_device = false;  // another rank of this process runs on the same GPU (single-GPU tests)
   uint32_t shard_epoch = 0;
   unsigned long long shard_timeout_ns = 10ull * 1000 * 1000 * 1000;
   int shard_world = 1, shard_rank = 0;
@@ -531,6 +534,7 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
     const int pg = grid_for((size_t)std::max(N, 1), kProjThreads * 2);
     if (F.bucket_count == 1) F.bucket_count = 13;  // the first insert of an empty table allocates 13 buckets before anything is ordered
     k_project<0><<<pg, kProjThreads, project_smem_bytes(P.nCol, kProjThreads), s>>>(P, h->D, F);
+    if (h->profiling && h->sev[2]) cudaEventRecord(h->sev[2], s);
     k_column<<<h->col_grid, kColThreads, h->col_smem_bytes, s>>>(P, h->D, F);
     h->launches += 2;
     return MLM_OK;  // no host sync: the exchange and the owner-side kernels follow on the stream (mlm_shard_submit_*)
@@ -1021,18 +1025,22 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   CUDA_TRY_H(cudaMallocHost((void **)&h->h_fp, sizeof(FrameParams)));
   CUDA_TRY_H(cudaHostAlloc((void **)&h->h_fc, sizeof(FrameCounters), cudaHostAllocMapped));
   memset(h->h_fc, 0, sizeof(FrameCounters));
-  CUDA_TRY_H(cudaFuncSetAttribute(k_column, cudaFuncAttributeMaxDynamicSharedMemorySize, h->col_smem_bytes));
+  // cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the FUNCTION, shared by every handle of the process: it
+  // is set to one configuration-independent ceiling, so that a later handle with a smaller column never lowers the limit
+  // under a live handle with a larger one (two configurations in one process, e.g. a depth map next to a LiDAR map)
+  const int smem_ceiling = max_optin - 1024;
+  CUDA_TRY_H(cudaFuncSetAttribute(k_column, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ceiling));
   if ((long long)project_smem_bytes(P.nCol, kProjThreads) > (long long)max_optin - 1024) {
-    delete h;
+    mlm_destroy(h);
     g_last_error = "n_Phi too large for the projection's shared-memory histogram";
     return MLM_ERR_INVALID_CONFIG;
   }
   // one cooperative launch per frame when every phase fits the resident CTA (not in exploration mode, whose
   // ordered passes need extra kernels between the phases)
   {
-    CUDA_TRY_H(cudaFuncSetAttribute(k_frame<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->col_smem_bytes));
-    CUDA_TRY_H(cudaFuncSetAttribute(k_frame<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->col_smem_bytes));
-    CUDA_TRY_H(cudaFuncSetAttribute(k_frame<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->col_smem_bytes));
+    CUDA_TRY_H(cudaFuncSetAttribute(k_frame<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ceiling));
+    CUDA_TRY_H(cudaFuncSetAttribute(k_frame<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ceiling));
+    CUDA_TRY_H(cudaFuncSetAttribute(k_frame<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ceiling));
     int per_sm = 0, coop = 0;
     CUDA_TRY_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame<1>, kColThreads, h->col_smem_bytes));
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
@@ -1041,12 +1049,9 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
                    project_smem_bytes(P.nCol, kColThreads) <= (size_t)h->col_smem_bytes;
     if (const char *e = getenv("MLM_NO_FUSED")) if (atoi(e)) h->use_fused = 0;
   }
-  if (project_smem_bytes(P.nCol, kProjThreads) > 48 * 1024) {
-    const int pb = (int)project_smem_bytes(P.nCol, kProjThreads);
-    CUDA_TRY_H(cudaFuncSetAttribute(k_project<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
-    CUDA_TRY_H(cudaFuncSetAttribute(k_project<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
-    CUDA_TRY_H(cudaFuncSetAttribute(k_project<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
-  }
+  CUDA_TRY_H(cudaFuncSetAttribute(k_project<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ceiling));
+  CUDA_TRY_H(cudaFuncSetAttribute(k_project<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ceiling));
+  CUDA_TRY_H(cudaFuncSetAttribute(k_project<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ceiling));
 
   DeviceBuffers &D = h->D;
   memset(&D, 0, sizeof(D));
@@ -1218,6 +1223,8 @@ int mlm_destroy(mlm_handle h) {
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (int i = 0; i <= MLM_NUM_FRAME_KERNELS; i++)
     if (h->kev[i]) cudaEventDestroy(h->kev[i]);
+  for (int i = 0; i <= MLM_NUM_SHARD_KERNELS; i++)
+    if (h->sev[i]) cudaEventDestroy(h->sev[i]);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return MLM_OK;
@@ -1412,6 +1419,7 @@ int mlm_get_odd_grad(mlm_handle h, const double *pos, size_t n, size_t max_iter,
 }
 int mlm_get_occupancy_device(mlm_handle h, const double *d_pos, size_t n, int32_t *d_out) {
   if (!h || (!d_pos && n) || (!d_out && n)) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
   if (n == 0) return MLM_OK;
   k_get_occupancy<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->D, d_pos, n, d_out);
   h->launches++;
@@ -1419,6 +1427,7 @@ int mlm_get_occupancy_device(mlm_handle h, const double *d_pos, size_t n, int32_
 }
 int mlm_get_odd_device(mlm_handle h, const double *d_pos, size_t n, float *d_out) {
   if (!h || (!d_pos && n) || (!d_out && n)) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
   if (n == 0) return MLM_OK;
   k_get_odd<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->D, d_pos, n, d_out);
   h->launches++;
@@ -1426,6 +1435,7 @@ int mlm_get_odd_device(mlm_handle h, const double *d_pos, size_t n, float *d_out
 }
 int mlm_get_odd_grad_device(mlm_handle h, const double *d_pos, size_t n, size_t max_iter, double *d_out3n) {
   if (!h || (!d_pos && n) || (!d_out3n && n)) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
   if (n == 0) return MLM_OK;
   k_get_odd_grad<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->D, d_pos, n, (int)max_iter, d_out3n);
   h->launches++;
@@ -1435,17 +1445,20 @@ int mlm_get_odd_grad_device(mlm_handle h, const double *d_pos, size_t n, size_t 
 // ---- stream control ----------------------------------------------------------------------------------
 int mlm_sync(mlm_handle h) {
   if (!h) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   CUDA_TRY(cudaGetLastError());
   return MLM_OK;
 }
 int mlm_timer_start(mlm_handle h) {
   if (!h) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
   return MLM_OK;
 }
 int mlm_timer_stop_ms(mlm_handle h, float *ms) {
   if (!h || !ms) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
   CUDA_TRY(cudaEventSynchronize(h->ev1));
   CUDA_TRY(cudaEventElapsedTime(ms, h->ev0, h->ev1));
@@ -1459,6 +1472,7 @@ int mlm_device_alloc(mlm_handle h, size_t bytes, void **d_ptr) {
 }
 int mlm_device_free(mlm_handle h, void *d_ptr) {
   if (!h) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaFree(d_ptr));
   return MLM_OK;
 }
@@ -1470,23 +1484,27 @@ int mlm_host_alloc(mlm_handle h, size_t bytes, void **ptr) {
 }
 int mlm_host_free(mlm_handle h, void *ptr) {
   if (!h) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaFreeHost(ptr));
   return MLM_OK;
 }
 int mlm_copy_to_device(mlm_handle h, void *d_dst, const void *src, size_t bytes) {
   if (!h || !d_dst || !src) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return MLM_OK;
 }
 int mlm_copy_to_host(mlm_handle h, void *dst, const void *d_src, size_t bytes) {
   if (!h || !dst || !d_src) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return MLM_OK;
 }
 int mlm_flush_l2(mlm_handle h) {
   if (!h) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
   if (!h->l2_buf) {
     h->l2_bytes = (size_t)256 << 20;  // > 126 MB L2
     CUDA_TRY(cudaMalloc(&h->l2_buf, h->l2_bytes));
@@ -1498,6 +1516,7 @@ int mlm_flush_l2(mlm_handle h) {
 }
 int mlm_set_profiling(mlm_handle h, int enable) {
   if (!h) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
   if (enable && !h->kev[0])
     for (int i = 0; i <= MLM_NUM_FRAME_KERNELS; i++) CUDA_TRY(cudaEventCreate(&h->kev[i]));
   h->profiling = enable != 0;
@@ -1510,6 +1529,7 @@ int mlm_last_frame_kernel_ms(mlm_handle h, float ms[MLM_NUM_FRAME_KERNELS]) {
 }
 int mlm_debug_phase_cycles(mlm_handle h, long long *out, size_t cap) {
   if (!h || !out) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
   size_t n = std::min(cap, (size_t)(h->P.nCol + 256) * 16);
   CUDA_TRY(cudaMemcpy(out, h->D.debug_cycles, n * sizeof(long long), cudaMemcpyDeviceToHost));
   return MLM_OK;
@@ -1724,7 +1744,25 @@ struct CkptFileHeader {
   int64_t cum_ram_expand, cum_obs, n_submaps;
   int32_t rng_r[31];
   int32_t rng_f, rng_b;
+  uint64_t checksum;        // FNV-1a 64 over the record bytes
 };
+uint64_t fnv1a64(const unsigned char *p, size_t n) {
+  uint64_t hsh = 0xcbf29ce484222325ull;
+  // 8 bytes per step (the images are tens of MB); the tail byte-wise
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    uint64_t w;
+    memcpy(&w, p + i, 8);
+    hsh = (hsh ^ w) * 0x100000001b3ull;
+  }
+  for (; i < n; i++) hsh = (hsh ^ p[i]) * 0x100000001b3ull;
+  return hsh;
+}
+bool on_bucket_chain(uint32_t B) {
+  for (int i = 0; i < kBucketChainLen; i++)
+    if (kBucketChain[i] == B) return true;
+  return false;
+}
 const char kCkptMagic[8] = {'M', 'L', 'M', 'C', 'K', 'P', 'T', '1'};
 bool same_map_config(const mlm_config &a, const mlm_config &b) {
   return a.am_d_rho == b.am_d_rho && a.am_d_phi_deg == b.am_d_phi_deg && a.am_d_z == b.am_d_z && a.am_n_rho == b.am_n_rho &&
@@ -1768,7 +1806,7 @@ int mlm_checkpoint_save(mlm_handle h, void *buf, size_t cap, size_t *written) {
   CkptFileHeader hd;
   memset(&hd, 0, sizeof(hd));
   memcpy(hd.magic, kCkptMagic, 8);
-  hd.version = 1;
+  hd.version = 2;
   hd.header_bytes = (uint32_t)sizeof(hd);
   hd.cfg = h->cfg;
   hd.cells = P.cells;
@@ -1784,6 +1822,7 @@ int mlm_checkpoint_save(mlm_handle h, void *buf, size_t cap, size_t *written) {
   memcpy(hd.rng_r, h->rng.r, sizeof(hd.rng_r));
   hd.rng_f = h->rng.f;
   hd.rng_b = h->rng.b;
+  hd.checksum = fnv1a64(nullptr, 0);
   memcpy(buf, &hd, sizeof(hd));
   if (n == 0) return MLM_OK;
   int *d_cnt = nullptr, *d_glb = nullptr, *d_blk = nullptr;
@@ -1809,6 +1848,8 @@ int mlm_checkpoint_save(mlm_handle h, void *buf, size_t cap, size_t *written) {
   CUDA_TRY(cudaFreeAsync(d_rec, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   CUDA_TRY(cudaGetLastError());
+  hd.checksum = fnv1a64(dst, n * rb);
+  memcpy(buf, &hd, sizeof(hd));
   return MLM_OK;
 }
 
@@ -1818,7 +1859,7 @@ int mlm_checkpoint_restore(mlm_handle h, const void *buf, size_t bytes) {
   memcpy(&hd, buf, sizeof(hd));
   const MapParams &P = h->P;
   const size_t rb = ckpt_record_bytes(P.cells, P.front_words, P.explore);
-  if (memcmp(hd.magic, kCkptMagic, 8) != 0 || hd.version != 1 || hd.header_bytes != sizeof(hd)) {
+  if (memcmp(hd.magic, kCkptMagic, 8) != 0 || hd.version != 2 || hd.header_bytes != sizeof(hd)) {
     g_last_error = "not a mlmap_b200 checkpoint (magic / version)";
     return MLM_ERR_INVALID_ARG;
   }
@@ -1833,6 +1874,49 @@ int mlm_checkpoint_restore(mlm_handle h, const void *buf, size_t bytes) {
   if (hd.n_records > (uint64_t)P.pool_blocks + (uint64_t)(P.explore ? P.ht_mask / 2 : 0)) {
     g_last_error = "checkpoint holds more subboxes than this handle's pool";
     return MLM_ERR_POOL_EXHAUSTED;
+  }
+  // Everything below is checked BEFORE the live map is touched: a refused image leaves the handle as it was.
+  // (1) the emulated bucket counts index this handle's activation arrays: they must be members of the growth chain and
+  //     fit the arrays (max_points is not part of the map configuration, so the saving handle may have had larger ones)
+  if (!on_bucket_chain(hd.bucket_count) || hd.bucket_count > h->act_cap ||
+      (P.explore && (!on_bucket_chain(hd.bucket_count_miss) || hd.bucket_count_miss > h->act_miss_cap))) {
+    g_last_error = "checkpoint bucket counts are not on the libstdc++ growth chain or exceed this handle's capacity (max_points)";
+    return MLM_ERR_CAPACITY;
+  }
+  // (2) the records are the bytes that were saved
+  const unsigned char *recs = reinterpret_cast<const unsigned char *>(buf) + sizeof(hd);
+  if (fnv1a64(recs, (size_t)hd.n_records * rb) != hd.checksum) {
+    g_last_error = "checkpoint checksum mismatch (corrupt image)";
+    return MLM_ERR_INVALID_ARG;
+  }
+  // (3) every record header is sane: flags, subbox index range, no duplicates, full blocks fit the pool
+  {
+    std::vector<uint64_t> keys;
+    keys.reserve((size_t)hd.n_records);
+    uint64_t full_blocks = 0;
+    const int lim = 1 << 20;
+    for (uint64_t i = 0; i < hd.n_records; i++) {
+      CkptRecHeader rh;
+      memcpy(&rh, recs + i * rb, sizeof(rh));
+      const bool collapsed = rh.flags == 1;
+      bool ok = (rh.flags == 0 || (collapsed && P.explore));
+      for (int a = 0; a < 3; a++) ok = ok && rh.g[a] >= -lim && rh.g[a] < lim;
+      if (!ok) {
+        g_last_error = "checkpoint record " + std::to_string(i) + " is malformed";
+        return MLM_ERR_INVALID_ARG;
+      }
+      if (!collapsed) full_blocks++;
+      keys.push_back(((uint64_t)(uint32_t)(rh.g[0] + lim) << 42) | ((uint64_t)(uint32_t)(rh.g[1] + lim) << 21) | (uint64_t)(uint32_t)(rh.g[2] + lim));
+    }
+    std::sort(keys.begin(), keys.end());
+    if (std::adjacent_find(keys.begin(), keys.end()) != keys.end()) {
+      g_last_error = "checkpoint holds a subbox twice";
+      return MLM_ERR_INVALID_ARG;
+    }
+    if (full_blocks > (uint64_t)P.pool_blocks) {
+      g_last_error = "checkpoint holds more subboxes than this handle's pool";
+      return MLM_ERR_POOL_EXHAUSTED;
+    }
   }
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
@@ -1874,21 +1958,27 @@ int mlm_checkpoint_restore(mlm_handle h, const void *buf, size_t bytes) {
     const size_t n = (size_t)hd.n_records;
     const size_t batch = std::max<size_t>(1, std::min<size_t>(n, ((size_t)256 << 20) / rb));
     CUDA_TRY(cudaMallocAsync((void **)&d_status, sizeof(int), s));
-    CUDA_TRY(cudaMallocAsync((void **)&d_rec, batch * rb, s));
-    CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int), s));
-    const unsigned char *src = reinterpret_cast<const unsigned char *>(buf) + sizeof(hd);
-    for (size_t first = 0; first < n; first += batch) {
-      const size_t m = std::min(batch, n - first);
-      CUDA_TRY(cudaMemcpyAsync(d_rec, src + first * rb, m * rb, cudaMemcpyHostToDevice, s));
-      k_ckpt_unpack<<<(unsigned)m, 256, 0, s>>>(P, D, (int)m, d_rec, d_status);
-      CUDA_TRY(cudaStreamSynchronize(s));
-      h->launches++;
+    if (cudaMallocAsync((void **)&d_rec, batch * rb, s) != cudaSuccess) {
+      cudaFreeAsync(d_status, s);
+      g_last_error = "checkpoint restore: out of device memory for the staging buffer";
+      return MLM_ERR_CUDA;
     }
     int status = 0;
-    CUDA_TRY(cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaFreeAsync(d_status, s));
-    CUDA_TRY(cudaFreeAsync(d_rec, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    cudaError_t ce = cudaMemsetAsync(d_status, 0, sizeof(int), s);
+    const unsigned char *src = reinterpret_cast<const unsigned char *>(buf) + sizeof(hd);
+    for (size_t first = 0; first < n && ce == cudaSuccess; first += batch) {
+      const size_t m = std::min(batch, n - first);
+      ce = cudaMemcpyAsync(d_rec, src + first * rb, m * rb, cudaMemcpyHostToDevice, s);
+      if (ce != cudaSuccess) break;
+      k_ckpt_unpack<<<(unsigned)m, 256, 0, s>>>(P, D, (int)m, d_rec, d_status);
+      ce = cudaStreamSynchronize(s);
+      h->launches++;
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaFreeAsync(d_status, s);  // the temporaries are released on every path
+    cudaFreeAsync(d_rec, s);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    CUDA_TRY(ce);
     if (status) {
       g_last_error = "checkpoint restore: device raised error code " + std::to_string(status);
       rc = map_device_error(status);
@@ -1903,7 +1993,7 @@ int mlm_checkpoint_restore(mlm_handle h, const void *buf, size_t bytes) {
   h->last_n_hit = 0;
   h->cum_ram_expand = hd.cum_ram_expand;
   h->cum_obs = hd.cum_obs;
-  h->n_submaps = hd.n_submaps;
+  h->n_submaps = (int64_t)hd.n_records;  // the records actually inserted, not a number taken from the image
   memcpy(h->rng.r, hd.rng_r, sizeof(hd.rng_r));
   h->rng.f = hd.rng_f;
   h->rng.b = hd.rng_b;
@@ -1956,42 +2046,68 @@ int shard_check(mlm_handle h, bool need_connected) {
 
 // everything of one scan after the input is on the device: stage the rank's columns, push keys and records to the
 // owners, signal, wait for every source, then the owner-side kernels; no host synchronisation
-int shard_enqueue(mlm_handle h, const double *d_xyz, int n, const double T_wb[7]) {
+int shard_enqueue(mlm_handle h, const double *d_xyz, int n, const double T_wb[7], const void *h2d_src = nullptr) {
   cudaStream_t s = h->stream;
   const ShardPeers &X = h->shard_peers;
   const uint32_t epoch = ++h->shard_epoch;
   const int par = (int)(epoch & 1);
   const int parity_next = (int)(h->frame_idx & 1);
+  const bool prof = h->profiling != 0;
+  if (prof && !h->sev[0])
+    for (int i = 0; i <= MLM_NUM_SHARD_KERNELS; i++) CUDA_TRY(cudaEventCreate(&h->sev[i]));
+#define MLM_SMARK(i) do { if (prof) cudaEventRecord(h->sev[i], s); } while (0)
+  static const bool host_timing = getenv("MLM_DEBUG_HOST_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point ht[8];
+  int hn = 0;
+#define MLM_HT() do { if (host_timing && hn < 8) ht[hn++] = std::chrono::steady_clock::now(); } while (0)
+  MLM_HT();
+  MLM_SMARK(0);
+  if (h2d_src && n > 0) CUDA_TRY(cudaMemcpyAsync(h->d_input, h2d_src, (size_t)n * 24, cudaMemcpyHostToDevice, s));
   // stale activation stamps of earlier scans must not survive: the staging kernels atomicMin into this buffer
   CUDA_TRY(cudaMemsetAsync(h->D.act[parity_next], 0xff, (size_t)h->act_cap * 4, s));
-  CUDA_TRY(cudaMemsetAsync(h->d_shard_cursor, 0, (kMaxWorld + 1) * sizeof(int), s));
+  CUDA_TRY(cudaMemsetAsync(h->d_shard_cursor, 0, (kMaxWorld + 2) * sizeof(int), s));  // sent[], skip flag, push ticket
   // the inbox cursor of the PREVIOUS scan's parity: its records are ingested, and no source can reserve in it again before
   // it has seen this scan's flag (raised further down this stream)
   CUDA_TRY(cudaMemsetAsync(X.a[X.rank].cursor + (par ^ 1), 0, sizeof(int), s));
+  MLM_SMARK(1);
+  MLM_HT();
   h->shard_stage_pending = true;
   int rc = run_frame(h, 0, d_xyz, 0, 0, n, T_wb, nullptr);
   h->shard_stage_pending = false;
   if (rc != MLM_OK) return rc;
+  MLM_SMARK(3);
+  MLM_HT();
   FrameParams F = *h->h_fp;  // as the staging kernels saw it (bucket_count already lifted from 1 to 13)
   int *skip = h->d_shard_cursor + kMaxWorld;
   const int G = h->sm_count * 2;
-  k_shard_push_hits<<<G, 256, 0, s>>>(X, h->D, F, par);
-  k_shard_emit<<<G * 2, 256, 0, s>>>(X, h->P, h->D, F, par, h->d_shard_cursor);
-  k_shard_signal<<<1, 32, 0, s>>>(X, h->D, F, par, h->d_shard_cursor, epoch);
-  k_shard_wait<<<1, 32, 0, s>>>(X, h->D, F, par, epoch, h->d_shard_state, skip, h->shard_timeout_ns);
-  // owner side (all of it returns at once when the wait kernel found a rehash scan or an error)
+  k_shard_push<<<G * 2, 256, 0, s>>>(X, h->P, h->D, F, par, h->d_shard_cursor, epoch);
+  MLM_SMARK(4);
+  // owner side (all of it returns at once when the wait at the head of k_shard_act found a rehash scan or an error)
   F.stage_only = 0;
   F.order_mode = 1;  // stamps are complete: first-insert stamps travel in the records, activations come from the gathered keys
   F.shard_world = 1;
+  F.inline_resolve = 1;  // the first record of a subbox resolves / allocates it (k_fuse's tail rearms the flags)
   F.skip_flag = skip;
-  k_shard_act<<<G, 256, 0, s>>>(X, h->P, par, h->d_shard_state, skip, h->D.act[F.parity], F.bucket_count);
+  // its CTAs spin at the head until every source has signalled: when several ranks share one GPU (tests) they must leave
+  // most SMs to the other ranks' staging kernels
+  k_shard_act<<<h->shard_shares_device ? 32 : G, 256, 0, s>>>(X, h->P, h->D, F, par, epoch, h->d_shard_state, skip, h->shard_timeout_ns, h->D.act[F.parity]);
+  MLM_SMARK(5);
   k_shard_ingest<<<G * 2, 256, 0, s>>>(X, h->P, h->D, F, par, h->d_shard_state, skip, nullptr);
-  k_shard_resolve<<<1, 1024, 0, s>>>(h->P, h->D, F);
+  MLM_SMARK(6);
   k_fuse<0><<<h->sm_count * 4, 256, 0, s>>>(h->P, h->D, F);
-  h->launches += 8;
+  MLM_SMARK(7);
+#undef MLM_SMARK
+  h->launches += 4;
   CUDA_TRY(cudaMemcpyAsync(h->h_shard_state, h->d_shard_state, sizeof(ShardState), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc[F.parity], sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaGetLastError());
+  MLM_HT();
+  if (host_timing) {
+    fprintf(stderr, "shard_enqueue host us:");
+    for (int i = 1; i < hn; i++) fprintf(stderr, " %.1f", std::chrono::duration<double, std::micro>(ht[i] - ht[i - 1]).count());
+    fprintf(stderr, "\n");
+  }
+#undef MLM_HT
   h->shard_pending = true;
   return MLM_OK;
 }
@@ -2057,10 +2173,10 @@ int shard_rehash_path(mlm_handle h, const ShardState &st, uint32_t *B_out) {
   F.order_mode = 1;
   F.shard_world = 1;
   F.skip_flag = nullptr;
+  F.inline_resolve = 1;
   F.bucket_count = Bs;
   const int G = h->sm_count * 2;
   k_shard_ingest<<<G * 2, 256, 0, s>>>(X, h->P, h->D, F, par, h->d_shard_state, nullptr, h->d_key_stamp);
-  k_shard_resolve<<<1, 1024, 0, s>>>(h->P, h->D, F);
   k_fuse<0><<<h->sm_count * 4, 256, 0, s>>>(h->P, h->D, F);
   h->launches += 8;
   CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc[F.parity], sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
@@ -2097,7 +2213,7 @@ int mlm_shard_open(mlm_handle h, int rank, int world, void *blob_out) {
     const size_t cells = (size_t)P.nZ * P.nPhi * P.nRho;
     CUDA_TRY(cudaMalloc((void **)&h->d_key_stamp, cells * sizeof(uint32_t)));
     h->allocs.push_back(h->d_key_stamp);
-    CUDA_TRY(cudaMalloc((void **)&h->d_shard_cursor, (kMaxWorld + 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc((void **)&h->d_shard_cursor, (kMaxWorld + 2) * sizeof(int)));
     h->allocs.push_back(h->d_shard_cursor);
     CUDA_TRY(cudaMalloc((void **)&h->d_shard_state, sizeof(ShardState)));
     h->allocs.push_back(h->d_shard_state);
@@ -2158,6 +2274,7 @@ int mlm_shard_connect(mlm_handle h, const void *blobs) {
     if (b.pid == (int64_t)getpid()) {
       // a handle of this process (several GPUs driven by one process, or several ranks on one GPU in the tests)
       base = reinterpret_cast<void *>((uintptr_t)b.ptr);
+      if (b.device == h->device) h->shard_shares_device = true;
       if (b.device != h->device) {
         int can = 0;
         CUDA_TRY(cudaDeviceCanAccessPeer(&can, h->device, b.device));
@@ -2220,18 +2337,18 @@ int mlm_shard_submit_points_f64(mlm_handle h, const double *xyz, int n, const do
   const size_t bytes = (size_t)std::max(n, 1) * 24;
   rc = ensure_input(h, bytes, (size_t)h->P.max_points * 24);
   if (rc != MLM_OK) return rc;
+  const void *src = nullptr;
   if (n > 0) {
     cudaPointerAttributes attr;
     const bool pinned = cudaPointerGetAttributes(&attr, xyz) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    const void *src = xyz;
+    src = xyz;
     if (!pinned) {
       memcpy(h->h_stage, xyz, (size_t)n * 24);
       src = h->h_stage;
     }
-    CUDA_TRY(cudaMemcpyAsync(h->d_input, src, (size_t)n * 24, cudaMemcpyHostToDevice, h->stream));
   }
-  return shard_enqueue(h, reinterpret_cast<const double *>(h->d_input), n, T_wb);
+  return shard_enqueue(h, reinterpret_cast<const double *>(h->d_input), n, T_wb, src);
 }
 
 int mlm_shard_finish(mlm_handle h, mlm_frame_stats *stats) {
@@ -2245,6 +2362,8 @@ int mlm_shard_finish(mlm_handle h, mlm_frame_stats *stats) {
   h->shard_pending = false;
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   CUDA_TRY(cudaGetLastError());
+  if (h->profiling && h->sev[0])
+    for (int i = 0; i < MLM_NUM_SHARD_KERNELS; i++) cudaEventElapsedTime(&h->skms[i], h->sev[i], h->sev[i + 1]);
   const ShardState st = *h->h_shard_state;
   if (st.error) {
     g_last_error = st.error == kErrPeer ? "sharded scan: a peer rank failed or did not signal within the timeout"
@@ -2276,6 +2395,12 @@ int mlm_shard_integrate_points_f64(mlm_handle h, const double *xyz, int n, const
   return mlm_shard_finish(h, stats);
 }
 
+int mlm_shard_last_kernel_ms(mlm_handle h, float ms[MLM_NUM_SHARD_KERNELS]) {
+  if (!h || !ms) return MLM_ERR_INVALID_ARG;
+  for (int i = 0; i < MLM_NUM_SHARD_KERNELS; i++) ms[i] = h->skms[i];
+  return MLM_OK;
+}
+
 int mlm_shard_last_exchange(mlm_handle h, mlm_shard_exchange *out) {
   if (!h || !out || !h->h_shard_state) return MLM_ERR_INVALID_ARG;
   const ShardState &st = *h->h_shard_state;
@@ -2301,6 +2426,7 @@ int mlm_dirty_count(mlm_handle h, int32_t *n_blocks, size_t *record_bytes) {
 }
 int mlm_dirty_export(mlm_handle h, void *d_out, int32_t n_blocks) {
   if (!h || (n_blocks && !d_out) || n_blocks < 0 || n_blocks > h->h_fc->n_touched_sub) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
   if (n_blocks) k_dirty_export<<<n_blocks, 256, 0, h->stream>>>(h->P, h->D, *h->h_fp, n_blocks, (unsigned char *)d_out);
   h->launches++;
   CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -2309,6 +2435,7 @@ int mlm_dirty_export(mlm_handle h, void *d_out, int32_t n_blocks) {
 }
 int mlm_dirty_import(mlm_handle h, const void *d_in, int32_t n_blocks) {
   if (!h || (n_blocks && !d_in) || n_blocks < 0) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
   if (h->P.explore) return MLM_ERR_UNSUPPORTED;
   cudaStream_t s = h->stream;
   int *d_cnt = nullptr;

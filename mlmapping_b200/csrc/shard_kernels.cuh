@@ -58,36 +58,72 @@ __device__ __forceinline__ int owner_of(const MapParams &P, const int c[3], int 
   return (int)(ht_hash(key) % (uint32_t)world);
 }
 
-// all-gather of the rank's distinct hit keys + stamps: written into every rank's gather region for this source
-__global__ void __launch_bounds__(256) k_shard_push_hits(ShardPeers X, DeviceBuffers D, FrameParams F, int par) {
-  FrameCounters *fc = D.fc[F.parity];
-  const int n = fc->n_hit;
-  if (n > X.hit_cap) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) fc->error = kErrCapacity;
-    return;
+// CTA-wide slot reservation: every thread asks for `want` (0 or more) consecutive slots of a global counter; one
+// atomicAdd per CTA and call (a per-warp atomic on one address serialises: 33 k of them cost 130 us per CFG-C scan)
+__device__ __forceinline__ int cta_reserve(int *ctr, int want, int *s_warp /*[33]*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  int incl = want;
+#pragma unroll
+  for (int ofs = 1; ofs < 32; ofs <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, ofs);
+    if (lane >= ofs) incl += t;
   }
-  const size_t region = ((size_t)par * X.world + X.rank) * X.hit_cap;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int key = D.hit_key[i];
-    const uint32_t st = D.hit_t[i];
-    for (int d = 0; d < X.world; d++) {
-      X.a[d].gather_key[region + i] = key;
-      X.a[d].gather_stamp[region + i] = st;
+  if (lane == 31) s_warp[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    const int v = lane < nw ? s_warp[lane] : 0;
+    int si = v;
+#pragma unroll
+    for (int ofs = 1; ofs < 32; ofs <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, si, ofs);
+      if (lane >= ofs) si += t;
     }
+    const int total = __shfl_sync(0xffffffffu, si, 31);
+    int base = 0;
+    if (lane == 0 && total > 0) base = atomicAdd(ctr, total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (lane < nw) s_warp[lane] = base + si - v;
   }
+  __syncthreads();
+  const int res = s_warp[w] + incl - want;
+  __syncthreads();  // s_warp is reused by the next call
+  return res;
 }
 
-// all-to-all of the update records: one thread per touched-list entry; records of a CTA chunk are grouped by
-// destination in shared memory, each group reserves its slots in the DESTINATION's inbox with one atomicAdd on that
-// rank's cursor (a remote atomic over NVLink for a peer: one per 256 list entries and destination) and is then
-// written there with plain stores.  `sent` counts what this source sent to each destination.  A voxel with hits and
-// misses has two list entries: the hit entry handles both.  Clears the local staging it consumes.
-__global__ void __launch_bounds__(256) k_shard_emit(ShardPeers X, MapParams P, DeviceBuffers D, FrameParams F, int par,
-                                                    int *sent /*[kMaxWorld]*/) {
+// ---- source side: ONE kernel per scan pushes everything this rank has for the others ----------------------------
+// (1) all-gather of the rank's distinct hit keys + stamps: written into every rank's gather region for this source;
+// (2) all-to-all of the update records: one thread per touched-list entry; records of a CTA chunk are grouped by
+//     destination in shared memory, each group reserves its slots in the DESTINATION's inbox with one atomicAdd on that
+//     rank's cursor (a remote atomic over NVLink for a peer: one per 256 list entries and destination) and is then
+//     written there with plain stores.  A voxel with hits and misses has two list entries: the hit entry handles both.
+//     Clears the local staging it consumes;
+// (3) the last CTA (completion ticket) publishes the counts to every destination's mailbox, makes everything visible
+//     system-wide and raises this source's epoch flag in every arena, then rearms the local staging counters for the
+//     owner-side ingest.
+__global__ void __launch_bounds__(256) k_shard_push(ShardPeers X, MapParams P, DeviceBuffers D, FrameParams F, int par,
+                                                    int *sent /*[kMaxWorld] records per destination; [kMaxWorld + 1] ticket*/,
+                                                    uint32_t epoch) {
   __shared__ int s_cnt[kMaxWorld];
   __shared__ int s_base[kMaxWorld];
+  __shared__ int s_last;
   FrameCounters *fc = D.fc[F.parity];
   const int world = X.world;
+  // (1)
+  const int n_hit = fc->n_hit;
+  if (n_hit > X.hit_cap) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) fc->error = kErrCapacity;
+  } else {
+    const size_t region = ((size_t)par * world + X.rank) * X.hit_cap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hit; i += gridDim.x * blockDim.x) {
+      const int key = D.hit_key[i];
+      const uint32_t st = D.hit_t[i];
+      for (int d = 0; d < world; d++) {
+        X.a[d].gather_key[region + i] = key;
+        X.a[d].gather_stamp[region + i] = st;
+      }
+    }
+  }
+  // (2)
   const int n = min(fc->n_touched, P.max_touched);
   const int dxy = P.lvg_dim_xy;
   for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
@@ -151,17 +187,17 @@ __global__ void __launch_bounds__(256) k_shard_emit(ShardPeers X, MapParams P, D
     }
     __syncthreads();
   }
-}
-
-// after the pushes of this scan have completed (stream order): publish the counts to every destination's mailbox,
-// make everything visible system-wide, raise this source's epoch flag in every arena; then rearm the local staging
-// counters for the owner-side ingest
-__global__ void k_shard_signal(ShardPeers X, DeviceBuffers D, FrameParams F, int par, const int *cursor, uint32_t epoch) {
-  FrameCounters *fc = D.fc[F.parity];
+  // (3) every thread orders its own (remote) stores system-wide, the CTA's last arrival takes a ticket
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&sent[kMaxWorld + 1], 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
   const int d = threadIdx.x;
-  if (d < X.world) {
-    const bool failed = fc->error != 0;
-    X.a[d].mbox[par * kMaxWorld + X.rank] = make_int2(failed ? -1 : fc->n_hit, failed ? -1 : cursor[d]);
+  if (d < world) {
+    const bool failed = __ldcg(&fc->error) != 0;
+    X.a[d].mbox[par * kMaxWorld + X.rank] = make_int2(failed ? -1 : n_hit, failed ? -1 : __ldcg(&sent[d]));
     __threadfence_system();
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(X.a[d].flags + X.rank), "r"(epoch) : "memory");
   }
@@ -173,10 +209,12 @@ __global__ void k_shard_signal(ShardPeers X, DeviceBuffers D, FrameParams F, int
   }
 }
 
-// owner side: wait until every source has raised its flag for this epoch, then total the counts and decide
-// whether the scan crosses a libstdc++ rehash (same decision on every rank: they all see the same counts)
-__global__ void k_shard_wait(ShardPeers X, DeviceBuffers D, FrameParams F, int par, uint32_t epoch, ShardState *st, int *skip,
-                             unsigned long long timeout_ns) {
+// ---- owner side ---------------------------------------------------------------------------------------------------
+// wait until every source has raised its flag for this epoch, total the counts and decide whether the scan crosses a
+// libstdc++ rehash (same decision on every rank: they all see the same counts).  Every CTA of the first owner-side
+// kernel runs this (the flags are read-only here); CTA 0 records the result for the later kernels and the host.
+__device__ __forceinline__ bool shard_wait(const ShardPeers &X, DeviceBuffers &D, const FrameParams &F, int par, uint32_t epoch,
+                                           ShardState *st, int *skip, unsigned long long timeout_ns, ShardState *s_st) {
   __shared__ int s_fail;
   const int s = threadIdx.x;
   if (s == 0) s_fail = 0;
@@ -194,7 +232,7 @@ __global__ void k_shard_wait(ShardPeers X, DeviceBuffers D, FrameParams F, int p
         s_fail = 1;
         break;
       }
-      __nanosleep(200);
+      __nanosleep(100);
     }
   }
   __syncthreads();
@@ -203,27 +241,33 @@ __global__ void k_shard_wait(ShardPeers X, DeviceBuffers D, FrameParams F, int p
     FrameCounters *fc = D.fc[F.parity];
     int n_total = 0, n_rec = 0, err = s_fail ? kErrPeer : 0;
     for (int r = 0; r < X.world; r++) {
-      int2 m = s_fail ? make_int2(0, 0) : X.a[X.rank].mbox[par * kMaxWorld + r];
+      int2 m = s_fail ? make_int2(0, 0) : __ldcg(&X.a[X.rank].mbox[par * kMaxWorld + r]);
       if (m.x < 0 || m.y < 0) {
         err = kErrPeer;
         m = make_int2(0, 0);
       }
-      st->cnt_hits[r] = m.x;
-      st->cnt_recs[r] = m.y;
+      s_st->cnt_hits[r] = m.x;
+      s_st->cnt_recs[r] = m.y;
       n_total += m.x;
       n_rec += m.y;
     }
     // every source has reserved and written all its records: the cursor is the number of records to ingest
     if (!err && __ldcg(X.a[X.rank].cursor + par) != n_rec) err = kErrCapacity;  // a source ran past rec_cap
-    if (fc->error) err = fc->error;
-    st->n_total = n_total;
-    st->n_rec_total = n_rec;
-    st->rehash = (err == 0 && (uint32_t)n_total > F.bucket_count) ? 1 : 0;
-    st->error = err;
-    st->wait_ns = t1 - t0;
-    if (err) fc->error = err;
-    *skip = (err != 0 || st->rehash) ? 1 : 0;
+    const int local_err = __ldcg(&fc->error);
+    if (local_err) err = local_err;
+    s_st->n_total = n_total;
+    s_st->n_rec_total = n_rec;
+    s_st->rehash = (err == 0 && (uint32_t)n_total > F.bucket_count) ? 1 : 0;
+    s_st->error = err;
+    s_st->wait_ns = t1 - t0;
+    if (blockIdx.x == 0) {
+      *st = *s_st;
+      if (err) fc->error = err;
+      *skip = (err != 0 || s_st->rehash) ? 1 : 0;
+    }
   }
+  __syncthreads();
+  return s_st->error == 0 && s_st->rehash == 0;
 }
 
 // global ordering info per key: key_stamp[key] = first-insert stamp (or virtual position on a rehash frame)
@@ -231,72 +275,81 @@ __global__ void k_shard_scatter_stamps(const int *keys, const uint32_t *stamps, 
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) key_stamp[keys[i]] = stamps[i];
 }
-// bucket activation stamps of a no-rehash scan from the gathered (key, stamp) lists of all sources
-__global__ void __launch_bounds__(256) k_shard_act(ShardPeers X, MapParams P, int par, const ShardState *st, const int *skip,
-                                                   uint32_t *act, uint32_t B) {
-  if (*skip) return;
+// first owner-side kernel: wait for the sources, then the bucket activation stamps of a no-rehash scan from the
+// gathered (key, stamp) lists of all sources
+__global__ void __launch_bounds__(256) k_shard_act(ShardPeers X, MapParams P, DeviceBuffers D, FrameParams F, int par, uint32_t epoch,
+                                                   ShardState *st, int *skip, unsigned long long timeout_ns, uint32_t *act) {
+  __shared__ ShardState s_st;
+  if (!shard_wait(X, D, F, par, epoch, st, skip, timeout_ns, &s_st)) return;
   const ShardArena &A = X.a[X.rank];
+  const uint32_t B = F.bucket_count;
   for (int src = 0; src < X.world; src++) {
-    const int n = st->cnt_hits[src];
+    const int n = s_st.cnt_hits[src];
     const size_t region = ((size_t)par * X.world + src) * X.hit_cap;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-      atomicMin(&act[cell_bucket(P, A.gather_key[region + i], B, 0)], A.gather_stamp[region + i]);
+      atomicMin(&act[cell_bucket(P, __ldcg(A.gather_key + region + i), B, 0)], __ldcg(A.gather_stamp + region + i));
   }
 }
 
-// owner side: one received record -> hit arrays + voxel-grid staging (the role k_column's staging plays on one GPU)
-__device__ __forceinline__ void ingest_record(const MapParams &P, DeviceBuffers &D, const FrameParams &F, FrameCounters *fc,
-                                              const ShardRecord &r, const uint32_t *key_stamp) {
-  CellRef cr;
-  for (int a = 0; a < 3; a++) {
-    cr.c[a] = r.c[a];
-    cr.g[a] = floor_div(r.c[a], P.n);
-  }
-  const int lv = lvg_index(P, F, cr);
-  if (lv < 0) {
-    fc->error = kErrInternal;
-    return;
-  }
-  if (r.key >= 0) {
-    const int idx = agg_inc(&fc->n_hit);
-    if (idx >= P.max_hits) {
-      fc->error = kErrCapacity;
-      return;
-    }
-    D.hit_key[idx] = r.key;
-    D.hit_p[idx] = r.p;
-    D.hit_t[idx] = key_stamp ? key_stamp[r.key] : (uint32_t)r.count;  // rehash frames: virtual position from the global order
-    D.hit_bucket[idx] = cell_bucket(P, r.key, F.bucket_count, 0);
-    const int old = atomicExch(&D.lvg[lv].x, idx);
-    D.hit_next[idx] = old;
-    if (old == kLvgEmpty) {
-      const int tp = agg_inc(&fc->n_touched);
-      if (tp < P.max_touched) D.touched[tp] = (uint32_t)lv | kTouchedHitTag; else fc->error = kErrCapacity;
-    }
-  } else {
-    const int old = atomicAdd(&D.lvg[lv].y, r.count);
-    if (old == 0) {
-      const int tp = agg_inc(&fc->n_touched);
-      if (tp < P.max_touched) D.touched[tp] = (uint32_t)lv; else fc->error = kErrCapacity;
-    }
-  }
-  touch_subbox(P, F, D, fc, cr.g);
-}
+// owner side: received records -> hit arrays + voxel-grid staging (the role k_column's staging plays on one GPU).
+// Slots of the hit list and of the touched list are reserved once per CTA and 256 records; the first toucher of a
+// subbox resolves / allocates it on the spot (F.inline_resolve, as in k_frame).
 __global__ void __launch_bounds__(256) k_shard_ingest(ShardPeers X, MapParams P, DeviceBuffers D, FrameParams F, int par,
                                                       const ShardState *st, const int *skip, const uint32_t *key_stamp) {
+  __shared__ int s_warp[33];
   if (skip && *skip) return;
   FrameCounters *fc = D.fc[F.parity];
   const int n = st->n_rec_total;
-  const ShardRecord *rec = X.a[X.rank].inbox + (size_t)par * X.rec_cap;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) ingest_record(P, D, F, fc, rec[i], key_stamp);
+  const int2 *rec = reinterpret_cast<const int2 *>(X.a[X.rank].inbox + (size_t)par * X.rec_cap);
+  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const int i = base + threadIdx.x;
+    const bool valid = i < n;
+    ShardRecord r;
+    int lv = -1;
+    CellRef cr;
+    if (valid) {
+      const int2 a = __ldcg(rec + 3 * (size_t)i), b = __ldcg(rec + 3 * (size_t)i + 1), c = __ldcg(rec + 3 * (size_t)i + 2);
+      r.c[0] = a.x;
+      r.c[1] = a.y;
+      r.c[2] = b.x;
+      r.key = b.y;
+      r.p = __int_as_float(c.x);
+      r.count = c.y;
+      for (int k = 0; k < 3; k++) {
+        cr.c[k] = r.c[k];
+        cr.g[k] = floor_div(r.c[k], P.n);
+      }
+      lv = lvg_index(P, F, cr);
+      if (lv < 0) fc->error = kErrInternal;
+    }
+    const bool is_hit = valid && lv >= 0 && r.key >= 0;
+    const bool is_miss = valid && lv >= 0 && r.key < 0;
+    const int idx = cta_reserve(&fc->n_hit, is_hit ? 1 : 0, s_warp);
+    bool new_voxel = false;
+    uint32_t tag = 0;
+    if (is_hit) {
+      if (idx >= P.max_hits) {
+        fc->error = kErrCapacity;
+      } else {
+        D.hit_key[idx] = r.key;
+        D.hit_p[idx] = r.p;
+        D.hit_t[idx] = key_stamp ? key_stamp[r.key] : (uint32_t)r.count;  // rehash scans: virtual position from the global order
+        D.hit_bucket[idx] = cell_bucket(P, r.key, F.bucket_count, 0);
+        const int old = atomicExch(&D.lvg[lv].x, idx);
+        D.hit_next[idx] = old;
+        new_voxel = old == kLvgEmpty;
+        tag = kTouchedHitTag;
+      }
+    } else if (is_miss) {
+      new_voxel = atomicAdd(&D.lvg[lv].y, r.count) == 0;
+    }
+    const int tp = cta_reserve(&fc->n_touched, new_voxel ? 1 : 0, s_warp);
+    if (new_voxel) {
+      if (tp < P.max_touched) D.touched[tp] = (uint32_t)lv | tag; else fc->error = kErrCapacity;
+    }
+    if (valid && lv >= 0) touch_subbox(P, F, D, fc, cr.g);
+  }
 }
-
-// standalone resolve (on one GPU the last k_column CTA does this)
-__global__ void __launch_bounds__(1024) k_shard_resolve(MapParams P, DeviceBuffers D, FrameParams F) {
-  if (F.skip_flag && *F.skip_flag) return;
-  resolve_subboxes(P, F, D, D.fc[F.parity], threadIdx.x, blockDim.x);
-}
-
 
 // ---- replicated map (query stream): after a frame the owner ships the subbox blocks the frame
 // touched ("dirty" blocks); replicas overwrite / create them.  Record = 16-byte header {g[3], cells} followed

@@ -72,6 +72,14 @@ class ShardedMLMap:
         self.last["gather_bytes_in"] = 8 * ex.n_hit_total
         return st
 
+    STAGES = ("resets_h2d", "k_project", "k_column", "k_shard_push", "k_shard_act_wait", "k_shard_ingest", "k_fuse")
+
+    def last_kernel_us(self):
+        """per-stage device times of the last scan (needs self.map.set_profiling(True))"""
+        ms = (C.c_float * len(self.STAGES))()
+        self.map._check(self.map._lib.mlm_shard_last_kernel_ms(self.map._h, ms))
+        return {k: 1e3 * float(v) for k, v in zip(self.STAGES, ms)}
+
     def integrate_points(self, xyz: np.ndarray, T_wb) -> FrameStats:
         self.submit(xyz, T_wb)
         return self.finish()
