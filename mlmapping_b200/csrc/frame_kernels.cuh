@@ -825,21 +825,27 @@ __host__ __device__ inline size_t col_smem_prefix_bytes(int col_words, int nRho,
 #define MLM_PHASE_G(i, leader) do { } while (0)
 #endif
 
-// One work column (a phi column or one of its halves), start to finish, by the whole CTA.
-__device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D, const FrameParams &F, const int vc,
+// One work item (a phi column or one of its halves), start to finish, by the whole CTA.
+// item < nCol: work column `item`; item >= nCol (split layouts only): the two halves of phi column item - nCol worked as
+// ONE whole column (the queue merges the lightest columns when there are more active halves than CTAs: a second round of
+// items costs more than the few larger ones).  The halves feed disjoint hit cells, so concatenating their records is exact.
+__device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D, const FrameParams &F, const int item,
                                             unsigned char *s_raw) {
   FrameCounters *fc = D.fc[F.parity];
   uint32_t *act = D.act[F.parity];
   // work column: a phi column, or one of its two halves (records below / at-or-above the sensor row n_below)
-  const int phi = P.split ? vc >> 1 : vc;
-  const int side = P.split ? (vc & 1) : -1;
+  const bool merged = P.split && item >= P.nCol;
+  const int phi = merged ? item - P.nCol : (P.split ? item >> 1 : item);
+  const int side = (P.split && !merged) ? (item & 1) : -1;
+  const int vc = merged ? 2 * phi : item;   // first (or only) work column of the item
+  const int vc2 = merged ? vc + 1 : -1;
   // miss-bitmap rows this CTA owns outright, and the one row (n_below) both halves mark: rays of either half
   // end at the sensor row, so that row goes to global memory with atomicOr and whoever sets a bit first stages it
   const int z_own_lo = side == 1 ? P.n_below + 1 : 0;
   const int z_own_hi = side == 0 ? P.n_below : P.nZ;
   const int z_shared = side >= 0 ? P.n_below : -1;
   const int tid = threadIdx.x;
-  const int n_c = D.phi_hist[vc];
+  const int n_c = D.phi_hist[vc] + (merged ? D.phi_hist[vc2] : 0);
   uint32_t *g_miss = D.miss_bitmap + (size_t)phi * P.col_words;
   MLM_PHASE(15);
   MLM_WALL(13);
@@ -864,7 +870,7 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
   // s_map[k] = index into rec_lin of the column's k-th record
   __shared__ int s_warp[33];
   __shared__ int s_off;
-  const int bound_c = D.phi_bound[vc];                  // upper bound of this column's hit contributions
+  const int bound_c = D.phi_bound[vc] + (merged ? D.phi_bound[vc2] : 0);   // upper bound of this item's hit contributions
   const bool in_smem = bound_c <= P.sort_cap_smem;       // sort buffer in shared memory, else global spill (slow, exact)
   const bool big = n_c > P.map_cap;                      // more records than the shared-memory index map holds
   int off = 0;
@@ -883,17 +889,25 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
     const int nb = (F.n_total + F.tile_pts - 1) / F.tile_pts;   // tiles of the projection
     const int per = (nb + (int)blockDim.x - 1) / (int)blockDim.x;
     const int b0 = min(tid * per, nb), b1 = min(b0 + per, nb);
-    uint32_t dsave[4];
+    uint32_t dsave[4], dsave2[4];
     int mine = 0;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       dsave[q] = 0;
+      dsave2[q] = 0;
       if (b0 + q < b1) {
         dsave[q] = __ldcg(&D.rec_dir[(size_t)(b0 + q) * P.nCol + vc]);
         mine += (int)(dsave[q] & 0xffffu);
+        if (merged) {
+          dsave2[q] = __ldcg(&D.rec_dir[(size_t)(b0 + q) * P.nCol + vc2]);
+          mine += (int)(dsave2[q] & 0xffffu);
+        }
       }
     }
-    for (int b = b0 + 4; b < b1; b++) mine += (int)(__ldcg(&D.rec_dir[(size_t)b * P.nCol + vc]) & 0xffffu);
+    for (int b = b0 + 4; b < b1; b++) {
+      mine += (int)(__ldcg(&D.rec_dir[(size_t)b * P.nCol + vc]) & 0xffffu);
+      if (merged) mine += (int)(__ldcg(&D.rec_dir[(size_t)b * P.nCol + vc2]) & 0xffffu);
+    }
     // exclusive scan of `mine` over threads (thread order == CTA order)
     int incl = mine;
     const int lane = lane_id(), w = tid >> 5, nw = blockDim.x >> 5;
@@ -916,14 +930,17 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
     __syncthreads();
     int dst = s_warp[w] + incl - mine;
     for (int b = b0; b < b1; b++) {
-      const uint32_t d = b - b0 < 4 ? dsave[b - b0] : __ldcg(&D.rec_dir[(size_t)b * P.nCol + vc]);
-      const int c = (int)(d & 0xffffu);
-      const int src = b * F.tile_pts + (int)(d >> 16);
-      for (int r = 0; r < c; r++) {
-        if (big) D.rec_col[off + dst + r] = D.rec_lin[src + r];  // oversized column: materialise the records
-        else s_map[dst + r] = src + r;
+      for (int half = 0; half < (merged ? 2 : 1); half++) {
+        const int col = half ? vc2 : vc;
+        const uint32_t d = b - b0 < 4 ? (half ? dsave2[b - b0] : dsave[b - b0]) : __ldcg(&D.rec_dir[(size_t)b * P.nCol + col]);
+        const int c = (int)(d & 0xffffu);
+        const int src = b * F.tile_pts + (int)(d >> 16);
+        for (int r = 0; r < c; r++) {
+          if (big) D.rec_col[off + dst + r] = D.rec_lin[src + r];  // oversized column: materialise the records
+          else s_map[dst + r] = src + r;
+        }
+        dst += c;
       }
-      dst += c;
     }
   }
   __syncthreads();
@@ -1331,7 +1348,55 @@ __device__ __forceinline__ void column_phase(const MapParams &P, DeviceBuffers &
     if (my_active) atomicAdd(&s_nactive, my_active);
   }
   __syncthreads();
-  auto is_active = [&](int vc) { return sorted ? s_nrec[vc] > 0 : (D.phi_hist[vc] > 0 && !not_mine(vc)); };
+  // More active halves than CTAs would mean a second round of items, and even the lightest item costs ~15 us of
+  // barrier-separated phases: work the lightest columns whole instead (both halves as ONE item), as many as it takes
+  // to get down to one item per CTA; a LiDAR scan that lights every column ends up with whole columns only.
+  // s_nrec afterwards: > 0 half item, < 0 merged item (even slot, -records), kCovered odd slot of a merged column, 0 idle.
+  constexpr int kCovered = (int)0x80000000;
+  if (sorted && P.split && P.merge && s_nactive > (int)gridDim.x) {
+    __shared__ int s_mh[64];
+    __shared__ int s_T, s_sh2;
+    if (tid < 64) s_mh[tid] = 0;
+    if (tid == 0) {
+      int sh2 = 0;
+      while (((2 * s_wmax) >> sh2) > 63) sh2++;
+      s_sh2 = sh2;
+    }
+    __syncthreads();
+    const int sh2 = s_sh2, need = s_nactive - (int)gridDim.x;
+    for (int phi = tid; phi < P.nPhi; phi += blockDim.x)
+      if (s_nrec[2 * phi] > 0 && s_nrec[2 * phi + 1] > 0) atomicAdd(&s_mh[(s_wgt[2 * phi] + s_wgt[2 * phi + 1]) >> sh2], 1);
+    __syncthreads();
+    if (tid == 0) {
+      int cum = 0, T = 63;
+      for (int b = 0; b < 64; b++) {
+        cum += s_mh[b];
+        if (cum >= need) {
+          T = b;
+          break;
+        }
+      }
+      s_T = T;
+    }
+    __syncthreads();
+    int merged_here = 0;
+    for (int phi = tid; phi < P.nPhi; phi += blockDim.x) {
+      const int n0 = s_nrec[2 * phi], n1 = s_nrec[2 * phi + 1];
+      if (n0 > 0 && n1 > 0) {
+        const int w = s_wgt[2 * phi] + s_wgt[2 * phi + 1];
+        if ((w >> sh2) <= s_T) {
+          s_wgt[2 * phi] = w;
+          s_nrec[2 * phi] = -(n0 + n1);
+          s_nrec[2 * phi + 1] = kCovered;
+          merged_here++;
+          atomicMax(&s_wmax, w);
+        }
+      }
+    }
+    if (merged_here) atomicSub(&s_nactive, merged_here);
+    __syncthreads();
+  }
+  auto is_active = [&](int vc) { return sorted ? s_nrec[vc] != 0 : (D.phi_hist[vc] > 0 && !not_mine(vc)); };
   // idle work columns: their own rows of the miss bitmap are empty this frame (spread over the CTAs)
   for (int vc = blockIdx.x; vc < P.nCol; vc += gridDim.x) {
     if (is_active(vc)) continue;
@@ -1350,8 +1415,11 @@ __device__ __forceinline__ void column_phase(const MapParams &P, DeviceBuffers &
     uint64_t *q_src = s_keys + P.sort_cap_smem;           // second key buffer: sort input; output lands in the first
     uint64_t kq[8];
     int nk = 0;
-    for (int vc = tid; vc < P.nCol && nk < 8; vc += blockDim.x)
-      kq[nk++] = ((s_nrec[vc] > 0 ? (uint64_t)(63 - (s_wgt[vc] >> sh)) : 64ull) << 16) | (uint64_t)vc;
+    for (int vc = tid; vc < P.nCol && nk < 8; vc += blockDim.x) {
+      const int nr = s_nrec[vc];
+      const bool item = nr != 0 && nr != kCovered;
+      kq[nk++] = ((item ? (uint64_t)(63 - (s_wgt[vc] >> sh)) : 64ull) << 16) | (uint64_t)(nr < 0 ? P.nCol + (vc >> 1) : vc);
+    }
     __syncthreads();                                        // s_nrec / s_wgt are dead from here on
     nk = 0;
     for (int vc = tid; vc < P.nCol && nk < 8; vc += blockDim.x) q_src[vc] = kq[nk++];

@@ -907,6 +907,8 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   if (P.n_below < 1 || P.n_below >= P.nZ - 1 || P.nRho >= 4096 || 2 * P.nPhi > kMaxPhi) P.split = 0;
   if (const char *e = getenv("MLM_DEBUG_NO_SPLIT")) if (atoi(e)) P.split = 0;
   P.nCol = P.nPhi * (P.split ? 2 : 1);
+  P.merge = 1;
+  if (const char *e = getenv("MLM_DEBUG_NO_MERGE")) if (atoi(e)) P.merge = 0;
   // per end cell: the ray's slope and the z rows of its neighbour contributions, with the reference's arithmetic
   // (rate = (z - n_below) / (rho * 1.0); (int)round(z +/- d * rate)), src/map_awareness.cpp:64-71,151,161
   T.rate.resize((size_t)P.nZ * P.nRho);

@@ -42,6 +42,7 @@ struct MapParams {
   int col_words;          // nZ * words_per_row
   int cell_bits;          // bits of a cell id inside a column: ceil(log2(nZ*nRho))
   int split;              // 1: every phi column is worked as two half columns (records below / at-or-above the sensor row n_below)
+  int merge;              // 1: the column queue works the lightest columns whole when active halves outnumber the CTAs
   int nCol;               // work columns of k_column: nPhi * (split ? 2 : 1)
   uint32_t nRho_magic;    // ceil(2^32 / nRho): cell / nRho by multiply-high (cells < 2^20, nRho < 2^12)
   // local_map_cartesian members (include/map_local.h:66-78)
