@@ -282,7 +282,7 @@ typedef struct mlm_shard_exchange {
   int32_t n_hit_total;      /* distinct hit keys of the scan over all ranks */
   int32_t n_hit_local;      /* ... cast by this rank */
   int32_t records_received; /* update records this rank ingested (all sources) */
-  int32_t records_from_self;
+  int32_t records_from_self; /* -1: not tracked (sources reserve straight in the owner's inbox) */
   int32_t rehash_path;      /* 1: the scan took the rehash path */
   int64_t wait_ns;          /* time this rank's wait kernel spun for its peers */
   int64_t arena_bytes;      /* size of this rank's exchange arena */

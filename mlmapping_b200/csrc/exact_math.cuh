@@ -120,5 +120,20 @@ MLM_HD int vector_hash3(int a, int b, int c) {
 MLM_HD uint32_t libstdcxx_bucket(int h, uint32_t bucket_count) {
   return (uint32_t)((uint64_t)(int64_t)h % (uint64_t)bucket_count);
 }
+// same value with 32-bit arithmetic only: c64 = 2^64 mod bucket_count (host-computed per frame).  For h < 0 the size_t is
+// 2^64 - a with a = -h in [1, 2^31], so the bucket is (c64 - a mod B) mod B.
+MLM_HD uint32_t libstdcxx_bucket_fast(int h, uint32_t bucket_count, uint32_t c64) {
+  if (h >= 0) return (uint32_t)h % bucket_count;
+  const uint32_t r = (0u - (uint32_t)h) % bucket_count;
+  return c64 >= r ? c64 - r : c64 + (bucket_count - r);
+}
+
+// x / d for x < 2^31 by multiply-high; (mul, shift) from make_div_magic on the host; mul == 0 means d == 1
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t mul, int shift) { return mul ? (__umulhi(x, mul) >> shift) : x; }
+// floor(c / n) for |c| < 2^26 and n <= 64: bias into the non-negative range first
+__device__ __forceinline__ int fast_floor_div(int c, int n, uint32_t mul, int shift) {
+  const int bias_q = 1 << 21;
+  return (int)fast_div((uint32_t)(c + n * bias_q), mul, shift) - bias_q;
+}
 
 }  // namespace mlm

@@ -1128,7 +1128,7 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
         D.hit_p[idx] = __uint_as_float(s_dec[s_head[k]]);
         D.hit_t[idx] = stamp;
         // bucket activation stamp (libstdc++ iteration order)
-        const uint32_t bucket = libstdcxx_bucket(vector_hash3(rk, phi, zk), F.bucket_count);
+        const uint32_t bucket = libstdcxx_bucket_fast(vector_hash3(rk, phi, zk), F.bucket_count, F.bucket_c64);
         D.hit_bucket[idx] = bucket;
         atomicMin(&act[bucket], stamp);
         // p_w = T_wa * centre  (identity rotation: one add per axis), src/map_local.cpp:151
@@ -1348,14 +1348,14 @@ __device__ __forceinline__ void column_phase(const MapParams &P, DeviceBuffers &
     if (my_active) atomicAdd(&s_nactive, my_active);
   }
   __syncthreads();
-  // More active halves than CTAs would mean a second round of items, and even the lightest item costs ~15 us of
-  // barrier-separated phases: work the lightest columns whole instead (both halves as ONE item), as many as it takes
-  // to get down to one item per CTA; a LiDAR scan that lights every column ends up with whole columns only.
+  // More active halves than CTAs would mean another round of items, and even the lightest item costs ~15 us of
+  // barrier-separated phases: work the lightest columns whole instead (both halves as ONE item), as many as it takes to
+  // get down to one item per CTA.  The heavy columns stay split: the heaviest item bounds the phase.
   // s_nrec afterwards: > 0 half item, < 0 merged item (even slot, -records), kCovered odd slot of a merged column, 0 idle.
   constexpr int kCovered = (int)0x80000000;
   if (sorted && P.split && P.merge && s_nactive > (int)gridDim.x) {
     __shared__ int s_mh[64];
-    __shared__ int s_T, s_sh2;
+    __shared__ int s_T, s_sh2, s_need;
     if (tid < 64) s_mh[tid] = 0;
     if (tid == 0) {
       int sh2 = 0;
@@ -1363,13 +1363,19 @@ __device__ __forceinline__ void column_phase(const MapParams &P, DeviceBuffers &
       s_sh2 = sh2;
     }
     __syncthreads();
-    const int sh2 = s_sh2, need = s_nactive - (int)gridDim.x;
+    const int sh2 = s_sh2;
     for (int phi = tid; phi < P.nPhi; phi += blockDim.x)
       if (s_nrec[2 * phi] > 0 && s_nrec[2 * phi + 1] > 0) atomicAdd(&s_mh[(s_wgt[2 * phi] + s_wgt[2 * phi + 1]) >> sh2], 1);
     __syncthreads();
     if (tid == 0) {
-      int cum = 0, T = 63;
-      for (int b = 0; b < 64; b++) {
+      int c2 = 0;
+      for (int b = 0; b < 64; b++) c2 += s_mh[b];                       // columns with both halves active
+      // down to one item per CTA if that is possible, else every column whole: with more than one round the total work
+      // decides, and a whole column costs less than its two halves (measured on CFG-C: 360 whole items 175 us, 276 whole
+      // + 168 halves 193 us, 720 halves 210 us)
+      const int need = min(c2, s_nactive - (int)gridDim.x);
+      int cum = 0, T = -1;
+      for (int b = 0; b < 64 && need > 0; b++) {
         cum += s_mh[b];
         if (cum >= need) {
           T = b;
@@ -1377,14 +1383,31 @@ __device__ __forceinline__ void column_phase(const MapParams &P, DeviceBuffers &
         }
       }
       s_T = T;
+      s_need = need;
     }
     __syncthreads();
+    const int need = s_need;
+    // exactly `need` columns: every candidate below the threshold bucket, and of the threshold bucket itself the first
+    // ones in column order (columns of a LiDAR scan weigh alike: a whole bucket would merge the heavy ones too, and the
+    // heaviest item bounds the phase)
+    int *s_rank = reinterpret_cast<int *>(s_keys + P.sort_cap_smem);   // second key buffer, idle until the queue sort
+    int below = 0;
+    for (int b = 0; b < s_T; b++) below += s_mh[b];
+    const int take = need - below;                                        // how many of bucket s_T to merge (s_T < 0: none at all)
+    for (int phi = tid; phi < P.nPhi; phi += blockDim.x) {
+      const int n0 = s_nrec[2 * phi], n1 = s_nrec[2 * phi + 1];
+      s_rank[phi] = (n0 > 0 && n1 > 0 && ((s_wgt[2 * phi] + s_wgt[2 * phi + 1]) >> sh2) == s_T) ? 1 : 0;
+    }
+    __syncthreads();
+    __shared__ int s_scan_warp[33];
+    block_exclusive_scan(s_rank, P.nPhi, s_scan_warp);
     int merged_here = 0;
     for (int phi = tid; phi < P.nPhi; phi += blockDim.x) {
       const int n0 = s_nrec[2 * phi], n1 = s_nrec[2 * phi + 1];
       if (n0 > 0 && n1 > 0) {
         const int w = s_wgt[2 * phi] + s_wgt[2 * phi + 1];
-        if ((w >> sh2) <= s_T) {
+        const int bkt = w >> sh2;
+        if (bkt < s_T || (bkt == s_T && s_rank[phi] < take)) {
           s_wgt[2 * phi] = w;
           s_nrec[2 * phi] = -(n0 + n1);
           s_nrec[2 * phi + 1] = kCovered;
@@ -1520,14 +1543,21 @@ __device__ __forceinline__ void fuse_body(const MapParams &P, DeviceBuffers &D, 
   const int fw_ = (int)(threadIdx.x >> 5), fl_ = (int)(threadIdx.x & 31);
   for (int i = ((fw_ * (int)gridDim.x + (int)blockIdx.x) << 5) + fl_; i < n; i += (int)gridDim.x * (int)blockDim.x) {
     const uint32_t e = D.touched[i];
+    if (e == 0xffffffffu) continue;  // sharded ingest: a record whose voxel was staged by an earlier record
     const int lv = (int)(e & ~kTouchedHitTag);
     // subbox of this cell (independent of the claim below, so its load overlaps the atomic)
-    int c[3] = {lv % dxy + F.lvg_base[0], (lv / dxy) % dxy + F.lvg_base[1], lv / (dxy * dxy) + F.lvg_base[2]};
-    int g[3], sub;
+    int c[3], g[3], sub;
     {
+      // lv -> (x, y, z) of the voxel grid and the subbox split, all by multiply-high (no integer division on this path)
+      const int lz = (int)fast_div((uint32_t)lv, P.dxy2_mul, P.dxy2_shift);
+      const int rem = lv - lz * dxy * dxy;
+      const int ly = (int)fast_div((uint32_t)rem, P.dxy_mul, P.dxy_shift);
+      c[0] = rem - ly * dxy + F.lvg_base[0];
+      c[1] = ly + F.lvg_base[1];
+      c[2] = lz + F.lvg_base[2];
       int l[3];
       for (int a = 0; a < 3; a++) {
-        g[a] = floor_div(c[a], P.n);
+        g[a] = fast_floor_div(c[a], P.n, P.n_mul, P.n_shift);
         l[a] = c[a] - g[a] * P.n;
       }
       sub = (l[2] * P.n + l[1]) * P.n + l[0];
@@ -1669,14 +1699,23 @@ __device__ __forceinline__ void fuse_body(const MapParams &P, DeviceBuffers &D, 
     if (P.explore && (became_o || became_f))
       atomicAnd(&D.pool_front[(size_t)block * P.front_words + (sub >> 5)], ~(1u << (sub & 31)));
   }
-  // counters
+  // counters: warp shuffle, then shared memory, then ONE global atomic per CTA and counter (thousands of same-address
+  // atomics, one per warp, are paid for at a few ns each at the kernel's end)
+  __shared__ int s_ctr[2];
+  if (threadIdx.x < 2) s_ctr[threadIdx.x] = 0;
+  __syncthreads();
   for (int ofs = 16; ofs > 0; ofs >>= 1) {
     my_touched += __shfl_xor_sync(0xffffffffu, my_touched, ofs);
     my_obs += __shfl_xor_sync(0xffffffffu, my_obs, ofs);
   }
   if (lane_id() == 0) {
-    if (my_touched) atomicAdd(&fc->n_touched_voxels, my_touched);
-    if (my_obs) atomicAdd(&fc->obs_delta, my_obs);
+    if (my_touched) atomicAdd(&s_ctr[0], my_touched);
+    if (my_obs) atomicAdd(&s_ctr[1], my_obs);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_ctr[0]) atomicAdd(&fc->n_touched_voxels, s_ctr[0]);
+    if (s_ctr[1]) atomicAdd(&fc->obs_delta, s_ctr[1]);
   }
   if (kPhase == 1) return;  // the miss phase finishes the frame
   if (blockIdx.x == 0 && threadIdx.x == 0) fc->fused = 1;

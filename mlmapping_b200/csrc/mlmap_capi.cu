@@ -151,6 +151,21 @@ struct GlibcRand {
   }
 };
 
+// x / d == umulhi(x, mul) >> shift for every x < 2^31 (round-up method, checked in tests/test_host_logic.py); d == 1 -> mul 0
+void make_div_magic(uint32_t d, uint32_t *mul, int *shift) {
+  if (d < 2) {
+    *mul = 0;
+    *shift = 0;
+    return;
+  }
+  int sh = 0;
+  while ((2u << sh) <= d - 1) sh++;  // floor(log2(d - 1))
+  *shift = sh;
+  *mul = (uint32_t)(((1ull << (32 + sh)) / (uint64_t)d) + 1);
+}
+// 2^64 mod B (see libstdcxx_bucket_fast)
+uint32_t pow64_mod(uint32_t B) { return (uint32_t)((((unsigned __int128)1) << 64) % (unsigned __int128)B); }
+
 int next_pow2(int n) {
   int p = 1;
   while (p < n) p <<= 1;
@@ -435,6 +450,7 @@ int run_frame_explore(mlm_map *h, int mode, int N, mlm_frame_stats *stats) {
       int rc = order_slow_path(h, mid.n_hit, 0, h->bucket_count, &order_B);
       if (rc != MLM_OK) return rc;
       F.bucket_count = order_B;
+      F.bucket_c64 = pow64_mod(F.bucket_count);
     }
     if ((uint32_t)mid.n_miss_list > h->bucket_count_miss) {
       slow = 1;
@@ -504,6 +520,7 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
   F.n_points = n_points;
   F.n_total = N;
   F.bucket_count = h->bucket_count;
+  F.bucket_c64 = pow64_mod(F.bucket_count);
   F.bucket_count_miss = h->bucket_count_miss;
   const int parity = (int)(h->frame_idx & 1);
   h->frame_idx++;
@@ -532,7 +549,7 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
     F.stage_only = 1;
     F.order_mode = 1;
     const int pg = grid_for((size_t)std::max(N, 1), kProjThreads * 2);
-    if (F.bucket_count == 1) F.bucket_count = 13;  // the first insert of an empty table allocates 13 buckets before anything is ordered
+    if (F.bucket_count == 1) F.bucket_count = 13, F.bucket_c64 = pow64_mod(13);  // the first insert of an empty table allocates 13 buckets before anything is ordered
     k_project<0><<<pg, kProjThreads, project_smem_bytes(P.nCol, kProjThreads), s>>>(P, h->D, F);
     if (h->profiling && h->sev[2]) cudaEventRecord(h->sev[2], s);
     k_column<<<h->col_grid, kColThreads, h->col_smem_bytes, s>>>(P, h->D, F);
@@ -648,6 +665,7 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
     if (rc != MLM_OK) return rc;
     order_B = Bf;
     F.bucket_count = Bf;
+    F.bucket_c64 = pow64_mod(F.bucket_count);
     F.order_mode = 1;
     k_fuse<0><<<h->sm_count * 4, 256, 0, s>>>(P, h->D, F);
     h->launches += 1;
@@ -963,6 +981,9 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   const double R = P.nRho * P.dRho;
   P.lvg_dim_xy = (int)ceil(2 * R / P.d_sub) + 2 * P.lvg_margin + 2;
   P.lvg_dim_z = (int)ceil(P.nZ * P.dZ / P.d_sub) + 2 * P.lvg_margin + 2;
+  make_div_magic((uint32_t)P.lvg_dim_xy, &P.dxy_mul, &P.dxy_shift);
+  make_div_magic((uint32_t)P.lvg_dim_xy * (uint32_t)P.lvg_dim_xy, &P.dxy2_mul, &P.dxy2_shift);
+  make_div_magic((uint32_t)P.n, &P.n_mul, &P.n_shift);
   P.lsg_dim_xy = P.lvg_dim_xy / P.n + 3;
   P.lsg_dim_z = P.lvg_dim_z / P.n + 3;
   const long long n_cells = (long long)P.nZ * P.nPhi * P.nRho;
@@ -2065,12 +2086,12 @@ int shard_enqueue(mlm_handle h, const double *d_xyz, int n, const double T_wb[7]
   MLM_HT();
   MLM_SMARK(0);
   if (h2d_src && n > 0) CUDA_TRY(cudaMemcpyAsync(h->d_input, h2d_src, (size_t)n * 24, cudaMemcpyHostToDevice, s));
-  // stale activation stamps of earlier scans must not survive: the staging kernels atomicMin into this buffer
-  CUDA_TRY(cudaMemsetAsync(h->D.act[parity_next], 0xff, (size_t)h->act_cap * 4, s));
-  CUDA_TRY(cudaMemsetAsync(h->d_shard_cursor, 0, (kMaxWorld + 2) * sizeof(int), s));  // sent[], skip flag, push ticket
-  // the inbox cursor of the PREVIOUS scan's parity: its records are ingested, and no source can reserve in it again before
-  // it has seen this scan's flag (raised further down this stream)
-  CUDA_TRY(cudaMemsetAsync(X.a[X.rank].cursor + (par ^ 1), 0, sizeof(int), s));
+  // resets of the scan in one launch (only the buckets in use: the count can at most step up the growth chain on a rehash
+  // scan, which refills the array itself)
+  const uint32_t B_now = std::min<uint32_t>(h->bucket_count == 1 ? 13u : h->bucket_count, h->act_cap);
+  k_shard_begin<<<std::min(h->sm_count * 2, grid_for(B_now, 256)), 256, 0, s>>>(h->D.act[parity_next], B_now, h->d_shard_cursor, kMaxWorld + 2,
+                                                                            X.a[X.rank].cursor + (par ^ 1));
+  h->launches++;
   MLM_SMARK(1);
   MLM_HT();
   h->shard_stage_pending = true;
@@ -2082,7 +2103,8 @@ int shard_enqueue(mlm_handle h, const double *d_xyz, int n, const double T_wb[7]
   FrameParams F = *h->h_fp;  // as the staging kernels saw it (bucket_count already lifted from 1 to 13)
   int *skip = h->d_shard_cursor + kMaxWorld;
   const int G = h->sm_count * 2;
-  k_shard_push<<<G * 2, 256, 0, s>>>(X, h->P, h->D, F, par, h->d_shard_cursor, epoch);
+  // latency-bound list walks; one reservation (a same-address atomic per destination) per 1024 list entries
+  k_shard_push<<<h->sm_count * 2, kPushThreads, 0, s>>>(X, h->P, h->D, F, par, h->d_shard_cursor, epoch);
   MLM_SMARK(4);
   // owner side (all of it returns at once when the wait at the head of k_shard_act found a rehash scan or an error)
   F.stage_only = 0;
@@ -2094,9 +2116,9 @@ int shard_enqueue(mlm_handle h, const double *d_xyz, int n, const double T_wb[7]
   // most SMs to the other ranks' staging kernels
   k_shard_act<<<h->shard_shares_device ? 32 : G, 256, 0, s>>>(X, h->P, h->D, F, par, epoch, h->d_shard_state, skip, h->shard_timeout_ns, h->D.act[F.parity]);
   MLM_SMARK(5);
-  k_shard_ingest<<<G * 2, 256, 0, s>>>(X, h->P, h->D, F, par, h->d_shard_state, skip, nullptr);
+  k_shard_ingest<<<h->sm_count * 8, 256, 0, s>>>(X, h->P, h->D, F, par, h->d_shard_state, skip, nullptr);
   MLM_SMARK(6);
-  k_fuse<0><<<h->sm_count * 4, 256, 0, s>>>(h->P, h->D, F);
+  k_fuse<0><<<h->sm_count * 5, 256, 0, s>>>(h->P, h->D, F);
   MLM_SMARK(7);
 #undef MLM_SMARK
   h->launches += 4;
@@ -2177,6 +2199,7 @@ int shard_rehash_path(mlm_handle h, const ShardState &st, uint32_t *B_out) {
   F.skip_flag = nullptr;
   F.inline_resolve = 1;
   F.bucket_count = Bs;
+  F.bucket_c64 = pow64_mod(F.bucket_count);
   const int G = h->sm_count * 2;
   k_shard_ingest<<<G * 2, 256, 0, s>>>(X, h->P, h->D, F, par, h->d_shard_state, nullptr, h->d_key_stamp);
   k_fuse<0><<<h->sm_count * 4, 256, 0, s>>>(h->P, h->D, F);
@@ -2410,7 +2433,7 @@ int mlm_shard_last_exchange(mlm_handle h, mlm_shard_exchange *out) {
   out->n_hit_total = st.n_total;
   out->n_hit_local = st.cnt_hits[h->shard_rank];
   out->records_received = st.n_rec_total;
-  out->records_from_self = st.cnt_recs[h->shard_rank];
+  out->records_from_self = -1;  // not tracked: sources reserve straight in the owner's inbox
   out->rehash_path = st.rehash;
   out->wait_ns = (int64_t)st.wait_ns;
   out->world = h->shard_world;

@@ -67,6 +67,12 @@ __device__ __forceinline__ uint32_t cell_bucket(const MapParams &P, int key, uin
   int pk = rem / P.nRho, rk = rem - pk * P.nRho;
   return libstdcxx_bucket(vector_hash3(rk, pk, zk), B);
 }
+// hit-map bucket at the frame's bucket count, 32-bit arithmetic only (c64 = 2^64 mod B from the host)
+__device__ __forceinline__ uint32_t hit_bucket_fast(const MapParams &P, int key, uint32_t B, uint32_t c64) {
+  const int zk = key / (P.nRho * P.nPhi), rem = key - zk * (P.nRho * P.nPhi);
+  const int pk = rem / P.nRho, rk = rem - pk * P.nRho;
+  return libstdcxx_bucket_fast(vector_hash3(rk, pk, zk), B, c64);
+}
 struct OrderArrays {
   const int *key;      // awareness cell index of every element
   uint32_t *stamp;     // in: first-insert stamps; out (slow path): virtual positions

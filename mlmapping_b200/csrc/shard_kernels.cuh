@@ -46,16 +46,17 @@ struct ShardState {
   int rehash;             // 1: n_total exceeds the bucket count -> the owner-side kernels skipped, host runs the rehash path
   int error;              // device error code (peer failure, timeout, capacity)
   int cnt_hits[kMaxWorld];
-  int cnt_recs[kMaxWorld];
   unsigned long long wait_ns;  // time the wait kernel spent spinning (exchange skew seen by this rank)
 };
 constexpr int kErrPeer = 101;  // a peer did not signal in time / reported a failure
 
 __device__ __forceinline__ int owner_of(const MapParams &P, const int c[3], int world) {
-  int g[3] = {floor_div(c[0], P.n), floor_div(c[1], P.n), floor_div(c[2], P.n)};
+  int g[3] = {fast_floor_div(c[0], P.n, P.n_mul, P.n_shift), fast_floor_div(c[1], P.n, P.n_mul, P.n_shift),
+              fast_floor_div(c[2], P.n, P.n_mul, P.n_shift)};
   uint64_t key;
   if (!pack_glb(g, key)) return 0;
-  return (int)(ht_hash(key) % (uint32_t)world);
+  const uint32_t hsh = ht_hash(key);
+  return (world & (world - 1)) == 0 ? (int)(hsh & (uint32_t)(world - 1)) : (int)(hsh % (uint32_t)world);
 }
 
 // CTA-wide slot reservation: every thread asks for `want` (0 or more) consecutive slots of a global counter; one
@@ -90,21 +91,37 @@ __device__ __forceinline__ int cta_reserve(int *ctr, int want, int *s_warp /*[33
   return res;
 }
 
+// start of a scan: everything the staging and the push kernels expect to find reset, in one launch
+//   act[0, B)        activation stamps the staging kernels atomicMin into (stale stamps of earlier scans must not survive)
+//   scratch[...]     push ticket and skip flag
+//   cursor_prev      the inbox cursor of the PREVIOUS scan's parity: its records are ingested, and no source can reserve in
+//                    it again before it has seen this scan's flag (raised further down this stream)
+__global__ void __launch_bounds__(256) k_shard_begin(uint32_t *act, uint32_t B, int *scratch, int n_scratch, int *cursor_prev) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (uint32_t i = gtid; i < B; i += nth) act[i] = 0xffffffffu;
+  if (gtid < n_scratch) scratch[gtid] = 0;
+  if (gtid == 0) *cursor_prev = 0;
+}
+
+constexpr int kPushThreads = 1024;  // list entries per chunk = per reservation in the destinations' inboxes
+constexpr int kPushStage = 1792;   // records a CTA chunk stages in shared memory (42 KB)
 // ---- source side: ONE kernel per scan pushes everything this rank has for the others ----------------------------
 // (1) all-gather of the rank's distinct hit keys + stamps: written into every rank's gather region for this source;
 // (2) all-to-all of the update records: one thread per touched-list entry; records of a CTA chunk are grouped by
 //     destination in shared memory, each group reserves its slots in the DESTINATION's inbox with one atomicAdd on that
-//     rank's cursor (a remote atomic over NVLink for a peer: one per 256 list entries and destination) and is then
-//     written there with plain stores.  A voxel with hits and misses has two list entries: the hit entry handles both.
+//     rank's cursor (a remote atomic over NVLink for a peer: one per 1024 list entries and destination; same-address
+//     atomics complete at a few ns each, so their number, not their latency, is what a scan pays for) and is then
+//     written there with coalesced stores.  A voxel with hits and misses has two list entries: the hit entry handles both.
 //     Clears the local staging it consumes;
 // (3) the last CTA (completion ticket) publishes the counts to every destination's mailbox, makes everything visible
 //     system-wide and raises this source's epoch flag in every arena, then rearms the local staging counters for the
 //     owner-side ingest.
-__global__ void __launch_bounds__(256) k_shard_push(ShardPeers X, MapParams P, DeviceBuffers D, FrameParams F, int par,
-                                                    int *sent /*[kMaxWorld] records per destination; [kMaxWorld + 1] ticket*/,
-                                                    uint32_t epoch) {
+__global__ void __launch_bounds__(kPushThreads) k_shard_push(ShardPeers X, MapParams P, DeviceBuffers D, FrameParams F, int par,
+                                                             int *sent /*[kMaxWorld + 1] is the completion ticket*/, uint32_t epoch) {
   __shared__ int s_cnt[kMaxWorld];
   __shared__ int s_base[kMaxWorld];
+  __shared__ int s_goff[kMaxWorld + 1];
+  __shared__ ShardRecord s_stage[kPushStage];
   __shared__ int s_last;
   FrameCounters *fc = D.fc[F.parity];
   const int world = X.world;
@@ -139,9 +156,12 @@ __global__ void __launch_bounds__(256) k_shard_push(ShardPeers X, MapParams P, D
       if ((e & kTouchedHitTag) || st.x == kLvgEmpty) {  // the entry that owns the voxel
         head = st.x;
         mc = st.y;
-        c[0] = lv % dxy + F.lvg_base[0];
-        c[1] = (lv / dxy) % dxy + F.lvg_base[1];
-        c[2] = lv / (dxy * dxy) + F.lvg_base[2];
+        const int lz = (int)fast_div((uint32_t)lv, P.dxy2_mul, P.dxy2_shift);
+        const int rem = lv - lz * dxy * dxy;
+        const int ly = (int)fast_div((uint32_t)rem, P.dxy_mul, P.dxy_shift);
+        c[0] = rem - ly * dxy + F.lvg_base[0];
+        c[1] = ly + F.lvg_base[1];
+        c[2] = lz + F.lvg_base[2];
         dest = owner_of(P, c, world);
         for (int h = head; h != kLvgEmpty; h = D.hit_next[h]) nrec++;
         if (mc > 0) nrec++;
@@ -149,17 +169,26 @@ __global__ void __launch_bounds__(256) k_shard_push(ShardPeers X, MapParams P, D
       }
     }
     __syncthreads();
-    if (threadIdx.x < world && s_cnt[threadIdx.x]) {
-      s_base[threadIdx.x] = atomicAdd(X.a[threadIdx.x].cursor + par, s_cnt[threadIdx.x]);
-      atomicAdd(&sent[threadIdx.x], s_cnt[threadIdx.x]);
+    if (threadIdx.x < world && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(X.a[threadIdx.x].cursor + par, s_cnt[threadIdx.x]);
+    // records go to shared memory first, grouped by destination, and leave as contiguous runs of coalesced 8-byte
+    // stores (scattered 24-byte records written thread by thread cost 60 us per scan over NVLink)
+    if (threadIdx.x == 32) {
+      int acc = 0;
+      for (int d = 0; d < world; d++) {
+        s_goff[d] = acc;
+        acc += s_cnt[d];
+      }
+      s_goff[world] = acc;
     }
     __syncthreads();
+    const int chunk_total = s_goff[world];
+    const bool staged = chunk_total <= kPushStage;   // a chunk with unusually long hit lists writes straight through
     if (dest >= 0) {
       const int first = s_base[dest] + rank_in_cta;
       if (first + nrec > X.rec_cap) {
         fc->error = kErrCapacity;
       } else {
-        ShardRecord *o = X.a[dest].inbox + (size_t)par * X.rec_cap + first;
+        ShardRecord *o = staged ? s_stage + s_goff[dest] + rank_in_cta : X.a[dest].inbox + (size_t)par * X.rec_cap + first;
         for (int h = head; h != kLvgEmpty; h = D.hit_next[h]) {
           ShardRecord r;
           r.c[0] = c[0];
@@ -186,18 +215,32 @@ __global__ void __launch_bounds__(256) k_shard_push(ShardPeers X, MapParams P, D
       D.lvg[lv] = make_int2(kLvgEmpty, 0);
     }
     __syncthreads();
+    if (staged) {
+      const int2 *src = reinterpret_cast<const int2 *>(s_stage);
+      for (int d = 0; d < world; d++) {
+        const int cnt = s_cnt[d];
+        if (cnt == 0 || s_base[d] + cnt > X.rec_cap) continue;
+        int2 *dst = reinterpret_cast<int2 *>(X.a[d].inbox + (size_t)par * X.rec_cap + s_base[d]);
+        const int2 *sd = src + 3 * s_goff[d];
+        for (int q = threadIdx.x; q < 3 * cnt; q += blockDim.x) dst[q] = sd[q];
+      }
+    }
+    __syncthreads();
   }
-  // (3) every thread orders its own (remote) stores system-wide, the CTA's last arrival takes a ticket
-  __threadfence_system();
+  // (3) ONE system-scope fence per CTA, after the CTA barrier: fences are cumulative, so it orders the (remote) stores of
+  // every thread of the CTA (a fence.sys in every thread serialises inside the SM: ~40 us per scan); then the ticket
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(&sent[kMaxWorld + 1], 1) == (int)gridDim.x - 1;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = atomicAdd(&sent[kMaxWorld + 1], 1) == (int)gridDim.x - 1;
+  }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
   const int d = threadIdx.x;
   if (d < world) {
     const bool failed = __ldcg(&fc->error) != 0;
-    X.a[d].mbox[par * kMaxWorld + X.rank] = make_int2(failed ? -1 : n_hit, failed ? -1 : __ldcg(&sent[d]));
+    X.a[d].mbox[par * kMaxWorld + X.rank] = make_int2(failed ? -1 : n_hit, failed ? -1 : 0);
     __threadfence_system();
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(X.a[d].flags + X.rank), "r"(epoch) : "memory");
   }
@@ -247,12 +290,12 @@ __device__ __forceinline__ bool shard_wait(const ShardPeers &X, DeviceBuffers &D
         m = make_int2(0, 0);
       }
       s_st->cnt_hits[r] = m.x;
-      s_st->cnt_recs[r] = m.y;
       n_total += m.x;
-      n_rec += m.y;
     }
     // every source has reserved and written all its records: the cursor is the number of records to ingest
-    if (!err && __ldcg(X.a[X.rank].cursor + par) != n_rec) err = kErrCapacity;  // a source ran past rec_cap
+    n_rec = __ldcg(X.a[X.rank].cursor + par);
+    if (!err && n_rec > X.rec_cap) err = kErrCapacity;  // a source ran past rec_cap (it flagged its own error too)
+    if (err) n_rec = 0;
     const int local_err = __ldcg(&fc->error);
     if (local_err) err = local_err;
     s_st->n_total = n_total;
@@ -287,24 +330,36 @@ __global__ void __launch_bounds__(256) k_shard_act(ShardPeers X, MapParams P, De
     const int n = s_st.cnt_hits[src];
     const size_t region = ((size_t)par * X.world + src) * X.hit_cap;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-      atomicMin(&act[cell_bucket(P, __ldcg(A.gather_key + region + i), B, 0)], __ldcg(A.gather_stamp + region + i));
+      atomicMin(&act[hit_bucket_fast(P, __ldcg(A.gather_key + region + i), B, F.bucket_c64)], __ldcg(A.gather_stamp + region + i));
   }
 }
 
 // owner side: received records -> hit arrays + voxel-grid staging (the role k_column's staging plays on one GPU).
-// Slots of the hit list and of the touched list are reserved once per CTA and 256 records; the first toucher of a
-// subbox resolves / allocates it on the spot (F.inline_resolve, as in k_frame).
+// No list-building atomics: record i of the inbox owns slot i of the frame's touched list (an invalid marker when the
+// voxel was staged before) and, while the inbox fits the hit list, slot i of the hit arrays; k_fuse skips the markers.
+// The first toucher of a subbox resolves / allocates it on the spot (F.inline_resolve, as in k_frame).
+constexpr uint32_t kTouchedNone = 0xffffffffu;
 __global__ void __launch_bounds__(256) k_shard_ingest(ShardPeers X, MapParams P, DeviceBuffers D, FrameParams F, int par,
                                                       const ShardState *st, const int *skip, const uint32_t *key_stamp) {
   __shared__ int s_warp[33];
   if (skip && *skip) return;
   FrameCounters *fc = D.fc[F.parity];
   const int n = st->n_rec_total;
+  if (n > P.max_touched) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) fc->error = kErrCapacity;
+    return;
+  }
+  const bool dense_hits = n <= P.max_hits;   // uniform over the grid
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    fc->n_touched = n;
+    if (dense_hits) fc->n_hit = n;
+  }
   const int2 *rec = reinterpret_cast<const int2 *>(X.a[X.rank].inbox + (size_t)par * X.rec_cap);
   for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
     const int i = base + threadIdx.x;
     const bool valid = i < n;
     ShardRecord r;
+    r.key = -1;
     int lv = -1;
     CellRef cr;
     if (valid) {
@@ -317,16 +372,16 @@ __global__ void __launch_bounds__(256) k_shard_ingest(ShardPeers X, MapParams P,
       r.count = c.y;
       for (int k = 0; k < 3; k++) {
         cr.c[k] = r.c[k];
-        cr.g[k] = floor_div(r.c[k], P.n);
+        cr.g[k] = fast_floor_div(r.c[k], P.n, P.n_mul, P.n_shift);
       }
       lv = lvg_index(P, F, cr);
       if (lv < 0) fc->error = kErrInternal;
     }
     const bool is_hit = valid && lv >= 0 && r.key >= 0;
     const bool is_miss = valid && lv >= 0 && r.key < 0;
-    const int idx = cta_reserve(&fc->n_hit, is_hit ? 1 : 0, s_warp);
-    bool new_voxel = false;
-    uint32_t tag = 0;
+    int idx = i;
+    if (!dense_hits) idx = cta_reserve(&fc->n_hit, is_hit ? 1 : 0, s_warp);   // CTA-uniform branch
+    uint32_t entry = kTouchedNone;
     if (is_hit) {
       if (idx >= P.max_hits) {
         fc->error = kErrCapacity;
@@ -334,20 +389,18 @@ __global__ void __launch_bounds__(256) k_shard_ingest(ShardPeers X, MapParams P,
         D.hit_key[idx] = r.key;
         D.hit_p[idx] = r.p;
         D.hit_t[idx] = key_stamp ? key_stamp[r.key] : (uint32_t)r.count;  // rehash scans: virtual position from the global order
-        D.hit_bucket[idx] = cell_bucket(P, r.key, F.bucket_count, 0);
+        D.hit_bucket[idx] = hit_bucket_fast(P, r.key, F.bucket_count, F.bucket_c64);
         const int old = atomicExch(&D.lvg[lv].x, idx);
         D.hit_next[idx] = old;
-        new_voxel = old == kLvgEmpty;
-        tag = kTouchedHitTag;
+        if (old == kLvgEmpty) entry = (uint32_t)lv | kTouchedHitTag;
       }
     } else if (is_miss) {
-      new_voxel = atomicAdd(&D.lvg[lv].y, r.count) == 0;
+      if (atomicAdd(&D.lvg[lv].y, r.count) == 0) entry = (uint32_t)lv;
     }
-    const int tp = cta_reserve(&fc->n_touched, new_voxel ? 1 : 0, s_warp);
-    if (new_voxel) {
-      if (tp < P.max_touched) D.touched[tp] = (uint32_t)lv | tag; else fc->error = kErrCapacity;
+    if (valid) {
+      D.touched[i] = entry;
+      if (lv >= 0) touch_subbox(P, F, D, fc, cr.g);
     }
-    if (valid && lv >= 0) touch_subbox(P, F, D, fc, cr.g);
   }
 }
 

@@ -65,6 +65,9 @@ struct MapParams {
   int lvg_dim_xy, lvg_dim_z;   // cells per axis
   int lvg_margin;              // cells between awareness bounding box and grid border
   int lsg_dim_xy, lsg_dim_z;   // local submap grid dims
+  // division by the grid dimensions / subbox size by multiply-high (x / d == umulhi(x, mul) >> shift for x < 2^31; mul 0: d == 1)
+  uint32_t dxy_mul, dxy2_mul, n_mul;
+  int dxy_shift, dxy2_shift, n_shift;
   // capacities
   int max_points;
   int max_hits;           // capacity of the per-frame hit list
@@ -95,6 +98,7 @@ struct FrameParams {
   int n_points;     // point-cloud input
   int n_total;      // rows*cols or n_points: number of input slots this frame
   uint32_t bucket_count;  // emulated hit_idx_odds_hashmap.bucket_count() at frame start
+  uint32_t bucket_c64;    // 2^64 mod bucket_count: libstdc++'s bucket of a NEGATIVE int hash (sign-extended to size_t) without a 64-bit modulo
   int lvg_base[3];  // global cell coordinate of local voxel grid origin
   int lsg_base[3];  // global subbox coordinate of local submap grid origin
   int tbits;        // bits needed for a point stamp this frame (ceil(log2(#points)))

@@ -86,3 +86,37 @@ def test_pose_forwarding_matches_the_callback_and_the_oracle():
         a, b = compensate_pose(pos, q, v, w, go, gi, lat), oracle(list(pos), list(q), list(v), list(w), go, gi, lat)
         assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), (i, a, b)
         assert abs(np.linalg.norm(a[3:]) - 1) < 1e-15
+
+
+def test_multiply_high_division_and_bucket_shortcut():
+    """host-built constants of the device's division-free paths (mlmap_capi.cu make_div_magic / pow64_mod):
+    x / d == umulhi(x, mul) >> shift for every x < 2^31, and libstdc++'s bucket of a negative int hash
+    ((size_t)(int64)h % B) from 32-bit arithmetic with c64 = 2^64 mod B"""
+    rs = np.random.RandomState(7)
+
+    def magic(d):
+        sh = 0
+        while (2 << sh) <= d - 1:
+            sh += 1
+        return ((1 << (32 + sh)) // d) + 1, sh
+
+    for d in [2, 3, 7, 10, 16, 64, 154, 155, 524, 154 * 154, 524 * 524, 1000003, 2 ** 20 + 1, 2 ** 30 - 1]:
+        mul, sh = magic(d)
+        assert mul < 2 ** 32
+        xs = np.concatenate([rs.randint(0, 2 ** 31, 200000, dtype=np.int64), np.arange(0, 4096, dtype=np.int64),
+                             (np.arange(1, 3000, dtype=np.int64) * d).clip(0, 2 ** 31 - 1),
+                             (np.arange(1, 3000, dtype=np.int64) * d - 1).clip(0, 2 ** 31 - 1),
+                             2 ** 31 - 1 - np.arange(0, 4096, dtype=np.int64)])
+        q = ((xs.astype(object) * mul) >> 32) >> sh
+        assert np.array_equal(np.array(q, dtype=np.int64), xs // d), d
+    for B in [13, 29, 59, 172933, 351061, 712697, 2938679]:
+        c64 = (1 << 64) % B
+        hs = np.concatenate([rs.randint(-2 ** 31, 2 ** 31, 20000, dtype=np.int64), [-2 ** 31, -1, 0, 1, 2 ** 31 - 1, -B, -B - 1, -B + 1]])
+        for h in hs.tolist():
+            want = (h % (1 << 64)) % B
+            if h >= 0:
+                got = h % B
+            else:
+                r = (-h) % B
+                got = c64 - r if c64 >= r else c64 + (B - r)
+            assert got == want, (h, B)
