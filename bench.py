@@ -322,6 +322,117 @@ def run_lidar(rank, world, local_rank, barrier, scans=12, warm=4):
     return out
 
 
+def run_agents(rank, world, local_rank, barrier, steps, warm, n_queries, n_agents=8):
+    """BASELINE config 5 (CFG-D) as written: 8 independent agent maps (agent a: corridor shifted by y = 20 a, seeds + 10 a)
+    distributed round-robin over the N ranks, plus the 10 M planner queries per step.  A step advances EVERY agent by one
+    frame, so the total work is fixed: strong scaling (8 handles on one GPU at N = 1, one per GPU at N = 8).  Device time
+    per step = sum of the rank's frame times (CUDA events on each handle's stream, L2 flushed once per step), max over
+    ranks.  The query stream is answered twice: split over the ranks against each rank's own agent maps, and against
+    ONE map replicated on every rank (dirty subbox blocks of each frame broadcast over NCCL, ReplicatedMLMap)."""
+    import torch
+    from mlmapping_b200 import MLMap, config_cfg_a, scenes
+    from mlmapping_b200.sharding import agents_for_rank, reduce_timing, split_range
+    cfg = config_cfg_a()
+    mine = agents_for_rank(n_agents, rank, world)
+    total = steps + warm
+    maps, dev = {}, {}
+    for a in mine:
+        frames, poses = gen_frames(cfg, total, agent=a)
+        maps[a] = MLMap(cfg, device=local_rank)
+        dev[a] = [(maps[a].to_device(f), p) for f, p in zip(frames, poses)]
+    first = maps[mine[0]] if mine else None
+    step_ms, rays, frame_us = [], 0, []
+    for k in range(total):
+        if first is not None:
+            first.flush_l2()
+        t_step = 0.0
+        for a in mine:
+            m = maps[a]
+            m.timer_start()
+            st = m.integrate_depth_device(dev[a][k][0], ROWS, COLS, dev[a][k][1])
+            t = m.timer_stop_ms()
+            t_step += t
+            if k >= warm:
+                rays += st.n_points
+                frame_us.append(1e3 * t)
+        if k >= warm:
+            step_ms.append(t_step)
+    barrier()
+    (ms_sum,), (rays_all,) = reduce_timing([float(np.sum(step_ms))], [float(rays)], device="cuda" if world > 1 else None)
+    out = {"workload": "cfg_d_8_agent_maps_640x480_d0.1m (BASELINE config 5)", "agents": n_agents, "n_gpus": world,
+           "agents_this_rank": mine, "scaling": "strong", "steps": steps,
+           "rays_per_s": rays_all / (ms_sum * 1e-3), "ms_per_step": ms_sum / steps,
+           "us_per_frame_this_rank": {"median": float(np.median(frame_us)) if frame_us else None,
+                                      "max": float(np.max(frame_us)) if frame_us else None}}
+    # ---- queries against the agents' own maps: the stream is split over the ranks, each rank's share over its maps ----
+    if n_queries and mine:
+        qb, qe = split_range(n_queries, rank, world)
+        per = (qe - qb) // len(mine)
+        q_ms = 0.0
+        d = cfg.subbox_d_xyz * cfg.subbox_n
+        for a in mine:
+            m = maps[a]
+            ex = m.export_map()
+            pos = scenes.query_positions(per, ex["glb"].min(0) * d, (ex["glb"].max(0) + 1) * d, seed=5 + a)
+            n_odd, n_occ = int(0.4 * per), int(0.4 * per)
+            n_grad = per - n_odd - n_occ
+            d_pos = m.to_device(pos)
+            o1, o2, o3 = m.device_alloc(4 * n_odd), m.device_alloc(4 * n_occ), m.device_alloc(24 * n_grad)
+            for rep in range(4):
+                m.flush_l2()
+                m.timer_start()
+                m.getOdd_device(d_pos, n_odd, o1)
+                m.getOccupancy_device(d_pos + 24 * n_odd, n_occ, o2)
+                m.getOddGrad_device(d_pos + 24 * (n_odd + n_occ), n_grad, o3, 5)
+                t = m.timer_stop_ms()
+            q_ms += t
+            for pp in (d_pos, o1, o2, o3):
+                m.device_free(pp)
+        (q_max,), _ = reduce_timing([q_ms], [0.0], device="cuda" if world > 1 else None)
+        out["queries_own_maps"] = {"n_queries": n_queries, "ms_per_step": q_max, "queries_per_s": n_queries / (q_max * 1e-3),
+                                   "split": "evenly over ranks, a rank's share evenly over its agent maps"}
+    for m in maps.values():
+        m.close()
+    # ---- the same stream against ONE map replicated on every rank ----
+    if n_queries:
+        from mlmapping_b200.sharded import ReplicatedMLMap
+        rep = ReplicatedMLMap(cfg, rank=rank, world=world, src=0, device=local_rank)
+        frames, poses = gen_frames(cfg, min(total, 30), agent=0)
+        t_rep, nb = 0.0, 0
+        for k, (f, p) in enumerate(zip(frames, poses)):
+            barrier()
+            t0 = time.perf_counter()
+            rep.integrate_depth(f if rank == 0 else None, p)
+            torch.cuda.synchronize()
+            if k >= 5:
+                t_rep += time.perf_counter() - t0
+                nb += rep.last["broadcast_bytes"]
+        nrep = max(1, len(frames) - 5)
+        ex = rep.map.export_map()
+        d = cfg.subbox_d_xyz * cfg.subbox_n
+        qb, qe = split_range(n_queries, rank, world)
+        pos = scenes.query_positions(n_queries, ex["glb"].min(0) * d, (ex["glb"].max(0) + 1) * d, seed=5)[qb:qe]
+        n_odd, n_occ = int(0.4 * len(pos)), int(0.4 * len(pos))
+        n_grad = len(pos) - n_odd - n_occ
+        m = rep.map
+        d_pos = m.to_device(pos)
+        o1, o2, o3 = m.device_alloc(4 * n_odd), m.device_alloc(4 * n_occ), m.device_alloc(24 * n_grad)
+        for r_ in range(4):
+            m.flush_l2()
+            m.timer_start()
+            m.getOdd_device(d_pos, n_odd, o1)
+            m.getOccupancy_device(d_pos + 24 * n_odd, n_occ, o2)
+            m.getOddGrad_device(d_pos + 24 * (n_odd + n_occ), n_grad, o3, 5)
+            t = m.timer_stop_ms()
+        (q_max, t_rep_max), _ = reduce_timing([t, 1e3 * t_rep / nrep], [0.0], device="cuda" if world > 1 else None)
+        out["queries_replicated_map"] = {"n_queries": n_queries, "ms_per_step": q_max, "queries_per_s": n_queries / (q_max * 1e-3),
+                                         "replication_ms_per_frame": t_rep_max, "broadcast_bytes_per_frame": nb / nrep,
+                                         "note": "rank 0 integrates, the frame's dirty subbox blocks are broadcast (NCCL) and "
+                                                 "applied on every replica; wall clock incl. the update on rank 0"}
+        m.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -333,6 +444,8 @@ def main():
     ap.add_argument("--no-queries", action="store_true")
     ap.add_argument("--no-lidar", action="store_true")
     ap.add_argument("--lidar-only", action="store_true", help="run only the LiDAR section and print its JSON (tooling)")
+    ap.add_argument("--agents-only", action="store_true", help="run only the CFG-D agents section and print its JSON (tooling)")
+    ap.add_argument("--no-agents", action="store_true")
     ap.add_argument("--queries", type=int, default=10_000_000, help="planner queries per step (4:4:2 odd/occupancy/grad)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -369,6 +482,14 @@ def main():
         res = run_lidar(rank, world, local_rank, barrier)
         if rank == 0:
             print(json.dumps({"lidar": res}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    if args.agents_only:
+        res = run_agents(rank, world, local_rank, barrier, min(args.steps, 40), 5, args.queries)
+        if rank == 0:
+            print(json.dumps({"agents": res}), flush=True)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -451,6 +572,16 @@ def main():
                 lidar = {"error": f"{type(e).__name__}: {e}"[:300]}
         else:
             lidar = run_lidar(rank, world, local_rank, barrier)
+
+    # ---------------- CFG-D as written: 8 agent maps over the N ranks + the query stream (own maps / replicated map) ----
+    agents = None
+    if not args.no_agents:
+        try:
+            agents = run_agents(rank, world, local_rank, barrier, min(args.steps, 40), 5, 0 if args.no_queries else args.queries)
+        except Exception as e:
+            if world > 1:
+                raise
+            agents = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     # ---------------- pass 2: per-kernel events on the same frames (roofline share) ----------------
     m.close()
@@ -553,6 +684,8 @@ def main():
                               "split": "evenly over ranks, each rank queries its own agent map"}
         if lidar:
             out["lidar"] = lidar
+        if agents:
+            out["agents"] = agents
         if not args.no_cpu:
             nf = min(args.cpu_frames, total)
             c_rays, c_s = run_cpu_sample(cfg, frames, poses, nf)

@@ -7,9 +7,11 @@
 
 namespace mlm {
 
-// logit_inv, include/mlmap.h:40: pow(10, x) / (1 + pow(10, x)) in double, returned as float
+// logit_inv, include/mlmap.h:40: pow(10, x) / (1 + pow(10, x)) in double, returned as float.  10^x through exp10
+// (1 ulp in double, a third of pow's instructions): the float result differs from glibc's in the last bit at most,
+// which is the tolerance the parity tests state for getOdd
 __device__ __forceinline__ float logit_inv_f(float lo) {
-  double y = pow(10.0, (double)lo);
+  double y = exp10((double)lo);
   return (float)(y / (1 + y));
 }
 
@@ -117,14 +119,10 @@ __global__ void __launch_bounds__(256) k_get_odd_grad(MapParams P, DeviceBuffers
   if (i >= n) return;
   const double px = pos[3 * i], py = pos[3 * i + 1], pz = pos[3 * i + 2];
   CellRef c = locate_cell(P, px, py, pz);
-  // logit_inv is monotone non-decreasing in the log-odds (also after the cast to float), so a neighbour
-  // whose log-odds is not below the running minimum can never satisfy `tmp_odd < min_odd`: the double
-  // pow() is only evaluated for the candidates that can win.  The sequence of accepted minima, and
-  // therefore the result, is exactly the reference's.
   const int blk0 = grad_block(P, D, c.g);
-  float min_lo = grad_lo(P, D, blk0, c.sub);
-  float min_odd = logit_inv_f(min_lo);
-  const float ori_odd = min_odd;
+  const float lo0 = grad_lo(P, D, blk0, c.sub);
+  const float ori_odd = logit_inv_f(lo0);
+  float min_odd = ori_odd;
   // The six probes walk along +z,-z,+y,-y,+x,-x (subbox_neighbors row order, src/map_local.cpp:78-120):
   // only the coordinate on the probe's own axis changes, so each direction keeps (cell coordinate on its
   // axis, subbox index on its axis, pool block); the hash lookup is repeated only when a subbox border
@@ -138,9 +136,17 @@ __global__ void __launch_bounds__(256) k_get_odd_grad(MapParams P, DeviceBuffers
     ga[d] = c.g[2 - (d >> 1)];
     blk[d] = blk0;
   }
-  int best_g[3] = {0, 0, 0}, best_sub = 0;
-  bool flag = false;
-  for (int iter = 0; iter < max_iter && !flag; iter++) {
+  int best_d = -1;
+  // A round of the reference visits the six neighbours in order and keeps the first one with the strictly lowest odd
+  // below the running minimum; a round that finds one ends the search.  logit_inv is monotone non-decreasing in the
+  // log-odds (also after the cast to float), so the round's winner is the neighbour with the lowest log-odds (the first
+  // of those), unless an EARLIER neighbour with a slightly higher log-odds rounds to the same float odd; those rare
+  // near-ties (within kTie, far more than one float ulp of the odd anywhere in the clamped range) are settled with
+  // their own pow.  So a round costs ONE pow at a point where the whole warp is converged, instead of up to six at
+  // divergent ones (6980 instructions per query before, 83 % of them in diverged pow calls).
+  const float kTie = 1e-2f;
+  for (int iter = 0; iter < max_iter && best_d < 0; iter++) {
+    float lo_d[6];
 #pragma unroll
     for (int d = 0; d < 6; d++) {
       const int axis = 2 - (d >> 1);
@@ -155,26 +161,43 @@ __global__ void __launch_bounds__(256) k_get_odd_grad(MapParams P, DeviceBuffers
         ga[d] -= 1;
         crossed = true;
       }
-      int g[3] = {c.g[0], c.g[1], c.g[2]};
-      g[axis] = ga[d];
-      if (crossed) blk[d] = grad_block(P, D, g);
-      const int sub = c.sub + (ca[d] - cxyz[axis]) * stride[axis];
-      const float lo = grad_lo(P, D, blk[d], sub);
-      if (!(lo < min_lo)) continue;
-      const float tmp = logit_inv_f(lo);
-      if (tmp < min_odd) {
-        min_odd = tmp;
-        min_lo = lo;
-        best_g[0] = g[0];
-        best_g[1] = g[1];
-        best_g[2] = g[2];
-        best_sub = sub;
-        flag = true;
+      if (crossed) {
+        int g[3] = {c.g[0], c.g[1], c.g[2]};
+        g[axis] = ga[d];
+        blk[d] = grad_block(P, D, g);
       }
+      lo_d[d] = grad_lo(P, D, blk[d], c.sub + (ca[d] - cxyz[axis]) * stride[axis]);
     }
+    // lowest log-odds of the round, first direction wins ties
+    int m = 0;
+    float lo_m = lo_d[0];
+#pragma unroll
+    for (int d = 1; d < 6; d++)
+      if (lo_d[d] < lo_m) {
+        lo_m = lo_d[d];
+        m = d;
+      }
+    if (!(lo_m < lo0)) continue;          // nothing can be below the origin's odd this round
+    const float odd_m = logit_inv_f(lo_m);
+    if (!(odd_m < min_odd)) continue;     // rounds to the origin's odd (or above): not strictly lower
+    min_odd = odd_m;
+    best_d = m;
+    // earlier directions whose log-odds is a hair above the minimum: same float odd -> the reference keeps the earlier one
+#pragma unroll
+    for (int d = 0; d < 5; d++)
+      if (d < m && (lo_d[d] - lo_m <= kTie || lo_m < -30.0f) && lo_d[d] < lo0) {  // (below 10^-30 the float odd underflows: any gap can tie)
+        if (logit_inv_f(lo_d[d]) == odd_m) {
+          best_d = d;
+          break;
+        }
+      }
   }
   double gx = 0.0, gy = 0.0, gz = 0.0;
-  if (flag) {
+  if (best_d >= 0) {
+    const int axis = 2 - (best_d >> 1);
+    int best_g[3] = {c.g[0], c.g[1], c.g[2]};
+    best_g[axis] = ga[best_d];
+    const int best_sub = c.sub + (ca[best_d] - cxyz[axis]) * stride[axis];
     // subbox_id2xyz_glb_vec (map_local.h:208-213) - pos, times (double)(float)(ori - min)
     int x = best_sub % P.n, y = (best_sub / P.n) % P.n, z = best_sub / (P.n * P.n);
     double s = (double)__fsub_rn(ori_odd, min_odd);

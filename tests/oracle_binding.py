@@ -111,6 +111,12 @@ def _prototypes(lib):
     return lib
 
 
+def best_oracle(cfg, **kw):
+    """the checker the GPU parity tests use: the reference's own sources (oracle/_ref) when that library is available
+    (built here from /root/reference; the prebuilt file travels to the GPU box), else the restatement"""
+    return Oracle(cfg, impl="reference" if reference_available() else "port", **kw)
+
+
 def _d7(a):
     a = np.asarray(a, dtype=np.float64).reshape(-1)
     return (C.c_double * len(a))(*a.tolist())

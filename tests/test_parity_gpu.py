@@ -6,7 +6,7 @@ import pytest
 
 from mlmapping_b200 import MLMap, config_cfg_a, config_cfg_c, scenes
 from mlmapping_b200.capi import MlmError
-from oracle_binding import Oracle
+from oracle_binding import best_oracle as Oracle  # the reference's own sources when oracle/_ref is there, else the restatement
 from parity_utils import assert_cloud_parity, assert_frame_parity, assert_map_parity
 
 pytestmark = pytest.mark.gpu
