@@ -70,5 +70,25 @@ int main() {
   copy.restore(image);
   std::printf("occupied cloud %zu points, odds slice %zu cells, checkpoint %zu bytes, restored copy: wall=%d (%zu points)\n",
               cloud.size(), slice.size(), image.size(), copy.getOccupancy(wall), copy.map_cloud(MLM_CLOUD_OCCUPIED).size());
-  return 0;
+  // the layer-level calls of update_map (src/mlmap.cpp:382-386) and the index overload of getOdd
+  std::vector<Vec3> pc;
+  for (int i = 0; i < 2000; i++) pc.emplace_back(0.002 * (i % 50) - 0.05, 0.002 * (i / 50) - 0.04, 1.0 + 0.0005 * i);
+  copy.awareness_map->input_pc_pose(pc, SE3(1, 0, 0, 0, Vec3(6.0, 0, 1.2)));
+  const mlm_frame_stats &st2 = copy.local_map->input_pc_pose_direct(copy.awareness_map);
+  const float odd_idx = map.getOdd(Vec3I(7, 1, 1), 2 + 10 * 2 + 100 * 2);   // cell (2,2,2) of subbox (7,1,1): centre (7.25, 1.25, 1.25)
+  const float odd_pos = map.getOdd(Vec3(7.25, 1.25, 1.25));
+  std::printf("two-call update: %d points, %d hit cells; getOdd by index %.6f == by position %.6f\n", st2.n_points, st2.n_hit_cells,
+              odd_idx, odd_pos);
+  // self-checks: the C++ mirror must behave on a device, not just link
+  int bad = 0;
+  bad += map.getOccupancy(probe) != mlmap::FREE;
+  bad += map.getOccupancy(wall) != mlmap::OCCUPIED;
+  bad += map.getOccupancy(far) != mlmap::UNKNOWN;
+  bad += !(map.getOdd(wall) > 0.99f);
+  bad += copy.getOccupancy(wall) != mlmap::OCCUPIED;
+  bad += cloud.empty() || slice.empty();
+  bad += st2.n_points != 2000 || st2.n_hit_cells <= 0;
+  bad += odd_idx != odd_pos;
+  std::printf("harness self-checks: %s\n", bad ? "FAILED" : "ok");
+  return bad ? 1 : 0;
 }

@@ -146,6 +146,30 @@ int mlm_integrate_points_f64(mlm_handle h, const double *xyz, int n, const doubl
 int mlm_integrate_points_f64_device(mlm_handle h, const double *d_xyz, int n, const double T_wb[7],
                                     mlm_frame_stats *stats);
 
+/* The two layer entry points behind mlmap's public `awareness_map` / `local_map` pointers, which mlmap::update_map calls
+ * one after the other (reference src/mlmap.cpp:382-386, include/mlmap.h:107-108):
+ *   mlm_awareness_input_*            awareness_map_cylindrical::input_pc_pose (include/map_awareness.h:74,
+ *                                    src/map_awareness.cpp:173-282): the frame's hit map and miss set, readable with
+ *                                    mlm_last_frame_hits / mlm_last_frame_misses; the depth variant runs project_depth first
+ *   mlm_local_input_pc_pose_direct   local_map_cartesian::input_pc_pose_direct(awareness_map) (include/map_local.h:114,
+ *                                    src/map_local.cpp:143-237): fuses the staged sets into the local / global map
+ * One difference is visible between the two calls: the subboxes the frame touches are allocated by the first call already
+ * (all-unknown cells, so every query still answers like the reference; only mlm_export_map_count is ahead).
+ * mlm_integrate_* = both calls as ONE cooperative launch. */
+int mlm_awareness_input_pc_pose_f64(mlm_handle h, const double *xyz, int n, const double T_wb[7], mlm_frame_stats *stats);
+int mlm_awareness_input_depth_u16(mlm_handle h, const uint16_t *img, int rows, int cols, size_t stride_bytes,
+                                  const double T_wb[7], mlm_frame_stats *stats);
+int mlm_local_input_pc_pose_direct(mlm_handle h, mlm_frame_stats *stats);
+
+/* Asynchronous frames, for several maps of one process on one GPU (BASELINE config 5: 8 agent maps): submit enqueues the
+ * frame on the handle's stream and returns; mlm_frame_finish waits for it, settles a rehash frame and returns the
+ * counters.  mlm_set_sm_budget(h, n) makes the handle's frame kernel use n CTAs instead of one per SM (0 restores that),
+ * so that the cooperative launches of several handles are co-resident and overlap. */
+int mlm_set_sm_budget(mlm_handle h, int n_sms);
+int mlm_frame_submit_depth_u16_device(mlm_handle h, const uint16_t *d_img, int rows, int cols, const double T_wb[7]);
+int mlm_frame_submit_points_f64_device(mlm_handle h, const double *d_xyz, int n, const double T_wb[7]);
+int mlm_frame_finish(mlm_handle h, mlm_frame_stats *stats /* may be NULL */);
+
 /* mlmap::setFree_map_in_bound (reference src/mlmap.cpp:388-407) */
 int mlm_set_free_in_bound(mlm_handle h, const double box_min[3], const double box_max[3]);
 
@@ -159,6 +183,9 @@ int mlm_get_occupancy_inflate(mlm_handle h, const double *pos, size_t n, float i
 int mlm_get_inflate_occupancy(mlm_handle h, const double *pos, size_t n, int32_t *out);
 int mlm_get_odd(mlm_handle h, const double *pos, size_t n, float *out);
 int mlm_get_odd_grad(mlm_handle h, const double *pos, size_t n, size_t max_iter, double *out3n);
+/* getOdd(const Vec3I &glb_id, size_t subbox_id) (include/mlmap.h:128,227-235): glb3 = n x 3 subbox indices, sub = n cell ids */
+int mlm_get_odd_at(mlm_handle h, const int32_t *glb3, const int32_t *sub, size_t n, float *out);
+int mlm_get_odd_at_device(mlm_handle h, const int32_t *d_glb3, const int32_t *d_sub, size_t n, float *d_out);
 /* device-resident variants: pos/out are device pointers, the call only enqueues on the handle's stream */
 int mlm_get_occupancy_device(mlm_handle h, const double *d_pos, size_t n, int32_t *d_out);
 int mlm_get_odd_device(mlm_handle h, const double *d_pos, size_t n, float *d_out);

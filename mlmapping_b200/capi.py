@@ -121,6 +121,8 @@ ABI_SYMBOLS = [
     "mlm_last_frame_hits", "mlm_last_frame_misses", "mlm_export_map_count", "mlm_export_map",
     "mlm_debug_log10f", "mlm_set_profiling", "mlm_last_frame_kernel_ms", "mlm_sizeof_config",
     "mlm_sizeof_frame_stats", "mlm_debug_phase_cycles", "mlm_host_alloc", "mlm_host_free", "mlm_srand", "mlm_debug_rand", "mlm_export_frontier", 
+    "mlm_awareness_input_pc_pose_f64", "mlm_awareness_input_depth_u16", "mlm_local_input_pc_pose_direct", "mlm_set_sm_budget",
+    "mlm_frame_submit_depth_u16_device", "mlm_frame_submit_points_f64_device", "mlm_frame_finish", "mlm_get_odd_at", "mlm_get_odd_at_device",
     "mlm_shard_open", "mlm_shard_connect", "mlm_shard_submit_points_f64", "mlm_shard_submit_points_f64_device", "mlm_shard_finish",
     "mlm_shard_integrate_points_f64", "mlm_shard_last_exchange", "mlm_shard_last_kernel_ms", "mlm_shard_close", "mlm_dirty_count", "mlm_dirty_export", "mlm_dirty_import",
     "mlm_export_cloud", "mlm_export_cloud_device", "mlm_export_odds_slice",
@@ -203,6 +205,15 @@ def load_library() -> C.CDLL:
         "mlm_checkpoint_save": ([vp, vp, sz, C.POINTER(sz)], C.c_int),
         "mlm_checkpoint_restore": ([vp, vp, sz], C.c_int),
         "mlm_compensate_pose": ([dp, dp, dp, dp, C.c_double, C.c_double, C.c_double, dp], C.c_int),
+        "mlm_awareness_input_pc_pose_f64": ([vp, vp, C.c_int, dp, C.POINTER(FrameStats)], C.c_int),
+        "mlm_awareness_input_depth_u16": ([vp, vp, C.c_int, C.c_int, sz, dp, C.POINTER(FrameStats)], C.c_int),
+        "mlm_local_input_pc_pose_direct": ([vp, C.POINTER(FrameStats)], C.c_int),
+        "mlm_set_sm_budget": ([vp, C.c_int], C.c_int),
+        "mlm_frame_submit_depth_u16_device": ([vp, vp, C.c_int, C.c_int, dp], C.c_int),
+        "mlm_frame_submit_points_f64_device": ([vp, vp, C.c_int, dp], C.c_int),
+        "mlm_frame_finish": ([vp, C.POINTER(FrameStats)], C.c_int),
+        "mlm_get_odd_at": ([vp, vp, vp, sz, vp], C.c_int),
+        "mlm_get_odd_at_device": ([vp, vp, vp, sz, vp], C.c_int),
         "mlm_shard_open": ([vp, C.c_int, C.c_int, vp], C.c_int),
         "mlm_shard_connect": ([vp, vp], C.c_int),
         "mlm_shard_submit_points_f64": ([vp, vp, C.c_int, dp], C.c_int),
@@ -388,6 +399,49 @@ class MLMap:
         self._check(self._lib.mlm_integrate_points_f64(self._h, pts.ctypes.data, pts.shape[0], _pose7(T_wb), C.byref(st)))
         self.has_data = self.map_updated = True
         return st
+
+    # ---- the two layer entry points of update_map (awareness_map->input_pc_pose, local_map->input_pc_pose_direct) ----
+    def awareness_input_pc_pose(self, xyz: np.ndarray, T_wb) -> FrameStats:
+        pts = np.ascontiguousarray(np.asarray(xyz, dtype=np.float64).reshape(-1, 3))
+        st = FrameStats()
+        self._check(self._lib.mlm_awareness_input_pc_pose_f64(self._h, pts.ctypes.data, pts.shape[0], _pose7(T_wb), C.byref(st)))
+        return st
+
+    def awareness_input_depth(self, img: np.ndarray, T_wb) -> FrameStats:
+        img = np.ascontiguousarray(img, dtype=np.uint16)
+        st = FrameStats()
+        self._check(self._lib.mlm_awareness_input_depth_u16(self._h, img.ctypes.data, img.shape[0], img.shape[1], img.strides[0],
+                                                            _pose7(T_wb), C.byref(st)))
+        return st
+
+    def local_input_pc_pose_direct(self) -> FrameStats:
+        st = FrameStats()
+        self._check(self._lib.mlm_local_input_pc_pose_direct(self._h, C.byref(st)))
+        self.has_data = self.map_updated = True
+        return st
+
+    # ---- asynchronous frames (several maps of one process on one GPU) ----
+    def set_sm_budget(self, n_sms: int):
+        self._check(self._lib.mlm_set_sm_budget(self._h, n_sms))
+
+    def submit_depth_device(self, d_img: int, rows: int, cols: int, T_wb):
+        self._check(self._lib.mlm_frame_submit_depth_u16_device(self._h, d_img, rows, cols, self._pose(T_wb)))
+
+    def submit_points_device(self, d_xyz: int, n: int, T_wb):
+        self._check(self._lib.mlm_frame_submit_points_f64_device(self._h, d_xyz, n, self._pose(T_wb)))
+
+    def finish_frame(self) -> FrameStats:
+        st = FrameStats()
+        self._check(self._lib.mlm_frame_finish(self._h, C.byref(st)))
+        return st
+
+    def getOdd_at(self, glb3, sub) -> np.ndarray:
+        """getOdd(const Vec3I &glb_id, size_t subbox_id), include/mlmap.h:128"""
+        g = np.ascontiguousarray(np.asarray(glb3, dtype=np.int32).reshape(-1, 3))
+        sb = np.ascontiguousarray(np.asarray(sub, dtype=np.int32).reshape(-1))
+        out = np.empty(g.shape[0], dtype=np.float32)
+        self._check(self._lib.mlm_get_odd_at(self._h, g.ctypes.data, sb.ctypes.data, g.shape[0], out.ctypes.data))
+        return out
 
     def integrate_points_device(self, d_xyz: int, n: int, T_wb) -> FrameStats:
         st = FrameStats()

@@ -202,6 +202,17 @@ struct mlm_map {
   ShardPeers shard_peers;            // every rank's arena as mapped here
   void *shard_mapped[kMaxWorld] = {};  // cudaIpcOpenMemHandle results to close
   bool shard_open = false, shard_connected = false, shard_pending = false;
+  // two-call layer interface / asynchronous frames
+  int stage_call = 0;          // run_frame stops after the awareness layer (project + column)
+  bool staged = false;         // an awareness-layer update waits for mlm_local_input_pc_pose_direct
+  int staged_slow = 0;
+  uint32_t staged_order_B = 1;
+  int async_call = 0;          // run_frame returns after enqueueing; mlm_frame_finish completes the frame
+  bool frame_pending = false;
+  int pending_mode = 0;
+  int frame_sms = 0;           // CTAs of k_frame when the handle shares the GPU with other maps (0: one per SM)
+  int *d_sample_info = nullptr;  // sampled projection of a device image: {points, tries used}
+  uint2 *d_sample_tries = nullptr;
   cudaEvent_t sev[MLM_NUM_SHARD_KERNELS + 1] = {};
   float skms[MLM_NUM_SHARD_KERNELS] = {};
   bool shard_shares_device = false;  // another rank of this process runs on the same GPU (single-GPU tests)
@@ -418,10 +429,12 @@ int order_slow_path(mlm_map *h, int n, int kind, uint32_t B_start, uint32_t *B_f
 }
 
 int finish_frame(mlm_map *h, int slow, uint32_t order_B, mlm_frame_stats *stats);
+int run_frame_complete(mlm_map *h, mlm_frame_stats *stats);
 
 // Exploration mode (use_exploration_frontiers): the frame needs the neighbours' state between the hit and
 // the miss pass, and the miss-set iteration order, so it runs as direct launches with one host check of the
 // container sizes in the middle (rehash detection for both emulated containers).
+int run_frame_explore_direct(mlm_map *h, int slow, uint32_t order_B, mlm_frame_stats *stats);
 int run_frame_explore(mlm_map *h, int mode, int N, mlm_frame_stats *stats) {
   const MapParams &P = h->P;
   cudaStream_t s = h->stream;
@@ -460,6 +473,22 @@ int run_frame_explore(mlm_map *h, int mode, int N, mlm_frame_stats *stats) {
       F.bucket_count_miss = Bm;
     }
   }
+  if (h->stage_call) {  // awareness layer only: the local layer follows with mlm_local_input_pc_pose_direct
+    *h->h_fc = mid;
+    h->staged = true;
+    h->staged_slow = slow;
+    h->staged_order_B = order_B;
+    h->last_order_B = order_B;
+    h->last_n_hit = mid.n_hit;
+    return MLM_OK;
+  }
+  return run_frame_explore_direct(h, slow, order_B, stats);
+}
+int run_frame_explore_direct(mlm_map *h, int slow, uint32_t order_B, mlm_frame_stats *stats) {
+  const MapParams &P = h->P;
+  cudaStream_t s = h->stream;
+  FrameParams &F = *h->h_fp;
+  const int parity = F.parity;
   const int g4 = h->sm_count * 4;
   k_fuse<1><<<g4, 256, 0, s>>>(P, h->D, F);
   k_miss_tkey<<<g4, 256, 0, s>>>(P, h->D, F);
@@ -485,6 +514,11 @@ int run_frame_explore(mlm_map *h, int mode, int N, mlm_frame_stats *stats) {
 // mode: 0 = points, 1 = full depth image, 2 = sampled depth pixels (d_in = uint2 {pixel, raw} x n_points)
 int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_points, const double T_wb[7],
               mlm_frame_stats *stats) {
+  if (h->staged || h->frame_pending) {
+    g_last_error = h->staged ? "an awareness-layer update is waiting for mlm_local_input_pc_pose_direct"
+                             : "a submitted frame is waiting for mlm_frame_finish";
+    return MLM_ERR_INVALID_ARG;
+  }
   const bool depth = mode == 1;
   const MapParams &P = h->P;
   cudaStream_t s = h->stream;
@@ -557,6 +591,54 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
     return MLM_OK;  // no host sync: the exchange and the owner-side kernels follow on the stream (mlm_shard_submit_*)
   }
   if (P.explore) return run_frame_explore(h, mode, N, stats);
+  if (h->stage_call) {
+    // awareness layer only (awareness_map_cylindrical::input_pc_pose): hit map + miss set of the frame, staged in the
+    // frame-local voxel grid; the ordering of a rehash frame is settled here so that the frame's sets can be read
+    const int pg = grid_for((size_t)std::max(N, 1), kProjThreads * 2);
+    if (mode == 1)
+      k_project<1><<<pg, kProjThreads, project_smem_bytes(P.nCol, kProjThreads), s>>>(P, h->D, F);
+    else if (mode == 2)
+      k_project<2><<<pg, kProjThreads, project_smem_bytes(P.nCol, kProjThreads), s>>>(P, h->D, F);
+    else
+      k_project<0><<<pg, kProjThreads, project_smem_bytes(P.nCol, kProjThreads), s>>>(P, h->D, F);
+    k_column<<<h->col_grid, kColThreads, h->col_smem_bytes, s>>>(P, h->D, F);
+    h->launches += 2;
+    CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc[parity], sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaGetLastError());
+    int slow = 0;
+    uint32_t order_B = h->bucket_count;
+    const int n = h->h_fc->n_hit;
+    if (h->h_fc->error == 0 && (uint32_t)n > h->bucket_count) {
+      if (n > h->sort_cap) {
+        g_last_error = "hit count exceeds ordering scratch";
+        return MLM_ERR_CAPACITY;
+      }
+      slow = 1;
+      int rc = order_slow_path(h, n, 0, h->bucket_count, &order_B);
+      if (rc != MLM_OK) return rc;
+      F.bucket_count = order_B;
+      F.bucket_c64 = pow64_mod(order_B);
+      F.order_mode = 1;
+      CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    h->staged = true;
+    h->staged_slow = slow;
+    h->staged_order_B = order_B;
+    h->last_order_B = order_B;
+    h->last_n_hit = n;
+    if (stats) {
+      memset(stats, 0, sizeof(*stats));
+      stats->n_points = h->h_fc->n_points;
+      stats->n_inside = h->h_fc->n_inside;
+      stats->n_cast = h->h_fc->n_cast;
+      stats->n_hit_cells = h->h_fc->n_hit;
+      stats->n_miss_cells = h->h_fc->n_miss;
+      stats->ordering_slow_path = slow;
+      stats->status = map_device_error(h->h_fc->error);
+    }
+    return h->h_fc->error ? map_device_error(h->h_fc->error) : MLM_OK;
+  }
   const bool prof = h->profiling != 0;
   const int full_grid = grid_for((size_t)P.max_points, kProjThreads * 2);
   const int proj_grid = grid_for((size_t)std::max(N, 1), kProjThreads * 2);
@@ -581,7 +663,7 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
 #undef MLM_MARK
   } else if (h->use_fused) {
     // the whole frame is ONE cooperative kernel (k_frame), replayed as a single-node graph
-    const int G = h->frame_grid;
+    const int G = h->frame_sms > 0 ? std::min(h->frame_sms, h->frame_grid) : h->frame_grid;
     // one tile per CTA when the frame allows it: N points dealt evenly, in 32-point rounds, at most 128 per warp
     Fk.tile_pts = std::min(kProjMaxPts * kColThreads, std::max(32, (((N + G - 1) / G) + 31) & ~31));
     F.tile_pts = Fk.tile_pts;
@@ -646,6 +728,20 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
     }
   }
   h->launches += (prof || !h->use_graph || !h->use_fused) ? 3 : 1;
+  if (h->async_call) {  // mlm_frame_finish waits, settles a rehash frame and returns the counters
+    h->frame_pending = true;
+    h->pending_mode = mode;
+    return MLM_OK;
+  }
+  return run_frame_complete(h, stats);
+}
+
+// second half of a frame: wait for the launch, run the rehash path when the frame needs it, counters
+int run_frame_complete(mlm_map *h, mlm_frame_stats *stats) {
+  const MapParams &P = h->P;
+  cudaStream_t s = h->stream;
+  FrameParams &F = *h->h_fp;
+  const bool prof = h->profiling != 0;
   CUDA_TRY(cudaStreamSynchronize(s));
   CUDA_TRY(cudaGetLastError());
 
@@ -1317,11 +1413,46 @@ int mlm_integrate_depth_u16(mlm_handle h, const uint16_t *img, int rows, int col
 int mlm_integrate_depth_u16_device(mlm_handle h, const uint16_t *d_img, int rows, int cols, const double T_wb[7],
                                    mlm_frame_stats *stats) {
   if (!h || !d_img || !T_wb || rows <= 0 || cols <= 0) return MLM_ERR_INVALID_ARG;
-  if (h->cfg.sample_cnt > 0) {
-    g_last_error = "sampled project_depth needs the host image (pixel values decide how many rand() draws are consumed)";
-    return MLM_ERR_UNSUPPORTED;
+  if ((long long)rows * cols > h->P.max_points) {
+    g_last_error = "image larger than cfg.max_points";
+    return MLM_ERR_CAPACITY;
   }
   CUDA_TRY(cudaSetDevice(h->device));
+  if (h->cfg.sample_cnt > 0) {
+    // mlmap::project_depth (src/mlmap.cpp:321-346) on a device image: the rand() draws of all 2*sample_cnt possible tries
+    // are made up front on a COPY of the stream (two per try whatever the pixel holds); a kernel looks the pixels up,
+    // keeps the tries the reference's loop would have executed (it stops after sample_cnt valid pixels) and reports how
+    // many that were, and the handle's stream then advances by exactly that many tries
+    const int cnt_max = h->cfg.sample_cnt, max_iter = 2 * cnt_max;
+    cudaStream_t s = h->stream;
+    if (!h->d_sample_tries) {
+      CUDA_TRY(cudaMalloc((void **)&h->d_sample_tries, (size_t)max_iter * sizeof(uint2) * 2));
+      h->allocs.push_back(h->d_sample_tries);
+      CUDA_TRY(cudaMalloc((void **)&h->d_sample_info, 2 * sizeof(int)));
+      h->allocs.push_back(h->d_sample_info);
+    }
+    int rc2 = ensure_input(h, (size_t)max_iter * sizeof(uint2), (size_t)max_iter * sizeof(uint2));
+    if (rc2 != MLM_OK) return rc2;
+    GlibcRand ahead = h->rng;
+    uint2 *tries = reinterpret_cast<uint2 *>(h->h_stage);
+    for (int t = 0; t < max_iter; t++) {
+      const unsigned v = (unsigned)(ahead.next() % rows);
+      const unsigned u = (unsigned)(ahead.next() % cols);
+      tries[t] = make_uint2(v * (unsigned)cols + u, 0u);
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_sample_tries, tries, (size_t)max_iter * sizeof(uint2), cudaMemcpyHostToDevice, s));
+    uint2 *d_pairs = h->d_sample_tries + max_iter;
+    k_sample_gather<<<1, 1024, 0, s>>>(d_img, h->d_sample_tries, max_iter, cnt_max, d_pairs, h->d_sample_info);
+    h->launches++;
+    int info[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(info, h->d_sample_info, sizeof(info), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (int t = 0; t < info[1]; t++) {  // the tries the reference's loop executes: two draws each
+      h->rng.next();
+      h->rng.next();
+    }
+    return run_frame(h, 2, d_pairs, rows, cols, info[0], T_wb, stats);
+  }
   return run_frame(h, 1, d_img, rows, cols, 0, T_wb, stats);
 }
 
@@ -1336,8 +1467,16 @@ int mlm_integrate_points_f64(mlm_handle h, const double *xyz, int n, const doubl
   int rc = ensure_input(h, bytes, (size_t)h->P.max_points * 24);
   if (rc != MLM_OK) return rc;
   if (n > 0) {
-    memcpy(h->h_stage, xyz, (size_t)n * 24);
-    CUDA_TRY(cudaMemcpyAsync(h->d_input, h->h_stage, (size_t)n * 24, cudaMemcpyHostToDevice, h->stream));
+    // page-locked caller memory (mlm_host_alloc / cudaHostRegister) is copied straight from the caller's buffer
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, xyz) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const void *src = xyz;
+    if (!pinned) {
+      memcpy(h->h_stage, xyz, (size_t)n * 24);
+      src = h->h_stage;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_input, src, (size_t)n * 24, cudaMemcpyHostToDevice, h->stream));
   }
   return run_frame(h, 0, h->d_input, 0, 0, n, T_wb, stats);
 }
@@ -1347,6 +1486,115 @@ int mlm_integrate_points_f64_device(mlm_handle h, const double *d_xyz, int n, co
   if (!h || (!d_xyz && n > 0) || !T_wb || n < 0) return MLM_ERR_INVALID_ARG;
   CUDA_TRY(cudaSetDevice(h->device));
   return run_frame(h, 0, d_xyz, 0, 0, n, T_wb, stats);
+}
+
+// ---- the two layer entry points mlmap::update_map calls one after the other (src/mlmap.cpp:382-386) -----------------
+int mlm_awareness_input_pc_pose_f64(mlm_handle h, const double *xyz, int n, const double T_wb[7], mlm_frame_stats *stats) {
+  if (!h) return MLM_ERR_INVALID_ARG;
+  h->stage_call = 1;
+  const int rc = mlm_integrate_points_f64(h, xyz, n, T_wb, stats);
+  h->stage_call = 0;
+  return rc;
+}
+int mlm_awareness_input_depth_u16(mlm_handle h, const uint16_t *img, int rows, int cols, size_t stride_bytes, const double T_wb[7],
+                                  mlm_frame_stats *stats) {
+  if (!h) return MLM_ERR_INVALID_ARG;
+  h->stage_call = 1;
+  const int rc = mlm_integrate_depth_u16(h, img, rows, cols, stride_bytes, T_wb, stats);
+  h->stage_call = 0;
+  return rc;
+}
+int mlm_local_input_pc_pose_direct(mlm_handle h, mlm_frame_stats *stats) {
+  if (!h) return MLM_ERR_INVALID_ARG;
+  if (!h->staged) {
+    g_last_error = "no awareness-layer update is staged (mlm_awareness_input_* comes first)";
+    return MLM_ERR_INVALID_ARG;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  h->staged = false;
+  if (h->P.explore) return run_frame_explore_direct(h, h->staged_slow, h->staged_order_B, stats);
+  cudaStream_t s = h->stream;
+  k_fuse<0><<<h->sm_count * 4, 256, 0, s>>>(h->P, h->D, *h->h_fp);
+  h->launches++;
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  return finish_frame(h, h->staged_slow, h->staged_order_B, stats);
+}
+
+// ---- asynchronous frames: several maps of one process share a GPU (CFG-D: 8 agent maps) -------------------------------
+int mlm_set_sm_budget(mlm_handle h, int n_sms) {
+  if (!h || n_sms < 0) return MLM_ERR_INVALID_ARG;
+  h->frame_sms = n_sms;
+  return MLM_OK;
+}
+int mlm_frame_submit_depth_u16_device(mlm_handle h, const uint16_t *d_img, int rows, int cols, const double T_wb[7]) {
+  if (!h || !d_img || !T_wb || rows <= 0 || cols <= 0) return MLM_ERR_INVALID_ARG;
+  if (h->cfg.sample_cnt > 0 || h->P.explore) {
+    g_last_error = "asynchronous frames: full-frame projection without the exploration mode only";
+    return MLM_ERR_UNSUPPORTED;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  h->async_call = 1;
+  const int rc = run_frame(h, 1, d_img, rows, cols, 0, T_wb, nullptr);
+  h->async_call = 0;
+  return rc;
+}
+int mlm_frame_submit_points_f64_device(mlm_handle h, const double *d_xyz, int n, const double T_wb[7]) {
+  if (!h || (!d_xyz && n > 0) || !T_wb || n < 0) return MLM_ERR_INVALID_ARG;
+  if (h->P.explore) {
+    g_last_error = "asynchronous frames: not in the exploration mode";
+    return MLM_ERR_UNSUPPORTED;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  h->async_call = 1;
+  const int rc = run_frame(h, 0, d_xyz, 0, 0, n, T_wb, nullptr);
+  h->async_call = 0;
+  return rc;
+}
+int mlm_frame_finish(mlm_handle h, mlm_frame_stats *stats) {
+  if (!h) return MLM_ERR_INVALID_ARG;
+  if (!h->frame_pending) {
+    g_last_error = "no submitted frame";
+    return MLM_ERR_INVALID_ARG;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  h->frame_pending = false;
+  return run_frame_complete(h, stats);
+}
+
+// getOdd(const Vec3I &glb_id, size_t subbox_id), include/mlmap.h:128,227-235
+int mlm_get_odd_at_device(mlm_handle h, const int32_t *d_glb3, const int32_t *d_sub, size_t n, float *d_out) {
+  if (!h || ((!d_glb3 || !d_sub || !d_out) && n)) return MLM_ERR_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (n == 0) return MLM_OK;
+  k_get_odd_at<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->D, d_glb3, d_sub, n, d_out);
+  h->launches++;
+  return MLM_OK;
+}
+int mlm_get_odd_at(mlm_handle h, const int32_t *glb3, const int32_t *sub, size_t n, float *out) {
+  if (!h || ((!glb3 || !sub || !out) && n)) return MLM_ERR_INVALID_ARG;
+  if (n == 0) return MLM_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  int32_t *d_g = nullptr, *d_s = nullptr;
+  float *d_o = nullptr;
+  CUDA_TRY(cudaMallocAsync((void **)&d_g, n * 12, s));
+  CUDA_TRY(cudaMallocAsync((void **)&d_s, n * 4, s));
+  CUDA_TRY(cudaMallocAsync((void **)&d_o, n * 4, s));
+  cudaError_t e = cudaMemcpyAsync(d_g, glb3, n * 12, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_s, sub, n * 4, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) {
+    k_get_odd_at<<<grid_for(n, 256), 256, 0, s>>>(h->P, h->D, d_g, d_s, n, d_o);
+    h->launches++;
+    e = cudaMemcpyAsync(out, d_o, n * 4, cudaMemcpyDeviceToHost, s);
+  }
+  cudaFreeAsync(d_g, s);
+  cudaFreeAsync(d_s, s);
+  cudaFreeAsync(d_o, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  CUDA_TRY(e);
+  CUDA_TRY(cudaGetLastError());
+  return MLM_OK;
 }
 
 int mlm_set_free_in_bound(mlm_handle h, const double box_min[3], const double box_max[3]) {

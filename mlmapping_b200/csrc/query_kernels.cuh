@@ -83,6 +83,72 @@ __global__ void __launch_bounds__(256) k_get_odd(MapParams P, DeviceBuffers D, c
   out[i] = odd_at(P, D, c.g, c.sub);
 }
 
+// getOdd(const Vec3I &glb_id, size_t subbox_id), include/mlmap.h:227-235
+__global__ void __launch_bounds__(256) k_get_odd_at(MapParams P, DeviceBuffers D, const int *glb3, const int *sub, size_t n, float *out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int g[3] = {glb3[3 * i], glb3[3 * i + 1], glb3[3 * i + 2]};
+  out[i] = odd_at(P, D, g, sub[i]);
+}
+
+// sampled project_depth on a device image (src/mlmap.cpp:321-346): tries[t].x = pixel index of try t (v*cols + u from the
+// rand() stream).  A try is executed while fewer than cnt_max valid pixels have been collected; the valid pixels of the
+// executed tries are compacted in order into pairs {pixel, raw depth}; info = {points, tries executed}.  One CTA.
+__global__ void __launch_bounds__(1024) k_sample_gather(const uint16_t *img, const uint2 *tries, int max_iter, int cnt_max,
+                                                        uint2 *pairs, int *info) {
+  __shared__ int s_warp[33];
+  __shared__ int s_carry, s_tries;
+  if (threadIdx.x == 0) {
+    s_carry = 0;
+    s_tries = -1;
+  }
+  __syncthreads();
+  for (int base = 0; base < max_iter; base += blockDim.x) {
+    const int t = base + threadIdx.x;
+    unsigned pix = 0;
+    uint16_t raw = 0;
+    if (t < max_iter) {
+      pix = tries[t].x;
+      raw = img[pix];
+    }
+    const int valid = raw != 0 ? 1 : 0;
+    // inclusive count of valid pixels up to try t
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = valid;
+#pragma unroll
+    for (int ofs = 1; ofs < 32; ofs <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, ofs);
+      if (lane >= ofs) incl += v;
+    }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      int sv = s_warp[lane], si = sv;
+#pragma unroll
+      for (int ofs = 1; ofs < 32; ofs <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, si, ofs);
+        if (lane >= ofs) si += v;
+      }
+      s_warp[lane] = si - sv;
+      if (lane == 31) s_warp[32] = si;
+    }
+    __syncthreads();
+    const int upto = s_carry + s_warp[w] + incl;   // valid pixels among tries 0..t
+    // try t runs iff fewer than cnt_max valid pixels were collected before it
+    if (t < max_iter && upto - valid < cnt_max) {
+      if (valid) pairs[upto - 1] = make_uint2(pix, (unsigned)raw);
+      if (valid && upto == cnt_max) s_tries = t + 1;   // the try that fills the quota is the last one executed
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += s_warp[32];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    info[0] = min(s_carry, cnt_max);
+    info[1] = s_tries >= 0 ? s_tries : max_iter;
+  }
+}
+
 // subbox_neighbors row i of cell sub (src/map_local.cpp:78-120): order +z,-z,+y,-y,+x,-x
 __device__ __forceinline__ void neighbor_step(const MapParams &P, int dir, int g[3], int &sub) {
   int x = sub % P.n, y = (sub / P.n) % P.n, z = sub / (P.n * P.n);

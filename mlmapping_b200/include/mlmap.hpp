@@ -28,6 +28,14 @@ struct Vec3 {
   double operator[](int i) const { return v[i]; }
 };
 static_assert(sizeof(Vec3) == 3 * sizeof(double), "Vec3 must be 3 contiguous doubles");
+// layout-compatible stand-in for Eigen::Matrix<int,3,1> (reference include/common.h:23)
+struct Vec3I {
+  int32_t v[3];
+  Vec3I() : v{0, 0, 0} {}
+  Vec3I(int x, int y, int z) : v{x, y, z} {}
+  int32_t &operator[](int i) { return v[i]; }
+  int32_t operator[](int i) const { return v[i]; }
+};
 
 // pose[7] = tx,ty,tz,qw,qx,qy,qz — what Sophus::SE3(SO3(Quaterniond), Vector3d) is built from
 struct SE3 {
@@ -103,6 +111,31 @@ class mlmap {
     return stats_;
   }
 
+  // The reference exposes its two layers as public members and update_map() calls them one after the other
+  // (include/mlmap.h:107-108, src/mlmap.cpp:382-386):
+  //     awareness_map->input_pc_pose(pc_eigen, T_wb);    local_map->input_pc_pose_direct(awareness_map);
+  // the same two calls here, for callers that drive the layers themselves (frame sets readable in between)
+  struct awareness_layer {
+    mlmap *owner;
+    const mlm_frame_stats &input_pc_pose(const std::vector<Vec3> &PC_s, const SE3 &T_wb) {  // include/map_awareness.h:74
+      owner->check(mlm_awareness_input_pc_pose_f64(owner->h_, PC_s.empty() ? nullptr : PC_s[0].v, (int)PC_s.size(), T_wb.p,
+                                                   &owner->stats_), "mlm_awareness_input_pc_pose_f64");
+      return owner->stats_;
+    }
+  };
+  struct local_layer {
+    mlmap *owner;
+    const mlm_frame_stats &input_pc_pose_direct(awareness_layer *) {  // include/map_local.h:114
+      owner->check(mlm_local_input_pc_pose_direct(owner->h_, &owner->stats_), "mlm_local_input_pc_pose_direct");
+      owner->has_data = owner->map_updated = true;
+      return owner->stats_;
+    }
+  };
+  awareness_layer awareness_map_{this};
+  local_layer local_map_{this};
+  awareness_layer *awareness_map = &awareness_map_;
+  local_layer *local_map = &local_map_;
+
   void setFree_map_in_bound(Vec3 box_min, Vec3 box_max) {  // src/mlmap.cpp:388-407
     check(mlm_set_free_in_bound(h_, box_min.v, box_max.v), "mlm_set_free_in_bound");
   }
@@ -127,6 +160,12 @@ class mlmap {
   float getOdd(const Vec3 &pos_w) {
     float r;
     check(mlm_get_odd(h_, pos_w.v, 1, &r), "mlm_get_odd");
+    return r;
+  }
+  float getOdd(const Vec3I &glb_id, size_t subbox_id) {  // include/mlmap.h:128,227-235
+    float r;
+    const int32_t sub = (int32_t)subbox_id;
+    check(mlm_get_odd_at(h_, glb_id.v, &sub, 1, &r), "mlm_get_odd_at");
     return r;
   }
   Vec3 getOddGrad(const Vec3 &pos_w, size_t max_iter = 5) {

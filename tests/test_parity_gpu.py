@@ -513,3 +513,128 @@ def test_checkpoint_restore_round_trip_and_continuation():
     with pytest.raises(MlmError) as e:
         c.restore(image)
     assert e.value.code == 2
+
+
+def test_two_call_layer_interface_equals_the_fused_frame():
+    """awareness_map->input_pc_pose then local_map->input_pc_pose_direct (src/mlmap.cpp:382-386) as two calls: the frame's
+    sets are readable in between, and the map afterwards equals the oracle's (and the one-launch path's)"""
+    cfg = config_cfg_a()
+    two, one, orc = MLMap(cfg), MLMap(cfg), Oracle(cfg)
+    for k in range(5):
+        pose = scenes.corridor_trajectory_pose(k * 20)
+        img = scenes.corridor_depth_frame(cfg, pose, rows=240, cols=320, frame_idx=k)
+        st_a = two.awareness_input_depth(img, pose)
+        st_o = orc.integrate_depth(img, pose)
+        assert (st_a.n_points, st_a.n_inside, st_a.n_cast, st_a.n_hit_cells, st_a.n_miss_cells) == \
+               (st_o.n_points, st_o.n_inside, st_o.n_cast, st_o.n_hit_cells, st_o.n_miss_cells)
+        kg, pg = two.last_frame_hits()          # between the calls: the awareness layer's containers
+        ko, po = orc.last_frame_hits()
+        assert np.array_equal(kg, ko) and np.array_equal(pg.view(np.uint32), po.view(np.uint32))
+        assert np.array_equal(two.last_frame_misses(), orc.last_frame_misses())
+        with pytest.raises(MlmError):
+            two.integrate_depth(img, pose)      # a staged update must be fused first
+        st_g = two.local_input_pc_pose_direct()
+        one.integrate_depth(img, pose)
+        assert_frame_parity(two, orc, st_g, st_o, tag=f"two-call{k}")
+    assert_map_parity(two, orc, LO_TOL, tag="two-call")
+    a, b = two.export_map(), one.export_map()
+    for name in a:
+        assert np.array_equal(a[name].view(np.uint8), b[name].view(np.uint8)), name
+    # point-cloud entry + exploration mode through the same two calls
+    cfg = _lidar_small_cfg()
+    cfg.use_exploration_frontiers = 1
+    two, orc = MLMap(cfg), Oracle(cfg)
+    for k in range(3):
+        pose = scenes.lidar_loop_pose(k * 3)
+        pts = scenes.lidar_scan(pose, frame_idx=k, beams=32, azimuths=512, max_range=20.0)
+        two.awareness_input_pc_pose(pts, pose)
+        st_g, st_o = two.local_input_pc_pose_direct(), orc.integrate_points(pts, pose)
+        assert_frame_parity(two, orc, st_g, st_o, tag=f"two-call-explore{k}")
+    assert_map_parity(two, orc, LO_TOL, tag="two-call-explore")
+
+
+def test_sampled_projection_of_a_device_image():
+    """mlmapping_sample_cnt > 0 with the image already in device memory: same pixels, same number of rand() draws consumed
+    as mlmap::project_depth on the host image (src/mlmap.cpp:321-346), frame after frame"""
+    import ctypes as C
+    cfg = config_cfg_a()
+    cfg.sample_cnt = 300
+    dev, host, orc = MLMap(cfg), MLMap(cfg), Oracle(cfg)
+    C.CDLL("libc.so.6").srand(1)
+    for k in range(6):
+        pose = scenes.corridor_trajectory_pose(k * 11)
+        img = scenes.corridor_depth_frame(cfg, pose, frame_idx=k)
+        if k == 3:
+            img[:, ::2] = 0      # many invalid pixels: the quota is not reached, all 2*cnt tries are consumed
+            img[::2, :] = 0
+        d_img = dev.to_device(img)
+        st_d, st_h, st_o = dev.integrate_depth_device(d_img, 480, 640, pose), host.integrate_depth(img, pose), orc.integrate_depth(img, pose)
+        dev.device_free(d_img)
+        assert st_d.n_points == st_h.n_points == st_o.n_points, (k, st_d.n_points, st_h.n_points, st_o.n_points)
+        assert_frame_parity(dev, orc, st_d, st_o, tag=f"sampled-device{k}")
+    assert_map_parity(dev, orc, LO_TOL, tag="sampled-device")
+
+
+def test_get_odd_by_subbox_index():
+    """getOdd(const Vec3I &glb_id, size_t subbox_id) (mlmap.h:128,227-235): allocated, absent and collapsed subboxes"""
+    cfg = config_cfg_a()
+    cfg.use_exploration_frontiers = 1
+    gpu, orc = MLMap(cfg), Oracle(cfg)
+    for k in range(14):
+        pose = scenes.corridor_trajectory_pose(k * 10)
+        img = scenes.corridor_depth_frame(cfg, pose, frame_idx=k)
+        gpu.integrate_depth(img, pose), orc.integrate_depth(img, pose)
+    m = orc.export_map()
+    rs = np.random.RandomState(3)
+    sel = rs.randint(0, m["glb"].shape[0], 4000)
+    glb = m["glb"][sel].copy()
+    glb[:200] += 1000                      # absent subboxes -> 0.5
+    sub = rs.randint(0, 1000, 4000).astype(np.int32)
+    got = gpu.getOdd_at(glb, sub)
+    lo = np.where(m["collapsed"][sel] == 1, m["log_odds"][sel, 0], m["log_odds"][sel, sub]).astype(np.float64)
+    want = (np.power(10.0, lo) / (1 + np.power(10.0, lo)))
+    want[:200] = 0.5
+    assert m["collapsed"].sum() > 0 and np.abs(got.astype(np.float64) - want).max() <= 1.2e-7
+    if getattr(orc, "impl", "port") == "reference":   # the reference's own overload
+        ref = np.empty(4000, dtype=np.float32)
+        g32 = np.ascontiguousarray(glb.astype(np.int32))
+        orc.lib.orc_get_odd_at(orc.h, g32.ctypes.data, sub.ctypes.data, 4000, ref.ctypes.data)
+        assert np.abs(got.astype(np.float64) - ref).max() <= 1.2e-7
+
+
+def test_asynchronous_frames_of_several_maps_on_one_gpu():
+    """BASELINE config 5 on one GPU: frames of several agent maps submitted together, each handle with a share of the SMs
+    so that their cooperative launches are co-resident; every map equals its oracle"""
+    cfg = config_cfg_a()
+    n = 4
+    maps, orcs = [MLMap(cfg) for _ in range(n)], [Oracle(cfg) for _ in range(n)]
+    for m in maps:
+        m.set_sm_budget(148 // n)
+    for k in range(6):
+        dev, poses, imgs = [], [], []
+        for a in range(n):
+            pose = scenes.corridor_trajectory_pose(9 * k, y_offset=20.0 * a)
+            img = scenes.corridor_depth_frame(cfg, pose, rows=240, cols=320, frame_idx=k, seed_drop=1 + 10 * a, seed_noise=2 + 10 * a,
+                                              y_offset=20.0 * a)
+            dev.append(maps[a].to_device(img)), poses.append(pose), imgs.append(img)
+        for a in range(n):
+            maps[a].submit_depth_device(dev[a], 240, 320, poses[a])
+        for a in range(n):
+            st_g, st_o = maps[a].finish_frame(), orcs[a].integrate_depth(imgs[a], poses[a])
+            assert_frame_parity(maps[a], orcs[a], st_g, st_o, tag=f"async-agent{a}-frame{k}")
+            maps[a].device_free(dev[a])
+    for a in range(n):
+        assert_map_parity(maps[a], orcs[a], LO_TOL, tag=f"async-agent{a}")
+
+
+def test_cpp_mirror_harness_runs_on_the_device():
+    """examples/corridor_harness: the C++ mirror of class mlmap (mlmapping_b200/include/mlmap.hpp) over the C ABI, built by
+    __graft_entry__.build(); its own checks must pass on a device"""
+    import subprocess
+    from pathlib import Path
+    exe = Path(__file__).resolve().parent.parent / "examples" / "corridor_harness"
+    if not exe.exists():
+        pytest.skip("examples/corridor_harness not built (run __graft_entry__.build())")
+    res = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "frame" in res.stdout.lower() or "rays" in res.stdout.lower(), res.stdout[-500:]
