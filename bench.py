@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "10",
                  "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -119,10 +119,17 @@ def measured_peak_gbs():
     return 6650.0, "fallback"
 
 
+def cpu_impl():
+    """the CPU arm: the reference's OWN sources (oracle/_ref/libmlmap_ref.so, built from /root/reference by
+    oracle/ref_build/Makefile; the prebuilt file travels to the GPU box) when available, else the restatement"""
+    from oracle_binding import reference_available
+    return "reference" if reference_available() else "port"
+
+
 def run_cpu_sample(cfg, frames, poses, n_frames):
-    """oracle (port of the reference's algorithm) timed on the first n_frames of the workload, 1 core"""
+    """the reference's mapping code (cpu_impl()) timed on the first n_frames of the workload, 1 core"""
     from oracle_binding import Oracle
-    orc = Oracle(cfg, bookkeeping=False)
+    orc = Oracle(cfg, bookkeeping=False, impl=cpu_impl())
     rays, secs = 0, 0.0
     for k in range(n_frames):
         st = orc.integrate_depth(frames[k], poses[k])
@@ -133,9 +140,9 @@ def run_cpu_sample(cfg, frames, poses, n_frames):
 
 
 def run_reference(args, rank, world):
-    """CPU arm: the oracle (port of the reference's algorithm; the reference itself needs Eigen/PCL/ROS and
-    cannot be built here).  One map is single-threaded like the reference; with --gpus N the N independent
-    agent maps of the GPU arm run on N host threads (ctypes releases the GIL), one map each."""
+    """CPU arm: the reference's own mapping sources (oracle/_ref) when that library is present, else the restatement.
+    One map is single-threaded like the reference; with --gpus N the N independent agent maps of the GPU arm run on
+    N host threads (ctypes releases the GIL), one map each."""
     import threading
     from mlmapping_b200 import config_cfg_a
     if rank != 0:
@@ -146,10 +153,12 @@ def run_reference(args, rank, world):
     from oracle_binding import Oracle
     data = [gen_frames(cfg, total, agent=a) for a in range(n_agents)]
     res = [None] * n_agents
+    impl = cpu_impl()
+    orcs = [Oracle(cfg, bookkeeping=False, impl=impl) for _ in range(n_agents)]  # created one after the other (init is not re-entrant)
 
     def work(a):
         frames, poses = data[a]
-        orc = Oracle(cfg, bookkeeping=False)
+        orc = orcs[a]
         for k in range(args.warmup):
             orc.integrate_depth(frames[k], poses[k])
         rays, secs = 0, 0.0
@@ -173,8 +182,9 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rows": ROWS, "cols": COLS, "agents": n_agents,
-                   "timing": "steady_clock around project_depth+update_map (the region the reference times, src/mlmap.cpp:474-511)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_agents, "kind": "port", "sample": sample},
+                   "timing": "steady_clock around project_depth+update_map (the region the reference times, src/mlmap.cpp:474-511)",
+                   "cpu_code": "oracle/_ref: the reference's own sources" if impl == "reference" else "oracle/: restatement of the reference"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_agents, "kind": impl, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
@@ -251,7 +261,7 @@ def run_lidar(rank, world, local_rank, barrier, scans=12, warm=4):
                 torch.distributed.all_gather_object(gathered, mine)
             if rank == 0:
                 from oracle_binding import Oracle
-                oc = Oracle(cfg, bookkeeping=False)
+                oc = Oracle(cfg, bookkeeping=False, impl=cpu_impl())
                 for p, ps in data[:2]:
                     oc.integrate_points(p, ps)
                 o = oc.export_map()
@@ -362,8 +372,39 @@ def run_agents(rank, world, local_rank, barrier, steps, warm, n_queries, n_agent
     out = {"workload": "cfg_d_8_agent_maps_640x480_d0.1m (BASELINE config 5)", "agents": n_agents, "n_gpus": world,
            "agents_this_rank": mine, "scaling": "strong", "steps": steps,
            "rays_per_s": rays_all / (ms_sum * 1e-3), "ms_per_step": ms_sum / steps,
+           "mode": "a rank's maps one after the other, each frame ONE cooperative launch on all SMs",
            "us_per_frame_this_rank": {"median": float(np.median(frame_us)) if frame_us else None,
                                       "max": float(np.max(frame_us)) if frame_us else None}}
+    # ---- the same steps with the rank's maps in flight TOGETHER: every map gets a share of the SMs (its cooperative frame
+    # kernel uses that many CTAs), frames are submitted on all handles and then finished; fresh maps, same frames ----
+    if len(mine) > 1:
+        for m in maps.values():
+            m.close()
+        share = max(8, 148 // len(mine))
+        maps = {}
+        for a in mine:
+            maps[a] = MLMap(cfg, device=local_rank)
+            maps[a].set_sm_budget(share)
+            dev[a] = [(maps[a].to_device(f), p) for f, p in zip(*gen_frames(cfg, total, agent=a))]
+        first = maps[mine[0]]
+        c_secs, c_rays = 0.0, 0
+        for k in range(total):
+            first.flush_l2()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for a in mine:
+                maps[a].submit_depth_device(dev[a][k][0], ROWS, COLS, dev[a][k][1])
+            sts = [maps[a].finish_frame() for a in mine]
+            dt = time.perf_counter() - t0
+            if k >= warm:
+                c_secs += dt
+                c_rays += sum(st.n_points for st in sts)
+        barrier()
+        (c_max,), (c_rays_all,) = reduce_timing([1e3 * c_secs], [float(c_rays)], device="cuda" if world > 1 else None)
+        out["concurrent"] = {"mode": f"{len(mine)} maps of a rank in flight together, {share} SMs each (wall clock around submit-all / finish-all)",
+                             "rays_per_s": c_rays_all / (c_max * 1e-3), "ms_per_step": c_max / steps}
+        if out["concurrent"]["rays_per_s"] > out["rays_per_s"]:
+            out["best"] = "concurrent"
     # ---- queries against the agents' own maps: the stream is split over the ranks, each rank's share over its maps ----
     if n_queries and mine:
         qb, qe = split_range(n_queries, rank, world)
@@ -430,6 +471,90 @@ def run_agents(rank, world, local_rank, barrier, steps, warm, n_queries, n_agent
                                          "note": "rank 0 integrates, the frame's dirty subbox blocks are broadcast (NCCL) and "
                                                  "applied on every replica; wall clock incl. the update on rank 0"}
         m.close()
+    return out
+
+
+def run_other_configs(local_rank):
+    """what BASELINE.json's other single-GPU configurations cost: CFG-B frames (L515-like 1024x768 @ 0.05 m),
+    exploration-mode frames, and the first frame of a fresh map (libstdc++ rehash path, ~70 launches).  Device-resident
+    inputs, CUDA events on the library's stream, L2 flushed between frames; the CPU reference on a short sample."""
+    from mlmapping_b200 import MLMap, config_cfg_a, config_cfg_b, scenes
+    from oracle_binding import Oracle
+    peak, _ = measured_peak_gbs()
+    out = {}
+    # ---- CFG-B ----
+    cfg = config_cfg_b()
+    n, warm = 24, 6
+    frames, poses = [], []
+    for k in range(n):
+        pose = scenes.corridor_trajectory_pose(k, step=0.1)
+        frames.append(scenes.corridor_depth_frame(cfg, pose, rows=768, cols=1024, frame_idx=k, length=200.0))
+        poses.append(pose)
+    m = MLMap(cfg, device=local_rank)
+    dev = [m.to_device(f) for f in frames]
+    ms, rays, alg = 0.0, 0, 0
+    for k in range(n):
+        m.flush_l2()
+        m.timer_start()
+        st = m.integrate_depth_device(dev[k], 768, 1024, poses[k])
+        t = m.timer_stop_ms()
+        if k >= warm:
+            ms += t
+            rays += st.n_points
+            alg += 2 * 768 * 1024 + 56 + 10 * st.n_touched_voxels + 6000 * st.n_new_submaps
+    pin = m.pinned_array(frames[0].shape, np.uint16)
+    pin[...] = frames[warm - 1]
+    m.integrate_depth_ptr(pin.ctypes.data, 768, 1024, 2 * 1024, poses[warm - 1])  # first host-buffer call allocates the staging
+    e_s = 0.0
+    for k in range(warm, n):
+        pin[...] = frames[k]
+        m.flush_l2()
+        t0 = time.perf_counter()
+        m.integrate_depth_ptr(pin.ctypes.data, 768, 1024, 2 * 1024, poses[k])
+        e_s += time.perf_counter() - t0
+    m.close()
+    orc = Oracle(cfg, bookkeeping=False, impl=cpu_impl())
+    c_rays, c_s = 0, 0.0
+    for k in range(4):
+        st = orc.integrate_depth(frames[k], poses[k])
+        if k >= 1:
+            c_rays += st.n_points
+            c_s += orc.last_seconds
+    orc.close()
+    out["cfg_b_l515_1024x768_d0.05m"] = {
+        "us_per_frame": 1e3 * ms / (n - warm), "rays_per_s": rays / (ms * 1e-3), "e2e_us_per_frame": 1e6 * e_s / (n - warm),
+        "alg_GB_per_s": alg / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak,
+        "cpu_baseline": {"value": c_rays / c_s, "unit": UNIT, "cores": 1, "kind": cpu_impl(), "us_per_frame": 1e6 * c_s / 3,
+                         "sample": "frames 1-3 of the same series on the CPU oracle, single thread"}}
+    # ---- exploration mode (use_exploration_frontiers) and the first frame of a fresh map, CFG-A ----
+    cfg = config_cfg_a()
+    fr, ps = gen_frames(cfg, 30)
+    cfg_e = config_cfg_a()
+    cfg_e.use_exploration_frontiers = 1
+    m = MLMap(cfg_e, device=local_rank)
+    dev = [m.to_device(f) for f in fr]
+    ms = 0.0
+    for k in range(30):
+        m.flush_l2()
+        m.timer_start()
+        m.integrate_depth_device(dev[k], ROWS, COLS, ps[k])
+        t = m.timer_stop_ms()
+        if k >= 10:
+            ms += t
+    m.close()
+    out["cfg_a_exploration_mode"] = {"us_per_frame": 1e3 * ms / 20, "note": "frontier sets + release pass: direct launches with one host check"}
+    firsts = []
+    for rep in range(3):
+        m = MLMap(cfg, device=local_rank)
+        d0 = m.to_device(fr[0])
+        m.flush_l2()
+        m.timer_start()
+        st = m.integrate_depth_device(d0, ROWS, COLS, ps[0])
+        firsts.append(1e3 * m.timer_stop_ms())
+        assert st.ordering_slow_path == 1
+        m.close()
+    out["cfg_a_first_frame_of_a_fresh_map"] = {"us": float(np.median(firsts)),
+                                               "note": "crosses the libstdc++ rehash chain 1 -> 13 -> ... (staged re-sequencing, ~70 launches)"}
     return out
 
 
@@ -686,13 +811,18 @@ def main():
             out["lidar"] = lidar
         if agents:
             out["agents"] = agents
+        if world == 1 and not args.no_cpu:
+            try:
+                out["other_configs"] = run_other_configs(local_rank)
+            except Exception as e:
+                out["other_configs"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if not args.no_cpu:
             nf = min(args.cpu_frames, total)
             c_rays, c_s = run_cpu_sample(cfg, frames, poses, nf)
             if queries:
                 from mlmapping_b200 import scenes as _sc
                 from oracle_binding import Oracle
-                orc = Oracle(cfg, bookkeeping=False)
+                orc = Oracle(cfg, bookkeeping=False, impl=cpu_impl())
                 for k in range(min(20, total)):
                     orc.integrate_depth(frames[k], poses[k])
                 mo = orc.export_map()
@@ -700,14 +830,47 @@ def main():
                 qp = _sc.query_positions(300000, mo["glb"].min(0) * dd, (mo["glb"].max(0) + 1) * dd, seed=5)
                 t0 = time.perf_counter(); orc.getOdd(qp[:120000]); orc.getOccupancy(qp[120000:240000]); orc.getOddGrad(qp[240000:])
                 tq = time.perf_counter() - t0
-                out["queries"]["cpu_baseline"] = {"value": 300000 / tq, "unit": "queries/s", "cores": 1, "kind": "port",
+                out["queries"]["cpu_baseline"] = {"value": 300000 / tq, "unit": "queries/s", "cores": 1, "kind": cpu_impl(),
                                                   "sample": "300k queries (same 4:4:2 mix) on a 20-frame oracle map"}
+                # all host cores: getOddGrad keeps its search state in members of the map (like the reference, mlmap.h:100-101),
+                # so every thread integrates its own copy of the map and answers one slice of the same stream
+                import threading
+                ncore = min(os.cpu_count() or 1, 32)
+                chunks = np.array_split(np.arange(300000), ncore)
+                ready, go = threading.Barrier(ncore + 1), threading.Barrier(ncore + 1)
+                done_t = [0.0] * ncore
+
+                o2s = [Oracle(cfg, bookkeeping=False, impl=cpu_impl()) for _ in range(ncore)]
+
+                def _q(i, ix):
+                    o2 = o2s[i]
+                    for k in range(min(20, total)):
+                        o2.integrate_depth(frames[k], poses[k])
+                    a = ix[ix < 120000]
+                    b = ix[(ix >= 120000) & (ix < 240000)]
+                    c = ix[ix >= 240000]
+                    ready.wait()
+                    go.wait()
+                    if len(a): o2.getOdd(qp[a])
+                    if len(b): o2.getOccupancy(qp[b])
+                    if len(c): o2.getOddGrad(qp[c])
+                    done_t[i] = time.perf_counter()
+                    o2.close()
+                th = [threading.Thread(target=_q, args=(i, ix)) for i, ix in enumerate(chunks)]
+                [t_.start() for t_ in th]
+                ready.wait()
+                t0 = time.perf_counter()
+                go.wait()
+                [t_.join() for t_ in th]
+                tq_all = max(done_t) - t0
+                out["queries"]["cpu_baseline_all_cores"] = {"value": 300000 / tq_all, "unit": "queries/s", "cores": ncore, "kind": cpu_impl(),
+                                                            "sample": "the same 300k queries split over the host cores, one map copy per thread"}
                 orc.close()
             if lidar and "error" not in lidar:
                 from mlmapping_b200 import config_cfg_c, scenes as _sc2
                 from oracle_binding import Oracle as _Orc
                 cfg_c = config_cfg_c()
-                oc = _Orc(cfg_c, bookkeeping=False)
+                oc = _Orc(cfg_c, bookkeeping=False, impl=cpu_impl())
                 l_rays, l_s = 0, 0.0
                 for k in range(3):
                     pose = _sc2.lidar_loop_pose(k)
@@ -716,9 +879,9 @@ def main():
                         l_rays += st_l.n_points
                         l_s += oc.last_seconds
                 oc.close()
-                out["lidar"]["cpu_baseline"] = {"value": l_rays / l_s, "unit": UNIT, "cores": 1, "kind": "port",
+                out["lidar"]["cpu_baseline"] = {"value": l_rays / l_s, "unit": UNIT, "cores": 1, "kind": cpu_impl(),
                                                 "sample": "scans 1-2 of the same loop on the CPU oracle, single thread"}
-            out["cpu_baseline"] = {"value": c_rays / c_s, "unit": UNIT, "cores": 1, "kind": "port",
+            out["cpu_baseline"] = {"value": c_rays / c_s, "unit": UNIT, "cores": 1, "kind": cpu_impl(),
                                    "sample": f"first {nf} frames of {WORKLOAD} on the CPU oracle, single thread "
                                              f"({os.cpu_count()} host cores present)",
                                    "us_per_frame": 1e6 * c_s / nf}

@@ -179,8 +179,8 @@ __device__ __forceinline__ float grad_lo(const MapParams &P, const DeviceBuffers
   return 0.0f;
 }
 
-__global__ void __launch_bounds__(256) k_get_odd_grad(MapParams P, DeviceBuffers D, const double *pos, size_t n,
-                                                      int max_iter, double *out) {  // mlmap.h:237-295
+__global__ void __launch_bounds__(256, 4) k_get_odd_grad(MapParams P, DeviceBuffers D, const double *pos, size_t n,
+                                                         int max_iter, double *out) {  // mlmap.h:237-295
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double px = pos[3 * i], py = pos[3 * i + 1], pz = pos[3 * i + 2];
@@ -189,50 +189,54 @@ __global__ void __launch_bounds__(256) k_get_odd_grad(MapParams P, DeviceBuffers
   const float lo0 = grad_lo(P, D, blk0, c.sub);
   const float ori_odd = logit_inv_f(lo0);
   float min_odd = ori_odd;
-  // The six probes walk along +z,-z,+y,-y,+x,-x (subbox_neighbors row order, src/map_local.cpp:78-120):
-  // only the coordinate on the probe's own axis changes, so each direction keeps (cell coordinate on its
-  // axis, subbox index on its axis, pool block); the hash lookup is repeated only when a subbox border
-  // is crossed.  Fully unrolled so the per-direction state lives in registers.
+  // The six probes walk along +z,-z,+y,-y,+x,-x (subbox_neighbors row order, src/map_local.cpp:78-120): only the
+  // coordinate on the probe's own axis changes.  After k steps probe d sits at cell c_axis +- k of the origin's subbox
+  // or, once it has left it, of the neighbouring subbox in that direction.  The neighbours a walk of max_iter steps can
+  // reach are looked up ONCE, up front, where the whole warp is converged (a lookup inside the walk runs for the two or
+  // three lanes that happen to cross a border at that step: 30 such sites cost half of the kernel's instructions);
+  // a walk longer than a subbox falls back to a lookup per further crossing.
   const int cxyz[3] = {c.sub % P.n, (c.sub / P.n) % P.n, c.sub / (P.n * P.n)};
   const int stride[3] = {1, P.n, P.n * P.n};
-  int ca[6], ga[6], blk[6];
+  int blk_nb[6];
 #pragma unroll
   for (int d = 0; d < 6; d++) {
-    ca[d] = cxyz[2 - (d >> 1)];
-    ga[d] = c.g[2 - (d >> 1)];
-    blk[d] = blk0;
+    const int axis = 2 - (d >> 1);
+    const bool reach = (d & 1) ? (cxyz[axis] - max_iter < 0) : (cxyz[axis] + max_iter >= P.n);
+    blk_nb[d] = -1;
+    if (reach) {
+      int g[3] = {c.g[0], c.g[1], c.g[2]};
+      g[axis] += (d & 1) ? -1 : 1;
+      blk_nb[d] = grad_block(P, D, g);
+    }
   }
-  int best_d = -1;
+  int best_d = -1, best_k = 0;
   // A round of the reference visits the six neighbours in order and keeps the first one with the strictly lowest odd
   // below the running minimum; a round that finds one ends the search.  logit_inv is monotone non-decreasing in the
   // log-odds (also after the cast to float), so the round's winner is the neighbour with the lowest log-odds (the first
   // of those), unless an EARLIER neighbour with a slightly higher log-odds rounds to the same float odd; those rare
   // near-ties (within kTie, far more than one float ulp of the odd anywhere in the clamped range) are settled with
   // their own pow.  So a round costs ONE pow at a point where the whole warp is converged, instead of up to six at
-  // divergent ones (6980 instructions per query before, 83 % of them in diverged pow calls).
+  // divergent ones (6980 instructions per query in round 1, 83 % of them in diverged pow calls).
   const float kTie = 1e-2f;
-  for (int iter = 0; iter < max_iter && best_d < 0; iter++) {
+  for (int k = 1; k <= max_iter && best_d < 0; k++) {
     float lo_d[6];
 #pragma unroll
     for (int d = 0; d < 6; d++) {
       const int axis = 2 - (d >> 1);
-      ca[d] += (d & 1) ? -1 : 1;
-      bool crossed = false;
-      if (ca[d] >= P.n) {
-        ca[d] = 0;
-        ga[d] += 1;
-        crossed = true;
-      } else if (ca[d] < 0) {
-        ca[d] = P.n - 1;
-        ga[d] -= 1;
-        crossed = true;
+      int p = cxyz[axis] + ((d & 1) ? -k : k);
+      int blk = blk0;
+      if (p >= P.n || p < 0) {
+        int hops = p >= P.n ? p / P.n : -((-p + P.n - 1) / P.n);   // subboxes left behind (1 unless max_iter > n)
+        p -= hops * P.n;
+        if (hops == 1 || hops == -1) {
+          blk = blk_nb[d];
+        } else {
+          int g[3] = {c.g[0], c.g[1], c.g[2]};
+          g[axis] += hops;
+          blk = grad_block(P, D, g);
+        }
       }
-      if (crossed) {
-        int g[3] = {c.g[0], c.g[1], c.g[2]};
-        g[axis] = ga[d];
-        blk[d] = grad_block(P, D, g);
-      }
-      lo_d[d] = grad_lo(P, D, blk[d], c.sub + (ca[d] - cxyz[axis]) * stride[axis]);
+      lo_d[d] = grad_lo(P, D, blk, c.sub + (p - cxyz[axis]) * stride[axis]);
     }
     // lowest log-odds of the round, first direction wins ties
     int m = 0;
@@ -248,6 +252,7 @@ __global__ void __launch_bounds__(256) k_get_odd_grad(MapParams P, DeviceBuffers
     if (!(odd_m < min_odd)) continue;     // rounds to the origin's odd (or above): not strictly lower
     min_odd = odd_m;
     best_d = m;
+    best_k = k;
     // earlier directions whose log-odds is a hair above the minimum: same float odd -> the reference keeps the earlier one
 #pragma unroll
     for (int d = 0; d < 5; d++)
@@ -261,9 +266,12 @@ __global__ void __launch_bounds__(256) k_get_odd_grad(MapParams P, DeviceBuffers
   double gx = 0.0, gy = 0.0, gz = 0.0;
   if (best_d >= 0) {
     const int axis = 2 - (best_d >> 1);
+    int p = cxyz[axis] + ((best_d & 1) ? -best_k : best_k);
+    const int hops = p >= P.n ? p / P.n : (p < 0 ? -((-p + P.n - 1) / P.n) : 0);
+    p -= hops * P.n;
     int best_g[3] = {c.g[0], c.g[1], c.g[2]};
-    best_g[axis] = ga[best_d];
-    const int best_sub = c.sub + (ca[best_d] - cxyz[axis]) * stride[axis];
+    best_g[axis] += hops;
+    const int best_sub = c.sub + (p - cxyz[axis]) * stride[axis];
     // subbox_id2xyz_glb_vec (map_local.h:208-213) - pos, times (double)(float)(ori - min)
     int x = best_sub % P.n, y = (best_sub / P.n) % P.n, z = best_sub / (P.n * P.n);
     double s = (double)__fsub_rn(ori_odd, min_odd);

@@ -21,10 +21,17 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "launch__shared_mem_per_block_dynamic",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio"]
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
+        # atomic throughput (north star): L2 sectors touched by atomics / reductions, shared-memory atomics
+        "lts__t_sectors_op_atom.sum", "lts__t_sectors_op_red.sum", "smsp__inst_executed_op_shared_atom.sum",
+        "smsp__inst_executed_op_global_atom.sum", "smsp__inst_executed_op_global_red.sum",
+        # warp divergence (north star): active threads per executed warp instruction (32 = none)
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__thread_inst_executed_per_inst_executed.pct"]
 UNITS = {}
 summary = {}
-for name in ["prof_frame", "prof_queries"]:
+for name in ["prof_frame", "prof_queries", "prof_lidar", "prof_shard"]:
     rep = ROOT / "gpurun_out" / f"{name}_{tag}.ncu-rep"
     if not rep.exists():
         continue
@@ -47,7 +54,7 @@ if ll.exists():
     med = {k: sorted(v)[len(v) // 2] for k, v in acc.items()}
     phases = {k: v for k, v in med.items() if k.startswith(("k_project", "k_column", "k_fuse"))}
     tot = sum(phases.values())
-    lines = [f"# ncu launch list of `python bench.py --steps 6 --warmup 3 --no-cpu` ({tag}); cold-cache, serialised: compare SHARES",
+    lines = [f"# ncu launch list of `python bench.py --steps 6 --warmup 3 --no-cpu --no-lidar --no-agents` ({tag}); cold-cache, serialised: compare SHARES",
              "# a timed step launches ONE map kernel, k_frame (share 1.0 of the step); k_project / k_column / k_fuse are the same three",
              "# phases run as stand-alone kernels by bench.py's profiling pass: their shares split the step",
              "kernel,launches,median_us,share_of_step"]
