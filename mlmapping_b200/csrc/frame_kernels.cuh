@@ -1498,12 +1498,18 @@ __device__ __constant__ uint32_t c_bucket_chain[kBucketChainLen] = {
     42043,  85229,  172933,  351061,  712697,  1447153,  2938679,  5967347,  12117689, 24607243, 49969847, 101473717};
 
 // frame counters -> mapped pinned host memory (zero-copy store; visible to the host after the stream sync)
-__device__ __forceinline__ void publish_counters(const DeviceBuffers &D, FrameCounters *fc) {
+__device__ __forceinline__ void publish_counters(const DeviceBuffers &D, FrameCounters *fc, uint32_t frame_seq = 0) {
   // called by one whole warp: lane i moves word i (independent L2 reads and PCIe writes, not a serial chain)
   const int lane = threadIdx.x & 31;
-  const int n = (int)(sizeof(FrameCounters) / sizeof(int));
+  const int n = (int)(sizeof(FrameCounters) / sizeof(int)) - 1;   // all words but the sequence number
   for (int i = lane; i < n; i += 32) reinterpret_cast<volatile int *>(D.host_fc)[i] = __ldcg(reinterpret_cast<const int *>(fc) + i);
-  // no system-scope fence: the host reads the counters only after the stream has drained, which orders them
+  // the sequence number goes last, behind a system-scope fence: a host that polls it (instead of waiting for the stream
+  // to drain) finds the counters of that frame complete
+  __syncwarp();
+  if (lane == 0 && frame_seq) {
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(&D.host_fc->seq) = frame_seq;
+  }
 }
 
 // ---- K5: clamped log-odds fusion, one thread per touched cell (map_local.cpp:147-207) ---------------
@@ -1530,7 +1536,7 @@ __device__ __forceinline__ void fuse_body(const MapParams &P, DeviceBuffers &D, 
       }
     }
     __syncthreads();
-    if (s_ovf_last && threadIdx.x < 32) publish_counters(D, fc);
+    if (s_ovf_last && threadIdx.x < 32) publish_counters(D, fc, F.frame_seq);
     return;
   }
   const int n = min(fc->n_touched, P.max_touched);
@@ -1737,7 +1743,7 @@ __device__ __forceinline__ void fuse_body(const MapParams &P, DeviceBuffers &D, 
         __threadfence();
       }
       __syncwarp();
-      publish_counters(D, fc);
+      publish_counters(D, fc, F.frame_seq);
     }
   }
 

@@ -11,6 +11,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <chrono>
 #include <string>
@@ -211,6 +212,8 @@ struct mlm_map {
   bool frame_pending = false;
   int pending_mode = 0;
   int frame_sms = 0;           // CTAs of k_frame when the handle shares the GPU with other maps (0: one per SM)
+  int poll_counters = 1;       // the host polls the frame's sequence word in mapped memory instead of draining the stream
+  uint32_t frame_seq = 0;
   int *d_sample_info = nullptr;  // sampled projection of a device image: {points, tries used}
   uint2 *d_sample_tries = nullptr;
   cudaEvent_t sev[MLM_NUM_SHARD_KERNELS + 1] = {};
@@ -566,6 +569,7 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
   F.stage_only = 0;
   F.inline_resolve = 0;
   F.skip_flag = nullptr;
+  F.frame_seq = 0;
   F.tbits = 1;
   while ((1ll << F.tbits) < (long long)std::max(N, 2)) F.tbits++;
   F.tile_pts = kProjThreads * 2;  // stand-alone k_project: 512 threads x 2 rounds per warp
@@ -667,6 +671,10 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
     // one tile per CTA when the frame allows it: N points dealt evenly, in 32-point rounds, at most 128 per warp
     Fk.tile_pts = std::min(kProjMaxPts * kColThreads, std::max(32, (((N + G - 1) / G) + 31) & ~31));
     F.tile_pts = Fk.tile_pts;
+    if (h->poll_counters && !h->async_call) {
+      Fk.frame_seq = F.frame_seq = ++h->frame_seq ? h->frame_seq : ++h->frame_seq;
+      h->h_fc->seq = 0;
+    }
     Fk.inline_resolve = F.inline_resolve = 1;
     const int gi = mode;
     cudaKernelNodeParams np = {};
@@ -742,8 +750,28 @@ int run_frame_complete(mlm_map *h, mlm_frame_stats *stats) {
   cudaStream_t s = h->stream;
   FrameParams &F = *h->h_fp;
   const bool prof = h->profiling != 0;
-  CUDA_TRY(cudaStreamSynchronize(s));
-  CUDA_TRY(cudaGetLastError());
+  bool polled = false;
+  if (F.frame_seq) {
+    // the frame kernel stores the counters, then its sequence number, in mapped host memory before it rearms the next
+    // frame's scratch: poll that word (a PCIe write away) instead of waiting for the stream to drain; what follows on
+    // the stream is ordered behind the kernel anyway.  Falls back to the stream after 2 ms (a frame that takes that long
+    // is on the rehash path or in trouble).
+    volatile uint32_t *seq = &h->h_fc->seq;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int spin = 0;; spin++) {
+      if (*seq == F.frame_seq) {
+        polled = true;
+        break;
+      }
+      if ((spin & 1023) == 1023 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2)) break;
+      __builtin_ia32_pause();
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  }
+  if (!polled) {
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaGetLastError());
+  }
 
   if (prof)
     for (int i = 0; i < MLM_NUM_FRAME_KERNELS; i++) cudaEventElapsedTime(&h->kms[i], h->kev[i], h->kev[i + 1]);
@@ -1139,6 +1167,7 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   } while (0)
 
   CUDA_TRY_H(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  if (const char *e = getenv("MLM_NO_POLL")) if (atoi(e)) h->poll_counters = 0;
   CUDA_TRY_H(cudaEventCreate(&h->ev0));
   CUDA_TRY_H(cudaEventCreate(&h->ev1));
   CUDA_TRY_H(cudaMallocHost((void **)&h->h_fp, sizeof(FrameParams)));
@@ -1209,7 +1238,7 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   TRY(dev_alloc(h, &D.grid_bar, 1));
   TRY(dev_alloc(h, &D.rec_lin, (size_t)P.max_points));
   TRY(dev_alloc(h, &D.rec_col, (size_t)P.max_points));
-  TRY(dev_alloc(h, &D.rec_dir, (size_t)(std::max((P.max_points + 1023) / 1024, h->sm_count + 1)) * P.nCol));
+  TRY(dev_alloc(h, &D.rec_dir, (size_t)(std::max((P.max_points + 1023) / 1024, 2 * h->sm_count + 2)) * P.nCol));
   TRY(dev_alloc(h, &D.phi_hist, (size_t)P.nCol));
   TRY(dev_alloc(h, &D.phi_bound, (size_t)P.nCol));
   TRY(dev_alloc(h, &D.col_scratch, (size_t)2 * P.max_points * P.contrib_per_point));
@@ -1406,6 +1435,9 @@ int mlm_integrate_depth_u16(mlm_handle h, const uint16_t *img, int rows, int col
       return run_frame(h, 1, a2.devicePointer, rows, cols, 0, T_wb, stats);
     cudaGetLastError();
   }
+  // Overlapping the transfer with the projection was measured twice on B200 and lost both times against this one DMA
+  // (102.7 us per frame end to end): a second DMA for the lower half of the rows with a ready word the tiles wait for
+  // (+6 us: the extra copies cost more than the overlap returns), and reading that half in place over PCIe (+2 to +7 us).
   CUDA_TRY(cudaMemcpyAsync(h->d_input, src, bytes, cudaMemcpyHostToDevice, h->stream));
   return run_frame(h, 1, h->d_input, rows, cols, 0, T_wb, stats);
 }

@@ -109,6 +109,7 @@ struct FrameParams {
   int inline_resolve; // 1 (k_frame): the first thread to touch a subbox resolves / allocates it right away
   int parity;       // frame & 1: selects the double-buffered counters / activation stamps
   int order_mode;   // 0: stamps are (bucket activation, first-insert time); 1: virtual sequence positions
+  uint32_t frame_seq;        // published to the host counters last: the host may poll it instead of waiting for the stream
   const int *skip_flag;  // sharded scans: when non-null and *skip_flag != 0 the owner-side kernels (resolve, fuse) return at
                          // once; set on device when the gathered hit count calls for the rehash path (the host re-launches)
 };
@@ -126,6 +127,7 @@ struct FrameCounters {
   int n_miss_list;        // exploration mode: entries of the per-frame miss list
   int n_obs;              // exploration mode: subboxes handed to the release pass (observed_subboxes)
   int n_released;         // subboxes collapsed by the release pass this frame
+  uint32_t seq;           // host copy only: frame_seq of the frame these counters belong to, stored after everything else
 };
 
 struct DeviceBuffers {
