@@ -1355,11 +1355,9 @@ __device__ __forceinline__ void column_phase(const MapParams &P, DeviceBuffers &
   constexpr int kCovered = (int)0x80000000;
   if (sorted && P.split && P.merge && s_nactive > (int)gridDim.x) {
     __shared__ int s_mh[64];
-    __shared__ int s_T, s_sh2, s_need, s_wcut;
-    __shared__ long long s_wtot;
+    __shared__ int s_T, s_sh2, s_need;
     if (tid < 64) s_mh[tid] = 0;
     if (tid == 0) {
-      s_wtot = 0;
       int sh2 = 0;
       while (((2 * s_wmax) >> sh2) > 63) sh2++;
       s_sh2 = sh2;
@@ -1367,21 +1365,16 @@ __device__ __forceinline__ void column_phase(const MapParams &P, DeviceBuffers &
     __syncthreads();
     const int sh2 = s_sh2;
     for (int phi = tid; phi < P.nPhi; phi += blockDim.x)
-      if (s_nrec[2 * phi] > 0 && s_nrec[2 * phi + 1] > 0) {
-        atomicAdd(&s_mh[(s_wgt[2 * phi] + s_wgt[2 * phi + 1]) >> sh2], 1);
-        atomicAdd(reinterpret_cast<unsigned long long *>(&s_wtot), (unsigned long long)(s_wgt[2 * phi] + s_wgt[2 * phi + 1]));
-      }
+      if (s_nrec[2 * phi] > 0 && s_nrec[2 * phi + 1] > 0) atomicAdd(&s_mh[(s_wgt[2 * phi] + s_wgt[2 * phi + 1]) >> sh2], 1);
     __syncthreads();
     if (tid == 0) {
       int c2 = 0;
       for (int b = 0; b < 64; b++) c2 += s_mh[b];                       // columns with both halves active
-      // Down to one item per CTA when that is possible; else every column whole (a whole column costs less than its two
-      // halves: CFG-C, 360 columns on 148 CTAs: all whole 175 us, a mix that fills the rounds exactly 193 us, all halves
-      // 210 us) except the few much heavier than the average, which stay split: the heaviest item bounds the phase
-      // whenever there are about as many items as CTAs (2 ranks: 180 columns, the heaviest whole one takes 107 us).
-      const int G = (int)gridDim.x;
-      const int need = min(c2, s_nactive - G);
-      s_wcut = (s_nactive - c2 > G) ? (int)((14ll * s_wtot) / (10ll * max(c2, 1))) : 0x7fffffff;   // 1.4 x mean weight of a whole column
+      // Down to one item per CTA when that is possible, else every column whole: with more than one round the total work
+      // decides, and a whole column costs less than its two halves.  Measured on CFG-C (360 lit columns, 148 CTAs): all
+      // whole 175 us; a mix that fills the rounds exactly 193 us; whole except the columns 1.4x heavier than average
+      // 199 us; all halves 210 us.  With 2 ranks (180 columns each): 120 / 135 / 123 us.
+      const int need = min(c2, s_nactive - (int)gridDim.x);
       int cum = 0, T = -1;
       for (int b = 0; b < 64 && need > 0; b++) {
         cum += s_mh[b];
@@ -1415,7 +1408,7 @@ __device__ __forceinline__ void column_phase(const MapParams &P, DeviceBuffers &
       if (n0 > 0 && n1 > 0) {
         const int w = s_wgt[2 * phi] + s_wgt[2 * phi + 1];
         const int bkt = w >> sh2;
-        if ((bkt < s_T || (bkt == s_T && s_rank[phi] < take)) && w <= s_wcut) {
+        if (bkt < s_T || (bkt == s_T && s_rank[phi] < take)) {
           s_wgt[2 * phi] = w;
           s_nrec[2 * phi] = -(n0 + n1);
           s_nrec[2 * phi + 1] = kCovered;
