@@ -689,6 +689,9 @@ __device__ __forceinline__ void resolve_one(const MapParams &P, const FrameParam
       }
       if (k == key) {
         block = __ldcg(&D.ht_val[slot]);
+        // a subbox created while the pool was exhausted stays without a block: every frame that touches it again
+        // reports the exhaustion (its updates are dropped), not only the frame that hit it first
+        if (block == kBlockUnusable) fc->error = kErrPool;
         done = true;
         break;
       }

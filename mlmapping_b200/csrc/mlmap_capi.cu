@@ -212,6 +212,7 @@ struct mlm_map {
   bool frame_pending = false;
   int pending_mode = 0;
   int frame_sms = 0;           // CTAs of k_frame when the handle shares the GPU with other maps (0: one per SM)
+  bool poisoned = false;       // a frame failed after it had staged its sets: the staging was never consumed
   int poll_counters = 1;       // the host polls the frame's sequence word in mapped memory instead of draining the stream
   uint32_t frame_seq = 0;
   int *d_sample_info = nullptr;  // sampled projection of a device image: {points, tries used}
@@ -460,7 +461,10 @@ int run_frame_explore(mlm_map *h, int mode, int N, mlm_frame_stats *stats) {
   int slow = 0;
   uint32_t order_B = h->bucket_count;
   if (mid.error == 0) {
-    if (mid.n_hit > h->sort_cap || mid.n_miss_list > h->sort_cap) return MLM_ERR_CAPACITY;
+    if (mid.n_hit > h->sort_cap || mid.n_miss_list > h->sort_cap) {
+      h->poisoned = true;  // the frame's staging stays unconsumed
+      return MLM_ERR_CAPACITY;
+    }
     if ((uint32_t)mid.n_hit > h->bucket_count) {
       slow = 1;
       int rc = order_slow_path(h, mid.n_hit, 0, h->bucket_count, &order_B);
@@ -517,6 +521,11 @@ int run_frame_explore_direct(mlm_map *h, int slow, uint32_t order_B, mlm_frame_s
 // mode: 0 = points, 1 = full depth image, 2 = sampled depth pixels (d_in = uint2 {pixel, raw} x n_points)
 int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_points, const double T_wb[7],
               mlm_frame_stats *stats) {
+  if (h->poisoned) {
+    g_last_error = "an earlier frame failed after staging its sets (capacity); the handle refuses further frames: restore a "
+                   "checkpoint into a fresh handle";
+    return MLM_ERR_CAPACITY;
+  }
   if (h->staged || h->frame_pending) {
     g_last_error = h->staged ? "an awareness-layer update is waiting for mlm_local_input_pc_pose_direct"
                              : "a submitted frame is waiting for mlm_frame_finish";
@@ -782,11 +791,15 @@ int run_frame_complete(mlm_map *h, mlm_frame_stats *stats) {
     const int n = h->h_fc->n_hit;
     if (n > h->sort_cap) {
       g_last_error = "hit count exceeds ordering scratch";
+      h->poisoned = true;  // the frame's staging stays unconsumed
       return MLM_ERR_CAPACITY;
     }
     uint32_t Bf = 0;
     int rc = order_slow_path(h, n, 0, h->bucket_count, &Bf);
-    if (rc != MLM_OK) return rc;
+    if (rc != MLM_OK) {
+      h->poisoned = true;
+      return rc;
+    }
     order_B = Bf;
     F.bucket_count = Bf;
     F.bucket_c64 = pow64_mod(F.bucket_count);
