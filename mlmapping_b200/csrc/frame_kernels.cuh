@@ -146,6 +146,13 @@ __device__ __forceinline__ uint32_t ht_hash(uint64_t k) {  // splitmix64 finalis
   k ^= k >> 31;
   return (uint32_t)k;
 }
+// sharded maps: the rank that owns subbox g (every rank computes the same hash)
+__device__ __forceinline__ int subbox_owner(const int g[3], int world) {
+  uint64_t key;
+  if (world <= 1 || !pack_glb(g, key)) return 0;
+  const uint32_t hsh = ht_hash(key);
+  return (world & (world - 1)) == 0 ? (int)(hsh & (uint32_t)(world - 1)) : (int)(hsh % (uint32_t)world);
+}
 // lookup that also reports the hash slot (collapsed subboxes keep their element 0 in per-slot arrays)
 __device__ __forceinline__ int ht_find_slot(const MapParams &P, const DeviceBuffers &D, const int g[3], uint32_t &slot_out) {
   uint64_t key;
@@ -711,7 +718,6 @@ __device__ __forceinline__ void resolve_subboxes(const MapParams &P, const Frame
 
 __device__ __forceinline__ void touch_subbox(const MapParams &P, const FrameParams &F, DeviceBuffers &D,
                                              FrameCounters *fc, const int g[3]) {
-  if (F.stage_only) return;  // sharded staging: the subbox belongs to its owner rank
   int ls = lsg_index(P, F, g);
   if (ls < 0) {
     fc->error = kErrInternal;
@@ -1145,11 +1151,19 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
         }
         int old = atomicExch(&D.lvg[lv].x, idx);
         D.hit_next[idx] = old;
+        // sharded staging: voxels of subboxes another rank owns go to their own list (the push kernel sends them away),
+        // the others are staged exactly as on one GPU
+        const bool remote = F.stage_only && subbox_owner(cr.g, F.shard_world) != F.shard_rank;
         if (old == kLvgEmpty) {
-          int tp = agg_inc(&fc->n_touched);
-          if (tp < P.max_touched) D.touched[tp] = (uint32_t)lv | kTouchedHitTag; else fc->error = kErrCapacity;
+          if (!remote) {
+            int tp = agg_inc(&fc->n_touched);
+            if (tp < P.max_touched) D.touched[tp] = (uint32_t)lv | kTouchedHitTag; else fc->error = kErrCapacity;
+          } else {
+            int tp = agg_inc(&fc->n_touched_remote);
+            if (tp < P.max_touched) D.touched_remote[tp] = (uint32_t)lv | kTouchedHitTag; else fc->error = kErrCapacity;
+          }
         }
-        touch_subbox(P, F, D, fc, cr.g);
+        if (!remote) touch_subbox(P, F, D, fc, cr.g);
       }
     }
     group_bar(1, nFold);
@@ -1232,7 +1246,7 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
   // same-address atomic with return on every thread's dependent chain).
   uint32_t *s_list = reinterpret_cast<uint32_t *>(s_keys);
   uint32_t *s_tout = s_list + P.sort_cap_smem * 2;
-  __shared__ int s_tcnt, s_tbase;
+  __shared__ int s_tcnt, s_tbase, s_rcnt, s_rbase;
   const int list_cap = P.sort_cap_smem * 2;            // 32-bit entries in one key buffer
   const int words_per_chunk = max(1, list_cap >> 5);   // a chunk of words can never overflow the list
   for (int wi = z_own_lo * P.words_per_row + tid; wi < z_own_hi * P.words_per_row; wi += blockDim.x) g_miss[wi] = s_miss[wi];
@@ -1251,6 +1265,7 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
     if (tid == 0) {
       s_nk = 0;
       s_tcnt = 0;
+      s_rcnt = 0;
     }
     __syncthreads();
     compact_bits(s_miss, w0, min(w0 + words_per_chunk, stage_w1), s_list, &s_nk, tid >> 5, (int)blockDim.x >> 5);
@@ -1280,20 +1295,31 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
         D.miss_bucket[j] = bkt;
       }
       int old = atomicAdd(&D.lvg[lv].y, 1);
-      if (old == 0) s_tout[agg_inc(&s_tcnt)] = (uint32_t)lv;
-      touch_subbox(P, F, D, fc, cr.g);
+      const bool remote = F.stage_only && subbox_owner(cr.g, F.shard_world) != F.shard_rank;
+      if (old == 0) {
+        // voxels that stay fill the chunk's list from the front, voxels of other ranks' subboxes from the back
+        if (!remote) s_tout[agg_inc(&s_tcnt)] = (uint32_t)lv;
+        else s_tout[list_cap - 1 - agg_inc(&s_rcnt)] = (uint32_t)lv;
+      }
+      if (!remote) touch_subbox(P, F, D, fc, cr.g);
     }
     __syncthreads();
-    const int n_t = s_tcnt;
+    const int n_t = s_tcnt, n_r = s_rcnt;
     if (tid == 0) {
       s_nmiss += n_list;
       if (n_t) s_tbase = atomicAdd(&fc->n_touched, n_t);
     }
+    if (tid == 32 && n_r) s_rbase = atomicAdd(&fc->n_touched_remote, n_r);
     __syncthreads();
     if (n_t) {
       const int tb = s_tbase;
       if (tb + n_t > P.max_touched) fc->error = kErrCapacity;
       for (int i = tid; i < n_t && tb + i < P.max_touched; i += blockDim.x) D.touched[tb + i] = s_tout[i];
+    }
+    if (n_r) {
+      const int rb = s_rbase;
+      if (rb + n_r > P.max_touched) fc->error = kErrCapacity;
+      for (int i = tid; i < n_r && rb + i < P.max_touched; i += blockDim.x) D.touched_remote[rb + i] = s_tout[list_cap - 1 - i];
     }
     __syncthreads();
   }

@@ -594,6 +594,7 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
     F.shard_rank = h->shard_rank;
     F.shard_world = h->shard_world;
     F.stage_only = 1;
+    F.inline_resolve = 1;  // voxels of subboxes this rank owns are staged as on one GPU: the first toucher resolves the subbox
     F.order_mode = 1;
     const int pg = grid_for((size_t)std::max(N, 1), kProjThreads * 2);
     if (F.bucket_count == 1) F.bucket_count = 13, F.bucket_c64 = pow64_mod(13);  // the first insert of an empty table allocates 13 buckets before anything is ordered
@@ -2397,13 +2398,15 @@ int shard_enqueue(mlm_handle h, const double *d_xyz, int n, const double T_wb[7]
   int *skip = h->d_shard_cursor + kMaxWorld;
   const int G = h->sm_count * 2;
   // latency-bound list walks; one reservation (a same-address atomic per destination) per 1024 list entries
-  k_shard_push<<<h->sm_count * 2, kPushThreads, 0, s>>>(X, h->P, h->D, F, par, h->d_shard_cursor, epoch);
-  MLM_SMARK(4);
-  // owner side (all of it returns at once when the wait at the head of k_shard_act found a rehash scan or an error)
+  // from here on the owner-side view of the frame: the first record of a subbox (or, in the push kernel, the first voxel
+  // that stays on this rank) resolves / allocates it (k_fuse's tail rearms the flags)
   F.stage_only = 0;
   F.order_mode = 1;  // stamps are complete: first-insert stamps travel in the records, activations come from the gathered keys
   F.shard_world = 1;
-  F.inline_resolve = 1;  // the first record of a subbox resolves / allocates it (k_fuse's tail rearms the flags)
+  F.inline_resolve = 1;
+  k_shard_push<<<h->sm_count * 2, kPushThreads, 0, s>>>(X, h->P, h->D, F, par, h->d_shard_cursor, epoch);
+  MLM_SMARK(4);
+  // (all of the following returns at once when the wait at the head of k_shard_act found a rehash scan or an error)
   F.skip_flag = skip;
   // its CTAs spin at the head until every source has signalled: when several ranks share one GPU (tests) they must leave
   // most SMs to the other ranks' staging kernels
@@ -2486,6 +2489,7 @@ int shard_rehash_path(mlm_handle h, const ShardState &st, uint32_t *B_out) {
   k_fill_u32<<<grid_for(Bs, T), T, 0, s>>>(act, 0xffffffffu, (int)Bs);
   k_order_final<<<grid_for(n_total, T), T, 0, s>>>(h->P, O, act, h->d_seq_a, n_total, Bs);
   k_shard_scatter_stamps<<<grid_for(n_total, T), T, 0, s>>>(h->d_keys_all, h->d_stamps_all, n_total, h->d_key_stamp);
+  if (st.hit_base > 0) k_shard_restamp<<<grid_for(st.hit_base, T), T, 0, s>>>(h->P, h->D, st.hit_base, h->d_key_stamp, Bs);
   F.stage_only = 0;
   F.order_mode = 1;
   F.shard_world = 1;
@@ -2527,6 +2531,10 @@ int mlm_shard_open(mlm_handle h, int rank, int world, void *blob_out) {
   h->allocs.push_back(h->shard_arena);
   h->shard_arena_bytes = bytes;
   CUDA_TRY(cudaMemset(h->shard_arena, 0, align256(kMaxWorld * 4) + align256(2 * kMaxWorld * sizeof(int2)) + align256(8)));
+  if (!h->D.touched_remote) {
+    CUDA_TRY(cudaMalloc((void **)&h->D.touched_remote, (size_t)P.max_touched * sizeof(uint32_t)));
+    h->allocs.push_back(h->D.touched_remote);
+  }
   if (!h->d_key_stamp) {
     const size_t cells = (size_t)P.nZ * P.nPhi * P.nRho;
     CUDA_TRY(cudaMalloc((void **)&h->d_key_stamp, cells * sizeof(uint32_t)));

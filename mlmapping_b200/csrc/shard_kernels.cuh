@@ -45,18 +45,17 @@ struct ShardState {
   int n_rec_total;        // records received
   int rehash;             // 1: n_total exceeds the bucket count -> the owner-side kernels skipped, host runs the rehash path
   int error;              // device error code (peer failure, timeout, capacity)
+  int hit_base, touched_base;  // entries of the local hit / touched lists in front of the ingested records
   int cnt_hits[kMaxWorld];
   unsigned long long wait_ns;  // time the wait kernel spent spinning (exchange skew seen by this rank)
 };
 constexpr int kErrPeer = 101;  // a peer did not signal in time / reported a failure
 
-__device__ __forceinline__ int owner_of(const MapParams &P, const int c[3], int world) {
-  int g[3] = {fast_floor_div(c[0], P.n, P.n_mul, P.n_shift), fast_floor_div(c[1], P.n, P.n_mul, P.n_shift),
-              fast_floor_div(c[2], P.n, P.n_mul, P.n_shift)};
-  uint64_t key;
-  if (!pack_glb(g, key)) return 0;
-  const uint32_t hsh = ht_hash(key);
-  return (world & (world - 1)) == 0 ? (int)(hsh & (uint32_t)(world - 1)) : (int)(hsh % (uint32_t)world);
+__device__ __forceinline__ int owner_of(const MapParams &P, const int c[3], int world, int g[3]) {
+  g[0] = fast_floor_div(c[0], P.n, P.n_mul, P.n_shift);
+  g[1] = fast_floor_div(c[1], P.n, P.n_mul, P.n_shift);
+  g[2] = fast_floor_div(c[2], P.n, P.n_mul, P.n_shift);
+  return subbox_owner(g, world);
 }
 
 // CTA-wide slot reservation: every thread asks for `want` (0 or more) consecutive slots of a global counter; one
@@ -107,7 +106,9 @@ constexpr int kPushThreads = 1024;  // list entries per chunk = per reservation 
 constexpr int kPushStage = 1792;   // records a CTA chunk stages in shared memory (42 KB)
 // ---- source side: ONE kernel per scan pushes everything this rank has for the others ----------------------------
 // (1) all-gather of the rank's distinct hit keys + stamps: written into every rank's gather region for this source;
-// (2) all-to-all of the update records: one thread per touched-list entry; records of a CTA chunk are grouped by
+// (2) all-to-all of the update records: one thread per entry of the list of voxels OTHER ranks own (the staging kept the
+//     voxels this rank owns itself in the ordinary touched list, with their subboxes resolved: they never leave and meet
+//     the other ranks' records in the owner-side ingest).  Records of a CTA chunk are grouped by
 //     destination in shared memory, each group reserves its slots in the DESTINATION's inbox with one atomicAdd on that
 //     rank's cursor (a remote atomic over NVLink for a peer: one per 1024 list entries and destination; same-address
 //     atomics complete at a few ns each, so their number, not their latency, is what a scan pays for) and is then
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(kPushThreads) k_shard_push(ShardPeers X, MapPa
   __shared__ int s_last;
   FrameCounters *fc = D.fc[F.parity];
   const int world = X.world;
+  // F is the owner-side view of the frame (stage_only off, inline_resolve on): the voxels that stay resolve their subboxes here
   // (1)
   const int n_hit = fc->n_hit;
   if (n_hit > X.hit_cap) {
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(kPushThreads) k_shard_push(ShardPeers X, MapPa
     }
   }
   // (2)
-  const int n = min(fc->n_touched, P.max_touched);
+  const int n = min(fc->n_touched_remote, P.max_touched);
   const int dxy = P.lvg_dim_xy;
   for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
     if (threadIdx.x < world) s_cnt[threadIdx.x] = 0;
@@ -150,10 +152,10 @@ __global__ void __launch_bounds__(kPushThreads) k_shard_push(ShardPeers X, MapPa
     int dest = -1, nrec = 0, head = kLvgEmpty, mc = 0, lv = 0, rank_in_cta = 0;
     int c[3] = {0, 0, 0};
     if (i < n) {
-      const uint32_t e = D.touched[i];
+      const uint32_t e = D.touched_remote[i];
       lv = (int)(e & ~kTouchedHitTag);
       const int2 st = D.lvg[lv];
-      if ((e & kTouchedHitTag) || st.x == kLvgEmpty) {  // the entry that owns the voxel
+      if ((e & kTouchedHitTag) || st.x == kLvgEmpty) {  // the entry that speaks for the voxel
         head = st.x;
         mc = st.y;
         const int lz = (int)fast_div((uint32_t)lv, P.dxy2_mul, P.dxy2_shift);
@@ -162,7 +164,8 @@ __global__ void __launch_bounds__(kPushThreads) k_shard_push(ShardPeers X, MapPa
         c[0] = rem - ly * dxy + F.lvg_base[0];
         c[1] = ly + F.lvg_base[1];
         c[2] = lz + F.lvg_base[2];
-        dest = owner_of(P, c, world);
+        int g[3];
+        dest = owner_of(P, c, world, g);
         for (int h = head; h != kLvgEmpty; h = D.hit_next[h]) nrec++;
         if (mc > 0) nrec++;
         rank_in_cta = atomicAdd(&s_cnt[dest], nrec);
@@ -244,12 +247,6 @@ __global__ void __launch_bounds__(kPushThreads) k_shard_push(ShardPeers X, MapPa
     __threadfence_system();
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(X.a[d].flags + X.rank), "r"(epoch) : "memory");
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    fc->n_hit = 0;
-    fc->n_touched = 0;
-    fc->n_touched_sub = 0;
-  }
 }
 
 // ---- owner side ---------------------------------------------------------------------------------------------------
@@ -257,7 +254,8 @@ __global__ void __launch_bounds__(kPushThreads) k_shard_push(ShardPeers X, MapPa
 // libstdc++ rehash (same decision on every rank: they all see the same counts).  Every CTA of the first owner-side
 // kernel runs this (the flags are read-only here); CTA 0 records the result for the later kernels and the host.
 __device__ __forceinline__ bool shard_wait(const ShardPeers &X, DeviceBuffers &D, const FrameParams &F, int par, uint32_t epoch,
-                                           ShardState *st, int *skip, unsigned long long timeout_ns, ShardState *s_st) {
+                                           ShardState *st, int *skip, unsigned long long timeout_ns, ShardState *s_st,
+                                           int P_max_touched) {
   __shared__ int s_fail;
   const int s = threadIdx.x;
   if (s == 0) s_fail = 0;
@@ -300,6 +298,8 @@ __device__ __forceinline__ bool shard_wait(const ShardPeers &X, DeviceBuffers &D
     if (local_err) err = local_err;
     s_st->n_total = n_total;
     s_st->n_rec_total = n_rec;
+    s_st->hit_base = __ldcg(&fc->n_hit);
+    s_st->touched_base = min(__ldcg(&fc->n_touched), P_max_touched);
     s_st->rehash = (err == 0 && (uint32_t)n_total > F.bucket_count) ? 1 : 0;
     s_st->error = err;
     s_st->wait_ns = t1 - t0;
@@ -313,6 +313,14 @@ __device__ __forceinline__ bool shard_wait(const ShardPeers &X, DeviceBuffers &D
   return s_st->error == 0 && s_st->rehash == 0;
 }
 
+// rehash scans: the hit entries this rank staged itself get their virtual positions and buckets like the ingested ones
+__global__ void k_shard_restamp(MapParams P, DeviceBuffers D, int n_local, const uint32_t *key_stamp, uint32_t B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_local) return;
+  const int key = D.hit_key[i];
+  D.hit_t[i] = key_stamp[key];
+  D.hit_bucket[i] = cell_bucket(P, key, B, 0);
+}
 // global ordering info per key: key_stamp[key] = first-insert stamp (or virtual position on a rehash frame)
 __global__ void k_shard_scatter_stamps(const int *keys, const uint32_t *stamps, int n, uint32_t *key_stamp) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -323,7 +331,7 @@ __global__ void k_shard_scatter_stamps(const int *keys, const uint32_t *stamps, 
 __global__ void __launch_bounds__(256) k_shard_act(ShardPeers X, MapParams P, DeviceBuffers D, FrameParams F, int par, uint32_t epoch,
                                                    ShardState *st, int *skip, unsigned long long timeout_ns, uint32_t *act) {
   __shared__ ShardState s_st;
-  if (!shard_wait(X, D, F, par, epoch, st, skip, timeout_ns, &s_st)) return;
+  if (!shard_wait(X, D, F, par, epoch, st, skip, timeout_ns, &s_st, P.max_touched)) return;
   const ShardArena &A = X.a[X.rank];
   const uint32_t B = F.bucket_count;
   for (int src = 0; src < X.world; src++) {
@@ -344,15 +352,15 @@ __global__ void __launch_bounds__(256) k_shard_ingest(ShardPeers X, MapParams P,
   __shared__ int s_warp[33];
   if (skip && *skip) return;
   FrameCounters *fc = D.fc[F.parity];
-  const int n = st->n_rec_total;
-  if (n > P.max_touched) {
+  const int n = st->n_rec_total, hb = st->hit_base, tb = st->touched_base;   // the voxels this rank staged itself come first
+  if (tb + n > P.max_touched) {
     if (blockIdx.x == 0 && threadIdx.x == 0) fc->error = kErrCapacity;
     return;
   }
-  const bool dense_hits = n <= P.max_hits;   // uniform over the grid
+  const bool dense_hits = hb + n <= P.max_hits;   // uniform over the grid
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    fc->n_touched = n;
-    if (dense_hits) fc->n_hit = n;
+    fc->n_touched = tb + n;
+    if (dense_hits) fc->n_hit = hb + n;
   }
   const int2 *rec = reinterpret_cast<const int2 *>(X.a[X.rank].inbox + (size_t)par * X.rec_cap);
   for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
@@ -379,7 +387,7 @@ __global__ void __launch_bounds__(256) k_shard_ingest(ShardPeers X, MapParams P,
     }
     const bool is_hit = valid && lv >= 0 && r.key >= 0;
     const bool is_miss = valid && lv >= 0 && r.key < 0;
-    int idx = i;
+    int idx = hb + i;
     if (!dense_hits) idx = cta_reserve(&fc->n_hit, is_hit ? 1 : 0, s_warp);   // CTA-uniform branch
     uint32_t entry = kTouchedNone;
     if (is_hit) {
@@ -398,7 +406,7 @@ __global__ void __launch_bounds__(256) k_shard_ingest(ShardPeers X, MapParams P,
       if (atomicAdd(&D.lvg[lv].y, r.count) == 0) entry = (uint32_t)lv;
     }
     if (valid) {
-      D.touched[i] = entry;
+      D.touched[tb + i] = entry;
       if (lv >= 0) touch_subbox(P, F, D, fc, cr.g);
     }
   }

@@ -127,6 +127,7 @@ struct FrameCounters {
   int n_miss_list;        // exploration mode: entries of the per-frame miss list
   int n_obs;              // exploration mode: subboxes handed to the release pass (observed_subboxes)
   int n_released;         // subboxes collapsed by the release pass this frame
+  int n_touched_remote;   // sharded staging: entries of the list of voxels owned by OTHER ranks
   uint32_t seq;           // host copy only: frame_seq of the frame these counters belong to, stored after everything else
 };
 
@@ -155,6 +156,7 @@ struct DeviceBuffers {
   // local voxel / submap grids
   int2 *lvg;              // [lvg cells] .x head of this frame's hit list (-1 empty), .y number of miss cells
   uint32_t *touched;      // [max_touched] local voxel index (| kTouchedHitTag)
+  uint32_t *touched_remote; // [max_touched] sharded maps only: the same for voxels whose subbox another rank owns
   int *lsg_flag;          // [lsg cells]
   int *lsg_block;         // [lsg cells] pool block of that subbox this frame
   int *touched_sub;       // [lsg cells]
