@@ -323,8 +323,8 @@ int mlm_shard_integrate_points_f64(mlm_handle h, const double *xyz, int n, const
 int mlm_shard_last_exchange(mlm_handle h, mlm_shard_exchange *out);
 /* with mlm_set_profiling(h, 1): durations of the stages of the last scan between CUDA events on the handle's stream:
  * 0 resets (+ H2D copy), 1 k_project, 2 k_column (the rank's phi columns), 3 k_shard_push (keys + records to the owners, signal),
- * 4 k_shard_act (wait for the sources + activation stamps), 5 k_shard_ingest, 6 k_fuse */
-#define MLM_NUM_SHARD_KERNELS 7
+ * 4 k_shard_act_ingest (wait for the sources, activation stamps, staging of the received records), 5 k_fuse */
+#define MLM_NUM_SHARD_KERNELS 6
 int mlm_shard_last_kernel_ms(mlm_handle h, float ms[MLM_NUM_SHARD_KERNELS]);
 int mlm_shard_close(mlm_handle h); /* unmaps the peers' arenas; call on every rank before any rank is destroyed */
 

@@ -2406,18 +2406,17 @@ int shard_enqueue(mlm_handle h, const double *d_xyz, int n, const double T_wb[7]
   F.inline_resolve = 1;
   k_shard_push<<<h->sm_count * 2, kPushThreads, 0, s>>>(X, h->P, h->D, F, par, h->d_shard_cursor, epoch);
   MLM_SMARK(4);
-  // (all of the following returns at once when the wait at the head of k_shard_act found a rehash scan or an error)
+  // (all of the following returns at once when the wait at the head of k_shard_act_ingest found a rehash scan or an error)
   F.skip_flag = skip;
   // its CTAs spin at the head until every source has signalled: when several ranks share one GPU (tests) they must leave
   // most SMs to the other ranks' staging kernels
-  k_shard_act<<<h->shard_shares_device ? 32 : G, 256, 0, s>>>(X, h->P, h->D, F, par, epoch, h->d_shard_state, skip, h->shard_timeout_ns, h->D.act[F.parity]);
+  k_shard_act_ingest<<<h->shard_shares_device ? 32 : h->sm_count * 8, 256, 0, s>>>(X, h->P, h->D, F, par, epoch, h->d_shard_state, skip,
+                                                                                  h->shard_timeout_ns, h->D.act[F.parity]);
   MLM_SMARK(5);
-  k_shard_ingest<<<h->sm_count * 8, 256, 0, s>>>(X, h->P, h->D, F, par, h->d_shard_state, skip, nullptr);
-  MLM_SMARK(6);
   k_fuse<0><<<h->sm_count * 5, 256, 0, s>>>(h->P, h->D, F);
-  MLM_SMARK(7);
+  MLM_SMARK(6);
 #undef MLM_SMARK
-  h->launches += 4;
+  h->launches += 3;
   CUDA_TRY(cudaMemcpyAsync(h->h_shard_state, h->d_shard_state, sizeof(ShardState), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc[F.parity], sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaGetLastError());
@@ -2498,7 +2497,7 @@ int shard_rehash_path(mlm_handle h, const ShardState &st, uint32_t *B_out) {
   F.bucket_count = Bs;
   F.bucket_c64 = pow64_mod(F.bucket_count);
   const int G = h->sm_count * 2;
-  k_shard_ingest<<<G * 2, 256, 0, s>>>(X, h->P, h->D, F, par, h->d_shard_state, nullptr, h->d_key_stamp);
+  k_shard_ingest<<<G * 2, 256, 0, s>>>(X, h->P, h->D, F, par, h->d_shard_state, h->d_key_stamp);
   k_fuse<0><<<h->sm_count * 4, 256, 0, s>>>(h->P, h->D, F);
   h->launches += 8;
   CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc[F.parity], sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
@@ -2539,7 +2538,7 @@ int mlm_shard_open(mlm_handle h, int rank, int world, void *blob_out) {
     const size_t cells = (size_t)P.nZ * P.nPhi * P.nRho;
     CUDA_TRY(cudaMalloc((void **)&h->d_key_stamp, cells * sizeof(uint32_t)));
     h->allocs.push_back(h->d_key_stamp);
-    CUDA_TRY(cudaMalloc((void **)&h->d_shard_cursor, (kMaxWorld + 2) * sizeof(int)));
+    CUDA_TRY(cudaMalloc((void **)&h->d_shard_cursor, (kMaxWorld + 4) * sizeof(int)));
     h->allocs.push_back(h->d_shard_cursor);
     CUDA_TRY(cudaMalloc((void **)&h->d_shard_state, sizeof(ShardState)));
     h->allocs.push_back(h->d_shard_state);

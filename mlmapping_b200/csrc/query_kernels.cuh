@@ -165,103 +165,172 @@ __device__ __forceinline__ void neighbor_step(const MapParams &P, int dir, int g
   sub = (c[2] * P.n + c[1]) * P.n + c[0];
 }
 
-// log-odds the reference's getOdd(glb, sub) would convert: absent subbox -> odds 0.5 == logit_inv(0.f)
-// block id for the gradient walk: >= 0 pool block, -1 absent, <= -16 collapsed subbox stored at slot -(id+16)
-__device__ __forceinline__ int grad_block(const MapParams &P, const DeviceBuffers &D, const int g[3]) {
-  uint32_t slot;
-  int block = ht_find_slot(P, D, g, slot);
-  if (block == kBlockCollapsed) return -16 - (int)slot;
-  return block < 0 ? -1 : block;
+// ---- getOddGrad (include/mlmap.h:237-295) ---------------------------------------------------------------------------
+// where the log-odds of a subbox live: base + cell * mul (pool block: one float per cell; collapsed subbox: its single
+// element, mul 0; absent subbox: no storage, the reference's getOdd answers 0.5 == logit_inv(0.f))
+struct GradSource {
+  const float *base;
+  int mul;
+};
+__device__ __forceinline__ GradSource grad_source_key(const MapParams &P, const DeviceBuffers &D, uint64_t key) {
+  GradSource s = {nullptr, 0};
+  uint32_t slot = ht_hash(key) & P.ht_mask;
+  for (uint32_t probe = 0; probe <= P.ht_mask; probe++) {
+    const uint64_t k = D.ht_key[slot];
+    if (k == key) {
+      const int block = D.ht_val[slot];
+      if (block >= 0) {
+        s.base = D.pool_lo + (size_t)block * P.cell_stride;
+        s.mul = 1;
+      } else if (block == kBlockCollapsed) {
+        s.base = D.col_lo + slot;
+      }
+      return s;
+    }
+    if (k == kEmptyKey) return s;
+    slot = (slot + 1) & P.ht_mask;
+  }
+  return s;
 }
-__device__ __forceinline__ float grad_lo(const MapParams &P, const DeviceBuffers &D, int blk, int sub) {
-  if (blk >= 0) return D.pool_lo[(size_t)blk * P.cell_stride + sub];
-  if (blk <= -16) return D.col_lo[-(blk + 16)];
-  return 0.0f;
+__device__ __forceinline__ GradSource grad_source(const MapParams &P, const DeviceBuffers &D, const int g[3]) {
+  uint64_t key;
+  if (!pack_glb(g, key)) return GradSource{nullptr, 0};
+  return grad_source_key(P, D, key);
 }
+__device__ __forceinline__ float grad_lo(const GradSource &s, int sub) { return s.base ? __ldg(s.base + sub * s.mul) : 0.0f; }
 
 __global__ void __launch_bounds__(256, 4) k_get_odd_grad(MapParams P, DeviceBuffers D, const double *pos, size_t n,
-                                                         int max_iter, double *out) {  // mlmap.h:237-295
+                                                         int max_iter, double *out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double px = pos[3 * i], py = pos[3 * i + 1], pz = pos[3 * i + 2];
-  CellRef c = locate_cell(P, px, py, pz);
-  const int blk0 = grad_block(P, D, c.g);
-  const float lo0 = grad_lo(P, D, blk0, c.sub);
-  const float ori_odd = logit_inv_f(lo0);
-  float min_odd = ori_odd;
+  const CellRef c = locate_cell(P, px, py, pz);
   // The six probes walk along +z,-z,+y,-y,+x,-x (subbox_neighbors row order, src/map_local.cpp:78-120): only the
   // coordinate on the probe's own axis changes.  After k steps probe d sits at cell c_axis +- k of the origin's subbox
   // or, once it has left it, of the neighbouring subbox in that direction.  The neighbours a walk of max_iter steps can
   // reach are looked up ONCE, up front, where the whole warp is converged (a lookup inside the walk runs for the two or
-  // three lanes that happen to cross a border at that step: 30 such sites cost half of the kernel's instructions);
-  // a walk longer than a subbox falls back to a lookup per further crossing.
+  // three lanes that happen to cross a border at that step); their packed keys differ from the origin's in one field.
+  const int lim = 1 << 20;
+  uint64_t key0 = 0;
+  const bool packed = pack_glb(c.g, key0);
+  bool inner = packed;   // all six neighbours have a packed key too
+#pragma unroll
+  for (int a = 0; a < 3; a++) inner = inner && c.g[a] > -lim && c.g[a] < lim - 1;
+  const GradSource src0 = packed ? grad_source_key(P, D, key0) : GradSource{nullptr, 0};
+  const float lo0 = grad_lo(src0, c.sub);
   const int cxyz[3] = {c.sub % P.n, (c.sub / P.n) % P.n, c.sub / (P.n * P.n)};
   const int stride[3] = {1, P.n, P.n * P.n};
-  int blk_nb[6];
+  const bool short_walk = max_iter <= P.n;   // a probe leaves at most one subbox behind
+  GradSource nb[6];
+  bool any_source = src0.base != nullptr;
 #pragma unroll
   for (int d = 0; d < 6; d++) {
     const int axis = 2 - (d >> 1);
     const bool reach = (d & 1) ? (cxyz[axis] - max_iter < 0) : (cxyz[axis] + max_iter >= P.n);
-    blk_nb[d] = -1;
+    nb[d] = GradSource{nullptr, 0};
     if (reach) {
-      int g[3] = {c.g[0], c.g[1], c.g[2]};
-      g[axis] += (d & 1) ? -1 : 1;
-      blk_nb[d] = grad_block(P, D, g);
+      if (inner) {
+        const uint64_t step = 1ull << (21 * (d >> 1));   // pack_glb: x at bit 42, y at 21, z at 0
+        nb[d] = grad_source_key(P, D, (d & 1) ? key0 - step : key0 + step);
+      } else {
+        int g[3] = {c.g[0], c.g[1], c.g[2]};
+        g[axis] += (d & 1) ? -1 : 1;
+        nb[d] = grad_source(P, D, g);
+      }
+      any_source = any_source || nb[d].base != nullptr;
     }
   }
-  int best_d = -1, best_k = 0;
+  // log-odds of the six neighbours of round k
+  auto load_round = [&](int k, float lo_d[6]) {
+#pragma unroll
+    for (int d = 0; d < 6; d++) {
+      const int axis = 2 - (d >> 1);
+      int p = cxyz[axis] + ((d & 1) ? -k : k);
+      GradSource s = src0;
+      if (p >= P.n || p < 0) {
+        if (short_walk) {
+          p += (d & 1) ? P.n : -P.n;
+          s = nb[d];
+        } else {
+          const int hops = p >= P.n ? p / P.n : -((-p + P.n - 1) / P.n);   // subboxes left behind
+          p -= hops * P.n;
+          if (hops == 1 || hops == -1) {
+            s = nb[d];
+          } else {
+            int g[3] = {c.g[0], c.g[1], c.g[2]};
+            g[axis] += hops;
+            s = grad_source(P, D, g);
+          }
+        }
+      }
+      lo_d[d] = grad_lo(s, c.sub + (p - cxyz[axis]) * stride[axis]);
+    }
+  };
   // A round of the reference visits the six neighbours in order and keeps the first one with the strictly lowest odd
   // below the running minimum; a round that finds one ends the search.  logit_inv is monotone non-decreasing in the
   // log-odds (also after the cast to float), so the round's winner is the neighbour with the lowest log-odds (the first
   // of those), unless an EARLIER neighbour with a slightly higher log-odds rounds to the same float odd; those rare
   // near-ties (within kTie, far more than one float ulp of the odd anywhere in the clamped range) are settled with
-  // their own pow.  So a round costs ONE pow at a point where the whole warp is converged, instead of up to six at
-  // divergent ones (6980 instructions per query in round 1, 83 % of them in diverged pow calls).
+  // their own pow.  The walk itself compares log-odds only: the first round whose minimum lies below the origin's is the
+  // candidate, and its odd is computed AFTER the loop, next to the origin's, where the warp is converged again (a pow
+  // inside the loop runs for the few lanes whose search ends in that round, once per round).
   const float kTie = 1e-2f;
-  for (int k = 1; k <= max_iter && best_d < 0; k++) {
-    float lo_d[6];
+  float lo_d[6];
+  int m = 0, k = max_iter + 1;
+  float lo_m = lo0;
+  if (any_source || !short_walk) {   // nothing stored within reach: every probe reads 0.5, like the origin
+    for (k = 1; k <= max_iter; k++) {
+      load_round(k, lo_d);
+      m = 0;
+      lo_m = lo_d[0];
 #pragma unroll
-    for (int d = 0; d < 6; d++) {
-      const int axis = 2 - (d >> 1);
-      int p = cxyz[axis] + ((d & 1) ? -k : k);
-      int blk = blk0;
-      if (p >= P.n || p < 0) {
-        int hops = p >= P.n ? p / P.n : -((-p + P.n - 1) / P.n);   // subboxes left behind (1 unless max_iter > n)
-        p -= hops * P.n;
-        if (hops == 1 || hops == -1) {
-          blk = blk_nb[d];
-        } else {
-          int g[3] = {c.g[0], c.g[1], c.g[2]};
-          g[axis] += hops;
-          blk = grad_block(P, D, g);
+      for (int d = 1; d < 6; d++)
+        if (lo_d[d] < lo_m) {   // lowest log-odds of the round, first direction wins ties
+          lo_m = lo_d[d];
+          m = d;
         }
-      }
-      lo_d[d] = grad_lo(P, D, blk, c.sub + (p - cxyz[axis]) * stride[axis]);
+      if (lo_m < lo0) break;
     }
-    // lowest log-odds of the round, first direction wins ties
-    int m = 0;
-    float lo_m = lo_d[0];
+  }
+  const bool cand = k <= max_iter;
+  const float ori_odd = logit_inv_f(lo0);
+  float min_odd = ori_odd;
+  float odd_m = logit_inv_f(cand ? lo_m : lo0);
+  int best_d = -1, best_k = 0;
+  if (cand) {
+    // a lower log-odds that rounds to the origin's odd is not strictly lower: the search goes on (a few queries per million)
+    while (!(odd_m < min_odd)) {
+      bool found = false;
+      for (k = k + 1; k <= max_iter && !found; k++) {
+        load_round(k, lo_d);
+        m = 0;
+        lo_m = lo_d[0];
 #pragma unroll
-    for (int d = 1; d < 6; d++)
-      if (lo_d[d] < lo_m) {
-        lo_m = lo_d[d];
-        m = d;
+        for (int d = 1; d < 6; d++)
+          if (lo_d[d] < lo_m) {
+            lo_m = lo_d[d];
+            m = d;
+          }
+        found = lo_m < lo0;
       }
-    if (!(lo_m < lo0)) continue;          // nothing can be below the origin's odd this round
-    const float odd_m = logit_inv_f(lo_m);
-    if (!(odd_m < min_odd)) continue;     // rounds to the origin's odd (or above): not strictly lower
-    min_odd = odd_m;
-    best_d = m;
-    best_k = k;
-    // earlier directions whose log-odds is a hair above the minimum: same float odd -> the reference keeps the earlier one
+      if (!found) break;
+      k--;   // the round that was found
+      odd_m = logit_inv_f(lo_m);
+    }
+    if (odd_m < min_odd) {
+      min_odd = odd_m;
+      best_d = m;
+      best_k = k;
+      // earlier directions whose log-odds is a hair above the minimum: same float odd -> the reference keeps the earlier one
 #pragma unroll
-    for (int d = 0; d < 5; d++)
-      if (d < m && (lo_d[d] - lo_m <= kTie || lo_m < -30.0f) && lo_d[d] < lo0) {  // (below 10^-30 the float odd underflows: any gap can tie)
-        if (logit_inv_f(lo_d[d]) == odd_m) {
-          best_d = d;
-          break;
+      for (int d = 0; d < 5; d++)
+        if (d < m && (lo_d[d] - lo_m <= kTie || lo_m < -30.0f) && lo_d[d] < lo0) {  // (below 10^-30 the float odd underflows: any gap can tie)
+          if (logit_inv_f(lo_d[d]) == odd_m) {
+            best_d = d;
+            break;
+          }
         }
-      }
+    }
   }
   double gx = 0.0, gy = 0.0, gz = 0.0;
   if (best_d >= 0) {
@@ -271,13 +340,13 @@ __global__ void __launch_bounds__(256, 4) k_get_odd_grad(MapParams P, DeviceBuff
     p -= hops * P.n;
     int best_g[3] = {c.g[0], c.g[1], c.g[2]};
     best_g[axis] += hops;
-    const int best_sub = c.sub + (p - cxyz[axis]) * stride[axis];
+    int cb[3] = {cxyz[0], cxyz[1], cxyz[2]};
+    cb[axis] = p;
     // subbox_id2xyz_glb_vec (map_local.h:208-213) - pos, times (double)(float)(ori - min)
-    int x = best_sub % P.n, y = (best_sub / P.n) % P.n, z = best_sub / (P.n * P.n);
-    double s = (double)__fsub_rn(ori_odd, min_odd);
-    gx = ((((double)best_g[0] * P.d_glb + (double)x * P.d_sub) + P.d_sub_half) - px) * s;
-    gy = ((((double)best_g[1] * P.d_glb + (double)y * P.d_sub) + P.d_sub_half) - py) * s;
-    gz = ((((double)best_g[2] * P.d_glb + (double)z * P.d_sub) + P.d_sub_half) - pz) * s;
+    const double s = (double)__fsub_rn(ori_odd, min_odd);
+    gx = ((((double)best_g[0] * P.d_glb + (double)cb[0] * P.d_sub) + P.d_sub_half) - px) * s;
+    gy = ((((double)best_g[1] * P.d_glb + (double)cb[1] * P.d_sub) + P.d_sub_half) - py) * s;
+    gz = ((((double)best_g[2] * P.d_glb + (double)cb[2] * P.d_sub) + P.d_sub_half) - pz) * s;
   }
   out[3 * i] = gx;
   out[3 * i + 1] = gy;

@@ -241,10 +241,15 @@ __global__ void __launch_bounds__(kPushThreads) k_shard_push(ShardPeers X, MapPa
   if (!s_last) return;
   __threadfence();
   const int d = threadIdx.x;
+  if (d == X.rank) {   // the entries this rank staged for itself, for its owner-side kernel (the thread that raises this
+                       // rank's own flag writes them, ahead of its fence)
+    sent[kMaxWorld + 2] = n_hit;
+    sent[kMaxWorld + 3] = __ldcg(&fc->n_touched);
+  }
   if (d < world) {
     const bool failed = __ldcg(&fc->error) != 0;
     X.a[d].mbox[par * kMaxWorld + X.rank] = make_int2(failed ? -1 : n_hit, failed ? -1 : 0);
-    __threadfence_system();
+    // (the release orders this thread's stores above and, through the tickets behind the CTAs' fences, everyone else's)
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(X.a[d].flags + X.rank), "r"(epoch) : "memory");
   }
 }
@@ -255,7 +260,7 @@ __global__ void __launch_bounds__(kPushThreads) k_shard_push(ShardPeers X, MapPa
 // kernel runs this (the flags are read-only here); CTA 0 records the result for the later kernels and the host.
 __device__ __forceinline__ bool shard_wait(const ShardPeers &X, DeviceBuffers &D, const FrameParams &F, int par, uint32_t epoch,
                                            ShardState *st, int *skip, unsigned long long timeout_ns, ShardState *s_st,
-                                           int P_max_touched) {
+                                           int P_max_touched, const int *local_counts) {
   __shared__ int s_fail;
   const int s = threadIdx.x;
   if (s == 0) s_fail = 0;
@@ -298,8 +303,9 @@ __device__ __forceinline__ bool shard_wait(const ShardPeers &X, DeviceBuffers &D
     if (local_err) err = local_err;
     s_st->n_total = n_total;
     s_st->n_rec_total = n_rec;
-    s_st->hit_base = __ldcg(&fc->n_hit);
-    s_st->touched_base = min(__ldcg(&fc->n_touched), P_max_touched);
+    // (as the push kernel left them: the ingest part of this kernel moves fc->n_hit / n_touched while later CTAs still wait)
+    s_st->hit_base = __ldcg(local_counts);
+    s_st->touched_base = min(__ldcg(local_counts + 1), P_max_touched);
     s_st->rehash = (err == 0 && (uint32_t)n_total > F.bucket_count) ? 1 : 0;
     s_st->error = err;
     s_st->wait_ns = t1 - t0;
@@ -326,16 +332,13 @@ __global__ void k_shard_scatter_stamps(const int *keys, const uint32_t *stamps, 
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) key_stamp[keys[i]] = stamps[i];
 }
-// first owner-side kernel: wait for the sources, then the bucket activation stamps of a no-rehash scan from the
-// gathered (key, stamp) lists of all sources
-__global__ void __launch_bounds__(256) k_shard_act(ShardPeers X, MapParams P, DeviceBuffers D, FrameParams F, int par, uint32_t epoch,
-                                                   ShardState *st, int *skip, unsigned long long timeout_ns, uint32_t *act) {
-  __shared__ ShardState s_st;
-  if (!shard_wait(X, D, F, par, epoch, st, skip, timeout_ns, &s_st, P.max_touched)) return;
+// bucket activation stamps of a no-rehash scan from the gathered (key, stamp) lists of all sources
+__device__ __forceinline__ void act_body(const ShardPeers &X, const MapParams &P, const FrameParams &F, int par, const int *cnt_hits,
+                                         uint32_t *act) {
   const ShardArena &A = X.a[X.rank];
   const uint32_t B = F.bucket_count;
   for (int src = 0; src < X.world; src++) {
-    const int n = s_st.cnt_hits[src];
+    const int n = cnt_hits[src];
     const size_t region = ((size_t)par * X.world + src) * X.hit_cap;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
       atomicMin(&act[hit_bucket_fast(P, __ldcg(A.gather_key + region + i), B, F.bucket_c64)], __ldcg(A.gather_stamp + region + i));
@@ -347,13 +350,10 @@ __global__ void __launch_bounds__(256) k_shard_act(ShardPeers X, MapParams P, De
 // voxel was staged before) and, while the inbox fits the hit list, slot i of the hit arrays; k_fuse skips the markers.
 // The first toucher of a subbox resolves / allocates it on the spot (F.inline_resolve, as in k_frame).
 constexpr uint32_t kTouchedNone = 0xffffffffu;
-__global__ void __launch_bounds__(256) k_shard_ingest(ShardPeers X, MapParams P, DeviceBuffers D, FrameParams F, int par,
-                                                      const ShardState *st, const int *skip, const uint32_t *key_stamp) {
-  __shared__ int s_warp[33];
-  if (skip && *skip) return;
+__device__ __forceinline__ void ingest_body(const ShardPeers &X, const MapParams &P, DeviceBuffers &D, const FrameParams &F, int par,
+                                            int n, int hb, int tb, const uint32_t *key_stamp, int *s_warp) {
   FrameCounters *fc = D.fc[F.parity];
-  const int n = st->n_rec_total, hb = st->hit_base, tb = st->touched_base;   // the voxels this rank staged itself come first
-  if (tb + n > P.max_touched) {
+  if (tb + n > P.max_touched) {   // the voxels this rank staged itself come first
     if (blockIdx.x == 0 && threadIdx.x == 0) fc->error = kErrCapacity;
     return;
   }
@@ -410,6 +410,27 @@ __global__ void __launch_bounds__(256) k_shard_ingest(ShardPeers X, MapParams P,
       if (lv >= 0) touch_subbox(P, F, D, fc, cr.g);
     }
   }
+}
+
+// the owner-side kernel of a no-rehash scan: every CTA waits for the sources (the flags are read-only here), then the
+// grid derives the bucket activations from the gathered keys and stages the received records; the two parts touch
+// disjoint data, so they need no barrier between them.  A scan that needs the rehash path (or failed) returns at once,
+// with `skip` raised for k_fuse.
+__global__ void __launch_bounds__(256) k_shard_act_ingest(ShardPeers X, MapParams P, DeviceBuffers D, FrameParams F, int par, uint32_t epoch,
+                                                          ShardState *st, int *skip, unsigned long long timeout_ns, uint32_t *act) {
+  __shared__ ShardState s_st;
+  __shared__ int s_warp[33];
+  if (!shard_wait(X, D, F, par, epoch, st, skip, timeout_ns, &s_st, P.max_touched, skip + 2)) return;
+  act_body(X, P, F, par, s_st.cnt_hits, act);
+  ingest_body(X, P, D, F, par, s_st.n_rec_total, s_st.hit_base, s_st.touched_base, nullptr, s_warp);
+}
+
+// rehash scans (host-driven, mlmap_capi.cu shard_rehash_path): the records are staged with the virtual positions the
+// re-sequencing assigned
+__global__ void __launch_bounds__(256) k_shard_ingest(ShardPeers X, MapParams P, DeviceBuffers D, FrameParams F, int par,
+                                                      const ShardState *st, const uint32_t *key_stamp) {
+  __shared__ int s_warp[33];
+  ingest_body(X, P, D, F, par, st->n_rec_total, st->hit_base, st->touched_base, key_stamp, s_warp);
 }
 
 // ---- replicated map (query stream): after a frame the owner ships the subbox blocks the frame

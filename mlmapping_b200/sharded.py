@@ -72,7 +72,7 @@ class ShardedMLMap:
         self.last["gather_bytes_in"] = 8 * ex.n_hit_total
         return st
 
-    STAGES = ("resets_h2d", "k_project", "k_column", "k_shard_push", "k_shard_act_wait", "k_shard_ingest", "k_fuse")
+    STAGES = ("resets_h2d", "k_project", "k_column", "k_shard_push", "k_shard_act_ingest", "k_fuse")
 
     def last_kernel_us(self):
         """per-stage device times of the last scan (needs self.map.set_profiling(True))"""

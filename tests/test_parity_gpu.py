@@ -125,6 +125,10 @@ def test_queries_and_set_free():
     assert np.abs(og.astype(np.float64) - oo.astype(np.float64)).max() <= 1.2e-7  # <= 1 float ulp of odds in [0.5,1]
     gg, go = gpu.getOddGrad(pos[:100000]), orc.getOddGrad(pos[:100000])
     assert np.abs(gg - go).max() <= 1e-6
+    # one-step walks, walks that stay inside a subbox less often, and walks longer than a subbox (several borders crossed)
+    for it in (1, 3, cfg.subbox_n + 3, 2 * cfg.subbox_n + 1):
+        q = pos[100000:140000]
+        assert np.abs(gpu.getOddGrad(q, it) - orc.getOddGrad(q, it)).max() <= 1e-6, it
     assert np.array_equal(gpu.getOccupancy(pos[:50000], 0.15), orc.getOccupancy(pos[:50000], 0.15))
     # setFree_map_in_bound, then everything again
     bmin, bmax = [5.0, -0.5, 0.3], [8.0, 0.5, 2.0]
