@@ -20,7 +20,7 @@ __device__ __forceinline__ bool inside_exp_bd(const MapParams &P, double x, doub
 
 // per miss cell: key = (activation stamp of its bucket, its own stamp); the voxel keeps the largest key
 // (= the miss cell that the descending iteration reaches first)
-__global__ void __launch_bounds__(256) k_miss_tkey(MapParams P, DeviceBuffers D, FrameParams F) {
+__device__ __forceinline__ void miss_tkey_body(const MapParams &P, DeviceBuffers &D, const FrameParams &F) {
   const FrameCounters *fc = D.fc[F.parity];
   const int n = fc->n_miss_list;
   const uint32_t *am = D.act_miss[F.parity];
@@ -52,7 +52,7 @@ __device__ __forceinline__ void nb_of(const MapParams &P, int dir, const int g[3
 
 // pass A: the miss cell that turns its voxel from 'u' to 'f' evaluates update_observation: remembers which
 // neighbour becomes a frontier cell, allocates neighbour subboxes exactly like allocate_ram would.
-__global__ void __launch_bounds__(256) k_explore_a(MapParams P, DeviceBuffers D, FrameParams F) {
+__device__ __forceinline__ void explore_a_body(const MapParams &P, DeviceBuffers &D, const FrameParams &F) {
   FrameCounters *fc = D.fc[F.parity];
   const int n = fc->n_miss_list;
   const uint32_t *am = D.act_miss[F.parity];
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256) k_explore_a(MapParams P, DeviceBuffers D,
 }
 
 // pass B: frontier[glb_nb].emplace(sub_nb) for the choices of pass A (all subboxes exist now)
-__global__ void __launch_bounds__(256) k_explore_b(MapParams P, DeviceBuffers D, FrameParams F) {
+__device__ __forceinline__ void explore_b_body(const MapParams &P, DeviceBuffers &D, const FrameParams &F) {
   const FrameCounters *fc = D.fc[F.parity];
   const int n = fc->n_miss_list;
   const int dxy = P.lvg_dim_xy;
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) k_explore_b(MapParams P, DeviceBuffers D,
 // release pass (src/map_local.cpp:208-232): one warp per observed subbox; collapse if the frontier is empty
 // and all occupancy chars are equal.  The block returns to the free stack in its initial state; element 0 of
 // the three vectors stays readable through the per-slot arrays.
-__global__ void __launch_bounds__(256) k_release(MapParams P, DeviceBuffers D, FrameParams F) {
+__device__ __forceinline__ void release_body(const MapParams &P, DeviceBuffers &D, const FrameParams &F) {
   FrameCounters *fc = D.fc[F.parity];
   const int lane = lane_id();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -217,6 +217,49 @@ __global__ void __launch_bounds__(256) k_release(MapParams P, DeviceBuffers D, F
       D.free_stack[atomicAdd(D.free_top, 1)] = block;  // recycled: ready for the next allocate_ram
     }
   }
+}
+
+__global__ void __launch_bounds__(256) k_miss_tkey(MapParams P, DeviceBuffers D, FrameParams F) { miss_tkey_body(P, D, F); }
+__global__ void __launch_bounds__(256) k_explore_a(MapParams P, DeviceBuffers D, FrameParams F) { explore_a_body(P, D, F); }
+__global__ void __launch_bounds__(256) k_explore_b(MapParams P, DeviceBuffers D, FrameParams F) { explore_b_body(P, D, F); }
+__global__ void __launch_bounds__(256) k_release(MapParams P, DeviceBuffers D, FrameParams F) { release_body(P, D, F); }
+
+// ---- the exploration-mode frame as ONE cooperative launch (the k_frame of frame_kernels.cuh with the six exploration
+// passes behind further device-wide barriers).  A frame whose hit map or miss set would cross a libstdc++ rehash is
+// detected after staging, on the device: every CTA returns with the staging intact, the frame is flagged (overflow) and
+// the host re-sequences and runs the passes as stand-alone kernels (run_frame_complete in mlmap_capi.cu).
+template <int kMode>
+__global__ void __launch_bounds__(kColThreads, 1) k_frame_explore(MapParams P, DeviceBuffers D, FrameParams F) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const int G = (int)gridDim.x;
+  FrameCounters *fc = D.fc[F.parity];
+  {
+    const int n_tiles = (F.n_total + F.tile_pts - 1) / F.tile_pts;
+    for (int t = blockIdx.x; t < max(n_tiles, 1); t += G) {
+      project_tile<kMode>(P, D, F, t, reinterpret_cast<int *>(s_raw));
+      __syncthreads();
+    }
+  }
+  grid_barrier(D.grid_bar, G);
+  column_phase(P, D, F, s_raw);
+  grid_barrier(D.grid_bar, 2 * G);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *D.col_queue = 0;
+  if (__ldcg(&fc->n_hit) > (int)F.bucket_count || __ldcg(&fc->n_miss_list) > (int)F.bucket_count_miss) {
+    frame_bail(D, fc, F);
+    return;
+  }
+  fuse_body<1>(P, D, F);          // hits (the frame-local voxel grid stays intact)
+  grid_barrier(D.grid_bar, 3 * G);
+  miss_tkey_body(P, D, F);        // first miss cell of every voxel in set iteration order
+  grid_barrier(D.grid_bar, 4 * G);
+  explore_a_body(P, D, F);        // update_observation: neighbour choices, neighbour subboxes allocated
+  grid_barrier(D.grid_bar, 5 * G);
+  explore_b_body(P, D, F);        // frontier inserts
+  grid_barrier(D.grid_bar, 6 * G);
+  fuse_body<2, false>(P, D, F);   // misses
+  grid_barrier(D.grid_bar, 7 * G);
+  release_body(P, D, F);          // collapse pass over the observed subboxes
+  frame_finish(P, D, F, fc, __ldcg(&fc->n_hit));
 }
 
 }  // namespace mlm

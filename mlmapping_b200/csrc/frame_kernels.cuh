@@ -1544,9 +1544,28 @@ __device__ __forceinline__ void publish_counters(const DeviceBuffers &D, FrameCo
 
 // ---- K5: clamped log-odds fusion, one thread per touched cell (map_local.cpp:147-207) ---------------
 constexpr int kFuseLocal = 16;
+// a frame that crosses a libstdc++ rehash leaves the device untouched after staging: every CTA takes a ticket so that the
+// last one can rearm the launch-scoped counters safely, flags the frame and hands the counters to the host
+__device__ __forceinline__ void frame_bail(const DeviceBuffers &D, FrameCounters *fc, const FrameParams &F) {
+  __shared__ int s_ovf_last;
+  if (threadIdx.x == 0) {
+    s_ovf_last = atomicAdd(D.fuse_ticket, 1) == (int)gridDim.x - 1;
+    if (s_ovf_last) {
+      *D.fuse_ticket = 0;
+      *D.grid_bar = 0;
+      fc->overflow = 1;
+      __threadfence();
+    }
+  }
+  __syncthreads();
+  if (s_ovf_last && threadIdx.x < 32) publish_counters(D, fc, F.frame_seq);
+}
+
+__device__ __forceinline__ void frame_finish(const MapParams &P, DeviceBuffers &D, const FrameParams &F, FrameCounters *fc, int n_hit_frame);
+
 // kPhase 0: hits then misses (normal mode).  Exploration mode splits the pass so that update_observation can
 // look at the neighbours' state between them: kPhase 1 = hits only (LVG left intact), kPhase 2 = misses only.
-template <int kPhase>
+template <int kPhase, bool kFinish = true>
 __device__ __forceinline__ void fuse_body(const MapParams &P, DeviceBuffers &D, const FrameParams &F) {
   if (F.skip_flag && __ldcg(F.skip_flag)) return;  // sharded scan that needs the rehash path: nothing may be consumed yet
   FrameCounters *fc = D.fc[F.parity];
@@ -1554,19 +1573,7 @@ __device__ __forceinline__ void fuse_body(const MapParams &P, DeviceBuffers &D, 
   const int n_hit_frame = fc->n_hit;
   // a frame that crosses a libstdc++ rehash needs the slow ordering pass first (host re-launches)
   if (kPhase == 0 && F.order_mode == 0 && n_hit_frame > (int)F.bucket_count) {
-    // every CTA takes a ticket so that the last one can rearm the launch-scoped counters safely
-    __shared__ int s_ovf_last;
-    if (threadIdx.x == 0) {
-      s_ovf_last = atomicAdd(D.fuse_ticket, 1) == (int)gridDim.x - 1;
-      if (s_ovf_last) {
-        *D.fuse_ticket = 0;
-        *D.grid_bar = 0;
-        fc->overflow = 1;
-        __threadfence();
-      }
-    }
-    __syncthreads();
-    if (s_ovf_last && threadIdx.x < 32) publish_counters(D, fc, F.frame_seq);
+    frame_bail(D, fc, F);
     return;
   }
   const int n = min(fc->n_touched, P.max_touched);
@@ -1753,7 +1760,12 @@ __device__ __forceinline__ void fuse_body(const MapParams &P, DeviceBuffers &D, 
     if (s_ctr[0]) atomicAdd(&fc->n_touched_voxels, s_ctr[0]);
     if (s_ctr[1]) atomicAdd(&fc->obs_delta, s_ctr[1]);
   }
-  if (kPhase == 1) return;  // the miss phase finishes the frame
+  if (kPhase == 1 || !kFinish) return;  // the miss phase finishes the frame (the fused exploration frame: after its release pass)
+  frame_finish(P, D, F, fc, n_hit_frame);
+}
+
+// end of a frame: counters to the host, launch-scoped counters rearmed, the NEXT frame's scratch reset
+__device__ __forceinline__ void frame_finish(const MapParams &P, DeviceBuffers &D, const FrameParams &F, FrameCounters *fc, int n_hit_frame) {
   if (blockIdx.x == 0 && threadIdx.x == 0) fc->fused = 1;
   // the last block to get here publishes the frame counters to the host (no memcpy node in the graph)
   {

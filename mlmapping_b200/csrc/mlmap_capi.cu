@@ -439,6 +439,15 @@ int run_frame_complete(mlm_map *h, mlm_frame_stats *stats);
 // the miss pass, and the miss-set iteration order, so it runs as direct launches with one host check of the
 // container sizes in the middle (rehash detection for both emulated containers).
 int run_frame_explore_direct(mlm_map *h, int slow, uint32_t order_B, mlm_frame_stats *stats);
+// bucket-count evolution of miss_idx_set (clear() keeps the buckets)
+void miss_set_bucket_growth(mlm_map *h, int n_miss) {
+  if (n_miss > 0 && h->bucket_count_miss == 1) h->bucket_count_miss = 13;
+  while ((uint32_t)n_miss > h->bucket_count_miss) {
+    uint32_t nb = chain_next(h->bucket_count_miss);
+    if (nb == 0) break;
+    h->bucket_count_miss = nb;
+  }
+}
 int run_frame_explore(mlm_map *h, int mode, int N, mlm_frame_stats *stats) {
   const MapParams &P = h->P;
   cudaStream_t s = h->stream;
@@ -507,14 +516,7 @@ int run_frame_explore_direct(mlm_map *h, int slow, uint32_t order_B, mlm_frame_s
   CUDA_TRY(cudaMemcpyAsync(h->h_fc, h->D.fc[parity], sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   CUDA_TRY(cudaGetLastError());
-  // bucket-count evolution of miss_idx_set (clear() keeps the buckets)
-  const int n_miss = h->h_fc->n_miss_list;
-  if (n_miss > 0 && h->bucket_count_miss == 1) h->bucket_count_miss = 13;
-  while ((uint32_t)n_miss > h->bucket_count_miss) {
-    uint32_t nb = chain_next(h->bucket_count_miss);
-    if (nb == 0) break;
-    h->bucket_count_miss = nb;
-  }
+  miss_set_bucket_growth(h, h->h_fc->n_miss_list);
   return finish_frame(h, slow, order_B, stats);
 }
 
@@ -604,7 +606,9 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
     h->launches += 2;
     return MLM_OK;  // no host sync: the exchange and the owner-side kernels follow on the stream (mlm_shard_submit_*)
   }
-  if (P.explore) return run_frame_explore(h, mode, N, stats);
+  // exploration mode: one cooperative launch like a normal frame; the stand-alone passes serve the two-call interface,
+  // profiling runs and devices / configurations without the cooperative launch
+  if (P.explore && (h->stage_call || h->profiling || !h->use_graph || !h->use_fused)) return run_frame_explore(h, mode, N, stats);
   if (h->stage_call) {
     // awareness layer only (awareness_map_cylindrical::input_pc_pose): hit map + miss set of the frame, staged in the
     // frame-local voxel grid; the ordering of a rehash frame is settled here so that the frame's sets can be read
@@ -688,7 +692,10 @@ int run_frame(mlm_map *h, int mode, const void *d_in, int rows, int cols, int n_
     Fk.inline_resolve = F.inline_resolve = 1;
     const int gi = mode;
     cudaKernelNodeParams np = {};
-    np.func = mode == 1 ? (void *)k_frame<1> : (mode == 2 ? (void *)k_frame<2> : (void *)k_frame<0>);
+    if (P.explore)
+      np.func = mode == 1 ? (void *)k_frame_explore<1> : (mode == 2 ? (void *)k_frame_explore<2> : (void *)k_frame_explore<0>);
+    else
+      np.func = mode == 1 ? (void *)k_frame<1> : (mode == 2 ? (void *)k_frame<2> : (void *)k_frame<0>);
     np.gridDim = dim3(G);
     np.blockDim = dim3(kColThreads);
     np.sharedMemBytes = (unsigned)h->col_smem_bytes;
@@ -787,6 +794,42 @@ int run_frame_complete(mlm_map *h, mlm_frame_stats *stats) {
     for (int i = 0; i < MLM_NUM_FRAME_KERNELS; i++) cudaEventElapsedTime(&h->kms[i], h->kev[i], h->kev[i + 1]);
   int slow = 0;
   uint32_t order_B = h->bucket_count;
+  if (P.explore) {
+    // fused exploration frame: done, unless the hit map or the miss set crosses a rehash (the kernel returned after
+    // staging): re-sequence what needs it and run the passes as stand-alone kernels
+    if (h->h_fc->error == 0 && h->h_fc->overflow) {
+      const int n_hit = h->h_fc->n_hit, n_miss = h->h_fc->n_miss_list;
+      if (n_hit > h->sort_cap || n_miss > h->sort_cap) {
+        g_last_error = "hit / miss count exceeds ordering scratch";
+        h->poisoned = true;  // the frame's staging stays unconsumed
+        return MLM_ERR_CAPACITY;
+      }
+      F.order_mode = 1;
+      if ((uint32_t)n_hit > h->bucket_count) {
+        slow = 1;
+        int rc = order_slow_path(h, n_hit, 0, h->bucket_count, &order_B);
+        if (rc != MLM_OK) {
+          h->poisoned = true;
+          return rc;
+        }
+        F.bucket_count = order_B;
+        F.bucket_c64 = pow64_mod(F.bucket_count);
+      }
+      if ((uint32_t)n_miss > h->bucket_count_miss) {
+        slow = 1;
+        uint32_t Bm = 0;
+        int rc = order_slow_path(h, n_miss, 1, h->bucket_count_miss, &Bm);
+        if (rc != MLM_OK) {
+          h->poisoned = true;
+          return rc;
+        }
+        F.bucket_count_miss = Bm;
+      }
+      return run_frame_explore_direct(h, slow, order_B, stats);
+    }
+    miss_set_bucket_growth(h, h->h_fc->n_miss_list);
+    return finish_frame(h, slow, order_B, stats);
+  }
   if (h->h_fc->error == 0 && h->h_fc->overflow) {
     slow = 1;
     const int n = h->h_fc->n_hit;
@@ -1197,19 +1240,25 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
     g_last_error = "n_Phi too large for the projection's shared-memory histogram";
     return MLM_ERR_INVALID_CONFIG;
   }
-  // one cooperative launch per frame when every phase fits the resident CTA (not in exploration mode, whose
-  // ordered passes need extra kernels between the phases)
+  // one cooperative launch per frame when every phase fits the resident CTA (exploration mode: k_frame_explore, with
+  // its ordered passes behind further device-wide barriers)
   {
     CUDA_TRY_H(cudaFuncSetAttribute(k_frame<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ceiling));
     CUDA_TRY_H(cudaFuncSetAttribute(k_frame<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ceiling));
     CUDA_TRY_H(cudaFuncSetAttribute(k_frame<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ceiling));
+    CUDA_TRY_H(cudaFuncSetAttribute(k_frame_explore<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ceiling));
+    CUDA_TRY_H(cudaFuncSetAttribute(k_frame_explore<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ceiling));
+    CUDA_TRY_H(cudaFuncSetAttribute(k_frame_explore<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ceiling));
     int per_sm = 0, coop = 0;
-    CUDA_TRY_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame<1>, kColThreads, h->col_smem_bytes));
+    if (P.explore)
+      CUDA_TRY_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame_explore<1>, kColThreads, h->col_smem_bytes));
+    else
+      CUDA_TRY_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame<1>, kColThreads, h->col_smem_bytes));
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
     h->frame_grid = h->sm_count * std::min(per_sm, 1);
-    h->use_fused = coop && per_sm >= 1 && !P.explore &&
-                   project_smem_bytes(P.nCol, kColThreads) <= (size_t)h->col_smem_bytes;
+    h->use_fused = coop && per_sm >= 1 && project_smem_bytes(P.nCol, kColThreads) <= (size_t)h->col_smem_bytes;
     if (const char *e = getenv("MLM_NO_FUSED")) if (atoi(e)) h->use_fused = 0;
+    if (const char *e = getenv("MLM_NO_FUSED_EXPLORE")) if (atoi(e) && P.explore) h->use_fused = 0;
   }
   CUDA_TRY_H(cudaFuncSetAttribute(k_project<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ceiling));
   CUDA_TRY_H(cudaFuncSetAttribute(k_project<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ceiling));

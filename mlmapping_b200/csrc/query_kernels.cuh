@@ -169,22 +169,18 @@ __device__ __forceinline__ void neighbor_step(const MapParams &P, int dir, int g
 // where the log-odds of a subbox live: base + cell * mul (pool block: one float per cell; collapsed subbox: its single
 // element, mul 0; absent subbox: no storage, the reference's getOdd answers 0.5 == logit_inv(0.f))
 struct GradSource {
-  const float *base;
-  int mul;
+  unsigned long long v;   // address of element 0 (4-byte aligned) | mul in bit 0; 0 = absent
+  __device__ __forceinline__ bool present() const { return v != 0; }
 };
 __device__ __forceinline__ GradSource grad_source_key(const MapParams &P, const DeviceBuffers &D, uint64_t key) {
-  GradSource s = {nullptr, 0};
+  GradSource s = {0ull};
   uint32_t slot = ht_hash(key) & P.ht_mask;
   for (uint32_t probe = 0; probe <= P.ht_mask; probe++) {
     const uint64_t k = D.ht_key[slot];
     if (k == key) {
       const int block = D.ht_val[slot];
-      if (block >= 0) {
-        s.base = D.pool_lo + (size_t)block * P.cell_stride;
-        s.mul = 1;
-      } else if (block == kBlockCollapsed) {
-        s.base = D.col_lo + slot;
-      }
+      if (block >= 0) s.v = reinterpret_cast<unsigned long long>(D.pool_lo + (size_t)block * P.cell_stride) | 1ull;
+      else if (block == kBlockCollapsed) s.v = reinterpret_cast<unsigned long long>(D.col_lo + slot);
       return s;
     }
     if (k == kEmptyKey) return s;
@@ -194,12 +190,19 @@ __device__ __forceinline__ GradSource grad_source_key(const MapParams &P, const 
 }
 __device__ __forceinline__ GradSource grad_source(const MapParams &P, const DeviceBuffers &D, const int g[3]) {
   uint64_t key;
-  if (!pack_glb(g, key)) return GradSource{nullptr, 0};
+  if (!pack_glb(g, key)) return GradSource{0ull};
   return grad_source_key(P, D, key);
 }
-__device__ __forceinline__ float grad_lo(const GradSource &s, int sub) { return s.base ? __ldg(s.base + sub * s.mul) : 0.0f; }
+__device__ __forceinline__ float grad_lo(const GradSource &s, int sub) {
+  if (!s.present()) return 0.0f;
+  const float *base = reinterpret_cast<const float *>(s.v & ~3ull);
+  return __ldg(base + ((s.v & 1ull) ? sub : 0));
+}
 
-__global__ void __launch_bounds__(256, 4) k_get_odd_grad(MapParams P, DeviceBuffers D, const double *pos, size_t n,
+#ifndef MLM_GRAD_MINB
+#define MLM_GRAD_MINB 4
+#endif
+__global__ void __launch_bounds__(256, MLM_GRAD_MINB) k_get_odd_grad(MapParams P, DeviceBuffers D, const double *pos, size_t n,
                                                          int max_iter, double *out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -216,28 +219,39 @@ __global__ void __launch_bounds__(256, 4) k_get_odd_grad(MapParams P, DeviceBuff
   bool inner = packed;   // all six neighbours have a packed key too
 #pragma unroll
   for (int a = 0; a < 3; a++) inner = inner && c.g[a] > -lim && c.g[a] < lim - 1;
-  const GradSource src0 = packed ? grad_source_key(P, D, key0) : GradSource{nullptr, 0};
+  const GradSource src0 = packed ? grad_source_key(P, D, key0) : GradSource{0ull};
   const float lo0 = grad_lo(src0, c.sub);
   const int cxyz[3] = {c.sub % P.n, (c.sub / P.n) % P.n, c.sub / (P.n * P.n)};
   const int stride[3] = {1, P.n, P.n * P.n};
   const bool short_walk = max_iter <= P.n;   // a probe leaves at most one subbox behind
   GradSource nb[6];
-  bool any_source = src0.base != nullptr;
+  bool any_source = src0.present();
+  // per axis usually ONE of the two probes can leave the subbox (both only when max_iter exceeds half a subbox): one
+  // lookup site per axis serves whichever direction a lane needs, so the warp runs three lookups, not six half-empty ones
 #pragma unroll
-  for (int d = 0; d < 6; d++) {
-    const int axis = 2 - (d >> 1);
-    const bool reach = (d & 1) ? (cxyz[axis] - max_iter < 0) : (cxyz[axis] + max_iter >= P.n);
-    nb[d] = GradSource{nullptr, 0};
-    if (reach) {
+  for (int h = 0; h < 3; h++) {   // h = d >> 1: z, y, x
+    const int axis = 2 - h;
+    const bool reach_p = cxyz[axis] + max_iter >= P.n, reach_m = cxyz[axis] - max_iter < 0;
+    nb[2 * h] = GradSource{0ull};
+    nb[2 * h + 1] = GradSource{0ull};
+    auto neighbour = [&](bool minus) {
       if (inner) {
-        const uint64_t step = 1ull << (21 * (d >> 1));   // pack_glb: x at bit 42, y at 21, z at 0
-        nb[d] = grad_source_key(P, D, (d & 1) ? key0 - step : key0 + step);
-      } else {
-        int g[3] = {c.g[0], c.g[1], c.g[2]};
-        g[axis] += (d & 1) ? -1 : 1;
-        nb[d] = grad_source(P, D, g);
+        const uint64_t step = 1ull << (21 * h);   // pack_glb: x at bit 42, y at 21, z at 0
+        return grad_source_key(P, D, minus ? key0 - step : key0 + step);
       }
-      any_source = any_source || nb[d].base != nullptr;
+      int g[3] = {c.g[0], c.g[1], c.g[2]};
+      g[axis] += minus ? -1 : 1;
+      return grad_source(P, D, g);
+    };
+    if (reach_p || reach_m) {
+      const GradSource s = neighbour(!reach_p);
+      if (reach_p) nb[2 * h] = s;
+      else nb[2 * h + 1] = s;
+      any_source = any_source || s.present();
+    }
+    if (reach_p && reach_m) {
+      nb[2 * h + 1] = neighbour(true);
+      any_source = any_source || nb[2 * h + 1].present();
     }
   }
   // log-odds of the six neighbours of round k
@@ -278,14 +292,15 @@ __global__ void __launch_bounds__(256, 4) k_get_odd_grad(MapParams P, DeviceBuff
   float lo_d[6];
   int m = 0, k = max_iter + 1;
   float lo_m = lo0;
-  if (any_source || !short_walk) {   // nothing stored within reach: every probe reads 0.5, like the origin
+  if (any_source || !short_walk)   // (nothing stored within reach: every probe reads 0.5, like the origin)
+  {
     for (k = 1; k <= max_iter; k++) {
       load_round(k, lo_d);
       m = 0;
       lo_m = lo_d[0];
 #pragma unroll
       for (int d = 1; d < 6; d++)
-        if (lo_d[d] < lo_m) {   // lowest log-odds of the round, first direction wins ties
+        if (lo_d[d] < lo_m) {
           lo_m = lo_d[d];
           m = d;
         }

@@ -291,10 +291,15 @@ def test_sampled_project_depth_matches_glibc_rand_stream():
     assert_map_parity(gpu, orc, LO_TOL)
 
 
-def test_exploration_frontiers_and_memory_release():
+@pytest.mark.parametrize("one_launch", [True, False])
+def test_exploration_frontiers_and_memory_release(one_launch, monkeypatch):
     """use_exploration_frontiers = true (config2.yaml:36): update_observation in miss-set iteration order,
     frontier sets, neighbour subbox allocation, release pass (collapse to element 0), queries on collapsed
-    subboxes — SURVEY §8a a14-a15"""
+    subboxes — SURVEY §8a a14-a15.  Once as the single cooperative launch per frame (k_frame_explore; the frames
+    that cross a rehash of the hit map or the miss set fall back to the stand-alone passes), once with the
+    stand-alone passes for every frame."""
+    if not one_launch:
+        monkeypatch.setenv("MLM_NO_FUSED_EXPLORE", "1")
     cfg = config_cfg_a()
     cfg.use_exploration_frontiers = 1
     gpu, orc = MLMap(cfg), Oracle(cfg)
