@@ -97,7 +97,7 @@ __device__ __forceinline__ void explore_a_body(const MapParams &P, DeviceBuffers
       }
       // allocate_ram(glb_idx_nb): find, or create (a fresh subbox is all 'u')
       uint32_t slot = ht_hash(hkey) & P.ht_mask;
-      int val = kBlockPending;
+      int val = kBlockPending, created = -1;
       bool found = false;
       for (uint32_t probe = 0; probe <= P.ht_mask; probe++) {
         uint64_t k = D.ht_key[slot];
@@ -111,7 +111,8 @@ __device__ __forceinline__ void explore_a_body(const MapParams &P, DeviceBuffers
               D.ht_val[slot] = kBlockUnusable;
               fc->error = kErrPool;
             } else {
-              D.ht_val[slot] = D.free_stack[top];
+              created = D.free_stack[top];
+              D.ht_val[slot] = created;
               atomicAdd(&fc->n_new_blocks, 1);
             }
             val = kBlockPending;  // created in this pass: every cell 'u'
@@ -146,14 +147,18 @@ __device__ __forceinline__ void explore_a_body(const MapParams &P, DeviceBuffers
         }
       }
       if (is_u) {
-        D.miss_choice[j] = (signed char)i;
+        // frontier[glb_nb].emplace(sub_nb): at once when the neighbour's block is known here (nobody reads the frontier
+        // words during this pass); a subbox another thread is creating right now is left to pass B
+        const int blk = val >= 0 ? val : created;
+        if (blk >= 0) atomicOr(&D.pool_front[(size_t)blk * P.front_words + (subn >> 5)], 1u << (subn & 31));
+        else D.miss_choice[j] = (signed char)i;
         break;
       }
     }
   }
 }
 
-// pass B: frontier[glb_nb].emplace(sub_nb) for the choices of pass A (all subboxes exist now)
+// pass B: frontier[glb_nb].emplace(sub_nb) for the choices pass A could not place itself (all subboxes exist now)
 __device__ __forceinline__ void explore_b_body(const MapParams &P, DeviceBuffers &D, const FrameParams &F) {
   const FrameCounters *fc = D.fc[F.parity];
   const int n = fc->n_miss_list;
@@ -192,10 +197,19 @@ __device__ __forceinline__ void release_body(const MapParams &P, DeviceBuffers &
     const int block = ht_find_slot(P, D, g, slot);
     if (block < 0) continue;  // absent or already collapsed (occupancy.size() == 1)
     const size_t base = (size_t)block * P.cell_stride;
+    // (no short-circuit: the loads of a lane are independent and all in flight together)
     bool ok = true;
-    for (int w = lane; w < P.front_words; w += 32) ok = ok && D.pool_front[(size_t)block * P.front_words + w] == 0;
+    for (int w = lane; w < P.front_words; w += 32) ok &= D.pool_front[(size_t)block * P.front_words + w] == 0;
     const char first = D.pool_occ[base];
-    for (int i = lane; i < P.cells; i += 32) ok = ok && D.pool_occ[base + i] == first;
+    if ((base & 3) == 0) {
+      const uint32_t first4 = 0x01010101u * (uint32_t)(unsigned char)first;
+      const uint32_t *occ4 = reinterpret_cast<const uint32_t *>(D.pool_occ + base);
+      const int n4 = P.cells >> 2;
+      for (int i = lane; i < n4; i += 32) ok &= occ4[i] == first4;
+      for (int i = (n4 << 2) + lane; i < P.cells; i += 32) ok &= D.pool_occ[base + i] == first;
+    } else {
+      for (int i = lane; i < P.cells; i += 32) ok &= D.pool_occ[base + i] == first;
+    }
     if (!__all_sync(0xffffffffu, ok)) continue;
     if (lane == 0) {
       D.col_occ[slot] = first;
@@ -233,6 +247,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_frame_explore(MapParams P, D
   extern __shared__ __align__(16) unsigned char s_raw[];
   const int G = (int)gridDim.x;
   FrameCounters *fc = D.fc[F.parity];
+  MLM_FRAME_WALL(0);
   {
     const int n_tiles = (F.n_total + F.tile_pts - 1) / F.tile_pts;
     for (int t = blockIdx.x; t < max(n_tiles, 1); t += G) {
@@ -240,25 +255,35 @@ __global__ void __launch_bounds__(kColThreads, 1) k_frame_explore(MapParams P, D
       __syncthreads();
     }
   }
+  MLM_FRAME_WALL(1);
   grid_barrier(D.grid_bar, G);
+  MLM_FRAME_WALL(2);
   column_phase(P, D, F, s_raw);
+  MLM_FRAME_WALL(3);
   grid_barrier(D.grid_bar, 2 * G);
+  MLM_FRAME_WALL(4);
   if (blockIdx.x == 0 && threadIdx.x == 0) *D.col_queue = 0;
   if (__ldcg(&fc->n_hit) > (int)F.bucket_count || __ldcg(&fc->n_miss_list) > (int)F.bucket_count_miss) {
     frame_bail(D, fc, F);
     return;
   }
   fuse_body<1>(P, D, F);          // hits (the frame-local voxel grid stays intact)
+  MLM_FRAME_WALL(5);
   grid_barrier(D.grid_bar, 3 * G);
   miss_tkey_body(P, D, F);        // first miss cell of every voxel in set iteration order
+  MLM_FRAME_WALL(6);
   grid_barrier(D.grid_bar, 4 * G);
   explore_a_body(P, D, F);        // update_observation: neighbour choices, neighbour subboxes allocated
+  MLM_FRAME_WALL(9);
   grid_barrier(D.grid_bar, 5 * G);
   explore_b_body(P, D, F);        // frontier inserts
+  MLM_FRAME_WALL(10);
   grid_barrier(D.grid_bar, 6 * G);
   fuse_body<2, false>(P, D, F);   // misses
+  MLM_FRAME_WALL(11);
   grid_barrier(D.grid_bar, 7 * G);
   release_body(P, D, F);          // collapse pass over the observed subboxes
+  MLM_FRAME_WALL(12);
   frame_finish(P, D, F, fc, __ldcg(&fc->n_hit));
 }
 

@@ -1246,7 +1246,7 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
   // same-address atomic with return on every thread's dependent chain).
   uint32_t *s_list = reinterpret_cast<uint32_t *>(s_keys);
   uint32_t *s_tout = s_list + P.sort_cap_smem * 2;
-  __shared__ int s_tcnt, s_tbase, s_rcnt, s_rbase;
+  __shared__ int s_tcnt, s_tbase, s_rcnt, s_rbase, s_mbase;
   const int list_cap = P.sort_cap_smem * 2;            // 32-bit entries in one key buffer
   const int words_per_chunk = max(1, list_cap >> 5);   // a chunk of words can never overflow the list
   for (int wi = z_own_lo * P.words_per_row + tid; wi < z_own_hi * P.words_per_row; wi += blockDim.x) g_miss[wi] = s_miss[wi];
@@ -1271,6 +1271,12 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
     compact_bits(s_miss, w0, min(w0 + words_per_chunk, stage_w1), s_list, &s_nk, tid >> 5, (int)blockDim.x >> 5);
     __syncthreads();
     const int n_list = s_nk;
+    if (P.explore) {
+      // the chunk's miss cells take a contiguous run of the frame's miss list: ONE reservation per chunk (an atomic per
+      // warp on the list's counter, from every CTA, serialises at that address for tens of microseconds per frame)
+      if (tid == 0) s_mbase = n_list ? atomicAdd(&fc->n_miss_list, n_list) : 0;
+      __syncthreads();
+    }
     for (int k = tid; k < n_list; k += blockDim.x) {
       const uint32_t e = s_list[k];
       const int wi = (int)(e >> 5), z = wi / P.words_per_row, wr = wi - z * P.words_per_row;
@@ -1278,21 +1284,21 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
       double2 cxy = __ldg(&P.centre_xy[phi * P.nRho + r]);
       CellRef cr = locate_cell(P, cxy.x + F.t_wa[0], cxy.y + F.t_wa[1], __ldg(&P.centre_z[z]) + F.t_wa[2]);
       int lv = lvg_index(P, F, cr);
-      if (lv < 0) {
-        fc->error = kErrInternal;
-        continue;
-      }
       if (P.explore) {
         // per-frame miss list for the ordered exploration passes
         const int idx_cell = (z * P.nPhi + phi) * P.nRho + r;  // mapIdx
         const uint32_t st = stamp_col[z * P.nRho + r];
-        const uint32_t bkt = (uint32_t)((uint64_t)(uint32_t)idx_cell % (uint64_t)F.bucket_count_miss);
+        const uint32_t bkt = (uint32_t)idx_cell % F.bucket_count_miss;   // identity hash of the size_t key
         atomicMin(&D.act_miss[F.parity][bkt], st);
-        const int j = agg_inc(&fc->n_miss_list);
+        const int j = s_mbase + k;
         D.miss_idx[j] = idx_cell;
-        D.miss_lv[j] = lv;
+        D.miss_lv[j] = lv < 0 ? 0 : lv;   // (lv < 0 fails the frame below; the slot stays well-formed)
         D.miss_t[j] = st;
         D.miss_bucket[j] = bkt;
+      }
+      if (lv < 0) {
+        fc->error = kErrInternal;
+        continue;
       }
       int old = atomicAdd(&D.lvg[lv].y, 1);
       const bool remote = F.stage_only && subbox_owner(cr.g, F.shard_world) != F.shard_rank;
