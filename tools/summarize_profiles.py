@@ -31,7 +31,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__thread_inst_executed_per_inst_executed.pct"]
 UNITS = {}
 summary = {}
-for name in ["prof_frame", "prof_queries", "prof_lidar", "prof_shard"]:
+for name in ["prof_frame", "prof_queries", "prof_lidar", "prof_shard", "prof_explore"]:
     rep = ROOT / "gpurun_out" / f"{name}_{tag}.ncu-rep"
     if not rep.exists():
         continue
