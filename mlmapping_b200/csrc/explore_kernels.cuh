@@ -233,6 +233,7 @@ __device__ __forceinline__ void release_body(const MapParams &P, DeviceBuffers &
   }
 }
 
+__global__ void __launch_bounds__(256) k_miss_finalize(MapParams P, DeviceBuffers D, FrameParams F) { miss_finalize_body(P, D, F); }
 __global__ void __launch_bounds__(256) k_miss_tkey(MapParams P, DeviceBuffers D, FrameParams F) { miss_tkey_body(P, D, F); }
 __global__ void __launch_bounds__(256) k_explore_a(MapParams P, DeviceBuffers D, FrameParams F) { explore_a_body(P, D, F); }
 __global__ void __launch_bounds__(256) k_explore_b(MapParams P, DeviceBuffers D, FrameParams F) { explore_b_body(P, D, F); }
@@ -263,6 +264,7 @@ __global__ void __launch_bounds__(kColThreads, 1) k_frame_explore(MapParams P, D
   grid_barrier(D.grid_bar, 2 * G);
   MLM_FRAME_WALL(4);
   if (blockIdx.x == 0 && threadIdx.x == 0) *D.col_queue = 0;
+  miss_finalize_body(P, D, F);    // split layouts: stamps of the sensor-row miss cells (read again behind the next barriers)
   if (__ldcg(&fc->n_hit) > (int)F.bucket_count || __ldcg(&fc->n_miss_list) > (int)F.bucket_count_miss) {
     frame_bail(D, fc, F);
     return;

@@ -835,6 +835,25 @@ __host__ __device__ inline size_t col_smem_prefix_bytes(int col_words, int nRho,
 #endif
 
 // One work item (a phi column or one of its halves), start to finish, by the whole CTA.
+// exploration mode, split layouts: first-insert stamp of a miss-list entry whose cell lies in the sensor row, once every
+// column of the frame has walked (the stamp is the minimum over the walks of both halves of the column)
+constexpr uint32_t kMissStampPending = 0xffffffffu;
+__device__ __forceinline__ void miss_finalize_body(const MapParams &P, DeviceBuffers &D, const FrameParams &F) {
+  if (!P.explore || !P.split) return;
+  const FrameCounters *fc = D.fc[F.parity];
+  const int n = __ldcg(&fc->n_miss_list);
+  const int per_z = P.nRho * P.nPhi;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    if (__ldcg(&D.miss_t[j]) != kMissStampPending) continue;
+    const int idx = __ldcg(&D.miss_idx[j]);                       // mapIdx = (z * nPhi + phi) * nRho + r
+    const int z = idx / per_z, rem = idx - z * per_z;
+    const int phi = rem / P.nRho, r = rem - phi * P.nRho;
+    const uint32_t st = __ldcg(&D.miss_stamp[((size_t)phi * P.nZ + z) * P.nRho + r]);
+    D.miss_t[j] = st;
+    atomicMin(&D.act_miss[F.parity][__ldcg(&D.miss_bucket[j])], st);
+  }
+}
+
 // item < nCol: work column `item`; item >= nCol (split layouts only): the two halves of phi column item - nCol worked as
 // ONE whole column (the queue merges the lightest columns when there are more active halves than CTAs: a second round of
 // items costs more than the few larger ones).  The halves feed disjoint hit cells, so concatenating their records is exact.
@@ -870,11 +889,14 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
   // exploration mode: per-column stamp arrays (earliest point stamp per end cell, first-insert stamp per miss cell)
   uint32_t *end_t_col = P.explore ? D.end_t + (size_t)phi * P.nZ * P.nRho : nullptr;
   uint32_t *stamp_col = P.explore ? D.miss_stamp + (size_t)phi * P.nZ * P.nRho : nullptr;
-  if (P.explore)
-    for (int i = tid; i < P.nZ * P.nRho; i += blockDim.x) {
-      end_t_col[i] = 0xffffffffu;
-      stamp_col[i] = 0xffffffffu;
-    }
+  if (P.explore) {
+    // rows of this item.  Split layouts: the end cells of the sensor row belong to the upper half; the miss stamps of that
+    // row are written by the walks of BOTH halves, so nobody resets them here (frame_finish leaves them reset)
+    const int e_lo = side == 1 ? P.n_below : z_own_lo;
+    for (int i = e_lo * P.nRho + tid; i < z_own_hi * P.nRho; i += blockDim.x) end_t_col[i] = 0xffffffffu;
+    for (int i = z_own_lo * P.nRho + tid; i < z_own_hi * P.nRho; i += blockDim.x)
+      if (!P.split || i < P.n_below * P.nRho || i >= (P.n_below + 1) * P.nRho) stamp_col[i] = 0xffffffffu;
+  }
   // ---- locate this column's records in the per-CTA windows k_project wrote (replaces a scatter pass):
   // s_map[k] = index into rec_lin of the column's k-th record
   __shared__ int s_warp[33];
@@ -1287,9 +1309,12 @@ __device__ __forceinline__ void column_item(const MapParams &P, DeviceBuffers &D
       if (P.explore) {
         // per-frame miss list for the ordered exploration passes
         const int idx_cell = (z * P.nPhi + phi) * P.nRho + r;  // mapIdx
-        const uint32_t st = stamp_col[z * P.nRho + r];
+        // split layouts: a cell of the sensor row gets its stamp from the walks of both halves, and the other half may
+        // still be walking: the entry stays pending until miss_finalize_body (after all columns)
+        const bool pending = P.split && z == P.n_below;
+        const uint32_t st = pending ? kMissStampPending : stamp_col[z * P.nRho + r];
         const uint32_t bkt = (uint32_t)idx_cell % F.bucket_count_miss;   // identity hash of the size_t key
-        atomicMin(&D.act_miss[F.parity][bkt], st);
+        if (!pending) atomicMin(&D.act_miss[F.parity][bkt], st);
         const int j = s_mbase + k;
         D.miss_idx[j] = idx_cell;
         D.miss_lv[j] = lv < 0 ? 0 : lv;   // (lv < 0 fails the frame below; the slot stays well-formed)
@@ -1823,6 +1848,11 @@ __device__ __forceinline__ void frame_finish(const MapParams &P, DeviceBuffers &
       D.phi_hist[i] = 0;
       D.phi_bound[i] = 0;
     }
+    if (P.explore && P.split)   // miss stamps of the sensor row (both halves of a column write them; this frame is done with them)
+      for (int i = gtid; i < P.nPhi * P.nRho; i += nth) {
+        const int phi = i / P.nRho, r = i - phi * P.nRho;
+        D.miss_stamp[((size_t)phi * P.nZ + P.n_below) * P.nRho + r] = 0xffffffffu;
+      }
     if (gtid < (int)(sizeof(FrameCounters) / sizeof(int))) reinterpret_cast<int *>(D.fc[F.parity ^ 1])[gtid] = 0;
   }
 }

@@ -462,6 +462,10 @@ int run_frame_explore(mlm_map *h, int mode, int N, mlm_frame_stats *stats) {
   else
     k_project<0><<<proj_grid, kProjThreads, project_smem_bytes(P.nCol, kProjThreads), s>>>(P, h->D, F);
   k_column<<<h->col_grid, kColThreads, h->col_smem_bytes, s>>>(P, h->D, F);
+  if (P.split) {
+    k_miss_finalize<<<h->sm_count * 4, 256, 0, s>>>(P, h->D, F);
+    h->launches++;
+  }
   FrameCounters mid;
   CUDA_TRY(cudaMemcpyAsync(&mid, h->D.fc[parity], sizeof(mid), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
@@ -1098,9 +1102,11 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
   // Half-column split: records below the sensor row (z_idx < n_below) and at/above it never feed the same hit
   // cell when every neighbour step stays on its side of the row, i.e. z - n_below and
   // round(z -/+ d*rate) - n_below = round((z - n_below) * (1 -/+ d/rho)) have the same sign: 2*K(rho) < rho.
-  // Their ray walks share only the row n_below itself (arbitrated through the global miss bitmap).  The
-  // exploration mode needs per-cell first-insert stamps across both halves, so it keeps whole columns.
-  P.split = cfg->use_exploration_frontiers ? 0 : 1;
+  // Their ray walks share only the row n_below itself (arbitrated through the global miss bitmap).  In the
+  // exploration mode the first-insert stamps of that row's miss cells come from both halves: they are settled after
+  // all columns (miss_finalize_body).
+  P.split = 1;
+  if (const char *e = getenv("MLM_DEBUG_NO_SPLIT_EXPLORE")) if (atoi(e) && cfg->use_exploration_frontiers) P.split = 0;
   for (int r = 0; r < P.nRho; r++)
     if (T.k_reach[r] > 0 && 2 * T.k_reach[r] >= r) P.split = 0;
   if (P.n_below < 1 || P.n_below >= P.nZ - 1 || P.nRho >= 4096 || 2 * P.nPhi > kMaxPhi) P.split = 0;
@@ -1343,6 +1349,7 @@ int mlm_create(const mlm_config *cfg, int device, mlm_handle *out) {
     TRY(dev_alloc(h, &D.col_lo, (size_t)ht_cap));
     TRY(dev_alloc(h, &D.end_t, (size_t)n_cells));
     TRY(dev_alloc(h, &D.miss_stamp, (size_t)n_cells));
+    CUDA_TRY_H(cudaMemset(D.miss_stamp, 0xff, (size_t)n_cells * 4));  // (split layouts rely on the sensor row being reset between frames)
     h->act_miss_cap = chain_cover((uint32_t)n_cells);
     if (h->act_miss_cap == 0) {
       g_last_error = "awareness cell count exceeds the bucket chain table";
