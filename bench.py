@@ -765,13 +765,13 @@ def main():
         achieved = per_rank_bytes / (top_ms * 1e-3) / 1e9
         traffic, traffic_src = None, None
         try:  # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
-            prof = json.loads((ROOT / "profiles" / "ncu_full_summary_r01.json").read_text())[top][0]
+            prof = json.loads((ROOT / "profiles" / "ncu_full_summary_r02.json").read_text())[top][0]
 
             def _bytes(v):
                 num, unit = v.split()
                 return float(num) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
             traffic = _bytes(prof["dram__bytes_read.sum"]) + _bytes(prof["dram__bytes_write.sum"])
-            traffic_src = "profiles/ncu_full_summary_r01.json (bytes per launch, cold-cache ncu capture)"
+            traffic_src = "profiles/ncu_full_summary_r02.json (bytes per launch, cold-cache ncu capture)"
         except Exception:
             pass
         out = {

@@ -278,12 +278,14 @@ __global__ void __launch_bounds__(kColThreads, 1) k_frame_explore(MapParams P, D
   explore_a_body(P, D, F);        // update_observation: neighbour choices, neighbour subboxes allocated
   MLM_FRAME_WALL(9);
   grid_barrier(D.grid_bar, 5 * G);
-  explore_b_body(P, D, F);        // frontier inserts
+  // frontier inserts pass A left over: neighbours in subboxes another thread was creating at that moment.  Such a subbox
+  // did not exist when the frame was staged, so no voxel of it is touched this frame and the miss pass erases no
+  // frontier bit in it: the two passes share a phase
+  explore_b_body(P, D, F);
   MLM_FRAME_WALL(10);
-  grid_barrier(D.grid_bar, 6 * G);
   fuse_body<2, false>(P, D, F);   // misses
   MLM_FRAME_WALL(11);
-  grid_barrier(D.grid_bar, 7 * G);
+  grid_barrier(D.grid_bar, 6 * G);
   release_body(P, D, F);          // collapse pass over the observed subboxes
   MLM_FRAME_WALL(12);
   frame_finish(P, D, F, fc, __ldcg(&fc->n_hit));
