@@ -749,6 +749,15 @@ def main():
     # ---------------- reduce over ranks: max time, sum of rays ----------------
     from mlmapping_b200.sharding import reduce_timing
     q_ms_local = queries["total_ms"] if queries else 0.0
+    # per-rank device time of the timed steps (every rank integrates ITS agent's trajectory: other walls, other seeds, so
+    # the frames of different ranks are not the same work; the headline takes the max, the spread is reported next to it)
+    per_rank_us = [1e3 * dev_ms / args.steps]
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.zeros(world, dtype=torch.float64, device="cuda")
+        tt[rank] = per_rank_us[0]
+        dist.all_reduce(tt)
+        per_rank_us = tt.tolist()
     (dev_ms, e2e_s, q_ms_max), (rays, e2e_rays, launches) = reduce_timing(
         [dev_ms, e2e_s, q_ms_local], [rays, e2e_rays, launches], device="cuda" if world > 1 else None)
     rays, e2e_rays, launches = int(rays), int(e2e_rays), int(launches)
@@ -783,6 +792,10 @@ def main():
                        "slow_ordering_frames": slow_frames, "submaps_allocated_rank0": submaps,
                        "wall_s_timed_loop": wall1 - wall0},
             "us_per_frame": 1e3 * dev_ms / args.steps,
+            "us_per_frame_over_ranks": {"min": float(np.min(per_rank_us)), "median": float(np.median(per_rank_us)),
+                                        "max": float(np.max(per_rank_us)), "per_rank": [round(v, 2) for v in per_rank_us],
+                                        "note": "rank r integrates agent r's own trajectory (different geometry and seeds): "
+                                                "the max over ranks is the heaviest trajectory, not a slower GPU"},
             "e2e": {"value": e2e_rays / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 2 * ROWS * COLS + 136,
                     "d2h_bytes_per_step": 64 + 24, "us_per_frame": 1e6 * e2e_s / args.steps},
             "gpu_launches": launches,

@@ -335,6 +335,20 @@ int mlm_dirty_count(mlm_handle h, int32_t *n_blocks, size_t *record_bytes);
 int mlm_dirty_export(mlm_handle h, void *d_out, int32_t n_blocks);
 int mlm_dirty_import(mlm_handle h, const void *d_in, int32_t n_blocks);
 
+/* The same replication without a collective of the caller: every rank opens an inbox arena (mlm_replica_open fills
+ * a MLM_SHARD_BLOB_BYTES setup blob), the `world` blobs are exchanged once (any transport) and handed to
+ * mlm_replica_connect in rank order.  After each frame the source rank calls mlm_replica_publish: one kernel packs the
+ * frame's dirty blocks straight into every replica's inbox over NVLink peer memory (CUDA IPC between processes) and
+ * raises the frame's flag; every replica calls mlm_replica_apply: one kernel waits for the flag (bounded device-side
+ * spin, MLM_SHARD_TIMEOUT_MS), applies the records and acknowledges to the source.  Inboxes are double-buffered by
+ * frame parity: the source may be two frames ahead of the slowest replica.  Calls come in lock step, one publish and
+ * one apply per frame.  n_blocks_out (may be NULL) receives the number of blocks shipped / applied. */
+int mlm_replica_open(mlm_handle h, int rank, int world, int src_rank, void *blob_out /* MLM_SHARD_BLOB_BYTES */);
+int mlm_replica_connect(mlm_handle h, const void *blobs /* world * MLM_SHARD_BLOB_BYTES, rank order */);
+int mlm_replica_publish(mlm_handle h, int32_t *n_blocks_out);
+int mlm_replica_apply(mlm_handle h, int32_t *n_blocks_out);
+int mlm_replica_close(mlm_handle h); /* unmaps the peers' arenas; call on every rank before any rank is destroyed */
+
 /* glibc-2.39 log10f as evaluated on device (parity test hook, SURVEY §7 hard part 3) */
 int mlm_debug_log10f(mlm_handle h, const float *x, size_t n, float *out);
 

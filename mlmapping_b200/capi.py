@@ -125,6 +125,7 @@ ABI_SYMBOLS = [
     "mlm_frame_submit_depth_u16_device", "mlm_frame_submit_points_f64_device", "mlm_frame_finish", "mlm_get_odd_at", "mlm_get_odd_at_device",
     "mlm_shard_open", "mlm_shard_connect", "mlm_shard_submit_points_f64", "mlm_shard_submit_points_f64_device", "mlm_shard_finish",
     "mlm_shard_integrate_points_f64", "mlm_shard_last_exchange", "mlm_shard_last_kernel_ms", "mlm_shard_close", "mlm_dirty_count", "mlm_dirty_export", "mlm_dirty_import",
+    "mlm_replica_open", "mlm_replica_connect", "mlm_replica_publish", "mlm_replica_apply", "mlm_replica_close",
     "mlm_export_cloud", "mlm_export_cloud_device", "mlm_export_odds_slice",
     "mlm_checkpoint_size", "mlm_checkpoint_save", "mlm_checkpoint_restore", "mlm_compensate_pose",
     "mlm_export_cloud", "mlm_export_cloud_device", "mlm_export_odds_slice",
@@ -226,6 +227,11 @@ def load_library() -> C.CDLL:
         "mlm_dirty_count": ([vp, ip, C.POINTER(sz)], C.c_int),
         "mlm_dirty_export": ([vp, vp, C.c_int32], C.c_int),
         "mlm_dirty_import": ([vp, vp, C.c_int32], C.c_int),
+        "mlm_replica_open": ([vp, C.c_int, C.c_int, C.c_int, vp], C.c_int),
+        "mlm_replica_connect": ([vp, vp], C.c_int),
+        "mlm_replica_publish": ([vp, C.POINTER(C.c_int32)], C.c_int),
+        "mlm_replica_apply": ([vp, C.POINTER(C.c_int32)], C.c_int),
+        "mlm_replica_close": ([vp], C.c_int),
         "mlm_debug_log10f": ([vp, vp, sz, vp], C.c_int),
         "mlm_debug_phase_cycles": ([vp, vp, sz], C.c_int),
         "mlm_srand": ([vp, C.c_uint], C.c_int),

@@ -222,6 +222,14 @@ struct mlm_map {
   bool shard_shares_device = false;  // another rank of this process runs on the same GPU (single-GPU tests)
   uint32_t shard_epoch = 0;
   unsigned long long shard_timeout_ns = 10ull * 1000 * 1000 * 1000;
+  // replicated map over peer memory (mlm_replica_*)
+  ReplicaPeers replica_peers = {};
+  void *replica_arena = nullptr;
+  void *replica_mapped[kMaxWorld] = {};
+  bool replica_open = false, replica_connected = false;
+  uint32_t replica_epoch = 0;
+  int *d_replica_state = nullptr;   // source: {ticket, error}; replica: {new blocks, error, ticket, records}
+  int replica_last_blocks = 0;
   int shard_world = 1, shard_rank = 0;
   bool shard_stage_pending = false;
   cudaGraphExec_t graph_exec[3] = {nullptr, nullptr, nullptr};  // by input mode: points, depth image, sampled pixels
@@ -2832,6 +2840,201 @@ int mlm_dirty_import(mlm_handle h, const void *d_in, int32_t n_blocks) {
   h->cum_ram_expand += cnt[0];
   h->n_submaps += cnt[0];
   return cnt[1] ? map_device_error(cnt[1]) : MLM_OK;
+}
+
+// ---- replicated map over NVLink peer memory (query streams split over GPUs) -------------------------------
+namespace {
+constexpr uint32_t kReplicaMagic = 0x4d4c5250u;  // "MLRP"
+ReplicaArena carve_replica(void *base, size_t half_bytes, size_t *total) {
+  unsigned char *p = reinterpret_cast<unsigned char *>(base);
+  size_t off = 0;
+  ReplicaArena a;
+  a.flags = reinterpret_cast<uint32_t *>(p + off);
+  off = align256(off + 2 * sizeof(uint32_t));
+  a.count = reinterpret_cast<int *>(p + off);
+  off = align256(off + 2 * sizeof(int));
+  a.ack = reinterpret_cast<uint32_t *>(p + off);
+  off = align256(off + kMaxWorld * sizeof(uint32_t));
+  a.inbox = p + off;
+  off = align256(off + 2 * half_bytes);
+  if (total) *total = off;
+  return a;
+}
+int replica_check(mlm_handle h) {
+  if (!h) return MLM_ERR_INVALID_ARG;
+  if (!h->replica_open || !h->replica_connected) {
+    g_last_error = "mlm_replica_open / mlm_replica_connect must come first";
+    return MLM_ERR_INVALID_ARG;
+  }
+  return MLM_OK;
+}
+}  // namespace
+
+int mlm_replica_open(mlm_handle h, int rank, int world, int src, void *blob_out) {
+  if (!h || !blob_out || world < 1 || world > kMaxWorld || rank < 0 || rank >= world || src < 0 || src >= world) return MLM_ERR_INVALID_ARG;
+  if (h->P.explore) return MLM_ERR_UNSUPPORTED;
+  if (h->replica_open) {
+    g_last_error = "handle is already part of a replicated map";
+    return MLM_ERR_INVALID_ARG;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  const MapParams &P = h->P;
+  // dirty blocks of one frame: at most the subboxes of the frame-local subbox grid (MLM_REPLICA_MAX_BLOCKS overrides)
+  long long cap = std::min<long long>((long long)P.lsg_dim_xy * P.lsg_dim_xy * P.lsg_dim_z, 32768);
+  if (const char *e = getenv("MLM_REPLICA_MAX_BLOCKS")) cap = std::max(1ll, atoll(e));
+  const size_t half = (size_t)cap * dirty_record_bytes(P.cells);
+  size_t bytes = 0;
+  carve_replica(nullptr, half, &bytes);
+  CUDA_TRY(cudaMalloc(&h->replica_arena, bytes));
+  h->allocs.push_back(h->replica_arena);
+  CUDA_TRY(cudaMemset(h->replica_arena, 0, 3 * 256));
+  CUDA_TRY(cudaMalloc((void **)&h->d_replica_state, 4 * sizeof(int)));
+  h->allocs.push_back(h->d_replica_state);
+  CUDA_TRY(cudaMemset(h->d_replica_state, 0, 4 * sizeof(int)));
+  if (const char *e = getenv("MLM_SHARD_TIMEOUT_MS")) h->shard_timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
+  ReplicaPeers &X = h->replica_peers;
+  memset(&X, 0, sizeof(X));
+  X.rank = rank;
+  X.world = world;
+  X.src = src;
+  X.cap_blocks = (int)cap;
+  X.half_bytes = half;
+  X.a[rank] = carve_replica(h->replica_arena, half, nullptr);
+  h->replica_epoch = 0;
+  ShardBlob b;
+  memset(&b, 0, sizeof(b));
+  b.magic = kReplicaMagic;
+  b.rank = rank;
+  b.world = world;
+  b.device = h->device;
+  b.hit_cap = src;
+  b.rec_cap = (int)cap;
+  b.pid = (int64_t)getpid();
+  b.ptr = (uint64_t)(uintptr_t)h->replica_arena;
+  if (world > 1) CUDA_TRY(cudaIpcGetMemHandle(&b.ipc, h->replica_arena));
+  memset(blob_out, 0, MLM_SHARD_BLOB_BYTES);
+  memcpy(blob_out, &b, sizeof(b));
+  h->replica_open = true;
+  h->replica_connected = world == 1;
+  return MLM_OK;
+}
+
+int mlm_replica_connect(mlm_handle h, const void *blobs) {
+  if (!h || !blobs) return MLM_ERR_INVALID_ARG;
+  if (!h->replica_open) {
+    g_last_error = "mlm_replica_open must come first";
+    return MLM_ERR_INVALID_ARG;
+  }
+  if (h->replica_connected) return MLM_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  ReplicaPeers &X = h->replica_peers;
+  for (int r = 0; r < X.world; r++) {
+    ShardBlob b;
+    memcpy(&b, reinterpret_cast<const unsigned char *>(blobs) + (size_t)r * MLM_SHARD_BLOB_BYTES, sizeof(b));
+    if (b.magic != kReplicaMagic || b.rank != r || b.world != X.world || b.hit_cap != X.src || b.rec_cap != X.cap_blocks) {
+      g_last_error = "replica blob " + std::to_string(r) + " does not describe a rank of this replicated map (same configuration on every rank?)";
+      return MLM_ERR_INVALID_ARG;
+    }
+    if (r == X.rank) continue;
+    // the source stores into every replica; a replica only into the source (its acknowledgements)
+    if (X.rank != X.src && r != X.src) continue;
+    void *base = nullptr;
+    if (b.pid == (int64_t)getpid()) {
+      base = reinterpret_cast<void *>((uintptr_t)b.ptr);
+      if (b.device != h->device) {
+        int can = 0;
+        CUDA_TRY(cudaDeviceCanAccessPeer(&can, h->device, b.device));
+        if (!can) {
+          g_last_error = "no peer access between devices " + std::to_string(h->device) + " and " + std::to_string(b.device);
+          return MLM_ERR_UNSUPPORTED;
+        }
+        cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_TRY(e);
+        cudaGetLastError();
+      }
+    } else {
+      CUDA_TRY(cudaIpcOpenMemHandle(&base, b.ipc, cudaIpcMemLazyEnablePeerAccess));
+      h->replica_mapped[r] = base;
+    }
+    X.a[r] = carve_replica(base, X.half_bytes, nullptr);
+  }
+  h->replica_connected = true;
+  return MLM_OK;
+}
+
+int mlm_replica_publish(mlm_handle h, int32_t *n_blocks_out) {
+  int rc = replica_check(h);
+  if (rc != MLM_OK) return rc;
+  ReplicaPeers &X = h->replica_peers;
+  if (X.rank != X.src) {
+    g_last_error = "only the source rank publishes";
+    return MLM_ERR_INVALID_ARG;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int n = h->h_fc->n_touched_sub;
+  if (n > X.cap_blocks) {
+    g_last_error = "frame touched more subboxes than the replicas' inboxes hold (MLM_REPLICA_MAX_BLOCKS)";
+    return MLM_ERR_CAPACITY;
+  }
+  const uint32_t epoch = ++h->replica_epoch;
+  cudaStream_t s = h->stream;
+  k_replica_push<<<std::max(n, 1), 256, 0, s>>>(X, h->P, h->D, *h->h_fp, n, epoch, h->d_replica_state, h->shard_timeout_ns);
+  h->launches++;
+  int st[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(st, h->d_replica_state, sizeof(st), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  h->replica_last_blocks = n;
+  if (n_blocks_out) *n_blocks_out = n;
+  if (st[1]) {
+    g_last_error = "a replica did not acknowledge an earlier frame in time (MLM_SHARD_TIMEOUT_MS)";
+    return MLM_ERR_CUDA;
+  }
+  return MLM_OK;
+}
+
+int mlm_replica_apply(mlm_handle h, int32_t *n_blocks_out) {
+  int rc = replica_check(h);
+  if (rc != MLM_OK) return rc;
+  ReplicaPeers &X = h->replica_peers;
+  if (X.rank == X.src) {
+    g_last_error = "the source rank has nothing to apply";
+    return MLM_ERR_INVALID_ARG;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  const uint32_t epoch = ++h->replica_epoch;
+  cudaStream_t s = h->stream;
+  CUDA_TRY(cudaMemsetAsync(h->d_replica_state, 0, 4 * sizeof(int), s));
+  k_replica_pull<<<h->sm_count * 2, 256, 0, s>>>(X, h->P, h->D, epoch, h->d_replica_state, h->shard_timeout_ns);
+  h->launches++;
+  int cnt[4] = {0, 0, 0, 0};
+  CUDA_TRY(cudaMemcpyAsync(cnt, h->d_replica_state, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  h->cum_ram_expand += cnt[0];
+  h->n_submaps += cnt[0];
+  h->replica_last_blocks = cnt[3];
+  if (n_blocks_out) *n_blocks_out = cnt[3];
+  if (cnt[1] == kErrPeer) {
+    g_last_error = "the source did not publish the frame in time (MLM_SHARD_TIMEOUT_MS) or reported a failure";
+    return MLM_ERR_CUDA;
+  }
+  return cnt[1] ? map_device_error(cnt[1]) : MLM_OK;
+}
+
+int mlm_replica_close(mlm_handle h) {
+  if (!h) return MLM_ERR_INVALID_ARG;
+  if (!h->replica_open) return MLM_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (int r = 0; r < kMaxWorld; r++)
+    if (h->replica_mapped[r]) {
+      cudaIpcCloseMemHandle(h->replica_mapped[r]);
+      h->replica_mapped[r] = nullptr;
+    }
+  cudaGetLastError();
+  h->replica_connected = false;  // the arena itself is released by mlm_destroy (peers must have closed by then)
+  return MLM_OK;
 }
 
 int mlm_debug_log10f(mlm_handle h, const float *x, size_t n, float *out) {

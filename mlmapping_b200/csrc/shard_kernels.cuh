@@ -438,12 +438,10 @@ __global__ void __launch_bounds__(256) k_shard_ingest(ShardPeers X, MapParams P,
 // by log_odds[cells] f32, occupancy[cells], inflate[cells] (padded to 16 bytes).
 __host__ __device__ inline size_t dirty_record_bytes(int cells) { return (16 + (size_t)cells * 6 + 15) & ~(size_t)15; }
 
-__global__ void __launch_bounds__(256) k_dirty_export(MapParams P, DeviceBuffers D, FrameParams F, int n, unsigned char *out) {
-  const int i = blockIdx.x;
-  if (i >= n) return;
+// record i of the frame's dirty list -> rec
+__device__ __forceinline__ void dirty_pack_record(const MapParams &P, const DeviceBuffers &D, const FrameParams &F, int i, unsigned char *rec) {
   const int ls = D.touched_sub[i];
   const int block = D.lsg_block[ls];
-  unsigned char *rec = out + (size_t)i * dirty_record_bytes(P.cells);
   int *hdr = reinterpret_cast<int *>(rec);
   if (threadIdx.x == 0) {
     int lx = ls % P.lsg_dim_xy, ly = (ls / P.lsg_dim_xy) % P.lsg_dim_xy, lz = ls / (P.lsg_dim_xy * P.lsg_dim_xy);
@@ -464,13 +462,17 @@ __global__ void __launch_bounds__(256) k_dirty_export(MapParams P, DeviceBuffers
   }
 }
 
-__global__ void __launch_bounds__(256) k_dirty_import(MapParams P, DeviceBuffers D, int n, const unsigned char *in, int *counters) {
-  __shared__ int s_block;
+__global__ void __launch_bounds__(256) k_dirty_export(MapParams P, DeviceBuffers D, FrameParams F, int n, unsigned char *out) {
   const int i = blockIdx.x;
   if (i >= n) return;
-  const unsigned char *rec = in + (size_t)i * dirty_record_bytes(P.cells);
+  dirty_pack_record(P, D, F, i, out + (size_t)i * dirty_record_bytes(P.cells));
+}
+
+// rec -> the replica's map: the subbox is found or created (hash insert + free-stack pop by thread 0), then overwritten.
+// Called by a whole CTA; counters[0] += new blocks, counters[1] = error
+__device__ __forceinline__ void dirty_apply_record(const MapParams &P, DeviceBuffers &D, const unsigned char *rec, int *counters, int *s_block) {
   const int *hdr = reinterpret_cast<const int *>(rec);
-  if (hdr[3] == 0) return;
+  if (hdr[3] == 0) return;   // (uniform over the CTA)
   if (threadIdx.x == 0) {
     int g[3] = {hdr[0], hdr[1], hdr[2]};
     uint64_t key;
@@ -504,10 +506,10 @@ __global__ void __launch_bounds__(256) k_dirty_import(MapParams P, DeviceBuffers
         slot = (slot + 1) & P.ht_mask;
       }
     }
-    s_block = block;
+    *s_block = block;
   }
   __syncthreads();
-  const int block = s_block;
+  const int block = *s_block;
   if (block < 0) return;
   const float *lo = reinterpret_cast<const float *>(rec + 16);
   const char *occ = reinterpret_cast<const char *>(rec + 16 + (size_t)P.cells * 4);
@@ -519,6 +521,114 @@ __global__ void __launch_bounds__(256) k_dirty_import(MapParams P, DeviceBuffers
     D.pool_inf[dst + c] = inf[c];
   }
 }
+
+__global__ void __launch_bounds__(256) k_dirty_import(MapParams P, DeviceBuffers D, int n, const unsigned char *in, int *counters) {
+  __shared__ int s_block;
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  dirty_apply_record(P, D, in + (size_t)i * dirty_record_bytes(P.cells), counters, &s_block);
+}
+
+// ---- the same replication with the records stored straight into the replicas' arenas over NVLink peer memory --------
+// Every rank of a replicated map owns one arena of the same layout: inbox[2][cap] (dirty records of a frame, by frame
+// parity), count[2], flags[2] (the frame number whose records sit in that half; written by the source with a system-
+// scope release), ack[world] (in the SOURCE's arena: the last frame each replica has applied, written by the replica).
+// The source may run at most two frames ahead of the slowest replica: before it overwrites a half it waits for the acks
+// of the frame that used it.
+struct ReplicaArena {
+  uint32_t *flags;
+  int *count;
+  uint32_t *ack;
+  unsigned char *inbox;
+};
+struct ReplicaPeers {
+  int rank, world, src, cap_blocks;
+  unsigned long long half_bytes;   // bytes of one inbox half
+  ReplicaArena a[kMaxWorld];
+};
+
+__device__ __forceinline__ bool spin_until(const uint32_t *word, uint32_t target, unsigned long long timeout_ns) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(word) : "memory");
+    if ((int)(v - target) >= 0) return true;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > timeout_ns) return false;
+    __nanosleep(100);
+  }
+}
+
+// source: one CTA per dirty block packs it into every replica's inbox; the last CTA publishes the count and the flag.
+// state[0] = completion ticket, state[1] = error
+__global__ void __launch_bounds__(256) k_replica_push(ReplicaPeers X, MapParams P, DeviceBuffers D, FrameParams F, int n, uint32_t epoch,
+                                                      int *state, unsigned long long timeout_ns) {
+  __shared__ int s_fail, s_last;
+  const int par = (int)(epoch & 1);
+  if (threadIdx.x == 0) s_fail = 0;
+  __syncthreads();
+  if (epoch > 2 && threadIdx.x < X.world && threadIdx.x != X.src)
+    if (!spin_until(X.a[X.src].ack + threadIdx.x, epoch - 2, timeout_ns)) s_fail = 1;
+  __syncthreads();
+  const bool failed = s_fail != 0;
+  if (!failed && (int)blockIdx.x < n) {
+    const size_t off = (size_t)par * X.half_bytes + (size_t)blockIdx.x * dirty_record_bytes(P.cells);
+    for (int r = 0; r < X.world; r++)
+      if (r != X.src) dirty_pack_record(P, D, F, (int)blockIdx.x, X.a[r].inbox + off);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (failed) state[1] = kErrPeer;
+    __threadfence_system();
+    s_last = atomicAdd(&state[0], 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) state[0] = 0;
+  const int d = threadIdx.x;
+  if (d < X.world && d != X.src) {
+    X.a[d].count[par] = __ldcg(&state[1]) ? -1 : n;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(X.a[d].flags + par), "r"(epoch) : "memory");
+  }
+}
+
+// replica: wait for the frame's flag, apply its records, acknowledge.  counters: [0] new blocks, [1] error, [2] ticket, [3] records
+__global__ void __launch_bounds__(256) k_replica_pull(ReplicaPeers X, MapParams P, DeviceBuffers D, uint32_t epoch, int *counters,
+                                                      unsigned long long timeout_ns) {
+  __shared__ int s_n, s_last, s_block;
+  const int par = (int)(epoch & 1);
+  const ReplicaArena &A = X.a[X.rank];
+  if (threadIdx.x == 0) {
+    int n = -1;
+    if (spin_until(A.flags + par, epoch, timeout_ns)) n = __ldcg(A.count + par);
+    if (n < 0 || n > X.cap_blocks) {
+      counters[1] = kErrPeer;
+      n = 0;
+    }
+    s_n = n;
+  }
+  __syncthreads();
+  const int n = s_n;
+  const unsigned char *in = A.inbox + (size_t)par * X.half_bytes;
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    dirty_apply_record(P, D, in + (size_t)i * dirty_record_bytes(P.cells), counters, &s_block);
+    __syncthreads();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&counters[2], 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  counters[2] = 0;
+  counters[3] = n;
+  // the half may be overwritten once every CTA has read it: tell the source
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(X.a[X.src].ack + X.rank), "r"(epoch) : "memory");
+}
+
 
 // ---- checkpoint / restore of the submap pool (the reference has no persistence) -------------------
 // One fixed-size record per subbox: 32-byte header {g[3], flags, element 0 of a collapsed subbox} followed by

@@ -108,19 +108,69 @@ def sharded_group_in_process(cfg: MlmConfig, world: int, devices=None):
 
 class ReplicatedMLMap:
     """One map updated on `src` rank and replicated on the others for split query streams: after each
-    frame the dirty subbox blocks (those the frame touched) are broadcast and applied on the replicas."""
+    frame the dirty subbox blocks (those the frame touched) reach the replicas.
 
-    def __init__(self, cfg: MlmConfig, rank: int = 0, world: int = 1, src: int = 0, device: int | None = None):
+    transport "p2p" (default): the library's kernels store the records straight into the replicas' inboxes over NVLink
+    peer memory (mlm_replica_*); this class only carries the setup blobs once.  transport "nccl": the caller-side
+    broadcast of mlm_dirty_export / mlm_dirty_import buffers (kept as the baseline and for devices without peer access)."""
+
+    def __init__(self, cfg: MlmConfig, rank: int = 0, world: int = 1, src: int = 0, device: int | None = None,
+                 transport: str = "p2p", connect: bool = True):
         import torch
 
         self.torch = torch
         self.rank, self.world, self.src = rank, world, src
+        self.transport = transport
         self.map = MLMap(cfg, device=rank if device is None else device)
         self.dev = torch.device("cuda", rank if device is None else device)
         self.last = {}
+        self.blob = b""
+        if transport == "p2p":
+            blob = (C.c_ubyte * SHARD_BLOB_BYTES)()
+            self.map._check(self.map._lib.mlm_replica_open(self.map._h, rank, world, src, blob))
+            self.blob = bytes(blob)
+            if connect and world > 1:
+                self.connect(self._all_gather_blobs())
+
+    def _all_gather_blobs(self):
+        import torch
+        import torch.distributed as dist
+        dev = self.dev if dist.get_backend() == "nccl" else torch.device("cpu")
+        mine = torch.frombuffer(bytearray(self.blob), dtype=torch.uint8).to(dev)
+        allb = torch.empty(self.world * SHARD_BLOB_BYTES, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allb, mine)
+        return bytes(allb.cpu().numpy().tobytes())
+
+    def connect(self, blobs: bytes):
+        assert len(blobs) == self.world * SHARD_BLOB_BYTES
+        buf = (C.c_ubyte * len(blobs)).from_buffer_copy(blobs)
+        self.map._check(self.map._lib.mlm_replica_connect(self.map._h, buf))
 
     def integrate_depth(self, img, T_wb):
         """call on every rank; only `src` needs the real image"""
+        if self.transport != "p2p":
+            return self._integrate_depth_nccl(img, T_wb)
+        m, lib = self.map, self.map._lib
+        st = None
+        n = C.c_int32(0)
+        if self.rank == self.src:
+            st = m.integrate_depth(img, T_wb)
+            if self.world > 1:
+                m._check(lib.mlm_replica_publish(m._h, C.byref(n)))
+            else:
+                n.value = 0
+        else:
+            m._check(lib.mlm_replica_apply(m._h, C.byref(n)))
+        self.last = {"dirty_blocks": n.value, "broadcast_bytes": n.value * ((16 + 6 * m.cells + 15) & ~15)}
+        return st
+
+    def close(self):
+        if self.map._h is not None and self.map._h.value:
+            if self.transport == "p2p":
+                self.map._lib.mlm_replica_close(self.map._h)
+        self.map.close()
+
+    def _integrate_depth_nccl(self, img, T_wb):
         torch, m, lib = self.torch, self.map, self.map._lib
         st = None
         n, rb = C.c_int32(0), C.c_size_t(0)
@@ -148,3 +198,15 @@ class ReplicatedMLMap:
 
     def import_from(self, buf_ptr: int, nb: int):
         self.map._check(self.map._lib.mlm_dirty_import(self.map._h, buf_ptr, nb))
+
+
+def replicated_group_in_process(cfg: MlmConfig, world: int, src: int = 0, devices=None):
+    """`world` ranks of a replicated map driven by ONE process (several GPUs, or several handles on one GPU as the
+    single-GPU tests do).  Per frame: integrate_depth on the source first, then on every replica."""
+    devices = devices or [0] * world
+    ranks = [ReplicatedMLMap(cfg, rank=r, world=world, src=src, device=devices[r], connect=False) for r in range(world)]
+    blobs = b"".join(r.blob for r in ranks)
+    if world > 1:
+        for r in ranks:
+            r.connect(blobs)
+    return ranks

@@ -1,5 +1,5 @@
 """Run under torchrun on N GPUs: rank 0 integrates the CFG-A trajectory; after every frame the dirty subbox blocks
-are broadcast (NCCL) and applied on the replicas; the query stream is split evenly over the ranks and the
+reach the replicas (stored into their inboxes over NVLink peer memory by the library; `--nccl`: broadcast by the caller); the query stream is split evenly over the ranks and the
 concatenated answers must equal the CPU oracle's."""
 import json
 import os
@@ -25,7 +25,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg = config_cfg_a()
-    rm = ReplicatedMLMap(cfg, rank=rank, world=world, src=0, device=local)
+    rm = ReplicatedMLMap(cfg, rank=rank, world=world, src=0, device=local, transport="nccl" if "--nccl" in sys.argv else "p2p")
     orc = None
     if rank == 0:
         from oracle_binding import Oracle
@@ -58,6 +58,8 @@ def main():
         print(json.dumps({"replicated_check": "ok", "world": world, "queries": 2 * nq,
                           "host_path_queries_per_s": 2 * nq / max(p[2] for p in parts),
                           "broadcast_bytes_per_frame": shipped}))
+    dist.barrier()
+    rm.close()
     dist.barrier()
     dist.destroy_process_group()
 

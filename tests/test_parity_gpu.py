@@ -459,6 +459,44 @@ def test_replicated_map_dirty_block_shipping_single_gpu():
     assert np.array_equal(replica.getOddGrad(pos[:20000]), owner.getOddGrad(pos[:20000]))
 
 
+@pytest.mark.gpu
+def test_replicated_map_over_peer_memory_in_process():
+    """mlm_replica_*: the source's kernel stores each frame's dirty blocks into the replicas' inboxes and raises the
+    frame's flag, the replicas' kernels wait on the device, apply and acknowledge (three handles on one GPU stand in
+    for three ranks; tests/multi_gpu/replicated_check.py runs the same over CUDA IPC between processes)"""
+    from mlmapping_b200.sharded import replicated_group_in_process
+    cfg = config_cfg_a()
+    ranks = replicated_group_in_process(cfg, 3, src=1)
+    orc = Oracle(cfg)
+    for k in range(9):   # more frames than inbox halves: the acknowledgements are exercised
+        pose = scenes.corridor_trajectory_pose(k * 12)
+        img = scenes.corridor_depth_frame(cfg, pose, frame_idx=k)
+        orc.integrate_depth(img, pose)
+        ranks[1].integrate_depth(img, pose)
+        assert ranks[1].last["dirty_blocks"] > 0
+        for r in (0, 2):
+            ranks[r].integrate_depth(None, pose)
+            assert ranks[r].last["dirty_blocks"] == ranks[1].last["dirty_blocks"]
+    for r in (0, 2):
+        assert_map_parity(ranks[r].map, orc, LO_TOL, tag=f"replica{r}")
+    m = orc.export_map()
+    pos = scenes.query_positions(100000, m["glb"].min(0) * 1.0, (m["glb"].max(0) + 1) * 1.0, seed=3, inflate=2.0)
+    assert np.array_equal(ranks[2].map.getOccupancy(pos), orc.getOccupancy(pos))
+    # out of lock step: a replica that applies without a published frame times out on the device and reports it
+    import os
+    os.environ["MLM_SHARD_TIMEOUT_MS"] = "50"
+    try:
+        lone = replicated_group_in_process(cfg, 2, src=0)
+        with pytest.raises(MlmError):
+            lone[1].integrate_depth(None, pose)
+        for r in lone:
+            r.close()
+    finally:
+        del os.environ["MLM_SHARD_TIMEOUT_MS"]
+    for r in ranks:
+        r.close()
+
+
 def test_replicated_map_two_gpus_matches_oracle():
     """dirty-block broadcast over NCCL + split query stream on 2 ranks.  Skipped on a single-GPU box."""
     import subprocess
