@@ -468,9 +468,10 @@ def run_agents(rank, world, local_rank, barrier, steps, warm, n_queries, n_agent
         (q_max, t_rep_max), _ = reduce_timing([t, 1e3 * t_rep / nrep], [0.0], device="cuda" if world > 1 else None)
         out["queries_replicated_map"] = {"n_queries": n_queries, "ms_per_step": q_max, "queries_per_s": n_queries / (q_max * 1e-3),
                                          "replication_ms_per_frame": t_rep_max, "broadcast_bytes_per_frame": nb / nrep,
-                                         "note": "rank 0 integrates, the frame's dirty subbox blocks are broadcast (NCCL) and "
-                                                 "applied on every replica; wall clock incl. the update on rank 0"}
-        m.close()
+                                         "note": "rank 0 integrates, then its kernel stores the frame's dirty subbox blocks into every replica's "
+                                                 "inbox over NVLink peer memory (mlm_replica_publish / apply); wall clock incl. the "
+                                                 "update on rank 0"}
+        rep.close()
     return out
 
 
