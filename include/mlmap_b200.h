@@ -318,6 +318,11 @@ int mlm_shard_open(mlm_handle h, int rank, int world, void *blob_out /* MLM_SHAR
 int mlm_shard_connect(mlm_handle h, const void *blobs /* world * MLM_SHARD_BLOB_BYTES, rank order */);
 int mlm_shard_submit_points_f64(mlm_handle h, const double *xyz, int n, const double T_wb[7]);
 int mlm_shard_submit_points_f64_device(mlm_handle h, const double *d_xyz, int n, const double T_wb[7]);
+/* the same scan handed over in slices: rank r passes points [first, first + n_slice) of the n_total points (the ranks'
+ * slices partition the scan; xyz_slice is host memory, page-locked for a direct copy).  Every rank copies only its
+ * slice from the host; the slices reach the other ranks' arenas over NVLink peer memory and every rank waits on the
+ * device until the scan is complete. */
+int mlm_shard_submit_points_slice_f64(mlm_handle h, const double *xyz_slice, int first, int n_slice, int n_total, const double T_wb[7]);
 int mlm_shard_finish(mlm_handle h, mlm_frame_stats *stats /* may be NULL */);
 int mlm_shard_integrate_points_f64(mlm_handle h, const double *xyz, int n, const double T_wb[7], mlm_frame_stats *stats);
 int mlm_shard_last_exchange(mlm_handle h, mlm_shard_exchange *out);

@@ -123,7 +123,7 @@ ABI_SYMBOLS = [
     "mlm_sizeof_frame_stats", "mlm_debug_phase_cycles", "mlm_host_alloc", "mlm_host_free", "mlm_srand", "mlm_debug_rand", "mlm_export_frontier", 
     "mlm_awareness_input_pc_pose_f64", "mlm_awareness_input_depth_u16", "mlm_local_input_pc_pose_direct", "mlm_set_sm_budget",
     "mlm_frame_submit_depth_u16_device", "mlm_frame_submit_points_f64_device", "mlm_frame_finish", "mlm_get_odd_at", "mlm_get_odd_at_device",
-    "mlm_shard_open", "mlm_shard_connect", "mlm_shard_submit_points_f64", "mlm_shard_submit_points_f64_device", "mlm_shard_finish",
+    "mlm_shard_open", "mlm_shard_connect", "mlm_shard_submit_points_f64", "mlm_shard_submit_points_f64_device", "mlm_shard_submit_points_slice_f64", "mlm_shard_finish",
     "mlm_shard_integrate_points_f64", "mlm_shard_last_exchange", "mlm_shard_last_kernel_ms", "mlm_shard_close", "mlm_dirty_count", "mlm_dirty_export", "mlm_dirty_import",
     "mlm_replica_open", "mlm_replica_connect", "mlm_replica_publish", "mlm_replica_apply", "mlm_replica_close",
     "mlm_export_cloud", "mlm_export_cloud_device", "mlm_export_odds_slice",
@@ -219,6 +219,7 @@ def load_library() -> C.CDLL:
         "mlm_shard_connect": ([vp, vp], C.c_int),
         "mlm_shard_submit_points_f64": ([vp, vp, C.c_int, dp], C.c_int),
         "mlm_shard_submit_points_f64_device": ([vp, vp, C.c_int, dp], C.c_int),
+        "mlm_shard_submit_points_slice_f64": ([vp, vp, C.c_int, C.c_int, C.c_int, dp], C.c_int),
         "mlm_shard_finish": ([vp, C.POINTER(FrameStats)], C.c_int),
         "mlm_shard_integrate_points_f64": ([vp, vp, C.c_int, dp, C.POINTER(FrameStats)], C.c_int),
         "mlm_shard_last_exchange": ([vp, C.POINTER(ShardExchange)], C.c_int),

@@ -2387,6 +2387,7 @@ struct ShardBlob {  // what a rank publishes so that its peers can map its excha
   uint32_t magic;
   int32_t rank, world, device;
   int32_t hit_cap, rec_cap;
+  int32_t max_points, reserved;
   int64_t pid;
   uint64_t ptr;  // arena address in the exporting process (used directly by handles of the same process)
   cudaIpcMemHandle_t ipc;
@@ -2396,7 +2397,7 @@ constexpr uint32_t kShardMagic = 0x4d4c5342u;  // "MLSB"
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 // carve the arena of one rank: flags | mailboxes | cursors | gathered keys | gathered stamps | inboxes
-ShardArena carve_arena(void *base, int world, int hit_cap, int rec_cap, size_t *total) {
+ShardArena carve_arena(void *base, int world, int hit_cap, int rec_cap, int max_points, size_t *total) {
   unsigned char *p = reinterpret_cast<unsigned char *>(base);
   size_t off = 0;
   ShardArena a;
@@ -2412,6 +2413,10 @@ ShardArena carve_arena(void *base, int world, int hit_cap, int rec_cap, size_t *
   off = align256(off + (size_t)2 * world * hit_cap * sizeof(uint32_t));
   a.inbox = reinterpret_cast<ShardRecord *>(p + off);
   off = align256(off + (size_t)2 * rec_cap * sizeof(ShardRecord));
+  a.pflags = reinterpret_cast<uint32_t *>(p + off);
+  off = align256(off + kMaxWorld * sizeof(uint32_t));
+  a.points = reinterpret_cast<double *>(p + off);
+  off = align256(off + (size_t)2 * 3 * max_points * sizeof(double));
   if (total) *total = off;
   return a;
 }
@@ -2589,7 +2594,7 @@ int mlm_shard_open(mlm_handle h, int rank, int world, void *blob_out) {
   if (const char *e = getenv("MLM_SHARD_REC_CAP")) rc_ll = std::max(1ll, atoll(e));
   const int rec_cap = (int)std::min<long long>(rc_ll, (1ll << 30));
   size_t bytes = 0;
-  carve_arena(nullptr, world, hit_cap, rec_cap, &bytes);
+  carve_arena(nullptr, world, hit_cap, rec_cap, P.max_points, &bytes);
   CUDA_TRY(cudaMalloc(&h->shard_arena, bytes));
   h->allocs.push_back(h->shard_arena);
   h->shard_arena_bytes = bytes;
@@ -2602,8 +2607,11 @@ int mlm_shard_open(mlm_handle h, int rank, int world, void *blob_out) {
     const size_t cells = (size_t)P.nZ * P.nPhi * P.nRho;
     CUDA_TRY(cudaMalloc((void **)&h->d_key_stamp, cells * sizeof(uint32_t)));
     h->allocs.push_back(h->d_key_stamp);
-    CUDA_TRY(cudaMalloc((void **)&h->d_shard_cursor, (kMaxWorld + 4) * sizeof(int)));
+    // [0, kMaxWorld) push cursors, [kMaxWorld] skip flag, [+1] push ticket (k_shard_begin rearms those), [+2, +3] the
+    // rank's own entry counts, [+4] ticket of the point scatter (rearmed by its last CTA)
+    CUDA_TRY(cudaMalloc((void **)&h->d_shard_cursor, (kMaxWorld + 8) * sizeof(int)));
     h->allocs.push_back(h->d_shard_cursor);
+    CUDA_TRY(cudaMemset(h->d_shard_cursor, 0, (kMaxWorld + 8) * sizeof(int)));
     CUDA_TRY(cudaMalloc((void **)&h->d_shard_state, sizeof(ShardState)));
     h->allocs.push_back(h->d_shard_state);
     CUDA_TRY(cudaMemset(h->d_shard_state, 0, sizeof(ShardState)));
@@ -2622,7 +2630,9 @@ int mlm_shard_open(mlm_handle h, int rank, int world, void *blob_out) {
   h->shard_peers.world = world;
   h->shard_peers.hit_cap = hit_cap;
   h->shard_peers.rec_cap = rec_cap;
-  h->shard_peers.a[rank] = carve_arena(h->shard_arena, world, hit_cap, rec_cap, nullptr);
+  h->shard_peers.a[rank] = carve_arena(h->shard_arena, world, hit_cap, rec_cap, P.max_points, nullptr);
+  h->shard_peers.max_points = P.max_points;
+  CUDA_TRY(cudaMemset(h->shard_peers.a[rank].pflags, 0, kMaxWorld * sizeof(uint32_t)));
   h->shard_rank = rank;
   h->shard_world = world;
   h->shard_epoch = 0;
@@ -2634,6 +2644,7 @@ int mlm_shard_open(mlm_handle h, int rank, int world, void *blob_out) {
   b.device = h->device;
   b.hit_cap = hit_cap;
   b.rec_cap = rec_cap;
+  b.max_points = P.max_points;
   b.pid = (int64_t)getpid();
   b.ptr = (uint64_t)(uintptr_t)h->shard_arena;
   if (world > 1) CUDA_TRY(cudaIpcGetMemHandle(&b.ipc, h->shard_arena));
@@ -2654,7 +2665,8 @@ int mlm_shard_connect(mlm_handle h, const void *blobs) {
   for (int r = 0; r < X.world; r++) {
     ShardBlob b;
     memcpy(&b, reinterpret_cast<const unsigned char *>(blobs) + (size_t)r * MLM_SHARD_BLOB_BYTES, sizeof(b));
-    if (b.magic != kShardMagic || b.rank != r || b.world != X.world || b.hit_cap != X.hit_cap || b.rec_cap != X.rec_cap) {
+    if (b.magic != kShardMagic || b.rank != r || b.world != X.world || b.hit_cap != X.hit_cap || b.rec_cap != X.rec_cap ||
+        b.max_points != X.max_points) {
       g_last_error = "shard blob " + std::to_string(r) + " does not describe a rank of this sharded map (same configuration on every rank?)";
       return MLM_ERR_INVALID_ARG;
     }
@@ -2679,7 +2691,7 @@ int mlm_shard_connect(mlm_handle h, const void *blobs) {
       CUDA_TRY(cudaIpcOpenMemHandle(&base, b.ipc, cudaIpcMemLazyEnablePeerAccess));
       h->shard_mapped[r] = base;
     }
-    X.a[r] = carve_arena(base, X.world, X.hit_cap, X.rec_cap, nullptr);
+    X.a[r] = carve_arena(base, X.world, X.hit_cap, X.rec_cap, X.max_points, nullptr);
   }
   h->shard_connected = true;
   return MLM_OK;
@@ -2738,6 +2750,45 @@ int mlm_shard_submit_points_f64(mlm_handle h, const double *xyz, int n, const do
     }
   }
   return shard_enqueue(h, reinterpret_cast<const double *>(h->d_input), n, T_wb, src);
+}
+
+// every rank passes ITS slice [first, first + n_slice) of the same scan of n_total points (the slices partition the
+// scan): 1/world of the H2D traffic per rank, the slices reach the other ranks over NVLink peer memory
+int mlm_shard_submit_points_slice_f64(mlm_handle h, const double *xyz_slice, int first, int n_slice, int n_total, const double T_wb[7]) {
+  int rc = shard_check(h, true);
+  if (rc != MLM_OK) return rc;
+  if ((!xyz_slice && n_slice > 0) || !T_wb || first < 0 || n_slice < 0 || n_total < 0 || (long long)first + n_slice > n_total) return MLM_ERR_INVALID_ARG;
+  if (n_total > h->P.max_points) return MLM_ERR_CAPACITY;
+  if (h->shard_pending) {
+    g_last_error = "mlm_shard_finish of the previous scan is missing";
+    return MLM_ERR_INVALID_ARG;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const ShardPeers &X = h->shard_peers;
+  const uint32_t epoch = h->shard_epoch + 1;   // shard_enqueue advances it
+  const int par = (int)(epoch & 1);
+  double *mine = X.a[X.rank].points + (size_t)par * 3 * X.max_points;
+  if (n_slice > 0) {
+    const void *src = xyz_slice;
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, xyz_slice) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!pinned) {
+      rc = ensure_input(h, (size_t)n_slice * 24, (size_t)h->P.max_points * 24);   // (allocates the pinned staging buffer too)
+      if (rc != MLM_OK) return rc;
+      memcpy(h->h_stage, xyz_slice, (size_t)n_slice * 24);
+      src = h->h_stage;
+    }
+    CUDA_TRY(cudaMemcpyAsync(mine + 3 * (size_t)first, src, (size_t)n_slice * 24, cudaMemcpyHostToDevice, s));
+  }
+  if (X.world > 1) {
+    const int g = std::max(1, std::min(h->sm_count * 2, (int)((3ll * n_slice + 255) / 256)));
+    k_shard_scatter_points<<<g, 256, 0, s>>>(X, par, first, n_slice, epoch, h->d_shard_cursor + kMaxWorld + 4);
+    k_shard_wait_points<<<1, 32, 0, s>>>(X, epoch, h->shard_timeout_ns, h->D.fc[h->frame_idx & 1]);
+    h->launches += 2;
+  }
+  return shard_enqueue(h, mine, n_total, T_wb);
 }
 
 int mlm_shard_finish(mlm_handle h, mlm_frame_stats *stats) {

@@ -33,11 +33,14 @@ struct ShardArena {
   uint32_t *gather_stamp; // [2][world][hit_cap] ... and their first-insert stamps
   int *cursor;            // [2] by parity: records reserved in the inbox so far (sources reserve with a remote atomicAdd)
   ShardRecord *inbox;     // [2][rec_cap] by parity: update records for voxels this rank owns, all sources interleaved
+  uint32_t *pflags;       // [kMaxWorld] epoch of the last scan whose point slice the source has delivered here
+  double *points;         // [2][3 * max_points] by parity: the scan, assembled from the ranks' slices (submit_points_slice)
 };
 struct ShardPeers {
   ShardArena a[kMaxWorld];
   int rank, world;
   int hit_cap, rec_cap;
+  int max_points;
 };
 // what the wait kernel found (device copy read by the owner-side kernels, pinned host copy read by the caller)
 struct ShardState {
@@ -251,6 +254,52 @@ __global__ void __launch_bounds__(kPushThreads) k_shard_push(ShardPeers X, MapPa
     X.a[d].mbox[par * kMaxWorld + X.rank] = make_int2(failed ? -1 : n_hit, failed ? -1 : 0);
     // (the release orders this thread's stores above and, through the tickets behind the CTAs' fences, everyone else's)
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(X.a[d].flags + X.rank), "r"(epoch) : "memory");
+  }
+}
+
+// ---- the scan itself: every rank copies 1/world of it from the host, the slices travel over NVLink ------------------
+// (a scan of 262 k points is 6.3 MB: copied whole by every rank it costs 125-210 us of PCIe time per scan and rank)
+// source: own slice [first, first + n) of points[par] (already in this rank's arena) -> the same place in every peer's
+// arena with 16-byte stores; the last CTA raises this rank's point flag everywhere.  state[0] = ticket
+__global__ void __launch_bounds__(256) k_shard_scatter_points(ShardPeers X, int par, int first, int n, uint32_t epoch, int *state) {
+  __shared__ int s_last;
+  const size_t base = (size_t)par * 3 * X.max_points;
+  // 3 doubles per point: the slice is a run of 8-byte words [3 * first, 3 * (first + n))
+  const double *src = X.a[X.rank].points + base + 3 * (size_t)first;
+  const size_t words = 3 * (size_t)n;
+  for (int r = 0; r < X.world; r++) {
+    if (r == X.rank) continue;
+    double *dst = X.a[r].points + base + 3 * (size_t)first;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = atomicAdd(&state[0], 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) state[0] = 0;
+  if (threadIdx.x < X.world)
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(X.a[threadIdx.x].pflags + X.rank), "r"(epoch) : "memory");
+}
+// every rank: all slices of the scan have arrived (bounded spin; *err = kErrPeer otherwise, which fails the scan)
+__global__ void k_shard_wait_points(ShardPeers X, uint32_t epoch, unsigned long long timeout_ns, FrameCounters *fc) {
+  if ((int)threadIdx.x >= X.world) return;
+  const uint32_t *flag = X.a[X.rank].pflags + threadIdx.x;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if ((int)(v - epoch) >= 0) return;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > timeout_ns) {
+      fc->error = kErrPeer;
+      return;
+    }
+    __nanosleep(100);
   }
 }
 

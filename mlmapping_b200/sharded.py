@@ -57,6 +57,14 @@ class ShardedMLMap:
         m._check(m._lib.mlm_shard_submit_points_f64(m._h, pts.ctypes.data, pts.shape[0], _pose7(T_wb)))
         self._keep = pts
 
+    def submit_slice(self, xyz_slice: np.ndarray, first: int, n_total: int, T_wb):
+        """this rank's slice [first, first + len(xyz_slice)) of a scan of n_total points (the ranks' slices partition it):
+        1/world of the host-to-device traffic per rank, the rest travels over NVLink inside the library"""
+        pts = np.ascontiguousarray(np.asarray(xyz_slice, dtype=np.float64).reshape(-1, 3))
+        m = self.map
+        m._check(m._lib.mlm_shard_submit_points_slice_f64(m._h, pts.ctypes.data, first, pts.shape[0], n_total, _pose7(T_wb)))
+        self._keep = pts
+
     def submit_device(self, d_xyz: int, n: int, T_wb):
         m = self.map
         m._check(m._lib.mlm_shard_submit_points_f64_device(m._h, d_xyz, n, _pose7(T_wb)))

@@ -43,7 +43,12 @@ def main():
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        st = sh.integrate_points(pts, pose)
+        if "--slices" in sys.argv:   # every rank copies only its part of the scan from the host
+            lo, hi = (rank * pts.shape[0]) // world, ((rank + 1) * pts.shape[0]) // world
+            sh.submit_slice(pts[lo:hi], lo, pts.shape[0], pose)
+            st = sh.finish()
+        else:
+            st = sh.integrate_points(pts, pose)
         times.append(time.perf_counter() - t0)
         if orc is not None:
             st_o = orc.integrate_points(pts, pose)
