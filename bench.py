@@ -199,6 +199,7 @@ def run_lidar(rank, world, local_rank, barrier, scans=12, warm=4):
     oracle (union of the ranks' subboxes == the oracle map, bit for bit)."""
     import torch
     from mlmapping_b200 import MLMap, config_cfg_c, scenes
+    from mlmapping_b200.sharding import split_range
     from mlmapping_b200.sharded import ShardedMLMap
     cfg = config_cfg_c()
     data = []
