@@ -88,3 +88,36 @@ def test_rand_stream_is_glibc_rand(lib):
     libc.srand(1)
     ref = np.array([libc.rand() for _ in range(out.size)], dtype=np.int32)
     assert np.array_equal(out, ref)
+
+
+def test_multi_gpu_and_layer_entry_points_reject_bad_arguments_without_a_device(lib):
+    """the sharded-map, replicated-map, two-call, asynchronous-frame and index-query entry points validate their handle
+    and arguments before they touch a device (MLM_ERR_INVALID_ARG = 1)"""
+    blob = (C.c_ubyte * capi.SHARD_BLOB_BYTES)()
+    pose = (C.c_double * 7)(0, 0, 0, 1, 0, 0, 0)
+    n32 = C.c_int32()
+    assert lib.mlm_shard_open(None, 0, 1, blob) == 1
+    assert lib.mlm_shard_connect(None, blob) == 1
+    assert lib.mlm_shard_submit_points_f64(None, None, 0, pose) == 1
+    assert lib.mlm_shard_submit_points_f64_device(None, None, 0, pose) == 1
+    assert lib.mlm_shard_submit_points_slice_f64(None, None, 0, 0, 0, pose) == 1
+    assert lib.mlm_shard_finish(None, None) == 1
+    assert lib.mlm_shard_integrate_points_f64(None, None, 0, pose, None) == 1
+    assert lib.mlm_shard_last_exchange(None, None) == 1
+    assert lib.mlm_shard_last_kernel_ms(None, None) == 1
+    assert lib.mlm_shard_close(None) == 1
+    assert lib.mlm_replica_open(None, 0, 1, 0, blob) == 1
+    assert lib.mlm_replica_connect(None, blob) == 1
+    assert lib.mlm_replica_publish(None, C.byref(n32)) == 1
+    assert lib.mlm_replica_apply(None, C.byref(n32)) == 1
+    assert lib.mlm_replica_close(None) == 1
+    assert lib.mlm_dirty_count(None, None, None) == 1
+    assert lib.mlm_awareness_input_pc_pose_f64(None, None, 0, pose, None) == 1
+    assert lib.mlm_awareness_input_depth_u16(None, None, 0, 0, 0, pose, None) == 1
+    assert lib.mlm_local_input_pc_pose_direct(None, None) == 1
+    assert lib.mlm_set_sm_budget(None, 4) == 1
+    assert lib.mlm_frame_submit_depth_u16_device(None, None, 0, 0, pose) == 1
+    assert lib.mlm_frame_submit_points_f64_device(None, None, 0, pose) == 1
+    assert lib.mlm_frame_finish(None, None) == 1
+    assert lib.mlm_get_odd_at(None, None, None, 1, None) == 1
+    assert lib.mlm_get_odd_at_device(None, None, None, 1, None) == 1
