@@ -15,6 +15,7 @@ import ctypes as C
 import numpy as np
 
 from .capi import SHARD_BLOB_BYTES, FrameStats, MLMap, MlmConfig, ShardExchange, _pose7
+from .sharding import all_gather_blobs
 
 
 class ShardedMLMap:
@@ -32,11 +33,8 @@ class ShardedMLMap:
     def _all_gather_blobs(self):
         import torch
         import torch.distributed as dist
-        dev = torch.device("cuda", self.map.device) if dist.get_backend() == "nccl" else torch.device("cpu")
-        mine = torch.frombuffer(bytearray(self.blob), dtype=torch.uint8).to(dev)
-        allb = torch.empty(self.world * SHARD_BLOB_BYTES, dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(allb, mine)
-        return bytes(allb.cpu().numpy().tobytes())
+        dev = torch.device("cuda", self.map.device) if dist.get_backend() == "nccl" else None
+        return all_gather_blobs(self.blob, self.world, dev)
 
     def connect(self, blobs: bytes):
         """blobs: the `world` setup blobs in rank order"""
@@ -141,13 +139,8 @@ class ReplicatedMLMap:
                 self.connect(self._all_gather_blobs())
 
     def _all_gather_blobs(self):
-        import torch
         import torch.distributed as dist
-        dev = self.dev if dist.get_backend() == "nccl" else torch.device("cpu")
-        mine = torch.frombuffer(bytearray(self.blob), dtype=torch.uint8).to(dev)
-        allb = torch.empty(self.world * SHARD_BLOB_BYTES, dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(allb, mine)
-        return bytes(allb.cpu().numpy().tobytes())
+        return all_gather_blobs(self.blob, self.world, self.dev if dist.get_backend() == "nccl" else None)
 
     def connect(self, blobs: bytes):
         assert len(blobs) == self.world * SHARD_BLOB_BYTES

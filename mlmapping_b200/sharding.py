@@ -29,3 +29,20 @@ def reduce_timing(times_ms: list[float], counts: list[float], device=None):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(c, op=dist.ReduceOp.SUM)
     return t.tolist(), c.tolist()
+
+
+def all_gather_blobs(blob: bytes, world: int, device=None) -> bytes:
+    """the ranks' fixed-size setup blobs (mlm_shard_open / mlm_replica_open) concatenated in rank order: the one
+    collective a sharded or replicated map needs, once, at setup.  `device`: where the backend wants its tensors
+    (a CUDA device for nccl, None / cpu for gloo)"""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return bytes(blob)
+    mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
+    if device is not None:
+        mine = mine.to(device)
+    allb = torch.empty(world * len(blob), dtype=torch.uint8, device=mine.device)
+    dist.all_gather_into_tensor(allb, mine)
+    return bytes(allb.cpu().numpy().tobytes())
