@@ -3021,6 +3021,10 @@ int mlm_replica_publish(mlm_handle h, int32_t *n_blocks_out) {
     g_last_error = "only the source rank publishes";
     return MLM_ERR_INVALID_ARG;
   }
+  if (h->frame_pending || h->staged) {
+    g_last_error = "the frame whose blocks are to be published is not complete (mlm_frame_finish / mlm_local_input_pc_pose_direct first)";
+    return MLM_ERR_INVALID_ARG;
+  }
   CUDA_TRY(cudaSetDevice(h->device));
   const int n = h->h_fc->n_touched_sub;
   if (n > X.cap_blocks) {
